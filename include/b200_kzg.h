@@ -1,0 +1,110 @@
+/*
+ * b200_kzg.h -- C ABI of libb200kzg.so, the B200 (sm_100a) backend for the rust-kzg hot path.
+ *
+ * Every entry point replaces (or extends) one interface of the reference, cited as file:line under
+ * grandinetech/rust-kzg @ 62f9fd85.  Plain pointers and sizes only; host pointers unless a name says _device.
+ * All field/curve data uses blst's memory layouts (kzg/src/eth/c_bindings.rs:427-474): little-endian u64 limbs,
+ * Montgomery form.  There is NO CPU fallback: every compute entry point needs a CUDA device and fails loudly
+ * (error code / C_KZG_ERROR) when none is usable.
+ */
+#ifndef B200_KZG_H
+#define B200_KZG_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_API __attribute__((visibility("default")))
+
+/* ---- blst data layouts (kzg/src/eth/c_bindings.rs:427-474) -------------------------------------------------- */
+typedef struct { uint64_t l[4]; } blst_fr;          /* Montgomery, R = 2^256 */
+typedef struct { uint64_t l[6]; } blst_fp;          /* Montgomery, R = 2^384 */
+typedef struct { blst_fp x, y, z; } blst_p1;        /* Jacobian; infinity <=> z == 0 */
+typedef struct { blst_fp x, y; } blst_p1_affine;    /* infinity <=> all zero */
+typedef struct { blst_fp fp[2]; } blst_fp2;
+typedef struct { blst_fp2 x, y, z; } blst_p2;
+
+/* ============================================================================================================== */
+/* B1 -- GPU MSM plug-in FFI.  Same names, argument order and meaning as the sppark shim the blst backend binds   */
+/* under --features sppark:  blst-sppark/cuda/pippenger.cu:23-38  <->  blst-sppark/src/lib.rs:8-62.               */
+/* ============================================================================================================== */
+
+/* sppark's RustError, returned BY VALUE; code == 0 is success; message is strdup'd and owned by the caller
+ * (arkworks3-sppark-wlc/sppark/util/rusterror.h:15-27). */
+typedef struct { int code; char *message; } RustError;
+
+/* blst-sppark/cuda/pippenger.cu:23-26.  Uploads the bases and builds the device-resident fixed-base table
+ * (rows 2^(c*j) * P_i).  Returns an opaque handle, NULL on failure.  Thread-safe; the handle may be shared
+ * between threads (kzg/src/msm/sppark.rs:24-44 declares it Send + Sync). */
+B200_API void *prepare_msm(const blst_p1_affine points[], size_t npoints);
+
+/* blst-sppark/cuda/pippenger.cu:28-31.  out = sum scalars[i] * points[i], i < npoints <= prepared npoints.
+ * scalars are Montgomery-form blst_fr (the reference passes mont = true). */
+B200_API RustError mult_pippenger_prepared(void *msm, blst_p1 *out, size_t npoints, const blst_fr scalars[]);
+
+/* blst-sppark/cuda/pippenger.cu:33-38.  Variable-base MSM; bases travel with the call. */
+B200_API RustError mult_pippenger(blst_p1 *out, const blst_p1_affine points[], size_t npoints, const blst_fr scalars[]);
+
+/* Extension: release a prepare_msm handle (the blst shim leaks it; the wlc variant exports a free,
+ * arkworks3-sppark-wlc/src/lib.rs:24-42). */
+B200_API void b200_free_msm(void *msm);
+
+/* Extension for measurement and for callers that keep data on the GPU: scalars_dev / out_dev are DEVICE pointers
+ * (batch * npoints blst_fr, batch blst_p1), stream is a cudaStream_t (NULL = default).  Asynchronous. */
+B200_API RustError b200_msm_prepared_device(void *msm, void *out_dev, size_t npoints, const void *scalars_dev, int batch,
+                                   void *stream);
+/* batched host variant: batch scalar vectors of npoints each over the same prepared bases -- the device side of
+ * G1LinComb::g1_lincomb_batch (kzg/src/lib.rs:160-181). */
+B200_API RustError b200_msm_prepared_batch(void *msm, blst_p1 out[], size_t npoints, const blst_fr scalars[], int batch);
+
+/* introspection (bench / tests): window bits, windows, table bytes, kernel launches of the last run */
+B200_API void b200_msm_info(void *msm, int *c, int *W, size_t *table_bytes, int *launches);
+
+
+/* ============================================================================================================== */
+/* NTT -- FFTSettings / FFTFr / DASExtension (kzg/src/lib.rs:421-431, 465-481) as implemented by the blst backend  */
+/* (blst/src/types/fft_settings.rs:28-58, blst/src/fft_fr.rs:112-165, blst/src/data_availability_sampling.rs:78-100) */
+/* Errors: code 1 carries the reference's Err(String) text (bad length etc.); other codes are CUDA errors.        */
+/* ============================================================================================================== */
+
+/* FsFFTSettings::new(scale): roots_of_unity[0..=2^scale] resident on the device. NULL on failure (scale >= 32, no GPU). */
+B200_API void *b200_fft_settings_new(int scale);
+B200_API void b200_fft_settings_free(void *fs);
+B200_API size_t b200_fft_settings_max_width(void *fs);
+/* copy a roots table to the host: which = 0 roots_of_unity (max_width+1), 1 brp_roots_of_unity (max_width),
+ * 2 reverse_roots_of_unity (max_width+1)   (FFTSettings getters, kzg/src/lib.rs:465-481) */
+B200_API RustError b200_fft_settings_roots(void *fs, int which, blst_fr *out);
+
+/* FFTFr::fft_fr(data, inverse) -> out; n must be a power of two <= max_width; natural order in and out. */
+B200_API RustError b200_fft_fr(void *fs, blst_fr *out, const blst_fr *in, size_t n, bool inverse);
+/* DASExtension::das_fft_extension(evens) -> odds; n = len(evens), 2n <= max_width. */
+B200_API RustError b200_das_fft_extension(void *fs, blst_fr *odds, const blst_fr *evens, size_t n);
+/* device-pointer, batched (batch contiguous transforms of n), asynchronous on stream; out_dev != in_dev */
+B200_API RustError b200_fft_fr_device(void *fs, void *out_dev, const void *in_dev, size_t n, int inverse, int batch, void *stream);
+B200_API RustError b200_das_fft_extension_device(void *fs, void *odds_dev, const void *evens_dev, size_t n, int batch, void *stream);
+B200_API int b200_fft_launches(void *fs);
+
+/* ---- device self-test hooks: elementwise field / point kernels on host arrays, used by the parity tests ------- */
+/* op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 inverse(a), 5 to-Montgomery(a), 6 from-Montgomery(a) */
+B200_API RustError b200_selftest_fp(int op, blst_fp *out, const blst_fp *a, const blst_fp *b, size_t n);
+B200_API RustError b200_selftest_fr(int op, blst_fr *out, const blst_fr *a, const blst_fr *b, size_t n);
+/* out[i] = a[i] + b[i] (Jacobian in/out, through the XYZZ mixed / full adders; mixed != 0 converts b to affine first) */
+B200_API RustError b200_selftest_p1_add(blst_p1 *out, const blst_p1 *a, const blst_p1 *b, size_t n, int mixed);
+/* out48[i] = compress(p[i]) */
+B200_API RustError b200_selftest_p1_compress(uint8_t *out48, const blst_p1 *p, size_t n);
+/* integer-pipe microbenchmark: returns achieved 32x32->64 multiply-adds per second (all SMs) through *imad_per_s
+ * and the same for a stream of dependent Fp multiplications through *fpmul_per_s */
+B200_API RustError b200_microbench_int(double *imad_per_s, double *fpmul_per_s);
+
+/* number of CUDA devices usable; 0 means every compute entry point will fail */
+B200_API int b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_KZG_H */

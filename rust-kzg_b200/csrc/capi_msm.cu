@@ -1,0 +1,181 @@
+// capi_msm.cu -- the sppark-shaped MSM FFI (include/b200_kzg.h, section B1) on top of MsmEngine.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+
+#include "../../include/b200_kzg.h"
+#include "capi_common.cuh"
+#include "g1.cuh"
+#include "msm.cuh"
+#include "util.cuh"
+
+using namespace b200;
+
+namespace b200 {
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// window choice.  Work = n * W mixed additions + O(2^(c-1)) reduce additions; the reduce is latency-bound, so
+// stay a notch below the pure work optimum.  Overridable for tuning: B200_MSM_C, B200_MSM_L.
+MsmConfig choose_config(size_t n, bool fixed, int max_batch) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    int c;
+    if (fixed) c = lg >= 18 ? 16 : lg >= 14 ? lg - 2 : lg >= 11 ? 12 : lg >= 8 ? 10 : 8;
+    else c = lg >= 20 ? 16 : lg >= 16 ? 14 : lg >= 12 ? 12 : lg >= 9 ? 10 : 8;
+    c = env_int(fixed ? "B200_MSM_C" : "B200_MSM_VC", c);
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;  // the reduce handles up to 15 bucket-index bits (three 5-bit digits)
+    MsmConfig cfg;
+    cfg.c = c;
+    cfg.W = (256 + c - 1) / c;
+    cfg.fixed = fixed;
+    cfg.n = n;
+    cfg.max_batch = fixed ? max_batch : 1;
+    cfg.L = env_int("B200_MSM_L", 64);
+    return cfg;
+}
+
+struct MsmHandle {
+    std::mutex mu;  // the handle is Send + Sync on the Rust side: serialise users
+    std::unique_ptr<MsmEngine> eng;
+    size_t npoints = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t* scalars_dev = nullptr;  // staging for host-pointer calls
+    uint8_t* out_dev = nullptr;
+    size_t scalars_cap = 0;
+    int out_cap = 0;
+    ~MsmHandle() {
+        cudaFree(scalars_dev);
+        cudaFree(out_dev);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    void ensure_staging(size_t nscalars, int batch) {
+        if (nscalars > scalars_cap) {
+            cudaFree(scalars_dev);
+            scalars_dev = dev_alloc<uint8_t>(nscalars * 32);
+            scalars_cap = nscalars;
+        }
+        if (batch > out_cap) {
+            cudaFree(out_dev);
+            out_dev = dev_alloc<uint8_t>((size_t)batch * 144);
+            out_cap = batch;
+        }
+    }
+};
+
+MsmHandle* msm_handle_create(const void* points, size_t npoints, bool host_points, bool fixed, int max_batch) {
+    require_device();
+    std::unique_ptr<MsmHandle> h(new MsmHandle());
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    MsmConfig cfg = choose_config(npoints, fixed, max_batch);
+    h->eng.reset(new MsmEngine(cfg, points, host_points, h->stream));
+    h->npoints = npoints;
+    return h.release();
+}
+
+}  // namespace b200
+
+extern "C" {
+
+void* prepare_msm(const blst_p1_affine points[], size_t npoints) {
+    try {
+        if (!points || npoints == 0) return nullptr;
+        return msm_handle_create(points, npoints, true, true, env_int("B200_MSM_MAX_BATCH", 1));
+    } catch (const std::exception& e) {
+        fprintf(stderr, "b200kzg: prepare_msm failed: %s\n", e.what());
+        return nullptr;
+    }
+}
+
+void b200_free_msm(void* msm) { delete static_cast<MsmHandle*>(msm); }
+
+RustError b200_msm_prepared_device(void* msm, void* out_dev, size_t npoints, const void* scalars_dev, int batch,
+                                   void* stream) {
+    return guarded([&] {
+        MsmHandle* h = static_cast<MsmHandle*>(msm);
+        if (!h) throw CudaError(-1, "null msm handle");
+        std::lock_guard<std::mutex> lk(h->mu);
+        h->eng->run(scalars_dev, npoints, batch, true, out_dev, (cudaStream_t)stream);
+    });
+}
+
+RustError b200_msm_prepared_batch(void* msm, blst_p1 out[], size_t npoints, const blst_fr scalars[], int batch) {
+    return guarded([&] {
+        MsmHandle* h = static_cast<MsmHandle*>(msm);
+        if (!h) throw CudaError(-1, "null msm handle");
+        if (npoints > h->npoints) throw CudaError(-1, "npoints exceeds the prepared table");
+        if (batch < 1 || batch > h->eng->config().max_batch) throw CudaError(-1, "batch exceeds the prepared capacity");
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (npoints == 0) {
+            memset(out, 0, sizeof(blst_p1) * batch);
+            return;
+        }
+        h->ensure_staging((size_t)batch * npoints, batch);
+        B200_CUDA_CHECK(cudaMemcpyAsync(h->scalars_dev, scalars, (size_t)batch * npoints * 32, cudaMemcpyHostToDevice, h->stream));
+        h->eng->run(h->scalars_dev, npoints, batch, true, h->out_dev, h->stream);
+        B200_CUDA_CHECK(cudaMemcpyAsync(out, h->out_dev, (size_t)batch * 144, cudaMemcpyDeviceToHost, h->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    });
+}
+
+RustError mult_pippenger_prepared(void* msm, blst_p1* out, size_t npoints, const blst_fr scalars[]) {
+    return b200_msm_prepared_batch(msm, out, npoints, scalars, 1);
+}
+
+// variable-base engines are cached per capacity (next power of two) so repeated calls do not re-allocate
+static std::mutex g_var_mu;
+static std::map<size_t, MsmHandle*> g_var_engines;
+
+RustError mult_pippenger(blst_p1* out, const blst_p1_affine points[], size_t npoints, const blst_fr scalars[]) {
+    return guarded([&] {
+        require_device();
+        if (npoints == 0) {
+            memset(out, 0, sizeof(blst_p1));
+            return;
+        }
+        size_t cap = 256;
+        while (cap < npoints) cap <<= 1;
+        MsmHandle* h;
+        {
+            std::lock_guard<std::mutex> lk(g_var_mu);
+            auto it = g_var_engines.find(cap);
+            if (it == g_var_engines.end()) {
+                h = msm_handle_create(nullptr, cap, true, false, 1);
+                g_var_engines[cap] = h;
+            } else {
+                h = it->second;
+            }
+        }
+        std::lock_guard<std::mutex> lk(h->mu);
+        h->ensure_staging(npoints, 1);
+        // bases go straight into the engine's table; scalars to staging
+        B200_CUDA_CHECK(cudaMemcpyAsync(const_cast<void*>(h->eng->table()), points, npoints * 96, cudaMemcpyHostToDevice, h->stream));
+        B200_CUDA_CHECK(cudaMemcpyAsync(h->scalars_dev, scalars, npoints * 32, cudaMemcpyHostToDevice, h->stream));
+        h->eng->run(h->scalars_dev, npoints, 1, true, h->out_dev, h->stream);
+        B200_CUDA_CHECK(cudaMemcpyAsync(out, h->out_dev, 144, cudaMemcpyDeviceToHost, h->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    });
+}
+
+void b200_msm_info(void* msm, int* c, int* W, size_t* table_bytes, int* launches) {
+    MsmHandle* h = static_cast<MsmHandle*>(msm);
+    if (!h) return;
+    if (c) *c = h->eng->config().c;
+    if (W) *W = h->eng->config().W;
+    if (table_bytes) *table_bytes = h->eng->table_bytes();
+    if (launches) *launches = h->eng->launches_per_run();
+}
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+// mont.cuh -- Montgomery arithmetic for BLS12-381 Fp (381 bit, 12 x u32) and Fr (255 bit, 8 x u32) on sm_100a.
+//
+// Layout: little-endian 32-bit limbs in registers, Montgomery form with R = 2^384 (Fp) / 2^256 (Fr) -- bit-identical
+// to blst's blst_fp / blst_fr (kzg/src/eth/c_bindings.rs:427-474), so values cross the C ABI without conversion.
+// Values are always fully reduced to [0, mod) between operations (bit-exact byte output, cheap zero tests).
+//
+// Multiplication is word-serial Montgomery (CIOS) on the integer pipe.  The running sum T is held as two
+// staggered arrays of 64-bit columns,
+//        T = E + (O << 32),     E column k = (E[2k], E[2k+1]),   O column k = (O[2k], O[2k+1]),
+// so that every 32x32->64 product lands on a 64-bit aligned column and a whole row a[even]*w (resp. a[odd]*w) is one
+// carry chain of mad.lo.cc/madc.hi.cc pairs, which ptxas fuses into IMAD.WIDE.U32(.X) -- one SASS instruction per
+// 32x32 product.  Dividing by 2^32 after each row swaps the roles of E and O (a register renaming in the fully
+// unrolled code); the one stray word (old E[1]) is added to new E[0] and its carry is absorbed as the carry-in of
+// the next O-chain, which sits exactly one limb higher.  Per row: 2N wide multiply-adds + 4 scalar ops.
+#pragma once
+#include <stdint.h>
+
+namespace b200 {
+
+// ---- carry-chain rows: acc(2*PAIRS limbs) += a[0], a[2], ... (stride 2) * w ------------------------------------
+// CIN: take the incoming carry flag; the outgoing carry flag is left live for the caller's next asm statement
+// (the statements are adjacent and compiler-generated PTX never touches CC).
+template <int PAIRS, bool CIN>
+struct Chain;
+
+template <bool CIN>
+struct Chain<6, CIN> {
+    static __device__ __forceinline__ void mad(uint32_t* acc, const uint32_t* a, uint32_t w) {
+        if (CIN)
+            asm volatile(
+                "madc.lo.cc.u32 %0, %12, %18, %0;  madc.hi.cc.u32 %1, %12, %18, %1;\n\t"
+                "madc.lo.cc.u32 %2, %13, %18, %2;  madc.hi.cc.u32 %3, %13, %18, %3;\n\t"
+                "madc.lo.cc.u32 %4, %14, %18, %4;  madc.hi.cc.u32 %5, %14, %18, %5;\n\t"
+                "madc.lo.cc.u32 %6, %15, %18, %6;  madc.hi.cc.u32 %7, %15, %18, %7;\n\t"
+                "madc.lo.cc.u32 %8, %16, %18, %8;  madc.hi.cc.u32 %9, %16, %18, %9;\n\t"
+                "madc.lo.cc.u32 %10, %17, %18, %10; madc.hi.cc.u32 %11, %17, %18, %11;"
+                : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+                  "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11])
+                : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(a[8]), "r"(a[10]), "r"(w));
+        else
+            asm volatile(
+                "mad.lo.cc.u32 %0, %12, %18, %0;   madc.hi.cc.u32 %1, %12, %18, %1;\n\t"
+                "madc.lo.cc.u32 %2, %13, %18, %2;  madc.hi.cc.u32 %3, %13, %18, %3;\n\t"
+                "madc.lo.cc.u32 %4, %14, %18, %4;  madc.hi.cc.u32 %5, %14, %18, %5;\n\t"
+                "madc.lo.cc.u32 %6, %15, %18, %6;  madc.hi.cc.u32 %7, %15, %18, %7;\n\t"
+                "madc.lo.cc.u32 %8, %16, %18, %8;  madc.hi.cc.u32 %9, %16, %18, %9;\n\t"
+                "madc.lo.cc.u32 %10, %17, %18, %10; madc.hi.cc.u32 %11, %17, %18, %11;"
+                : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+                  "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11])
+                : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(a[8]), "r"(a[10]), "r"(w));
+    }
+    // acc = a * w (no accumulate), no carries can occur
+    static __device__ __forceinline__ void mul(uint32_t* acc, const uint32_t* a, uint32_t w) {
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(acc[2 * k]), "=r"(acc[2 * k + 1]) : "r"(a[2 * k]), "r"(w));
+    }
+};
+
+template <bool CIN>
+struct Chain<4, CIN> {
+    static __device__ __forceinline__ void mad(uint32_t* acc, const uint32_t* a, uint32_t w) {
+        if (CIN)
+            asm volatile(
+                "madc.lo.cc.u32 %0, %8, %12, %0;  madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+                "madc.lo.cc.u32 %2, %9, %12, %2;  madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+                "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+                "madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.cc.u32 %7, %11, %12, %7;"
+                : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+                  "+r"(acc[7])
+                : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(w));
+        else
+            asm volatile(
+                "mad.lo.cc.u32 %0, %8, %12, %0;   madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
+                "madc.lo.cc.u32 %2, %9, %12, %2;  madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+                "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
+                "madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.cc.u32 %7, %11, %12, %7;"
+                : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+                  "+r"(acc[7])
+                : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(w));
+    }
+    static __device__ __forceinline__ void mul(uint32_t* acc, const uint32_t* a, uint32_t w) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(acc[2 * k]), "=r"(acc[2 * k + 1]) : "r"(a[2 * k]), "r"(w));
+    }
+};
+
+// ---- field parameters -------------------------------------------------------------------------------------------
+// moduli: zkcrypto/bls12_381/src/fp.rs:71, scalar.rs:77 (cross-checked with arkworks3-sppark-wlc/sppark/ff/bls12-381.hpp:10-39)
+struct FpParams {
+    static constexpr int N = 12;
+    static constexpr uint32_t INV = 0xfffcfffdu;  // -p^-1 mod 2^32
+    static __device__ __forceinline__ constexpr uint32_t mod(int i) {
+        constexpr uint32_t M[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                    0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        return M[i];
+    }
+    static __device__ __forceinline__ constexpr uint32_t one(int i) {  // R mod p
+        constexpr uint32_t M[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                                    0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        return M[i];
+    }
+    static __device__ __forceinline__ constexpr uint32_t rr(int i) {  // R^2 mod p
+        constexpr uint32_t M[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
+                                    0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+        return M[i];
+    }
+};
+struct FrParams {
+    static constexpr int N = 8;
+    static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+    static __device__ __forceinline__ constexpr uint32_t mod(int i) {
+        constexpr uint32_t M[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                   0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return M[i];
+    }
+    static __device__ __forceinline__ constexpr uint32_t one(int i) {  // R mod r
+        constexpr uint32_t M[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                                   0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return M[i];
+    }
+    static __device__ __forceinline__ constexpr uint32_t rr(int i) {  // R^2 mod r
+        constexpr uint32_t M[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                                   0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return M[i];
+    }
+};
+
+// ---- the field element ------------------------------------------------------------------------------------------
+template <class P>
+struct __align__(16) Mont {
+    static constexpr int N = P::N;
+    uint32_t v[N];
+
+    static __device__ __forceinline__ Mont zero() {
+        Mont r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = 0;
+        return r;
+    }
+    static __device__ __forceinline__ Mont one() {
+        Mont r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+        return r;
+    }
+    static __device__ __forceinline__ Mont rr() {
+        Mont r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.v[i] = P::rr(i);
+        return r;
+    }
+    __device__ __forceinline__ bool is_zero() const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= v[i];
+        return acc == 0;
+    }
+    __device__ __forceinline__ bool operator==(const Mont& o) const {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) acc |= v[i] ^ o.v[i];
+        return acc == 0;
+    }
+    __device__ __forceinline__ bool operator!=(const Mont& o) const { return !(*this == o); }
+
+    // r = r - mod if r >= mod   (r < 2*mod on entry, top carry bit passed in `hi`)
+    __device__ __forceinline__ void final_sub(uint32_t hi) {
+        uint32_t t[N];
+        uint32_t borrow;
+        asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(t[0]) : "r"(v[0]), "r"(P::mod(0)));
+#pragma unroll
+        for (int i = 1; i < N; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(t[i]) : "r"(v[i]), "r"(P::mod(i)));
+        asm volatile("subc.u32 %0, %1, 0;" : "=r"(borrow) : "r"(hi));
+        // borrow == 0  <=>  value >= mod  -> keep t
+        if (borrow == 0) {
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = t[i];
+        }
+    }
+
+    friend __device__ __forceinline__ Mont operator+(const Mont& a, const Mont& b) {
+        Mont r;
+        uint32_t hi;
+        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+        for (int i = 1; i < N; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
+        asm volatile("addc.u32 %0, 0, 0;" : "=r"(hi));
+        r.final_sub(hi);
+        return r;
+    }
+    friend __device__ __forceinline__ Mont operator-(const Mont& a, const Mont& b) {
+        Mont r;
+        uint32_t borrow;
+        asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+        for (int i = 1; i < N; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
+        asm volatile("subc.u32 %0, 0, 0;" : "=r"(borrow));
+        // borrow is 0 or 0xffffffff: add (mod & borrow)
+        asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r.v[0]) : "r"(P::mod(0) & borrow));
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r.v[i]) : "r"(P::mod(i) & borrow));
+        asm volatile("addc.u32 %0, %0, %1;" : "+r"(r.v[N - 1]) : "r"(P::mod(N - 1) & borrow));
+        return r;
+    }
+    __device__ __forceinline__ Mont neg() const {  // -a mod m  (0 -> 0)
+        Mont r;
+        uint32_t nz = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) nz |= v[i];
+        asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(P::mod(0)), "r"(v[0]));
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(P::mod(i)), "r"(v[i]));
+        asm volatile("subc.u32 %0, %1, %2;" : "=r"(r.v[N - 1]) : "r"(P::mod(N - 1)), "r"(v[N - 1]));
+        if (nz == 0) r = *this;
+        return r;
+    }
+    __device__ __forceinline__ Mont cneg(bool flag) const {
+        Mont n = neg();
+        return flag ? n : *this;
+    }
+    __device__ __forceinline__ Mont dbl() const { return *this + *this; }
+
+    // Montgomery product a*b*R^-1 mod m, fully reduced.
+    friend __device__ __forceinline__ Mont operator*(const Mont& a, const Mont& b) {
+        constexpr int H = N / 2;
+        uint32_t E[N + 2], O[N + 2];  // E uses N+1 limbs, O uses N; +1 so that the renaming below stays in bounds
+        uint32_t mod_[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) mod_[i] = P::mod(i);
+
+        // row 0: T = a * b[0]
+        Chain<H, false>::mul(E, a.v, b.v[0]);
+        Chain<H, false>::mul(O, a.v + 1, b.v[0]);
+        E[N] = 0;
+#pragma unroll
+        for (int i = 0;; i++) {
+            // reduce: T += m * mod, m chosen so that the low word becomes zero
+            uint32_t m = E[0] * P::INV;
+            Chain<H, false>::mad(O, mod_ + 1, m);  // no carry out: (O << 32) <= T < 2^(32(N+1))
+            Chain<H, false>::mad(E, mod_, m);
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(E[N]));
+            if (i == N - 1) break;
+            // T >>= 32:  E' = O (+ stray E[1]),  O'[k] = E[k+2]
+            uint32_t stray = E[1];
+            uint32_t nE[N + 2], nO[N + 2];
+#pragma unroll
+            for (int k = 0; k < N; k++) nE[k] = O[k];
+#pragma unroll
+            for (int k = 0; k < N - 1; k++) nO[k] = E[k + 2];
+            nO[N - 1] = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) { E[k] = nE[k]; O[k] = nO[k]; }
+            // next row: T += a * b[i+1]; the stray word's carry enters the O chain, one limb up
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[0]) : "r"(stray));
+            Chain<H, true>::mad(O, a.v + 1, b.v[i + 1]);
+            Chain<H, false>::mad(E, a.v, b.v[i + 1]);
+            asm volatile("addc.u32 %0, 0, 0;" : "=r"(E[N]));
+        }
+        // result = (E >> 32) + O, then one conditional subtraction
+        Mont r;
+        uint32_t hi;
+        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(O[0]), "r"(E[1]));
+#pragma unroll
+        for (int k = 1; k < N; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.v[k]) : "r"(O[k]), "r"(E[k + 1]));
+        asm volatile("addc.u32 %0, 0, 0;" : "=r"(hi));
+        r.final_sub(hi);
+        return r;
+    }
+    __device__ __forceinline__ Mont sqr() const { return *this * *this; }
+
+    // a^e for a compile-time-known exponent array (little-endian u32 words), plain square-and-multiply
+    template <int W>
+    __device__ __noinline__ Mont pow_words(const uint32_t (&e)[W]) const {
+        Mont acc = one();
+        bool started = false;
+        for (int i = W * 32 - 1; i >= 0; i--) {
+            if (started) acc = acc.sqr();
+            if ((e[i >> 5] >> (i & 31)) & 1) {
+                acc = started ? acc * *this : *this;
+                started = true;
+            }
+        }
+        return acc;
+    }
+    // a^(mod-2)
+    __device__ __noinline__ Mont inverse() const {
+        uint32_t e[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) e[i] = P::mod(i);
+        // subtract 2 with borrow (Fr's low word is 1)
+        uint32_t borrow = 2;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t t = e[i];
+            e[i] = t - borrow;
+            borrow = t < borrow ? 1u : 0u;
+        }
+        return pow_words(e);
+    }
+    __device__ __forceinline__ Mont to_mont() const { return *this * rr(); }  // canonical -> Montgomery
+    __device__ __forceinline__ Mont from_mont() const {                        // Montgomery -> canonical
+        Mont o = zero();
+        o.v[0] = 1;
+        return *this * o;
+    }
+};
+
+typedef Mont<FpParams> fp_t;
+typedef Mont<FrParams> fr_t;
+
+// load / store through 128-bit accesses (fp_t = 48 B = 3 x uint4, fr_t = 32 B = 2 x uint4)
+template <class F>
+__device__ __forceinline__ F load_field(const void* p) {
+    F r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < F::N / 4; i++) {
+        uint4 t = q[i];
+        r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+    }
+    return r;
+}
+template <class F>
+__device__ __forceinline__ F load_field_ro(const void* p) {  // read-only path (LDG.NC)
+    F r;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < F::N / 4; i++) {
+        uint4 t = __ldg(q + i);
+        r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w;
+    }
+    return r;
+}
+template <class F>
+__device__ __forceinline__ void store_field(void* p, const F& a) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < F::N / 4; i++) q[i] = make_uint4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+}
+
+}  // namespace b200

@@ -1,0 +1,543 @@
+// msm.cu -- bucket-method MSM over BLS12-381 G1, hand-written for sm_100a.  See msm.cuh for the pipeline.
+#include "msm.cuh"
+
+#include <algorithm>
+#include <vector>
+
+#include "g1.cuh"
+#include "util.cuh"
+
+namespace b200 {
+
+static constexpr int kAccThreads = 128;  // accumulate CTA: 4 warps, one per SM sub-partition
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1 / 3: signed digits of every scalar; histogram (SCATTER = false) or counting-sort scatter (SCATTER = true).
+// Scalars are read with two 128-bit loads per thread, consecutive threads read consecutive scalars (coalesced).
+// The digit of window j is  raw = bits[c*j, c*j+c) + carry;  raw > 2^(c-1) becomes raw - 2^c with carry 1, so
+// |digit| <= 2^(c-1) and bucket |digit| - 1 of 2^(c-1) buckets; c*W >= 256 > 255 bits guarantees no final carry.
+// Same digit set as the reference's Booth recoding (kzg/src/msm/pippenger_utils.rs:251-281): sum digit_j 2^(cj) = s.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalars, size_t n, size_t row_stride, size_t total,
+                                                int c, int W, int nb, int fixed, int mont, uint32_t* __restrict__ ctr,
+                                                uint32_t* __restrict__ entries) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    size_t vec = gid / n, i = gid - vec * n;
+    fr_t s = load_field_ro<fr_t>(scalars + 2 * gid);
+    if (mont) s = s.from_mont();
+    uint32_t w[9];
+#pragma unroll
+    for (int k = 0; k < 8; k++) w[k] = s.v[k];
+    w[8] = 0;
+    const uint32_t mask = (1u << c) - 1;
+    uint32_t carry = 0;
+    for (int j = 0; j < W; j++) {
+        int o = c * j;
+        uint32_t raw = 0;
+        if (o < 256) {
+            int word = o >> 5, sh = o & 31;
+            uint64_t two = ((uint64_t)w[word + 1] << 32) | w[word];
+            raw = (uint32_t)(two >> sh) & mask;
+        }
+        raw += carry;
+        uint32_t neg = raw > (uint32_t)nb;
+        uint32_t mag = neg ? (1u << c) - raw : raw;
+        carry = neg;
+        if (mag != 0) {
+            size_t group = fixed ? vec : vec * W + j;
+            size_t key = group * nb + (mag - 1);
+            if (SCATTER) {
+                uint32_t pos = atomicAdd(&ctr[key], 1u);
+                uint32_t idx = (uint32_t)(fixed ? (size_t)j * row_stride + i : i);
+                entries[pos] = idx | (neg << 31);
+            } else {
+                atomicAdd(&ctr[key], 1u);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2: exclusive scan of u32 (three small kernels; n up to ~2^21 keys).  out[n] = total.
+static constexpr int kScanBlock = 1024;
+static constexpr int kScanItems = 4;  // per thread -> 4096 per CTA
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += y;
+        }
+        warp_sums[lane] = s;
+    }
+    __syncthreads();
+    uint32_t base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[31];
+    __syncthreads();
+    return base + x - v;
+}
+// f: 0 = identity, otherwise ceil(x / f)  (task counts)
+__global__ void __launch_bounds__(kScanBlock) k_scan_partial(const uint32_t* __restrict__ in, size_t n, uint32_t f,
+                                                             uint32_t* __restrict__ block_sums) {
+    size_t base = ((size_t)blockIdx.x * kScanBlock + threadIdx.x) * kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++)
+        if (base + k < n) { uint32_t x = in[base + k]; s += f ? (x + f - 1) / f : x; }
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_blocks(uint32_t* block_sums, int nblocks) {
+    // single CTA, nblocks <= kScanBlock * kScanItems
+    uint32_t v[kScanItems], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        int idx = threadIdx.x * kScanItems + k;
+        v[k] = idx < nblocks ? block_sums[idx] : 0;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        int idx = threadIdx.x * kScanItems + k;
+        if (idx < nblocks) block_sums[idx] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[nblocks] = total;
+}
+__global__ void __launch_bounds__(kScanBlock) k_scan_final(const uint32_t* __restrict__ in, size_t n, uint32_t f,
+                                                           const uint32_t* __restrict__ block_sums,
+                                                           uint32_t* __restrict__ out, uint32_t* __restrict__ out2) {
+    size_t base = ((size_t)blockIdx.x * kScanBlock + threadIdx.x) * kScanItems;
+    uint32_t v[kScanItems], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        uint32_t x = base + k < n ? in[base + k] : 0;
+        v[k] = f ? (x + f - 1) / f : x;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) {
+            out[base + k] = ex;
+            if (out2) out2[base + k] = ex;
+        }
+        ex += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanBlock - 1) {
+        out[n] = block_sums[gridDim.x];
+        if (out2) out2[n] = block_sums[gridDim.x];
+    }
+}
+// out[i] = exclusive prefix of f(in[i]) for i < n; out[n] = total; out2 (optional) gets a copy.
+static int scan_exclusive(const uint32_t* in, size_t n, uint32_t f, uint32_t* out, uint32_t* out2, uint32_t* tmp,
+                          cudaStream_t st) {
+    int nblocks = (int)div_up(n, (size_t)kScanBlock * kScanItems);
+    if (nblocks > kScanBlock * kScanItems) throw CudaError(-1, "scan_exclusive: too many keys");
+    k_scan_partial<<<nblocks, kScanBlock, 0, st>>>(in, n, f, tmp);
+    k_scan_blocks<<<1, kScanBlock, 0, st>>>(tmp, nblocks);
+    k_scan_final<<<nblocks, kScanBlock, 0, st>>>(in, n, f, tmp, out, out2);
+    B200_LAUNCH_CHECK();
+    return 3;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 4: tasks.  Bucket `key` with cnt entries becomes ceil(cnt/L) tasks; tasks are counting-sorted by length
+// (descending) so the 32 lanes of a warp run the same trip count and long tasks start first.
+// size_hist layout: [0..L] histogram, [L+1..2L+1] base, [2L+2..3L+2] cursor.
+__global__ void __launch_bounds__(256) k_task_hist(const uint32_t* __restrict__ counts, size_t nkeys, int L,
+                                                   uint32_t* __restrict__ size_hist) {
+    extern __shared__ uint32_t sh[];
+    for (int k = threadIdx.x; k <= L; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    size_t key = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (key < nkeys) {
+        uint32_t cnt = counts[key];
+        if (cnt) {
+            uint32_t tc = (cnt + L - 1) / L, rem = cnt - (tc - 1) * L;
+            atomicAdd(&sh[rem], 1u);
+            if (tc > 1) atomicAdd(&sh[L], tc - 1);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k <= L; k += blockDim.x)
+        if (sh[k]) atomicAdd(&size_hist[k], sh[k]);
+}
+__global__ void k_task_bases(uint32_t* size_hist, int L) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t run = 0;
+        for (int s = L; s >= 1; s--) {
+            size_hist[L + 1 + s] = run;
+            size_hist[2 * L + 2 + s] = 0;
+            run += size_hist[s];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_task_emit(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                   const uint32_t* __restrict__ task_base, size_t nkeys, int L,
+                                                   uint32_t* __restrict__ size_hist, uint32_t* __restrict__ sorted_tasks) {
+    size_t key = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nkeys) return;
+    uint32_t cnt = counts[key];
+    if (!cnt) return;
+    uint32_t tc = (cnt + L - 1) / L, rem = cnt - (tc - 1) * L;
+    uint32_t start = offsets[key], slot = task_base[key];
+    const uint32_t* base = size_hist + L + 1;
+    uint32_t* cur = size_hist + 2 * L + 2;
+    if (tc > 1) {
+        uint32_t p = base[L] + atomicAdd(&cur[L], tc - 1);
+        for (uint32_t q = 0; q + 1 < tc; q++) {
+            sorted_tasks[3 * (size_t)(p + q)] = start + q * L;
+            sorted_tasks[3 * (size_t)(p + q) + 1] = L;
+            sorted_tasks[3 * (size_t)(p + q) + 2] = slot + q;
+        }
+    }
+    uint32_t p = base[rem] + atomicAdd(&cur[rem], 1u);
+    sorted_tasks[3 * (size_t)p] = start + (tc - 1) * L;
+    sorted_tasks[3 * (size_t)p + 1] = rem;
+    sorted_tasks[3 * (size_t)p + 2] = slot + tc - 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 5: bucket accumulation -- the dominant kernel.  One thread per task; the running XYZZ sum lives in registers, each
+// step gathers one 96-byte affine point (six 128-bit read-only loads) and does a mixed addition (8M + 2S).
+__global__ void __launch_bounds__(kAccThreads) k_accumulate(const uint8_t* __restrict__ table,
+                                                            const uint32_t* __restrict__ entries,
+                                                            const uint32_t* __restrict__ sorted_tasks,
+                                                            const uint32_t* __restrict__ n_tasks_ptr,
+                                                            uint8_t* __restrict__ partials) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *n_tasks_ptr) return;
+    uint32_t start = sorted_tasks[3 * t], len = sorted_tasks[3 * t + 1], slot = sorted_tasks[3 * t + 2];
+    xyzz_t acc = xyzz_t::inf();
+    const uint32_t* e = entries + start;
+    for (uint32_t k = 0; k < len; k++) {
+        uint32_t v = e[k];
+        affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
+        p.y = p.y.cneg(v >> 31);
+        xyzz_add_affine(acc, p);
+    }
+    store_xyzz(partials + (size_t)slot * 192, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 6: bucket reduction  S_g = sum_b (b+1) * B_b  per group.  A running sum over 2^(c-1) buckets is a chain of
+// dependent point additions (the reference's p1_integrate_buckets, kzg/src/msm/tiling_pippenger_ops.rs:21-45), and a
+// single thread needs several microseconds per addition, so the chain is replaced by a shallow, wide form.
+// Write the bucket index in D <= 3 "digits" b = sum_a v_a << sh_a (each digit <= 5 bits).  Then
+//        sum_b b * B_b = sum_a 2^(sh_a) * sum_v v * M[a][v],     M[a][v] = sum of the buckets whose digit a equals v,
+// i.e. D*32 independent plain sums (tree reductions) followed by D weighted sums over <= 32 items, each done by one
+// warp with a suffix scan in registers (sum_v v*M_v = sum_{k>=1} Suf_k).  Depth ~ 30 additions instead of 2^c.
+
+__device__ __forceinline__ fp_t shfl_down_fp(const fp_t& a, int d) {
+    fp_t r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
+    return r;
+}
+__device__ __forceinline__ xyzz_t shfl_down_xyzz(const xyzz_t& v, int d) {
+    xyzz_t o;
+    o.x = shfl_down_fp(v.x, d); o.y = shfl_down_fp(v.y, d); o.zzz = shfl_down_fp(v.zzz, d); o.zz = shfl_down_fp(v.zz, d);
+    return o;
+}
+// lane 0 ends up with the sum over the warp
+__device__ __forceinline__ xyzz_t warp_sum_xyzz(xyzz_t v) {
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(v, d);
+        xyzz_add(v, o);
+    }
+    return v;
+}
+// inclusive suffix scan: lane l gets sum_{m >= l} v_m
+__device__ __forceinline__ xyzz_t warp_suffix_scan_xyzz(xyzz_t v) {
+    int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        xyzz_t o = shfl_down_xyzz(v, d);
+        if (lane + d >= 32) o = xyzz_t::inf();
+        xyzz_add(v, o);
+    }
+    return v;
+}
+
+// 6a: buckets that were cut into several tasks: fold the task partials into the first slot.
+// WARP = false: one thread per bucket, 2..32 partials.  WARP = true: one warp per bucket with more than 32 partials.
+template <bool WARP>
+__global__ void __launch_bounds__(128) k_bucket_combine(uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
+                                                        size_t nkeys) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t key = WARP ? gid >> 5 : gid;
+    if (key >= nkeys) return;
+    uint32_t s0 = task_base[key], s1 = task_base[key + 1];
+    uint32_t tc = s1 - s0;
+    if (WARP) {
+        if (tc <= 32) return;
+        int lane = threadIdx.x & 31;
+        xyzz_t acc = xyzz_t::inf();
+        for (uint32_t s = s0 + lane; s < s1; s += 32) {
+            xyzz_t part = load_xyzz(partials + (size_t)s * 192);
+            xyzz_add(acc, part);
+        }
+        acc = warp_sum_xyzz(acc);
+        if (lane == 0) store_xyzz(partials + (size_t)s0 * 192, acc);
+    } else {
+        if (tc < 2 || tc > 32) return;
+        xyzz_t acc = load_xyzz(partials + (size_t)s0 * 192);
+        for (uint32_t s = s0 + 1; s < s1; s++) {
+            xyzz_t part = load_xyzz(partials + (size_t)s * 192);
+            xyzz_add(acc, part);
+        }
+        store_xyzz(partials + (size_t)s0 * 192, acc);
+    }
+}
+
+struct AxisPlan {
+    int D;
+    int w[3];   // digit widths (bits), sum = c - 1
+    int sh[3];  // digit bit offsets
+};
+
+// 6b: marginal sums.  CTA (v, a, g) adds up the nb >> w[a] buckets of group g whose digit a equals v.
+static constexpr int kMargThreads = 128;
+__global__ void __launch_bounds__(kMargThreads) k_marginals(const uint8_t* __restrict__ partials,
+                                                            const uint32_t* __restrict__ task_base, int nb, AxisPlan ap,
+                                                            uint8_t* __restrict__ marg) {
+    __shared__ __align__(16) uint8_t sh[(kMargThreads / 32) * 192];
+    const int v = blockIdx.x, a = blockIdx.y;
+    const size_t g = blockIdx.z;
+    uint8_t* dst = marg + ((g * 3 + a) * 32 + v) * 192;
+    const int wa = ap.w[a], sa = ap.sh[a];
+    if (v >= (1 << wa)) {
+        if (threadIdx.x == 0) store_xyzz(dst, xyzz_t::inf());
+        return;
+    }
+    const int count = nb >> wa;
+    xyzz_t acc = xyzz_t::inf();
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        int b = ((i >> sa) << (sa + wa)) | (v << sa) | (i & ((1 << sa) - 1));
+        size_t key = g * nb + b;
+        uint32_t s0 = task_base[key];
+        if (task_base[key + 1] > s0) {
+            xyzz_t part = load_xyzz(partials + (size_t)s0 * 192);
+            xyzz_add(acc, part);
+        }
+    }
+    acc = warp_sum_xyzz(acc);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) store_xyzz(sh + wid * 192, acc);
+    __syncthreads();
+    if (wid == 0) {
+        xyzz_t u = lane < (kMargThreads / 32) ? load_xyzz(sh + lane * 192) : xyzz_t::inf();
+        // only kMargThreads/32 lanes hold data: a short tree
+#pragma unroll 1
+        for (int d = (kMargThreads / 64); d >= 1; d >>= 1) {
+            xyzz_t o = shfl_down_xyzz(u, d);
+            xyzz_add(u, o);
+        }
+        if (lane == 0) store_xyzz(dst, u);
+    }
+}
+
+// 6c: one CTA per group, one warp per digit axis: weighted sum over the <= 32 marginals, scale by 2^sh, combine.
+__global__ void __launch_bounds__(96) k_group_finish(const uint8_t* __restrict__ marg, AxisPlan ap,
+                                                     uint8_t* __restrict__ group_sums, uint8_t* __restrict__ out_jac) {
+    __shared__ __align__(16) uint8_t sh[4 * 192];
+    const size_t g = blockIdx.x;
+    const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
+    if (a < ap.D) {
+        xyzz_t m = load_xyzz(marg + ((g * 3 + a) * 32 + lane) * 192);
+        xyzz_t suf = warp_suffix_scan_xyzz(m);          // Suf_l = sum_{v >= l} M_v ; Suf_0 = sum of all buckets
+        if (a == 0 && lane == 0) store_xyzz(sh + 3 * 192, suf);
+        if (lane == 0) suf = xyzz_t::inf();              // sum_v v*M_v = sum_{k >= 1} Suf_k
+        xyzz_t wsum = warp_sum_xyzz(suf);
+        if (lane == 0) {
+            for (int k = 0; k < ap.sh[a]; k++) xyzz_dbl(wsum);
+            store_xyzz(sh + a * 192, wsum);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        xyzz_t acc = load_xyzz(sh + 3 * 192);            // the "+1" of the weights b+1
+        for (int k = 0; k < ap.D; k++) {
+            xyzz_t o = load_xyzz(sh + k * 192);
+            xyzz_add(acc, o);
+        }
+        if (group_sums) store_xyzz(group_sums + g * 192, acc);
+        if (out_jac) store_jac(out_jac + g * 144, xyzz_to_jac(acc));
+    }
+}
+// 7 (VARIABLE): result = sum_j 2^(c*j) S_j, Horner from the top window (as tiling_pippenger does,
+// kzg/src/msm/tiling_pippenger_ops.rs:106-138).  One thread: W*c doublings.
+__global__ void k_horner(const uint8_t* __restrict__ group_sums, int W, int c, uint8_t* __restrict__ out_jac) {
+    if (threadIdx.x || blockIdx.x) return;
+    xyzz_t acc = load_xyzz(group_sums + (size_t)(W - 1) * 192);
+    for (int j = W - 2; j >= 0; j--) {
+        for (int k = 0; k < c; k++) xyzz_dbl(acc);
+        xyzz_t s = load_xyzz(group_sums + (size_t)j * 192);
+        xyzz_add(acc, s);
+    }
+    store_jac(out_jac, xyzz_to_jac(acc));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// table rows for FIXED engines: row j = 2^(c*j) * P_i, affine.  One thread per point walks all rows
+// (c doublings in XYZZ, then one field inversion back to affine).  One-time cost at prepare.
+__global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table, size_t n, int W, int c) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t p = load_affine(table + i * 96);
+    for (int j = 1; j < W; j++) {
+        xyzz_t q = affine_to_xyzz(p);
+        for (int k = 0; k < c; k++) xyzz_dbl(q);
+        p = xyzz_to_affine(q);
+        store_affine(table + ((size_t)j * n + i) * 96, p);
+    }
+}
+
+// Jacobian -> 48-byte compressed (blst_p1_compress): one thread per point, one inversion each.
+__global__ void k_compress(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    jac_t p = load_jac(jac + (size_t)i * 144);
+    affine_t a = jac_to_affine(p);
+    affine_compress(out + (size_t)i * 48, a);
+}
+void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int count, cudaStream_t stream) {
+    if (count <= 0) return;
+    k_compress<<<div_up(count, 32), 32, 0, stream>>>((const uint8_t*)jac_dev, out48_dev, count);
+    B200_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points, cudaStream_t stream) : cfg_(cfg) {
+    if (cfg_.c < 2 || cfg_.c > 16 || cfg_.c * cfg_.W < 256) throw CudaError(-1, "MsmEngine: bad window configuration");
+    if (cfg_.L < 1 || cfg_.L > 1024) throw CudaError(-1, "MsmEngine: bad task length");
+    if (!cfg_.fixed) cfg_.max_batch = 1;
+    nb_ = 1 << (cfg_.c - 1);
+    groups_max_ = cfg_.fixed ? (size_t)cfg_.max_batch : (size_t)cfg_.W;
+    keys_max_ = groups_max_ * nb_;
+    entries_max_ = (size_t)cfg_.max_batch * cfg_.n * cfg_.W;
+    if (entries_max_ >= (1ull << 32) || (cfg_.fixed ? cfg_.n * cfg_.W : cfg_.n) >= (1ull << 31))
+        throw CudaError(-1, "MsmEngine: problem too large for 32-bit entry indices");
+    tasks_max_ = entries_max_ / cfg_.L + keys_max_ + 1;
+    size_t rows = cfg_.fixed ? cfg_.W : 1;
+    table_bytes_ = rows * cfg_.n * 96;
+    table_ = dev_alloc<uint8_t>(table_bytes_);
+    counts_ = dev_alloc<uint32_t>(keys_max_ + 1);
+    offsets_ = dev_alloc<uint32_t>(keys_max_ + 1);
+    cursor_ = dev_alloc<uint32_t>(keys_max_ + 1);
+    task_base_ = dev_alloc<uint32_t>(keys_max_ + 1);
+    entries_ = dev_alloc<uint32_t>(entries_max_);
+    sorted_tasks_ = dev_alloc<uint32_t>(3 * tasks_max_);
+    size_hist_ = dev_alloc<uint32_t>(3 * (cfg_.L + 1));
+    scan_tmp_ = dev_alloc<uint32_t>(kScanBlock * kScanItems + 1);
+    partials_ = dev_alloc<uint8_t>(tasks_max_ * 192);
+    chunk_sums_ = dev_alloc<uint8_t>(groups_max_ * 3 * 32 * 192);  // marginal sums [group][axis][32]
+    group_sums_ = dev_alloc<uint8_t>(groups_max_ * 192);
+    if (points) {
+        B200_CUDA_CHECK(cudaMemcpyAsync(table_, points, cfg_.n * 96, host_points ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
+        if (cfg_.fixed && cfg_.W > 1) {
+            k_build_rows<<<div_up(cfg_.n, 128), 128, 0, stream>>>((uint8_t*)table_, cfg_.n, cfg_.W, cfg_.c);
+            B200_LAUNCH_CHECK();
+        }
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+}
+
+MsmEngine::~MsmEngine() {
+    cudaFree(table_); cudaFree(counts_); cudaFree(offsets_); cudaFree(cursor_); cudaFree(task_base_); cudaFree(entries_);
+    cudaFree(sorted_tasks_); cudaFree(size_hist_); cudaFree(scan_tmp_); cudaFree(partials_); cudaFree(chunk_sums_);
+    cudaFree(group_sums_);
+}
+
+void MsmEngine::set_points(const void* points_dev, size_t npoints, cudaStream_t stream) {
+    if (cfg_.fixed) throw CudaError(-1, "set_points on a FIXED engine");
+    if (npoints > cfg_.n) throw CudaError(-1, "set_points: too many points");
+    B200_CUDA_CHECK(cudaMemcpyAsync(table_, points_dev, npoints * 96, cudaMemcpyDeviceToDevice, stream));
+}
+
+void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mont, void* out_dev, cudaStream_t st) {
+    if (npoints > cfg_.n || batch < 1 || batch > cfg_.max_batch) throw CudaError(-1, "MsmEngine::run: bad sizes");
+    const int c = cfg_.c, W = cfg_.W, L = cfg_.L;
+    const size_t groups = cfg_.fixed ? (size_t)batch : (size_t)W;
+    const size_t nkeys = groups * nb_;
+    const size_t total = (size_t)batch * npoints;
+    int launches = 0;
+    if (total == 0) {
+        B200_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, (size_t)batch * 144, st));
+        launches_ = 0;
+        return;
+    }
+    B200_CUDA_CHECK(cudaMemsetAsync(counts_, 0, (nkeys + 1) * sizeof(uint32_t), st));
+    B200_CUDA_CHECK(cudaMemsetAsync(size_hist_, 0, 3 * (L + 1) * sizeof(uint32_t), st));
+    // 1 digits + histogram
+    k_digits<false><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, cfg_.n, total, c, W, nb_,
+                                                        cfg_.fixed, mont, counts_, nullptr);
+    launches++;
+    // 2 offsets (and a working copy for the scatter cursors), task bases
+    launches += scan_exclusive(counts_, nkeys, 0, offsets_, cursor_, scan_tmp_, st);
+    launches += scan_exclusive(counts_, nkeys, (uint32_t)L, task_base_, nullptr, scan_tmp_, st);
+    // 3 scatter
+    k_digits<true><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, cfg_.n, total, c, W, nb_,
+                                                       cfg_.fixed, mont, cursor_, entries_);
+    launches++;
+    // 4 tasks sorted by length
+    k_task_hist<<<div_up(nkeys, 256), 256, (L + 1) * sizeof(uint32_t), st>>>(counts_, nkeys, L, size_hist_);
+    k_task_bases<<<1, 32, 0, st>>>(size_hist_, L);
+    k_task_emit<<<div_up(nkeys, 256), 256, 0, st>>>(counts_, offsets_, task_base_, nkeys, L, size_hist_, sorted_tasks_);
+    launches += 3;
+    // 5 accumulate: grid sized for the worst case, surplus threads exit on the device-side task count
+    size_t tasks_bound = std::min(tasks_max_, total * W / L + nkeys + 1);
+    k_accumulate<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
+                                                                          task_base_ + nkeys, (uint8_t*)partials_);
+    launches++;
+    // 6 reduce
+    k_bucket_combine<false><<<div_up(nkeys, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
+    k_bucket_combine<true><<<div_up(nkeys * 32, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
+    AxisPlan ap{};
+    {
+        int bits = c - 1;
+        ap.D = (bits + 4) / 5;
+        if (ap.D < 1) ap.D = 1;
+        int off = 0;
+        for (int a = 0; a < 3; a++) {
+            int wa = a < ap.D ? (bits - off + (ap.D - a) - 1) / (ap.D - a) : 0;
+            ap.w[a] = wa;
+            ap.sh[a] = off;
+            off += wa;
+        }
+    }
+    k_marginals<<<dim3(32, ap.D, (unsigned)groups), kMargThreads, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap,
+                                                                          (uint8_t*)chunk_sums_);
+    launches += 3;
+    if (cfg_.fixed) {
+        k_group_finish<<<(unsigned)groups, 96, 0, st>>>((const uint8_t*)chunk_sums_, ap, nullptr, (uint8_t*)out_dev);
+        launches += 1;
+    } else {
+        k_group_finish<<<(unsigned)groups, 96, 0, st>>>((const uint8_t*)chunk_sums_, ap, (uint8_t*)group_sums_, nullptr);
+        k_horner<<<1, 32, 0, st>>>((const uint8_t*)group_sums_, W, c, (uint8_t*)out_dev);
+        launches += 2;
+    }
+    B200_LAUNCH_CHECK();
+    launches_ = launches;
+}
+
+}  // namespace b200

@@ -1,0 +1,87 @@
+// msm.cuh -- interface of the bucket-method (Pippenger) MSM engine over BLS12-381 G1 for sm_100a.
+//
+// Replaces, behind the same contract, the reference's CPU MSM (kzg/src/msm/msm_impls.rs:114-148 -> tiling_pippenger /
+// BgmwTable) and its sppark GPU plug (blst-sppark/cuda/pippenger.cu:23-38).  Results are the same group element,
+// hence byte-identical after compression; window size, digit recoding and addition order are free
+// (SURVEY.md section 7 "hard parts").
+//
+// One engine serves both shapes of the path:
+//   FIXED    bases known in advance (prepare_msm / trusted setup): the table holds W rows  2^(c*j) * P_i  in affine
+//            form, so all W signed digits of a scalar go to ONE bucket set and no per-window Horner tail exists
+//            (the idea of the reference's default BGMW table, kzg/src/msm/bgmw.rs:206-304, re-laid for HBM).
+//            A batch of B scalar vectors over the same bases (B blobs) is one launch sequence: bucket sets are
+//            indexed (vector, bucket).
+//   VARIABLE bases arrive with the call (mult_pippenger, g1_lincomb(.., None)): one bucket set per window,
+//            then a device Horner pass.
+//
+// Pipeline (all on one stream, no host synchronisation inside):
+//   1 digits+count   signed c-bit digits of every scalar, histogram of (group, bucket) keys        [HBM/atomics]
+//   2 scan           exclusive prefix sums -> bucket offsets, task bases                           [tiny]
+//   3 scatter        counting-sort the (point index, sign) entries by key                          [HBM/atomics]
+//   4 tasks          cut every bucket into tasks of <= L entries, counting-sort tasks by length    [tiny]
+//   5 accumulate     one thread per task: XYZZ += affine over its entries  (the dominant kernel)   [integer pipe]
+//   6 reduce         per group: sum_b b * B_b  (chunked running sums, scalar offset, tree sum)     [latency]
+//   7 (VARIABLE)     Horner over the W window sums
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct MsmConfig {
+    int c;          // window width in bits
+    int W;          // number of windows, c*W >= 256
+    bool fixed;     // FIXED (table rows) or VARIABLE
+    size_t n;       // points per scalar vector
+    int max_batch;  // scalar vectors per call (FIXED only; VARIABLE uses 1)
+    int L;          // max entries per accumulate task
+};
+
+class MsmEngine {
+public:
+    // points: n affine points (blst_p1_affine layout), device or host pointer (host_points says which).
+    MsmEngine(const MsmConfig& cfg, const void* points, bool host_points, cudaStream_t stream);
+    ~MsmEngine();
+    MsmEngine(const MsmEngine&) = delete;
+
+    // scalars_dev: batch * n scalars of 32 B in device memory; mont = blst_fr Montgomery form (else canonical LE).
+    // out_dev: batch Jacobian points (blst_p1 layout) in device memory.  npoints <= n uses the first npoints bases.
+    void run(const void* scalars_dev, size_t npoints, int batch, bool mont, void* out_dev, cudaStream_t stream);
+
+    // VARIABLE engines only: replace the bases (device pointer, n points).
+    void set_points(const void* points_dev, size_t npoints, cudaStream_t stream);
+
+    const MsmConfig& config() const { return cfg_; }
+    size_t table_bytes() const { return table_bytes_; }
+    // launches of our kernels per run() (for bench.py's gpu_launches)
+    int launches_per_run() const { return launches_; }
+    const void* table() const { return table_; }
+
+private:
+    MsmConfig cfg_;
+    int nb_;              // buckets per group = 2^(c-1)
+    size_t groups_max_;   // max_batch (FIXED) or W (VARIABLE)
+    size_t keys_max_;     // groups_max * nb
+    size_t entries_max_;  // max_batch * n * W
+    size_t tasks_max_;
+    size_t table_bytes_;
+    int launches_ = 0;
+    void* table_ = nullptr;      // affine rows
+    uint32_t* counts_ = nullptr;  // [keys+1]
+    uint32_t* offsets_ = nullptr;
+    uint32_t* cursor_ = nullptr;
+    uint32_t* task_base_ = nullptr;
+    uint32_t* entries_ = nullptr;
+    uint32_t* sorted_tasks_ = nullptr;  // 3 x u32 per task
+    uint32_t* size_hist_ = nullptr;     // [L+1] hist, [L+1] base, [L+1] cursor
+    uint32_t* scan_tmp_ = nullptr;
+    void* partials_ = nullptr;  // xyzz per task
+    void* chunk_sums_ = nullptr;
+    void* group_sums_ = nullptr;
+};
+
+// helpers shared with other translation units
+void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int count, cudaStream_t stream);
+
+}  // namespace b200

@@ -1,0 +1,248 @@
+// ntt.cu -- Fr NTT / inverse NTT / DAS extension kernels for sm_100a.  See ntt.cuh for the decomposition.
+#include "ntt.cuh"
+
+#include <algorithm>
+
+#include "mont.cuh"
+#include "util.cuh"
+
+namespace b200 {
+
+static constexpr int kNttThreads = 256;
+static constexpr int kMaxLogM = 11;          // largest in-CTA sub-transform: 2^11 points = 64 KiB of shared memory
+static constexpr int kTileElems = 1 << 11;   // G * m points per CTA
+
+struct NttPass {
+    const uint8_t* in;
+    uint8_t* out;
+    int log_m;              // sub-transform size m = 2^log_m
+    int G;                  // columns handled by one CTA
+    size_t ncols;           // columns per transform
+    size_t in_cstride, in_rstride, out_cstride, out_rstride;  // element strides
+    int in_col_fast, out_col_fast;  // which index runs fastest across consecutive threads (coalescing)
+    const uint8_t* roots;   // w^0 .. w^nmax
+    size_t nmax;
+    size_t unit_m;          // nmax / m
+    int inverse;
+    size_t tw_unit;         // 0: none; else outputs (q, col) are multiplied by w_N^(q*col), w_N = roots[tw_unit]
+    size_t twist_unit;      // 0: none; else input element with natural index j is multiplied by roots[j*twist_unit]
+    const uint8_t* scale;   // nullptr or one Fr multiplied into every output (n^-1)
+    size_t batch_stride;    // elements between consecutive transforms of the batch
+};
+
+__device__ __forceinline__ fr_t root_at(const NttPass& p, size_t e_units) {
+    // e_units = exponent * unit, 0 <= e_units <= nmax
+    size_t idx = p.inverse ? p.nmax - e_units : e_units;
+    return load_field_ro<fr_t>(p.roots + idx * 32);
+}
+
+__global__ void __launch_bounds__(kNttThreads) k_ntt_pass(NttPass p) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int m = 1 << p.log_m;
+    const int tile = p.G * m;
+    const size_t col0 = (size_t)blockIdx.x * p.G;
+    const uint8_t* in = p.in + (size_t)blockIdx.y * p.batch_stride * 32;
+    uint8_t* out = p.out + (size_t)blockIdx.y * p.batch_stride * 32;
+
+    // load (optionally twisted), bit-reversed row index into shared memory
+    for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+        int g, r;
+        if (p.in_col_fast) { g = e % p.G; r = e / p.G; } else { g = e >> p.log_m; r = e & (m - 1); }
+        size_t col = col0 + g;
+        fr_t x = fr_t::zero();
+        if (col < p.ncols) {
+            size_t j = col * p.in_cstride + (size_t)r * p.in_rstride;
+            x = load_field_ro<fr_t>(in + j * 32);
+            if (p.twist_unit) x = x * load_field_ro<fr_t>(p.roots + (j * p.twist_unit) * 32);
+        }
+        int rr = p.log_m ? (int)(__brev((unsigned)r) >> (32 - p.log_m)) : 0;
+        store_field(sm + (size_t)(g * m + rr) * 32, x);
+    }
+    __syncthreads();
+
+    // radix-2 decimation-in-time butterflies (blst/src/fft_fr.rs:98-103): lo' = lo + w*hi, hi' = lo - w*hi
+    const int halfm = m >> 1;
+    for (int t = 0; t < p.log_m; t++) {
+        const int half = 1 << t;
+        for (int b = threadIdx.x; b < p.G * halfm; b += blockDim.x) {
+            int g = b / halfm, k = b - g * halfm;
+            int lowk = k & (half - 1);
+            int i = ((k >> t) << (t + 1)) | lowk;
+            uint8_t* plo = sm + (size_t)(g * m + i) * 32;
+            uint8_t* phi = plo + (size_t)half * 32;
+            fr_t u = load_field<fr_t>(plo), v = load_field<fr_t>(phi);
+            if (lowk) v = v * root_at(p, ((size_t)lowk << (p.log_m - 1 - t)) * p.unit_m);
+            store_field(plo, u + v);
+            store_field(phi, u - v);
+        }
+        __syncthreads();
+    }
+
+    // store (optionally with the inter-pass twiddle and the 1/n scale)
+    fr_t sc;
+    if (p.scale) sc = load_field_ro<fr_t>(p.scale);
+    for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+        int g, q;
+        if (p.out_col_fast) { g = e % p.G; q = e / p.G; } else { g = e >> p.log_m; q = e & (m - 1); }
+        size_t col = col0 + g;
+        if (col >= p.ncols) continue;
+        fr_t x = load_field<fr_t>(sm + (size_t)(g * m + q) * 32);
+        if (p.tw_unit && q && col) x = x * root_at(p, (size_t)q * col * p.tw_unit);
+        if (p.scale) x = x * sc;
+        store_field(out + (col * p.out_cstride + (size_t)q * p.out_rstride) * 32, x);
+    }
+}
+
+// ---- settings: roots of unity on the device -------------------------------------------------------------------
+// pw[b] = root^(2^b), b <= scale  (single thread)
+__global__ void k_root_powers(const uint32_t* exp_words /*8*/, uint8_t* pw, int scale, uint8_t* inv_n /*32 Fr*/) {
+    if (threadIdx.x || blockIdx.x) return;
+    // SCALE2_ROOT_OF_UNITY[scale] = 7^((r-1)/2^scale) (blst/src/consts.rs:14-50); the exponent arrives precomputed
+    fr_t seven = fr_t::zero();
+    seven.v[0] = 7;
+    seven = seven.to_mont();
+    fr_t acc = fr_t::one();
+    for (int i = 255; i >= 0; i--) {
+        acc = acc.sqr();
+        if ((exp_words[i >> 5] >> (i & 31)) & 1) acc = acc * seven;
+    }
+    for (int b = 0; b <= scale; b++) {
+        store_field(pw + b * 32, acc);
+        acc = acc.sqr();
+    }
+    // inv_n[k] = (2^k)^-1: halve repeatedly from 1 (multiply by 2^-1 = (r+1)/2)
+    fr_t two = fr_t::one() + fr_t::one();
+    fr_t half = two.inverse();
+    fr_t cur = fr_t::one();
+    for (int k = 0; k < 32; k++) {
+        store_field(inv_n + k * 32, cur);
+        cur = cur * half;
+    }
+}
+// roots[i] = root^i for i in [0, n], by binary expansion over pw[]
+__global__ void k_roots_table(const uint8_t* pw, uint8_t* roots, uint8_t* brp, size_t n, int scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    fr_t acc = fr_t::one();
+    for (int b = 0; b <= scale; b++)
+        if ((i >> b) & 1) acc = acc * load_field_ro<fr_t>(pw + b * 32);
+    store_field(roots + i * 32, acc);
+    if (i < n) {
+        size_t r = scale ? (size_t)(__brevll((unsigned long long)i) >> (64 - scale)) : 0;
+        store_field(brp + r * 32, acc);
+    }
+}
+
+FFTSettingsDev::FFTSettingsDev(int scale, cudaStream_t st) : scale_(scale) {
+    if (scale < 0 || scale >= 32) throw CudaError(1, "Scale is expected to be within root of unity matrix row size");
+    max_width_ = (size_t)1 << scale;
+    roots_ = dev_alloc<uint8_t>((max_width_ + 1) * 32 + 33 * 32 + 32 * 32 + 32);
+    brp_roots_ = dev_alloc<uint8_t>(max_width_ * 32);
+    // (r - 1) >> scale as 8 little-endian words (plain integer shifting, no field arithmetic on the host)
+    uint32_t e[8] = {0x00000000u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    for (int s = 0; s < scale; s++)
+        for (int i = 0; i < 8; i++) e[i] = (e[i] >> 1) | (i < 7 ? e[i + 1] << 31 : 0);
+    uint8_t* tail = (uint8_t*)roots_ + (max_width_ + 1) * 32;  // [pw 33 Fr][inv_n 32 Fr][exp 32 B]
+    uint8_t* pw = tail;
+    uint8_t* inv_n = tail + 33 * 32;
+    uint32_t* exp_dev = (uint32_t*)(inv_n + 32 * 32);
+    B200_CUDA_CHECK(cudaMemcpyAsync(exp_dev, e, 32, cudaMemcpyHostToDevice, st));
+    k_root_powers<<<1, 32, 0, st>>>(exp_dev, pw, scale, inv_n);
+    k_roots_table<<<div_up(max_width_ + 1, 128), 128, 0, st>>>(pw, (uint8_t*)roots_, (uint8_t*)brp_roots_, max_width_, scale);
+    B200_LAUNCH_CHECK();
+    B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 32));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+FFTSettingsDev::~FFTSettingsDev() {
+    cudaFree(roots_);
+    cudaFree(brp_roots_);
+    cudaFree(scratch_);
+    cudaFree(scratch2_);
+}
+
+void FFTSettingsDev::ensure_scratch(size_t elems) {
+    if (elems <= scratch_elems_) return;
+    cudaFree(scratch_);
+    cudaFree(scratch2_);
+    scratch_ = dev_alloc<uint8_t>(elems * 32);
+    scratch2_ = dev_alloc<uint8_t>(elems * 32);
+    scratch_elems_ = elems;
+}
+
+static void launch_pass(const NttPass& p, int batch, cudaStream_t st) {
+    int m = 1 << p.log_m;
+    unsigned blocks = div_up(p.ncols, (size_t)p.G);
+    k_ntt_pass<<<dim3(blocks, (unsigned)batch), kNttThreads, (size_t)p.G * m * 32, st>>>(p);
+    B200_LAUNCH_CHECK();
+}
+
+void FFTSettingsDev::run_passes(const void* in, void* out, size_t n, bool inverse, int batch, bool scale,
+                                size_t twist_unit, cudaStream_t st) {
+    int k = 0;
+    while (((size_t)1 << k) < n) k++;
+    const uint8_t* inv_n = (const uint8_t*)roots_ + (max_width_ + 1) * 32 + 33 * 32;
+    NttPass p{};
+    p.roots = (const uint8_t*)roots_;
+    p.nmax = max_width_;
+    p.inverse = inverse;
+    p.batch_stride = n;
+    if (k <= kMaxLogM) {
+        p.in = (const uint8_t*)in; p.out = (uint8_t*)out;
+        p.log_m = k; p.G = 1; p.ncols = 1;
+        p.in_cstride = 0; p.in_rstride = 1; p.out_cstride = 0; p.out_rstride = 1;
+        p.in_col_fast = 0; p.out_col_fast = 0;
+        p.unit_m = max_width_ >> k;
+        p.tw_unit = 0; p.twist_unit = twist_unit;
+        p.scale = scale ? inv_n + k * 32 : nullptr;
+        launch_pass(p, batch, st);
+        launches_ += 1;
+        return;
+    }
+    if (k > 2 * kMaxLogM) throw CudaError(1, "fft_fr: sizes above 2^22 are not supported by this build");
+    int k2 = (k + 1) / 2, k1 = k - k2;  // n2 = 2^k2 (pass 1, strided columns), n1 = 2^k1 (pass 2, contiguous rows)
+    size_t n1 = (size_t)1 << k1, n2 = (size_t)1 << k2;
+    ensure_scratch((size_t)batch * n);
+    // pass 1: for every column j1 < n1, transform the n2 points x[j1 + n1*j2]; times w_n^(i2*j1); in-place layout
+    p.in = (const uint8_t*)in; p.out = (uint8_t*)scratch_;
+    p.log_m = k2; p.G = std::max(1, kTileElems >> k2); p.ncols = n1;
+    p.in_cstride = 1; p.in_rstride = n1; p.out_cstride = 1; p.out_rstride = n1;
+    p.in_col_fast = 1; p.out_col_fast = 1;
+    p.unit_m = max_width_ >> k2;
+    p.tw_unit = max_width_ >> k; p.twist_unit = twist_unit;
+    p.scale = nullptr;
+    launch_pass(p, batch, st);
+    // pass 2: for every i2 < n2, transform the n1 contiguous points y[n1*i2 + j1]; X[i2 + n2*i1]
+    p.in = (const uint8_t*)scratch_; p.out = (uint8_t*)out;
+    p.log_m = k1; p.G = std::max(1, kTileElems >> k1); p.ncols = n2;
+    p.in_cstride = n1; p.in_rstride = 1; p.out_cstride = 1; p.out_rstride = n2;
+    p.in_col_fast = 0; p.out_col_fast = 1;
+    p.unit_m = max_width_ >> k1;
+    p.tw_unit = 0; p.twist_unit = 0;
+    p.scale = scale ? inv_n + k * 32 : nullptr;
+    launch_pass(p, batch, st);
+    launches_ += 2;
+}
+
+void FFTSettingsDev::fft_fr(const void* in_dev, void* out_dev, size_t n, bool inverse, int batch, cudaStream_t st) {
+    // argument checks of fft_fr_output (blst/src/fft_fr.rs:118-133)
+    if (n > max_width_) throw CudaError(1, "Supplied list is longer than the available max width");
+    if (n == 0 || (n & (n - 1))) throw CudaError(1, "A list with power-of-two length expected");
+    launches_ = 0;
+    run_passes(in_dev, out_dev, n, inverse, batch, inverse, 0, st);
+}
+
+void FFTSettingsDev::das_fft_extension(const void* evens_dev, void* odds_dev, size_t n, int batch, cudaStream_t st) {
+    // argument checks of das_fft_extension (blst/src/data_availability_sampling.rs:79-87)
+    if (n == 0) throw CudaError(1, "A non-zero list ab expected");
+    if (n & (n - 1)) throw CudaError(1, "A list with power-of-two length expected");
+    if (n * 2 > max_width_) throw CudaError(1, "Supplied list is longer than the available max width");
+    launches_ = 0;
+    // odds = NTT_n( INTT_n(evens) .* w_2n^j ): the unique degree < n extension evaluated on the odd coset
+    ensure_scratch((size_t)batch * n);
+    void* coeffs = scratch2_;
+    run_passes(evens_dev, coeffs, n, true, batch, true, 0, st);
+    run_passes(coeffs, odds_dev, n, false, batch, false, max_width_ / (2 * n), st);
+}
+
+}  // namespace b200

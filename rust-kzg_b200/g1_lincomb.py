@@ -1,0 +1,103 @@
+"""Host-side mirror of the reference's MSM operator surface over the C ABI.
+
+  PreparedMsm            <-> rust_kzg_blst_sppark::prepare_multi_scalar_mult / multi_scalar_mult_prepared
+                             (blst-sppark/src/lib.rs:8-38), the handle kept in SpparkPrecomputation
+                             (kzg/src/msm/sppark.rs:5-22)
+  g1_lincomb             <-> G1LinComb::g1_lincomb(points, scalars, len, precomputation) (kzg/src/lib.rs:142-159)
+                             via blst::kzg_proofs::g1_linear_combination (blst/src/kzg_proofs.rs:25-72)
+Arrays are numpy uint64 in blst layouts: scalars (n,4) Montgomery Fr, affine points (n,12), Jacobian (n,18).
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+__all__ = ["PreparedMsm", "g1_lincomb", "mult_pippenger", "microbench_int"]
+
+
+def _L():
+    from . import lib
+    return lib()
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a, width):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, width)
+    return a
+
+
+class PreparedMsm:
+    """Fixed-base MSM context resident on the GPU (prepare_msm)."""
+
+    def __init__(self, affine_points):
+        pts = _u64(affine_points, 12)
+        self.npoints = pts.shape[0]
+        self.h = _L().prepare_msm(_p(pts), self.npoints)
+        if not self.h:
+            raise _lib.B200Error("prepare_msm failed (no CUDA device or out of memory); no CPU fallback")
+
+    def info(self):
+        c, w, l = C.c_int(), C.c_int(), C.c_int()
+        tb = C.c_size_t()
+        _L().b200_msm_info(self.h, C.byref(c), C.byref(w), C.byref(tb), C.byref(l))
+        return {"c": c.value, "W": w.value, "table_bytes": tb.value, "launches": l.value}
+
+    def mult(self, scalars):
+        """multi_scalar_mult_prepared: -> Jacobian point (18 u64)."""
+        sc = _u64(scalars, 4)
+        out = np.zeros(18, np.uint64)
+        _lib.check(_L().mult_pippenger_prepared(self.h, _p(out), sc.shape[0], _p(sc)))
+        return out
+
+    def mult_batch(self, scalars, batch):
+        sc = _u64(scalars, 4)
+        n = sc.shape[0] // batch
+        out = np.zeros((batch, 18), np.uint64)
+        _lib.check(_L().b200_msm_prepared_batch(self.h, _p(out), n, _p(sc), batch))
+        return out
+
+    def mult_device(self, out_ptr, npoints, scalars_ptr, batch=1, stream=0):
+        """Device-pointer variant (asynchronous on `stream`)."""
+        _lib.check(_L().b200_msm_prepared_device(self.h, C.c_void_p(out_ptr), npoints, C.c_void_p(scalars_ptr), batch,
+                                                 C.c_void_p(stream)))
+
+    def close(self):
+        if self.h:
+            _L().b200_free_msm(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def mult_pippenger(affine_points, scalars):
+    """multi_scalar_mult (blst-sppark/src/lib.rs:40-62): variable-base, bases travel with the call."""
+    pts, sc = _u64(affine_points, 12), _u64(scalars, 4)
+    if pts.shape[0] != sc.shape[0]:
+        raise ValueError("length mismatch")
+    out = np.zeros(18, np.uint64)
+    _lib.check(_L().mult_pippenger(_p(out), _p(pts), pts.shape[0], _p(sc)))
+    return out
+
+
+def g1_lincomb(affine_points, scalars, length=None, precomputation: PreparedMsm = None):
+    """G1LinComb::g1_lincomb.  Unlike the reference's sppark branch (blst/src/kzg_proofs.rs:37-45) small lengths
+    (< 8) also run on the device -- same group element."""
+    sc = _u64(scalars, 4)
+    if length is None:
+        length = sc.shape[0]
+    if precomputation is not None:
+        return precomputation.mult(sc[:length])
+    return mult_pippenger(_u64(affine_points, 12)[:length], sc[:length])
+
+
+def microbench_int():
+    a, b = C.c_double(), C.c_double()
+    _lib.check(_L().b200_microbench_int(C.byref(a), C.byref(b)))
+    return {"imad_per_s": a.value, "fpmul_per_s": b.value}

@@ -1,0 +1,39 @@
+"""Small target for ncu launch lists: a few invocations of one hot-path call (not a bench)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rust_kzg_b200 as B
+from oracle import c_oracle as K
+
+what, logn, reps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 2
+rng = np.random.default_rng(1)
+n = 1 << logn
+
+
+def rand_fr(n):
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64(0x3FFFFFFFFFFFFFFF)
+    return a
+
+
+if what == "msm":
+    text = open(os.path.join(os.path.dirname(B.LIB_PATH), "data", "trusted_setup.txt")).read()
+    L = K.p1s_to_affine(K.KZGSettings(text).g1_lagrange_brp)
+    pts = np.tile(L, (max(1, n // 4096), 1))[:n]
+    h = B.PreparedMsm(pts)
+    d_sc = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+    d_out = torch.zeros(18, dtype=torch.int64, device="cuda")
+    for _ in range(reps):
+        h.mult_device(d_out.data_ptr(), n, d_sc.data_ptr(), 1, 0)
+    torch.cuda.synchronize()
+elif what == "ntt":
+    fs = B.FFTSettings(max(logn, 1))
+    d_in = torch.from_numpy(rand_fr(n).view(np.int64)).cuda()
+    d_out = torch.zeros_like(d_in)
+    for _ in range(reps):
+        fs.fft_fr_device(d_out.data_ptr(), d_in.data_ptr(), n, False, 1, 0)
+    torch.cuda.synchronize()

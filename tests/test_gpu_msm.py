@@ -1,0 +1,146 @@
+"""MSM through the C ABI (prepare_msm / mult_pippenger_prepared / mult_pippenger) vs the CPU oracle.
+Parity is on the 48-byte compressed encoding, the reference's own definition (fuzz/src/lib.rs:81-95)."""
+import numpy as np
+import pytest
+
+from conftest import R_MOD, rand_fr_mont, rand_ints
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def prepared(B, lagrange_affine):
+    h = B.PreparedMsm(lagrange_affine)
+    yield h
+    h.close()
+
+
+def _same(K, got, exp):
+    assert K.p1_compress(got) == K.p1_compress(exp)
+
+
+@pytest.mark.parametrize("n", [4096, 4095, 1000, 129, 64, 33, 8, 7, 2, 1])
+def test_prepared_matches_oracle(B, K, prepared, lagrange_affine, n):
+    rng = np.random.default_rng(n)
+    sc = K.fr_from_ints(rand_ints(rng, n, R_MOD))
+    got = prepared.mult(sc)
+    exp = K.msm_affine(lagrange_affine[:n], sc)
+    _same(K, got, exp)
+
+
+def test_variable_base_matches_oracle(B, K, lagrange_affine):
+    rng = np.random.default_rng(5)
+    for n in (4096, 300, 31, 8, 3, 1):
+        sc = K.fr_from_ints(rand_ints(rng, n, R_MOD))
+        got = B.mult_pippenger(lagrange_affine[:n], sc)
+        _same(K, got, K.msm_affine(lagrange_affine[:n], sc))
+
+
+def test_edge_scalars(B, K, prepared, lagrange_affine):
+    """all-zero, all-one, r-1, small scalars, 10% zeros (kzg-bench/src/tests/bls12_381.rs:282-296)"""
+    n = 4096
+    rng = np.random.default_rng(9)
+    cases = {
+        "zeros": [0] * n,
+        "ones": [1] * n,
+        "r-1": [R_MOD - 1] * n,
+        "small": [int(x) for x in rng.integers(0, 1 << 16, n)],
+        "same": [0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % R_MOD] * n,
+        "window-edges": [(1 << (16 * (i % 16))) * 0x8000 % R_MOD for i in range(n)],
+    }
+    sparse = rand_ints(rng, n, R_MOD)
+    for i in range(n):
+        if rng.random() < 0.1:
+            sparse[i] = 0
+    cases["10pct-zero"] = sparse
+    for name, ints in cases.items():
+        sc = K.fr_from_ints(ints)
+        exp = K.msm_affine(lagrange_affine, sc)
+        assert K.p1_compress(prepared.mult(sc)) == K.p1_compress(exp), name
+        assert K.p1_compress(B.mult_pippenger(lagrange_affine, sc)) == K.p1_compress(exp), name + "/variable"
+
+
+def test_infinity_and_repeated_points(B, K, lagrange_affine):
+    """10% points at infinity; repeated points; P and -P in one call (SURVEY.md section 7 hard parts)"""
+    n = 2048
+    rng = np.random.default_rng(21)
+    pts = lagrange_affine[:n].copy()
+    for i in range(n):
+        if rng.random() < 0.1:
+            pts[i] = 0                      # infinity = all-zero affine
+    pts[100:200] = pts[300]                 # repeats
+    negp = pts[301].copy()
+    negp[6:12] = K.fp_sub(np.zeros((1, 6), np.uint64), negp[6:12].reshape(1, 6))[0]
+    pts[400:450] = negp
+    pts[450:500] = pts[301]
+    sc_i = rand_ints(rng, n, R_MOD)
+    for i in range(400, 500):
+        sc_i[i] = sc_i[400]                 # P and -P with equal scalars land in the same bucket and cancel
+    sc = K.fr_from_ints(sc_i)
+    exp = K.msm_affine(pts, sc)
+    _same(K, B.mult_pippenger(pts, sc), exp)
+    h = B.PreparedMsm(pts)
+    _same(K, h.mult(sc), exp)
+    h.close()
+
+
+def test_generator_sum_closed_form(B, K):
+    """sum (i+1)*G, i < 255 == (255*256/2)*G (kzg-bench/src/tests/bls12_381.rs:184-221)"""
+    import os
+    from conftest import GOLDEN
+    dat = open(os.path.join(GOLDEN, "g1_compressed_valid_test_vectors.dat"), "rb").read()
+    G = K.p1_uncompress(dat[48:96])
+    n = 255
+    pts = K.p1s_to_affine(np.tile(G, (n, 1)))
+    sc = K.fr_from_ints(range(1, n + 1))
+    exp = K.p1_mult(G, K.fr_from_ints([n * (n + 1) // 2])[0])
+    _same(K, B.mult_pippenger(pts, sc), exp)
+    h = B.PreparedMsm(pts)
+    _same(K, h.mult(sc), exp)
+    h.close()
+
+
+def test_prefix_lengths_reuse_table(B, K, prepared, lagrange_affine):
+    """every prefix length 0..128 with one prepared table (kzg-bench/src/tests/bls12_381.rs:298-387)"""
+    rng = np.random.default_rng(3)
+    sc = K.fr_from_ints(rand_ints(rng, 128, R_MOD))
+    for n in list(range(0, 20)) + [31, 32, 33, 63, 64, 65, 127, 128]:
+        if n == 0:
+            got = np.zeros(18, np.uint64)
+            from rust_kzg_b200 import _lib
+            import ctypes as C
+            _lib.check(B.lib().mult_pippenger_prepared(prepared.h, got.ctypes.data_as(C.c_void_p), 0, None))
+            assert K.p1_is_inf(got)
+            continue
+        _same(K, prepared.mult(sc[:n]), K.msm_affine(lagrange_affine[:n], sc[:n]))
+
+
+def test_batch_matches_single(B, K, lagrange_affine):
+    import os
+    os.environ["B200_MSM_MAX_BATCH"] = "8"
+    try:
+        h = B.PreparedMsm(lagrange_affine)
+    finally:
+        del os.environ["B200_MSM_MAX_BATCH"]
+    rng = np.random.default_rng(17)
+    sc = rand_fr_mont(rng, 8 * 4096)
+    outs = h.mult_batch(sc, 8)
+    for b in range(8):
+        _same(K, outs[b], K.msm_affine(lagrange_affine, sc[b * 4096:(b + 1) * 4096], nthreads=8))
+    h.close()
+
+
+def test_large_tiled_bases_folded_oracle(B, K, lagrange_affine):
+    """2^16 terms over tiled bases P_i = L[i mod 4096]: exact cheap oracle by folding scalars."""
+    n = 1 << 16
+    rng = np.random.default_rng(31)
+    sc = rand_fr_mont(rng, n)
+    pts = np.tile(lagrange_affine, (n // 4096, 1))
+    folded = sc[:4096].copy()
+    for k in range(1, n // 4096):
+        folded = K.fr_add(folded, sc[k * 4096:(k + 1) * 4096])
+    exp = K.msm_affine(lagrange_affine, folded, nthreads=8)
+    h = B.PreparedMsm(pts)
+    _same(K, h.mult(sc), exp)
+    h.close()
+    _same(K, B.mult_pippenger(pts, sc), exp)

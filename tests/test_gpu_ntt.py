@@ -1,0 +1,106 @@
+"""Fr NTT / DAS extension through the C ABI vs the oracle and the reference's KATs (bit-exact Montgomery limbs)."""
+import numpy as np
+import pytest
+
+from conftest import R_MOD, rand_fr_mont, rand_ints
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fs20(B):
+    s = B.FFTSettings(20)
+    yield s
+    s.close()
+
+
+def test_roots_tables_match_oracle(B, K):
+    for scale in (0, 1, 4, 13):
+        d, o = B.FFTSettings(scale), K.FFTSettings(scale)
+        assert np.array_equal(d.get_roots_of_unity(), o.roots_of_unity)
+        assert np.array_equal(d.get_brp_roots_of_unity(), o.brp_roots_of_unity)
+        assert np.array_equal(d.get_reversed_roots_of_unity(), o.reverse_roots_of_unity)
+        d.close()
+
+
+def test_inverse_fft_kat(B, K, kats):
+    """kzg-bench/src/tests/fft_fr.rs:49-84"""
+    fs = B.FFTSettings(4)
+    out = fs.fft_fr(K.fr_from_ints(range(16)), True)
+    got = [[int(x) for x in K.fr_to_ints([row])[0:1]] for row in out]
+    exp = [sum(v << (64 * i) for i, v in enumerate(row)) for row in kats["inv_fft_expected"]]
+    assert [g[0] for g in got] == exp
+    fs.close()
+
+
+def test_das_extension_kat(B, K, kats):
+    """kzg-bench/src/tests/das.rs:4-31"""
+    fs = B.FFTSettings(4)
+    odds = fs.das_fft_extension(K.fr_from_ints(range(8)))
+    exp = [sum(v << (64 * i) for i, v in enumerate(row)) for row in kats["das_expected_u"]]
+    assert K.fr_to_ints(odds) == exp
+    fs.close()
+
+
+@pytest.mark.parametrize("logn", [0, 1, 2, 3, 5, 8, 10, 11, 12, 13, 15, 16, 17, 20])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_fft_matches_oracle(B, K, fs20, logn, inverse):
+    n = 1 << logn
+    rng = np.random.default_rng(100 + logn)
+    data = rand_fr_mont(rng, n)
+    ofs = K.FFTSettings(20)
+    exp = ofs.fft_fr(data, inverse, nthreads=8)
+    got = fs20.fft_fr(data, inverse)
+    assert np.array_equal(got, exp)
+
+
+def test_fft_slow_dft_and_roundtrip(B, K):
+    """fft_fr vs the O(n^2) DFT at 2^12 and forward/inverse roundtrip (kzg-bench/src/tests/fft_fr.rs:5-46)"""
+    fs = B.FFTSettings(12)
+    ofs = K.FFTSettings(12)
+    data = K.fr_from_ints(range(4096))
+    fwd = fs.fft_fr(data, False)
+    assert np.array_equal(fwd, ofs.fft_fr_slow(data, False))
+    assert np.array_equal(fs.fft_fr(fwd, True), data)
+    fs.close()
+
+
+def test_stride_invariance(B, K):
+    """kzg-bench/src/tests/fft_fr.rs:87-106"""
+    a, b = B.FFTSettings(9), B.FFTSettings(12)
+    data = K.fr_from_ints(range(512))
+    assert np.array_equal(a.fft_fr(data), b.fft_fr(data))
+    a.close()
+    b.close()
+
+
+def test_bad_lengths_error(B, K, fs20):
+    from rust_kzg_b200 import B200Error
+    fs = B.FFTSettings(4)
+    with pytest.raises(B200Error, match="longer than the available max width"):
+        fs.fft_fr(K.fr_from_ints(range(32)))
+    with pytest.raises(B200Error, match="power-of-two"):
+        fs.fft_fr(K.fr_from_ints(range(12)))
+    with pytest.raises(B200Error, match="longer than the available max width"):
+        fs.das_fft_extension(K.fr_from_ints(range(16)))
+    with pytest.raises(B200Error, match="power-of-two"):
+        fs.das_fft_extension(K.fr_from_ints(range(3)))
+    fs.close()
+    assert B.lib().b200_fft_settings_new(32) is None
+
+
+@pytest.mark.parametrize("scale", list(range(1, 16)) + [20])
+def test_das_extension_random(B, K, fs20, scale):
+    """odds from evens: matches the oracle's recursion, and the upper half of the IFFT of the interleaved vector is
+    zero (kzg-bench/src/tests/das.rs:35-68)"""
+    width = 1 << scale
+    rng = np.random.default_rng(scale)
+    evens = rand_fr_mont(rng, width // 2)
+    odds = fs20.das_fft_extension(evens)
+    if scale <= 16:
+        assert np.array_equal(odds, K.FFTSettings(20).das_fft_extension(evens))
+    data = np.empty((width, 4), np.uint64)
+    data[0::2] = evens
+    data[1::2] = odds
+    coeffs = fs20.fft_fr(data, True)
+    assert not coeffs[width // 2:].any()
