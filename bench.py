@@ -1,0 +1,402 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the rust-kzg hot path on B200 (contract in the task statement).
+
+A "step" is one pass of the hot path over one batch of synthetic input.  Workload at every N (weak scaling):
+BASELINE.json configs[1], an MSM of 2^20 uniformly random Fr scalars x trusted-setup G1 points per GPU, bit-exact
+vs the CPU oracle.  For N > 1 the 2^20*N terms are sharded by rank: every rank runs its local MSM,
+the 144-byte partial results are all-gathered over NCCL and summed locally (NCCL cannot add curve points).
+
+Unit: "G1-adds/s" = canonical bucket additions per second = 16 per term (canonical c = 16 ->
+16 mixed additions per term), so both arms (this one and --impl reference) are counted identically.  points/s =
+value / 16.  `value` has scalars resident in HBM; `e2e` goes through the reference-facing C ABI call
+mult_pippenger_prepared with pinned HOST scalars (H2D + D2H inside the timed region).
+
+Extra keys report the other BASELINE metric (blobs/s for blob_to_kzg_commitment / compute_blob_kzg_proof, batch 64)
+and the Fr NTT at 2^20.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_N = int(os.environ.get("B200_BENCH_LOGN", "20"))
+ADDS_PER_TERM = 16          # canonical c = 16
+BYTES_PER_TERM = 128        # 32 B scalar + 96 B affine point
+IMAD_PER_ADD = 10 * 300     # mixed add = 8M + 2S ~ 10 Fp mul; Fp mul = 144 + 144 + 12 32x32 multiply-adds
+SEED = 0x4B5A47
+METRIC = "MSM G1-adds/sec at 2^20 (per GPU, weak scaling); blobs/sec blob_to_kzg_commitment in extra"
+
+
+def rand_fr(rng, n):
+    """uniform-looking Montgomery Fr limbs below 2^254 < r (numpy PCG64, seed SEED)"""
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64(0x3FFFFFFFFFFFFFFF)
+    return a
+
+
+def rand_blobs(rng, n):
+    b = rng.integers(0, 256, size=(n, 4096, 32), dtype=np.uint8)
+    b[:, :, 0] = 0   # canonical field elements (kzg-bench/src/tests/eip_4844.rs:28-37)
+    return b.reshape(n, 131072)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def load_bases():
+    """affine Lagrange bases of the EIP-4844 trusted setup, bit-reversed, via the oracle's parser (host, one-time)"""
+    from oracle import c_oracle as K
+    text = open(os.path.join(ROOT, "rust-kzg_b200", "data", "trusted_setup.txt")).read()
+    s = K.KZGSettings(text, nthreads=os.cpu_count() or 1)
+    return K, s, K.p1s_to_affine(s.g1_lagrange_brp)
+
+
+def folded_expectation(K, L, sc, nthreads):
+    """exact oracle for tiled bases P_i = L[i mod 4096]: fold the scalars, then a 4096-term CPU MSM"""
+    folded = sc[:4096].copy()
+    for k in range(1, sc.shape[0] // 4096):
+        folded = K.fr_add(folded, sc[k * 4096:(k + 1) * 4096])
+    return K.msm_affine(L, folded, nthreads=nthreads)
+
+
+def cpu_baseline(K, L, n_terms, nthreads, steps=1, warmup=0):
+    """the oracle's restatement of tiling_parallel_pippenger on the host cores over the first n_terms terms"""
+    rng = np.random.default_rng(SEED)
+    sc = rand_fr(rng, n_terms)
+    pts = np.tile(L, (max(1, n_terms // 4096), 1))[:n_terms]
+    for _ in range(warmup):
+        K.msm_affine(pts, sc, nthreads=nthreads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        K.msm_affine(pts, sc, nthreads=nthreads)
+    dt = (time.perf_counter() - t0) / steps
+    return n_terms * ADDS_PER_TERM / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Rust reference cannot be built here) on all
+    host threads, a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, s, L = load_bases()
+    cores = os.cpu_count() or 1
+    # size the sample so that (steps + warmup) passes end within a few minutes: ~24 us of CPU per term per core
+    budget_s = 90.0
+    per_term = 30e-6 / cores
+    n = 1 << 18
+    while n > (1 << 12) and n * per_term * (args.steps + args.warmup) > budget_s:
+        n >>= 1
+    value, dt = cpu_baseline(K, L, n, cores, steps=args.steps, warmup=args.warmup)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "G1-adds/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "MSM over the first 2^%d of 2^%d random Fr scalars x tiled EIP-4844 trusted-setup G1 points, "
+                               "CPU, all host threads" % (n.bit_length() - 1, LOG_N), "seed": SEED},
+        "cpu_baseline": {"value": value, "unit": "G1-adds/s", "cores": cores, "kind": "port",
+                         "sample": "first 2^%d terms of the 2^%d-term MSM, tiling_parallel_pippenger restatement "
+                                   "(oracle/kzg_oracle.c), not blst assembly" % (n.bit_length() - 1, LOG_N)},
+        "e2e": {"value": value, "unit": "G1-adds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-extra", action="store_true", help="skip the blob / NTT extra metrics")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import rust_kzg_b200 as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or B.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = 1 << LOG_N
+    K, osettings, L = load_bases()
+
+    # ---- inputs: rank r owns terms [r*n, (r+1)*n) of the N*n-term MSM; bases tile the 4096 setup points ----------
+    rng = np.random.default_rng(SEED + rank)
+    sc = rand_fr(rng, n)
+    pts = np.tile(L, (n // 4096, 1)) if n >= 4096 else L[:n]
+    msm = B.PreparedMsm(pts)
+    info = msm.info()
+    h_sc = torch.from_numpy(sc.view(np.int64)).pin_memory()
+    d_sc = h_sc.cuda(non_blocking=True)
+    d_out = torch.zeros(18, dtype=torch.int64, device="cuda")
+    d_all = torch.zeros((world, 18), dtype=torch.int64, device="cuda")
+    d_total = torch.zeros(18, dtype=torch.int64, device="cuda")
+    stream = 0  # the library launches on the legacy default stream = torch's current stream, so torch events see it
+
+    def step():
+        msm.mult_device(d_out.data_ptr(), n, d_sc.data_ptr(), 1, stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_out)
+            B.g1_sum_device(d_total.data_ptr(), d_all.data_ptr(), world, stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    # parity of the thing being timed: local result vs the folded-scalar oracle
+    exp = folded_expectation(K, L, sc, os.cpu_count() or 1)
+    if K.p1_compress(d_out.cpu().numpy().view(np.uint64)) != K.p1_compress(exp):
+        raise SystemExit("bench.py: MSM result differs from the oracle -- refusing to report a number")
+
+    msm.set_profiling(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    acc_ms_sum, acc_runs = msm.profile_read()
+    msm.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * n * ADDS_PER_TERM / (ms_step * 1e-3)
+
+    # ---- e2e: the reference-facing call with host scalars (pinned), H2D + D2H inside the timed region -----------
+    h_np = h_sc.numpy().view(np.uint64).reshape(n, 4)
+    for _ in range(2):
+        msm.mult(h_np)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        res = msm.mult(h_np)
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    if K.p1_compress(res) != K.p1_compress(exp):
+        raise SystemExit("bench.py: e2e MSM result differs from the oracle")
+    e2e_value = world * n * ADDS_PER_TERM / t_e2e
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_accumulate), measured live with CUDA events on its stream -----------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    acc_ms = acc_ms_sum / max(acc_runs, 1)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "accumulate_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    achieved_gbs = BYTES_PER_TERM * n / (acc_ms * 1e-3) / 1e9 if acc_ms else None
+    mb = B.microbench_int()
+    adds_per_launch = n * info["W"]
+    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak if achieved_gbs else None, "traffic": traffic,
+                "kernel": "k_accumulate", "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_step if acc_ms else None,
+                "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback",
+                "note": "the path is bound by the integer multiply pipe, not HBM (SURVEY.md 8d); see int_roofline"}
+    int_roofline = {"bound": "int32 multiply pipe (IMAD.WIDE)", "unit": "T multiply-adds/s",
+                    "achieved": adds_per_launch * IMAD_PER_ADD / (acc_ms * 1e-3) / 1e12 if acc_ms else None,
+                    "peak": mb["imad_per_s"] / 1e12, "peak_source": "b200_microbench_int, measured in this run",
+                    "fp_mul_per_s_measured": mb["fpmul_per_s"],
+                    "note": "carry-chained IMAD.WIDE.X issues at half the plain IMAD.WIDE rate on sm_100a (measured), "
+                            "so 0.5 is the ceiling of a 32-bit-limb carry-chain multiplier"}
+    if int_roofline["achieved"]:
+        int_roofline["frac"] = int_roofline["achieved"] / int_roofline["peak"]
+
+    # ---- CPU baseline beside it: oracle port on the host cores, bounded sample ------------------------------------
+    cores = os.cpu_count() or 1
+    n_cpu = 1 << min(LOG_N, 18)
+    cpu_value, cpu_dt = cpu_baseline(K, L, n_cpu, cores)
+    cpu = {"value": cpu_value, "unit": "G1-adds/s", "cores": cores, "kind": "port",
+           "sample": "first 2^%d terms of the 2^%d-term MSM, %.2f s on %d threads; C restatement of "
+                     "tiling_parallel_pippenger (oracle/kzg_oracle.c), not blst assembly" % (n_cpu.bit_length() - 1, LOG_N, cpu_dt, cores)}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "G1-adds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": "MSM 2^%d random Fr scalars x EIP-4844 trusted-setup G1 points (4096 Lagrange points tiled), "
+                               "per GPU; prepared fixed-base table resident in HBM" % LOG_N,
+                   "points_per_s": value / ADDS_PER_TERM, "window_bits": info["c"], "windows": info["W"],
+                   "table_bytes": info["table_bytes"], "seed": SEED, "prng": "numpy PCG64",
+                   "l2": "inputs larger than L2: 32 MiB scalars + %.1f GiB table per step" % (info["table_bytes"] / 2 ** 30),
+                   "parity": "compressed result == folded-scalar oracle (checked before timing)",
+                   "multi_gpu": "terms sharded by rank, NCCL all-gather of 144 B partial results + local add" if world > 1 else "single GPU"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "G1-adds/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 144,
+                "ms_per_step": t_e2e * 1e3, "api": "mult_pippenger_prepared (C ABI), pinned host scalars"},
+        "gpu_launches": (info["launches"] + (1 if world > 1 else 0)) * args.steps,
+        "roofline": roofline, "int_roofline": int_roofline, "cpu_baseline": cpu,
+    }
+    if not args.no_extra and world == 1:
+        try:
+            out["extra"] = extra_metrics(B, K, osettings, torch)
+        except Exception as e:  # extras must not take the headline down
+            out["extra"] = {"error": repr(e)}
+    if world > 1:
+        dist.destroy_process_group()
+    print(json.dumps(out))
+
+
+def extra_metrics(B, K, osettings, torch):
+    """the other half of BASELINE's metric: blobs/s (batch 64, BASELINE config 3) and the Fr NTT (config 4)"""
+    ex = {}
+    rng = np.random.default_rng(SEED)
+    nb = 64
+    blobs = rand_blobs(rng, nb)
+    ts = B.KZGSettings.load_trusted_setup_file()
+    h_blobs = torch.from_numpy(blobs).pin_memory()
+    d_blobs = h_blobs.cuda()
+    d_out = torch.zeros((nb, 48), dtype=torch.uint8, device="cuda")
+    d_y = torch.zeros((nb, 32), dtype=torch.uint8, device="cuda")
+    d_status = torch.zeros(nb, dtype=torch.int32, device="cuda")
+
+    def timed(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms = timed(lambda: ts.blob_to_kzg_commitment_device(d_out.data_ptr(), d_blobs.data_ptr(), nb, d_status.data_ptr(), 0))
+    comm = d_out.cpu().numpy()
+    osettings.set_threads(os.cpu_count() or 1)
+    ok = all(comm[i].tobytes() == K.blob_to_kzg_commitment(blobs[i].tobytes(), osettings) for i in (0, 17, 63))
+    ex["blob_to_kzg_commitment"] = {"blobs_per_s": nb / (ms * 1e-3), "ms_per_batch": ms, "batch": nb, "parity_ok": bool(ok),
+                                    "launches_per_batch": ts.launches()}
+    # e2e through the C ABI with pinned host blobs
+    h_out = torch.zeros((nb, 48), dtype=torch.uint8).pin_memory()
+    t0 = time.perf_counter()
+    reps = 5
+    ts.blob_to_kzg_commitment_batch_ptr(h_out.data_ptr(), h_blobs.data_ptr(), nb)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ts.blob_to_kzg_commitment_batch_ptr(h_out.data_ptr(), h_blobs.data_ptr(), nb)
+    dt = (time.perf_counter() - t0) / reps
+    ex["blob_to_kzg_commitment"]["e2e_blobs_per_s"] = nb / dt
+    ex["blob_to_kzg_commitment"]["e2e_parity_ok"] = bool(np.array_equal(h_out.numpy(), comm))
+    # compute_kzg_proof on device-resident blobs (z given), compute_blob_kzg_proof end to end (incl. host SHA-256)
+    zs = rand_blobs(rng, 1)[0, :32 * nb].reshape(nb, 32).copy()
+    d_z = torch.from_numpy(zs).cuda()
+    ms = timed(lambda: ts.compute_kzg_proof_device(d_out.data_ptr(), d_y.data_ptr(), d_blobs.data_ptr(), d_z.data_ptr(), nb,
+                                                   d_status.data_ptr(), 0, 0))
+    p0, y0 = K.compute_kzg_proof(blobs[5].tobytes(), zs[5].tobytes(), osettings)
+    ex["compute_kzg_proof"] = {"blobs_per_s": nb / (ms * 1e-3), "ms_per_batch": ms, "batch": nb,
+                               "parity_ok": bool(d_out[5].cpu().numpy().tobytes() == p0 and d_y[5].cpu().numpy().tobytes() == y0)}
+    h_comm = torch.from_numpy(comm.copy()).pin_memory()
+    ts.compute_blob_kzg_proof_batch_ptr(h_out.data_ptr(), h_blobs.data_ptr(), h_comm.data_ptr(), nb)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ts.compute_blob_kzg_proof_batch_ptr(h_out.data_ptr(), h_blobs.data_ptr(), h_comm.data_ptr(), nb)
+    dt = (time.perf_counter() - t0) / reps
+    pb = K.compute_blob_kzg_proof(blobs[9].tobytes(), comm[9].tobytes(), osettings)
+    ex["compute_blob_kzg_proof"] = {"e2e_blobs_per_s": nb / dt, "ms_per_batch": dt * 1e3, "batch": nb,
+                                    "parity_ok": bool(h_out[9].numpy().tobytes() == pb)}
+    # CPU beside it: the oracle port, one blob per thread-parallel MSM
+    t0 = time.perf_counter()
+    for i in range(4):
+        K.blob_to_kzg_commitment(blobs[i].tobytes(), osettings)
+    ex["blob_to_kzg_commitment"]["cpu_port_blobs_per_s"] = 4 / (time.perf_counter() - t0)
+    ex["blob_to_kzg_commitment"]["cpu_cores"] = os.cpu_count()
+    ts.free()
+    # Fr NTT sweep (BASELINE config 4)
+    fs = B.FFTSettings(20)
+    ofs = K.FFTSettings(20)
+    ntt = {}
+    for logn in (12, 16, 20):
+        m = 1 << logn
+        data = rand_fr(rng, m)
+        d_in = torch.from_numpy(data.view(np.int64)).cuda()
+        d_o = torch.zeros_like(d_in)
+        ms = timed(lambda: fs.fft_fr_device(d_o.data_ptr(), d_in.data_ptr(), m, False, 1, 0))
+        rec = {"ms": ms, "elements_per_s": m / (ms * 1e-3), "butterflies_per_s": (m // 2) * logn / (ms * 1e-3),
+               "hbm_gbs_algorithmic": 64 * m * (2 if logn > 11 else 1) / (ms * 1e-3) / 1e9}
+        if logn <= 16:
+            rec["parity_ok"] = bool(np.array_equal(d_o.cpu().numpy().view(np.uint64).reshape(m, 4), ofs.fft_fr(data, False, nthreads=os.cpu_count() or 1)))
+        ntt["2^%d" % logn] = rec
+    ex["fft_fr"] = ntt
+    fs.close()
+    return ex
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,14 @@ B200_API RustError b200_msm_prepared_device(void *msm, void *out_dev, size_t npo
  * G1LinComb::g1_lincomb_batch (kzg/src/lib.rs:160-181). */
 B200_API RustError b200_msm_prepared_batch(void *msm, blst_p1 out[], size_t npoints, const blst_fr scalars[], int batch);
 
+/* measurement hooks: bracket the accumulate kernel of every run with CUDA events on the launching stream; read
+ * returns the summed duration (ms) and the number of runs since the last read */
+B200_API void b200_msm_set_profiling(void *msm, int on);
+B200_API RustError b200_msm_profile_read(void *msm, double *accumulate_ms_sum, int *runs);
+/* out_dev = sum of n Jacobian points (device pointers): the local combine after an all-gather of per-GPU partial
+ * MSM results (NCCL has no reduction over curve points) */
+B200_API RustError b200_g1_sum_device(void *out_dev, const void *points_dev, size_t n, void *stream);
+
 /* introspection (bench / tests): window bits, windows, table bytes, kernel launches of the last run */
 B200_API void b200_msm_info(void *msm, int *c, int *W, size_t *table_bytes, int *launches);
 
@@ -88,6 +96,62 @@ B200_API RustError b200_das_fft_extension(void *fs, blst_fr *odds, const blst_fr
 B200_API RustError b200_fft_fr_device(void *fs, void *out_dev, const void *in_dev, size_t n, int inverse, int batch, void *stream);
 B200_API RustError b200_das_fft_extension_device(void *fs, void *odds_dev, const void *evens_dev, size_t n, int batch, void *stream);
 B200_API int b200_fft_launches(void *fs);
+
+/* ============================================================================================================== */
+/* B2 -- c-kzg-4844 C ABI (pinned upstream 00ae727c, .github/workflows/backend-tests.yml:4), commitment / proof     */
+/* path only.  Replaces blst/src/eip_4844.rs:160-530 for the functions below; types from                            */
+/* kzg/src/eth/c_bindings.rs:16-113.  Verification / EIP-7594 entry points are not exported (out of the hot path). */
+/* ============================================================================================================== */
+typedef enum { C_KZG_OK = 0, C_KZG_BADARGS = 1, C_KZG_ERROR = 2, C_KZG_MALLOC = 3 } C_KZG_RET;  /* c_bindings.rs:16-23 */
+typedef struct { uint8_t bytes[32]; } Bytes32;
+typedef struct { uint8_t bytes[48]; } Bytes48;
+typedef struct { uint8_t bytes[131072]; } Blob;
+typedef Bytes48 KZGCommitment;
+typedef Bytes48 KZGProof;
+/* CKZGSettings (kzg/src/eth/c_bindings.rs:55-108).  All arrays are host memory owned by the library between
+ * load_trusted_setup* and free_trusted_setup; the device context is found through g1_values_lagrange_brp. */
+typedef struct {
+    blst_fr *roots_of_unity;          /* 8193 */
+    blst_fr *brp_roots_of_unity;      /* 8192 */
+    blst_fr *reverse_roots_of_unity;  /* 8193 */
+    blst_p1 *g1_values_monomial;      /* 4096 */
+    blst_p1 *g1_values_lagrange_brp;  /* 4096 */
+    blst_p2 *g2_values_monomial;      /* 65, allocated but NOT decoded by this backend (verification is out of scope) */
+    blst_p1 **x_ext_fft_columns;      /* NULL (FK20 data, out of scope) */
+    blst_p1_affine **tables;          /* NULL */
+    size_t wbits;
+    size_t scratch_size;
+} KZGSettings;
+typedef KZGSettings CKZGSettings;
+
+/* blst/src/eip_4844.rs:180-222.  Decompresses the points on the GPU, builds the fixed-base MSM table and the
+ * roots-of-unity tables, fills the host arrays.  BADARGS on wrong counts / undecodable points.  The reference's
+ * pairing sanity check for monomial-form ("old") setups (kzg/src/eip_4844.rs:1005-1020) is NOT performed. */
+B200_API C_KZG_RET load_trusted_setup(KZGSettings *out, const uint8_t *g1_monomial_bytes, uint64_t num_g1_monomial_bytes,
+                             const uint8_t *g1_lagrange_bytes, uint64_t num_g1_lagrange_bytes,
+                             const uint8_t *g2_monomial_bytes, uint64_t num_g2_monomial_bytes, uint64_t precompute);
+/* blst/src/eip_4844.rs:227-269 (text format of kzg/src/eip_4844.rs:151-228) */
+B200_API C_KZG_RET load_trusted_setup_file(KZGSettings *out, FILE *in);
+/* blst/src/eip_4844.rs:296-378: frees and NULLs every array, drops the device context; NULL-safe */
+B200_API void free_trusted_setup(KZGSettings *s);
+/* blst/src/eip_4844.rs:163-175 */
+B200_API C_KZG_RET blob_to_kzg_commitment(KZGCommitment *out, const Blob *blob, const KZGSettings *s);
+/* blst/src/eip_4844.rs:476-496 */
+B200_API C_KZG_RET compute_kzg_proof(KZGProof *proof_out, Bytes32 *y_out, const Blob *blob, const Bytes32 *z_bytes, const KZGSettings *s);
+/* blst/src/eip_4844.rs:274-291 */
+B200_API C_KZG_RET compute_blob_kzg_proof(KZGProof *out, const Blob *blob, const Bytes48 *commitment_bytes, const KZGSettings *s);
+
+/* Batched extensions: n independent blobs in one launch sequence (BASELINE config 3: 64 blobs).  Any invalid
+ * element makes the whole call return C_KZG_BADARGS.  n may exceed the context's batch capacity (chunked). */
+B200_API C_KZG_RET b200_blob_to_kzg_commitment_batch(KZGCommitment *out, const Blob *blobs, size_t n, const KZGSettings *s);
+B200_API C_KZG_RET b200_compute_kzg_proof_batch(KZGProof *proofs, Bytes32 *ys, const Blob *blobs, const Bytes32 *zs, size_t n, const KZGSettings *s);
+B200_API C_KZG_RET b200_compute_blob_kzg_proof_batch(KZGProof *out, const Blob *blobs, const Bytes48 *commitments, size_t n, const KZGSettings *s);
+/* Device-pointer extensions (asynchronous on stream; status_dev[i] != 0 marks an invalid blob / z; n <= capacity) */
+B200_API C_KZG_RET b200_blob_to_kzg_commitment_device(void *out48_dev, const void *blobs_dev, size_t n, int *status_dev, const KZGSettings *s, void *stream);
+B200_API C_KZG_RET b200_compute_kzg_proof_device(void *proofs48_dev, void *y32_dev, const void *blobs_dev, const void *z32_dev, size_t n, int z_reduce, int *status_dev, const KZGSettings *s, void *stream);
+B200_API int b200_kzg_launches(const KZGSettings *s);
+B200_API int b200_kzg_max_batch(const KZGSettings *s);
+B200_API void b200_selftest_sha256(uint8_t out[32], const uint8_t *msg, size_t len, int portable);
 
 /* ---- device self-test hooks: elementwise field / point kernels on host arrays, used by the parity tests ------- */
 /* op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 inverse(a), 5 to-Montgomery(a), 6 from-Montgomery(a) */

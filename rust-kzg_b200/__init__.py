@@ -24,3 +24,5 @@ def device_count() -> int:
 
 from .g1_lincomb import *  # noqa: E402,F401,F403
 from .fft import *  # noqa: E402,F401,F403
+from .eip4844 import *  # noqa: E402,F401,F403
+from . import eip4844  # noqa: E402

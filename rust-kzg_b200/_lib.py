@@ -47,6 +47,9 @@ def load():
         "b200_selftest_p1_compress": (RustError, [vp, vp, sz]),
         "b200_microbench_int": (RustError, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "b200_device_count": (ci, []),
+        "b200_msm_set_profiling": (None, [vp, ci]),
+        "b200_msm_profile_read": (RustError, [vp, C.POINTER(C.c_double), C.POINTER(ci)]),
+        "b200_g1_sum_device": (RustError, [vp, vp, sz, vp]),
         "b200_fft_settings_new": (vp, [ci]),
         "b200_fft_settings_free": (None, [vp]),
         "b200_fft_settings_max_width": (sz, [vp]),

@@ -1,0 +1,373 @@
+// capi_ckzg.cu -- the c-kzg-4844 C ABI for the commitment / proof path (include/b200_kzg.h, section B2), replacing
+// blst/src/eip_4844.rs:160-530 for: load_trusted_setup, load_trusted_setup_file, free_trusted_setup,
+// blob_to_kzg_commitment, compute_kzg_proof, compute_blob_kzg_proof, plus batched and device-pointer extensions.
+//
+// Like the reference, the settings struct the caller holds carries only host arrays; the device context hangs off a
+// side registry keyed by the g1_values_lagrange_brp pointer (the reference keys its PrecomputationTableManager the
+// same way, kzg/src/eip_4844.rs:105-145) -- but instead of rebuilding an FsKZGSettings on every call
+// (blst/src/types/kzg_settings.rs:314-437) the resident context is looked up.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200_kzg.h"
+#include "capi_common.cuh"
+#include "eip4844.cuh"
+#include "sha256.cpp.inc"
+#include "util.cuh"
+
+using namespace b200;
+
+namespace {
+
+constexpr size_t kG1 = 4096, kG2 = 65;
+
+struct KzgCtx {
+    std::mutex mu;
+    cudaStream_t stream = nullptr, side = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_side = nullptr;
+    std::unique_ptr<KzgSettingsDev> dev;
+    int max_batch = 0;
+    // device staging
+    uint8_t *d_blobs = nullptr, *d_z = nullptr, *d_comm = nullptr, *d_out48 = nullptr, *d_y32 = nullptr;
+    int *d_status = nullptr, *d_status2 = nullptr;
+    // pinned host staging for the small results
+    uint8_t* h_small = nullptr;  // [48 * mb][32 * mb][int * mb][int * mb][32 * mb (z)]
+    ~KzgCtx() {
+        dev.reset();
+        cudaFree(d_blobs); cudaFree(d_z); cudaFree(d_comm); cudaFree(d_out48); cudaFree(d_y32); cudaFree(d_status); cudaFree(d_status2);
+        if (h_small) cudaFreeHost(h_small);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_side) cudaEventDestroy(ev_side);
+        if (stream) cudaStreamDestroy(stream);
+        if (side) cudaStreamDestroy(side);
+    }
+    uint8_t* h_out48() { return h_small; }
+    uint8_t* h_y32() { return h_small + 48 * (size_t)max_batch; }
+    int* h_status() { return reinterpret_cast<int*>(h_small + 80 * (size_t)max_batch); }
+    int* h_status2() { return h_status() + max_batch; }
+    uint8_t* h_z() { return h_small + 88 * (size_t)max_batch; }
+};
+
+std::mutex g_reg_mu;
+std::map<const void*, std::shared_ptr<KzgCtx>> g_registry;
+
+std::shared_ptr<KzgCtx> find_ctx(const KZGSettings* s) {
+    if (!s || !s->g1_values_lagrange_brp) return nullptr;
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    auto it = g_registry.find(s->g1_values_lagrange_brp);
+    return it == g_registry.end() ? nullptr : it->second;
+}
+
+void zero_settings(KZGSettings* out) { memset(out, 0, sizeof(*out)); }
+
+C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono, const uint8_t* g1_lagrange, size_t n_lag,
+                    const uint8_t* g2_monomial, size_t n_g2) {
+    zero_settings(out);
+    // load_trusted_setup_rust's length checks (kzg/src/eip_4844.rs:1037-1049)
+    if (n_mono / 48 != kG1 || n_lag / 48 != kG1 || n_g2 / 96 != kG2) return C_KZG_BADARGS;
+    std::shared_ptr<KzgCtx> ctx(new KzgCtx());
+    try {
+        require_device();
+        ctx->max_batch = env_int("B200_KZG_MAX_BATCH", 64);
+        if (ctx->max_batch < 1) ctx->max_batch = 1;
+        const int mb = ctx->max_batch;
+        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
+        ctx->dev.reset(new KzgSettingsDev(g1_monomial, g1_lagrange, mb, ctx->stream));
+        ctx->d_blobs = dev_alloc<uint8_t>((size_t)mb * kBytesPerBlob);
+        ctx->d_z = dev_alloc<uint8_t>((size_t)mb * 32);
+        ctx->d_comm = dev_alloc<uint8_t>((size_t)mb * 48);
+        ctx->d_out48 = dev_alloc<uint8_t>((size_t)mb * 48);
+        ctx->d_y32 = dev_alloc<uint8_t>((size_t)mb * 32);
+        ctx->d_status = dev_alloc<int>(mb);
+        ctx->d_status2 = dev_alloc<int>(mb);
+        B200_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_small, (size_t)mb * 120 + 64));
+    } catch (const CudaError& e) {
+        if (e.code != 1) fprintf(stderr, "b200kzg: load_trusted_setup failed: %s\n", e.what());
+        return e.code == 1 ? C_KZG_BADARGS : C_KZG_ERROR;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "b200kzg: load_trusted_setup failed: %s\n", e.what());
+        return C_KZG_ERROR;
+    }
+    // host arrays of the C struct (kzg_settings_to_c, blst/src/eip_4844.rs:40-144)
+    FFTSettingsDev& fs = ctx->dev->fft();
+    const size_t w = fs.max_width();  // 8192
+    out->roots_of_unity = (blst_fr*)malloc((w + 1) * sizeof(blst_fr));
+    out->brp_roots_of_unity = (blst_fr*)malloc(w * sizeof(blst_fr));
+    out->reverse_roots_of_unity = (blst_fr*)malloc((w + 1) * sizeof(blst_fr));
+    out->g1_values_monomial = (blst_p1*)malloc(kG1 * sizeof(blst_p1));
+    out->g1_values_lagrange_brp = (blst_p1*)malloc(kG1 * sizeof(blst_p1));
+    // G2 monomial points are only used by verification (pairings), which is outside this backend's path
+    // (SURVEY.md section 8f-2): the array is allocated (so the struct has the reference's shape) but left zero.
+    out->g2_values_monomial = (blst_p2*)calloc(kG2, sizeof(blst_p2));
+    if (!out->roots_of_unity || !out->brp_roots_of_unity || !out->reverse_roots_of_unity || !out->g1_values_monomial ||
+        !out->g1_values_lagrange_brp || !out->g2_values_monomial) {
+        free_trusted_setup(out);
+        return C_KZG_MALLOC;
+    }
+    (void)g2_monomial;
+    bool ok = cudaMemcpy(out->roots_of_unity, fs.roots_dev(), (w + 1) * 32, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(out->brp_roots_of_unity, fs.brp_roots_dev(), w * 32, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(out->g1_values_monomial, ctx->dev->g1_monomial_jac_dev(), kG1 * 144, cudaMemcpyDeviceToHost) == cudaSuccess &&
+              cudaMemcpy(out->g1_values_lagrange_brp, ctx->dev->g1_lagrange_brp_jac_dev(), kG1 * 144, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (!ok) {
+        free_trusted_setup(out);
+        return C_KZG_ERROR;
+    }
+    for (size_t i = 0; i <= w; i++) out->reverse_roots_of_unity[i] = out->roots_of_unity[w - i];
+    out->x_ext_fft_columns = nullptr;  // FK20 data: outside this backend's path
+    out->tables = nullptr;
+    out->wbits = 0;
+    out->scratch_size = 0;
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    g_registry[out->g1_values_lagrange_brp] = ctx;
+    return C_KZG_OK;
+}
+
+int hexval(int c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; }
+
+// load_trusted_setup_string (kzg/src/eip_4844.rs:151-228): "4096 65" then hex bytes of the G1 Lagrange points,
+// the G2 monomial points and the G1 monomial points, whitespace separated.
+bool parse_setup_text(const char* text, size_t len, std::vector<uint8_t>& mono, std::vector<uint8_t>& lag, std::vector<uint8_t>& g2) {
+    const char *p = text, *end = text + len;
+    size_t counts[2];
+    for (int k = 0; k < 2; k++) {
+        while (p < end && isspace((unsigned char)*p)) p++;
+        if (p >= end || !isdigit((unsigned char)*p)) return false;
+        size_t v = 0;
+        while (p < end && isdigit((unsigned char)*p)) { v = v * 10 + (size_t)(*p - '0'); p++; }
+        if (p >= end) return false;
+        counts[k] = v;
+    }
+    if (counts[0] != kG1 || counts[1] != kG2) return false;
+    lag.resize(kG1 * 48); g2.resize(kG2 * 96); mono.resize(kG1 * 48);
+    std::vector<uint8_t>* parts[3] = {&lag, &g2, &mono};
+    for (auto* part : parts) {
+        for (size_t i = 0; i < part->size(); i++) {
+            while (p < end && isspace((unsigned char)*p)) p++;
+            if (p >= end) return false;
+            int hi = hexval(*p), lo = p + 1 < end ? hexval(p[1]) : -1;
+            if (hi < 0) return false;
+            if (lo >= 0) { (*part)[i] = (uint8_t)(hi << 4 | lo); p += 2; } else { (*part)[i] = (uint8_t)hi; p += 1; }
+        }
+    }
+    return true;
+}
+
+// Fiat-Shamir challenge bytes of compute_challenge_rust (kzg/src/eip_4844.rs:920-945): the canonical blob bytes and
+// the canonical commitment bytes are exactly the caller's bytes once both have passed validation.
+void challenge_hash(uint8_t out[32], const uint8_t* blob, const uint8_t* commitment) {
+    sha256::Ctx c;
+    uint8_t head[32] = {'F', 'S', 'B', 'L', 'O', 'B', 'V', 'E', 'R', 'I', 'F', 'Y', '_', 'V', '1', '_'};
+    head[30] = (kFieldElementsPerBlob >> 8) & 0xff;
+    head[31] = kFieldElementsPerBlob & 0xff;
+    c.update(head, 32);
+    c.update(blob, kBytesPerBlob);
+    c.update(commitment, 48);
+    c.finish(out);
+}
+void challenge_hash_many(uint8_t* out32, const uint8_t* blobs, const uint8_t* commitments, size_t n) {
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = std::min<size_t>(n, hw ? hw : 1);
+    nt = std::min<size_t>(nt, (size_t)env_int("B200_SHA_THREADS", 16));
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; i++) challenge_hash(out32 + 32 * i, blobs + i * kBytesPerBlob, commitments + 48 * i);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([=] {
+            for (size_t i = t; i < n; i += nt) challenge_hash(out32 + 32 * i, blobs + i * kBytesPerBlob, commitments + 48 * i);
+        });
+    for (auto& x : th) x.join();
+}
+
+template <class F>
+C_KZG_RET ckzg_guard(F&& f) {
+    try {
+        return f();
+    } catch (const CudaError& e) {
+        cudaGetLastError();
+        if (e.code == 1) return C_KZG_BADARGS;
+        fprintf(stderr, "b200kzg: %s\n", e.what());
+        return C_KZG_ERROR;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "b200kzg: %s\n", e.what());
+        return C_KZG_ERROR;
+    }
+}
+
+bool any_set(const int* st, int n) {
+    for (int i = 0; i < n; i++)
+        if (st[i]) return true;
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+C_KZG_RET load_trusted_setup(KZGSettings* out, const uint8_t* g1_monomial_bytes, uint64_t num_g1_monomial_bytes,
+                             const uint8_t* g1_lagrange_bytes, uint64_t num_g1_lagrange_bytes,
+                             const uint8_t* g2_monomial_bytes, uint64_t num_g2_monomial_bytes, uint64_t precompute) {
+    (void)precompute;
+    if (!out) return C_KZG_BADARGS;
+    return load_impl(out, g1_monomial_bytes, num_g1_monomial_bytes, g1_lagrange_bytes, num_g1_lagrange_bytes,
+                     g2_monomial_bytes, num_g2_monomial_bytes);
+}
+
+C_KZG_RET load_trusted_setup_file(KZGSettings* out, FILE* in) {
+    if (!out) return C_KZG_BADARGS;
+    zero_settings(out);
+    if (!in) return C_KZG_BADARGS;
+    std::vector<char> buf(1024 * 1024);
+    size_t len = fread(buf.data(), 1, buf.size(), in);
+    std::vector<uint8_t> mono, lag, g2;
+    if (!parse_setup_text(buf.data(), len, mono, lag, g2)) return C_KZG_BADARGS;
+    return load_impl(out, mono.data(), mono.size(), lag.data(), lag.size(), g2.data(), g2.size());
+}
+
+void free_trusted_setup(KZGSettings* s) {
+    if (!s) return;
+    if (s->g1_values_lagrange_brp) {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        g_registry.erase(s->g1_values_lagrange_brp);
+    }
+    free(s->roots_of_unity); free(s->brp_roots_of_unity); free(s->reverse_roots_of_unity);
+    free(s->g1_values_monomial); free(s->g1_values_lagrange_brp); free(s->g2_values_monomial);
+    zero_settings(s);
+}
+
+// ---- batched host-pointer entry points ---------------------------------------------------------------------------
+C_KZG_RET b200_blob_to_kzg_commitment_batch(KZGCommitment* out, const Blob* blobs, size_t n, const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !out || !blobs) return C_KZG_BADARGS;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (size_t off = 0; off < n; off += ctx->max_batch) {
+            int m = (int)std::min<size_t>(ctx->max_batch, n - off);
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
+            B200_CUDA_CHECK(cudaMemsetAsync(ctx->d_status, 0, m * sizeof(int), ctx->stream));
+            ctx->dev->blob_to_commitments(ctx->d_blobs, m, ctx->d_out48, ctx->d_status, ctx->stream);
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_out48(), ctx->d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, ctx->stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status(), ctx->d_status, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            if (any_set(ctx->h_status(), m)) return C_KZG_BADARGS;
+            memcpy(out + off, ctx->h_out48(), (size_t)m * 48);
+        }
+        return C_KZG_OK;
+    });
+}
+
+C_KZG_RET b200_compute_kzg_proof_batch(KZGProof* proofs, Bytes32* ys, const Blob* blobs, const Bytes32* zs, size_t n,
+                                       const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !proofs || !ys || !blobs || !zs) return C_KZG_BADARGS;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (size_t off = 0; off < n; off += ctx->max_batch) {
+            int m = (int)std::min<size_t>(ctx->max_batch, n - off);
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_z, zs + off, (size_t)m * 32, cudaMemcpyHostToDevice, ctx->stream));
+            B200_CUDA_CHECK(cudaMemsetAsync(ctx->d_status, 0, m * sizeof(int), ctx->stream));
+            ctx->dev->compute_proofs(ctx->d_blobs, ctx->d_z, 0, m, ctx->d_out48, ctx->d_y32, ctx->d_status, ctx->stream);
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_out48(), ctx->d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, ctx->stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_y32(), ctx->d_y32, (size_t)m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status(), ctx->d_status, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            if (any_set(ctx->h_status(), m)) return C_KZG_BADARGS;
+            memcpy(proofs + off, ctx->h_out48(), (size_t)m * 48);
+            memcpy(ys + off, ctx->h_y32(), (size_t)m * 32);
+        }
+        return C_KZG_OK;
+    });
+}
+
+C_KZG_RET b200_compute_blob_kzg_proof_batch(KZGProof* out, const Blob* blobs, const Bytes48* commitments, size_t n,
+                                            const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !out || !blobs || !commitments) return C_KZG_BADARGS;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (size_t off = 0; off < n; off += ctx->max_batch) {
+            int m = (int)std::min<size_t>(ctx->max_batch, n - off);
+            // commitments first: their validation (decode + subgroup test) runs on the side stream under everything else
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_comm, commitments + off, (size_t)m * 48, cudaMemcpyHostToDevice, ctx->stream));
+            B200_CUDA_CHECK(cudaMemsetAsync(ctx->d_status, 0, m * sizeof(int), ctx->stream));
+            B200_CUDA_CHECK(cudaMemsetAsync(ctx->d_status2, 0, m * sizeof(int), ctx->stream));
+            B200_CUDA_CHECK(cudaEventRecord(ctx->ev_in, ctx->stream));
+            B200_CUDA_CHECK(cudaStreamWaitEvent(ctx->side, ctx->ev_in, 0));
+            ctx->dev->validate_commitments(ctx->d_comm, m, ctx->d_status2, ctx->side);
+            B200_CUDA_CHECK(cudaEventRecord(ctx->ev_side, ctx->side));
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
+            // the hash chain runs on the host while the blobs cross PCIe
+            challenge_hash_many(ctx->h_z(), (const uint8_t*)(blobs + off), (const uint8_t*)(commitments + off), m);
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_z, ctx->h_z(), (size_t)m * 32, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->dev->compute_proofs(ctx->d_blobs, ctx->d_z, 1, m, ctx->d_out48, nullptr, ctx->d_status, ctx->stream);
+            B200_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_out48(), ctx->d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, ctx->stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status(), ctx->d_status, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status2(), ctx->d_status2, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            if (any_set(ctx->h_status(), m) || any_set(ctx->h_status2(), m)) return C_KZG_BADARGS;
+            memcpy(out + off, ctx->h_out48(), (size_t)m * 48);
+        }
+        return C_KZG_OK;
+    });
+}
+
+// ---- the c-kzg-4844 single-blob entry points ---------------------------------------------------------------------
+C_KZG_RET blob_to_kzg_commitment(KZGCommitment* out, const Blob* blob, const KZGSettings* s) {
+    return b200_blob_to_kzg_commitment_batch(out, blob, 1, s);
+}
+C_KZG_RET compute_kzg_proof(KZGProof* proof_out, Bytes32* y_out, const Blob* blob, const Bytes32* z_bytes, const KZGSettings* s) {
+    return b200_compute_kzg_proof_batch(proof_out, y_out, blob, z_bytes, 1, s);
+}
+C_KZG_RET compute_blob_kzg_proof(KZGProof* out, const Blob* blob, const Bytes48* commitment_bytes, const KZGSettings* s) {
+    return b200_compute_blob_kzg_proof_batch(out, blob, commitment_bytes, 1, s);
+}
+
+// ---- device-pointer extensions (inputs resident in HBM; asynchronous on `stream`) --------------------------------
+C_KZG_RET b200_blob_to_kzg_commitment_device(void* out48_dev, const void* blobs_dev, size_t n, int* status_dev,
+                                             const KZGSettings* s, void* stream) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || n > (size_t)ctx->max_batch) return C_KZG_BADARGS;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->dev->blob_to_commitments((const uint8_t*)blobs_dev, (int)n, (uint8_t*)out48_dev, status_dev, (cudaStream_t)stream);
+        return C_KZG_OK;
+    });
+}
+C_KZG_RET b200_compute_kzg_proof_device(void* proofs48_dev, void* y32_dev, const void* blobs_dev, const void* z32_dev, size_t n,
+                                        int z_reduce, int* status_dev, const KZGSettings* s, void* stream) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || n > (size_t)ctx->max_batch) return C_KZG_BADARGS;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->dev->compute_proofs((const uint8_t*)blobs_dev, (const uint8_t*)z32_dev, z_reduce, (int)n, (uint8_t*)proofs48_dev,
+                                 (uint8_t*)y32_dev, status_dev, (cudaStream_t)stream);
+        return C_KZG_OK;
+    });
+}
+int b200_kzg_launches(const KZGSettings* s) {
+    auto ctx = find_ctx(s);
+    return ctx ? ctx->dev->launches_last() : 0;
+}
+int b200_kzg_max_batch(const KZGSettings* s) {
+    auto ctx = find_ctx(s);
+    return ctx ? ctx->max_batch : 0;
+}
+// test hook: SHA-256 of a host buffer (portable != 0 forces the non-SHA-NI code path)
+void b200_selftest_sha256(uint8_t out[32], const uint8_t* msg, size_t len, int portable) {
+    sha256::digest(out, msg, len, portable != 0);
+}
+
+}  // extern "C"

@@ -172,6 +172,25 @@ void b200_msm_info(void* msm, int* c, int* W, size_t* table_bytes, int* launches
     if (launches) *launches = h->eng->launches_per_run();
 }
 
+void b200_msm_set_profiling(void* msm, int on) {
+    MsmHandle* h = static_cast<MsmHandle*>(msm);
+    if (h) h->eng->set_profiling(on != 0);
+}
+RustError b200_msm_profile_read(void* msm, double* accumulate_ms_sum, int* runs) {
+    return guarded([&] {
+        MsmHandle* h = static_cast<MsmHandle*>(msm);
+        if (!h) throw CudaError(-1, "null msm handle");
+        h->eng->profile_read(accumulate_ms_sum, runs);
+    });
+}
+// out = sum of n Jacobian points (device pointers): the local add after the all-gather of per-GPU partial results
+RustError b200_g1_sum_device(void* out_dev, const void* points_dev, size_t n, void* stream) {
+    return guarded([&] {
+        require_device();
+        launch_g1_sum(points_dev, out_dev, (int)n, (cudaStream_t)stream);
+    });
+}
+
 int b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

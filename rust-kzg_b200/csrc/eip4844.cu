@@ -1,0 +1,396 @@
+// eip4844.cu -- device kernels and host driver of the batched EIP-4844 commitment / proof path.  See eip4844.cuh.
+#include "eip4844.cuh"
+
+#include <cstdlib>
+#include <vector>
+
+#include "g1.cuh"
+#include "util.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------------------
+// wire formats
+// 32 big-endian bytes -> 8 little-endian words
+__device__ __forceinline__ void load_be32(const uint8_t* p, uint32_t w[8]) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);  // blobs are 32-byte aligned inside a 128 KiB array
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[7 - i] = __byte_perm(q[i], 0, 0x0123);
+}
+__device__ __forceinline__ bool lt_r(const uint32_t w[8]) {  // w < r ?
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        uint32_t m = FrParams::mod(i);
+        if (w[i] < m) return true;
+        if (w[i] > m) return false;
+    }
+    return false;
+}
+
+// bytes_to_blob (kzg/src/eip_4844.rs:867-880) = 4096 x Fr::from_bytes (blst/src/types/fr.rs:64-86): big-endian,
+// canonical (< r) or the whole blob is rejected.  Writes the canonical little-endian scalar (MSM input) and,
+// if poly != nullptr, the Montgomery form (polynomial arithmetic).  One thread per field element, 32 B in, coalesced.
+__global__ void __launch_bounds__(256) k_blob_to_fr(const uint8_t* __restrict__ blobs, size_t total, uint8_t* __restrict__ scalars,
+                                                    uint8_t* __restrict__ poly, int* __restrict__ status) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    fr_t v;
+    load_be32(blobs + gid * 32, v.v);
+    if (!lt_r(v.v)) status[gid / kFieldElementsPerBlob] = 1;
+    if (scalars) store_field(scalars + gid * 32, v);
+    if (poly) store_field(poly + gid * 32, v.to_mont());
+}
+
+// z: Fr::from_bytes (reject >= r) or hash_to_bls_field (reduce mod r) -> Montgomery
+__global__ void k_z_to_fr(const uint8_t* __restrict__ z_bytes, int n, int reduce, uint8_t* __restrict__ z_out, int* __restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t v;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint8_t* p = z_bytes + (size_t)i * 32 + 4 * (7 - k);
+        v.v[k] = (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+    }
+    if (!reduce && !lt_r(v.v)) status[i] = 1;
+    // hash_to_bls_field reduces mod r (blst_fr_from_scalar, blst/src/types/fr.rs:88-107): 2^256 < 3r, so at most two
+    // subtractions bring the value into [0, r) before the Montgomery conversion (which needs a reduced operand)
+    for (int it = 0; it < 2; it++) {
+        if (lt_r(v.v)) break;
+        uint32_t borrow = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint64_t d = (uint64_t)v.v[k] - FrParams::mod(k) - borrow;
+            v.v[k] = (uint32_t)d;
+            borrow = (uint32_t)(d >> 63);
+        }
+    }
+    store_field(z_out + (size_t)i * 32, v.to_mont());
+}
+// Fr::to_bytes (blst/src/types/fr.rs:127-136)
+__global__ void k_fr_to_bytes(const uint8_t* __restrict__ fr_mont, int n, uint8_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_t v = load_field<fr_t>(fr_mont + (size_t)i * 32).from_mont();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t w = v.v[7 - k];
+        uint8_t* p = out + (size_t)i * 32 + 4 * k;
+        p[0] = w >> 24; p[1] = w >> 16; p[2] = w >> 8; p[3] = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// G1 decompression (blst_p1_uncompress via FsG1::from_bytes, blst/src/types/g1.rs:65-87; encoding:
+// zkcrypto/bls12_381/src/notes/serialization.rs:1-29).  One thread per point; sqrt = y2^((p+1)/4).
+__device__ __forceinline__ bool uncompress_point(const uint8_t* in, cc::affine_t& out) {
+    using cc::fp_t;
+    uint32_t b0 = in[0];
+    uint32_t cflag = b0 >> 7, iflag = (b0 >> 6) & 1, sflag = (b0 >> 5) & 1;
+    fp_t x;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const uint8_t* p = in + 4 * (11 - k);
+        x.v[k] = (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+    }
+    x.v[11] &= 0x1fffffffu;
+    out.x = fp_t::zero();
+    out.y = fp_t::zero();
+    if (!cflag) return false;
+    if (iflag) return !sflag && x.is_zero();
+    // x < p ?
+    bool lt = false;
+#pragma unroll
+    for (int i = 11; i >= 0; i--) {
+        uint32_t m = FpParams::mod(i);
+        if (x.v[i] != m) { lt = x.v[i] < m; break; }
+    }
+    if (!lt) return false;
+    fp_t xm = x.to_mont();
+    fp_t four = fp_t::one().dbl().dbl();
+    fp_t y2 = xm.sqr() * xm + four;
+    const uint32_t E[12] = {0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u,
+                            0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au};  // (p+1)/4
+    fp_t y = y2.pow_words(E);
+    if (y.sqr() != y2) return false;
+    if (cc::fp_is_lex_largest(y) != (bool)sflag) y = y.neg();
+    out.x = xm;
+    out.y = y;
+    return true;
+}
+__global__ void __launch_bounds__(64) k_uncompress_g1(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int* __restrict__ flags, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cc::affine_t a;
+    bool ok = uncompress_point(in + (size_t)i * 48, a);
+    if (!ok && flags) flags[i] = 1;
+    cc::store_affine(out + (size_t)i * 96, a);
+}
+void launch_uncompress_g1(const uint8_t* in48_dev, void* affine_out_dev, int* flags_dev, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_uncompress_g1<<<div_up(n, 64), 64, 0, st>>>(in48_dev, (uint8_t*)affine_out_dev, flags_dev, n);
+    B200_LAUNCH_CHECK();
+}
+
+// affine -> Jacobian (blst_p1_from_affine), optionally writing to the bit-reversed position
+// (reverse_bit_order of the Lagrange points, kzg/src/eip_4844.rs:1070)
+__global__ void k_affine_to_jac(const uint8_t* __restrict__ aff, uint8_t* __restrict__ jac, uint8_t* __restrict__ aff_out, int n, int log_n, int brp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cc::affine_t a = cc::load_affine(aff + (size_t)i * 96);
+    int j = brp ? (int)(__brev((unsigned)i) >> (32 - log_n)) : i;
+    cc::jac_t p{a.x, a.y, a.is_inf() ? cc::fp_t::zero() : cc::fp_t::one()};
+    cc::store_jac(jac + (size_t)j * 144, p);
+    if (aff_out) cc::store_affine(aff_out + (size_t)j * 96, a);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// subgroup membership (blst_p1_in_g1 via G1::is_valid, blst/src/types/g1.rs:110-119).  Uses the endomorphism test
+// of eprint 2021/1130 sec. 6 as zkcrypto does (zkcrypto/bls12_381/src/g1.rs:401-410): P in G1  <=>
+// (beta*x, y) == -[z^2] P, z = -0xd201000000010000: two 64-bit scalar multiplications instead of one by r.
+__device__ __forceinline__ void mul_by_abs_z(cc::xyzz_t& acc, const cc::affine_t& base) {
+    // |z| = 0xd201000000010000, MSB first; acc starts as base
+    const uint64_t Z = 0xd201000000010000ull;
+    for (int bit = 62; bit >= 0; bit--) {
+        cc::xyzz_dbl(acc);
+        if ((Z >> bit) & 1) cc::xyzz_add_affine(acc, base);
+    }
+}
+__device__ __forceinline__ bool in_g1(const cc::affine_t& p) {
+    using cc::fp_t;
+    if (p.is_inf()) return true;
+    cc::xyzz_t t = cc::affine_to_xyzz(p);
+    mul_by_abs_z(t, p);                         // |z| P
+    cc::affine_t zp = cc::xyzz_to_affine(t);    // one inversion; keeps the second ladder a mixed-add ladder
+    if (zp.is_inf()) return false;
+    cc::xyzz_t u = cc::affine_to_xyzz(zp);
+    mul_by_abs_z(u, zp);                        // z^2 P
+    if (u.is_inf()) return false;
+    fp_t beta;
+    {
+        const uint32_t Bm[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
+                                 0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
+#pragma unroll
+        for (int i = 0; i < 12; i++) beta.v[i] = Bm[i];
+    }
+    // (beta x, y) == -(X/ZZ, Y/ZZZ)  <=>  beta x ZZ == X  and  y ZZZ == -Y
+    return (beta * p.x * u.zz == u.x) && (p.y * u.zzz == u.y.neg());
+}
+// status[i] = 1 unless commitment i decodes and (is infinity or lies in G1)
+__global__ void __launch_bounds__(32) k_validate_commitments(const uint8_t* __restrict__ in, int n, int* __restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cc::affine_t a;
+    if (!uncompress_point(in + (size_t)i * 48, a) || !in_g1(a)) status[i] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// compute_kzg_proof_rust up to the MSM (kzg/src/eip_4844.rs:437-519) with
+// evaluate_polynomial_in_evaluation_form (:954-1003) fused in.  One CTA per blob:
+//   d_i = z - w_i;  inv_i = 1/d_i by the batch-inversion product trick of fr_batch_inv (:882-914), per thread over
+//   its 16 elements with one Fermat inversion per thread (all threads invert in parallel: same latency as one);
+//   y = (z^4096 - 1)/4096 * sum p_i w_i inv_i;   q_i = (p_i - y)/(w_i - z) = (y - p_i) inv_i.
+// The reference's second batch inversion is unnecessary: 1/(w_i - z) = -inv_i.
+// z equal to a domain point w_m (:458-462, 484-510): y = p_m, q_m = (1/z) sum_{i != m} (p_i - y) w_i inv_i.
+static constexpr int kQThreads = 256;
+static constexpr int kQPer = (int)(kFieldElementsPerBlob / kQThreads);  // 16
+
+__device__ __forceinline__ frc_t block_sum_fr(frc_t v, uint8_t* sh /* 8 Fr */) {
+    // warp tree through shuffles, then the 8 warp leaders through shared memory; result valid in every thread
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        frc_t o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.v[k] = __shfl_down_sync(0xffffffffu, v.v[k], d);
+        v = v + o;
+    }
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) store_field(sh + wid * 32, v);
+    __syncthreads();
+    frc_t total = load_field<frc_t>(sh);
+    for (int w = 1; w < kQThreads / 32; w++) total = total + load_field<frc_t>(sh + w * 32);
+    return total;
+}
+
+__global__ void __launch_bounds__(kQThreads) k_quotient(const uint8_t* __restrict__ poly, const uint8_t* __restrict__ z_all,
+                                                        const uint8_t* __restrict__ domain, uint8_t* __restrict__ q_out,
+                                                        uint8_t* __restrict__ y_out) {
+    extern __shared__ __align__(16) uint8_t sm[];  // 4096 Fr scratch (prefix products, then inverses) + 8 Fr + flags
+    uint8_t* pref = sm;
+    uint8_t* red = sm + kFieldElementsPerBlob * 32;
+    int* found = reinterpret_cast<int*>(red + 8 * 32);
+    const size_t blob = blockIdx.x;
+    const uint8_t* p = poly + blob * kFieldElementsPerBlob * 32;
+    const frc_t z = load_field<frc_t>(z_all + blob * 32);
+    if (threadIdx.x == 0) *found = -1;
+    __syncthreads();
+
+    // element k of this thread is i = k * 256 + tid (coalesced across the CTA)
+    frc_t acc = frc_t::one();
+#pragma unroll 1
+    for (int k = 0; k < kQPer; k++) {
+        int i = k * kQThreads + threadIdx.x;
+        frc_t d = z - load_field_ro<frc_t>(domain + (size_t)i * 32);
+        if (d.is_zero()) { *found = i; d = frc_t::one(); }
+        store_field(pref + (size_t)i * 32, acc);
+        acc = acc * d;
+    }
+    frc_t inv = acc.inverse();
+    frc_t ysum = frc_t::zero();
+#pragma unroll 1
+    for (int k = kQPer - 1; k >= 0; k--) {
+        int i = k * kQThreads + threadIdx.x;
+        frc_t w = load_field_ro<frc_t>(domain + (size_t)i * 32);
+        frc_t d = z - w;
+        bool at_root = d.is_zero();
+        if (at_root) d = frc_t::one();
+        frc_t inv_i = load_field<frc_t>(pref + (size_t)i * 32) * inv;
+        inv = inv * d;
+        store_field(pref + (size_t)i * 32, inv_i);
+        if (!at_root) ysum = ysum + inv_i * w * load_field_ro<frc_t>(p + (size_t)i * 32);
+    }
+    frc_t total = block_sum_fr(ysum, red);
+    const int m = *found;
+    frc_t y;
+    if (m >= 0) {
+        y = load_field_ro<frc_t>(p + (size_t)m * 32);
+    } else {
+        // y = total / 4096 * (z^4096 - 1)
+        frc_t zn = z;
+#pragma unroll 1
+        for (int s = 0; s < 12; s++) zn = zn.sqr();
+        frc_t n_inv = frc_t::one();
+        {
+            frc_t two = frc_t::one() + frc_t::one();
+            frc_t half = two.inverse();
+#pragma unroll 1
+            for (int s = 0; s < 12; s++) n_inv = n_inv * half;
+        }
+        y = total * n_inv * (zn - frc_t::one());
+    }
+    // quotient
+    frc_t qm_sum = frc_t::zero();
+#pragma unroll 1
+    for (int k = 0; k < kQPer; k++) {
+        int i = k * kQThreads + threadIdx.x;
+        frc_t pi = load_field_ro<frc_t>(p + (size_t)i * 32);
+        frc_t inv_i = load_field<frc_t>(pref + (size_t)i * 32);
+        frc_t q;
+        if (i == m) {
+            q = frc_t::zero();
+        } else {
+            q = (y - pi) * inv_i;
+            if (m >= 0) qm_sum = qm_sum + (pi - y) * load_field_ro<frc_t>(domain + (size_t)i * 32) * inv_i;
+        }
+        store_field(q_out + (blob * kFieldElementsPerBlob + i) * 32, q.from_mont());
+    }
+    if (m >= 0) {
+        frc_t t = block_sum_fr(qm_sum, red);
+        if (threadIdx.x == 0) {
+            frc_t qm = t * z.inverse();
+            store_field(q_out + (blob * kFieldElementsPerBlob + m) * 32, qm.from_mont());
+        }
+    }
+    if (threadIdx.x == 0) store_field(y_out + blob * 32, y);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static int env_int_local(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lagrange, int max_batch, cudaStream_t st)
+    : max_batch_(max_batch) {
+    const int n = (int)kFieldElementsPerBlob;
+    uint8_t* comp = dev_alloc<uint8_t>((size_t)2 * n * 48);
+    uint8_t* aff = dev_alloc<uint8_t>((size_t)2 * n * 96);
+    uint8_t* aff_brp = dev_alloc<uint8_t>((size_t)n * 96);
+    int* flags = dev_alloc<int>(2 * n);
+    lagrange_jac_ = dev_alloc<uint8_t>((size_t)n * 144);
+    monomial_jac_ = dev_alloc<uint8_t>((size_t)n * 144);
+    B200_CUDA_CHECK(cudaMemcpyAsync(comp, g1_lagrange, (size_t)n * 48, cudaMemcpyHostToDevice, st));
+    B200_CUDA_CHECK(cudaMemcpyAsync(comp + (size_t)n * 48, g1_monomial, (size_t)n * 48, cudaMemcpyHostToDevice, st));
+    B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, 2 * n * sizeof(int), st));
+    launch_uncompress_g1(comp, aff, flags, 2 * n, st);
+    k_affine_to_jac<<<div_up(n, 128), 128, 0, st>>>(aff, (uint8_t*)lagrange_jac_, aff_brp, n, 12, 1);
+    k_affine_to_jac<<<div_up(n, 128), 128, 0, st>>>(aff + (size_t)n * 96, (uint8_t*)monomial_jac_, nullptr, n, 12, 0);
+    B200_LAUNCH_CHECK();
+    std::vector<int> hflags(2 * n);
+    B200_CUDA_CHECK(cudaMemcpyAsync(hflags.data(), flags, 2 * n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    bool bad = false;
+    for (int f : hflags) bad |= f != 0;
+    if (!bad) {
+        fs_.reset(new FFTSettingsDev(13, st));  // FIELD_ELEMENTS_PER_EXT_BLOB = 8192 (kzg/src/eip_4844.rs:1072-1077)
+        MsmConfig cfg;
+        cfg.c = env_int_local("B200_BLOB_C", 12);
+        cfg.W = (256 + cfg.c - 1) / cfg.c;
+        cfg.fixed = true;
+        cfg.n = n;
+        cfg.max_batch = max_batch;
+        cfg.L = env_int_local("B200_BLOB_L", 64);
+        msm_.reset(new MsmEngine(cfg, aff_brp, false, st));
+        // the 4096 domain = first half of the bit-reversed 8192 roots (kzg/src/eip_4844.rs:463, 976)
+        domain_ = dev_alloc<uint8_t>((size_t)n * 32);
+        B200_CUDA_CHECK(cudaMemcpyAsync(domain_, fs_->brp_roots_dev(), (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
+        scalars_ = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
+        poly_ = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
+        z_ = dev_alloc<uint8_t>((size_t)max_batch * 32);
+        y_ = dev_alloc<uint8_t>((size_t)max_batch * 32);
+        out_jac_ = dev_alloc<uint8_t>((size_t)max_batch * 144);
+        B200_CUDA_CHECK(cudaFuncSetAttribute(k_quotient, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(kFieldElementsPerBlob * 32 + 8 * 32 + 64)));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    cudaFree(comp); cudaFree(aff); cudaFree(aff_brp); cudaFree(flags);
+    if (bad) {
+        cudaFree(lagrange_jac_); cudaFree(monomial_jac_);
+        lagrange_jac_ = monomial_jac_ = nullptr;
+        throw CudaError(1, "Failed to uncompress");  // FsG1::from_bytes error text (blst/src/types/g1.rs:82)
+    }
+}
+
+KzgSettingsDev::~KzgSettingsDev() {
+    cudaFree(lagrange_jac_); cudaFree(monomial_jac_); cudaFree(domain_); cudaFree(scalars_); cudaFree(poly_);
+    cudaFree(z_); cudaFree(y_); cudaFree(out_jac_);
+}
+
+void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st) {
+    if (n < 1 || n > max_batch_) throw CudaError(-1, "blob batch exceeds the settings' capacity");
+    size_t total = (size_t)n * kFieldElementsPerBlob;
+    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, (uint8_t*)scalars_, nullptr, status);
+    B200_LAUNCH_CHECK();
+    msm_->run(scalars_, kFieldElementsPerBlob, n, false, out_jac_, st);
+    launch_points_to_compressed(out_jac_, out48, n, st);
+    launches_ = 2 + msm_->launches_per_run();
+}
+
+void KzgSettingsDev::compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes, int z_reduce, int n, uint8_t* proofs48,
+                                    uint8_t* y32, int* status, cudaStream_t st) {
+    if (n < 1 || n > max_batch_) throw CudaError(-1, "blob batch exceeds the settings' capacity");
+    size_t total = (size_t)n * kFieldElementsPerBlob;
+    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)poly_, status);
+    k_z_to_fr<<<div_up(n, 64), 64, 0, st>>>(z_bytes, n, z_reduce, (uint8_t*)z_, status);
+    k_quotient<<<n, kQThreads, kFieldElementsPerBlob * 32 + 8 * 32 + 64, st>>>((const uint8_t*)poly_, (const uint8_t*)z_,
+                                                                              (const uint8_t*)domain_, (uint8_t*)scalars_,
+                                                                              (uint8_t*)y_);
+    B200_LAUNCH_CHECK();
+    msm_->run(scalars_, kFieldElementsPerBlob, n, false, out_jac_, st);
+    launch_points_to_compressed(out_jac_, proofs48, n, st);
+    int extra = 0;
+    if (y32) {
+        k_fr_to_bytes<<<div_up(n, 64), 64, 0, st>>>((const uint8_t*)y_, n, y32);
+        B200_LAUNCH_CHECK();
+        extra = 1;
+    }
+    launches_ = 4 + extra + msm_->launches_per_run();
+}
+
+void KzgSettingsDev::validate_commitments(const uint8_t* commitments48, int n, int* status, cudaStream_t st) {
+    if (n < 1) return;
+    k_validate_commitments<<<div_up(n, 32), 32, 0, st>>>(commitments48, n, status);
+    B200_LAUNCH_CHECK();
+}
+
+}  // namespace b200

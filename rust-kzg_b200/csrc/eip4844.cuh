@@ -1,0 +1,67 @@
+// eip4844.cuh -- device-resident KZGSettings and the batched EIP-4844 commitment / proof pipeline.
+//
+// Mirrors, for the hot path only, the reference's FsKZGSettings (blst/src/types/kzg_settings.rs:66-136) and
+// kzg::eip_4844::{blob_to_kzg_commitment_rust, compute_kzg_proof_rust, compute_blob_kzg_proof_rust}
+// (kzg/src/eip_4844.rs:278-295, 437-519, 541-563).  A batch of blobs is one launch sequence; every blob owns one
+// bucket set of the fixed-base MSM over the bit-reversed Lagrange points.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <memory>
+
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace b200 {
+
+constexpr size_t kFieldElementsPerBlob = 4096;  // kzg/src/eip_4844.rs:32
+constexpr size_t kBytesPerBlob = 131072;
+
+class KzgSettingsDev {
+public:
+    // g1_monomial / g1_lagrange: 4096 x 48-byte compressed points each (host), as parsed from the trusted setup
+    // (kzg/src/eip_4844.rs:151-228).  Throws CudaError(code 1) on malformed / off-curve points.
+    KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lagrange, int max_batch, cudaStream_t stream);
+    ~KzgSettingsDev();
+    KzgSettingsDev(const KzgSettingsDev&) = delete;
+
+    int max_batch() const { return max_batch_; }
+    FFTSettingsDev& fft() { return *fs_; }
+    MsmEngine& msm() { return *msm_; }
+    // Jacobian (blst_p1) copies for CKZGSettings: bit-reversed Lagrange points and monomial points, device memory
+    const void* g1_lagrange_brp_jac_dev() const { return lagrange_jac_; }
+    const void* g1_monomial_jac_dev() const { return monomial_jac_; }
+
+    // All pointers below are DEVICE pointers; status[i] (int, device) is set to 1 when blob / argument i is invalid
+    // (the reference's Err -> C_KZG_BADARGS); outputs of invalid items are unspecified.
+    // blob_to_kzg_commitment_raw (kzg/src/eip_4844.rs:297-314), n <= max_batch
+    void blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st);
+    // compute_kzg_proof_raw (kzg/src/eip_4844.rs:521-539); z_bytes: n x 32 big-endian; z_reduce: 0 = reject z >= r
+    // (Fr::from_bytes), 1 = reduce mod r (hash_to_bls_field, kzg/src/eip_4844.rs:916-918)
+    void compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes, int z_reduce, int n, uint8_t* proofs48,
+                        uint8_t* y32, int* status, cudaStream_t st);
+    // G1::from_bytes + (is_inf || is_valid) of compute_blob_kzg_proof_rust (kzg/src/eip_4844.rs:556-558)
+    void validate_commitments(const uint8_t* commitments48, int n, int* status, cudaStream_t st);
+    int launches_last() const { return launches_; }
+
+private:
+    int max_batch_;
+    int launches_ = 0;
+    std::unique_ptr<FFTSettingsDev> fs_;
+    std::unique_ptr<MsmEngine> msm_;
+    void* lagrange_jac_ = nullptr;
+    void* monomial_jac_ = nullptr;
+    void* domain_ = nullptr;    // brp_roots_of_unity[0..4096) of the 8192 table (Montgomery)
+    void* scalars_ = nullptr;   // max_batch * 4096 canonical scalars (MSM input)
+    void* poly_ = nullptr;      // max_batch * 4096 Montgomery field elements
+    void* z_ = nullptr;         // max_batch Montgomery
+    void* y_ = nullptr;         // max_batch Montgomery
+    void* out_jac_ = nullptr;   // max_batch Jacobian results
+};
+
+// uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input
+void launch_uncompress_g1(const uint8_t* in48_dev, void* affine_out_dev, int* flags_dev, int n, cudaStream_t st);
+
+}  // namespace b200

@@ -128,8 +128,14 @@ struct FrParams {
 };
 
 // ---- the field element ------------------------------------------------------------------------------------------
-template <class P>
+// COMPACT = false: fully unrolled multiplier (register renaming, ~370 SASS instructions) for the throughput kernels.
+// COMPACT = true: the same row recurrence as a rolled loop (~1 KiB of code).  Cold, low-occupancy phases (bucket
+// reduction, table build, compression) are instruction-fetch bound with the unrolled form: a point addition is
+// ~80 KiB of straight-line code, far beyond the 32 KiB instruction cache, and runs at tens of cycles per
+// instruction when every line misses.
+template <class P, bool COMPACT = false>
 struct __align__(16) Mont {
+    typedef P params_t;
     static constexpr int N = P::N;
     uint32_t v[N];
 
@@ -224,6 +230,51 @@ struct __align__(16) Mont {
 
     // Montgomery product a*b*R^-1 mod m, fully reduced.
     friend __device__ __forceinline__ Mont operator*(const Mont& a, const Mont& b) {
+        if (COMPACT) return mul_compact(a, b);
+        return mul_unrolled(a, b);
+    }
+    static __device__ __forceinline__ Mont mul_compact(const Mont& a, const Mont& b) {
+        constexpr int H = N / 2;
+        uint32_t E[N + 2], O[N + 2], bw[N];
+        uint32_t mod_[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) { mod_[i] = P::mod(i); bw[i] = b.v[i]; }
+        Chain<H, false>::mul(E, a.v, bw[0]);
+        Chain<H, false>::mul(O, a.v + 1, bw[0]);
+        E[N] = 0;
+#pragma unroll 1
+        for (int i = 1; i < N; i++) {
+            uint32_t m = E[0] * P::INV;
+            Chain<H, false>::mad(O, mod_ + 1, m);
+            Chain<H, false>::mad(E, mod_, m);
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(E[N]));
+            uint32_t stray = E[1];
+            // T >>= 32 by moving registers; rotate the multiplier words so that bw[0] is always the next one
+#pragma unroll
+            for (int k = 0; k < N; k++) { uint32_t t = O[k]; O[k] = k < N - 1 ? E[k + 2] : 0; E[k] = t; }
+#pragma unroll
+            for (int k = 0; k < N - 1; k++) bw[k] = bw[k + 1];
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[0]) : "r"(stray));
+            Chain<H, true>::mad(O, a.v + 1, bw[0]);
+            Chain<H, false>::mad(E, a.v, bw[0]);
+            asm volatile("addc.u32 %0, 0, 0;" : "=r"(E[N]));
+        }
+        {
+            uint32_t m = E[0] * P::INV;
+            Chain<H, false>::mad(O, mod_ + 1, m);
+            Chain<H, false>::mad(E, mod_, m);
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(E[N]));
+        }
+        Mont r;
+        uint32_t hi;
+        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(O[0]), "r"(E[1]));
+#pragma unroll
+        for (int k = 1; k < N; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.v[k]) : "r"(O[k]), "r"(E[k + 1]));
+        asm volatile("addc.u32 %0, 0, 0;" : "=r"(hi));
+        r.final_sub(hi);
+        return r;
+    }
+    static __device__ __forceinline__ Mont mul_unrolled(const Mont& a, const Mont& b) {
         constexpr int H = N / 2;
         uint32_t E[N + 2], O[N + 2];  // E uses N+1 limbs, O uses N; +1 so that the renaming below stays in bounds
         uint32_t mod_[N];
@@ -307,8 +358,10 @@ struct __align__(16) Mont {
     }
 };
 
-typedef Mont<FpParams> fp_t;
-typedef Mont<FrParams> fr_t;
+typedef Mont<FpParams, false> fp_t;
+typedef Mont<FrParams, false> fr_t;
+typedef Mont<FpParams, true> fpc_t;  // compact-code variants, identical data layout
+typedef Mont<FrParams, true> frc_t;
 
 // load / store through 128-bit accesses (fp_t = 48 B = 3 x uint4, fr_t = 32 B = 2 x uint4)
 template <class F>

@@ -388,13 +388,13 @@ __global__ void __launch_bounds__(96) k_group_finish(const uint8_t* __restrict__
 // kzg/src/msm/tiling_pippenger_ops.rs:106-138).  One thread: W*c doublings.
 __global__ void k_horner(const uint8_t* __restrict__ group_sums, int W, int c, uint8_t* __restrict__ out_jac) {
     if (threadIdx.x || blockIdx.x) return;
-    xyzz_t acc = load_xyzz(group_sums + (size_t)(W - 1) * 192);
+    cc::xyzz_t acc = cc::load_xyzz(group_sums + (size_t)(W - 1) * 192);
     for (int j = W - 2; j >= 0; j--) {
-        for (int k = 0; k < c; k++) xyzz_dbl(acc);
-        xyzz_t s = load_xyzz(group_sums + (size_t)j * 192);
-        xyzz_add(acc, s);
+        for (int k = 0; k < c; k++) cc::xyzz_dbl(acc);
+        cc::xyzz_t s = cc::load_xyzz(group_sums + (size_t)j * 192);
+        cc::xyzz_add(acc, s);
     }
-    store_jac(out_jac, xyzz_to_jac(acc));
+    cc::store_jac(out_jac, cc::xyzz_to_jac(acc));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -403,12 +403,12 @@ __global__ void k_horner(const uint8_t* __restrict__ group_sums, int W, int c, u
 __global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table, size_t n, int W, int c) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    affine_t p = load_affine(table + i * 96);
+    cc::affine_t p = cc::load_affine(table + i * 96);
     for (int j = 1; j < W; j++) {
-        xyzz_t q = affine_to_xyzz(p);
-        for (int k = 0; k < c; k++) xyzz_dbl(q);
-        p = xyzz_to_affine(q);
-        store_affine(table + ((size_t)j * n + i) * 96, p);
+        cc::xyzz_t q = cc::affine_to_xyzz(p);
+        for (int k = 0; k < c; k++) cc::xyzz_dbl(q);
+        p = cc::xyzz_to_affine(q);
+        cc::store_affine(table + ((size_t)j * n + i) * 96, p);
     }
 }
 
@@ -416,9 +416,34 @@ __global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table,
 __global__ void k_compress(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    jac_t p = load_jac(jac + (size_t)i * 144);
-    affine_t a = jac_to_affine(p);
-    affine_compress(out + (size_t)i * 48, a);
+    cc::jac_t p = cc::load_jac(jac + (size_t)i * 144);
+    cc::affine_t a = cc::jac_to_affine(p);
+    cc::affine_compress(out + (size_t)i * 48, a);
+}
+// sum of `count` Jacobian points by one warp (multi-GPU combine: count = number of ranks)
+__global__ void k_g1_sum(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count) {
+    int lane = threadIdx.x;
+    cc::xyzz_t acc = cc::xyzz_t::inf();
+    for (int i = lane; i < count; i += 32) {
+        cc::xyzz_t p = cc::jac_to_xyzz(cc::load_jac(jac + (size_t)i * 144));
+        cc::xyzz_add(acc, p);
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        cc::xyzz_t o;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            o.x.v[k] = __shfl_down_sync(0xffffffffu, acc.x.v[k], d);
+            o.y.v[k] = __shfl_down_sync(0xffffffffu, acc.y.v[k], d);
+            o.zzz.v[k] = __shfl_down_sync(0xffffffffu, acc.zzz.v[k], d);
+            o.zz.v[k] = __shfl_down_sync(0xffffffffu, acc.zz.v[k], d);
+        }
+        cc::xyzz_add(acc, o);
+    }
+    if (lane == 0) cc::store_jac(out, cc::xyzz_to_jac(acc));
+}
+void launch_g1_sum(const void* jac_dev, void* out_jac_dev, int count, cudaStream_t stream) {
+    k_g1_sum<<<1, 32, 0, stream>>>((const uint8_t*)jac_dev, (uint8_t*)out_jac_dev, count);
+    B200_LAUNCH_CHECK();
 }
 void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int count, cudaStream_t stream) {
     if (count <= 0) return;
@@ -462,7 +487,22 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     }
 }
 
+void MsmEngine::profile_read(double* accumulate_ms_sum, int* runs) {
+    double sum = 0;
+    for (int i = 0; i < prof_count_; i++) {
+        float ms = 0;
+        B200_CUDA_CHECK(cudaEventSynchronize(prof_ev_[2 * i + 1]));
+        B200_CUDA_CHECK(cudaEventElapsedTime(&ms, prof_ev_[2 * i], prof_ev_[2 * i + 1]));
+        sum += ms;
+    }
+    if (accumulate_ms_sum) *accumulate_ms_sum = sum;
+    if (runs) *runs = prof_count_;
+    prof_count_ = 0;
+}
+
 MsmEngine::~MsmEngine() {
+    for (auto& e : prof_ev_)
+        if (e) cudaEventDestroy(e);
     cudaFree(table_); cudaFree(counts_); cudaFree(offsets_); cudaFree(cursor_); cudaFree(task_base_); cudaFree(entries_);
     cudaFree(sorted_tasks_); cudaFree(size_hist_); cudaFree(scan_tmp_); cudaFree(partials_); cudaFree(chunk_sums_);
     cudaFree(group_sums_);
@@ -506,8 +546,18 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     launches += 3;
     // 5 accumulate: grid sized for the worst case, surplus threads exit on the device-side task count
     size_t tasks_bound = std::min(tasks_max_, total * W / L + nkeys + 1);
+    const bool prof = profiling_ && prof_count_ < kProfSlots;
+    if (prof) {
+        for (int k = 0; k < 2; k++)
+            if (!prof_ev_[2 * prof_count_ + k]) B200_CUDA_CHECK(cudaEventCreate(&prof_ev_[2 * prof_count_ + k]));
+        B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_], st));
+    }
     k_accumulate<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
                                                                           task_base_ + nkeys, (uint8_t*)partials_);
+    if (prof) {
+        B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_ + 1], st));
+        prof_count_++;
+    }
     launches++;
     // 6 reduce
     k_bucket_combine<false><<<div_up(nkeys, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);

@@ -57,6 +57,10 @@ public:
     // launches of our kernels per run() (for bench.py's gpu_launches)
     int launches_per_run() const { return launches_; }
     const void* table() const { return table_; }
+    // optional device-side timing of the accumulate kernel (bench.py's roofline): when enabled, every run() brackets
+    // k_accumulate with CUDA events on the launching stream; profile_read() sums the completed pairs and resets.
+    void set_profiling(bool on) { profiling_ = on; }
+    void profile_read(double* accumulate_ms_sum, int* runs);
 
 private:
     MsmConfig cfg_;
@@ -67,6 +71,10 @@ private:
     size_t tasks_max_;
     size_t table_bytes_;
     int launches_ = 0;
+    bool profiling_ = false;
+    static constexpr int kProfSlots = 512;
+    cudaEvent_t prof_ev_[2 * kProfSlots] = {};
+    int prof_count_ = 0;
     void* table_ = nullptr;      // affine rows
     uint32_t* counts_ = nullptr;  // [keys+1]
     uint32_t* offsets_ = nullptr;
@@ -82,6 +90,7 @@ private:
 };
 
 // helpers shared with other translation units
+void launch_g1_sum(const void* jac_dev, void* out_jac_dev, int count, cudaStream_t stream);
 void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int count, cudaStream_t stream);
 
 }  // namespace b200

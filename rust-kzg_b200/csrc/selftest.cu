@@ -8,6 +8,7 @@
 
 using namespace b200;
 
+// op + 16 selects the compact-code multiplier (same results required)
 template <class F>
 __global__ void k_field_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,7 +93,10 @@ static RustError field_op(int op, void* out, const void* a, const void* b, size_
         DevBuf<uint8_t> da(bytes), db(bytes), dout(bytes);
         B200_CUDA_CHECK(cudaMemcpy(da.p, a, bytes, cudaMemcpyHostToDevice));
         if (b) B200_CUDA_CHECK(cudaMemcpy(db.p, b, bytes, cudaMemcpyHostToDevice));
-        k_field_op<F><<<div_up(n, 128), 128>>>(op, dout.p, da.p, b ? db.p : nullptr, n);
+        if (op & 16)
+            k_field_op<Mont<typename F::params_t, true>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);
+        else
+            k_field_op<F><<<div_up(n, 128), 128>>>(op, dout.p, da.p, b ? db.p : nullptr, n);
         B200_LAUNCH_CHECK();
         B200_CUDA_CHECK(cudaMemcpy(out, dout.p, bytes, cudaMemcpyDeviceToHost));
     });

@@ -1,0 +1,229 @@
+"""Host-side mirror of the c-kzg-4844 commitment / proof functions (blst/src/eip_4844.rs:160-530) over the C ABI.
+Same names and argument meaning as the reference's bindings; errors (C_KZG_BADARGS) raise KzgError like the
+upstream Python binding raises on a non-OK return."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["KZGSettings", "KzgError", "BYTES_PER_BLOB", "load_trusted_setup_file", "default_trusted_setup_path"]
+
+BYTES_PER_BLOB = 131072
+C_KZG_OK, C_KZG_BADARGS, C_KZG_ERROR, C_KZG_MALLOC = 0, 1, 2, 3
+
+
+class KzgError(ValueError):
+    def __init__(self, code, what):
+        super().__init__("%s failed: C_KZG_RET %d" % (what, code))
+        self.code = code
+
+
+class CKZGSettings(C.Structure):
+    _fields_ = [("roots_of_unity", C.c_void_p), ("brp_roots_of_unity", C.c_void_p), ("reverse_roots_of_unity", C.c_void_p),
+                ("g1_values_monomial", C.c_void_p), ("g1_values_lagrange_brp", C.c_void_p), ("g2_values_monomial", C.c_void_p),
+                ("x_ext_fft_columns", C.c_void_p), ("tables", C.c_void_p), ("wbits", C.c_size_t), ("scratch_size", C.c_size_t)]
+
+
+def _L():
+    from . import lib
+    L = lib()
+    if not getattr(L, "_ckzg_sigs", False):
+        vp, sz, ci, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+        S = C.POINTER(CKZGSettings)
+        sigs = {
+            "load_trusted_setup": (ci, [S, vp, u64, vp, u64, vp, u64, u64]),
+            "load_trusted_setup_file": (ci, [S, vp]),
+            "free_trusted_setup": (None, [S]),
+            "blob_to_kzg_commitment": (ci, [vp, vp, S]),
+            "compute_kzg_proof": (ci, [vp, vp, vp, vp, S]),
+            "compute_blob_kzg_proof": (ci, [vp, vp, vp, S]),
+            "b200_blob_to_kzg_commitment_batch": (ci, [vp, vp, sz, S]),
+            "b200_compute_kzg_proof_batch": (ci, [vp, vp, vp, vp, sz, S]),
+            "b200_compute_blob_kzg_proof_batch": (ci, [vp, vp, vp, sz, S]),
+            "b200_blob_to_kzg_commitment_device": (ci, [vp, vp, sz, vp, S, vp]),
+            "b200_compute_kzg_proof_device": (ci, [vp, vp, vp, vp, sz, ci, vp, S, vp]),
+            "b200_kzg_launches": (ci, [S]),
+            "b200_kzg_max_batch": (ci, [S]),
+            "b200_selftest_sha256": (None, [vp, vp, sz, ci]),
+        }
+        for name, (res, args) in sigs.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        L._ckzg_sigs = True
+    return L
+
+
+_libc = C.CDLL(None)
+_libc.fopen.restype = C.c_void_p
+_libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+_libc.fclose.argtypes = [C.c_void_p]
+
+
+def default_trusted_setup_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "trusted_setup.txt")
+
+
+def _buf(b, size=None, what="argument"):
+    b = bytes(b) if not isinstance(b, (bytes, bytearray, np.ndarray)) else b
+    if isinstance(b, np.ndarray):
+        arr = np.ascontiguousarray(b, dtype=np.uint8).reshape(-1)
+    else:
+        arr = np.frombuffer(b, dtype=np.uint8)
+    if size is not None and arr.size != size:
+        # the C ABI takes fixed-size arrays; a wrong length is the reference's "Invalid byte length" Err
+        raise KzgError(C_KZG_BADARGS, "%s length %d != %d" % (what, arr.size, size))
+    return arr
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class KZGSettings:
+    """CKZGSettings + the device context behind it."""
+
+    def __init__(self):
+        self.c = CKZGSettings()
+        self.loaded = False
+
+    @classmethod
+    def load_trusted_setup_file(cls, path=None):
+        self = cls()
+        path = path or default_trusted_setup_path()
+        fp = _libc.fopen(path.encode(), b"r")
+        if not fp:
+            raise FileNotFoundError(path)
+        try:
+            rc = _L().load_trusted_setup_file(C.byref(self.c), fp)
+        finally:
+            _libc.fclose(fp)
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "load_trusted_setup_file")
+        self.loaded = True
+        return self
+
+    @classmethod
+    def load_trusted_setup(cls, g1_monomial_bytes, g1_lagrange_bytes, g2_monomial_bytes, precompute=0):
+        self = cls()
+        a, b, c = _buf(g1_monomial_bytes), _buf(g1_lagrange_bytes), _buf(g2_monomial_bytes)
+        rc = _L().load_trusted_setup(C.byref(self.c), _p(a), a.size, _p(b), b.size, _p(c), c.size, precompute)
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "load_trusted_setup")
+        self.loaded = True
+        return self
+
+    def free(self):
+        if self.loaded:
+            _L().free_trusted_setup(C.byref(self.c))
+            self.loaded = False
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # host arrays as numpy copies (tests)
+    def array(self, name, count, width):
+        ptr = getattr(self.c, name)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(count, width)).copy()
+
+    @property
+    def max_batch(self):
+        return _L().b200_kzg_max_batch(C.byref(self.c))
+
+    def launches(self):
+        return _L().b200_kzg_launches(C.byref(self.c))
+
+    # ---- c-kzg-4844 functions
+    def blob_to_kzg_commitment(self, blob) -> bytes:
+        b = _buf(blob, BYTES_PER_BLOB, "blob")
+        out = np.zeros(48, np.uint8)
+        rc = _L().blob_to_kzg_commitment(_p(out), _p(b), C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "blob_to_kzg_commitment")
+        return out.tobytes()
+
+    def compute_kzg_proof(self, blob, z):
+        b, zb = _buf(blob, BYTES_PER_BLOB, "blob"), _buf(z, 32, "z")
+        proof, y = np.zeros(48, np.uint8), np.zeros(32, np.uint8)
+        rc = _L().compute_kzg_proof(_p(proof), _p(y), _p(b), _p(zb), C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_kzg_proof")
+        return proof.tobytes(), y.tobytes()
+
+    def compute_blob_kzg_proof(self, blob, commitment) -> bytes:
+        b, cb = _buf(blob, BYTES_PER_BLOB, "blob"), _buf(commitment, 48, "commitment")
+        proof = np.zeros(48, np.uint8)
+        rc = _L().compute_blob_kzg_proof(_p(proof), _p(b), _p(cb), C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_blob_kzg_proof")
+        return proof.tobytes()
+
+    # ---- batched extensions: blobs (n,131072) u8, returns (n,48) u8 ...
+    def blob_to_kzg_commitment_batch(self, blobs, out=None):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, BYTES_PER_BLOB)
+        n = blobs.shape[0]
+        out = np.zeros((n, 48), np.uint8) if out is None else out
+        rc = _L().b200_blob_to_kzg_commitment_batch(_p(out), _p(blobs), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "blob_to_kzg_commitment_batch")
+        return out
+
+    def compute_kzg_proof_batch(self, blobs, zs):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, BYTES_PER_BLOB)
+        zs = np.ascontiguousarray(zs, dtype=np.uint8).reshape(-1, 32)
+        n = blobs.shape[0]
+        proofs, ys = np.zeros((n, 48), np.uint8), np.zeros((n, 32), np.uint8)
+        rc = _L().b200_compute_kzg_proof_batch(_p(proofs), _p(ys), _p(blobs), _p(zs), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_kzg_proof_batch")
+        return proofs, ys
+
+    def compute_blob_kzg_proof_batch(self, blobs, commitments, out=None):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, BYTES_PER_BLOB)
+        commitments = np.ascontiguousarray(commitments, dtype=np.uint8).reshape(-1, 48)
+        n = blobs.shape[0]
+        out = np.zeros((n, 48), np.uint8) if out is None else out
+        rc = _L().b200_compute_blob_kzg_proof_batch(_p(out), _p(blobs), _p(commitments), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_blob_kzg_proof_batch")
+        return out
+
+    # raw-pointer variants (host pinned or device memory owned by the caller)
+    def blob_to_kzg_commitment_batch_ptr(self, out_ptr, blobs_ptr, n):
+        rc = _L().b200_blob_to_kzg_commitment_batch(C.c_void_p(out_ptr), C.c_void_p(blobs_ptr), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "blob_to_kzg_commitment_batch")
+
+    def compute_blob_kzg_proof_batch_ptr(self, out_ptr, blobs_ptr, commitments_ptr, n):
+        rc = _L().b200_compute_blob_kzg_proof_batch(C.c_void_p(out_ptr), C.c_void_p(blobs_ptr), C.c_void_p(commitments_ptr), n,
+                                                    C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_blob_kzg_proof_batch")
+
+    def blob_to_kzg_commitment_device(self, out_ptr, blobs_ptr, n, status_ptr, stream=0):
+        rc = _L().b200_blob_to_kzg_commitment_device(C.c_void_p(out_ptr), C.c_void_p(blobs_ptr), n, C.c_void_p(status_ptr),
+                                                     C.byref(self.c), C.c_void_p(stream))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "blob_to_kzg_commitment_device")
+
+    def compute_kzg_proof_device(self, proofs_ptr, y_ptr, blobs_ptr, z_ptr, n, status_ptr, z_reduce=0, stream=0):
+        rc = _L().b200_compute_kzg_proof_device(C.c_void_p(proofs_ptr), C.c_void_p(y_ptr), C.c_void_p(blobs_ptr),
+                                                C.c_void_p(z_ptr), n, z_reduce, C.c_void_p(status_ptr), C.byref(self.c),
+                                                C.c_void_p(stream))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_kzg_proof_device")
+
+
+def load_trusted_setup_file(path=None):
+    return KZGSettings.load_trusted_setup_file(path)
+
+
+def sha256(msg: bytes, portable=False) -> bytes:
+    out = np.zeros(32, np.uint8)
+    m = np.frombuffer(msg, dtype=np.uint8) if len(msg) else np.zeros(1, np.uint8)
+    _L().b200_selftest_sha256(_p(out), _p(m), len(msg), int(portable))
+    return out.tobytes()

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["PreparedMsm", "g1_lincomb", "mult_pippenger", "microbench_int"]
+__all__ = ["PreparedMsm", "g1_lincomb", "mult_pippenger", "microbench_int", "g1_sum_device"]
 
 
 def _L():
@@ -64,6 +64,14 @@ class PreparedMsm:
         _lib.check(_L().b200_msm_prepared_device(self.h, C.c_void_p(out_ptr), npoints, C.c_void_p(scalars_ptr), batch,
                                                  C.c_void_p(stream)))
 
+    def set_profiling(self, on=True):
+        _L().b200_msm_set_profiling(self.h, int(on))
+
+    def profile_read(self):
+        ms, runs = C.c_double(), C.c_int()
+        _lib.check(_L().b200_msm_profile_read(self.h, C.byref(ms), C.byref(runs)))
+        return ms.value, runs.value
+
     def close(self):
         if self.h:
             _L().b200_free_msm(self.h)
@@ -95,6 +103,11 @@ def g1_lincomb(affine_points, scalars, length=None, precomputation: PreparedMsm 
     if precomputation is not None:
         return precomputation.mult(sc[:length])
     return mult_pippenger(_u64(affine_points, 12)[:length], sc[:length])
+
+
+def g1_sum_device(out_ptr, points_ptr, n, stream=0):
+    """sum of n Jacobian points resident on the device (multi-GPU combine step)"""
+    _lib.check(_L().b200_g1_sum_device(C.c_void_p(out_ptr), C.c_void_p(points_ptr), n, C.c_void_p(stream)))
 
 
 def microbench_int():

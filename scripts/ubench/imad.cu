@@ -153,6 +153,8 @@ int main() {
         int blocks = sms * occ, th = 128, iters = 100;
         float ms = timeit([&] { k_mul<fp_t><<<blocks, th>>>((uint8_t*)sink, iters); });
         printf("fpmul occ=%d (warps/SM=%d): %.2f G mul/s\n", occ, occ * 4, (double)blocks * th * iters * 4 / ms / 1e6);
+        ms = timeit([&] { k_mul<fpc_t><<<blocks, th>>>((uint8_t*)sink, iters); });
+        printf("fpmul-compact occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
         ms = timeit([&] { k_mul<fr_t><<<blocks, th>>>((uint8_t*)sink, iters); });
         printf("frmul occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
         ms = timeit([&] { k_add<<<blocks, th>>>((uint8_t*)sink, iters * 10); });

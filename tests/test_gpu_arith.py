@@ -48,6 +48,11 @@ def test_field_ops_match_oracle(B, K, which):
     canon = np.array([[(v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(w)] for v in xs], dtype=np.uint64)
     assert np.array_equal(_field(B, which, 5, canon), a)
     assert np.array_equal(_field(B, which, 6, a), canon)
+    # the compact-code multiplier (op + 16) used by the latency-bound kernels must agree bit for bit
+    assert np.array_equal(_field(B, which, 16, a, b), omul(a, b))
+    assert np.array_equal(_field(B, which, 16, a, a), omul(a, a))
+    assert np.array_equal(_field(B, which, 16 + 5, canon), a)
+    assert np.array_equal(_field(B, which, 16 + 6, a), canon)
 
 
 @pytest.mark.parametrize("which", ["fp", "fr"])
@@ -59,6 +64,7 @@ def test_field_inverse(B, K, which):
     a = conv(xs)
     oinv = K.fp_inv if which == "fp" else K.fr_inv
     assert np.array_equal(_field(B, which, 4, a), oinv(a))
+    assert np.array_equal(_field(B, which, 16 + 4, a), oinv(a))
 
 
 def _rand_points(K, rng, n):

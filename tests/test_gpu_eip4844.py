@@ -1,0 +1,214 @@
+"""c-kzg-4844 commitment / proof functions through the C ABI vs the reference's consensus-spec vectors
+(kzg-bench/src/test_vectors/*, extracted to tests/golden/) and vs the oracle on random blobs."""
+import numpy as np
+import pytest
+
+from conftest import R_MOD
+
+pytestmark = pytest.mark.gpu
+
+
+def H(x):
+    return bytes.fromhex(x[2:])
+
+
+@pytest.fixture(scope="module")
+def ts(B):
+    s = B.KZGSettings.load_trusted_setup_file()
+    yield s
+    s.free()
+
+
+def _blob_of(case, golden_blobs):
+    if "blob" in case:
+        return golden_blobs[case["blob"]]
+    return bytes([0]) * case["blob_len"]      # malformed length: content irrelevant
+
+
+def test_settings_arrays_match_oracle(B, K, ts, oracle_settings):
+    """CKZGSettings host arrays (kzg_settings_to_c, blst/src/eip_4844.rs:40-144) are the reference's values"""
+    assert np.array_equal(ts.array("roots_of_unity", 8193, 4), oracle_settings.fs.roots_of_unity)
+    assert np.array_equal(ts.array("brp_roots_of_unity", 8192, 4), oracle_settings.fs.brp_roots_of_unity)
+    assert np.array_equal(ts.array("reverse_roots_of_unity", 8193, 4), oracle_settings.fs.reverse_roots_of_unity)
+    assert np.array_equal(ts.array("g1_values_lagrange_brp", 4096, 18), oracle_settings.g1_lagrange_brp)
+    assert np.array_equal(ts.array("g1_values_monomial", 4096, 18), oracle_settings.g1_monomial)
+
+
+def test_blob_to_kzg_commitment_vectors(B, ts, vectors, golden_blobs):
+    for c in vectors["blob_to_kzg_commitment"]:
+        try:
+            out = "0x" + ts.blob_to_kzg_commitment(_blob_of(c, golden_blobs)).hex()
+        except B.KzgError:
+            out = None
+        assert out == c["output"], c["name"]
+
+
+def test_compute_kzg_proof_vectors(B, ts, vectors, golden_blobs):
+    for c in vectors["compute_kzg_proof"]:
+        try:
+            p, y = ts.compute_kzg_proof(_blob_of(c, golden_blobs), H(c["z"]))
+            out = ["0x" + p.hex(), "0x" + y.hex()]
+        except (B.KzgError, ValueError):
+            out = None
+        assert out == c["output"], c["name"]
+
+
+def test_compute_blob_kzg_proof_vectors(B, ts, vectors, golden_blobs):
+    for c in vectors["compute_blob_kzg_proof"]:
+        try:
+            out = "0x" + ts.compute_blob_kzg_proof(_blob_of(c, golden_blobs), H(c["commitment"])).hex()
+        except (B.KzgError, ValueError):
+            out = None
+        assert out == c["output"], c["name"]
+
+
+def test_commitment_and_proof_kats(B, ts, kats):
+    """kzg-bench/src/tests/eip_4844.rs:85-175"""
+    k = kats["commitment_kat"]
+    blob = H(k["blob0"]) + bytes(131072 - 32)
+    assert "0x" + ts.blob_to_kzg_commitment(blob).hex() == k["commitment"]
+    k = kats["proof_kat"]
+    blob = H(k["blob0"]) + bytes(131072 - 32)
+    proof, _ = ts.compute_kzg_proof(blob, H(k["z"]))
+    assert "0x" + proof.hex() == k["proof"]
+
+
+def _rand_blobs(rng, n):
+    """kzg-bench/src/tests/eip_4844.rs:28-37: random bytes with the top byte of every element zeroed"""
+    b = rng.integers(0, 256, size=(n, 4096, 32), dtype=np.uint8)
+    b[:, :, 0] = 0
+    return b.reshape(n, 131072)
+
+
+def test_batches_match_oracle(B, K, ts, oracle_settings):
+    rng = np.random.default_rng(0x4B5A47)
+    n = 5
+    blobs = _rand_blobs(rng, n)
+    blobs[1, 32:] = 0                                      # sparse blob
+    blobs[2] = np.tile(blobs[2, :32], 4096)                # all elements equal (one hot bucket per window)
+    oracle_settings.set_threads(8)
+    comm = ts.blob_to_kzg_commitment_batch(blobs)
+    for i in range(n):
+        assert comm[i].tobytes() == K.blob_to_kzg_commitment(blobs[i].tobytes(), oracle_settings), i
+    zs = _rand_blobs(rng, 1)[0, : 32 * n].reshape(n, 32).copy()
+    # z inside the evaluation domain (kzg/src/eip_4844.rs:458-462, 484-510): a bit-reversed root of unity
+    zs[3] = np.frombuffer(K.fr_to_bytes(oracle_settings.fs.brp_roots_of_unity[5]), dtype=np.uint8)
+    zs[4] = np.frombuffer(K.fr_to_bytes(oracle_settings.fs.brp_roots_of_unity[0]), dtype=np.uint8)   # z = 1
+    proofs, ys = ts.compute_kzg_proof_batch(blobs, zs)
+    for i in range(n):
+        ep, ey = K.compute_kzg_proof(blobs[i].tobytes(), zs[i].tobytes(), oracle_settings)
+        assert (proofs[i].tobytes(), ys[i].tobytes()) == (ep, ey), i
+    bp = ts.compute_blob_kzg_proof_batch(blobs, comm)
+    for i in range(n):
+        assert bp[i].tobytes() == K.compute_blob_kzg_proof(blobs[i].tobytes(), comm[i].tobytes(), oracle_settings), i
+    oracle_settings.set_threads(1)
+
+
+def test_full_batch_of_64_and_chunking(B, K, ts, oracle_settings):
+    """BASELINE config 3: 64 blobs per call; 70 exercises the chunking past the context capacity"""
+    rng = np.random.default_rng(64)
+    blobs = _rand_blobs(rng, 70)
+    comm = ts.blob_to_kzg_commitment_batch(blobs)
+    oracle_settings.set_threads(8)
+    for i in (0, 31, 63, 64, 69):
+        assert comm[i].tobytes() == K.blob_to_kzg_commitment(blobs[i].tobytes(), oracle_settings), i
+    proofs = ts.compute_blob_kzg_proof_batch(blobs, comm)
+    for i in (0, 63, 69):
+        assert proofs[i].tobytes() == K.compute_blob_kzg_proof(blobs[i].tobytes(), comm[i].tobytes(), oracle_settings), i
+    oracle_settings.set_threads(1)
+    # size-independent property: the commitment is linear in the blob -> commit(a) + commit(b) == commit(a + b)
+    a = K.fr_from_ints([int.from_bytes(blobs[0, 32 * i:32 * i + 32].tobytes(), "big") for i in range(4096)])
+    b = K.fr_from_ints([int.from_bytes(blobs[1, 32 * i:32 * i + 32].tobytes(), "big") for i in range(4096)])
+    s = K.fr_add(a, b)
+    sum_blob = b"".join(K.fr_to_bytes(x) for x in s)
+    lhs = K.p1_add(K.p1_uncompress(comm[0].tobytes()), K.p1_uncompress(comm[1].tobytes()))
+    assert K.p1_compress(lhs) == ts.blob_to_kzg_commitment(sum_blob)
+
+
+def test_error_cases(B, K, ts, golden_blobs):
+    """kzg-bench/src/tests/c_bindings.rs:65-97, 584-616 and SURVEY.md appendix B.8"""
+    good = golden_blobs[3]
+    bad = bytearray(good)
+    bad[64:96] = R_MOD.to_bytes(32, "big")                 # element == r: non-canonical
+    with pytest.raises(B.KzgError):
+        ts.blob_to_kzg_commitment(bytes(bad))
+    with pytest.raises(B.KzgError):
+        ts.compute_kzg_proof(bytes(bad), bytes(32))
+    with pytest.raises(B.KzgError):
+        ts.compute_kzg_proof(good, R_MOD.to_bytes(32, "big"))          # z == r
+    comm = ts.blob_to_kzg_commitment(good)
+    with pytest.raises(B.KzgError):
+        ts.compute_blob_kzg_proof(bytes(bad), comm)
+    # commitment at infinity is accepted
+    inf = bytes([0xC0]) + bytes(47)
+    assert ts.compute_blob_kzg_proof(good, inf) == K.compute_blob_kzg_proof(good, inf, K.KZGSettings(open(B.default_trusted_setup_path()).read()))
+    # not compressed / not on curve / wrong subgroup
+    with pytest.raises(B.KzgError):
+        ts.compute_blob_kzg_proof(good, bytes(48))
+    x = 5
+    P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+    found = None
+    while found is None:                                   # a curve point outside G1: x such that x^3+4 is a square
+        y2 = (x ** 3 + 4) % P
+        y = pow(y2, (P + 1) // 4, P)
+        if y * y % P == y2:
+            enc = bytearray(x.to_bytes(48, "big"))
+            enc[0] |= 0x80 | (0x20 if y > (P - 1) // 2 else 0)
+            pt = K.p1_uncompress(bytes(enc))
+            if not K.p1_in_g1(pt):
+                found = bytes(enc)
+        x += 1
+    with pytest.raises(B.KzgError):
+        ts.compute_blob_kzg_proof(good, found)
+    # a batch with one bad element fails as a whole
+    blobs = np.frombuffer(good + bytes(bad), dtype=np.uint8).reshape(2, 131072)
+    with pytest.raises(B.KzgError):
+        ts.blob_to_kzg_commitment_batch(blobs)
+
+
+def test_malformed_trusted_setups(B, tmp_path):
+    """load_trusted_setup error paths (kzg-bench/src/tests/fixtures/*): wrong counts, bad hex, bad points"""
+    text = open(B.default_trusted_setup_path()).read()
+    toks = text.split()
+    cases = {
+        "wrong_g1_count": ["4095"] + toks[1:],
+        "wrong_g2_count": [toks[0], "64"] + toks[2:],
+        "truncated": toks[:500],
+        "bad_hex": toks[:2] + ["zz" + toks[2][2:]] + toks[3:],
+        "point_not_on_curve": toks[:2] + [toks[2][:-2] + ("00" if toks[2][-2:] != "00" else "01")] + toks[3:],
+    }
+    for name, tk in cases.items():
+        p = tmp_path / (name + ".txt")
+        p.write_text("\n".join(tk) + "\n")
+        with pytest.raises(B.KzgError):
+            B.KZGSettings.load_trusted_setup_file(str(p))
+    # free is idempotent and NULL-safe; a freed handle is rejected (kzg-bench/src/tests/c_bindings.rs free tests)
+    s = B.KZGSettings.load_trusted_setup_file()
+    s.free()
+    s.free()
+    assert s.c.g1_values_lagrange_brp is None and s.c.roots_of_unity is None
+    B.lib().free_trusted_setup(None)
+    s.loaded = False
+    with pytest.raises(B.KzgError):
+        s.blob_to_kzg_commitment(bytes(131072))
+
+
+def test_load_from_bytes(B, K, setup_text):
+    """load_trusted_setup (bytes form, blst/src/eip_4844.rs:180-222)"""
+    from oracle import kzg_oracle as O
+    mono, lag, g2 = O.load_trusted_setup_string(setup_text)
+    s = B.KZGSettings.load_trusted_setup(b"".join(mono), b"".join(lag), b"".join(g2))
+    assert s.blob_to_kzg_commitment(bytes(131072)) == bytes([0xC0]) + bytes(47)
+    s.free()
+    with pytest.raises(B.KzgError):
+        B.KZGSettings.load_trusted_setup(b"".join(mono[:-1]), b"".join(lag), b"".join(g2))
+
+
+def test_sha256_paths(B):
+    import hashlib
+    from rust_kzg_b200 import eip4844
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 55, 56, 63, 64, 65, 119, 120, 1000, 131152):
+        msg = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert eip4844.sha256(msg) == hashlib.sha256(msg).digest()
+        assert eip4844.sha256(msg, portable=True) == hashlib.sha256(msg).digest()
