@@ -174,7 +174,6 @@ def main():
     sc = rand_fr(rng, n)
     pts = np.tile(L, (n // 4096, 1)) if n >= 4096 else L[:n]
     msm = B.PreparedMsm(pts)
-    info = msm.info()
     h_sc = torch.from_numpy(sc.view(np.int64)).pin_memory()
     d_sc = h_sc.cuda(non_blocking=True)
     d_out = torch.zeros(18, dtype=torch.int64, device="cuda")
@@ -188,18 +187,19 @@ def main():
             dist.all_gather_into_tensor(d_all, d_out)
             B.g1_sum_device(d_total.data_ptr(), d_all.data_ptr(), world, stream)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi takes a moment to start: sample from the warm-up through the e2e leg
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
+    info = msm.info()
     # parity of the thing being timed: local result vs the folded-scalar oracle
     exp = folded_expectation(K, L, sc, os.cpu_count() or 1)
     if K.p1_compress(d_out.cpu().numpy().view(np.uint64)) != K.p1_compress(exp):
         raise SystemExit("bench.py: MSM result differs from the oracle -- refusing to report a number")
 
     msm.set_profiling(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -218,7 +218,6 @@ def main():
         t = torch.tensor([ms_total], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * n * ADDS_PER_TERM / (ms_step * 1e-3)
 
@@ -241,6 +240,7 @@ def main():
     if K.p1_compress(res) != K.p1_compress(exp):
         raise SystemExit("bench.py: e2e MSM result differs from the oracle")
     e2e_value = world * n * ADDS_PER_TERM / t_e2e
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:

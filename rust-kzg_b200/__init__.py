@@ -26,3 +26,4 @@ from .g1_lincomb import *  # noqa: E402,F401,F403
 from .fft import *  # noqa: E402,F401,F403
 from .eip4844 import *  # noqa: E402,F401,F403
 from . import eip4844  # noqa: E402
+from .sharded import *  # noqa: E402,F401,F403
