@@ -11,7 +11,7 @@ from oracle import c_oracle as K
 
 what, logn, reps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 2
 rng = np.random.default_rng(1)
-n = 1 << logn
+n = 1 << logn if what in ('msm', 'ntt') else logn
 
 
 def rand_fr(n):
@@ -36,4 +36,28 @@ elif what == "ntt":
     d_out = torch.zeros_like(d_in)
     for _ in range(reps):
         fs.fft_fr_device(d_out.data_ptr(), d_in.data_ptr(), n, False, 1, 0)
+    torch.cuda.synchronize()
+elif what == "blob":
+    ts = B.KZGSettings.load_trusted_setup_file()
+    nb = n if n <= 64 else 64
+    blobs = rng.integers(0, 256, size=(nb, 4096, 32), dtype=np.uint8)
+    blobs[:, :, 0] = 0
+    d_blobs = torch.from_numpy(blobs.reshape(nb, 131072)).cuda()
+    d_out = torch.zeros((nb, 48), dtype=torch.uint8, device="cuda")
+    d_st = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    for _ in range(reps):
+        ts.blob_to_kzg_commitment_device(d_out.data_ptr(), d_blobs.data_ptr(), nb, d_st.data_ptr(), 0)
+    torch.cuda.synchronize()
+elif what == "proof":
+    ts = B.KZGSettings.load_trusted_setup_file()
+    nb = 64
+    blobs = rng.integers(0, 256, size=(nb, 4096, 32), dtype=np.uint8)
+    blobs[:, :, 0] = 0
+    d_blobs = torch.from_numpy(blobs.reshape(nb, 131072)).cuda()
+    d_z = torch.from_numpy(blobs.reshape(nb, 131072)[0, :32 * nb].copy()).cuda()
+    d_out = torch.zeros((nb, 48), dtype=torch.uint8, device="cuda")
+    d_y = torch.zeros((nb, 32), dtype=torch.uint8, device="cuda")
+    d_st = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    for _ in range(reps):
+        ts.compute_kzg_proof_device(d_out.data_ptr(), d_y.data_ptr(), d_blobs.data_ptr(), d_z.data_ptr(), nb, d_st.data_ptr(), 0, 0)
     torch.cuda.synchronize()
