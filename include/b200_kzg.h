@@ -95,6 +95,9 @@ B200_API RustError b200_das_fft_extension(void *fs, blst_fr *odds, const blst_fr
 /* device-pointer, batched (batch contiguous transforms of n), asynchronous on stream; out_dev != in_dev */
 B200_API RustError b200_fft_fr_device(void *fs, void *out_dev, const void *in_dev, size_t n, int inverse, int batch, void *stream);
 B200_API RustError b200_das_fft_extension_device(void *fs, void *odds_dev, const void *evens_dev, size_t n, int batch, void *stream);
+/* FFTG1::fft_g1(data, inverse) (kzg/src/lib.rs:425-427, blst/src/fft_g1.rs:53-83): transform over G1 points */
+B200_API RustError b200_fft_g1(void *fs, blst_p1 *out, const blst_p1 *in, size_t n, bool inverse);
+B200_API RustError b200_fft_g1_device(void *fs, void *out_dev, const void *in_dev, size_t n, int inverse, int batch, void *stream);
 B200_API int b200_fft_launches(void *fs);
 
 /* ============================================================================================================== */

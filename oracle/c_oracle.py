@@ -47,6 +47,7 @@ def _load():
         "ko_fft_settings_new": (vp, [ci]), "ko_fft_settings_free": (None, [vp]), "ko_fft_settings_roots": (vp, [vp, ci]),
         "ko_fft_fr": (ci, [vp, vp, vp, sz, ci, ci]), "ko_fft_fr_slow": (None, [vp, vp, vp, sz, ci]),
         "ko_das_fft_extension": (ci, [vp, vp, vp, sz]),
+        "ko_fft_g1": (ci, [vp, vp, vp, sz, ci]), "ko_fft_g1_slow": (None, [vp, vp, vp, sz, ci]),
         "ko_sha256": (None, [vp, vp, sz]),
         "ko_load_trusted_setup_text": (vp, [C.c_char_p, sz]), "ko_settings_set_threads": (None, [vp, ci]),
         "ko_settings_g1_lagrange_brp": (vp, [vp]), "ko_settings_g1_monomial": (vp, [vp]), "ko_settings_fft": (vp, [vp]),
@@ -305,6 +306,19 @@ class FFTSettings:
         data = _u64(data, 4)
         out = np.zeros_like(data)
         lib.ko_fft_fr_slow(self.h, _p(out), _p(data), data.shape[0], int(inverse))
+        return out
+
+    def fft_g1(self, points, inverse=False):
+        pts = _u64(points, 18)
+        out = np.zeros_like(pts)
+        if lib.ko_fft_g1(self.h, _p(out), _p(pts), pts.shape[0], int(inverse)):
+            raise OracleError("fft_g1: bad length")
+        return out
+
+    def fft_g1_slow(self, points, inverse=False):
+        pts = _u64(points, 18)
+        out = np.zeros_like(pts)
+        lib.ko_fft_g1_slow(self.h, _p(out), _p(pts), pts.shape[0], int(inverse))
         return out
 
     def das_fft_extension(self, evens):

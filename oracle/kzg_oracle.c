@@ -882,6 +882,48 @@ API void ko_fft_fr_slow(void *h, fr_t *out, const fr_t *data, size_t n, int inve
         for (size_t i = 0; i < n; i++) fr_mul(&out[i], &out[i], &inv);
     }
 }
+/* fft_g1_fast + FFTG1::fft_g1 (blst/src/fft_g1.rs:13-83): the same recursion over G1 with a full scalar
+ * multiplication per butterfly.  returns 0 ok, 1 Err */
+static void fft_g1_fast(p1_t *ret, size_t n, const p1_t *data, size_t stride, const fr_t *roots, size_t roots_stride) {
+    size_t half = n / 2;
+    if (half == 0) { ret[0] = data[0]; return; }
+    fft_g1_fast(ret, half, data, stride * 2, roots, roots_stride * 2);
+    fft_g1_fast(ret + half, half, data + stride, stride * 2, roots, roots_stride * 2);
+    for (size_t i = 0; i < half; i++) {
+        p1_t yr, neg;
+        ko_p1_mult(&yr, &ret[i + half], &roots[i * roots_stride]);
+        neg = yr; fp_neg(&neg.y, &neg.y);
+        p1_add_or_double(&ret[i + half], &ret[i], &neg);
+        p1_add_or_double(&ret[i], &ret[i], &yr);
+    }
+}
+API int ko_fft_g1(void *h, p1_t *out, const p1_t *data, size_t n, int inverse) {
+    fft_settings_t *fs = (fft_settings_t *)h;
+    if (n > fs->max_width) return 1;
+    if (n == 0 || (n & (n - 1))) return 1;
+    size_t stride = fs->max_width / n;
+    fft_g1_fast(out, n, data, 1, inverse ? fs->reverse_roots_of_unity : fs->roots_of_unity, stride);
+    if (inverse) {
+        fr_t inv; fr_from_u64(&inv, (u64)n); fr_inv(&inv, &inv);
+        for (size_t i = 0; i < n; i++) ko_p1_mult(&out[i], &out[i], &inv);
+    }
+    return 0;
+}
+/* fft_g1_slow (blst/src/fft_g1.rs:86-104) */
+API void ko_fft_g1_slow(void *h, p1_t *out, const p1_t *data, size_t n, int inverse) {
+    fft_settings_t *fs = (fft_settings_t *)h;
+    size_t rs = fs->max_width / n;
+    const fr_t *roots = inverse ? fs->reverse_roots_of_unity : fs->roots_of_unity;
+    for (size_t i = 0; i < n; i++) {
+        p1_t acc; ko_p1_mult(&acc, &data[0], &roots[0]);
+        for (size_t j = 1; j < n; j++) {
+            p1_t v; ko_p1_mult(&v, &data[j], &roots[((i * j) % n) * rs]);
+            p1_add_or_double(&acc, &acc, &v);
+        }
+        out[i] = acc;
+    }
+}
+
 /* das_fft_extension_stride (blst/src/data_availability_sampling.rs:14-71) */
 static void das_stride(const fft_settings_t *fs, fr_t *ev, size_t n, size_t stride) {
     if (n < 2) return;

@@ -59,6 +59,8 @@ def load():
         "b200_fft_fr_device": (RustError, [vp, vp, vp, sz, ci, ci, vp]),
         "b200_das_fft_extension_device": (RustError, [vp, vp, vp, sz, ci, vp]),
         "b200_fft_launches": (ci, [vp]),
+        "b200_fft_g1": (RustError, [vp, vp, vp, sz, C.c_bool]),
+        "b200_fft_g1_device": (RustError, [vp, vp, vp, sz, ci, ci, vp]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(lib, name)          # AttributeError here = header / library mismatch: fail loudly

@@ -112,6 +112,28 @@ RustError b200_das_fft_extension(void* fs, blst_fr* odds, const blst_fr* evens, 
         B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     });
 }
+RustError b200_fft_g1_device(void* fs, void* out_dev, const void* in_dev, size_t n, int inverse, int batch, void* stream) {
+    return guarded([&] {
+        FftHandle* h = static_cast<FftHandle*>(fs);
+        if (!h) throw CudaError(-1, "null fft settings");
+        std::lock_guard<std::mutex> lk(h->mu);
+        h->fs->fft_g1(in_dev, out_dev, n, inverse != 0, batch, (cudaStream_t)stream);
+    });
+}
+RustError b200_fft_g1(void* fs, blst_p1* out, const blst_p1* in, size_t n, bool inverse) {
+    return guarded([&] {
+        FftHandle* h = static_cast<FftHandle*>(fs);
+        if (!h) throw CudaError(-1, "null fft settings");
+        std::lock_guard<std::mutex> lk(h->mu);
+        if (n > h->fs->max_width()) throw CudaError(1, "Supplied list is longer than the available max width");
+        if (n == 0 || (n & (n - 1))) throw CudaError(1, "A list with power-of-two length expected");
+        h->ensure(n * 9);  // 2 x 144 B per point inside the 32-byte-element staging buffers
+        B200_CUDA_CHECK(cudaMemcpyAsync(h->in_dev, in, n * 144, cudaMemcpyHostToDevice, h->stream));
+        h->fs->fft_g1(h->in_dev, h->out_dev, n, inverse, 1, h->stream);
+        B200_CUDA_CHECK(cudaMemcpyAsync(out, h->out_dev, n * 144, cudaMemcpyDeviceToHost, h->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    });
+}
 int b200_fft_launches(void* fs) { return fs ? static_cast<FftHandle*>(fs)->fs->launches_last() : 0; }
 
 }  // extern "C"

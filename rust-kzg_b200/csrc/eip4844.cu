@@ -259,13 +259,8 @@ __global__ void __launch_bounds__(kQThreads) k_quotient(const uint8_t* __restric
         frc_t zn = z;
 #pragma unroll 1
         for (int s = 0; s < 12; s++) zn = zn.sqr();
-        frc_t n_inv = frc_t::one();
-        {
-            frc_t two = frc_t::one() + frc_t::one();
-            frc_t half = two.inverse();
-#pragma unroll 1
-            for (int s = 0; s < 12; s++) n_inv = n_inv * half;
-        }
+        frc_t n_inv = frc_t::zero();
+        n_inv.v[7] = 0x00100000u;  // 4096^-1 in Montgomery form: 2^-12 * 2^256 = 2^244
         y = total * n_inv * (zn - frc_t::one());
     }
     // quotient

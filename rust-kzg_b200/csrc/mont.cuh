@@ -335,12 +335,11 @@ struct __align__(16) Mont {
         }
         return acc;
     }
-    // a^(mod-2)
-    __device__ __noinline__ Mont inverse() const {
+    // a^(mod-2) (Fermat); kept as the cross-check of inverse()
+    __device__ __noinline__ Mont inverse_fermat() const {
         uint32_t e[N];
 #pragma unroll
         for (int i = 0; i < N; i++) e[i] = P::mod(i);
-        // subtract 2 with borrow (Fr's low word is 1)
         uint32_t borrow = 2;
 #pragma unroll
         for (int i = 0; i < N; i++) {
@@ -349,6 +348,71 @@ struct __align__(16) Mont {
             borrow = t < borrow ? 1u : 0u;
         }
         return pow_words(e);
+    }
+    // Modular inverse by the binary extended Euclid (right-shift) algorithm on the ALU pipe: ~1.5 * bits iterations
+    // of shifts / subtractions instead of ~1.5 * bits Montgomery multiplications -- several times lower latency than
+    // Fermat, which matters because every use is a latency-bound tail (compression, affine conversion, batch
+    // inversion).  Variable time: no secrets on this path.  0 -> 0 like blst_fr_eucl_inverse / blst_fp_inverse.
+    // Input is the Montgomery residue x = a R; the integer inverse t = x^-1 = a^-1 R^-1 is lifted back with two
+    // multiplications by R^2:  (t R^2 R^-1) R^2 R^-1 = a^-1 R.
+    __device__ __noinline__ Mont inverse() const {
+        if (is_zero()) return *this;
+        uint32_t u[N], w[N], x1[N], x2[N];  // invariants: x1 * x == u, x2 * x == w (mod m); w stays odd
+#pragma unroll
+        for (int i = 0; i < N; i++) { u[i] = v[i]; w[i] = P::mod(i); x1[i] = 0; x2[i] = 0; }
+        x1[0] = 1;
+        for (;;) {
+            uint32_t nz = 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) nz |= u[i];
+            if (nz == 0) break;
+            if ((u[0] & 1) == 0) {
+                // u /= 2, x1 /= 2 mod m
+#pragma unroll
+                for (int i = 0; i < N - 1; i++) u[i] = __funnelshift_r(u[i], u[i + 1], 1);
+                u[N - 1] >>= 1;
+                uint32_t odd = 0u - (x1[0] & 1), carry;
+                asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(x1[0]) : "r"(P::mod(0) & odd));
+#pragma unroll
+                for (int i = 1; i < N; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(x1[i]) : "r"(P::mod(i) & odd));
+                asm volatile("addc.u32 %0, 0, 0;" : "=r"(carry));
+#pragma unroll
+                for (int i = 0; i < N - 1; i++) x1[i] = __funnelshift_r(x1[i], x1[i + 1], 1);
+                x1[N - 1] = __funnelshift_r(x1[N - 1], carry, 1);
+            } else {
+                // both odd: make u the larger, then u -= w (even), x1 -= x2 mod m
+                bool lt = false;
+#pragma unroll
+                for (int i = N - 1; i >= 0; i--) {
+                    if (u[i] != w[i]) { lt = u[i] < w[i]; break; }
+                }
+                if (lt) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        uint32_t t = u[i]; u[i] = w[i]; w[i] = t;
+                        t = x1[i]; x1[i] = x2[i]; x2[i] = t;
+                    }
+                }
+                asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(u[0]) : "r"(w[0]));
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(u[i]) : "r"(w[i]));
+                asm volatile("subc.u32 %0, %0, %1;" : "+r"(u[N - 1]) : "r"(w[N - 1]));
+                uint32_t borrow;
+                asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(x1[0]) : "r"(x2[0]));
+#pragma unroll
+                for (int i = 1; i < N; i++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(x1[i]) : "r"(x2[i]));
+                asm volatile("subc.u32 %0, 0, 0;" : "=r"(borrow));
+                asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(x1[0]) : "r"(P::mod(0) & borrow));
+#pragma unroll
+                for (int i = 1; i < N - 1; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(x1[i]) : "r"(P::mod(i) & borrow));
+                asm volatile("addc.u32 %0, %0, %1;" : "+r"(x1[N - 1]) : "r"(P::mod(N - 1) & borrow));
+            }
+        }
+        // gcd = w = 1 (the modulus is prime), inverse = x2
+        Mont t;
+#pragma unroll
+        for (int i = 0; i < N; i++) t.v[i] = x2[i];
+        return (t * rr()) * rr();
     }
     __device__ __forceinline__ Mont to_mont() const { return *this * rr(); }  // canonical -> Montgomery
     __device__ __forceinline__ Mont from_mont() const {                        // Montgomery -> canonical

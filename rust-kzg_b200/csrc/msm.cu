@@ -356,6 +356,43 @@ __global__ void __launch_bounds__(kMargThreads) k_marginals(const uint8_t* __res
     }
 }
 
+// 6b': the same marginal sums for many groups (blob batches): S lanes per marginal instead of a CTA, so that the
+// tree steps waste few lanes -- with 64 groups x 40 marginals the CTA form spends most of its FMA-pipe time on
+// additions with the point at infinity.  One launch per axis; S = 2^log_s lanes sum count/S buckets each, then a
+// log_s-step shuffle tree inside the S-lane group.
+__global__ void __launch_bounds__(128) k_marginals_sub(const uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
+                                                       int nb, AxisPlan ap, int a, int log_s, size_t total_threads,
+                                                       uint8_t* __restrict__ marg) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int S = 1 << log_s;
+    const int wa = ap.w[a], sa = ap.sh[a];
+    const bool live = gid < total_threads;
+    size_t mi = (live ? gid : total_threads - 1) >> log_s;  // marginal index = g * 2^wa + v
+    int sub = (int)(gid & (S - 1));
+    size_t g = mi >> wa;
+    int v = (int)(mi & ((1 << wa) - 1));
+    const int count = nb >> wa;
+    xyzz_t acc = xyzz_t::inf();
+    if (live) {
+        for (int i = sub; i < count; i += S) {
+            int b = ((i >> sa) << (sa + wa)) | (v << sa) | (i & ((1 << sa) - 1));
+            size_t key = g * nb + b;
+            uint32_t s0 = task_base[key];
+            if (task_base[key + 1] > s0) {
+                xyzz_t part = load_xyzz(partials + (size_t)s0 * 192);
+                xyzz_add(acc, part);
+            }
+        }
+    }
+#pragma unroll 1
+    for (int d = S >> 1; d >= 1; d >>= 1) {
+        xyzz_t o = shfl_down_xyzz(acc, d);
+        if (sub + d >= S) o = xyzz_t::inf();
+        xyzz_add(acc, o);
+    }
+    if (live && sub == 0) store_xyzz(marg + ((g * 3 + a) * 32 + v) * 192, acc);
+}
+
 // 6c: one CTA per group, one warp per digit axis: weighted sum over the <= 32 marginals, scale by 2^sh, combine.
 __global__ void __launch_bounds__(96) k_group_finish(const uint8_t* __restrict__ marg, AxisPlan ap,
                                                      uint8_t* __restrict__ group_sums, uint8_t* __restrict__ out_jac) {
@@ -575,9 +612,24 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
             off += wa;
         }
     }
-    k_marginals<<<dim3(32, ap.D, (unsigned)groups), kMargThreads, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap,
-                                                                          (uint8_t*)chunk_sums_);
-    launches += 3;
+    if (groups * 32 * ap.D >= 2048) {
+        // many groups: lane-efficient sub-warp marginals, one launch per digit axis.  Slots of digit values that do
+        // not exist (v >= 2^w) must read as infinity (all-zero XYZZ).
+        B200_CUDA_CHECK(cudaMemsetAsync(chunk_sums_, 0, groups * 3 * 32 * 192, st));
+        for (int a = 0; a < ap.D; a++) {
+            int count = nb_ >> ap.w[a];
+            int log_s = 0;
+            while (log_s < 5 && (count >> log_s) > 16) log_s++;
+            size_t total_threads = (groups << ap.w[a]) << log_s;
+            k_marginals_sub<<<div_up(total_threads, 128), 128, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap, a, log_s,
+                                                                       total_threads, (uint8_t*)chunk_sums_);
+        }
+        launches += 2 + ap.D;
+    } else {
+        k_marginals<<<dim3(32, ap.D, (unsigned)groups), kMargThreads, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap,
+                                                                              (uint8_t*)chunk_sums_);
+        launches += 3;
+    }
     if (cfg_.fixed) {
         k_group_finish<<<(unsigned)groups, 96, 0, st>>>((const uint8_t*)chunk_sums_, ap, nullptr, (uint8_t*)out_dev);
         launches += 1;

@@ -159,6 +159,7 @@ FFTSettingsDev::~FFTSettingsDev() {
     cudaFree(brp_roots_);
     cudaFree(scratch_);
     cudaFree(scratch2_);
+    cudaFree(g1_work_);
 }
 
 void FFTSettingsDev::ensure_scratch(size_t elems) {

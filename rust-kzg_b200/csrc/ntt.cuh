@@ -32,6 +32,8 @@ public:
     void fft_fr(const void* in_dev, void* out_dev, size_t n, bool inverse, int batch, cudaStream_t stream);
     // DASExtension::das_fft_extension (blst/src/data_availability_sampling.rs:78-100): odds from evens, n = len(evens)
     void das_fft_extension(const void* evens_dev, void* odds_dev, size_t n, int batch, cudaStream_t stream);
+    // FFTG1::fft_g1 (blst/src/fft_g1.rs:53-83): batch transforms of n Jacobian points (blst_p1), device pointers
+    void fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n, bool inverse, int batch, cudaStream_t stream);
     int launches_last() const { return launches_; }
 
 private:
@@ -45,6 +47,8 @@ private:
     void* scratch_ = nullptr;
     void* scratch2_ = nullptr;
     size_t scratch_elems_ = 0;
+    void* g1_work_ = nullptr;
+    size_t g1_work_elems_ = 0;
     int launches_ = 0;
 };
 

@@ -21,6 +21,7 @@ __global__ void k_field_op(int op, uint8_t* out, const uint8_t* a, const uint8_t
         case 2: r = x - y; break;
         case 3: r = x.neg(); break;
         case 4: r = x.inverse(); break;
+        case 7: r = x.inverse_fermat(); break;
         case 5: r = x.to_mont(); break;
         default: r = x.from_mont(); break;
     }

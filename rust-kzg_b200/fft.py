@@ -55,6 +55,17 @@ class FFTSettings:
         _lib.check(_L().b200_das_fft_extension(self.h, _p(out), _p(evens), evens.shape[0]))
         return out
 
+    def fft_g1(self, points, inverse=False):
+        """FFTG1::fft_g1: (n,18) Jacobian points in and out"""
+        pts = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 18)
+        out = np.zeros_like(pts)
+        _lib.check(_L().b200_fft_g1(self.h, _p(out), _p(pts), pts.shape[0], bool(inverse)))
+        return out
+
+    def fft_g1_device(self, out_ptr, in_ptr, n, inverse=False, batch=1, stream=0):
+        _lib.check(_L().b200_fft_g1_device(self.h, C.c_void_p(out_ptr), C.c_void_p(in_ptr), n, int(inverse), batch,
+                                           C.c_void_p(stream)))
+
     def fft_fr_device(self, out_ptr, in_ptr, n, inverse=False, batch=1, stream=0):
         _lib.check(_L().b200_fft_fr_device(self.h, C.c_void_p(out_ptr), C.c_void_p(in_ptr), n, int(inverse), batch,
                                            C.c_void_p(stream)))

@@ -104,3 +104,37 @@ def test_das_extension_random(B, K, fs20, scale):
     data[1::2] = odds
     coeffs = fs20.fft_fr(data, True)
     assert not coeffs[width // 2:].any()
+
+
+@pytest.mark.parametrize("logn", [0, 1, 3, 6, 8])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_fft_g1_matches_oracle(B, K, oracle_settings, logn, inverse):
+    """FFTG1::fft_g1 vs the oracle's restatement of fft_g1_fast (kzg-bench/src/tests/fft_g1.rs); compressed bytes"""
+    n = 1 << logn
+    fs, ofs = B.FFTSettings(10), K.FFTSettings(10)
+    pts = oracle_settings.g1_lagrange_brp[100:100 + n].copy()
+    if n >= 8:
+        pts[3] = 0                          # a point at infinity
+        pts[5] = pts[4]                     # a repeated point
+    got = fs.fft_g1(pts, inverse)
+    exp = ofs.fft_g1(pts, inverse)
+    for i in range(n):
+        assert K.p1_compress(got[i]) == K.p1_compress(exp[i]), i
+    fs.close()
+
+
+def test_fft_g1_roundtrip_and_slow(B, K, oracle_settings):
+    fs, ofs = B.FFTSettings(6), K.FFTSettings(6)
+    pts = oracle_settings.g1_monomial[:64].copy()
+    fwd = fs.fft_g1(pts, False)
+    slow = ofs.fft_g1_slow(pts, False)
+    back = fs.fft_g1(fwd, True)
+    for i in range(64):
+        assert K.p1_compress(fwd[i]) == K.p1_compress(slow[i]), i
+        assert K.p1_compress(back[i]) == K.p1_compress(pts[i]), i
+    from rust_kzg_b200 import B200Error
+    with pytest.raises(B200Error, match="power-of-two"):
+        fs.fft_g1(pts[:12])
+    with pytest.raises(B200Error, match="longer than the available max width"):
+        fs.fft_g1(np.tile(pts, (2, 1)))
+    fs.close()
