@@ -268,12 +268,13 @@ def main():
                 "kernel": "k_accumulate", "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_step if acc_ms else None,
                 "peak_source": "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback",
                 "note": "the path is bound by the integer multiply pipe, not HBM (SURVEY.md 8d); see int_roofline"}
-    int_roofline = {"bound": "int32 multiply pipe (IMAD.WIDE)", "unit": "T multiply-adds/s",
+    int_roofline = {"bound": "FMA-heavy pipe (IMAD.WIDE.U32, 32x32+64 multiply-add)", "unit": "T multiply-adds/s",
                     "achieved": adds_per_launch * IMAD_PER_ADD / (acc_ms * 1e-3) / 1e12 if acc_ms else None,
-                    "peak": mb["imad_per_s"] / 1e12, "peak_source": "b200_microbench_int, measured in this run",
+                    "peak": mb["imad_per_s"] / 1e12, "peak_source": "b200_microbench_int (dependent-operand IMAD.WIDE loop), measured in this run",
                     "fp_mul_per_s_measured": mb["fpmul_per_s"],
-                    "note": "carry-chained IMAD.WIDE.X issues at half the plain IMAD.WIDE rate on sm_100a (measured), "
-                            "so 0.5 is the ceiling of a 32-bit-limb carry-chain multiplier"}
+                    "note": "achieved counts 3000 algorithmic multiply-adds per bucket addition (10 Fp mul x 300); every "
+                            "IMAD.WIDE form issues at 32/clk/SM on sm_100a (measured, with or without carry), ncu shows "
+                            "the FMA-heavy pipe 83% busy in k_accumulate (profiles/r01_accumulate_full.md)"}
     if int_roofline["achieved"]:
         int_roofline["frac"] = int_roofline["achieved"] / int_roofline["peak"]
 

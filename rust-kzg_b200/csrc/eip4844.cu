@@ -290,6 +290,36 @@ __global__ void __launch_bounds__(kQThreads) k_quotient(const uint8_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// compute_cells (kzg/src/das.rs:244-275, 618-629): cells = BRP( NTT_8192( INTT_4096( BRP(blob) ) || 0 ) ).
+// in: n x 4096 Montgomery; out: n x 8192, element brev12(i) of the low half, upper half zero
+__global__ void __launch_bounds__(256) k_cells_brp_in(const uint8_t* __restrict__ poly, uint8_t* __restrict__ out, size_t total) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    size_t blob = gid / kFieldElementsPerBlob, i = gid % kFieldElementsPerBlob;
+    size_t r = __brev((unsigned)i) >> 20;
+    fr_t v = load_field_ro<fr_t>(poly + gid * 32);
+    store_field(out + (blob * kFieldElementsPerBlob + r) * 32, v);
+}
+// zero-pad the 4096 monomial coefficients to 8192
+__global__ void __launch_bounds__(256) k_cells_pad(const uint8_t* __restrict__ mono, uint8_t* __restrict__ out, size_t total) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    size_t blob = gid / (2 * kFieldElementsPerBlob), i = gid % (2 * kFieldElementsPerBlob);
+    fr_t v = i < kFieldElementsPerBlob ? load_field_ro<fr_t>(mono + (blob * kFieldElementsPerBlob + i) * 32) : fr_t::zero();
+    store_field(out + gid * 32, v);
+}
+// bit-reverse (13 bits) and serialise: cell c, element e = position 64 c + e of the bit-reversed extended evaluation
+__global__ void __launch_bounds__(256) k_cells_out(const uint8_t* __restrict__ ext, uint8_t* __restrict__ cells, size_t total) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    size_t blob = gid / (2 * kFieldElementsPerBlob), i = gid % (2 * kFieldElementsPerBlob);
+    size_t r = __brev((unsigned)i) >> 19;
+    fr_t v = load_field_ro<fr_t>(ext + (blob * 2 * kFieldElementsPerBlob + r) * 32).from_mont();
+    uint32_t* o = reinterpret_cast<uint32_t*>(cells + gid * 32);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = __byte_perm(v.v[7 - k], 0, 0x0123);
+}
+
 static int env_int_local(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -348,7 +378,7 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
 
 KzgSettingsDev::~KzgSettingsDev() {
     cudaFree(lagrange_jac_); cudaFree(monomial_jac_); cudaFree(domain_); cudaFree(scalars_); cudaFree(poly_);
-    cudaFree(z_); cudaFree(y_); cudaFree(out_jac_);
+    cudaFree(z_); cudaFree(y_); cudaFree(out_jac_); cudaFree(cells_a_); cudaFree(cells_b_);
 }
 
 void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st) {
@@ -380,6 +410,25 @@ void KzgSettingsDev::compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes
         extra = 1;
     }
     launches_ = 4 + extra + msm_->launches_per_run();
+}
+
+void KzgSettingsDev::compute_cells(const uint8_t* blobs, int n, uint8_t* cells_out, int* status, cudaStream_t st) {
+    if (n < 1 || n > max_batch_) throw CudaError(-1, "blob batch exceeds the settings' capacity");
+    size_t total = (size_t)n * kFieldElementsPerBlob;
+    if (!cells_a_) {
+        cells_a_ = dev_alloc<uint8_t>((size_t)max_batch_ * 2 * kFieldElementsPerBlob * 32);
+        cells_b_ = dev_alloc<uint8_t>((size_t)max_batch_ * 2 * kFieldElementsPerBlob * 32);
+    }
+    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)poly_, status);
+    k_cells_brp_in<<<div_up(total, 256), 256, 0, st>>>((const uint8_t*)poly_, (uint8_t*)cells_a_, total);
+    B200_LAUNCH_CHECK();
+    fs_->fft_fr(cells_a_, cells_b_, kFieldElementsPerBlob, true, n, st);             // poly_lagrange_to_monomial
+    k_cells_pad<<<div_up(2 * total, 256), 256, 0, st>>>((const uint8_t*)cells_b_, (uint8_t*)cells_a_, 2 * total);
+    B200_LAUNCH_CHECK();
+    fs_->fft_fr(cells_a_, cells_b_, 2 * kFieldElementsPerBlob, false, n, st);
+    k_cells_out<<<div_up(2 * total, 256), 256, 0, st>>>((const uint8_t*)cells_b_, cells_out, 2 * total);
+    B200_LAUNCH_CHECK();
+    launches_ = 7;
 }
 
 void KzgSettingsDev::validate_commitments(const uint8_t* commitments48, int n, int* status, cudaStream_t st) {

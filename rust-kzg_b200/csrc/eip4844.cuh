@@ -44,6 +44,8 @@ public:
                         uint8_t* y32, int* status, cudaStream_t st);
     // G1::from_bytes + (is_inf || is_valid) of compute_blob_kzg_proof_rust (kzg/src/eip_4844.rs:556-558)
     void validate_commitments(const uint8_t* commitments48, int n, int* status, cudaStream_t st);
+    // cells of compute_cells_and_kzg_proofs(cells, None, blob) (kzg/src/das.rs:244-275): n x 128 cells x 2048 bytes
+    void compute_cells(const uint8_t* blobs, int n, uint8_t* cells_out, int* status, cudaStream_t st);
     int launches_last() const { return launches_; }
 
 private:
@@ -59,6 +61,8 @@ private:
     void* z_ = nullptr;         // max_batch Montgomery
     void* y_ = nullptr;         // max_batch Montgomery
     void* out_jac_ = nullptr;   // max_batch Jacobian results
+    void* cells_a_ = nullptr;   // max_batch * 8192 Fr ping-pong buffers (compute_cells), allocated on first use
+    void* cells_b_ = nullptr;
 };
 
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input

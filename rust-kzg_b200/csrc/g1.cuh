@@ -18,4 +18,8 @@ namespace cc {
 typedef fpc_t fp_t;
 #include "g1_body.inc"
 }  // namespace cc
+namespace cl {  // multiplier behind a call: small loop bodies for the instruction cache
+typedef Mont<FpParams, MONT_CALL> fp_t;
+#include "g1_body.inc"
+}  // namespace cl
 }  // namespace b200

@@ -133,8 +133,17 @@ struct FrParams {
 // reduction, table build, compression) are instruction-fetch bound with the unrolled form: a point addition is
 // ~80 KiB of straight-line code, far beyond the 32 KiB instruction cache, and runs at tens of cycles per
 // instruction when every line misses.
-template <class P, bool COMPACT = false>
+//
+// MODE 2 ("r28"): the same Montgomery product (same R, same packed operands and result) computed in radix 2^28:
+// with 28-bit limbs a 64-bit column absorbs all 2L partial products (< 2^56 each) of a CIOS sweep without overflow,
+// so every product is a carry-free IMAD.WIDE and the carries become shifts / adds on the ALU pipe.  R = 2^(32N) is
+// kept by making the last reduction step 32N - 28(L-1) bits wide (20 for Fp, 4 for Fr); the result is re-packed to
+// 32-bit limbs from that bit offset.  An experiment that did NOT pay off on B200 (IMAD.WIDE costs the same with or
+// without carries, and this form needs 406 of them instead of 302); kept as an independently derived cross-check.
+enum { MONT_UNROLLED = 0, MONT_COMPACT = 1, MONT_R28 = 2, MONT_CALL = 3 };
+template <class P, int MODE = MONT_UNROLLED>
 struct __align__(16) Mont {
+    static constexpr bool COMPACT = MODE == MONT_COMPACT;
     typedef P params_t;
     static constexpr int N = P::N;
     uint32_t v[N];
@@ -230,8 +239,99 @@ struct __align__(16) Mont {
 
     // Montgomery product a*b*R^-1 mod m, fully reduced.
     friend __device__ __forceinline__ Mont operator*(const Mont& a, const Mont& b) {
-        if (COMPACT) return mul_compact(a, b);
+        if (MODE == MONT_COMPACT) return mul_compact(a, b);
+        if (MODE == MONT_R28) return mul_r28(a, b, false);
+        if (MODE == MONT_CALL) return mul_call(a, b);
         return mul_unrolled(a, b);
+    }
+    // MODE 3: the unrolled multiplier behind a real call, so a point addition is ~10 calls instead of 60 KiB of inlined
+    // code (the accumulate loop body otherwise exceeds the instruction cache: ncu shows "no instruction" stalls)
+    static __device__ __noinline__ Mont mul_call(Mont a, Mont b) { return mul_unrolled(a, b); }
+    // ---- radix-2^28 product ------------------------------------------------------------------------------------
+    static constexpr int L28 = (32 * N + 27) / 28;            // limbs
+    static constexpr int LAST_BITS = 32 * N - 28 * (L28 - 1);  // width of the final reduction step
+    static constexpr uint32_t M28 = (1u << 28) - 1;
+    static __device__ __forceinline__ constexpr uint32_t mod28(int k) {  // limb k of the modulus in radix 2^28
+        int bit = 28 * k, w = bit >> 5, sh = bit & 31;
+        uint64_t two = (uint64_t)(w < N ? P::mod(w) : 0u) | ((uint64_t)(w + 1 < N ? P::mod(w + 1) : 0u) << 32);
+        return (uint32_t)(two >> sh) & M28;
+    }
+    static __device__ __forceinline__ void unpack28(uint32_t* l, const Mont& a) {
+#pragma unroll
+        for (int k = 0; k < L28; k++) {
+            const int bit = 28 * k, w = bit >> 5, sh = bit & 31;
+            uint32_t lo = a.v[w], hi = w + 1 < N ? a.v[w + 1] : 0u;
+            l[k] = (sh ? __funnelshift_r(lo, hi, sh) : lo) & M28;
+        }
+    }
+    // c + a * b as one carry-free IMAD.WIDE.U32 (explicit PTX: the C++ form makes nvcc treat constant operands as
+    // 64-bit and emit a redundant high-word add per product)
+    static __device__ __forceinline__ uint64_t madw(uint32_t a, uint32_t b, uint64_t c) {
+        return c + (uint64_t)a * b;
+    }
+    static __device__ __forceinline__ Mont mul_r28(const Mont& a, const Mont& b, bool square) {
+        uint32_t al[L28], bl[L28];
+        unpack28(al, a);
+        if (square) {
+#pragma unroll
+            for (int k = 0; k < L28; k++) bl[k] = al[k] << 1;  // doubled operand for the cross terms, < 2^29
+        } else {
+            unpack28(bl, b);
+        }
+        uint64_t c[L28 + 1];
+#pragma unroll
+        for (int k = 0; k <= L28; k++) c[k] = 0;
+#pragma unroll
+        for (int i = 0; i < L28; i++) {
+            // row i of the product (columns are relative to the current shift).  Squaring: only the pairs (i, j >= i),
+            // cross terms doubled; every pair (i', j') reaches absolute column i' + j' in row min(i', j') <= column.
+            if (square) {
+                c[i] = madw(al[i], al[i], c[i]);
+#pragma unroll
+                for (int j = i + 1; j < L28; j++) c[j] = madw(bl[j], al[i], c[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < L28; j++) c[j] = madw(al[j], bl[i], c[j]);
+            }
+            // reduction step: make the lowest column divisible by 2^bits, then drop it
+            const int bits = i == L28 - 1 ? LAST_BITS : 28;
+            const uint32_t mask = (1u << bits) - 1;
+            // (inline PTX keeps m a 32-bit value: otherwise nvcc widens the masked product to 64 bits and the row
+            // below becomes 64x64 multiplies)
+            uint32_t m, c0 = (uint32_t)c[0];
+            asm("mul.lo.u32 %0, %1, %2; and.b32 %0, %0, %3;" : "=r"(m) : "r"(c0), "r"(P::INV), "r"(mask));
+#pragma unroll
+            for (int j = 0; j < L28; j++) c[j] = madw(m, mod28(j), c[j]);
+            if (i < L28 - 1) {
+                c[1] += c[0] >> 28;
+#pragma unroll
+                for (int k = 0; k < L28; k++) c[k] = c[k + 1];
+                c[L28] = 0;
+            }
+        }
+        // value = (sum_k c[k] 2^(28k)) >> LAST_BITS : normalise the columns to 28-bit limbs, then re-pack to 32-bit words
+        uint32_t l[L28 + 2];
+#pragma unroll
+        for (int k = 0; k < L28; k++) {
+            l[k] = (uint32_t)c[k] & M28;
+            c[k + 1] += c[k] >> 28;
+        }
+        l[L28] = (uint32_t)c[L28] & M28;
+        l[L28 + 1] = (uint32_t)(c[L28] >> 28);
+        Mont r;
+#pragma unroll
+        for (int w = 0; w < N; w++) {
+            const int bit = LAST_BITS + 32 * w, k = bit / 28, off = bit % 28;
+            // 32 bits starting at limb k, offset off: off <= 24 for both fields, so two limbs always suffice... unless
+            // 28 - off < 4; take a third limb when needed
+            uint32_t x = l[k] >> off;
+            x |= l[k + 1] << (28 - off);
+            if (56 - off < 32) x |= l[k + 2] << (56 - off);
+            r.v[w] = x;
+        }
+        // T < 2 * mod: the bit above the packed words is zero for both fields (2p < 2^384, 2r < 2^256)
+        r.final_sub(0);
+        return r;
     }
     static __device__ __forceinline__ Mont mul_compact(const Mont& a, const Mont& b) {
         constexpr int H = N / 2;
@@ -319,7 +419,10 @@ struct __align__(16) Mont {
         r.final_sub(hi);
         return r;
     }
-    __device__ __forceinline__ Mont sqr() const { return *this * *this; }
+    __device__ __forceinline__ Mont sqr() const {
+        if (MODE == MONT_R28) return mul_r28(*this, *this, true);
+        return *this * *this;
+    }
 
     // a^e for a compile-time-known exponent array (little-endian u32 words), plain square-and-multiply
     template <int W>
@@ -422,10 +525,18 @@ struct __align__(16) Mont {
     }
 };
 
-typedef Mont<FpParams, false> fp_t;
-typedef Mont<FrParams, false> fr_t;
-typedef Mont<FpParams, true> fpc_t;  // compact-code variants, identical data layout
-typedef Mont<FrParams, true> frc_t;
+// All variants share one data layout and give identical results.  The default is the unrolled carry-chain
+// multiplier: measured on B200 (scripts/ubench, profiles/r01_multiplier_variants.md) EVERY IMAD.WIDE form issues at
+// 32/clk/SM, with or without carry, so the radix-2^28 variant -- more, carry-free products -- is slower (21.2 vs
+// 29.8 G Fp-mul/s) even though both keep the FMA-heavy pipe > 90 % busy.  It stays as a tested cross-check.
+typedef Mont<FpParams, MONT_UNROLLED> fp_t;
+typedef Mont<FrParams, MONT_UNROLLED> fr_t;
+typedef Mont<FpParams, MONT_COMPACT> fpc_t;   // compact-code carry-chain variant (cold kernels)
+typedef Mont<FrParams, MONT_COMPACT> frc_t;
+typedef Mont<FpParams, MONT_R28> fp28_t;      // radix-2^28 variant
+typedef Mont<FrParams, MONT_R28> fr28_t;
+typedef fp_t fpu_t;
+typedef fr_t fru_t;
 
 // load / store through 128-bit accesses (fp_t = 48 B = 3 x uint4, fr_t = 32 B = 2 x uint4)
 template <class F>

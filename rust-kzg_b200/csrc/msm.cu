@@ -2,6 +2,7 @@
 #include "msm.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "g1.cuh"
@@ -237,6 +238,26 @@ __global__ void __launch_bounds__(kAccThreads) k_accumulate(const uint8_t* __res
     store_xyzz(partials + (size_t)slot * 192, acc);
 }
 
+// variant with the field multiplication out of line (B200_ACC_CALL=1): same work, ~20x smaller loop body
+__global__ void __launch_bounds__(kAccThreads) k_accumulate_call(const uint8_t* __restrict__ table,
+                                                                 const uint32_t* __restrict__ entries,
+                                                                 const uint32_t* __restrict__ sorted_tasks,
+                                                                 const uint32_t* __restrict__ n_tasks_ptr,
+                                                                 uint8_t* __restrict__ partials) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *n_tasks_ptr) return;
+    uint32_t start = sorted_tasks[3 * t], len = sorted_tasks[3 * t + 1], slot = sorted_tasks[3 * t + 2];
+    cl::xyzz_t acc = cl::xyzz_t::inf();
+    const uint32_t* e = entries + start;
+    for (uint32_t k = 0; k < len; k++) {
+        uint32_t v = e[k];
+        cl::affine_t p = cl::load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
+        p.y = p.y.cneg(v >> 31);
+        cl::xyzz_add_affine(acc, p);
+    }
+    cl::store_xyzz(partials + (size_t)slot * 192, acc);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // 6: bucket reduction  S_g = sum_b (b+1) * B_b  per group.  A running sum over 2^(c-1) buckets is a chain of
 // dependent point additions (the reference's p1_integrate_buckets, kzg/src/msm/tiling_pippenger_ops.rs:21-45), and a
@@ -358,14 +379,17 @@ __global__ void __launch_bounds__(kMargThreads) k_marginals(const uint8_t* __res
 
 // 6b': the same marginal sums for many groups (blob batches): S lanes per marginal instead of a CTA, so that the
 // tree steps waste few lanes -- with 64 groups x 40 marginals the CTA form spends most of its FMA-pipe time on
-// additions with the point at infinity.  One launch per axis; S = 2^log_s lanes sum count/S buckets each, then a
+// additions with the point at infinity.  S = 2^log_s lanes sum count/S buckets each, then a
 // log_s-step shuffle tree inside the S-lane group.
 __global__ void __launch_bounds__(128) k_marginals_sub(const uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
-                                                       int nb, AxisPlan ap, int a, int log_s, size_t total_threads,
-                                                       uint8_t* __restrict__ marg) {
+                                                       int nb, AxisPlan ap, size_t groups, uint8_t* __restrict__ marg) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int S = 1 << log_s;
+    const int a = blockIdx.y;  // one grid row per digit axis: the axes are independent and run concurrently
     const int wa = ap.w[a], sa = ap.sh[a];
+    int log_s = 0;
+    while (log_s < 5 && ((nb >> wa) >> log_s) > 16) log_s++;
+    const int S = 1 << log_s;
+    const size_t total_threads = (groups << wa) << log_s;
     const bool live = gid < total_threads;
     size_t mi = (live ? gid : total_threads - 1) >> log_s;  // marginal index = g * 2^wa + v
     int sub = (int)(gid & (S - 1));
@@ -589,8 +613,13 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
             if (!prof_ev_[2 * prof_count_ + k]) B200_CUDA_CHECK(cudaEventCreate(&prof_ev_[2 * prof_count_ + k]));
         B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_], st));
     }
-    k_accumulate<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
-                                                                          task_base_ + nkeys, (uint8_t*)partials_);
+    static const bool acc_call = getenv("B200_ACC_CALL") && atoi(getenv("B200_ACC_CALL"));
+    if (acc_call)
+        k_accumulate_call<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
+                                                                                   task_base_ + nkeys, (uint8_t*)partials_);
+    else
+        k_accumulate<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
+                                                                              task_base_ + nkeys, (uint8_t*)partials_);
     if (prof) {
         B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_ + 1], st));
         prof_count_++;
@@ -616,15 +645,15 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
         // many groups: lane-efficient sub-warp marginals, one launch per digit axis.  Slots of digit values that do
         // not exist (v >= 2^w) must read as infinity (all-zero XYZZ).
         B200_CUDA_CHECK(cudaMemsetAsync(chunk_sums_, 0, groups * 3 * 32 * 192, st));
+        size_t max_threads = 0;
         for (int a = 0; a < ap.D; a++) {
-            int count = nb_ >> ap.w[a];
             int log_s = 0;
-            while (log_s < 5 && (count >> log_s) > 16) log_s++;
-            size_t total_threads = (groups << ap.w[a]) << log_s;
-            k_marginals_sub<<<div_up(total_threads, 128), 128, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap, a, log_s,
-                                                                       total_threads, (uint8_t*)chunk_sums_);
+            while (log_s < 5 && ((nb_ >> ap.w[a]) >> log_s) > 16) log_s++;
+            max_threads = std::max(max_threads, (groups << ap.w[a]) << log_s);
         }
-        launches += 2 + ap.D;
+        k_marginals_sub<<<dim3(div_up(max_threads, 128), ap.D), 128, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap, groups,
+                                                                             (uint8_t*)chunk_sums_);
+        launches += 3;
     } else {
         k_marginals<<<dim3(32, ap.D, (unsigned)groups), kMargThreads, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap,
                                                                               (uint8_t*)chunk_sums_);

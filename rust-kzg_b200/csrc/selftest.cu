@@ -8,7 +8,7 @@
 
 using namespace b200;
 
-// op + 16 selects the compact-code multiplier (same results required)
+// default: unrolled carry-chain multiplier; op + 16 selects the compact one, op + 32 the radix-2^28 one
 template <class F>
 __global__ void k_field_op(int op, uint8_t* out, const uint8_t* a, const uint8_t* b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -22,6 +22,7 @@ __global__ void k_field_op(int op, uint8_t* out, const uint8_t* a, const uint8_t
         case 3: r = x.neg(); break;
         case 4: r = x.inverse(); break;
         case 7: r = x.inverse_fermat(); break;
+        case 8: r = x.sqr(); break;
         case 5: r = x.to_mont(); break;
         default: r = x.from_mont(); break;
     }
@@ -49,22 +50,25 @@ __global__ void k_p1_compress(uint8_t* out, const uint8_t* p, size_t n) {
     affine_compress(out + i * 48, jac_to_affine(load_jac(p + i * 144)));
 }
 
-// 8 independent 32x32+64 multiply-add chains per thread: measures the IMAD.WIDE issue rate of the integer pipe
+// IMAD.WIDE issue rate of the FMA-heavy pipe: four independent carry chains of six 32x32+64 multiply-adds per thread
+// (exactly the instruction the Montgomery rows are made of).  The operands are loop-carried, so ptxas cannot hoist
+// the products (a loop-invariant product turns the loop into 64-bit additions and reports a bogus 2x rate).
 __global__ void __launch_bounds__(256) k_imad_bench(uint64_t* sink, uint32_t a, uint32_t b, int iters) {
-    uint64_t acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = threadIdx.x + k;
-    uint32_t x = a + threadIdx.x, y = b + blockIdx.x;
+    uint32_t A[4][12], v[12];
+    for (int c = 0; c < 4; c++)
+        for (int k = 0; k < 12; k++) A[c][k] = threadIdx.x + k + c;
+    for (int k = 0; k < 12; k++) v[k] = a + k * 77 + threadIdx.x;
+    uint32_t y = b + blockIdx.x;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r < 2; r++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(x), "r"(y));
+            for (int c = 0; c < 4; c++) Chain<6, false>::mad(A[c], v, y + c);
         }
     }
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) s ^= acc[k];
+    uint32_t s = 0;
+    for (int c = 0; c < 4; c++)
+        for (int k = 0; k < 12; k++) s ^= A[c][k];
     if (s == 0x1234567) sink[0] = s;
 }
 __global__ void __launch_bounds__(128) k_fpmul_bench(uint8_t* sink, int iters) {
@@ -94,8 +98,10 @@ static RustError field_op(int op, void* out, const void* a, const void* b, size_
         DevBuf<uint8_t> da(bytes), db(bytes), dout(bytes);
         B200_CUDA_CHECK(cudaMemcpy(da.p, a, bytes, cudaMemcpyHostToDevice));
         if (b) B200_CUDA_CHECK(cudaMemcpy(db.p, b, bytes, cudaMemcpyHostToDevice));
-        if (op & 16)
-            k_field_op<Mont<typename F::params_t, true>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);
+        if (op & 32)
+            k_field_op<Mont<typename F::params_t, MONT_R28>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);
+        else if (op & 16)
+            k_field_op<Mont<typename F::params_t, MONT_COMPACT>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);
         else
             k_field_op<F><<<div_up(n, 128), 128>>>(op, dout.p, da.p, b ? db.p : nullptr, n);
         B200_LAUNCH_CHECK();
@@ -154,7 +160,7 @@ RustError b200_microbench_int(double* imad_per_s, double* fpmul_per_s) {
             B200_CUDA_CHECK(cudaEventRecord(e1));
             B200_CUDA_CHECK(cudaEventSynchronize(e1));
             B200_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-            if (imad_per_s) *imad_per_s = (double)blocks * threads * iters * 64.0 / (ms * 1e-3);
+            if (imad_per_s) *imad_per_s = (double)blocks * threads * iters * 48.0 / (ms * 1e-3);
         }
         {
             int iters = 200, blocks = sms * 16, threads = 128;

@@ -44,6 +44,8 @@ def _L():
             "b200_compute_blob_kzg_proof_batch": (ci, [vp, vp, vp, sz, S]),
             "b200_blob_to_kzg_commitment_device": (ci, [vp, vp, sz, vp, S, vp]),
             "b200_compute_kzg_proof_device": (ci, [vp, vp, vp, vp, sz, ci, vp, S, vp]),
+            "compute_cells_and_kzg_proofs": (ci, [vp, vp, vp, S]),
+            "b200_compute_cells_batch": (ci, [vp, vp, sz, S]),
             "b200_kzg_launches": (ci, [S]),
             "b200_kzg_max_batch": (ci, [S]),
             "b200_selftest_sha256": (None, [vp, vp, sz, ci]),
@@ -161,6 +163,25 @@ class KZGSettings:
         if rc != C_KZG_OK:
             raise KzgError(rc, "compute_blob_kzg_proof")
         return proof.tobytes()
+
+    def compute_cells(self, blob):
+        """compute_cells_and_kzg_proofs(cells, NULL, blob): -> list of 128 cells (2048 bytes each)"""
+        b = _buf(blob, BYTES_PER_BLOB, "blob")
+        out = np.zeros(128 * 2048, np.uint8)
+        rc = _L().compute_cells_and_kzg_proofs(_p(out), None, _p(b), C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_cells_and_kzg_proofs")
+        raw = out.tobytes()
+        return [raw[i * 2048:(i + 1) * 2048] for i in range(128)]
+
+    def compute_cells_batch(self, blobs):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, BYTES_PER_BLOB)
+        n = blobs.shape[0]
+        out = np.zeros((n, 128, 2048), np.uint8)
+        rc = _L().b200_compute_cells_batch(_p(out), _p(blobs), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_cells_batch")
+        return out
 
     # ---- batched extensions: blobs (n,131072) u8, returns (n,48) u8 ...
     def blob_to_kzg_commitment_batch(self, blobs, out=None):

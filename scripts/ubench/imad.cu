@@ -155,6 +155,10 @@ int main() {
         printf("fpmul occ=%d (warps/SM=%d): %.2f G mul/s\n", occ, occ * 4, (double)blocks * th * iters * 4 / ms / 1e6);
         ms = timeit([&] { k_mul<fpc_t><<<blocks, th>>>((uint8_t*)sink, iters); });
         printf("fpmul-compact occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
+        ms = timeit([&] { k_mul<fp28_t><<<blocks, th>>>((uint8_t*)sink, iters); });
+        printf("fpmul-r28 occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
+        ms = timeit([&] { k_mul<fr28_t><<<blocks, th>>>((uint8_t*)sink, iters); });
+        printf("frmul-r28 occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
         ms = timeit([&] { k_mul<fr_t><<<blocks, th>>>((uint8_t*)sink, iters); });
         printf("frmul occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
         ms = timeit([&] { k_add<<<blocks, th>>>((uint8_t*)sink, iters * 10); });

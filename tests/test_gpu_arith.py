@@ -48,11 +48,15 @@ def test_field_ops_match_oracle(B, K, which):
     canon = np.array([[(v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(w)] for v in xs], dtype=np.uint64)
     assert np.array_equal(_field(B, which, 5, canon), a)
     assert np.array_equal(_field(B, which, 6, a), canon)
-    # the compact-code multiplier (op + 16) used by the latency-bound kernels must agree bit for bit
-    assert np.array_equal(_field(B, which, 16, a, b), omul(a, b))
-    assert np.array_equal(_field(B, which, 16, a, a), omul(a, a))
-    assert np.array_equal(_field(B, which, 16 + 5, canon), a)
-    assert np.array_equal(_field(B, which, 16 + 6, a), canon)
+    # the three multiplier variants (default unrolled carry chain, +16 compact carry chain, +32 radix-2^28) agree
+    for var in (16, 32):
+        assert np.array_equal(_field(B, which, var, a, b), omul(a, b))
+        assert np.array_equal(_field(B, which, var, a, a), omul(a, a))
+        assert np.array_equal(_field(B, which, var + 5, canon), a)
+        assert np.array_equal(_field(B, which, var + 6, a), canon)
+    # squaring has its own code path in the radix-2^28 multiplier
+    assert np.array_equal(_field(B, which, 32 + 8, a), omul(a, a))
+    assert np.array_equal(_field(B, which, 8, a), omul(a, a))
 
 
 @pytest.mark.parametrize("which", ["fp", "fr"])

@@ -212,3 +212,34 @@ def test_sha256_paths(B):
         msg = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
         assert eip4844.sha256(msg) == hashlib.sha256(msg).digest()
         assert eip4844.sha256(msg, portable=True) == hashlib.sha256(msg).digest()
+
+
+def test_compute_cells_vectors(B, ts, vectors, golden_blobs):
+    """the reference's NTT golden vectors (kzg-bench/src/test_vectors/compute_cells): INTT_4096 + NTT_8192 on the device"""
+    import hashlib
+    for c in vectors["compute_cells"]:
+        try:
+            cells = ts.compute_cells(_blob_of(c, golden_blobs))
+        except B.KzgError:
+            cells = None
+        if c["output"] is None:
+            assert cells is None, c["name"]
+            continue
+        assert [hashlib.sha256(x).hexdigest() for x in cells] == c["output"]["cell_sha256"], c["name"]
+        assert "0x" + cells[0].hex() == c["output"]["cell0"] and "0x" + cells[127].hex() == c["output"]["cell127"]
+
+
+def test_compute_cells_batch_and_proofs_refused(B, K, ts, oracle_settings):
+    import ctypes as C
+    rng = np.random.default_rng(77)
+    blobs = _rand_blobs(rng, 3)
+    out = ts.compute_cells_batch(blobs)
+    for i in range(3):
+        exp = K.compute_cells(blobs[i].tobytes(), oracle_settings)
+        assert out[i].tobytes() == b"".join(exp), i
+    # FK20 proofs are out of scope: a non-NULL proofs pointer is refused loudly (C_KZG_ERROR), never silently skipped
+    cells = np.zeros(128 * 2048, np.uint8)
+    proofs = np.zeros(128 * 48, np.uint8)
+    rc = B.lib().compute_cells_and_kzg_proofs(cells.ctypes.data_as(C.c_void_p), proofs.ctypes.data_as(C.c_void_p),
+                                              blobs[0].ctypes.data_as(C.c_void_p), C.byref(ts.c))
+    assert rc == 2
