@@ -144,12 +144,13 @@ B200_API C_KZG_RET compute_kzg_proof(KZGProof *proof_out, Bytes32 *y_out, const 
 /* blst/src/eip_4844.rs:274-291 */
 B200_API C_KZG_RET compute_blob_kzg_proof(KZGProof *out, const Blob *blob, const Bytes48 *commitment_bytes, const KZGSettings *s);
 
-/* EIP-7594 cells (the NTT half of compute_cells_and_kzg_proofs, kzg/src/das.rs:244-275; C ABI
- * kzg/src/eth/c_bindings.rs:134-199): cells = BRP(NTT_8192(INTT_4096(BRP(blob)))).  proofs must be NULL -- the FK20
- * proofs are outside this backend's path and a non-NULL proofs pointer returns C_KZG_ERROR. */
+/* EIP-7594 compute_cells_and_kzg_proofs (kzg/src/das.rs:244-292; C ABI kzg/src/eth/c_bindings.rs:134-199):
+ * cells = BRP(NTT_8192(INTT_4096(BRP(blob)))); proofs by FK20 (64 x NTT_128, 128 fixed-base lincombs of 64 points over
+ * x_ext_fft_columns, inverse + forward fft_g1 of size 128).  Either output pointer may be NULL, not both. */
 typedef struct { uint8_t bytes[2048]; } Cell;
 B200_API C_KZG_RET compute_cells_and_kzg_proofs(Cell *cells, KZGProof *proofs, const Blob *blob, const KZGSettings *s);
 B200_API C_KZG_RET b200_compute_cells_batch(Cell *cells, const Blob *blobs, size_t n, const KZGSettings *s);
+B200_API C_KZG_RET b200_compute_cell_proofs_batch(KZGProof *proofs, const Blob *blobs, size_t n, const KZGSettings *s);
 
 /* Batched extensions: n independent blobs in one launch sequence (BASELINE config 3: 64 blobs).  Any invalid
  * element makes the whole call return C_KZG_BADARGS.  n may exceed the context's batch capacity (chunked). */

@@ -56,6 +56,7 @@ def _load():
         "ko_compute_quotient": (ci, [vp, vp, vp, vp, vp]),
         "ko_compute_kzg_proof": (ci, [vp, vp, vp, vp, vp]), "ko_compute_blob_kzg_proof": (ci, [vp, vp, vp, vp]),
         "ko_compute_cells": (ci, [vp, vp, vp]),
+        "ko_compute_cells_and_kzg_proofs": (ci, [vp, vp, vp, vp]), "ko_settings_x_ext_fft_columns": (vp, [vp]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(lib, name)
@@ -416,3 +417,20 @@ def compute_cells(blob: bytes, s: KZGSettings):
         raise OracleError("Invalid scalar")
     b = out.tobytes()
     return [b[i * 2048:(i + 1) * 2048] for i in range(128)]
+
+
+def compute_cells_and_kzg_proofs(blob: bytes, s: KZGSettings, want_cells=True):
+    """-> (cells list or None, proofs list of 128 x 48 bytes)   (kzg/src/das.rs:244-292)"""
+    cells = np.zeros(128 * 2048, np.uint8) if want_cells else None
+    proofs = np.zeros(128 * 48, np.uint8)
+    if lib.ko_compute_cells_and_kzg_proofs(_p(cells) if want_cells else None, _p(proofs), _p(_blob(blob)), s.h):
+        raise OracleError("Invalid scalar")
+    pb = proofs.tobytes()
+    cb = cells.tobytes() if want_cells else None
+    return ([cb[i * 2048:(i + 1) * 2048] for i in range(128)] if want_cells else None,
+            [pb[i * 48:(i + 1) * 48] for i in range(128)])
+
+
+def x_ext_fft_columns(s: KZGSettings):
+    ptr = lib.ko_settings_x_ext_fft_columns(s.h)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(128, 64, 18)).copy()

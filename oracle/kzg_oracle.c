@@ -1015,6 +1015,7 @@ typedef struct {
     fft_settings_t *fs;                 /* scale 13 (eip_4844.rs:1072-1077) */
     p1_t *g1_lagrange_brp;              /* 4096, bit-reversed (eip_4844.rs:1070) */
     p1_t *g1_monomial;                  /* 4096 */
+    p1_t *x_ext_fft_columns;            /* [128 rows][64 offsets], built on first use (kzg_settings.rs:84-101) */
     int nthreads;
 } kzg_settings_t;
 
@@ -1068,7 +1069,7 @@ API void *ko_settings_fft(void *h) { return ((kzg_settings_t *)h)->fs; }
 API void ko_free_trusted_setup(void *h) {
     kzg_settings_t *s = (kzg_settings_t *)h;
     if (!s) return;
-    ko_fft_settings_free(s->fs); free(s->g1_lagrange_brp); free(s->g1_monomial); free(s);
+    ko_fft_settings_free(s->fs); free(s->g1_lagrange_brp); free(s->g1_monomial); free(s->x_ext_fft_columns); free(s);
 }
 
 /* bytes_to_blob (eip_4844.rs:867-880). returns 0 ok, 1 Err */
@@ -1234,5 +1235,88 @@ API int ko_compute_cells(uint8_t *cells_out, const uint8_t *blob, void *h) {
     ko_fft_fr(s->fs, ext, mono, 8192, 0, 1);
     for (size_t i = 0; i < 8192; i++) ko_fr_to_bendian(cells_out + 32 * brp_index(i, 13), &ext[i]);
     free(poly); free(brp); free(mono); free(ext);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* EIP-7594 cell proofs by FK20 (kzg/src/das.rs:244-292, 626-696; setup in blst/src/types/kzg_settings.rs:38-101) */
+#define CELL_SIZE 64
+#define FK_K 64      /* n / cell_size */
+#define FK_K2 128
+typedef struct { kzg_settings_t *s; size_t next; } fkjob_t;
+static void *fk_setup_worker(void *arg) {
+    fkjob_t *j = (fkjob_t *)arg;
+    kzg_settings_t *s = j->s;
+    const size_t n = 4096;
+    p1_t *x_ext = (p1_t *)calloc(FK_K2, sizeof(p1_t)), *points = (p1_t *)malloc(FK_K2 * sizeof(p1_t));
+    for (;;) {
+        size_t offset = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (offset >= CELL_SIZE) break;
+        size_t start = n - CELL_SIZE - 1 - offset;
+        memset(x_ext, 0, FK_K2 * sizeof(p1_t));
+        for (size_t i = 0; i + 1 < FK_K; i++) x_ext[i] = s->g1_monomial[start - i * CELL_SIZE];
+        /* toeplitz_part_1: fft_g1_fast over the zero-extended vector, roots stride = 8192 / 128 */
+        fft_g1_fast(points, FK_K2, x_ext, 1, s->fs->roots_of_unity, s->fs->max_width / FK_K2);
+        for (size_t row = 0; row < FK_K2; row++) s->x_ext_fft_columns[row * CELL_SIZE + offset] = points[row];
+    }
+    free(x_ext); free(points);
+    return NULL;
+}
+static void fk20_setup(kzg_settings_t *s) {
+    if (s->x_ext_fft_columns) return;
+    s->x_ext_fft_columns = (p1_t *)malloc(FK_K2 * CELL_SIZE * sizeof(p1_t));
+    fkjob_t job = {s, 0};
+    int nt = s->nthreads > 1 ? s->nthreads : 1;
+    if (nt > 64) nt = 64;
+    pthread_t th[64];
+    for (int i = 0; i < nt; i++) pthread_create(&th[i], NULL, fk_setup_worker, &job);
+    for (int i = 0; i < nt; i++) pthread_join(th[i], NULL);
+}
+API const p1_t *ko_settings_x_ext_fft_columns(void *h) { fk20_setup((kzg_settings_t *)h); return ((kzg_settings_t *)h)->x_ext_fft_columns; }
+
+/* toeplitz_coeffs_stride (kzg/src/das.rs:626-658) */
+static void toeplitz_coeffs_stride(fr_t *out, const fr_t *in, size_t n, size_t offset, size_t stride) {
+    size_t r = n / stride, l = stride, d = n - 1, d_minus_i = d - offset;
+    memset(out, 0, 2 * r * sizeof(fr_t));
+    out[0] = in[d_minus_i];
+    for (size_t j = 1; j < r - 1; j++) out[2 * r - j] = in[d_minus_i - j * l];
+}
+/* compute_cells_and_kzg_proofs (kzg/src/das.rs:244-292) through the byte-level wrapper; cells_out (128*2048 B) and
+ * proofs_out (128*48 B) may each be NULL but not both.  returns 0 ok, 1 Err */
+API int ko_compute_cells_and_kzg_proofs(uint8_t *cells_out, uint8_t *proofs_out, const uint8_t *blob, void *h) {
+    kzg_settings_t *s = (kzg_settings_t *)h;
+    if (!cells_out && !proofs_out) return 1;
+    const size_t n = 4096;
+    fr_t *poly = (fr_t *)malloc(n * sizeof(fr_t));
+    if (bytes_to_blob(poly, blob)) { free(poly); return 1; }
+    fr_t *brp = (fr_t *)calloc(2 * n, sizeof(fr_t)), *mono = (fr_t *)calloc(2 * n, sizeof(fr_t));
+    for (size_t i = 0; i < n; i++) brp[brp_index(i, 12)] = poly[i];
+    ko_fft_fr(s->fs, mono, brp, n, 1, 1);                       /* poly_lagrange_to_monomial; upper half stays zero */
+    if (cells_out) {
+        fr_t *ext = (fr_t *)malloc(2 * n * sizeof(fr_t));
+        ko_fft_fr(s->fs, ext, mono, 2 * n, 0, 1);
+        for (size_t i = 0; i < 2 * n; i++) ko_fr_to_bendian(cells_out + 32 * brp_index(i, 13), &ext[i]);
+        free(ext);
+    }
+    if (proofs_out) {
+        fk20_setup(s);
+        /* compute_fk20_proofs (:660-696) */
+        fr_t *coeffs = (fr_t *)malloc(FK_K2 * CELL_SIZE * sizeof(fr_t));   /* [row j][offset i] */
+        fr_t tc[FK_K2], tf[FK_K2];
+        for (size_t i = 0; i < CELL_SIZE; i++) {
+            toeplitz_coeffs_stride(tc, mono, n, i, CELL_SIZE);
+            ko_fft_fr(s->fs, tf, tc, FK_K2, 0, 1);
+            for (size_t j = 0; j < FK_K2; j++) coeffs[j * CELL_SIZE + i] = tf[j];
+        }
+        p1_t hext[FK_K2], hh[FK_K2], pr[FK_K2];
+        for (size_t j = 0; j < FK_K2; j++)   /* g1_lincomb_batch: one 64-term lincomb per row */
+            ko_g1_lincomb(&hext[j], s->x_ext_fft_columns + j * CELL_SIZE, coeffs + j * CELL_SIZE, CELL_SIZE, 1);
+        ko_fft_g1(s->fs, hh, hext, FK_K2, 1);
+        for (size_t j = FK_K; j < FK_K2; j++) p1_set_inf(&hh[j]);
+        ko_fft_g1(s->fs, pr, hh, FK_K2, 0);
+        for (size_t j = 0; j < FK_K2; j++) ko_p1_compress(proofs_out + 48 * brp_index(j, 7), &pr[j]);
+        free(coeffs);
+    }
+    free(poly); free(brp); free(mono);
     return 0;
 }

@@ -357,9 +357,7 @@ C_KZG_RET b200_compute_kzg_proof_device(void* proofs48_dev, void* y32_dev, const
         return C_KZG_OK;
     });
 }
-// kzg/src/eth/c_bindings.rs:134-199 (eip7594 macro) -> compute_cells_and_kzg_proofs.  Cells only: the FK20 proofs are
-// outside this backend's path, so proofs must be NULL, as the reference allows (cells Some,
-// proofs None, kzg/src/das.rs:244-252).
+// cells of compute_cells_and_kzg_proofs for n blobs (kzg/src/das.rs:244-275): cells = n x 128 x 2048 bytes
 C_KZG_RET b200_compute_cells_batch(Cell* cells, const Blob* blobs, size_t n, const KZGSettings* s) {
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
@@ -386,13 +384,43 @@ C_KZG_RET b200_compute_cells_batch(Cell* cells, const Blob* blobs, size_t n, con
         return rc;
     });
 }
+// FK20 proofs for n blobs: proofs = n x 128 x 48 bytes
+C_KZG_RET b200_compute_cell_proofs_batch(KZGProof* proofs, const Blob* blobs, size_t n, const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !proofs || !blobs) return C_KZG_BADARGS;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        const int cap = ctx->dev->fk20_batch(ctx->stream);
+        uint8_t* d_proofs = dev_alloc<uint8_t>((size_t)cap * 128 * 48);
+        C_KZG_RET rc = C_KZG_OK;
+        try {
+            for (size_t off = 0; off < n; off += cap) {
+                int m = (int)std::min<size_t>(cap, n - off);
+                B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
+                B200_CUDA_CHECK(cudaMemsetAsync(ctx->d_status, 0, m * sizeof(int), ctx->stream));
+                ctx->dev->compute_cell_proofs(ctx->d_blobs, m, d_proofs, ctx->d_status, ctx->stream);
+                B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status(), ctx->d_status, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                if (any_set(ctx->h_status(), m)) { rc = C_KZG_BADARGS; break; }
+                B200_CUDA_CHECK(cudaMemcpy(proofs + off * 128, d_proofs, (size_t)m * 128 * 48, cudaMemcpyDeviceToHost));
+            }
+        } catch (...) {
+            cudaFree(d_proofs);
+            throw;
+        }
+        cudaFree(d_proofs);
+        return rc;
+    });
+}
+// kzg/src/eth/c_bindings.rs:134-199 (eip7594 macro): either output may be NULL, not both (kzg/src/das.rs:250-252)
 C_KZG_RET compute_cells_and_kzg_proofs(Cell* cells, KZGProof* proofs, const Blob* blob, const KZGSettings* s) {
-    if (proofs) {
-        fprintf(stderr, "b200kzg: compute_cells_and_kzg_proofs: FK20 proofs are not implemented by this backend (pass proofs = NULL)\n");
-        return C_KZG_ERROR;
+    if (!cells && !proofs) return C_KZG_BADARGS;
+    if (cells) {
+        C_KZG_RET rc = b200_compute_cells_batch(cells, blob, 1, s);
+        if (rc != C_KZG_OK) return rc;
     }
-    if (!cells) return C_KZG_BADARGS;  // "Both cells & proofs cannot be none" (kzg/src/das.rs:250-252)
-    return b200_compute_cells_batch(cells, blob, 1, s);
+    if (proofs) return b200_compute_cell_proofs_batch(proofs, blob, 1, s);
+    return C_KZG_OK;
 }
 
 int b200_kzg_launches(const KZGSettings* s) {

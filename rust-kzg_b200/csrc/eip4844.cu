@@ -1,6 +1,7 @@
 // eip4844.cu -- device kernels and host driver of the batched EIP-4844 commitment / proof path.  See eip4844.cuh.
 #include "eip4844.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -320,6 +321,58 @@ __global__ void __launch_bounds__(256) k_cells_out(const uint8_t* __restrict__ e
     for (int k = 0; k < 8; k++) o[k] = __byte_perm(v.v[7 - k], 0, 0x0123);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// FK20 cell proofs (compute_fk20_proofs, kzg/src/das.rs:660-696; setup blst/src/types/kzg_settings.rs:38-101)
+constexpr int kCellSize = 64, kFkK = 64, kFkK2 = 128;
+
+// setup: x_ext[offset][t] = g1_monomial[4096 - 64 - 1 - offset - 64 t] for t < 63, infinity otherwise (Jacobian)
+__global__ void k_fk_gather_x(const uint8_t* __restrict__ monomial_jac, uint8_t* __restrict__ x_ext) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= kCellSize * kFkK2) return;
+    int offset = gid / kFkK2, t = gid % kFkK2;
+    uint4* dst = reinterpret_cast<uint4*>(x_ext + (size_t)gid * 144);
+    if (t < kFkK - 1) {
+        int src = (int)kFieldElementsPerBlob - kCellSize - 1 - offset - t * kCellSize;
+        const uint4* q = reinterpret_cast<const uint4*>(monomial_jac + (size_t)src * 144);
+#pragma unroll
+        for (int k = 0; k < 9; k++) dst[k] = q[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; k++) dst[k] = make_uint4(0, 0, 0, 0);
+    }
+}
+// setup: table[row * 64 + offset] = affine(points[offset][row])
+__global__ void __launch_bounds__(64) k_fk_table(const uint8_t* __restrict__ points_jac, uint8_t* __restrict__ table_aff) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= kCellSize * kFkK2) return;
+    int row = gid / kCellSize, offset = gid % kCellSize;
+    cc::jac_t p = cc::load_jac(points_jac + ((size_t)offset * kFkK2 + row) * 144);
+    cc::store_affine(table_aff + (size_t)gid * 96, cc::jac_to_affine(p));
+}
+// toeplitz_coeffs_stride (kzg/src/das.rs:626-658) for every (blob, offset): 128 Fr each
+__global__ void __launch_bounds__(256) k_fk_toeplitz(const uint8_t* __restrict__ mono, uint8_t* __restrict__ out, size_t total) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    size_t t = gid % kFkK2, bi = gid / kFkK2, i = bi % kCellSize, b = bi / kCellSize;
+    const size_t d = kFieldElementsPerBlob - 1;
+    fr_t v = fr_t::zero();
+    if (t == 0) {
+        v = load_field_ro<fr_t>(mono + (b * kFieldElementsPerBlob + d - i) * 32);
+    } else if (t > (size_t)kFkK2 - (kFkK - 1)) {  // t = 2r - j, j = 1 .. r-2
+        size_t j = kFkK2 - t;
+        v = load_field_ro<fr_t>(mono + (b * kFieldElementsPerBlob + d - i - j * kCellSize) * 32);
+    }
+    store_field(out + gid * 32, v);
+}
+// coeffs[j][i] = fft[(b, i)][j]: transpose into the MSM's scalar layout [vector = b*128 + j][i], canonical form
+__global__ void __launch_bounds__(256) k_fk_transpose(const uint8_t* __restrict__ fft, uint8_t* __restrict__ scalars, size_t total) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    size_t i = gid % kCellSize, vj = gid / kCellSize, j = vj % kFkK2, b = vj / kFkK2;
+    fr_t v = load_field_ro<fr_t>(fft + ((b * kCellSize + i) * kFkK2 + j) * 32).from_mont();
+    store_field(scalars + gid * 32, v);
+}
+
 static int env_int_local(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -379,6 +432,7 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
 KzgSettingsDev::~KzgSettingsDev() {
     cudaFree(lagrange_jac_); cudaFree(monomial_jac_); cudaFree(domain_); cudaFree(scalars_); cudaFree(poly_);
     cudaFree(z_); cudaFree(y_); cudaFree(out_jac_); cudaFree(cells_a_); cudaFree(cells_b_);
+    cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_);
 }
 
 void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st) {
@@ -429,6 +483,65 @@ void KzgSettingsDev::compute_cells(const uint8_t* blobs, int n, uint8_t* cells_o
     k_cells_out<<<div_up(2 * total, 256), 256, 0, st>>>((const uint8_t*)cells_b_, cells_out, 2 * total);
     B200_LAUNCH_CHECK();
     launches_ = 7;
+}
+
+void KzgSettingsDev::ensure_fk20(cudaStream_t st) {
+    if (fk_msm_) return;
+    fk_batch_ = std::max(1, std::min(max_batch_, env_int_local("B200_FK20_BATCH", 16)));
+    const int npts = kCellSize * kFkK2;  // 8192
+    uint8_t* x_ext = dev_alloc<uint8_t>((size_t)npts * 144);
+    uint8_t* points = dev_alloc<uint8_t>((size_t)npts * 144);
+    uint8_t* table = dev_alloc<uint8_t>((size_t)npts * 96);
+    k_fk_gather_x<<<div_up(npts, 128), 128, 0, st>>>((const uint8_t*)monomial_jac_, x_ext);
+    B200_LAUNCH_CHECK();
+    // toeplitz_part_1: 64 forward fft_g1 of size 128 over the zero-extended vectors (kzg_settings.rs:38-61)
+    fs_->fft_g1(x_ext, points, kFkK2, false, kCellSize, st);
+    k_fk_table<<<div_up(npts, 64), 64, 0, st>>>(points, table);
+    B200_LAUNCH_CHECK();
+    MsmConfig cfg;
+    cfg.c = env_int_local("B200_FK20_C", 8);
+    cfg.W = (256 + cfg.c - 1) / cfg.c;
+    cfg.fixed = true;
+    cfg.n = kCellSize;
+    cfg.max_batch = fk_batch_ * kFkK2;
+    cfg.L = 64;
+    cfg.bases_period = kFkK2;
+    fk_msm_.reset(new MsmEngine(cfg, table, false, st));
+    fk_a_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kCellSize * kFkK2 * 32);
+    fk_b_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kCellSize * kFkK2 * 32);
+    fk_pts_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kFkK2 * 144);
+    if (!cells_a_) {
+        cells_a_ = dev_alloc<uint8_t>((size_t)max_batch_ * 2 * kFieldElementsPerBlob * 32);
+        cells_b_ = dev_alloc<uint8_t>((size_t)max_batch_ * 2 * kFieldElementsPerBlob * 32);
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(x_ext); cudaFree(points); cudaFree(table);
+}
+
+void KzgSettingsDev::compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* proofs48, int* status, cudaStream_t st) {
+    ensure_fk20(st);
+    if (n < 1 || n > fk_batch_) throw CudaError(-1, "blob batch exceeds the FK20 capacity");
+    size_t total = (size_t)n * kFieldElementsPerBlob;
+    // polynomial in monomial form (poly_lagrange_to_monomial, kzg/src/das.rs:618-629)
+    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)poly_, status);
+    k_cells_brp_in<<<div_up(total, 256), 256, 0, st>>>((const uint8_t*)poly_, (uint8_t*)cells_a_, total);
+    B200_LAUNCH_CHECK();
+    fs_->fft_fr(cells_a_, cells_b_, kFieldElementsPerBlob, true, n, st);
+    // Toeplitz coefficient vectors and their 128-point transforms
+    size_t tt = (size_t)n * kCellSize * kFkK2;
+    k_fk_toeplitz<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)cells_b_, (uint8_t*)fk_a_, tt);
+    B200_LAUNCH_CHECK();
+    fs_->fft_fr(fk_a_, fk_b_, kFkK2, false, n * kCellSize, st);
+    k_fk_transpose<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)fk_b_, (uint8_t*)fk_a_, tt);
+    B200_LAUNCH_CHECK();
+    // g1_lincomb_batch: 128 lincombs of 64 fixed points per blob (kzg/src/das.rs:676-680)
+    fk_msm_->run(fk_a_, kCellSize, n * kFkK2, false, fk_pts_, st);
+    // h = inverse fft_g1, upper half := identity, forward fft_g1 (:682-695)
+    fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, true, n, st);
+    B200_CUDA_CHECK(cudaMemset2DAsync((uint8_t*)fk_pts_ + (size_t)kFkK * 144, (size_t)kFkK2 * 144, 0, (size_t)kFkK * 144, n, st));
+    fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, false, n, st);
+    launch_points_to_compressed(fk_pts_, proofs48, n * kFkK2, st, 7);  // reverse_bit_order(proofs) (:287)
+    launches_ = 8 + fk_msm_->launches_per_run() + 2 * 9;
 }
 
 void KzgSettingsDev::validate_commitments(const uint8_t* commitments48, int n, int* status, cudaStream_t st) {

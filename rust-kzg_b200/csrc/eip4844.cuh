@@ -46,9 +46,17 @@ public:
     void validate_commitments(const uint8_t* commitments48, int n, int* status, cudaStream_t st);
     // cells of compute_cells_and_kzg_proofs(cells, None, blob) (kzg/src/das.rs:244-275): n x 128 cells x 2048 bytes
     void compute_cells(const uint8_t* blobs, int n, uint8_t* cells_out, int* status, cudaStream_t st);
+    // FK20 proofs of compute_cells_and_kzg_proofs (kzg/src/das.rs:276-289, 660-696): n x 128 proofs x 48 bytes,
+    // n <= fk20_batch().  The 128 x 64 table of x_ext_fft_columns is built on first use.
+    void compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* proofs48, int* status, cudaStream_t st);
+    int fk20_batch(cudaStream_t st) { ensure_fk20(st); return fk_batch_; }
     int launches_last() const { return launches_; }
 
 private:
+    void ensure_fk20(cudaStream_t st);
+    std::unique_ptr<MsmEngine> fk_msm_;
+    int fk_batch_ = 0;
+    void *fk_a_ = nullptr, *fk_b_ = nullptr, *fk_pts_ = nullptr;
     int max_batch_;
     int launches_ = 0;
     std::unique_ptr<FFTSettingsDev> fs_;

@@ -21,7 +21,7 @@ static constexpr int kAccThreads = 128;  // accumulate CTA: 4 warps, one per SM 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalars, size_t n, size_t row_stride, size_t total,
                                                 int c, int W, int nb, int fixed, int mont, uint32_t* __restrict__ ctr,
-                                                uint32_t* __restrict__ entries) {
+                                                uint32_t* __restrict__ entries, size_t period, size_t period_n) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     size_t vec = gid / n, i = gid - vec * n;
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalar
             size_t key = group * nb + (mag - 1);
             if (SCATTER) {
                 uint32_t pos = atomicAdd(&ctr[key], 1u);
-                uint32_t idx = (uint32_t)(fixed ? (size_t)j * row_stride + i : i);
+                uint32_t idx = (uint32_t)(fixed ? (size_t)j * row_stride + (vec % period) * period_n + i : i);
                 entries[pos] = idx | (neg << 31);
             } else {
                 atomicAdd(&ctr[key], 1u);
@@ -474,12 +474,18 @@ __global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table,
 }
 
 // Jacobian -> 48-byte compressed (blst_p1_compress): one thread per point, one inversion each.
-__global__ void k_compress(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count) {
+// brp_bits > 0: output index = bit-reversal of the low brp_bits bits of i (reverse_bit_order per group of 2^brp_bits)
+__global__ void k_compress(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count, int brp_bits) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
+    int o = i;
+    if (brp_bits) {
+        int low = i & ((1 << brp_bits) - 1);
+        o = (i - low) | (int)(__brev((unsigned)low) >> (32 - brp_bits));
+    }
     cc::jac_t p = cc::load_jac(jac + (size_t)i * 144);
     cc::affine_t a = cc::jac_to_affine(p);
-    cc::affine_compress(out + (size_t)i * 48, a);
+    cc::affine_compress(out + (size_t)o * 48, a);
 }
 // sum of `count` Jacobian points by one warp (multi-GPU combine: count = number of ranks)
 __global__ void k_g1_sum(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count) {
@@ -506,9 +512,19 @@ void launch_g1_sum(const void* jac_dev, void* out_jac_dev, int count, cudaStream
     k_g1_sum<<<1, 32, 0, stream>>>((const uint8_t*)jac_dev, (uint8_t*)out_jac_dev, count);
     B200_LAUNCH_CHECK();
 }
-void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int count, cudaStream_t stream) {
+__global__ void k_jac_to_affine(const uint8_t* __restrict__ jac, uint8_t* __restrict__ aff, int count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    cc::store_affine(aff + (size_t)i * 96, cc::jac_to_affine(cc::load_jac(jac + (size_t)i * 144)));
+}
+void launch_jac_to_affine(const void* jac_dev, void* affine_dev, int count, cudaStream_t stream) {
     if (count <= 0) return;
-    k_compress<<<div_up(count, 32), 32, 0, stream>>>((const uint8_t*)jac_dev, out48_dev, count);
+    k_jac_to_affine<<<div_up(count, 64), 64, 0, stream>>>((const uint8_t*)jac_dev, (uint8_t*)affine_dev, count);
+    B200_LAUNCH_CHECK();
+}
+void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int count, cudaStream_t stream, int brp_bits) {
+    if (count <= 0) return;
+    k_compress<<<div_up(count, 32), 32, 0, stream>>>((const uint8_t*)jac_dev, out48_dev, count, brp_bits);
     B200_LAUNCH_CHECK();
 }
 
@@ -517,15 +533,17 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     if (cfg_.c < 2 || cfg_.c > 16 || cfg_.c * cfg_.W < 256) throw CudaError(-1, "MsmEngine: bad window configuration");
     if (cfg_.L < 1 || cfg_.L > 1024) throw CudaError(-1, "MsmEngine: bad task length");
     if (!cfg_.fixed) cfg_.max_batch = 1;
+    if (!cfg_.fixed || cfg_.bases_period < 1) cfg_.bases_period = 1;
+    const size_t table_points = (size_t)cfg_.bases_period * cfg_.n;
     nb_ = 1 << (cfg_.c - 1);
     groups_max_ = cfg_.fixed ? (size_t)cfg_.max_batch : (size_t)cfg_.W;
     keys_max_ = groups_max_ * nb_;
     entries_max_ = (size_t)cfg_.max_batch * cfg_.n * cfg_.W;
-    if (entries_max_ >= (1ull << 32) || (cfg_.fixed ? cfg_.n * cfg_.W : cfg_.n) >= (1ull << 31))
+    if (entries_max_ >= (1ull << 32) || (cfg_.fixed ? table_points * cfg_.W : cfg_.n) >= (1ull << 31))
         throw CudaError(-1, "MsmEngine: problem too large for 32-bit entry indices");
     tasks_max_ = entries_max_ / cfg_.L + keys_max_ + 1;
     size_t rows = cfg_.fixed ? cfg_.W : 1;
-    table_bytes_ = rows * cfg_.n * 96;
+    table_bytes_ = rows * table_points * 96;
     table_ = dev_alloc<uint8_t>(table_bytes_);
     counts_ = dev_alloc<uint32_t>(keys_max_ + 1);
     offsets_ = dev_alloc<uint32_t>(keys_max_ + 1);
@@ -539,9 +557,9 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     chunk_sums_ = dev_alloc<uint8_t>(groups_max_ * 3 * 32 * 192);  // marginal sums [group][axis][32]
     group_sums_ = dev_alloc<uint8_t>(groups_max_ * 192);
     if (points) {
-        B200_CUDA_CHECK(cudaMemcpyAsync(table_, points, cfg_.n * 96, host_points ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
+        B200_CUDA_CHECK(cudaMemcpyAsync(table_, points, table_points * 96, host_points ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
         if (cfg_.fixed && cfg_.W > 1) {
-            k_build_rows<<<div_up(cfg_.n, 128), 128, 0, stream>>>((uint8_t*)table_, cfg_.n, cfg_.W, cfg_.c);
+            k_build_rows<<<div_up(table_points, 128), 128, 0, stream>>>((uint8_t*)table_, table_points, cfg_.W, cfg_.c);
             B200_LAUNCH_CHECK();
         }
         B200_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -590,15 +608,16 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     B200_CUDA_CHECK(cudaMemsetAsync(counts_, 0, (nkeys + 1) * sizeof(uint32_t), st));
     B200_CUDA_CHECK(cudaMemsetAsync(size_hist_, 0, 3 * (L + 1) * sizeof(uint32_t), st));
     // 1 digits + histogram
-    k_digits<false><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, cfg_.n, total, c, W, nb_,
-                                                        cfg_.fixed, mont, counts_, nullptr);
+    const size_t row_stride = (size_t)cfg_.bases_period * cfg_.n;
+    k_digits<false><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, W, nb_,
+                                                        cfg_.fixed, mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n);
     launches++;
     // 2 offsets (and a working copy for the scatter cursors), task bases
     launches += scan_exclusive(counts_, nkeys, 0, offsets_, cursor_, scan_tmp_, st);
     launches += scan_exclusive(counts_, nkeys, (uint32_t)L, task_base_, nullptr, scan_tmp_, st);
     // 3 scatter
-    k_digits<true><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, cfg_.n, total, c, W, nb_,
-                                                       cfg_.fixed, mont, cursor_, entries_);
+    k_digits<true><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, W, nb_,
+                                                       cfg_.fixed, mont, cursor_, entries_, (size_t)cfg_.bases_period, cfg_.n);
     launches++;
     // 4 tasks sorted by length
     k_task_hist<<<div_up(nkeys, 256), 256, (L + 1) * sizeof(uint32_t), st>>>(counts_, nkeys, L, size_hist_);

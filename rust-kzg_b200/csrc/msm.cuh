@@ -36,6 +36,8 @@ struct MsmConfig {
     size_t n;       // points per scalar vector
     int max_batch;  // scalar vectors per call (FIXED only; VARIABLE uses 1)
     int L;          // max entries per accumulate task
+    int bases_period = 1;  // FIXED only: the table holds bases_period * n points per row and scalar vector v uses the
+                           // bases [(v mod bases_period) * n, +n)  (FK20: 128 rows of 64 points, kzg/src/msm/bgmw.rs:306-380)
 };
 
 class MsmEngine {
@@ -91,6 +93,7 @@ private:
 
 // helpers shared with other translation units
 void launch_g1_sum(const void* jac_dev, void* out_jac_dev, int count, cudaStream_t stream);
-void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int count, cudaStream_t stream);
+void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int count, cudaStream_t stream, int brp_bits = 0);
+void launch_jac_to_affine(const void* jac_dev, void* affine_dev, int count, cudaStream_t stream);
 
 }  // namespace b200

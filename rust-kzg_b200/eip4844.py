@@ -46,6 +46,7 @@ def _L():
             "b200_compute_kzg_proof_device": (ci, [vp, vp, vp, vp, sz, ci, vp, S, vp]),
             "compute_cells_and_kzg_proofs": (ci, [vp, vp, vp, S]),
             "b200_compute_cells_batch": (ci, [vp, vp, sz, S]),
+            "b200_compute_cell_proofs_batch": (ci, [vp, vp, sz, S]),
             "b200_kzg_launches": (ci, [S]),
             "b200_kzg_max_batch": (ci, [S]),
             "b200_selftest_sha256": (None, [vp, vp, sz, ci]),
@@ -173,6 +174,25 @@ class KZGSettings:
             raise KzgError(rc, "compute_cells_and_kzg_proofs")
         raw = out.tobytes()
         return [raw[i * 2048:(i + 1) * 2048] for i in range(128)]
+
+    def compute_cells_and_kzg_proofs(self, blob):
+        """-> (128 cells of 2048 bytes, 128 proofs of 48 bytes)"""
+        b = _buf(blob, BYTES_PER_BLOB, "blob")
+        cells, proofs = np.zeros(128 * 2048, np.uint8), np.zeros(128 * 48, np.uint8)
+        rc = _L().compute_cells_and_kzg_proofs(_p(cells), _p(proofs), _p(b), C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_cells_and_kzg_proofs")
+        cb, pb = cells.tobytes(), proofs.tobytes()
+        return [cb[i * 2048:(i + 1) * 2048] for i in range(128)], [pb[i * 48:(i + 1) * 48] for i in range(128)]
+
+    def compute_cell_proofs_batch(self, blobs):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, BYTES_PER_BLOB)
+        n = blobs.shape[0]
+        out = np.zeros((n, 128, 48), np.uint8)
+        rc = _L().b200_compute_cell_proofs_batch(_p(out), _p(blobs), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_cell_proofs_batch")
+        return out
 
     def compute_cells_batch(self, blobs):
         blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, BYTES_PER_BLOB)

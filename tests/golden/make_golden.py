@@ -67,6 +67,18 @@ for n, y in cases("compute_cells"):
                            all_sha256=hashlib.sha256(b"".join(unhex(c) for c in out)).hexdigest())
     cc.append(e)
 vec["compute_cells"] = cc
+fk = []
+for n, y in cases("compute_cells_and_kzg_proofs"):
+    out = y["output"]
+    e = dict(name=n, **blob_ref(y["input"]["blob"]))
+    if out is None:
+        e["output"] = None
+    else:
+        cells, proofs = out
+        assert len(cells) == 128 and len(proofs) == 128
+        e["output"] = dict(cells_sha256=hashlib.sha256(b"".join(unhex(c) for c in cells)).hexdigest(), proofs=proofs)
+    fk.append(e)
+vec["compute_cells_and_kzg_proofs"] = fk
 
 with open(os.path.join(OUT, "blobs.bin"), "wb") as f:
     for b in blobs:

@@ -229,17 +229,39 @@ def test_compute_cells_vectors(B, ts, vectors, golden_blobs):
         assert "0x" + cells[0].hex() == c["output"]["cell0"] and "0x" + cells[127].hex() == c["output"]["cell127"]
 
 
-def test_compute_cells_batch_and_proofs_refused(B, K, ts, oracle_settings):
-    import ctypes as C
+def test_compute_cells_batch(B, K, ts, oracle_settings):
     rng = np.random.default_rng(77)
     blobs = _rand_blobs(rng, 3)
     out = ts.compute_cells_batch(blobs)
     for i in range(3):
         exp = K.compute_cells(blobs[i].tobytes(), oracle_settings)
         assert out[i].tobytes() == b"".join(exp), i
-    # FK20 proofs are out of scope: a non-NULL proofs pointer is refused loudly (C_KZG_ERROR), never silently skipped
-    cells = np.zeros(128 * 2048, np.uint8)
-    proofs = np.zeros(128 * 48, np.uint8)
-    rc = B.lib().compute_cells_and_kzg_proofs(cells.ctypes.data_as(C.c_void_p), proofs.ctypes.data_as(C.c_void_p),
-                                              blobs[0].ctypes.data_as(C.c_void_p), C.byref(ts.c))
-    assert rc == 2
+
+
+def test_compute_cells_and_kzg_proofs_vectors(B, ts, vectors, golden_blobs):
+    """kzg-bench/src/test_vectors/compute_cells_and_kzg_proofs: cells + FK20 proofs on the device"""
+    import hashlib
+    for c in vectors["compute_cells_and_kzg_proofs"]:
+        try:
+            cells, proofs = ts.compute_cells_and_kzg_proofs(_blob_of(c, golden_blobs))
+        except B.KzgError:
+            cells = proofs = None
+        if c["output"] is None:
+            assert cells is None, c["name"]
+            continue
+        assert hashlib.sha256(b"".join(cells)).hexdigest() == c["output"]["cells_sha256"], c["name"]
+        assert ["0x" + p.hex() for p in proofs] == c["output"]["proofs"], c["name"]
+
+
+def test_cell_proofs_batch_matches_oracle(B, K, ts, oracle_settings):
+    rng = np.random.default_rng(78)
+    blobs = _rand_blobs(rng, 18)             # more than one FK20 chunk (capacity 16)
+    oracle_settings.set_threads(8)
+    out = ts.compute_cell_proofs_batch(blobs)
+    for i in (0, 15, 17):
+        _, exp = K.compute_cells_and_kzg_proofs(blobs[i].tobytes(), oracle_settings, want_cells=False)
+        assert out[i].tobytes() == b"".join(exp), i
+    oracle_settings.set_threads(1)
+    # both outputs NULL is rejected (kzg/src/das.rs:250-252)
+    import ctypes as C
+    assert B.lib().compute_cells_and_kzg_proofs(None, None, blobs[0].ctypes.data_as(C.c_void_p), C.byref(ts.c)) == 1

@@ -118,6 +118,21 @@ def test_compute_cells_vectors(K, oracle_settings, vectors, golden_blobs):
         assert [hashlib.sha256(x).hexdigest() for x in cells] == c["output"]["cell_sha256"]
 
 
+def test_compute_cells_and_kzg_proofs_vectors(K, setup_text, vectors, golden_blobs):
+    """FK20 (kzg/src/das.rs:660-696): cells and all 128 proofs of every golden case"""
+    s = K.KZGSettings(setup_text, nthreads=8)
+    for c in vectors["compute_cells_and_kzg_proofs"]:
+        try:
+            cells, proofs = K.compute_cells_and_kzg_proofs(_blob(c, golden_blobs), s)
+        except K.OracleError:
+            cells = proofs = None
+        if c["output"] is None:
+            assert cells is None, c["name"]
+            continue
+        assert hashlib.sha256(b"".join(cells)).hexdigest() == c["output"]["cells_sha256"], c["name"]
+        assert ["0x" + p.hex() for p in proofs] == c["output"]["proofs"], c["name"]
+
+
 def test_commitment_and_proof_kats(K, oracle_settings, kats):
     k = kats["commitment_kat"]
     assert "0x" + K.blob_to_kzg_commitment(H(k["blob0"]) + bytes(131072 - 32), oracle_settings).hex() == k["commitment"]
