@@ -27,19 +27,30 @@ namespace {
 
 constexpr size_t kG1 = 4096, kG2 = 65;
 
-struct KzgCtx {
-    std::mutex mu;
+// one staging lane: stream, device buffers for a chunk of up to max_batch blobs, pinned host buffers for the results
+struct Stage {
     cudaStream_t stream = nullptr, side = nullptr;
     cudaEvent_t ev_in = nullptr, ev_side = nullptr;
-    std::unique_ptr<KzgSettingsDev> dev;
-    int max_batch = 0;
-    // device staging
     uint8_t *d_blobs = nullptr, *d_z = nullptr, *d_comm = nullptr, *d_out48 = nullptr, *d_y32 = nullptr;
     int *d_status = nullptr, *d_status2 = nullptr;
-    // pinned host staging for the small results
-    uint8_t* h_small = nullptr;  // [48 * mb][32 * mb][int * mb][int * mb][32 * mb (z)]
-    ~KzgCtx() {
-        dev.reset();
+    uint8_t* h_small = nullptr;  // pinned: [48 * mb out][32 * mb y][int * mb][int * mb][32 * mb z]
+    int mb = 0;
+    void init(int max_batch) {
+        mb = max_batch;
+        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+        d_blobs = dev_alloc<uint8_t>((size_t)mb * kBytesPerBlob);
+        d_z = dev_alloc<uint8_t>((size_t)mb * 32);
+        d_comm = dev_alloc<uint8_t>((size_t)mb * 48);
+        d_out48 = dev_alloc<uint8_t>((size_t)mb * 48);
+        d_y32 = dev_alloc<uint8_t>((size_t)mb * 32);
+        d_status = dev_alloc<int>(mb);
+        d_status2 = dev_alloc<int>(mb);
+        B200_CUDA_CHECK(cudaMallocHost((void**)&h_small, (size_t)mb * 120 + 64));
+    }
+    ~Stage() {
         cudaFree(d_blobs); cudaFree(d_z); cudaFree(d_comm); cudaFree(d_out48); cudaFree(d_y32); cudaFree(d_status); cudaFree(d_status2);
         if (h_small) cudaFreeHost(h_small);
         if (ev_in) cudaEventDestroy(ev_in);
@@ -48,11 +59,51 @@ struct KzgCtx {
         if (side) cudaStreamDestroy(side);
     }
     uint8_t* h_out48() { return h_small; }
-    uint8_t* h_y32() { return h_small + 48 * (size_t)max_batch; }
-    int* h_status() { return reinterpret_cast<int*>(h_small + 80 * (size_t)max_batch); }
-    int* h_status2() { return h_status() + max_batch; }
-    uint8_t* h_z() { return h_small + 88 * (size_t)max_batch; }
+    uint8_t* h_y32() { return h_small + 48 * (size_t)mb; }
+    int* h_status() { return reinterpret_cast<int*>(h_small + 80 * (size_t)mb); }
+    int* h_status2() { return h_status() + mb; }
+    uint8_t* h_z() { return h_small + 88 * (size_t)mb; }
 };
+
+struct KzgCtx {
+    std::mutex mu;
+    std::unique_ptr<KzgSettingsDev> dev;
+    int max_batch = 0;
+    Stage stage[KzgSettingsDev::kLanes];
+    // lane 0 aliases used by the single-lane paths (cells, FK20)
+    cudaStream_t stream = nullptr;
+    uint8_t* d_blobs = nullptr;
+    int* d_status = nullptr;
+    int* h_status() { return stage[0].h_status(); }
+    ~KzgCtx() { dev.reset(); }
+};
+
+// Run `n` items in chunks of at most `cap`, alternating between the two lanes: chunk k+1 is enqueued (copies, host
+// hashing, kernels) while chunk k is still executing, and a lane is drained only when it is needed again.
+// launch(lane, off, m) enqueues a chunk; finish(lane, off, m) runs after that lane's stream has been synchronised.
+template <class Launch, class Finish>
+C_KZG_RET run_chunks(KzgCtx& ctx, size_t n, size_t cap, Launch&& launch, Finish&& finish) {
+    struct Pending { bool live = false; size_t off = 0; int m = 0; } pend[KzgSettingsDev::kLanes];
+    C_KZG_RET rc = C_KZG_OK;
+    auto drain = [&](int lane) {
+        if (!pend[lane].live) return;
+        B200_CUDA_CHECK(cudaStreamSynchronize(ctx.stage[lane].stream));
+        pend[lane].live = false;
+        if (rc == C_KZG_OK) rc = finish(lane, pend[lane].off, pend[lane].m);
+    };
+    size_t k = 0;
+    for (size_t off = 0; off < n && rc == C_KZG_OK; off += cap, k++) {
+        int lane = (int)(k % KzgSettingsDev::kLanes);
+        drain(lane);
+        if (rc != C_KZG_OK) break;
+        int m = (int)std::min(cap, n - off);
+        launch(lane, off, m);
+        pend[lane] = {true, off, m};
+    }
+    // drain in submission order
+    for (int d = 0; d < KzgSettingsDev::kLanes; d++) drain((int)((k + d) % KzgSettingsDev::kLanes));
+    return rc;
+}
 
 std::mutex g_reg_mu;
 std::map<const void*, std::shared_ptr<KzgCtx>> g_registry;
@@ -77,19 +128,11 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
         ctx->max_batch = env_int("B200_KZG_MAX_BATCH", 64);
         if (ctx->max_batch < 1) ctx->max_batch = 1;
         const int mb = ctx->max_batch;
-        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
-        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming));
-        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming));
+        for (Stage& st : ctx->stage) st.init(mb);
+        ctx->stream = ctx->stage[0].stream;
+        ctx->d_blobs = ctx->stage[0].d_blobs;
+        ctx->d_status = ctx->stage[0].d_status;
         ctx->dev.reset(new KzgSettingsDev(g1_monomial, g1_lagrange, mb, ctx->stream));
-        ctx->d_blobs = dev_alloc<uint8_t>((size_t)mb * kBytesPerBlob);
-        ctx->d_z = dev_alloc<uint8_t>((size_t)mb * 32);
-        ctx->d_comm = dev_alloc<uint8_t>((size_t)mb * 48);
-        ctx->d_out48 = dev_alloc<uint8_t>((size_t)mb * 48);
-        ctx->d_y32 = dev_alloc<uint8_t>((size_t)mb * 32);
-        ctx->d_status = dev_alloc<int>(mb);
-        ctx->d_status2 = dev_alloc<int>(mb);
-        B200_CUDA_CHECK(cudaMallocHost((void**)&ctx->h_small, (size_t)mb * 120 + 64));
     } catch (const CudaError& e) {
         if (e.code != 1) fprintf(stderr, "b200kzg: load_trusted_setup failed: %s\n", e.what());
         return e.code == 1 ? C_KZG_BADARGS : C_KZG_ERROR;
@@ -252,18 +295,21 @@ C_KZG_RET b200_blob_to_kzg_commitment_batch(KZGCommitment* out, const Blob* blob
         auto ctx = find_ctx(s);
         if (!ctx || !out || !blobs) return C_KZG_BADARGS;
         std::lock_guard<std::mutex> lk(ctx->mu);
-        for (size_t off = 0; off < n; off += ctx->max_batch) {
-            int m = (int)std::min<size_t>(ctx->max_batch, n - off);
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
-            B200_CUDA_CHECK(cudaMemsetAsync(ctx->d_status, 0, m * sizeof(int), ctx->stream));
-            ctx->dev->blob_to_commitments(ctx->d_blobs, m, ctx->d_out48, ctx->d_status, ctx->stream);
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_out48(), ctx->d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, ctx->stream));
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status(), ctx->d_status, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            if (any_set(ctx->h_status(), m)) return C_KZG_BADARGS;
-            memcpy(out + off, ctx->h_out48(), (size_t)m * 48);
-        }
-        return C_KZG_OK;
+        return run_chunks(*ctx, n, ctx->max_batch,
+            [&](int lane, size_t off, int m) {
+                Stage& g = ctx->stage[lane];
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
+                B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
+                ctx->dev->blob_to_commitments(g.d_blobs, m, g.d_out48, g.d_status, g.stream, lane);
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_out48(), g.d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, g.stream));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_status(), g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+            },
+            [&](int lane, size_t off, int m) -> C_KZG_RET {
+                Stage& g = ctx->stage[lane];
+                if (any_set(g.h_status(), m)) return C_KZG_BADARGS;
+                memcpy(out + off, g.h_out48(), (size_t)m * 48);
+                return C_KZG_OK;
+            });
     });
 }
 
@@ -273,21 +319,24 @@ C_KZG_RET b200_compute_kzg_proof_batch(KZGProof* proofs, Bytes32* ys, const Blob
         auto ctx = find_ctx(s);
         if (!ctx || !proofs || !ys || !blobs || !zs) return C_KZG_BADARGS;
         std::lock_guard<std::mutex> lk(ctx->mu);
-        for (size_t off = 0; off < n; off += ctx->max_batch) {
-            int m = (int)std::min<size_t>(ctx->max_batch, n - off);
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_z, zs + off, (size_t)m * 32, cudaMemcpyHostToDevice, ctx->stream));
-            B200_CUDA_CHECK(cudaMemsetAsync(ctx->d_status, 0, m * sizeof(int), ctx->stream));
-            ctx->dev->compute_proofs(ctx->d_blobs, ctx->d_z, 0, m, ctx->d_out48, ctx->d_y32, ctx->d_status, ctx->stream);
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_out48(), ctx->d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, ctx->stream));
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_y32(), ctx->d_y32, (size_t)m * 32, cudaMemcpyDeviceToHost, ctx->stream));
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status(), ctx->d_status, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            if (any_set(ctx->h_status(), m)) return C_KZG_BADARGS;
-            memcpy(proofs + off, ctx->h_out48(), (size_t)m * 48);
-            memcpy(ys + off, ctx->h_y32(), (size_t)m * 32);
-        }
-        return C_KZG_OK;
+        return run_chunks(*ctx, n, ctx->max_batch,
+            [&](int lane, size_t off, int m) {
+                Stage& g = ctx->stage[lane];
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_z, zs + off, (size_t)m * 32, cudaMemcpyHostToDevice, g.stream));
+                B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
+                ctx->dev->compute_proofs(g.d_blobs, g.d_z, 0, m, g.d_out48, g.d_y32, g.d_status, g.stream, lane);
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_out48(), g.d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, g.stream));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_y32(), g.d_y32, (size_t)m * 32, cudaMemcpyDeviceToHost, g.stream));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_status(), g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+            },
+            [&](int lane, size_t off, int m) -> C_KZG_RET {
+                Stage& g = ctx->stage[lane];
+                if (any_set(g.h_status(), m)) return C_KZG_BADARGS;
+                memcpy(proofs + off, g.h_out48(), (size_t)m * 48);
+                memcpy(ys + off, g.h_y32(), (size_t)m * 32);
+                return C_KZG_OK;
+            });
     });
 }
 
@@ -297,30 +346,33 @@ C_KZG_RET b200_compute_blob_kzg_proof_batch(KZGProof* out, const Blob* blobs, co
         auto ctx = find_ctx(s);
         if (!ctx || !out || !blobs || !commitments) return C_KZG_BADARGS;
         std::lock_guard<std::mutex> lk(ctx->mu);
-        for (size_t off = 0; off < n; off += ctx->max_batch) {
-            int m = (int)std::min<size_t>(ctx->max_batch, n - off);
-            // commitments first: their validation (decode + subgroup test) runs on the side stream under everything else
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_comm, commitments + off, (size_t)m * 48, cudaMemcpyHostToDevice, ctx->stream));
-            B200_CUDA_CHECK(cudaMemsetAsync(ctx->d_status, 0, m * sizeof(int), ctx->stream));
-            B200_CUDA_CHECK(cudaMemsetAsync(ctx->d_status2, 0, m * sizeof(int), ctx->stream));
-            B200_CUDA_CHECK(cudaEventRecord(ctx->ev_in, ctx->stream));
-            B200_CUDA_CHECK(cudaStreamWaitEvent(ctx->side, ctx->ev_in, 0));
-            ctx->dev->validate_commitments(ctx->d_comm, m, ctx->d_status2, ctx->side);
-            B200_CUDA_CHECK(cudaEventRecord(ctx->ev_side, ctx->side));
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
-            // the hash chain runs on the host while the blobs cross PCIe
-            challenge_hash_many(ctx->h_z(), (const uint8_t*)(blobs + off), (const uint8_t*)(commitments + off), m);
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_z, ctx->h_z(), (size_t)m * 32, cudaMemcpyHostToDevice, ctx->stream));
-            ctx->dev->compute_proofs(ctx->d_blobs, ctx->d_z, 1, m, ctx->d_out48, nullptr, ctx->d_status, ctx->stream);
-            B200_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_out48(), ctx->d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, ctx->stream));
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status(), ctx->d_status, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status2(), ctx->d_status2, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            if (any_set(ctx->h_status(), m) || any_set(ctx->h_status2(), m)) return C_KZG_BADARGS;
-            memcpy(out + off, ctx->h_out48(), (size_t)m * 48);
-        }
-        return C_KZG_OK;
+        return run_chunks(*ctx, n, ctx->max_batch,
+            [&](int lane, size_t off, int m) {
+                Stage& g = ctx->stage[lane];
+                // commitments first: their validation (decode + subgroup test) runs on the side stream under everything else
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_comm, commitments + off, (size_t)m * 48, cudaMemcpyHostToDevice, g.stream));
+                B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
+                B200_CUDA_CHECK(cudaMemsetAsync(g.d_status2, 0, m * sizeof(int), g.stream));
+                B200_CUDA_CHECK(cudaEventRecord(g.ev_in, g.stream));
+                B200_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.ev_in, 0));
+                ctx->dev->validate_commitments(g.d_comm, m, g.d_status2, g.side);
+                B200_CUDA_CHECK(cudaEventRecord(g.ev_side, g.side));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
+                // the hash chain runs on the host while the blobs cross PCIe (and the other lane computes)
+                challenge_hash_many(g.h_z(), (const uint8_t*)(blobs + off), (const uint8_t*)(commitments + off), m);
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_z, g.h_z(), (size_t)m * 32, cudaMemcpyHostToDevice, g.stream));
+                ctx->dev->compute_proofs(g.d_blobs, g.d_z, 1, m, g.d_out48, nullptr, g.d_status, g.stream, lane);
+                B200_CUDA_CHECK(cudaStreamWaitEvent(g.stream, g.ev_side, 0));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_out48(), g.d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, g.stream));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_status(), g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_status2(), g.d_status2, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+            },
+            [&](int lane, size_t off, int m) -> C_KZG_RET {
+                Stage& g = ctx->stage[lane];
+                if (any_set(g.h_status(), m) || any_set(g.h_status2(), m)) return C_KZG_BADARGS;
+                memcpy(out + off, g.h_out48(), (size_t)m * 48);
+                return C_KZG_OK;
+            });
     });
 }
 

@@ -117,8 +117,7 @@ RustError b200_msm_prepared_batch(void* msm, blst_p1 out[], size_t npoints, cons
             return;
         }
         h->ensure_staging((size_t)batch * npoints, batch);
-        B200_CUDA_CHECK(cudaMemcpyAsync(h->scalars_dev, scalars, (size_t)batch * npoints * 32, cudaMemcpyHostToDevice, h->stream));
-        h->eng->run(h->scalars_dev, npoints, batch, true, h->out_dev, h->stream);
+        h->eng->run(h->scalars_dev, npoints, batch, true, h->out_dev, h->stream, scalars);
         B200_CUDA_CHECK(cudaMemcpyAsync(out, h->out_dev, (size_t)batch * 144, cudaMemcpyDeviceToHost, h->stream));
         B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     });

@@ -408,15 +408,17 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
         cfg.n = n;
         cfg.max_batch = max_batch;
         cfg.L = env_int_local("B200_BLOB_L", 64);
-        msm_.reset(new MsmEngine(cfg, aff_brp, false, st));
+        for (Lane& ln : lanes_) {
+            ln.msm.reset(new MsmEngine(cfg, aff_brp, false, st));
+            ln.scalars = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
+            ln.poly = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
+            ln.z = dev_alloc<uint8_t>((size_t)max_batch * 32);
+            ln.y = dev_alloc<uint8_t>((size_t)max_batch * 32);
+            ln.out_jac = dev_alloc<uint8_t>((size_t)max_batch * 144);
+        }
         // the 4096 domain = first half of the bit-reversed 8192 roots (kzg/src/eip_4844.rs:463, 976)
         domain_ = dev_alloc<uint8_t>((size_t)n * 32);
         B200_CUDA_CHECK(cudaMemcpyAsync(domain_, fs_->brp_roots_dev(), (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
-        scalars_ = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
-        poly_ = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
-        z_ = dev_alloc<uint8_t>((size_t)max_batch * 32);
-        y_ = dev_alloc<uint8_t>((size_t)max_batch * 32);
-        out_jac_ = dev_alloc<uint8_t>((size_t)max_batch * 144);
         B200_CUDA_CHECK(cudaFuncSetAttribute(k_quotient, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(kFieldElementsPerBlob * 32 + 8 * 32 + 64)));
         B200_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -430,40 +432,43 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
 }
 
 KzgSettingsDev::~KzgSettingsDev() {
-    cudaFree(lagrange_jac_); cudaFree(monomial_jac_); cudaFree(domain_); cudaFree(scalars_); cudaFree(poly_);
-    cudaFree(z_); cudaFree(y_); cudaFree(out_jac_); cudaFree(cells_a_); cudaFree(cells_b_);
+    cudaFree(lagrange_jac_); cudaFree(monomial_jac_); cudaFree(domain_);
+    for (Lane& ln : lanes_) { cudaFree(ln.scalars); cudaFree(ln.poly); cudaFree(ln.z); cudaFree(ln.y); cudaFree(ln.out_jac); }
+    cudaFree(cells_a_); cudaFree(cells_b_);
     cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_);
 }
 
-void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st) {
+void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st, int lane) {
     if (n < 1 || n > max_batch_) throw CudaError(-1, "blob batch exceeds the settings' capacity");
+    Lane& ln = lanes_[lane % kLanes];
     size_t total = (size_t)n * kFieldElementsPerBlob;
-    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, (uint8_t*)scalars_, nullptr, status);
+    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, (uint8_t*)ln.scalars, nullptr, status);
     B200_LAUNCH_CHECK();
-    msm_->run(scalars_, kFieldElementsPerBlob, n, false, out_jac_, st);
-    launch_points_to_compressed(out_jac_, out48, n, st);
-    launches_ = 2 + msm_->launches_per_run();
+    ln.msm->run(ln.scalars, kFieldElementsPerBlob, n, false, ln.out_jac, st);
+    launch_points_to_compressed(ln.out_jac, out48, n, st);
+    launches_ = 2 + ln.msm->launches_per_run();
 }
 
 void KzgSettingsDev::compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes, int z_reduce, int n, uint8_t* proofs48,
-                                    uint8_t* y32, int* status, cudaStream_t st) {
+                                    uint8_t* y32, int* status, cudaStream_t st, int lane) {
     if (n < 1 || n > max_batch_) throw CudaError(-1, "blob batch exceeds the settings' capacity");
+    Lane& ln = lanes_[lane % kLanes];
     size_t total = (size_t)n * kFieldElementsPerBlob;
-    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)poly_, status);
-    k_z_to_fr<<<div_up(n, 64), 64, 0, st>>>(z_bytes, n, z_reduce, (uint8_t*)z_, status);
-    k_quotient<<<n, kQThreads, kFieldElementsPerBlob * 32 + 8 * 32 + 64, st>>>((const uint8_t*)poly_, (const uint8_t*)z_,
-                                                                              (const uint8_t*)domain_, (uint8_t*)scalars_,
-                                                                              (uint8_t*)y_);
+    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)ln.poly, status);
+    k_z_to_fr<<<div_up(n, 64), 64, 0, st>>>(z_bytes, n, z_reduce, (uint8_t*)ln.z, status);
+    k_quotient<<<n, kQThreads, kFieldElementsPerBlob * 32 + 8 * 32 + 64, st>>>((const uint8_t*)ln.poly, (const uint8_t*)ln.z,
+                                                                              (const uint8_t*)domain_, (uint8_t*)ln.scalars,
+                                                                              (uint8_t*)ln.y);
     B200_LAUNCH_CHECK();
-    msm_->run(scalars_, kFieldElementsPerBlob, n, false, out_jac_, st);
-    launch_points_to_compressed(out_jac_, proofs48, n, st);
+    ln.msm->run(ln.scalars, kFieldElementsPerBlob, n, false, ln.out_jac, st);
+    launch_points_to_compressed(ln.out_jac, proofs48, n, st);
     int extra = 0;
     if (y32) {
-        k_fr_to_bytes<<<div_up(n, 64), 64, 0, st>>>((const uint8_t*)y_, n, y32);
+        k_fr_to_bytes<<<div_up(n, 64), 64, 0, st>>>((const uint8_t*)ln.y, n, y32);
         B200_LAUNCH_CHECK();
         extra = 1;
     }
-    launches_ = 4 + extra + msm_->launches_per_run();
+    launches_ = 4 + extra + ln.msm->launches_per_run();
 }
 
 void KzgSettingsDev::compute_cells(const uint8_t* blobs, int n, uint8_t* cells_out, int* status, cudaStream_t st) {
@@ -473,8 +478,8 @@ void KzgSettingsDev::compute_cells(const uint8_t* blobs, int n, uint8_t* cells_o
         cells_a_ = dev_alloc<uint8_t>((size_t)max_batch_ * 2 * kFieldElementsPerBlob * 32);
         cells_b_ = dev_alloc<uint8_t>((size_t)max_batch_ * 2 * kFieldElementsPerBlob * 32);
     }
-    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)poly_, status);
-    k_cells_brp_in<<<div_up(total, 256), 256, 0, st>>>((const uint8_t*)poly_, (uint8_t*)cells_a_, total);
+    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)lanes_[0].poly, status);
+    k_cells_brp_in<<<div_up(total, 256), 256, 0, st>>>((const uint8_t*)lanes_[0].poly, (uint8_t*)cells_a_, total);
     B200_LAUNCH_CHECK();
     fs_->fft_fr(cells_a_, cells_b_, kFieldElementsPerBlob, true, n, st);             // poly_lagrange_to_monomial
     k_cells_pad<<<div_up(2 * total, 256), 256, 0, st>>>((const uint8_t*)cells_b_, (uint8_t*)cells_a_, 2 * total);
@@ -523,8 +528,8 @@ void KzgSettingsDev::compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* p
     if (n < 1 || n > fk_batch_) throw CudaError(-1, "blob batch exceeds the FK20 capacity");
     size_t total = (size_t)n * kFieldElementsPerBlob;
     // polynomial in monomial form (poly_lagrange_to_monomial, kzg/src/das.rs:618-629)
-    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)poly_, status);
-    k_cells_brp_in<<<div_up(total, 256), 256, 0, st>>>((const uint8_t*)poly_, (uint8_t*)cells_a_, total);
+    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)lanes_[0].poly, status);
+    k_cells_brp_in<<<div_up(total, 256), 256, 0, st>>>((const uint8_t*)lanes_[0].poly, (uint8_t*)cells_a_, total);
     B200_LAUNCH_CHECK();
     fs_->fft_fr(cells_a_, cells_b_, kFieldElementsPerBlob, true, n, st);
     // Toeplitz coefficient vectors and their 128-point transforms

@@ -29,19 +29,22 @@ public:
 
     int max_batch() const { return max_batch_; }
     FFTSettingsDev& fft() { return *fs_; }
-    MsmEngine& msm() { return *msm_; }
+    MsmEngine& msm() { return *lanes_[0].msm; }
     // Jacobian (blst_p1) copies for CKZGSettings: bit-reversed Lagrange points and monomial points, device memory
     const void* g1_lagrange_brp_jac_dev() const { return lagrange_jac_; }
     const void* g1_monomial_jac_dev() const { return monomial_jac_; }
 
     // All pointers below are DEVICE pointers; status[i] (int, device) is set to 1 when blob / argument i is invalid
     // (the reference's Err -> C_KZG_BADARGS); outputs of invalid items are unspecified.
+    // Two independent "lanes" (MSM engine + workspace each) let a caller keep two batches in flight on two streams:
+    // the latency-bound tail of one batch (bucket reduction, compression) overlaps the accumulation of the next.
+    static constexpr int kLanes = 2;
     // blob_to_kzg_commitment_raw (kzg/src/eip_4844.rs:297-314), n <= max_batch
-    void blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st);
+    void blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st, int lane = 0);
     // compute_kzg_proof_raw (kzg/src/eip_4844.rs:521-539); z_bytes: n x 32 big-endian; z_reduce: 0 = reject z >= r
     // (Fr::from_bytes), 1 = reduce mod r (hash_to_bls_field, kzg/src/eip_4844.rs:916-918)
     void compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes, int z_reduce, int n, uint8_t* proofs48,
-                        uint8_t* y32, int* status, cudaStream_t st);
+                        uint8_t* y32, int* status, cudaStream_t st, int lane = 0);
     // G1::from_bytes + (is_inf || is_valid) of compute_blob_kzg_proof_rust (kzg/src/eip_4844.rs:556-558)
     void validate_commitments(const uint8_t* commitments48, int n, int* status, cudaStream_t st);
     // cells of compute_cells_and_kzg_proofs(cells, None, blob) (kzg/src/das.rs:244-275): n x 128 cells x 2048 bytes
@@ -60,15 +63,17 @@ private:
     int max_batch_;
     int launches_ = 0;
     std::unique_ptr<FFTSettingsDev> fs_;
-    std::unique_ptr<MsmEngine> msm_;
+    struct Lane {
+        std::unique_ptr<MsmEngine> msm;
+        void* scalars = nullptr;   // max_batch * 4096 canonical scalars (MSM input)
+        void* poly = nullptr;      // max_batch * 4096 Montgomery field elements
+        void* z = nullptr;         // max_batch Montgomery
+        void* y = nullptr;         // max_batch Montgomery
+        void* out_jac = nullptr;   // max_batch Jacobian results
+    } lanes_[kLanes];
     void* lagrange_jac_ = nullptr;
     void* monomial_jac_ = nullptr;
     void* domain_ = nullptr;    // brp_roots_of_unity[0..4096) of the 8192 table (Montgomery)
-    void* scalars_ = nullptr;   // max_batch * 4096 canonical scalars (MSM input)
-    void* poly_ = nullptr;      // max_batch * 4096 Montgomery field elements
-    void* z_ = nullptr;         // max_batch Montgomery
-    void* y_ = nullptr;         // max_batch Montgomery
-    void* out_jac_ = nullptr;   // max_batch Jacobian results
     void* cells_a_ = nullptr;   // max_batch * 8192 Fr ping-pong buffers (compute_cells), allocated on first use
     void* cells_b_ = nullptr;
 };

@@ -140,7 +140,7 @@ struct FrParams {
 // kept by making the last reduction step 32N - 28(L-1) bits wide (20 for Fp, 4 for Fr); the result is re-packed to
 // 32-bit limbs from that bit offset.  An experiment that did NOT pay off on B200 (IMAD.WIDE costs the same with or
 // without carries, and this form needs 406 of them instead of 302); kept as an independently derived cross-check.
-enum { MONT_UNROLLED = 0, MONT_COMPACT = 1, MONT_R28 = 2, MONT_CALL = 3 };
+enum { MONT_UNROLLED = 0, MONT_COMPACT = 1, MONT_R28 = 2, MONT_CALL = 3, MONT_DFMA = 4 };
 template <class P, int MODE = MONT_UNROLLED>
 struct __align__(16) Mont {
     static constexpr bool COMPACT = MODE == MONT_COMPACT;
@@ -242,7 +242,98 @@ struct __align__(16) Mont {
         if (MODE == MONT_COMPACT) return mul_compact(a, b);
         if (MODE == MONT_R28) return mul_r28(a, b, false);
         if (MODE == MONT_CALL) return mul_call(a, b);
+        if (MODE == MONT_DFMA) return mul_dfma(a, b);
         return mul_unrolled(a, b);
+    }
+    // ---- MODE 4: the a*b half of the product on the FP64 pipe ---------------------------------------------------
+    // B200 issues DFMA at 64/clk/SM on a pipe of its own, while every IMAD.WIDE costs 4 cycles of the FMA-heavy pipe
+    // and the carry-chain multiplier is bound by exactly that pipe.  The 2N x 32-bit product a*b is therefore formed
+    // from 48-bit limbs held as doubles: for limbs A, B < 2^48 (A*B < 2^96)
+    //      s1 = fma_rz(A, B, 2^100)          = 2^100 + H * 2^48,   H = floor(A*B / 2^48)   (ulp(2^100) = 2^48)
+    //      s2 = fma_rz(A, B, 2^100 + 2^52 - s1) = 2^52 + L,         L = A*B - H * 2^48      (exact)
+    // so the IEEE mantissa fields of s1, s2 ARE H and L.  The raw 64-bit patterns are summed per 48-bit column with
+    // integer adds (ALU pipe); at most 16 terms < 2^48 land in a column, so the low 52 bits of the sum are the exact
+    // column value and the exponent bits above never interfere.  The columns are carried into 32-bit words and the
+    // 2N-word product is Montgomery-reduced word by word with the carry-chain rows (the m*p half stays on IMAD.WIDE).
+    static constexpr int LD = (32 * N + 47) / 48;  // 48-bit limbs
+    static __device__ __forceinline__ void limbs48(double* d, const Mont& a) {
+#pragma unroll
+        for (int i = 0; i < LD; i++) {
+            const int bit = 48 * i, w = bit >> 5, sh = bit & 31;  // sh is 0 or 16
+            uint32_t w0 = w < N ? a.v[w] : 0u, w1 = w + 1 < N ? a.v[w + 1] : 0u, w2 = w + 2 < N ? a.v[w + 2] : 0u;
+            uint32_t lo, hi16;
+            if (sh == 0) { lo = w0; hi16 = w1 & 0xffffu; }
+            else { lo = (w0 >> 16) | (w1 << 16); hi16 = (w1 >> 16) | ((w2 & 0u) << 16); hi16 &= 0xffffu; }
+            // 2^52 + limb as a bit pattern, minus 2^52: exact conversion without the (slow) I2F unit
+            d[i] = __dsub_rn(__hiloint2double((int)(0x43300000u | hi16), (int)lo), 4503599627370496.0);
+        }
+    }
+    static __device__ __forceinline__ Mont mul_dfma(const Mont& a, const Mont& b) {
+        double ad[LD], bd[LD];
+        limbs48(ad, a);
+        limbs48(bd, b);
+        const double C1 = 1267650600228229401496703205376.0;                       // 2^100
+        const double C1P = 1267650600228229401496703205376.0 + 4503599627370496.0;  // 2^100 + 2^52 (exact: 49 bits)
+        uint64_t col[2 * LD];
+#pragma unroll
+        for (int k = 0; k < 2 * LD; k++) col[k] = 0;
+#pragma unroll
+        for (int i = 0; i < LD; i++) {
+#pragma unroll
+            for (int j = 0; j < LD; j++) {
+                double s1 = __fma_rz(ad[i], bd[j], C1);
+                double s2 = __fma_rz(ad[i], bd[j], __dsub_rn(C1P, s1));
+                col[i + j + 1] += (uint64_t)__double_as_longlong(s1);
+                col[i + j] += (uint64_t)__double_as_longlong(s2);
+            }
+        }
+        // columns (weight 2^(48k), value < 2^52 in the low 52 bits) -> 2N words of 32 bits
+        uint32_t T[2 * N + 1];
+        {
+            const uint64_t M52 = (1ull << 52) - 1, M48 = (1ull << 48) - 1;
+            uint64_t carry = 0;
+            uint64_t limb[2 * LD];
+#pragma unroll
+            for (int k = 0; k < 2 * LD; k++) {
+                uint64_t v = (col[k] & M52) + carry;
+                limb[k] = v & M48;
+                carry = v >> 48;
+            }
+#pragma unroll
+            for (int w = 0; w < 2 * N; w++) {
+                const int bit = 32 * w, k = bit / 48, off = bit % 48;  // off in {0, 32, 16}
+                uint64_t x = limb[k] >> off;
+                if (off > 16 && k + 1 < 2 * LD) x |= limb[k + 1] << (48 - off);
+                T[w] = (uint32_t)x;
+            }
+            T[2 * N] = 0;
+        }
+        // word-serial Montgomery reduction of the 2N-word product: T += m_i * mod * 2^(32 i)
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t m = T[i] * P::INV;
+            // even-indexed modulus words: 64-bit products aligned at T[i + 2k]
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(T[i]), "+r"(T[i + 1]) : "r"(m), "r"(P::mod(0)));
+#pragma unroll
+            for (int k = 2; k < N; k += 2)
+                asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(T[i + k]), "+r"(T[i + k + 1]) : "r"(m), "r"(P::mod(k)));
+#pragma unroll
+            for (int k = i + N; k < 2 * N; k++) asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(T[k]));
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(T[2 * N]));
+            // odd-indexed modulus words: aligned at T[i + 1 + 2k]
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(T[i + 1]), "+r"(T[i + 2]) : "r"(m), "r"(P::mod(1)));
+#pragma unroll
+            for (int k = 3; k < N; k += 2)
+                asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(T[i + k]), "+r"(T[i + k + 1]) : "r"(m), "r"(P::mod(k)));
+#pragma unroll
+            for (int k = i + N + 1; k < 2 * N; k++) asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(T[k]));
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(T[2 * N]));
+        }
+        Mont r;
+#pragma unroll
+        for (int k = 0; k < N; k++) r.v[k] = T[N + k];
+        r.final_sub(T[2 * N]);
+        return r;
     }
     // MODE 3: the unrolled multiplier behind a real call, so a point addition is ~10 calls instead of 60 KiB of inlined
     // code (the accumulate loop body otherwise exceeds the instruction cache: ncu shows "no instruction" stalls)
@@ -537,6 +628,8 @@ typedef Mont<FpParams, MONT_R28> fp28_t;      // radix-2^28 variant
 typedef Mont<FrParams, MONT_R28> fr28_t;
 typedef fp_t fpu_t;
 typedef fr_t fru_t;
+typedef Mont<FpParams, MONT_DFMA> fpd_t;      // a*b on the FP64 pipe, reduction on IMAD.WIDE
+typedef Mont<FrParams, MONT_DFMA> frd_t;
 
 // load / store through 128-bit accesses (fp_t = 48 B = 3 x uint4, fr_t = 32 B = 2 x uint4)
 template <class F>

@@ -21,8 +21,8 @@ static constexpr int kAccThreads = 128;  // accumulate CTA: 4 warps, one per SM 
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalars, size_t n, size_t row_stride, size_t total,
                                                 int c, int W, int nb, int fixed, int mont, uint32_t* __restrict__ ctr,
-                                                uint32_t* __restrict__ entries, size_t period, size_t period_n) {
-    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                uint32_t* __restrict__ entries, size_t period, size_t period_n, size_t gid0) {
+    size_t gid = gid0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     size_t vec = gid / n, i = gid - vec * n;
     fr_t s = load_field_ro<fr_t>(scalars + 2 * gid);
@@ -582,6 +582,10 @@ void MsmEngine::profile_read(double* accumulate_ms_sum, int* runs) {
 MsmEngine::~MsmEngine() {
     for (auto& e : prof_ev_)
         if (e) cudaEventDestroy(e);
+    for (auto& e : copy_ev_)
+        if (e) cudaEventDestroy(e);
+    if (copy_start_) cudaEventDestroy(copy_start_);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     cudaFree(table_); cudaFree(counts_); cudaFree(offsets_); cudaFree(cursor_); cudaFree(task_base_); cudaFree(entries_);
     cudaFree(sorted_tasks_); cudaFree(size_hist_); cudaFree(scan_tmp_); cudaFree(partials_); cudaFree(chunk_sums_);
     cudaFree(group_sums_);
@@ -593,7 +597,8 @@ void MsmEngine::set_points(const void* points_dev, size_t npoints, cudaStream_t 
     B200_CUDA_CHECK(cudaMemcpyAsync(table_, points_dev, npoints * 96, cudaMemcpyDeviceToDevice, stream));
 }
 
-void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mont, void* out_dev, cudaStream_t st) {
+void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mont, void* out_dev, cudaStream_t st,
+                    const void* scalars_host) {
     if (npoints > cfg_.n || batch < 1 || batch > cfg_.max_batch) throw CudaError(-1, "MsmEngine::run: bad sizes");
     const int c = cfg_.c, W = cfg_.W, L = cfg_.L;
     const size_t groups = cfg_.fixed ? (size_t)batch : (size_t)W;
@@ -609,15 +614,40 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     B200_CUDA_CHECK(cudaMemsetAsync(size_hist_, 0, 3 * (L + 1) * sizeof(uint32_t), st));
     // 1 digits + histogram
     const size_t row_stride = (size_t)cfg_.bases_period * cfg_.n;
-    k_digits<false><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, W, nb_,
-                                                        cfg_.fixed, mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n);
-    launches++;
+    if (scalars_host) {
+        // host scalars: copy in chunks on a second stream and histogram each chunk as it lands, so the PCIe transfer
+        // overlaps the first kernel instead of preceding it
+        if (!copy_stream_) {
+            B200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+            for (auto& e : copy_ev_) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            B200_CUDA_CHECK(cudaEventCreateWithFlags(&copy_start_, cudaEventDisableTiming));
+        }
+        const int nchunks = total >= (1u << 16) ? kCopyChunks : 1;
+        const size_t per = (total + nchunks - 1) / nchunks;
+        B200_CUDA_CHECK(cudaEventRecord(copy_start_, st));           // the staging buffer is free once st reaches here
+        B200_CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, copy_start_, 0));
+        for (int k = 0; k < nchunks; k++) {
+            size_t lo = (size_t)k * per, hi = std::min(total, lo + per);
+            if (lo >= hi) break;
+            B200_CUDA_CHECK(cudaMemcpyAsync((uint8_t*)scalars_dev + lo * 32, (const uint8_t*)scalars_host + lo * 32, (hi - lo) * 32,
+                                            cudaMemcpyHostToDevice, copy_stream_));
+            B200_CUDA_CHECK(cudaEventRecord(copy_ev_[k], copy_stream_));
+            B200_CUDA_CHECK(cudaStreamWaitEvent(st, copy_ev_[k], 0));
+            k_digits<false><<<div_up(hi - lo, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, hi, c, W, nb_, cfg_.fixed,
+                                                                 mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n, lo);
+            launches++;
+        }
+    } else {
+        k_digits<false><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, W, nb_,
+                                                            cfg_.fixed, mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n, 0);
+        launches++;
+    }
     // 2 offsets (and a working copy for the scatter cursors), task bases
     launches += scan_exclusive(counts_, nkeys, 0, offsets_, cursor_, scan_tmp_, st);
     launches += scan_exclusive(counts_, nkeys, (uint32_t)L, task_base_, nullptr, scan_tmp_, st);
     // 3 scatter
     k_digits<true><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, W, nb_,
-                                                       cfg_.fixed, mont, cursor_, entries_, (size_t)cfg_.bases_period, cfg_.n);
+                                                       cfg_.fixed, mont, cursor_, entries_, (size_t)cfg_.bases_period, cfg_.n, 0);
     launches++;
     // 4 tasks sorted by length
     k_task_hist<<<div_up(nkeys, 256), 256, (L + 1) * sizeof(uint32_t), st>>>(counts_, nkeys, L, size_hist_);

@@ -49,7 +49,10 @@ public:
 
     // scalars_dev: batch * n scalars of 32 B in device memory; mont = blst_fr Montgomery form (else canonical LE).
     // out_dev: batch Jacobian points (blst_p1 layout) in device memory.  npoints <= n uses the first npoints bases.
-    void run(const void* scalars_dev, size_t npoints, int batch, bool mont, void* out_dev, cudaStream_t stream);
+    // scalars_host != nullptr: the scalars are still on the host; they are copied into scalars_dev (a device staging
+    // buffer of batch * npoints * 32 bytes) in chunks that overlap the digit histogram.
+    void run(const void* scalars_dev, size_t npoints, int batch, bool mont, void* out_dev, cudaStream_t stream,
+             const void* scalars_host = nullptr);
 
     // VARIABLE engines only: replace the bases (device pointer, n points).
     void set_points(const void* points_dev, size_t npoints, cudaStream_t stream);
@@ -77,6 +80,10 @@ private:
     static constexpr int kProfSlots = 512;
     cudaEvent_t prof_ev_[2 * kProfSlots] = {};
     int prof_count_ = 0;
+    static constexpr int kCopyChunks = 4;
+    cudaStream_t copy_stream_ = nullptr;
+    cudaEvent_t copy_ev_[kCopyChunks] = {};
+    cudaEvent_t copy_start_ = nullptr;
     void* table_ = nullptr;      // affine rows
     uint32_t* counts_ = nullptr;  // [keys+1]
     uint32_t* offsets_ = nullptr;

@@ -98,7 +98,9 @@ static RustError field_op(int op, void* out, const void* a, const void* b, size_
         DevBuf<uint8_t> da(bytes), db(bytes), dout(bytes);
         B200_CUDA_CHECK(cudaMemcpy(da.p, a, bytes, cudaMemcpyHostToDevice));
         if (b) B200_CUDA_CHECK(cudaMemcpy(db.p, b, bytes, cudaMemcpyHostToDevice));
-        if (op & 32)
+        if (op & 64)
+            k_field_op<Mont<typename F::params_t, MONT_DFMA>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);
+        else if (op & 32)
             k_field_op<Mont<typename F::params_t, MONT_R28>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);
         else if (op & 16)
             k_field_op<Mont<typename F::params_t, MONT_COMPACT>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);

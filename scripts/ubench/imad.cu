@@ -104,6 +104,21 @@ __global__ void __launch_bounds__(256) k_lo(uint64_t* sink, uint32_t a, uint32_t
     for (int k = 0; k < 8; k++) s ^= lo[k];
     if (s == 0x1234567) sink[0] = s;
 }
+// (viii) DFMA issue rate: 8 independent chains
+__global__ void __launch_bounds__(256) k_dfma(uint64_t* sink, uint32_t a, uint32_t b, int iters) {
+    double acc[8];
+    for (int k = 0; k < 8; k++) acc[k] = 1.0 + threadIdx.x + k;
+    double x = 1.0000001 + a * 1e-9, y = 1e-7 * (b + blockIdx.x);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = __fma_rz(acc[k], x, y);
+    }
+    double s = 0;
+    for (int k = 0; k < 8; k++) s += acc[k];
+    if (s == 0.12345) sink[0] = 1;
+}
 // (iv) full Fp / Fr multiplications, 2 independent streams per thread
 template <class F>
 __global__ void __launch_bounds__(128) k_mul(uint8_t* sink, int iters) {
@@ -144,6 +159,8 @@ int main() {
         printf("lohi  occ=%d: %.2f T mul-ops/s\n", occ, (double)blocks * th * iters * 64 / ms / 1e9);
         ms = timeit([&] { k_cout<<<blocks, th>>>(sink, 3, 5, iters); });
         printf("cout  occ=%d: %.2f T mad/s\n", occ, (double)blocks * th * iters * 64 / ms / 1e9);
+        ms = timeit([&] { k_dfma<<<blocks, th>>>(sink, 3, 5, iters); });
+        printf("dfma  occ=%d: %.2f T dfma/s\n", occ, (double)blocks * th * iters * 64 / ms / 1e9);
         ms = timeit([&] { k_hi<<<blocks, th>>>(sink, 3, 5, iters); });
         printf("hi    occ=%d: %.2f T mad/s\n", occ, (double)blocks * th * iters * 64 / ms / 1e9);
         ms = timeit([&] { k_lo<<<blocks, th>>>(sink, 3, 5, iters); });
@@ -155,6 +172,10 @@ int main() {
         printf("fpmul occ=%d (warps/SM=%d): %.2f G mul/s\n", occ, occ * 4, (double)blocks * th * iters * 4 / ms / 1e6);
         ms = timeit([&] { k_mul<fpc_t><<<blocks, th>>>((uint8_t*)sink, iters); });
         printf("fpmul-compact occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
+        ms = timeit([&] { k_mul<fpd_t><<<blocks, th>>>((uint8_t*)sink, iters); });
+        printf("fpmul-dfma occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
+        ms = timeit([&] { k_mul<frd_t><<<blocks, th>>>((uint8_t*)sink, iters); });
+        printf("frmul-dfma occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
         ms = timeit([&] { k_mul<fp28_t><<<blocks, th>>>((uint8_t*)sink, iters); });
         printf("fpmul-r28 occ=%d: %.2f G mul/s\n", occ, (double)blocks * th * iters * 4 / ms / 1e6);
         ms = timeit([&] { k_mul<fr28_t><<<blocks, th>>>((uint8_t*)sink, iters); });

@@ -49,7 +49,7 @@ def test_field_ops_match_oracle(B, K, which):
     assert np.array_equal(_field(B, which, 5, canon), a)
     assert np.array_equal(_field(B, which, 6, a), canon)
     # the three multiplier variants (default unrolled carry chain, +16 compact carry chain, +32 radix-2^28) agree
-    for var in (16, 32):
+    for var in (16, 32, 64):   # 64: a*b on the FP64 pipe (DFMA), reduction on IMAD.WIDE
         assert np.array_equal(_field(B, which, var, a, b), omul(a, b))
         assert np.array_equal(_field(B, which, var, a, a), omul(a, a))
         assert np.array_equal(_field(B, which, var + 5, canon), a)

@@ -144,3 +144,29 @@ def test_large_tiled_bases_folded_oracle(B, K, lagrange_affine):
     _same(K, h.mult(sc), exp)
     h.close()
     _same(K, B.mult_pippenger(pts, sc), exp)
+
+
+def test_adversarial_distributions_at_scale(B, K, lagrange_affine):
+    """2^16 terms whose digits all collide: every term lands in the same few buckets, so a bucket holds up to 2^16
+    entries and is cut into ~1000 tasks + a warp-parallel combine (bucket load imbalance)."""
+    n = 1 << 16
+    reps = n // 4096
+    pts = np.tile(lagrange_affine, (reps, 1))
+    h = B.PreparedMsm(pts)
+    rng = np.random.default_rng(41)
+    s0, s1 = rand_ints(rng, 2, R_MOD)
+    cases = {
+        "all-equal": [s0] * n,
+        "two-values": [s0 if (i * 7) % 3 else s1 for i in range(n)],
+        "all-r-minus-1": [R_MOD - 1] * n,
+        "one-hot-window": [1 << 200] * n,
+    }
+    for name, ints in cases.items():
+        sc = K.fr_from_ints(ints[:4096 * 2])          # conversion is slow in Python: build two tiles, then repeat
+        sc = np.tile(sc, (reps // 2, 1))
+        ints_eff = (ints[:4096 * 2]) * (reps // 2)
+        folded = [sum(ints_eff[j + 4096 * k] for k in range(reps)) % R_MOD for j in range(4096)]
+        exp = K.msm_affine(lagrange_affine, K.fr_from_ints(folded), nthreads=8)
+        assert K.p1_compress(h.mult(sc)) == K.p1_compress(exp), name
+        assert K.p1_compress(B.mult_pippenger(pts, sc)) == K.p1_compress(exp), name + "/variable"
+    h.close()
