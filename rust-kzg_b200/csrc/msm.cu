@@ -90,14 +90,19 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     __syncthreads();
     return base + x - v;
 }
-// f: 0 = identity, otherwise ceil(x / f)  (task counts)
+// f: 0 = identity; f > 0: ceil(x / f) (task counts); f | 0x80000000: floor(x / f) (pair counts)
+__device__ __forceinline__ uint32_t scan_map(uint32_t x, uint32_t f) {
+    if (f == 0) return x;
+    if (f & 0x80000000u) return x / (f & 0x7fffffffu);
+    return (x + f - 1) / f;
+}
 __global__ void __launch_bounds__(kScanBlock) k_scan_partial(const uint32_t* __restrict__ in, size_t n, uint32_t f,
                                                              uint32_t* __restrict__ block_sums) {
     size_t base = ((size_t)blockIdx.x * kScanBlock + threadIdx.x) * kScanItems;
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; k++)
-        if (base + k < n) { uint32_t x = in[base + k]; s += f ? (x + f - 1) / f : x; }
+        if (base + k < n) { uint32_t x = in[base + k]; s += scan_map(x, f); }
     uint32_t total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_final(const uint32_t* __res
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) {
         uint32_t x = base + k < n ? in[base + k] : 0;
-        v[k] = f ? (x + f - 1) / f : x;
+        v[k] = scan_map(x, f);
         s += v[k];
     }
     uint32_t total;
@@ -233,6 +238,153 @@ __global__ void __launch_bounds__(kAccThreads) k_accumulate(const uint8_t* __res
         uint32_t v = e[k];
         affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
         p.y = p.y.cneg(v >> 31);
+        xyzz_add_affine(acc, p);
+    }
+    store_xyzz(partials + (size_t)slot * 192, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 5a: batch-affine pre-reduction.  A mixed XYZZ addition costs 8M + 2S; adding two AFFINE points costs 3M once
+// 1/(x2 - x1) is known, and inverting K denominators together (Montgomery's trick: 3M each + one inversion) makes
+// that 6M per addition.  The inversion itself is the binary-Euclid routine, which runs on the ALU pipe while the
+// multiplications keep the FMA-heavy pipe busy.  Buckets are summed as trees: every round adds adjacent pairs of each
+// bucket's point list (all pairs of all buckets are independent, so a thread takes K consecutive pairs of the flat
+// pair list, across bucket boundaries), halving the lists; after a few rounds the XYZZ task kernel finishes the rest.
+// All exceptional cases are explicit: infinity operands, P + P (tangent slope) and P + (-P) (result infinity).
+static constexpr int kAffK = 16;  // pairs per thread = denominators per inversion
+
+struct AffinePair {
+    affine_t p1, p2;
+};
+// gather mode (round 0): points come from the table through the sorted entries (index | sign << 31)
+__device__ __forceinline__ affine_t load_round_point(const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
+                                                     const uint8_t* __restrict__ buf, size_t pos, bool gather) {
+    if (gather) {
+        uint32_t v = entries[pos];
+        affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
+        if (!p.is_inf()) p.y = p.y.cneg(v >> 31);
+        return p;
+    }
+    return load_affine(buf + pos * 96);
+}
+// denominator of the slope: x2 - x1, or 2*y1 when the points coincide; zero means "no inversion needed"
+__device__ __forceinline__ fp_t pair_denominator(const affine_t& p1, const affine_t& p2) {
+    if (p1.is_inf() || p2.is_inf()) return fp_t::zero();
+    fp_t dx = p2.x - p1.x;
+    if (!dx.is_zero()) return dx;
+    if (p1.y == p2.y) return p1.y.dbl();
+    return fp_t::zero();  // P + (-P)
+}
+__global__ void __launch_bounds__(128) k_affine_round(const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
+                                                      const uint8_t* __restrict__ in_buf, uint8_t* __restrict__ out_buf,
+                                                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                                      const uint32_t* __restrict__ pair_base, size_t nkeys, int gather) {
+    const size_t total_pairs = pair_base[nkeys];
+    size_t p0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kAffK;
+    if (p0 >= total_pairs) return;
+    const int npairs = (int)min((size_t)kAffK, total_pairs - p0);
+    // locate the bucket of the first pair: last key with pair_base[key] <= p0
+    size_t lo = 0, hi = nkeys;
+    while (hi - lo > 1) {
+        size_t mid = (lo + hi) >> 1;
+        if (pair_base[mid] <= p0) lo = mid; else hi = mid;
+    }
+    size_t key0 = lo;
+    uint32_t k0 = (uint32_t)(p0 - pair_base[key0]);
+
+    fp_t prefix[kAffK];
+    fp_t acc = fp_t::one();
+    {
+        size_t key = key0;
+        uint32_t k = k0, npk = counts[key] >> 1, off = offsets[key];
+#pragma unroll 1
+        for (int i = 0; i < npairs; i++) {
+            while (k >= npk) { key++; k = 0; npk = counts[key] >> 1; off = offsets[key]; }
+            affine_t a = load_round_point(table, entries, in_buf, (size_t)off + 2 * k, gather);
+            affine_t b = load_round_point(table, entries, in_buf, (size_t)off + 2 * k + 1, gather);
+            fp_t d = pair_denominator(a, b);
+            prefix[i] = acc;
+            if (!d.is_zero()) acc = acc * d;
+            k++;
+        }
+    }
+    fp_t inv = acc.inverse();
+    // second sweep, backwards, recomputing the (cheap) denominators: inv_i = prefix_i * inv; inv *= d_i
+    {
+        // re-walk forward to find the position of the last pair, then go back; simpler: recompute positions per pair
+        // by walking forward again and storing (key, k) compactly
+        uint32_t pk_key[kAffK], pk_k[kAffK];
+        size_t key = key0;
+        uint32_t k = k0, npk = counts[key] >> 1;
+#pragma unroll 1
+        for (int i = 0; i < npairs; i++) {
+            while (k >= npk) { key++; k = 0; npk = counts[key] >> 1; }
+            pk_key[i] = (uint32_t)key;
+            pk_k[i] = k;
+            k++;
+        }
+#pragma unroll 1
+        for (int i = npairs - 1; i >= 0; i--) {
+            uint32_t off = offsets[pk_key[i]];
+            uint32_t kk = pk_k[i];
+            affine_t a = load_round_point(table, entries, in_buf, (size_t)off + 2 * kk, gather);
+            affine_t b = load_round_point(table, entries, in_buf, (size_t)off + 2 * kk + 1, gather);
+            affine_t r;
+            if (a.is_inf()) {
+                r = b;
+            } else if (b.is_inf()) {
+                r = a;
+            } else {
+                fp_t dx = b.x - a.x;
+                bool dbl = dx.is_zero();
+                if (dbl && !(a.y == b.y)) {
+                    r.x = fp_t::zero();
+                    r.y = fp_t::zero();  // P + (-P)
+                } else {
+                    fp_t d = dbl ? a.y.dbl() : dx;
+                    fp_t inv_i = prefix[i] * inv;
+                    inv = inv * d;
+                    fp_t num;
+                    if (dbl) {
+                        fp_t xx = a.x.sqr();
+                        num = xx.dbl() + xx;  // 3 x^2
+                    } else {
+                        num = b.y - a.y;
+                    }
+                    fp_t lam = num * inv_i;
+                    fp_t x3 = lam.sqr() - a.x - b.x;
+                    r.x = x3;
+                    r.y = lam * (a.x - x3) - a.y;
+                }
+            }
+            store_affine(out_buf + ((size_t)off + kk) * 96, r);
+        }
+    }
+}
+// odd bucket sizes: the unpaired last point moves to the end of the halved list; then counts := ceil(counts / 2)
+__global__ void __launch_bounds__(256) k_affine_leftover(const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
+                                                         const uint8_t* __restrict__ in_buf, uint8_t* __restrict__ out_buf,
+                                                         const uint32_t* __restrict__ offsets, uint32_t* __restrict__ counts,
+                                                         size_t nkeys, int gather) {
+    size_t key = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nkeys) return;
+    uint32_t c = counts[key];
+    if (c & 1) {
+        uint32_t off = offsets[key];
+        affine_t p = load_round_point(table, entries, in_buf, (size_t)off + c - 1, gather);
+        store_affine(out_buf + ((size_t)off + (c >> 1)) * 96, p);
+    }
+    counts[key] = (c + 1) >> 1;
+}
+// the XYZZ task kernel on an already materialised (and partly reduced) point list: contiguous reads, no gather
+__global__ void __launch_bounds__(kAccThreads) k_accumulate_direct(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ sorted_tasks,
+                                                                   const uint32_t* __restrict__ n_tasks_ptr, uint8_t* __restrict__ partials) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *n_tasks_ptr) return;
+    uint32_t start = sorted_tasks[3 * t], len = sorted_tasks[3 * t + 1], slot = sorted_tasks[3 * t + 2];
+    xyzz_t acc = xyzz_t::inf();
+    for (uint32_t k = 0; k < len; k++) {
+        affine_t p = load_affine(buf + ((size_t)start + k) * 96);
         xyzz_add_affine(acc, p);
     }
     store_xyzz(partials + (size_t)slot * 192, acc);
@@ -377,6 +529,7 @@ __global__ void __launch_bounds__(kMargThreads) k_marginals(const uint8_t* __res
     }
 }
 
+static constexpr int kMargSerial = 8;  // buckets summed serially per lane before the shuffle tree
 // 6b': the same marginal sums for many groups (blob batches): S lanes per marginal instead of a CTA, so that the
 // tree steps waste few lanes -- with 64 groups x 40 marginals the CTA form spends most of its FMA-pipe time on
 // additions with the point at infinity.  S = 2^log_s lanes sum count/S buckets each, then a
@@ -387,7 +540,7 @@ __global__ void __launch_bounds__(128) k_marginals_sub(const uint8_t* __restrict
     const int a = blockIdx.y;  // one grid row per digit axis: the axes are independent and run concurrently
     const int wa = ap.w[a], sa = ap.sh[a];
     int log_s = 0;
-    while (log_s < 5 && ((nb >> wa) >> log_s) > 16) log_s++;
+    while (log_s < 5 && ((nb >> wa) >> log_s) > kMargSerial) log_s++;
     const int S = 1 << log_s;
     const size_t total_threads = (groups << wa) << log_s;
     const bool live = gid < total_threads;
@@ -556,6 +709,19 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     partials_ = dev_alloc<uint8_t>(tasks_max_ * 192);
     chunk_sums_ = dev_alloc<uint8_t>(groups_max_ * 3 * 32 * 192);  // marginal sums [group][axis][32]
     group_sums_ = dev_alloc<uint8_t>(groups_max_ * 192);
+    pair_base_ = dev_alloc<uint32_t>(keys_max_ + 1);
+    {
+        const char* e = getenv("B200_AFFINE_ROUNDS");
+        // OFF by default: measured on B200 (MSM 2^20) the rounds make the accumulation phase 16.1 ms instead of 6.4 ms --
+        // one binary-Euclid inversion per 16 additions costs more ALU-pipe time than the 4 multiplications it saves
+        // per addition (profiles/r01_multiplier_variants.md).  Kept as a tested option for larger inversion batches.
+        max_rounds_ = e && *e ? atoi(e) : 0;
+        // two point buffers of one point per entry; only for fixed-base engines and while they stay within 16 GiB
+        if (cfg_.fixed && max_rounds_ > 0 && entries_max_ * 96 * 2 <= (16ull << 30)) {
+            aff_buf_[0] = dev_alloc<uint8_t>(entries_max_ * 96);
+            aff_buf_[1] = dev_alloc<uint8_t>(entries_max_ * 96);
+        }
+    }
     if (points) {
         B200_CUDA_CHECK(cudaMemcpyAsync(table_, points, table_points * 96, host_points ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
         if (cfg_.fixed && cfg_.W > 1) {
@@ -586,6 +752,7 @@ MsmEngine::~MsmEngine() {
         if (e) cudaEventDestroy(e);
     if (copy_start_) cudaEventDestroy(copy_start_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    cudaFree(pair_base_); cudaFree(aff_buf_[0]); cudaFree(aff_buf_[1]);
     cudaFree(table_); cudaFree(counts_); cudaFree(offsets_); cudaFree(cursor_); cudaFree(task_base_); cudaFree(entries_);
     cudaFree(sorted_tasks_); cudaFree(size_hist_); cudaFree(scan_tmp_); cudaFree(partials_); cudaFree(chunk_sums_);
     cudaFree(group_sums_);
@@ -649,6 +816,40 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     k_digits<true><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, W, nb_,
                                                        cfg_.fixed, mont, cursor_, entries_, (size_t)cfg_.bases_period, cfg_.n, 0);
     launches++;
+    // 5a batch-affine rounds (FIXED engines with room for the two point buffers): halve every bucket's list R times
+    const bool prof = profiling_ && prof_count_ < kProfSlots;
+    if (prof) {
+        for (int k = 0; k < 2; k++)
+            if (!prof_ev_[2 * prof_count_ + k]) B200_CUDA_CHECK(cudaEventCreate(&prof_ev_[2 * prof_count_ + k]));
+        B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_], st));
+    }
+    int rounds = 0;
+    const uint8_t* reduced = nullptr;  // buffer holding the current point lists once rounds > 0
+    if (aff_buf_[0]) {
+        // expected entries per bucket decides how many halvings pay: stop while a round still fills the machine
+        double per_bucket = (double)total * W / (double)nkeys;
+        size_t pairs = (size_t)((double)total * W / 2);
+        while (per_bucket >= 8.0 && pairs >= (size_t)kAffK * 32768 && rounds < max_rounds_) {
+            rounds++;
+            per_bucket /= 2;
+            pairs /= 2;
+        }
+        size_t pair_bound = total * W / 2;
+        for (int r = 0; r < rounds; r++) {
+            launches += scan_exclusive(counts_, nkeys, 0x80000002u, pair_base_, nullptr, scan_tmp_, st);
+            const uint8_t* in = r == 0 ? nullptr : aff_buf_[(r - 1) & 1];
+            uint8_t* out = aff_buf_[r & 1];
+            size_t threads = pair_bound / kAffK + 1;
+            k_affine_round<<<div_up(threads, 128), 128, 0, st>>>((const uint8_t*)table_, entries_, in, out, offsets_, counts_, pair_base_,
+                                                                nkeys, r == 0);
+            k_affine_leftover<<<div_up(nkeys, 256), 256, 0, st>>>((const uint8_t*)table_, entries_, in, out, offsets_, counts_, nkeys,
+                                                                 r == 0);
+            launches += 2;
+            pair_bound = pair_bound / 2 + nkeys;
+            reduced = out;
+        }
+        if (rounds) launches += scan_exclusive(counts_, nkeys, (uint32_t)L, task_base_, nullptr, scan_tmp_, st);
+    }
     // 4 tasks sorted by length
     k_task_hist<<<div_up(nkeys, 256), 256, (L + 1) * sizeof(uint32_t), st>>>(counts_, nkeys, L, size_hist_);
     k_task_bases<<<1, 32, 0, st>>>(size_hist_, L);
@@ -656,14 +857,11 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     launches += 3;
     // 5 accumulate: grid sized for the worst case, surplus threads exit on the device-side task count
     size_t tasks_bound = std::min(tasks_max_, total * W / L + nkeys + 1);
-    const bool prof = profiling_ && prof_count_ < kProfSlots;
-    if (prof) {
-        for (int k = 0; k < 2; k++)
-            if (!prof_ev_[2 * prof_count_ + k]) B200_CUDA_CHECK(cudaEventCreate(&prof_ev_[2 * prof_count_ + k]));
-        B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_], st));
-    }
     static const bool acc_call = getenv("B200_ACC_CALL") && atoi(getenv("B200_ACC_CALL"));
-    if (acc_call)
+    if (reduced)
+        k_accumulate_direct<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>(reduced, sorted_tasks_, task_base_ + nkeys,
+                                                                                     (uint8_t*)partials_);
+    else if (acc_call)
         k_accumulate_call<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
                                                                                    task_base_ + nkeys, (uint8_t*)partials_);
     else
@@ -697,7 +895,7 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
         size_t max_threads = 0;
         for (int a = 0; a < ap.D; a++) {
             int log_s = 0;
-            while (log_s < 5 && ((nb_ >> ap.w[a]) >> log_s) > 16) log_s++;
+            while (log_s < 5 && ((nb_ >> ap.w[a]) >> log_s) > kMargSerial) log_s++;
             max_threads = std::max(max_threads, (groups << ap.w[a]) << log_s);
         }
         k_marginals_sub<<<dim3(div_up(max_threads, 128), ap.D), 128, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap, groups,

@@ -93,6 +93,9 @@ private:
     uint32_t* sorted_tasks_ = nullptr;  // 3 x u32 per task
     uint32_t* size_hist_ = nullptr;     // [L+1] hist, [L+1] base, [L+1] cursor
     uint32_t* scan_tmp_ = nullptr;
+    uint32_t* pair_base_ = nullptr;     // [keys+1] flat pair index of each bucket in a batch-affine round
+    uint8_t* aff_buf_[2] = {nullptr, nullptr};  // ping-pong affine point lists (one slot per entry)
+    int max_rounds_ = 0;
     void* partials_ = nullptr;  // xyzz per task
     void* chunk_sums_ = nullptr;
     void* group_sums_ = nullptr;
