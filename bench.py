@@ -305,6 +305,23 @@ def main():
     }
     if not args.no_extra and world == 1:
         try:
+            # variable-base call of the reference's L4 benchmark shape (bench_g1_lincomb, points + scalars travel with
+            # every call: kzg-bench/src/benches/lincomb.rs:35-46; 116.75 ms on L4 + sppark)
+            h_pts = torch.from_numpy(pts.view(np.int64)).pin_memory()
+            hp = h_pts.numpy().view(np.uint64).reshape(n, 12)
+            B.mult_pippenger(hp, h_np)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                rv = B.mult_pippenger(hp, h_np)
+            t_var = (time.perf_counter() - t0) / 3
+            out["variable_base_e2e"] = {"api": "mult_pippenger (C ABI), pinned host points + scalars",
+                                        "ms_per_call": t_var * 1e3, "points_per_s": n / t_var,
+                                        "h2d_bytes_per_call": 128 * n, "parity_ok": bool(K.p1_compress(rv) == K.p1_compress(exp))}
+            del h_pts, hp
+        except Exception as e:
+            out["variable_base_e2e"] = {"error": repr(e)}
+        msm.close()
+        try:
             out["extra"] = extra_metrics(B, K, osettings, torch)
         except Exception as e:  # extras must not take the headline down
             out["extra"] = {"error": repr(e)}
@@ -372,6 +389,15 @@ def extra_metrics(B, K, osettings, torch):
     pb = K.compute_blob_kzg_proof(blobs[9].tobytes(), comm[9].tobytes(), osettings)
     ex["compute_blob_kzg_proof"] = {"e2e_blobs_per_s": nb / dt, "ms_per_batch": dt * 1e3, "batch": nb,
                                     "parity_ok": bool(h_out[9].numpy().tobytes() == pb)}
+    # single-blob latency through the c-kzg entry point (52.4 ms blst 1 core, 6.35 ms 16 cores, 5.21 ms L4+sppark)
+    one = h_blobs[0].numpy().tobytes()
+    for _ in range(3):
+        ts.blob_to_kzg_commitment(one)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        c1 = ts.blob_to_kzg_commitment(one)
+    ex["blob_to_kzg_commitment"]["single_blob_ms"] = (time.perf_counter() - t0) / 10 * 1e3
+    ex["blob_to_kzg_commitment"]["single_blob_parity_ok"] = bool(c1 == comm[0].tobytes())
     # sustained rate on a stream of 512 blobs through the same host-pointer calls: chunks of 64 alternate between two
     # lanes, so the latency-bound tail of one chunk overlaps the accumulation of the next
     big = 512

@@ -36,7 +36,47 @@ __device__ __forceinline__ fr_t root_at(const NttPass& p, size_t e_units) {
     return load_field_ro<fr_t>(p.roots + idx * 32);
 }
 
-__global__ void __launch_bounds__(kNttThreads) k_ntt_pass(NttPass p) {
+// Shared-memory slot of tile element i.  The XOR swizzle spreads the 8-element groups a thread owns in the first
+// butterfly group (stride-256-byte accesses, otherwise an 8-way bank conflict) over the banks.
+__device__ __forceinline__ int slot(int i) { return i ^ ((i >> 3) & 7); }
+
+// R consecutive radix-2 DIT stages (t .. t+R-1) on the 2^R elements whose in-column indices differ only in bits
+// t .. t+R-1, entirely in registers: one shared-memory round trip and one barrier per R stages instead of per stage.
+// The butterfly is the reference's (blst/src/fft_fr.rs:98-103): lo' = lo + w*hi, hi' = lo - w*hi.
+template <int R>
+__device__ __forceinline__ void butterfly_group(uint8_t* sm, const NttPass& p, int m, int t, int unit) {
+    constexpr int E = 1 << R;
+    const int units_per_col = m >> R;
+    const int g = unit / units_per_col, rem = unit - g * units_per_col;
+    const int lo = rem & ((1 << t) - 1), hi = rem >> t;
+    const int base = (hi << (t + R)) | lo;
+    fr_t x[E];
+#pragma unroll
+    for (int j = 0; j < E; j++) x[j] = load_field<fr_t>(sm + (size_t)slot(g * m + base + (j << t)) * 32);
+#pragma unroll
+    for (int s = 0; s < R; s++) {
+        // stage t+s pairs j and j + 2^s; the twiddle exponent is (index mod 2^(t+s)) * m / 2^(t+s+1)
+#pragma unroll
+        for (int b = 0; b < (1 << s); b++) {
+            const int low = lo + (b << t);  // index mod 2^(t+s) of the pairs whose low s group-bits equal b
+            fr_t w;
+            const bool has_w = low != 0;
+            if (has_w) w = root_at(p, ((size_t)low << (p.log_m - 1 - (t + s))) * p.unit_m);
+#pragma unroll
+            for (int j = 0; j < E; j++) {
+                if ((j & ((1 << (s + 1)) - 1)) != b) continue;  // j has bit s clear and low s bits == b
+                fr_t u = x[j], v = x[j + (1 << s)];
+                if (has_w) v = v * w;
+                x[j] = u + v;
+                x[j + (1 << s)] = u - v;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < E; j++) store_field(sm + (size_t)slot(g * m + base + (j << t)) * 32, x[j]);
+}
+
+__global__ void __launch_bounds__(kNttThreads, 2) k_ntt_pass(NttPass p) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int m = 1 << p.log_m;
     const int tile = p.G * m;
@@ -56,25 +96,21 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt_pass(NttPass p) {
             if (p.twist_unit) x = x * load_field_ro<fr_t>(p.roots + (j * p.twist_unit) * 32);
         }
         int rr = p.log_m ? (int)(__brev((unsigned)r) >> (32 - p.log_m)) : 0;
-        store_field(sm + (size_t)(g * m + rr) * 32, x);
+        store_field(sm + (size_t)slot(g * m + rr) * 32, x);
     }
     __syncthreads();
 
-    // radix-2 decimation-in-time butterflies (blst/src/fft_fr.rs:98-103): lo' = lo + w*hi, hi' = lo - w*hi
-    const int halfm = m >> 1;
-    for (int t = 0; t < p.log_m; t++) {
-        const int half = 1 << t;
-        for (int b = threadIdx.x; b < p.G * halfm; b += blockDim.x) {
-            int g = b / halfm, k = b - g * halfm;
-            int lowk = k & (half - 1);
-            int i = ((k >> t) << (t + 1)) | lowk;
-            uint8_t* plo = sm + (size_t)(g * m + i) * 32;
-            uint8_t* phi = plo + (size_t)half * 32;
-            fr_t u = load_field<fr_t>(plo), v = load_field<fr_t>(phi);
-            if (lowk) v = v * root_at(p, ((size_t)lowk << (p.log_m - 1 - t)) * p.unit_m);
-            store_field(plo, u + v);
-            store_field(phi, u - v);
-        }
+    // butterflies: groups of three stages, then whatever is left (two or one)
+    int t = 0;
+    for (; t + 3 <= p.log_m; t += 3) {
+        for (int u = threadIdx.x; u < (tile >> 3); u += blockDim.x) butterfly_group<3>(sm, p, m, t, u);
+        __syncthreads();
+    }
+    if (p.log_m - t == 2) {
+        for (int u = threadIdx.x; u < (tile >> 2); u += blockDim.x) butterfly_group<2>(sm, p, m, t, u);
+        __syncthreads();
+    } else if (p.log_m - t == 1) {
+        for (int u = threadIdx.x; u < (tile >> 1); u += blockDim.x) butterfly_group<1>(sm, p, m, t, u);
         __syncthreads();
     }
 
@@ -86,7 +122,7 @@ __global__ void __launch_bounds__(kNttThreads) k_ntt_pass(NttPass p) {
         if (p.out_col_fast) { g = e % p.G; q = e / p.G; } else { g = e >> p.log_m; q = e & (m - 1); }
         size_t col = col0 + g;
         if (col >= p.ncols) continue;
-        fr_t x = load_field<fr_t>(sm + (size_t)(g * m + q) * 32);
+        fr_t x = load_field<fr_t>(sm + (size_t)slot(g * m + q) * 32);
         if (p.tw_unit && q && col) x = x * root_at(p, (size_t)q * col * p.tw_unit);
         if (p.scale) x = x * sc;
         store_field(out + (col * p.out_cstride + (size_t)q * p.out_rstride) * 32, x);
