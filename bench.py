@@ -52,34 +52,47 @@ def rand_blobs(rng, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every 20 ms during the timed region (B200_PROFILING.md recipe; NVML is what
+    nvidia-smi reads -- a piped `nvidia-smi -lms` block-buffers its output, so the library is polled directly)"""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.sm, self.bits, self.mx, self.index = [], 0, None, index
+        self.stop_flag, self.thread = threading.Event(), None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            return
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        def loop():
+            while not self.stop_flag.is_set():
+                try:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.bits |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    pass
+                time.sleep(0.02)
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def mark(self):
+        """forget samples taken so far (called right before the timed region)"""
+        self.sm, self.bits = [], 0
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        reasons = sorted(n for b, n in self.REASONS.items() if self.bits & b)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": reasons, "samples": len(self.sm)}
 
 
 def load_bases():
@@ -189,7 +202,7 @@ def main():
 
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()          # nvidia-smi takes a moment to start: sample from the warm-up through the e2e leg
+        sampler.start()          # samples from here are dropped at mark(); kept ones span the timed region + e2e leg
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -203,6 +216,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -280,7 +294,7 @@ def main():
 
     # ---- CPU baseline beside it: oracle port on the host cores, bounded sample ------------------------------------
     cores = os.cpu_count() or 1
-    n_cpu = 1 << min(LOG_N, 18)
+    n_cpu = 1 << min(LOG_N, 20 if cores >= 8 else 18)   # ~10-30 core-seconds of CPU work
     cpu_value, cpu_dt = cpu_baseline(K, L, n_cpu, cores)
     cpu = {"value": cpu_value, "unit": "G1-adds/s", "cores": cores, "kind": "port",
            "sample": "first 2^%d terms of the 2^%d-term MSM, %.2f s on %d threads; C restatement of "

@@ -195,11 +195,11 @@ __global__ void __launch_bounds__(32) k_validate_commitments(const uint8_t* __re
 static constexpr int kQThreads = 256;
 static constexpr int kQPer = (int)(kFieldElementsPerBlob / kQThreads);  // 16
 
-__device__ __forceinline__ frc_t block_sum_fr(frc_t v, uint8_t* sh /* 8 Fr */) {
+__device__ __forceinline__ fr_t block_sum_fr(fr_t v, uint8_t* sh /* 8 Fr */) {
     // warp tree through shuffles, then the 8 warp leaders through shared memory; result valid in every thread
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
-        frc_t o;
+        fr_t o;
 #pragma unroll
         for (int k = 0; k < 8; k++) o.v[k] = __shfl_down_sync(0xffffffffu, v.v[k], d);
         v = v + o;
@@ -208,8 +208,8 @@ __device__ __forceinline__ frc_t block_sum_fr(frc_t v, uint8_t* sh /* 8 Fr */) {
     __syncthreads();
     if (lane == 0) store_field(sh + wid * 32, v);
     __syncthreads();
-    frc_t total = load_field<frc_t>(sh);
-    for (int w = 1; w < kQThreads / 32; w++) total = total + load_field<frc_t>(sh + w * 32);
+    fr_t total = load_field<fr_t>(sh);
+    for (int w = 1; w < kQThreads / 32; w++) total = total + load_field<fr_t>(sh + w * 32);
     return total;
 }
 
@@ -222,68 +222,68 @@ __global__ void __launch_bounds__(kQThreads) k_quotient(const uint8_t* __restric
     int* found = reinterpret_cast<int*>(red + 8 * 32);
     const size_t blob = blockIdx.x;
     const uint8_t* p = poly + blob * kFieldElementsPerBlob * 32;
-    const frc_t z = load_field<frc_t>(z_all + blob * 32);
+    const fr_t z = load_field<fr_t>(z_all + blob * 32);
     if (threadIdx.x == 0) *found = -1;
     __syncthreads();
 
     // element k of this thread is i = k * 256 + tid (coalesced across the CTA)
-    frc_t acc = frc_t::one();
+    fr_t acc = fr_t::one();
 #pragma unroll 1
     for (int k = 0; k < kQPer; k++) {
         int i = k * kQThreads + threadIdx.x;
-        frc_t d = z - load_field_ro<frc_t>(domain + (size_t)i * 32);
-        if (d.is_zero()) { *found = i; d = frc_t::one(); }
+        fr_t d = z - load_field_ro<fr_t>(domain + (size_t)i * 32);
+        if (d.is_zero()) { *found = i; d = fr_t::one(); }
         store_field(pref + (size_t)i * 32, acc);
         acc = acc * d;
     }
-    frc_t inv = acc.inverse();
-    frc_t ysum = frc_t::zero();
+    fr_t inv = acc.inverse();
+    fr_t ysum = fr_t::zero();
 #pragma unroll 1
     for (int k = kQPer - 1; k >= 0; k--) {
         int i = k * kQThreads + threadIdx.x;
-        frc_t w = load_field_ro<frc_t>(domain + (size_t)i * 32);
-        frc_t d = z - w;
+        fr_t w = load_field_ro<fr_t>(domain + (size_t)i * 32);
+        fr_t d = z - w;
         bool at_root = d.is_zero();
-        if (at_root) d = frc_t::one();
-        frc_t inv_i = load_field<frc_t>(pref + (size_t)i * 32) * inv;
+        if (at_root) d = fr_t::one();
+        fr_t inv_i = load_field<fr_t>(pref + (size_t)i * 32) * inv;
         inv = inv * d;
         store_field(pref + (size_t)i * 32, inv_i);
-        if (!at_root) ysum = ysum + inv_i * w * load_field_ro<frc_t>(p + (size_t)i * 32);
+        if (!at_root) ysum = ysum + inv_i * w * load_field_ro<fr_t>(p + (size_t)i * 32);
     }
-    frc_t total = block_sum_fr(ysum, red);
+    fr_t total = block_sum_fr(ysum, red);
     const int m = *found;
-    frc_t y;
+    fr_t y;
     if (m >= 0) {
-        y = load_field_ro<frc_t>(p + (size_t)m * 32);
+        y = load_field_ro<fr_t>(p + (size_t)m * 32);
     } else {
         // y = total / 4096 * (z^4096 - 1)
-        frc_t zn = z;
+        fr_t zn = z;
 #pragma unroll 1
         for (int s = 0; s < 12; s++) zn = zn.sqr();
-        frc_t n_inv = frc_t::zero();
+        fr_t n_inv = fr_t::zero();
         n_inv.v[7] = 0x00100000u;  // 4096^-1 in Montgomery form: 2^-12 * 2^256 = 2^244
-        y = total * n_inv * (zn - frc_t::one());
+        y = total * n_inv * (zn - fr_t::one());
     }
     // quotient
-    frc_t qm_sum = frc_t::zero();
+    fr_t qm_sum = fr_t::zero();
 #pragma unroll 1
     for (int k = 0; k < kQPer; k++) {
         int i = k * kQThreads + threadIdx.x;
-        frc_t pi = load_field_ro<frc_t>(p + (size_t)i * 32);
-        frc_t inv_i = load_field<frc_t>(pref + (size_t)i * 32);
-        frc_t q;
+        fr_t pi = load_field_ro<fr_t>(p + (size_t)i * 32);
+        fr_t inv_i = load_field<fr_t>(pref + (size_t)i * 32);
+        fr_t q;
         if (i == m) {
-            q = frc_t::zero();
+            q = fr_t::zero();
         } else {
             q = (y - pi) * inv_i;
-            if (m >= 0) qm_sum = qm_sum + (pi - y) * load_field_ro<frc_t>(domain + (size_t)i * 32) * inv_i;
+            if (m >= 0) qm_sum = qm_sum + (pi - y) * load_field_ro<fr_t>(domain + (size_t)i * 32) * inv_i;
         }
         store_field(q_out + (blob * kFieldElementsPerBlob + i) * 32, q.from_mont());
     }
     if (m >= 0) {
-        frc_t t = block_sum_fr(qm_sum, red);
+        fr_t t = block_sum_fr(qm_sum, red);
         if (threadIdx.x == 0) {
-            frc_t qm = t * z.inverse();
+            fr_t qm = t * z.inverse();
             store_field(q_out + (blob * kFieldElementsPerBlob + m) * 32, qm.from_mont());
         }
     }

@@ -6,10 +6,12 @@
 #include <vector>
 
 #include "g1.cuh"
+#include "g1_quad.cuh"
 #include "util.cuh"
 
 namespace b200 {
 
+static constexpr int kMinTaskLen = 4;     // shortest accumulate task (entries) for latency-bound calls
 static constexpr int kAccThreads = 128;  // accumulate CTA: 4 warps, one per SM sub-partition
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(256) k_task_emit(const uint32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------------
 // 5: bucket accumulation -- the dominant kernel.  One thread per task; the running XYZZ sum lives in registers, each
 // step gathers one 96-byte affine point (six 128-bit read-only loads) and does a mixed addition (8M + 2S).
+template <bool PREFETCH>
 __global__ void __launch_bounds__(kAccThreads) k_accumulate(const uint8_t* __restrict__ table,
                                                             const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ sorted_tasks,
@@ -234,11 +237,28 @@ __global__ void __launch_bounds__(kAccThreads) k_accumulate(const uint8_t* __res
     uint32_t start = sorted_tasks[3 * t], len = sorted_tasks[3 * t + 1], slot = sorted_tasks[3 * t + 2];
     xyzz_t acc = xyzz_t::inf();
     const uint32_t* e = entries + start;
-    for (uint32_t k = 0; k < len; k++) {
-        uint32_t v = e[k];
+    if (PREFETCH) {
+        // software pipeline: the gather of point k+1 (index load, then six 128-bit loads) is in flight during the
+        // ~4000-instruction addition of point k
+        uint32_t v = e[0];
         affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
-        p.y = p.y.cneg(v >> 31);
-        xyzz_add_affine(acc, p);
+        for (uint32_t k = 0; k < len; k++) {
+            affine_t cur = p;
+            uint32_t cv = v;
+            if (k + 1 < len) {
+                v = e[k + 1];
+                p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
+            }
+            cur.y = cur.y.cneg(cv >> 31);
+            xyzz_add_affine(acc, cur);
+        }
+    } else {
+        for (uint32_t k = 0; k < len; k++) {
+            uint32_t v = e[k];
+            affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
+            p.y = p.y.cneg(v >> 31);
+            xyzz_add_affine(acc, p);
+        }
     }
     store_xyzz(partials + (size_t)slot * 192, acc);
 }
@@ -419,26 +439,6 @@ __global__ void __launch_bounds__(kAccThreads) k_accumulate_call(const uint8_t* 
 // i.e. D*32 independent plain sums (tree reductions) followed by D weighted sums over <= 32 items, each done by one
 // warp with a suffix scan in registers (sum_v v*M_v = sum_{k>=1} Suf_k).  Depth ~ 30 additions instead of 2^c.
 
-__device__ __forceinline__ fp_t shfl_down_fp(const fp_t& a, int d) {
-    fp_t r;
-#pragma unroll
-    for (int i = 0; i < 12; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
-    return r;
-}
-__device__ __forceinline__ xyzz_t shfl_down_xyzz(const xyzz_t& v, int d) {
-    xyzz_t o;
-    o.x = shfl_down_fp(v.x, d); o.y = shfl_down_fp(v.y, d); o.zzz = shfl_down_fp(v.zzz, d); o.zz = shfl_down_fp(v.zz, d);
-    return o;
-}
-// lane 0 ends up with the sum over the warp
-__device__ __forceinline__ xyzz_t warp_sum_xyzz(xyzz_t v) {
-#pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) {
-        xyzz_t o = shfl_down_xyzz(v, d);
-        xyzz_add(v, o);
-    }
-    return v;
-}
 // inclusive suffix scan: lane l gets sum_{m >= l} v_m
 __device__ __forceinline__ xyzz_t warp_suffix_scan_xyzz(xyzz_t v) {
     int lane = threadIdx.x & 31;
@@ -452,34 +452,63 @@ __device__ __forceinline__ xyzz_t warp_suffix_scan_xyzz(xyzz_t v) {
 }
 
 // 6a: buckets that were cut into several tasks: fold the task partials into the first slot.
-// WARP = false: one thread per bucket, 2..32 partials.  WARP = true: one warp per bucket with more than 32 partials.
-template <bool WARP>
+// Buckets with 2..32 partials: one thread per bucket when there are many buckets (throughput-bound), or, SUB = true,
+// kCombLanes lanes per bucket when there are few (latency-bound: strided partial sums, then a quad tree -- the chain is
+// ceil(tc/kCombLanes) + log2(kCombLanes) additions deep instead of tc - 1).
+// WARP = true: a small grid of warps strides over the keys and folds buckets with more than 32 partials.
+static constexpr int kCombLanes = 8;
+template <bool WARP, bool SUB>
 __global__ void __launch_bounds__(128) k_bucket_combine(uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
                                                         size_t nkeys) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t key = WARP ? gid >> 5 : gid;
+    if (WARP) {
+        // rare case (adversarial scalar distributions)
+        const int lane = threadIdx.x & 31;
+        const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+        for (size_t key = gid >> 5; key < nkeys; key += nwarps) {
+            uint32_t s0 = task_base[key], s1 = task_base[key + 1];
+            if (s1 - s0 <= 32) continue;
+            xyzz_t acc = xyzz_t::inf();
+            for (uint32_t s = s0 + lane; s < s1; s += 32) {
+                xyzz_t part = load_xyzz(partials + (size_t)s * 192);
+                xyzz_add(acc, part);
+            }
+            fp_t q = seg_sum_quad(acc, 32);
+            if (lane < 4) store_field(partials + (size_t)s0 * 192 + quad_store_offset(), q);
+        }
+        return;
+    }
+    if (SUB) {
+        const size_t key = gid / kCombLanes;
+        const int sub = (int)(gid % kCombLanes);
+        uint32_t s0 = 0, s1 = 0;
+        if (key < nkeys) { s0 = task_base[key]; s1 = task_base[key + 1]; }
+        const uint32_t tc = s1 - s0;
+        const bool live = tc >= 2 && tc <= 32;
+        // a warp none of whose buckets was cut has nothing to do
+        if (!__any_sync(0xffffffffu, live)) return;
+        xyzz_t acc = xyzz_t::inf();
+        if (live) {
+            for (uint32_t s = s0 + sub; s < s1; s += kCombLanes) {
+                xyzz_t part = load_xyzz(partials + (size_t)s * 192);
+                xyzz_add(acc, part);
+            }
+        }
+        fp_t q = seg_sum_quad(acc, kCombLanes);
+        if (live && sub < 4) store_field(partials + (size_t)s0 * 192 + quad_store_offset(), q);
+        return;
+    }
+    const size_t key = gid;
     if (key >= nkeys) return;
     uint32_t s0 = task_base[key], s1 = task_base[key + 1];
     uint32_t tc = s1 - s0;
-    if (WARP) {
-        if (tc <= 32) return;
-        int lane = threadIdx.x & 31;
-        xyzz_t acc = xyzz_t::inf();
-        for (uint32_t s = s0 + lane; s < s1; s += 32) {
-            xyzz_t part = load_xyzz(partials + (size_t)s * 192);
-            xyzz_add(acc, part);
-        }
-        acc = warp_sum_xyzz(acc);
-        if (lane == 0) store_xyzz(partials + (size_t)s0 * 192, acc);
-    } else {
-        if (tc < 2 || tc > 32) return;
-        xyzz_t acc = load_xyzz(partials + (size_t)s0 * 192);
-        for (uint32_t s = s0 + 1; s < s1; s++) {
-            xyzz_t part = load_xyzz(partials + (size_t)s * 192);
-            xyzz_add(acc, part);
-        }
-        store_xyzz(partials + (size_t)s0 * 192, acc);
+    if (tc < 2 || tc > 32) return;
+    xyzz_t acc = load_xyzz(partials + (size_t)s0 * 192);
+    for (uint32_t s = s0 + 1; s < s1; s++) {
+        xyzz_t part = load_xyzz(partials + (size_t)s * 192);
+        xyzz_add(acc, part);
     }
+    store_xyzz(partials + (size_t)s0 * 192, acc);
 }
 
 struct AxisPlan {
@@ -489,7 +518,7 @@ struct AxisPlan {
 };
 
 // 6b: marginal sums.  CTA (v, a, g) adds up the nb >> w[a] buckets of group g whose digit a equals v.
-static constexpr int kMargThreads = 128;
+template <int kMargThreads>
 __global__ void __launch_bounds__(kMargThreads) k_marginals(const uint8_t* __restrict__ partials,
                                                             const uint32_t* __restrict__ task_base, int nb, AxisPlan ap,
                                                             uint8_t* __restrict__ marg) {
@@ -513,19 +542,16 @@ __global__ void __launch_bounds__(kMargThreads) k_marginals(const uint8_t* __res
             xyzz_add(acc, part);
         }
     }
-    acc = warp_sum_xyzz(acc);
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) store_xyzz(sh + wid * 192, acc);
+    // warp sums (quad-distributed), then the kMargThreads/32 warp results are folded by warp 0, one quad each
+    fp_t q = seg_sum_quad(acc, 32);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane < 4) store_field(sh + wid * 192 + quad_store_offset(), q);
     __syncthreads();
     if (wid == 0) {
-        xyzz_t u = lane < (kMargThreads / 32) ? load_xyzz(sh + lane * 192) : xyzz_t::inf();
-        // only kMargThreads/32 lanes hold data: a short tree
-#pragma unroll 1
-        for (int d = (kMargThreads / 64); d >= 1; d >>= 1) {
-            xyzz_t o = shfl_down_xyzz(u, d);
-            xyzz_add(u, o);
-        }
-        if (lane == 0) store_xyzz(dst, u);
+        constexpr int nw = kMargThreads / 32;
+        fp_t a = (lane >> 2) < nw ? load_field<fp_t>(sh + (lane >> 2) * 192 + quad_store_offset()) : fp_t::zero();
+        a = quad_tree(a, 4 * nw);
+        if (lane < 4) store_field(dst + quad_store_offset(), a);
     }
 }
 
@@ -561,54 +587,62 @@ __global__ void __launch_bounds__(128) k_marginals_sub(const uint8_t* __restrict
             }
         }
     }
-#pragma unroll 1
-    for (int d = S >> 1; d >= 1; d >>= 1) {
-        xyzz_t o = shfl_down_xyzz(acc, d);
-        if (sub + d >= S) o = xyzz_t::inf();
-        xyzz_add(acc, o);
+    uint8_t* dst = marg + ((g * 3 + a) * 32 + v) * 192;
+    if (S >= 4) {
+        fp_t q = seg_sum_quad(acc, S);
+        if (live && sub < 4) store_field(dst + quad_store_offset(), q);
+    } else {
+        if (S == 2) {
+            xyzz_t o = shfl_down_xyzz(acc, 1);
+            if (sub) o = xyzz_t::inf();
+            xyzz_add(acc, o);
+        }
+        if (live && sub == 0) store_xyzz(dst, acc);
     }
-    if (live && sub == 0) store_xyzz(marg + ((g * 3 + a) * 32 + v) * 192, acc);
 }
 
 // 6c: one CTA per group, one warp per digit axis: weighted sum over the <= 32 marginals, scale by 2^sh, combine.
+// Everything after the suffix scan runs on quad-distributed points (g1_quad.cuh).
 __global__ void __launch_bounds__(96) k_group_finish(const uint8_t* __restrict__ marg, AxisPlan ap,
                                                      uint8_t* __restrict__ group_sums, uint8_t* __restrict__ out_jac) {
     __shared__ __align__(16) uint8_t sh[4 * 192];
     const size_t g = blockIdx.x;
     const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
+    const int off = quad_store_offset();
     if (a < ap.D) {
         xyzz_t m = load_xyzz(marg + ((g * 3 + a) * 32 + lane) * 192);
         xyzz_t suf = warp_suffix_scan_xyzz(m);          // Suf_l = sum_{v >= l} M_v ; Suf_0 = sum of all buckets
         if (a == 0 && lane == 0) store_xyzz(sh + 3 * 192, suf);
         if (lane == 0) suf = xyzz_t::inf();              // sum_v v*M_v = sum_{k >= 1} Suf_k
-        xyzz_t wsum = warp_sum_xyzz(suf);
-        if (lane == 0) {
-            for (int k = 0; k < ap.sh[a]; k++) xyzz_dbl(wsum);
-            store_xyzz(sh + a * 192, wsum);
-        }
+        fp_t w = seg_sum_quad(suf, 32);
+        for (int k = 0; k < ap.sh[a]; k++) w = quad_dbl(w);
+        if (lane < 4) store_field(sh + a * 192 + off, w);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        xyzz_t acc = load_xyzz(sh + 3 * 192);            // the "+1" of the weights b+1
-        for (int k = 0; k < ap.D; k++) {
-            xyzz_t o = load_xyzz(sh + k * 192);
-            xyzz_add(acc, o);
+    if (a == 0) {
+        fp_t acc = load_field<fp_t>(sh + 3 * 192 + off);  // the "+1" of the weights b+1
+        for (int k = 0; k < ap.D; k++) acc = quad_add(acc, load_field<fp_t>(sh + k * 192 + off));
+        if (group_sums && lane < 4) store_field(group_sums + g * 192 + off, acc);
+        if (out_jac) {
+            // Jacobian (X*ZZ, Y*ZZZ, ZZ), see xyzz_to_jac; infinity is all-zero in both forms
+            fp_t t = acc * shfl_xor_fp(acc, 2);
+            if (lane < 2) store_field(out_jac + g * 144 + lane * 48, t);
+            if (lane == 2) store_field(out_jac + g * 144 + 96, acc);
         }
-        if (group_sums) store_xyzz(group_sums + g * 192, acc);
-        if (out_jac) store_jac(out_jac + g * 144, xyzz_to_jac(acc));
     }
 }
 // 7 (VARIABLE): result = sum_j 2^(c*j) S_j, Horner from the top window (as tiling_pippenger does,
-// kzg/src/msm/tiling_pippenger_ops.rs:106-138).  One thread: W*c doublings.
-__global__ void k_horner(const uint8_t* __restrict__ group_sums, int W, int c, uint8_t* __restrict__ out_jac) {
-    if (threadIdx.x || blockIdx.x) return;
-    cc::xyzz_t acc = cc::load_xyzz(group_sums + (size_t)(W - 1) * 192);
+// kzg/src/msm/tiling_pippenger_ops.rs:106-138).  One warp, quad-distributed: W*c doublings of three levels each.
+__global__ void __launch_bounds__(32) k_horner(const uint8_t* __restrict__ group_sums, int W, int c, uint8_t* __restrict__ out_jac) {
+    const int lane = threadIdx.x & 31, off = quad_store_offset();
+    fp_t acc = load_field<fp_t>(group_sums + (size_t)(W - 1) * 192 + off);
     for (int j = W - 2; j >= 0; j--) {
-        for (int k = 0; k < c; k++) cc::xyzz_dbl(acc);
-        cc::xyzz_t s = cc::load_xyzz(group_sums + (size_t)j * 192);
-        cc::xyzz_add(acc, s);
+        for (int k = 0; k < c; k++) acc = quad_dbl(acc);
+        acc = quad_add(acc, load_field<fp_t>(group_sums + (size_t)j * 192 + off));
     }
-    cc::store_jac(out_jac, cc::xyzz_to_jac(acc));
+    fp_t t = acc * shfl_xor_fp(acc, 2);
+    if (lane < 2) store_field(out_jac + lane * 48, t);
+    if (lane == 2) store_field(out_jac + 96, acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -767,10 +801,20 @@ void MsmEngine::set_points(const void* points_dev, size_t npoints, cudaStream_t 
 void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mont, void* out_dev, cudaStream_t st,
                     const void* scalars_host) {
     if (npoints > cfg_.n || batch < 1 || batch > cfg_.max_batch) throw CudaError(-1, "MsmEngine::run: bad sizes");
-    const int c = cfg_.c, W = cfg_.W, L = cfg_.L;
+    const int c = cfg_.c, W = cfg_.W;
     const size_t groups = cfg_.fixed ? (size_t)batch : (size_t)W;
     const size_t nkeys = groups * nb_;
     const size_t total = (size_t)batch * npoints;
+    // task length: cfg_.L when the call fills the machine; short calls (one blob, 2^12-point MSMs) are latency-bound
+    // -- a thread's serial chain is L additions of ~10 us each with one warp per scheduler -- so they are cut into
+    // more, shorter tasks (down to kMinTaskLen) and the partial sums folded by the sub-warp trees of k_bucket_combine
+    int L = cfg_.L;
+    {
+        const size_t fill = (size_t)148 * 4 * 32 * 2;   // two warps on every SM sub-partition
+        size_t want = std::max<size_t>(kMinTaskLen, total * W / fill);
+        if ((size_t)L > want) L = (int)want;
+        while (L < cfg_.L && total * W / L + nkeys + 1 > tasks_max_) L++;
+    }
     int launches = 0;
     if (total == 0) {
         B200_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, (size_t)batch * 144, st));
@@ -858,23 +902,30 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     // 5 accumulate: grid sized for the worst case, surplus threads exit on the device-side task count
     size_t tasks_bound = std::min(tasks_max_, total * W / L + nkeys + 1);
     static const bool acc_call = getenv("B200_ACC_CALL") && atoi(getenv("B200_ACC_CALL"));
+    static const bool acc_prefetch = !getenv("B200_ACC_PREFETCH") || atoi(getenv("B200_ACC_PREFETCH"));  // default on: -2.2% at 2^20
     if (reduced)
         k_accumulate_direct<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>(reduced, sorted_tasks_, task_base_ + nkeys,
                                                                                      (uint8_t*)partials_);
     else if (acc_call)
         k_accumulate_call<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
                                                                                    task_base_ + nkeys, (uint8_t*)partials_);
+    else if (acc_prefetch)
+        k_accumulate<true><<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
+                                                                                    task_base_ + nkeys, (uint8_t*)partials_);
     else
-        k_accumulate<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
-                                                                              task_base_ + nkeys, (uint8_t*)partials_);
+        k_accumulate<false><<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
+                                                                                     task_base_ + nkeys, (uint8_t*)partials_);
     if (prof) {
         B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_ + 1], st));
         prof_count_++;
     }
     launches++;
     // 6 reduce
-    k_bucket_combine<false><<<div_up(nkeys, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
-    k_bucket_combine<true><<<div_up(nkeys * 32, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
+    if (nkeys <= 8192)
+        k_bucket_combine<false, true><<<div_up(nkeys * kCombLanes, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
+    else
+        k_bucket_combine<false, false><<<div_up(nkeys, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
+    k_bucket_combine<true, false><<<148 * 4, 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
     AxisPlan ap{};
     {
         int bits = c - 1;
@@ -902,7 +953,12 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
                                                                              (uint8_t*)chunk_sums_);
         launches += 3;
     } else {
-        k_marginals<<<dim3(32, ap.D, (unsigned)groups), kMargThreads, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap,
+        // one CTA per marginal; 256 threads once a marginal covers >= 1024 buckets (shorter serial chains)
+        if ((nb_ >> ap.w[0]) >= 1024)
+            k_marginals<256><<<dim3(32, ap.D, (unsigned)groups), 256, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap,
+                                                                              (uint8_t*)chunk_sums_);
+        else
+            k_marginals<128><<<dim3(32, ap.D, (unsigned)groups), 128, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap,
                                                                               (uint8_t*)chunk_sums_);
         launches += 3;
     }

@@ -61,3 +61,14 @@ elif what == "proof":
     for _ in range(reps):
         ts.compute_kzg_proof_device(d_out.data_ptr(), d_y.data_ptr(), d_blobs.data_ptr(), d_z.data_ptr(), nb, d_st.data_ptr(), 0, 0)
     torch.cuda.synchronize()
+elif what in ("cells", "fk20"):
+    ts = B.KZGSettings.load_trusted_setup_file()
+    nb = n
+    blobs = rng.integers(0, 256, size=(nb, 4096, 32), dtype=np.uint8)
+    blobs[:, :, 0] = 0
+    blobs = blobs.reshape(nb, 131072)
+    if what == "fk20":
+        ts.compute_cell_proofs_batch(blobs[:1])      # builds the FK20 table outside the launches of interest
+    for _ in range(reps):
+        (ts.compute_cells_batch if what == "cells" else ts.compute_cell_proofs_batch)(blobs)
+    torch.cuda.synchronize()

@@ -1,0 +1,15 @@
+#!/bin/bash
+# regenerates the ncu launch lists (and one --set full capture of k_accumulate) under gpurun_out/; run under gpurun
+set -x
+mkdir -p gpurun_out
+NCU="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
+$NCU -c 400 --log-file gpurun_out/launches_msm_20.csv python scripts/ncu_target.py msm 20 2 > /dev/null 2>&1
+$NCU -c 400 --log-file gpurun_out/launches_msm_12.csv python scripts/ncu_target.py msm 12 2 > /dev/null 2>&1
+$NCU -c 400 --log-file gpurun_out/launches_blob64.csv python scripts/ncu_target.py blob 64 2 > /dev/null 2>&1
+$NCU -c 400 --log-file gpurun_out/launches_blob1.csv python scripts/ncu_target.py blob 1 2 > /dev/null 2>&1
+$NCU -c 600 --log-file gpurun_out/launches_proof64.csv python scripts/ncu_target.py proof 64 2 > /dev/null 2>&1
+$NCU -c 400 --log-file gpurun_out/launches_ntt20.csv python scripts/ncu_target.py ntt 20 3 > /dev/null 2>&1
+$NCU -c 3000 --log-file gpurun_out/launches_fk20.csv python scripts/ncu_target.py fk20 16 1 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_accumulate -s 1 -c 1 -f -o gpurun_out/prof_accumulate_2p20 \
+    python scripts/ncu_target.py msm 20 2 > /dev/null 2>&1
+ls -la gpurun_out
