@@ -288,7 +288,7 @@ def main():
                     "fp_mul_per_s_measured": mb["fpmul_per_s"],
                     "note": "achieved counts 3000 algorithmic multiply-adds per bucket addition (10 Fp mul x 300); every "
                             "IMAD.WIDE form issues at 32/clk/SM on sm_100a (measured, with or without carry), ncu shows "
-                            "the FMA-heavy pipe 83% busy in k_accumulate (profiles/r01_accumulate_full.md)"}
+                            "the FMA-heavy pipe 86% busy in k_accumulate (profiles/r01_accumulate_full.md)"}
     if int_roofline["achieved"]:
         int_roofline["frac"] = int_roofline["achieved"] / int_roofline["peak"]
 
@@ -308,7 +308,7 @@ def main():
                                "per GPU; prepared fixed-base table resident in HBM" % LOG_N,
                    "points_per_s": value / ADDS_PER_TERM, "window_bits": info["c"], "windows": info["W"],
                    "table_bytes": info["table_bytes"], "seed": SEED, "prng": "numpy PCG64",
-                   "l2": "inputs larger than L2: 32 MiB scalars + %.1f GiB table per step" % (info["table_bytes"] / 2 ** 30),
+                   "l2": "inputs larger than L2: %d MiB scalars + %.1f GiB table per step" % (n * 32 >> 20, info["table_bytes"] / 2 ** 30),
                    "parity": "compressed result == folded-scalar oracle (checked before timing)",
                    "multi_gpu": "terms sharded by rank, NCCL all-gather of 144 B partial results + local add" if world > 1 else "single GPU"},
         "clocks": clocks,
@@ -438,6 +438,27 @@ def extra_metrics(B, K, osettings, torch):
         K.blob_to_kzg_commitment(blobs[i].tobytes(), osettings)
     ex["blob_to_kzg_commitment"]["cpu_port_blobs_per_s"] = 4 / (time.perf_counter() - t0)
     ex["blob_to_kzg_commitment"]["cpu_cores"] = os.cpu_count()
+    # EIP-7594 producer: cells (NTT-8192) and FK20 cell proofs, 64 blobs, host numpy in and out
+    try:
+        ts.compute_cell_proofs_batch(blobs[:1])           # builds the 128 x 64 FK20 table on first use
+        t0 = time.perf_counter()
+        cells = ts.compute_cells_batch(blobs)
+        dt_cells = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        proofs = ts.compute_cell_proofs_batch(blobs)
+        dt_proofs = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oc, op = K.compute_cells_and_kzg_proofs(blobs[3].tobytes(), osettings)
+        dt_cpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        K.compute_cells_and_kzg_proofs(blobs[4].tobytes(), osettings)
+        dt_cpu = min(dt_cpu, time.perf_counter() - t0)   # the first call also builds the oracle's FK20 columns
+        ex["compute_cells_and_kzg_proofs"] = {
+            "blobs_per_s": nb / (dt_cells + dt_proofs), "cells_ms_per_batch": dt_cells * 1e3, "proofs_ms_per_batch": dt_proofs * 1e3,
+            "batch": nb, "parity_ok": bool(np.asarray(cells[3]).tobytes() == b"".join(oc) and np.asarray(proofs[3]).tobytes() == b"".join(op)),
+            "cpu_port_blobs_per_s": 1.0 / dt_cpu, "cpu_cores": os.cpu_count()}
+    except Exception as e:  # an extra: never lose the headline line over it
+        ex["compute_cells_and_kzg_proofs"] = {"error": repr(e)[:200]}
     ts.free()
     # Fr NTT sweep (BASELINE config 4)
     fs = B.FFTSettings(20)

@@ -75,7 +75,12 @@ struct KzgCtx {
     uint8_t* d_blobs = nullptr;
     int* d_status = nullptr;
     int* h_status() { return stage[0].h_status(); }
-    ~KzgCtx() { dev.reset(); }
+    uint8_t* d_cells = nullptr;   // max_batch x 128 x 2048, allocated on first use (compute_cells)
+    uint8_t* d_proofs = nullptr;  // fk20 batch x 128 x 48, allocated on first use
+    ~KzgCtx() {
+        cudaFree(d_cells); cudaFree(d_proofs);
+        dev.reset();
+    }
 };
 
 // Run `n` items in chunks of at most `cap`, alternating between the two lanes: chunk k+1 is enqueued (copies, host
@@ -415,9 +420,10 @@ C_KZG_RET b200_compute_cells_batch(Cell* cells, const Blob* blobs, size_t n, con
         auto ctx = find_ctx(s);
         if (!ctx || !cells || !blobs) return C_KZG_BADARGS;
         std::lock_guard<std::mutex> lk(ctx->mu);
-        uint8_t* d_cells = dev_alloc<uint8_t>((size_t)ctx->max_batch * 128 * 2048);
+        if (!ctx->d_cells) ctx->d_cells = dev_alloc<uint8_t>((size_t)ctx->max_batch * 128 * 2048);
+        uint8_t* d_cells = ctx->d_cells;
         C_KZG_RET rc = C_KZG_OK;
-        try {
+        {
             for (size_t off = 0; off < n && rc == C_KZG_OK; off += ctx->max_batch) {
                 int m = (int)std::min<size_t>(ctx->max_batch, n - off);
                 B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
@@ -428,11 +434,7 @@ C_KZG_RET b200_compute_cells_batch(Cell* cells, const Blob* blobs, size_t n, con
                 if (any_set(ctx->h_status(), m)) { rc = C_KZG_BADARGS; break; }
                 B200_CUDA_CHECK(cudaMemcpy(cells + off * 128, d_cells, (size_t)m * 128 * 2048, cudaMemcpyDeviceToHost));
             }
-        } catch (...) {
-            cudaFree(d_cells);
-            throw;
         }
-        cudaFree(d_cells);
         return rc;
     });
 }
@@ -443,9 +445,10 @@ C_KZG_RET b200_compute_cell_proofs_batch(KZGProof* proofs, const Blob* blobs, si
         if (!ctx || !proofs || !blobs) return C_KZG_BADARGS;
         std::lock_guard<std::mutex> lk(ctx->mu);
         const int cap = ctx->dev->fk20_batch(ctx->stream);
-        uint8_t* d_proofs = dev_alloc<uint8_t>((size_t)cap * 128 * 48);
+        if (!ctx->d_proofs) ctx->d_proofs = dev_alloc<uint8_t>((size_t)cap * 128 * 48);
+        uint8_t* d_proofs = ctx->d_proofs;
         C_KZG_RET rc = C_KZG_OK;
-        try {
+        {
             for (size_t off = 0; off < n; off += cap) {
                 int m = (int)std::min<size_t>(cap, n - off);
                 B200_CUDA_CHECK(cudaMemcpyAsync(ctx->d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, ctx->stream));
@@ -456,11 +459,7 @@ C_KZG_RET b200_compute_cell_proofs_batch(KZGProof* proofs, const Blob* blobs, si
                 if (any_set(ctx->h_status(), m)) { rc = C_KZG_BADARGS; break; }
                 B200_CUDA_CHECK(cudaMemcpy(proofs + off * 128, d_proofs, (size_t)m * 128 * 48, cudaMemcpyDeviceToHost));
             }
-        } catch (...) {
-            cudaFree(d_proofs);
-            throw;
         }
-        cudaFree(d_proofs);
         return rc;
     });
 }

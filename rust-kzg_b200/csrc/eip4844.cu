@@ -364,12 +364,15 @@ __global__ void __launch_bounds__(256) k_fk_toeplitz(const uint8_t* __restrict__
     }
     store_field(out + gid * 32, v);
 }
-// coeffs[j][i] = fft[(b, i)][j]: transpose into the MSM's scalar layout [vector = b*128 + j][i], canonical form
-__global__ void __launch_bounds__(256) k_fk_transpose(const uint8_t* __restrict__ fft, uint8_t* __restrict__ scalars, size_t total) {
+// coeffs[j][i] = fft[(b, i)][j]: transpose into the MSM's scalar layout [vector = b*128 + j][i], canonical form.
+// The scalars are multiplied by 1/128 here: the inverse fft_g1 that follows the lincombs is linear, so scaling its
+// inputs replaces the [n^-1] scalar multiplication of every output point (blst/src/fft_g1.rs:74-79) by one Fr product.
+__global__ void __launch_bounds__(256) k_fk_transpose(const uint8_t* __restrict__ fft, uint8_t* __restrict__ scalars, size_t total,
+                                                      const uint8_t* __restrict__ inv_n) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     size_t i = gid % kCellSize, vj = gid / kCellSize, j = vj % kFkK2, b = vj / kFkK2;
-    fr_t v = load_field_ro<fr_t>(fft + ((b * kCellSize + i) * kFkK2 + j) * 32).from_mont();
+    fr_t v = (load_field_ro<fr_t>(fft + ((b * kCellSize + i) * kFkK2 + j) * 32) * load_field_ro<fr_t>(inv_n)).from_mont();
     store_field(scalars + gid * 32, v);
 }
 
@@ -492,7 +495,7 @@ void KzgSettingsDev::compute_cells(const uint8_t* blobs, int n, uint8_t* cells_o
 
 void KzgSettingsDev::ensure_fk20(cudaStream_t st) {
     if (fk_msm_) return;
-    fk_batch_ = std::max(1, std::min(max_batch_, env_int_local("B200_FK20_BATCH", 16)));
+    fk_batch_ = std::max(1, std::min(max_batch_, env_int_local("B200_FK20_BATCH", 64)));
     const int npts = kCellSize * kFkK2;  // 8192
     uint8_t* x_ext = dev_alloc<uint8_t>((size_t)npts * 144);
     uint8_t* points = dev_alloc<uint8_t>((size_t)npts * 144);
@@ -537,12 +540,12 @@ void KzgSettingsDev::compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* p
     k_fk_toeplitz<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)cells_b_, (uint8_t*)fk_a_, tt);
     B200_LAUNCH_CHECK();
     fs_->fft_fr(fk_a_, fk_b_, kFkK2, false, n * kCellSize, st);
-    k_fk_transpose<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)fk_b_, (uint8_t*)fk_a_, tt);
+    k_fk_transpose<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)fk_b_, (uint8_t*)fk_a_, tt, (const uint8_t*)fs_->inv_pow2_dev(7));
     B200_LAUNCH_CHECK();
     // g1_lincomb_batch: 128 lincombs of 64 fixed points per blob (kzg/src/das.rs:676-680)
     fk_msm_->run(fk_a_, kCellSize, n * kFkK2, false, fk_pts_, st);
     // h = inverse fft_g1, upper half := identity, forward fft_g1 (:682-695)
-    fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, true, n, st);
+    fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, true, n, st, /*apply_scale=*/false);
     B200_CUDA_CHECK(cudaMemset2DAsync((uint8_t*)fk_pts_ + (size_t)kFkK * 144, (size_t)kFkK2 * 144, 0, (size_t)kFkK * 144, n, st));
     fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, false, n, st);
     launch_points_to_compressed(fk_pts_, proofs48, n * kFkK2, st, 7);  // reverse_bit_order(proofs) (:287)

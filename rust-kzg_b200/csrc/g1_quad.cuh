@@ -175,6 +175,33 @@ __device__ __forceinline__ fp_t quad_tree(fp_t a, int lanes) {
     }
     return a;
 }
+// [k] p for quad-distributed p; k canonical little-endian words, the same value on the four lanes of a quad.
+// Fixed 4-bit windows, most significant first: 16-entry table of multiples per quad in shared memory
+// (kQuadTableBytes per warp; every lane only ever touches its own component slots, so no synchronisation), then 64 x
+// (4 quad doublings + 1 quad addition).  The instruction stream is uniform across the warp's quads -- with a
+// bit-serial double-and-add every quad would pay for an addition whenever any of the eight needs one.
+static constexpr int kQuadTableBytes = 8 * 16 * 192;
+__device__ __forceinline__ fp_t quad_mul_scalar(const fp_t& p, const uint32_t (&k)[8], uint8_t* warp_table) {
+    const int lane = threadIdx.x & 31;
+    uint8_t* tab = warp_table + (lane >> 2) * (16 * 192) + quad_store_offset();
+    store_field(tab, fp_t::zero());
+    store_field(tab + 192, p);
+#pragma unroll 1
+    for (int d = 2; d < 16; d++) {
+        fp_t t = (d & 1) ? quad_add(load_field<fp_t>(tab + (d - 1) * 192), p) : quad_dbl(load_field<fp_t>(tab + (d >> 1) * 192));
+        store_field(tab + d * 192, t);
+    }
+    fp_t acc = load_field<fp_t>(tab + ((k[7] >> 28) & 15) * 192);
+#pragma unroll 1
+    for (int j = 62; j >= 0; j--) {
+#pragma unroll 1
+        for (int r = 0; r < 4; r++) acc = quad_dbl(acc);
+        uint32_t d = (k[j >> 3] >> ((j & 7) * 4)) & 15;
+        acc = quad_add(acc, load_field<fp_t>(tab + d * 192));
+    }
+    return acc;
+}
+
 // lane 0 of the warp ends up with the sum over the warp's 32 points
 __device__ __forceinline__ xyzz_t warp_sum_xyzz(const xyzz_t& v) { return quad_gather(seg_sum_quad(v, 32)); }
 

@@ -226,8 +226,9 @@ __global__ void __launch_bounds__(256) k_task_emit(const uint32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------------
 // 5: bucket accumulation -- the dominant kernel.  One thread per task; the running XYZZ sum lives in registers, each
 // step gathers one 96-byte affine point (six 128-bit read-only loads) and does a mixed addition (8M + 2S).
-template <bool PREFETCH>
-__global__ void __launch_bounds__(kAccThreads) k_accumulate(const uint8_t* __restrict__ table,
+// MINB = CTAs per SM the register allocation is held to: 3 (<= 168 registers) or 4 (<= 128)
+template <bool PREFETCH, int MINB>
+__global__ void __launch_bounds__(kAccThreads, MINB) k_accumulate(const uint8_t* __restrict__ table,
                                                             const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ sorted_tasks,
                                                             const uint32_t* __restrict__ n_tasks_ptr,
@@ -440,10 +441,10 @@ __global__ void __launch_bounds__(kAccThreads) k_accumulate_call(const uint8_t* 
 // warp with a suffix scan in registers (sum_v v*M_v = sum_{k>=1} Suf_k).  Depth ~ 30 additions instead of 2^c.
 
 // inclusive suffix scan: lane l gets sum_{m >= l} v_m
-__device__ __forceinline__ xyzz_t warp_suffix_scan_xyzz(xyzz_t v) {
+__device__ __forceinline__ xyzz_t warp_suffix_scan_xyzz(xyzz_t v, int width) {
     int lane = threadIdx.x & 31;
 #pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {
+    for (int d = 1; d < width; d <<= 1) {   // lanes >= width hold infinity
         xyzz_t o = shfl_down_xyzz(v, d);
         if (lane + d >= 32) o = xyzz_t::inf();
         xyzz_add(v, o);
@@ -462,19 +463,26 @@ __global__ void __launch_bounds__(128) k_bucket_combine(uint8_t* __restrict__ pa
                                                         size_t nkeys) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (WARP) {
-        // rare case (adversarial scalar distributions)
+        // rare case (adversarial scalar distributions): each warp scans 32 keys per step with coalesced loads and
+        // folds the few buckets that have more than 32 partials
         const int lane = threadIdx.x & 31;
         const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-        for (size_t key = gid >> 5; key < nkeys; key += nwarps) {
-            uint32_t s0 = task_base[key], s1 = task_base[key + 1];
-            if (s1 - s0 <= 32) continue;
-            xyzz_t acc = xyzz_t::inf();
-            for (uint32_t s = s0 + lane; s < s1; s += 32) {
-                xyzz_t part = load_xyzz(partials + (size_t)s * 192);
-                xyzz_add(acc, part);
+        for (size_t key0 = (gid >> 5) * 32; key0 < nkeys; key0 += nwarps * 32) {
+            size_t key = key0 + lane;
+            uint32_t my0 = key < nkeys ? task_base[key] : 0, my1 = key < nkeys ? task_base[key + 1] : 0;
+            unsigned big = __ballot_sync(0xffffffffu, my1 - my0 > 32);
+            while (big) {
+                int src = __ffs(big) - 1;
+                big &= big - 1;
+                uint32_t s0 = __shfl_sync(0xffffffffu, my0, src), s1 = __shfl_sync(0xffffffffu, my1, src);
+                xyzz_t acc = xyzz_t::inf();
+                for (uint32_t s = s0 + lane; s < s1; s += 32) {
+                    xyzz_t part = load_xyzz(partials + (size_t)s * 192);
+                    xyzz_add(acc, part);
+                }
+                fp_t q = seg_sum_quad(acc, 32);
+                if (lane < 4) store_field(partials + (size_t)s0 * 192 + quad_store_offset(), q);
             }
-            fp_t q = seg_sum_quad(acc, 32);
-            if (lane < 4) store_field(partials + (size_t)s0 * 192 + quad_store_offset(), q);
         }
         return;
     }
@@ -611,10 +619,11 @@ __global__ void __launch_bounds__(96) k_group_finish(const uint8_t* __restrict__
     const int off = quad_store_offset();
     if (a < ap.D) {
         xyzz_t m = load_xyzz(marg + ((g * 3 + a) * 32 + lane) * 192);
-        xyzz_t suf = warp_suffix_scan_xyzz(m);          // Suf_l = sum_{v >= l} M_v ; Suf_0 = sum of all buckets
+        const int width = 1 << ap.w[a];                  // marginals of this axis; the other lanes read infinity
+        xyzz_t suf = warp_suffix_scan_xyzz(m, width);    // Suf_l = sum_{v >= l} M_v ; Suf_0 = sum of all buckets
         if (a == 0 && lane == 0) store_xyzz(sh + 3 * 192, suf);
         if (lane == 0) suf = xyzz_t::inf();              // sum_v v*M_v = sum_{k >= 1} Suf_k
-        fp_t w = seg_sum_quad(suf, 32);
+        fp_t w = seg_sum_quad(suf, width < 4 ? 4 : width);
         for (int k = 0; k < ap.sh[a]; k++) w = quad_dbl(w);
         if (lane < 4) store_field(sh + a * 192 + off, w);
     }
@@ -646,32 +655,75 @@ __global__ void __launch_bounds__(32) k_horner(const uint8_t* __restrict__ group
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Field inversion shared by a warp.  The binary-Euclid inverse is a data-dependent loop: 32 lanes inverting 32
+// different values run the union of their branch sequences (2.3x the time of one inversion, measured).  Instead the
+// warp forms prefix and suffix products of its inputs with two shuffle scans, every lane inverts the SAME total (no
+// divergence), and 1/z_i = (1/total) * prefix_{i-1} * suffix_{i+1}.
+template <class F>
+__device__ __forceinline__ F shfl_field(const F& a, int src) {
+    F r;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+    return r;
+}
+// 1/z on every lane (z != 0); must be called by all 32 lanes of the warp
+template <class F>
+__device__ __forceinline__ F warp_inverse(const F& z) {
+    const int lane = threadIdx.x & 31;
+    F pre = z, suf = z;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        F t = shfl_field(pre, lane >= d ? lane - d : lane);
+        F u = shfl_field(suf, lane + d < 32 ? lane + d : lane);
+        if (lane >= d) pre = pre * t;
+        if (lane + d < 32) suf = suf * u;
+    }
+    F inv = shfl_field(pre, 31).inverse();                 // identical on all lanes
+    F pl = shfl_field(pre, lane ? lane - 1 : 0), sr = shfl_field(suf, lane < 31 ? lane + 1 : 31);
+    if (lane) inv = inv * pl;
+    if (lane < 31) inv = inv * sr;
+    return inv;
+}
+
 // table rows for FIXED engines: row j = 2^(c*j) * P_i, affine.  One thread per point walks all rows
-// (c doublings in XYZZ, then one field inversion back to affine).  One-time cost at prepare.
+// (c doublings in XYZZ, then back to affine with one warp-shared field inversion).  One-time cost at prepare.
 __global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table, size_t n, int W, int c) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const bool live = i < n;
+    if (!live) i = n - 1;
     cc::affine_t p = cc::load_affine(table + i * 96);
     for (int j = 1; j < W; j++) {
         cc::xyzz_t q = cc::affine_to_xyzz(p);
         for (int k = 0; k < c; k++) cc::xyzz_dbl(q);
-        p = cc::xyzz_to_affine(q);
-        cc::store_affine(table + ((size_t)j * n + i) * 96, p);
+        const bool inf = q.is_inf();
+        // 1/ZZZ; then 1/ZZ = ZZZ^-2 * ZZ^2  (ZZ^3 = ZZZ^2), as xyzz_to_affine
+        cc::fp_t izzz = warp_inverse(inf ? cc::fp_t::one() : q.zzz);
+        cc::fp_t izz = izzz.sqr() * q.zz.sqr();
+        p = inf ? cc::affine_t{cc::fp_t::zero(), cc::fp_t::zero()} : cc::affine_t{q.x * izz, q.y * izzz};
+        if (live) cc::store_affine(table + ((size_t)j * n + i) * 96, p);
     }
 }
 
-// Jacobian -> 48-byte compressed (blst_p1_compress): one thread per point, one inversion each.
+// Jacobian -> 48-byte compressed (blst_p1_compress): one thread per point, one warp-shared field inversion.
 // brp_bits > 0: output index = bit-reversal of the low brp_bits bits of i (reverse_bit_order per group of 2^brp_bits)
-__global__ void k_compress(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count, int brp_bits) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+__global__ void __launch_bounds__(32) k_compress(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count, int brp_bits) {
+    const int lane = threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + lane;
+    const bool live = i < count;
     int o = i;
     if (brp_bits) {
         int low = i & ((1 << brp_bits) - 1);
         o = (i - low) | (int)(__brev((unsigned)low) >> (32 - brp_bits));
     }
-    cc::jac_t p = cc::load_jac(jac + (size_t)i * 144);
-    cc::affine_t a = cc::jac_to_affine(p);
+    cc::jac_t p = live ? cc::load_jac(jac + (size_t)i * 144) : cc::jac_t::inf();
+    const bool inf = p.is_inf();
+    cc::fp_t inv = warp_inverse(inf ? cc::fp_t::one() : p.z);
+    if (!live) return;
+    cc::affine_t a{cc::fp_t::zero(), cc::fp_t::zero()};
+    if (!inf) {
+        cc::fp_t zi2 = inv.sqr();
+        a = cc::affine_t{p.x * zi2, p.y * zi2 * inv};
+    }
     cc::affine_compress(out + (size_t)o * 48, a);
 }
 // sum of `count` Jacobian points by one warp (multi-GPU combine: count = number of ranks)
@@ -909,12 +961,13 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     else if (acc_call)
         k_accumulate_call<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
                                                                                    task_base_ + nkeys, (uint8_t*)partials_);
-    else if (acc_prefetch)
-        k_accumulate<true><<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
-                                                                                    task_base_ + nkeys, (uint8_t*)partials_);
-    else
-        k_accumulate<false><<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
-                                                                                     task_base_ + nkeys, (uint8_t*)partials_);
+    else {
+        static const int acc_occ = getenv("B200_ACC_OCC") ? atoi(getenv("B200_ACC_OCC")) : 3;
+        auto kern = acc_prefetch ? (acc_occ == 4 ? k_accumulate<true, 4> : k_accumulate<true, 3>)
+                                 : (acc_occ == 4 ? k_accumulate<false, 4> : k_accumulate<false, 3>);
+        kern<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
+                                                                       task_base_ + nkeys, (uint8_t*)partials_);
+    }
     if (prof) {
         B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_ + 1], st));
         prof_count_++;

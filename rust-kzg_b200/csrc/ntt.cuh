@@ -33,7 +33,12 @@ public:
     // DASExtension::das_fft_extension (blst/src/data_availability_sampling.rs:78-100): odds from evens, n = len(evens)
     void das_fft_extension(const void* evens_dev, void* odds_dev, size_t n, int batch, cudaStream_t stream);
     // FFTG1::fft_g1 (blst/src/fft_g1.rs:53-83): batch transforms of n Jacobian points (blst_p1), device pointers
-    void fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n, bool inverse, int batch, cudaStream_t stream);
+    // apply_scale = false leaves out the [n^-1] of the inverse transform (a caller that can scale the inputs' scalars
+    // instead saves one scalar multiplication per point: the transform is linear)
+    void fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n, bool inverse, int batch, cudaStream_t stream,
+                bool apply_scale = true);
+    // (2^log_n)^-1 as a Montgomery Fr, device memory
+    const void* inv_pow2_dev(int log_n) const { return (const uint8_t*)roots_ + (max_width_ + 1) * 32 + 33 * 32 + (size_t)log_n * 32; }
     int launches_last() const { return launches_; }
 
 private:
