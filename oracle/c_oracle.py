@@ -13,8 +13,8 @@ _SO = os.path.join(_HERE, "libkzg_oracle.so")
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "kzg_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("kzg_oracle.c", "kzg_oracle_pairing.inc")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return _SO
 
@@ -57,6 +57,10 @@ def _load():
         "ko_compute_kzg_proof": (ci, [vp, vp, vp, vp, vp]), "ko_compute_blob_kzg_proof": (ci, [vp, vp, vp, vp]),
         "ko_compute_cells": (ci, [vp, vp, vp]),
         "ko_compute_cells_and_kzg_proofs": (ci, [vp, vp, vp, vp]), "ko_settings_x_ext_fft_columns": (vp, [vp]),
+        "ko_p2_uncompress": (ci, [vp, vp]), "ko_p2_generator": (None, [vp]), "ko_p2_affine_on_curve": (ci, [vp]),
+        "ko_pairings_verify": (ci, [vp, vp, vp, vp]), "ko_settings_g2_monomial": (vp, [vp]),
+        "ko_verify_kzg_proof": (ci, [vp, vp, vp, vp, vp, vp]), "ko_verify_blob_kzg_proof": (ci, [vp, vp, vp, vp, vp]),
+        "ko_verify_blob_kzg_proof_batch": (ci, [vp, vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(lib, name)
@@ -434,3 +438,62 @@ def compute_cells_and_kzg_proofs(blob: bytes, s: KZGSettings, want_cells=True):
 def x_ext_fft_columns(s: KZGSettings):
     ptr = lib.ko_settings_x_ext_fft_columns(s.h)
     return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(128, 64, 18)).copy()
+
+
+# ---- pairings / verification (kzg/src/eip_4844.rs:328-435, 586-866; blst/src/kzg_proofs.rs:74-100) ----
+def p2_uncompress(b: bytes):
+    """96-byte compressed G2 -> affine (x.c0, x.c1, y.c0, y.c1) as 24 u64 limbs; infinity = all zero"""
+    out = np.zeros(24, np.uint64)
+    if len(b) != 96 or lib.ko_p2_uncompress(_p(out), _p(_bytes_arr(b))):
+        raise OracleError("Failed to uncompress")
+    return out
+
+
+def p2_generator():
+    out = np.zeros(24, np.uint64)
+    lib.ko_p2_generator(_p(out))
+    return out
+
+
+def pairings_verify(a1, a2, b1, b2) -> bool:
+    """e(a1, a2) == e(b1, b2); a1, b1 Jacobian G1 (18 limbs), a2, b2 affine G2 (24 limbs)"""
+    return bool(lib.ko_pairings_verify(_p(_u64(a1)), _p(_u64(a2)), _p(_u64(b1)), _p(_u64(b2))))
+
+
+def g2_monomial(s: KZGSettings):
+    ptr = lib.ko_settings_g2_monomial(s.h)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(65, 24)).copy()
+
+
+def verify_kzg_proof(commitment: bytes, z: bytes, y: bytes, proof: bytes, s: KZGSettings) -> bool:
+    if len(commitment) != 48 or len(z) != 32 or len(y) != 32 or len(proof) != 48:
+        raise OracleError("Invalid byte length")
+    ok = C.c_int(0)
+    if lib.ko_verify_kzg_proof(C.byref(ok), _p(_bytes_arr(commitment)), _p(_bytes_arr(z)), _p(_bytes_arr(y)),
+                               _p(_bytes_arr(proof)), s.h):
+        raise OracleError("bad input")
+    return bool(ok.value)
+
+
+def verify_blob_kzg_proof(blob: bytes, commitment: bytes, proof: bytes, s: KZGSettings) -> bool:
+    if len(commitment) != 48 or len(proof) != 48:
+        raise OracleError("Invalid byte length")
+    ok = C.c_int(0)
+    if lib.ko_verify_blob_kzg_proof(C.byref(ok), _p(_blob(blob)), _p(_bytes_arr(commitment)), _p(_bytes_arr(proof)), s.h):
+        raise OracleError("bad input")
+    return bool(ok.value)
+
+
+def verify_blob_kzg_proof_batch(blobs, commitments, proofs, s: KZGSettings) -> bool:
+    n = len(blobs)
+    if len(commitments) != n or len(proofs) != n:
+        raise OracleError("Invalid amount of arguments")
+    if any(len(c) != 48 for c in commitments) or any(len(p) != 48 for p in proofs):
+        raise OracleError("Invalid byte length")
+    bl = np.concatenate([_blob(b) for b in blobs]) if n else np.zeros(1, np.uint8)
+    cs = _bytes_arr(b"".join(commitments)) if n else np.zeros(1, np.uint8)
+    ps = _bytes_arr(b"".join(proofs)) if n else np.zeros(1, np.uint8)
+    ok = C.c_int(0)
+    if lib.ko_verify_blob_kzg_proof_batch(C.byref(ok), _p(bl), _p(cs), _p(ps), n, s.h):
+        raise OracleError("bad input")
+    return bool(ok.value)

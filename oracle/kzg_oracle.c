@@ -427,6 +427,8 @@ API int ko_p1_uncompress(p1_affine_t *out, const uint8_t in[48]) {
     return 0;
 }
 
+#include "kzg_oracle_pairing.inc"
+
 /* ------------------------------------------------------------------------------------------------------------ */
 /* Pippenger MSM (kzg/src/msm) */
 static inline int xyzz_is_inf(const p1xyzz_t *p) { return fp_is_zero(&p->zzz) && fp_is_zero(&p->zz); }
@@ -1016,6 +1018,7 @@ typedef struct {
     p1_t *g1_lagrange_brp;              /* 4096, bit-reversed (eip_4844.rs:1070) */
     p1_t *g1_monomial;                  /* 4096 */
     p1_t *x_ext_fft_columns;            /* [128 rows][64 offsets], built on first use (kzg_settings.rs:84-101) */
+    p2_affine_t g2_monomial[65];        /* [s^i]G2 (eip_4844.rs:1050-1053) */
     int nthreads;
 } kzg_settings_t;
 
@@ -1047,8 +1050,10 @@ API void *ko_load_trusted_setup_text(const char *text, size_t len) {
     kzg_settings_t *s = (kzg_settings_t *)calloc(1, sizeof(*s));
     s->g1_lagrange_brp = (p1_t *)malloc(4096 * sizeof(p1_t));
     s->g1_monomial = (p1_t *)malloc(4096 * sizeof(p1_t));
-    const uint8_t *lag = raw, *mono = raw + 4096 * 48 + 65 * 96;
+    const uint8_t *lag = raw, *mono = raw + 4096 * 48 + 65 * 96, *g2b = raw + 4096 * 48;
     int bad = 0;
+    for (size_t i = 0; i < 65 && !bad; i++)
+        if (ko_p2_uncompress(&s->g2_monomial[i], g2b + 96 * i)) bad = 1;
     for (size_t i = 0; i < 4096 && !bad; i++) {
         p1_affine_t a;
         if (ko_p1_uncompress(&a, lag + 48 * i)) bad = 1;
@@ -1320,3 +1325,132 @@ API int ko_compute_cells_and_kzg_proofs(uint8_t *cells_out, uint8_t *proofs_out,
     free(poly); free(brp); free(mono);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* EIP-4844 verification (kzg/src/eip_4844.rs:328-435, 586-866).  Return 0 = Ok(*ok), 1 = Err (C ABI: BadArgs). */
+static const uint8_t G1_GEN_COMPRESSED[48] = {  /* compress(G1 generator), zkcrypto/bls12_381/src/g1.rs:179-200 */
+    0x97, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f, 0xc3, 0x68, 0x8c, 0x4f,
+    0x97, 0x74, 0xb9, 0x05, 0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58, 0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef,
+    0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb};
+static void g1_generator(p1_t *g) { p1_affine_t a; ko_p1_uncompress(&a, G1_GEN_COMPRESSED); p1_from_affine(g, &a); }
+static void p1_neg(p1_t *r, const p1_t *p) { *r = *p; fp_neg(&r->y, &r->y); }
+static void p1_sub(p1_t *r, const p1_t *a, const p1_t *b) { p1_t nb; p1_neg(&nb, b); p1_add_or_double(r, a, &nb); }
+/* G1::from_bytes + the "!is_inf && !is_valid" check of verify_kzg_proof_rust (eip_4844.rs:601-606) */
+static int g1_from_bytes_valid(p1_t *out, const uint8_t in[48]) {
+    p1_affine_t a;
+    if (ko_p1_uncompress(&a, in)) return 1;
+    p1_from_affine(out, &a);
+    if (!p1_is_inf(out) && !ko_p1_in_g1(out)) return 1;
+    return 0;
+}
+/* check_proof_single (blst/src/types/kzg_settings.rs:178-196): e(C - [y]G1, G2) == e(proof, [s]G2 - [z]G2) */
+static int check_proof_single(const p1_t *com, const p1_t *proof, const fr_t *z, const fr_t *y, const kzg_settings_t *s) {
+    g2_init();
+    u64 zc[4];
+    fr_to_canon(zc, z);
+    p2_t g2, zg2, sg2, smz;
+    p2_from_affine(&g2, &G2_GEN);
+    p2_mult_canon(&zg2, &g2, zc, 255);
+    fp2_neg(&zg2.y, &zg2.y);
+    p2_from_affine(&sg2, &s->g2_monomial[1]);
+    p2_add_or_double(&smz, &sg2, &zg2);
+    p2_affine_t smz_a; p2_to_affine(&smz_a, &smz);
+    p1_t g1, yg1, cmy;
+    g1_generator(&g1);
+    ko_p1_mult(&yg1, &g1, y);
+    p1_sub(&cmy, com, &yg1);
+    return pairings_verify(&cmy, &G2_GEN, proof, &smz_a);
+}
+/* verify_kzg_proof_raw (eip_4844.rs:612-636) */
+API int ko_verify_kzg_proof(int *ok, const uint8_t commitment[48], const uint8_t z_bytes[32], const uint8_t y_bytes[32],
+                            const uint8_t proof[48], void *h) {
+    kzg_settings_t *s = (kzg_settings_t *)h;
+    p1_affine_t ca, pa; p1_t c, p; fr_t z, y;
+    if (ko_p1_uncompress(&ca, commitment) || ko_fr_from_bendian(&z, z_bytes) || ko_fr_from_bendian(&y, y_bytes) ||
+        ko_p1_uncompress(&pa, proof)) return 1;
+    p1_from_affine(&c, &ca); p1_from_affine(&p, &pa);
+    if (!p1_is_inf(&c) && !ko_p1_in_g1(&c)) return 1;
+    if (!p1_is_inf(&p) && !ko_p1_in_g1(&p)) return 1;
+    *ok = check_proof_single(&c, &p, &z, &y, s);
+    return 0;
+}
+/* verify_blob_kzg_proof_raw (eip_4844.rs:638-698) */
+API int ko_verify_blob_kzg_proof(int *ok, const uint8_t *blob, const uint8_t commitment[48], const uint8_t proof[48], void *h) {
+    kzg_settings_t *s = (kzg_settings_t *)h;
+    fr_t *poly = (fr_t *)malloc(FIELD_ELEMENTS_PER_BLOB * sizeof(fr_t));
+    p1_affine_t ca, pa; p1_t c, p; fr_t z, y;
+    int rc = 1;
+    if (!bytes_to_blob(poly, blob) && !ko_p1_uncompress(&ca, commitment) && !ko_p1_uncompress(&pa, proof)) {
+        p1_from_affine(&c, &ca); p1_from_affine(&p, &pa);
+        if ((p1_is_inf(&c) || ko_p1_in_g1(&c)) && (p1_is_inf(&p) || ko_p1_in_g1(&p))) {
+            compute_challenge(&z, poly, &c);
+            if (!evaluate_polynomial_in_evaluation_form(&y, poly, &z, s)) {
+                *ok = check_proof_single(&c, &p, &z, &y, s);
+                rc = 0;
+            }
+        }
+    }
+    free(poly);
+    return rc;
+}
+/* compute_r_powers + verify_kzg_proof_batch (eip_4844.rs:328-435) */
+static int verify_kzg_proof_batch(const p1_t *cs, const fr_t *zs, const fr_t *ys, const p1_t *ps, size_t n, const kzg_settings_t *s) {
+    g2_init();
+    size_t len = 32 + n * (48 + 32 + 32 + 48);
+    uint8_t *buf = (uint8_t *)calloc(1, len);
+    memcpy(buf, "RCKZGBATCH___V1_", 16);
+    for (int i = 0; i < 8; i++) { buf[16 + i] = (uint8_t)((u64)FIELD_ELEMENTS_PER_BLOB >> (8 * (7 - i))); buf[24 + i] = (uint8_t)((u64)n >> (8 * (7 - i))); }
+    for (size_t i = 0; i < n; i++) {
+        uint8_t *o = buf + 32 + i * 160;
+        ko_p1_compress(o, &cs[i]); ko_fr_to_bendian(o + 48, &zs[i]); ko_fr_to_bendian(o + 80, &ys[i]); ko_p1_compress(o + 112, &ps[i]);
+    }
+    uint8_t d[32]; fr_t r;
+    ko_sha256(d, buf, len);
+    ko_fr_from_bendian_unchecked(&r, d);
+    free(buf);
+    fr_t *rp = (fr_t *)malloc(2 * n * sizeof(fr_t)), *rz = rp + n;
+    p1_t *cmy = (p1_t *)malloc(n * sizeof(p1_t));
+    rp[0] = FR_ONE;
+    for (size_t i = 1; i < n; i++) fr_mul(&rp[i], &rp[i - 1], &r);
+    p1_t g1, proof_lincomb, proof_z_lincomb, cmy_lincomb, rhs;
+    g1_generator(&g1);
+    ko_msm_naive(&proof_lincomb, ps, rp, n);
+    for (size_t i = 0; i < n; i++) {
+        p1_t yg; ko_p1_mult(&yg, &g1, &ys[i]);
+        p1_sub(&cmy[i], &cs[i], &yg);
+        fr_mul(&rz[i], &rp[i], &zs[i]);
+    }
+    ko_msm_naive(&proof_z_lincomb, ps, rz, n);
+    ko_msm_naive(&cmy_lincomb, cmy, rp, n);
+    p1_add_or_double(&rhs, &cmy_lincomb, &proof_z_lincomb);
+    int ok = pairings_verify(&proof_lincomb, &s->g2_monomial[1], &rhs, &G2_GEN);
+    free(rp); free(cmy);
+    return ok;
+}
+/* verify_blob_kzg_proof_batch_raw (eip_4844.rs:728-866), the non-"parallel" branch */
+API int ko_verify_blob_kzg_proof_batch(int *ok, const uint8_t *blobs, const uint8_t *commitments, const uint8_t *proofs,
+                                       size_t n, void *h) {
+    kzg_settings_t *s = (kzg_settings_t *)h;
+    if (n == 0) { *ok = 1; return 0; }
+    if (n == 1) return ko_verify_blob_kzg_proof(ok, blobs, commitments, proofs, h);
+    fr_t *polys = (fr_t *)malloc(n * FIELD_ELEMENTS_PER_BLOB * sizeof(fr_t));
+    p1_t *cs = (p1_t *)malloc(2 * n * sizeof(p1_t)), *ps = cs + n;
+    fr_t *zs = (fr_t *)malloc(2 * n * sizeof(fr_t)), *ys = zs + n;
+    int rc = 1;
+    for (size_t i = 0; i < n; i++) if (bytes_to_blob(polys + i * FIELD_ELEMENTS_PER_BLOB, blobs + i * BYTES_PER_BLOB)) goto done;
+    for (size_t i = 0; i < n; i++) { p1_affine_t a; if (ko_p1_uncompress(&a, commitments + 48 * i)) goto done; p1_from_affine(&cs[i], &a); }
+    for (size_t i = 0; i < n; i++) { p1_affine_t a; if (ko_p1_uncompress(&a, proofs + 48 * i)) goto done; p1_from_affine(&ps[i], &a); }
+    for (size_t i = 0; i < n; i++) if (!p1_is_inf(&cs[i]) && !ko_p1_in_g1(&cs[i])) goto done;
+    for (size_t i = 0; i < n; i++) if (!p1_is_inf(&ps[i]) && !ko_p1_in_g1(&ps[i])) goto done;
+    for (size_t i = 0; i < n; i++) {
+        const fr_t *poly = polys + i * FIELD_ELEMENTS_PER_BLOB;
+        compute_challenge(&zs[i], poly, &cs[i]);
+        if (evaluate_polynomial_in_evaluation_form(&ys[i], poly, &zs[i], s)) goto done;
+    }
+    *ok = verify_kzg_proof_batch(cs, zs, ys, ps, n, s);
+    rc = 0;
+done:
+    free(polys); free(cs); free(zs);
+    return rc;
+}
+API const p2_affine_t *ko_settings_g2_monomial(void *h) { return ((kzg_settings_t *)h)->g2_monomial; }

@@ -80,6 +80,17 @@ for n, y in cases("compute_cells_and_kzg_proofs"):
     fk.append(e)
 vec["compute_cells_and_kzg_proofs"] = fk
 
+# verification vectors (kzg-bench/src/tests/eip_4844.rs:676-1010): outputs are booleans or null (error)
+vec["verify_kzg_proof"] = [
+    dict(name=n, commitment=y["input"]["commitment"], z=y["input"]["z"], y=y["input"]["y"], proof=y["input"]["proof"],
+         output=y["output"]) for n, y in cases("verify_kzg_proof")]
+vec["verify_blob_kzg_proof"] = [
+    dict(name=n, commitment=y["input"]["commitment"], proof=y["input"]["proof"], output=y["output"],
+         **blob_ref(y["input"]["blob"])) for n, y in cases("verify_blob_kzg_proof")]
+vec["verify_blob_kzg_proof_batch"] = [
+    dict(name=n, blobs=[blob_ref(b) for b in y["input"]["blobs"]], commitments=y["input"]["commitments"],
+         proofs=y["input"]["proofs"], output=y["output"]) for n, y in cases("verify_blob_kzg_proof_batch")]
+
 with open(os.path.join(OUT, "blobs.bin"), "wb") as f:
     for b in blobs:
         f.write(b)

@@ -196,3 +196,64 @@ def test_fft_properties(K):
         fs.fft_fr(data[:12])
     with pytest.raises(K.OracleError):
         fs.das_fft_extension(rand_fr_mont(rng, 1024))
+
+
+# ---- verification vectors: pin the oracle's pairing (kzg-bench/src/tests/eip_4844.rs:676-1010) ------------------
+def _blob_any(ref, golden_blobs):
+    if "blob" in ref:
+        return golden_blobs[ref["blob"]]
+    return bytes(ref.get("blob_len", 0))
+
+
+def _run(K, fn):
+    try:
+        return fn()
+    except (K.OracleError, ValueError):
+        return None
+
+
+def test_g2_generator_is_setup_point_zero(K, oracle_settings):
+    g2 = K.g2_monomial(oracle_settings)
+    assert np.array_equal(g2[0], K.p2_generator())
+    assert all(K.lib.ko_p2_affine_on_curve(g2[i].ctypes.data) for i in range(65))
+
+
+def test_verify_kzg_proof_vectors(K, oracle_settings, vectors):
+    cases = vectors["verify_kzg_proof"]
+    assert len(cases) == 122
+    seen = {True: 0, False: 0, None: 0}
+    for c in cases:
+        got = _run(K, lambda: K.verify_kzg_proof(H(c["commitment"]), H(c["z"]), H(c["y"]), H(c["proof"]), oracle_settings))
+        assert got == c["output"], c["name"]
+        seen[got] += 1
+    assert all(seen.values())
+
+
+def test_verify_blob_kzg_proof_vectors(K, oracle_settings, vectors, golden_blobs):
+    cases = vectors["verify_blob_kzg_proof"]
+    assert len(cases) == 29
+    for c in cases:
+        got = _run(K, lambda: K.verify_blob_kzg_proof(_blob_any(c, golden_blobs), H(c["commitment"]), H(c["proof"]),
+                                                      oracle_settings))
+        assert got == c["output"], c["name"]
+
+
+def test_verify_blob_kzg_proof_batch_vectors(K, oracle_settings, vectors, golden_blobs):
+    cases = vectors["verify_blob_kzg_proof_batch"]
+    assert len(cases) == 24
+    for c in cases:
+        got = _run(K, lambda: K.verify_blob_kzg_proof_batch([_blob_any(b, golden_blobs) for b in c["blobs"]],
+                                                            [H(x) for x in c["commitments"]],
+                                                            [H(x) for x in c["proofs"]], oracle_settings))
+        assert got == c["output"], c["name"]
+
+
+def test_pairing_bilinearity(K, oracle_settings):
+    """e([a]G1, [s]G2) == e([a s^1]... ) is not checkable without s; use e([a]P, Q) == e(P, Q)^a via e([a]P, Q) e(-[a]P, Q) and
+    the KZG identity on the setup itself: e(g1_monomial[1], g2[0]) == e(g1_monomial[0], g2[1])  (eip_4844.rs:1005-1020)"""
+    g1m, g2 = oracle_settings.g1_monomial, K.g2_monomial(oracle_settings)
+    assert K.pairings_verify(g1m[1], g2[0], g1m[0], g2[1])
+    assert K.pairings_verify(g1m[5], g2[3], g1m[2], g2[6])
+    assert not K.pairings_verify(g1m[5], g2[3], g1m[2], g2[5])
+    a = K.fr_from_ints([0x1234567890ABCDEF1234])[0]
+    assert K.pairings_verify(K.p1_mult(g1m[1], a), g2[0], K.p1_mult(g1m[0], a), g2[1])
