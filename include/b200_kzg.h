@@ -102,8 +102,8 @@ B200_API int b200_fft_launches(void *fs);
 
 /* ============================================================================================================== */
 /* B2 -- c-kzg-4844 C ABI (pinned upstream 00ae727c, .github/workflows/backend-tests.yml:4), commitment / proof     */
-/* path only.  Replaces blst/src/eip_4844.rs:160-530 for the functions below; types from                            */
-/* kzg/src/eth/c_bindings.rs:16-113.  Verification / EIP-7594 entry points are not exported (out of the hot path). */
+/* and verification path.  Replaces blst/src/eip_4844.rs:160-530 for the functions below; types from                */
+/* kzg/src/eth/c_bindings.rs:16-113.                                                                                */
 /* ============================================================================================================== */
 typedef enum { C_KZG_OK = 0, C_KZG_BADARGS = 1, C_KZG_ERROR = 2, C_KZG_MALLOC = 3 } C_KZG_RET;  /* c_bindings.rs:16-23 */
 typedef struct { uint8_t bytes[32]; } Bytes32;
@@ -119,7 +119,7 @@ typedef struct {
     blst_fr *reverse_roots_of_unity;  /* 8193 */
     blst_p1 *g1_values_monomial;      /* 4096 */
     blst_p1 *g1_values_lagrange_brp;  /* 4096 */
-    blst_p2 *g2_values_monomial;      /* 65, allocated but NOT decoded by this backend (verification is out of scope) */
+    blst_p2 *g2_values_monomial;      /* 65 */
     blst_p1 **x_ext_fft_columns;      /* NULL (FK20 data, out of scope) */
     blst_p1_affine **tables;          /* NULL */
     size_t wbits;
@@ -128,8 +128,9 @@ typedef struct {
 typedef KZGSettings CKZGSettings;
 
 /* blst/src/eip_4844.rs:180-222.  Decompresses the points on the GPU, builds the fixed-base MSM table and the
- * roots-of-unity tables, fills the host arrays.  BADARGS on wrong counts / undecodable points.  The reference's
- * pairing sanity check for monomial-form ("old") setups (kzg/src/eip_4844.rs:1005-1020) is NOT performed. */
+ * roots-of-unity tables, decodes the 65 G2 points and tabulates the Miller-loop lines of [1]G2, [s]G2, [s^64]G2, fills
+ * the host arrays.  BADARGS on wrong counts / undecodable points.  The reference's pairing sanity check for
+ * monomial-form ("old") setups (kzg/src/eip_4844.rs:1005-1020) is NOT performed. */
 B200_API C_KZG_RET load_trusted_setup(KZGSettings *out, const uint8_t *g1_monomial_bytes, uint64_t num_g1_monomial_bytes,
                              const uint8_t *g1_lagrange_bytes, uint64_t num_g1_lagrange_bytes,
                              const uint8_t *g2_monomial_bytes, uint64_t num_g2_monomial_bytes, uint64_t precompute);
@@ -143,6 +144,24 @@ B200_API C_KZG_RET blob_to_kzg_commitment(KZGCommitment *out, const Blob *blob, 
 B200_API C_KZG_RET compute_kzg_proof(KZGProof *proof_out, Bytes32 *y_out, const Blob *blob, const Bytes32 *z_bytes, const KZGSettings *s);
 /* blst/src/eip_4844.rs:274-291 */
 B200_API C_KZG_RET compute_blob_kzg_proof(KZGProof *out, const Blob *blob, const Bytes48 *commitment_bytes, const KZGSettings *s);
+
+/* blst/src/eip_4844.rs:383-405: *ok = e(C - [y]G1, G2) == e(proof, [s]G2 - [z]G2) (check_proof_single,
+ * blst/src/types/kzg_settings.rs:178-196).  BADARGS for non-canonical z / y, malformed, off-curve or out-of-subgroup
+ * points.  The pairing runs on the device against line tables of the fixed G2 points built at load time. */
+B200_API C_KZG_RET verify_kzg_proof(bool *ok, const Bytes48 *commitment_bytes, const Bytes32 *z_bytes, const Bytes32 *y_bytes,
+                                    const Bytes48 *proof_bytes, const KZGSettings *s);
+/* blst/src/eip_4844.rs:410-430 */
+B200_API C_KZG_RET verify_blob_kzg_proof(bool *ok, const Blob *blob, const Bytes48 *commitment_bytes, const Bytes48 *proof_bytes,
+                                         const KZGSettings *s);
+/* blst/src/eip_4844.rs:435-471 (*ok preset to false; n == 0 is true): challenges hashed on the host, evaluations and
+ * one random-linear-combination pairing check (kzg/src/eip_4844.rs:328-435) on the device */
+B200_API C_KZG_RET verify_blob_kzg_proof_batch(bool *ok, const Blob *blobs, const Bytes48 *commitments_bytes, const Bytes48 *proofs_bytes,
+                                               size_t n, const KZGSettings *s);
+/* extension: verify_kzg_proof_batch (kzg/src/eip_4844.rs:380-435) over caller-supplied (C, z, y, proof) tuples */
+B200_API C_KZG_RET b200_verify_kzg_proof_batch(bool *ok, const Bytes48 *commitments, const Bytes32 *zs, const Bytes32 *ys,
+                                               const Bytes48 *proofs, size_t n, const KZGSettings *s);
+/* test hook: e(a1, Q[qa]) == e(b1, Q[qb]) with Q = {[1]G2, [s]G2, [s^64]G2} (pairings_verify, blst/src/kzg_proofs.rs:74-100) */
+B200_API C_KZG_RET b200_selftest_pairings_verify(bool *ok, const blst_p1 *a1, int qa, const blst_p1 *b1, int qb, const KZGSettings *s);
 
 /* EIP-7594 compute_cells_and_kzg_proofs (kzg/src/das.rs:244-292; C ABI kzg/src/eth/c_bindings.rs:134-199):
  * cells = BRP(NTT_8192(INTT_4096(BRP(blob)))); proofs by FK20 (64 x NTT_128, 128 fixed-base lincombs of 64 points over

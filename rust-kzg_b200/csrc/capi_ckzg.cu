@@ -77,8 +77,24 @@ struct KzgCtx {
     int* h_status() { return stage[0].h_status(); }
     uint8_t* d_cells = nullptr;   // max_batch x 128 x 2048, allocated on first use (compute_cells)
     uint8_t* d_proofs = nullptr;  // fk20 batch x 128 x 48, allocated on first use
+    // verification staging, grown on demand: device [c48 n][p48 n][z32 n][y32 n][r32][status n ints][result int],
+    // pinned host mirror of the same layout
+    uint8_t* d_verify = nullptr;
+    uint8_t* h_verify = nullptr;
+    size_t verify_cap = 0;
+    static size_t verify_bytes(size_t n) { return n * (48 + 48 + 32 + 32 + sizeof(int)) + 32 + 64; }
+    void ensure_verify(size_t n) {
+        if (n <= verify_cap) return;
+        cudaFree(d_verify);
+        if (h_verify) cudaFreeHost(h_verify);
+        d_verify = nullptr; h_verify = nullptr; verify_cap = 0;
+        d_verify = dev_alloc<uint8_t>(verify_bytes(n));
+        B200_CUDA_CHECK(cudaMallocHost((void**)&h_verify, verify_bytes(n)));
+        verify_cap = n;
+    }
     ~KzgCtx() {
-        cudaFree(d_cells); cudaFree(d_proofs);
+        cudaFree(d_cells); cudaFree(d_proofs); cudaFree(d_verify);
+        if (h_verify) cudaFreeHost(h_verify);
         dev.reset();
     }
 };
@@ -138,6 +154,7 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
         ctx->d_blobs = ctx->stage[0].d_blobs;
         ctx->d_status = ctx->stage[0].d_status;
         ctx->dev.reset(new KzgSettingsDev(g1_monomial, g1_lagrange, mb, ctx->stream));
+        ctx->dev->load_g2(g2_monomial, (int)kG2, ctx->stream);  // G2::from_bytes of all 65 points (eip_4844.rs:1050-1053)
     } catch (const CudaError& e) {
         if (e.code != 1) fprintf(stderr, "b200kzg: load_trusted_setup failed: %s\n", e.what());
         return e.code == 1 ? C_KZG_BADARGS : C_KZG_ERROR;
@@ -153,16 +170,13 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
     out->reverse_roots_of_unity = (blst_fr*)malloc((w + 1) * sizeof(blst_fr));
     out->g1_values_monomial = (blst_p1*)malloc(kG1 * sizeof(blst_p1));
     out->g1_values_lagrange_brp = (blst_p1*)malloc(kG1 * sizeof(blst_p1));
-    // G2 monomial points are only used by verification (pairings), which is outside this backend's path
-    // (SURVEY.md section 8f-2): the array is allocated (so the struct has the reference's shape) but left zero.
     out->g2_values_monomial = (blst_p2*)calloc(kG2, sizeof(blst_p2));
     if (!out->roots_of_unity || !out->brp_roots_of_unity || !out->reverse_roots_of_unity || !out->g1_values_monomial ||
         !out->g1_values_lagrange_brp || !out->g2_values_monomial) {
         free_trusted_setup(out);
         return C_KZG_MALLOC;
     }
-    (void)g2_monomial;
-    bool ok = cudaMemcpy(out->roots_of_unity, fs.roots_dev(), (w + 1) * 32, cudaMemcpyDeviceToHost) == cudaSuccess &&
+    bool ok = cudaMemcpy(out->g2_values_monomial, ctx->dev->g2_monomial_jac_dev(), kG2 * sizeof(blst_p2), cudaMemcpyDeviceToHost) == cudaSuccess && cudaMemcpy(out->roots_of_unity, fs.roots_dev(), (w + 1) * 32, cudaMemcpyDeviceToHost) == cudaSuccess &&
               cudaMemcpy(out->brp_roots_of_unity, fs.brp_roots_dev(), w * 32, cudaMemcpyDeviceToHost) == cudaSuccess &&
               cudaMemcpy(out->g1_values_monomial, ctx->dev->g1_monomial_jac_dev(), kG1 * 144, cudaMemcpyDeviceToHost) == cudaSuccess &&
               cudaMemcpy(out->g1_values_lagrange_brp, ctx->dev->g1_lagrange_brp_jac_dev(), kG1 * 144, cudaMemcpyDeviceToHost) == cudaSuccess;
@@ -472,6 +486,122 @@ C_KZG_RET compute_cells_and_kzg_proofs(Cell* cells, KZGProof* proofs, const Blob
     }
     if (proofs) return b200_compute_cell_proofs_batch(proofs, blob, 1, s);
     return C_KZG_OK;
+}
+
+// ---- verification (blst/src/eip_4844.rs:383-471) -----------------------------------------------------------------
+// the batch challenge of compute_r_powers (kzg/src/eip_4844.rs:328-378); z / y are the canonical encodings
+static void batch_challenge_hash(uint8_t out[32], const uint8_t* c48, const uint8_t* z32, const uint8_t* y32, const uint8_t* p48, size_t n) {
+    sha256::Ctx c;
+    uint8_t head[32] = {'R', 'C', 'K', 'Z', 'G', 'B', 'A', 'T', 'C', 'H', '_', '_', '_', 'V', '1', '_'};
+    for (int i = 0; i < 8; i++) {
+        head[16 + i] = (uint8_t)((uint64_t)kFieldElementsPerBlob >> (8 * (7 - i)));
+        head[24 + i] = (uint8_t)((uint64_t)n >> (8 * (7 - i)));
+    }
+    c.update(head, 32);
+    for (size_t i = 0; i < n; i++) {
+        c.update(c48 + 48 * i, 48);
+        c.update(z32 + 32 * i, 32);
+        c.update(y32 + 32 * i, 32);
+        c.update(p48 + 48 * i, 48);
+    }
+    c.finish(out);
+}
+// verify_kzg_proof_batch (kzg/src/eip_4844.rs:380-435) on host arrays of wire bytes; ctx->mu held by the caller
+static C_KZG_RET verify_core(KzgCtx& ctx, bool* ok, const uint8_t* c48, const uint8_t* z32, const uint8_t* y32, const uint8_t* p48, size_t n) {
+    ctx.ensure_verify(n);
+    uint8_t* h = ctx.h_verify;
+    uint8_t* d = ctx.d_verify;
+    const size_t o_p = 48 * n, o_z = 96 * n, o_y = 128 * n, o_r = 160 * n, o_st = o_r + 32, o_res = o_st + n * sizeof(int);
+    memcpy(h, c48, 48 * n);
+    memcpy(h + o_p, p48, 48 * n);
+    memcpy(h + o_z, z32, 32 * n);
+    memcpy(h + o_y, y32, 32 * n);
+    if (n > 1) batch_challenge_hash(h + o_r, c48, z32, y32, p48, n); else memset(h + o_r, 0, 32);
+    memset(h + o_st, 0, n * sizeof(int) + sizeof(int));
+    cudaStream_t st = ctx.stream;
+    B200_CUDA_CHECK(cudaMemcpyAsync(d, h, o_res + sizeof(int), cudaMemcpyHostToDevice, st));
+    ctx.dev->verify_batch(d, d + o_p, d + o_z, d + o_y, 0, d + o_r, (int)n, reinterpret_cast<int*>(d + o_st),
+                          reinterpret_cast<int*>(d + o_res), st);
+    B200_CUDA_CHECK(cudaMemcpyAsync(h + o_st, d + o_st, n * sizeof(int) + sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (any_set(reinterpret_cast<int*>(h + o_st), (int)n)) return C_KZG_BADARGS;
+    *ok = *reinterpret_cast<int*>(h + o_res) != 0;
+    return C_KZG_OK;
+}
+/* b200 extension: verify_kzg_proof_batch over caller-supplied (commitment, z, y, proof) tuples */
+C_KZG_RET b200_verify_kzg_proof_batch(bool* ok, const Bytes48* commitments, const Bytes32* zs, const Bytes32* ys, const Bytes48* proofs,
+                                      size_t n, const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !ok) return C_KZG_BADARGS;
+        *ok = false;
+        if (n == 0) { *ok = true; return C_KZG_OK; }
+        if (!commitments || !zs || !ys || !proofs) return C_KZG_BADARGS;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        return verify_core(*ctx, ok, (const uint8_t*)commitments, (const uint8_t*)zs, (const uint8_t*)ys, (const uint8_t*)proofs, n);
+    });
+}
+C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Bytes32* z_bytes, const Bytes32* y_bytes,
+                           const Bytes48* proof_bytes, const KZGSettings* s) {
+    return b200_verify_kzg_proof_batch(ok, commitment_bytes, z_bytes, y_bytes, proof_bytes, 1, s);
+}
+C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48* commitments_bytes, const Bytes48* proofs_bytes, size_t n,
+                                      const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !ok) return C_KZG_BADARGS;
+        *ok = false;
+        if (n == 0) { *ok = true; return C_KZG_OK; }  // kzg/src/eip_4844.rs:760-763
+        if (!blobs || !commitments_bytes || !proofs_bytes) return C_KZG_BADARGS;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        // phase 1, chunked over the two lanes: z_i = challenge(blob_i, C_i) hashed on the host while the blobs cross
+        // PCIe, y_i = p_i(z_i) on the device (compute_challenges_and_evaluate_polynomial, :700-718)
+        std::vector<uint8_t> zs(32 * n), ys(32 * n);
+        C_KZG_RET rc = run_chunks(*ctx, n, ctx->max_batch,
+            [&](int lane, size_t off, int m) {
+                Stage& g = ctx->stage[lane];
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
+                B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
+                challenge_hash_many(g.h_z(), (const uint8_t*)(blobs + off), (const uint8_t*)(commitments_bytes + off), m);
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_z, g.h_z(), (size_t)m * 32, cudaMemcpyHostToDevice, g.stream));
+                ctx->dev->evaluate_blobs(g.d_blobs, g.d_z, 1, m, g.d_out48, g.d_y32, g.d_status, g.stream, lane);
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_out48(), g.d_out48, (size_t)m * 32, cudaMemcpyDeviceToHost, g.stream));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_y32(), g.d_y32, (size_t)m * 32, cudaMemcpyDeviceToHost, g.stream));
+                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_status(), g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+            },
+            [&](int lane, size_t off, int m) -> C_KZG_RET {
+                Stage& g = ctx->stage[lane];
+                if (any_set(g.h_status(), m)) return C_KZG_BADARGS;
+                memcpy(zs.data() + 32 * off, g.h_out48(), (size_t)m * 32);
+                memcpy(ys.data() + 32 * off, g.h_y32(), (size_t)m * 32);
+                return C_KZG_OK;
+            });
+        if (rc != C_KZG_OK) return rc;
+        // phase 2: one batched pairing check over all n (verify_kzg_proof_batch, :380-435)
+        return verify_core(*ctx, ok, (const uint8_t*)commitments_bytes, zs.data(), ys.data(), (const uint8_t*)proofs_bytes, n);
+    });
+}
+C_KZG_RET verify_blob_kzg_proof(bool* ok, const Blob* blob, const Bytes48* commitment_bytes, const Bytes48* proof_bytes, const KZGSettings* s) {
+    return verify_blob_kzg_proof_batch(ok, blob, commitment_bytes, proof_bytes, 1, s);
+}
+/* test hook for the pairing alone: e(a1, Q[qa]) == e(b1, Q[qb]), Q = {[1]G2, [s]G2, [s^64]G2}; host Jacobian points */
+C_KZG_RET b200_selftest_pairings_verify(bool* ok, const blst_p1* a1, int qa, const blst_p1* b1, int qb, const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !ok || !a1 || !b1) return C_KZG_BADARGS;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->ensure_verify(4);
+        uint8_t* d = ctx->d_verify;
+        B200_CUDA_CHECK(cudaMemcpyAsync(d, a1, 144, cudaMemcpyHostToDevice, ctx->stream));
+        B200_CUDA_CHECK(cudaMemcpyAsync(d + 144, b1, 144, cudaMemcpyHostToDevice, ctx->stream));
+        int* d_res = reinterpret_cast<int*>(d + 288);
+        ctx->dev->pairings_verify(d, qa, d + 144, qb, d_res, ctx->stream);
+        int res = 0;
+        B200_CUDA_CHECK(cudaMemcpyAsync(&res, d_res, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        *ok = res != 0;
+        return C_KZG_OK;
+    });
 }
 
 int b200_kzg_launches(const KZGSettings* s) {

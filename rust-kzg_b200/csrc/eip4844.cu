@@ -439,6 +439,7 @@ KzgSettingsDev::~KzgSettingsDev() {
     for (Lane& ln : lanes_) { cudaFree(ln.scalars); cudaFree(ln.poly); cudaFree(ln.z); cudaFree(ln.y); cudaFree(ln.out_jac); }
     cudaFree(cells_a_); cudaFree(cells_b_);
     cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_);
+    cudaFree(g2_affine_); cudaFree(g2_jac_); cudaFree(g2_lines_); cudaFree(vf_buf_);
 }
 
 void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st, int lane) {
@@ -550,6 +551,49 @@ void KzgSettingsDev::compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* p
     fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, false, n, st);
     launch_points_to_compressed(fk_pts_, proofs48, n * kFkK2, st, 7);  // reverse_bit_order(proofs) (:287)
     launches_ = 8 + fk_msm_->launches_per_run() + 2 * 9;
+}
+
+// G1::from_bytes + "!is_inf && !is_valid -> Err" of the verify_* functions (kzg/src/eip_4844.rs:601-606, 655-660,
+// 720-736): affine out, status[i] = 1 when point i is malformed, off the curve or outside the subgroup
+__global__ void __launch_bounds__(32) k_decode_g1_checked(const uint8_t* __restrict__ in, int n, uint8_t* __restrict__ out, int* __restrict__ status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cc::affine_t a;
+    if (!uncompress_point(in + (size_t)i * 48, a) || !in_g1(a)) status[i] = 1;
+    cc::store_affine(out + (size_t)i * 96, a);
+}
+void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st) {
+    if (n < 1) return;
+    k_decode_g1_checked<<<div_up(n, 32), 32, 0, st>>>(in48_dev, n, (uint8_t*)affine_out_dev, status_dev);
+    B200_LAUNCH_CHECK();
+}
+void launch_fr_from_bytes(const uint8_t* bytes32_dev, int n, int reduce, void* fr_mont_dev, int* status_dev, cudaStream_t st) {
+    if (n < 1) return;
+    k_z_to_fr<<<div_up(n, 64), 64, 0, st>>>(bytes32_dev, n, reduce, (uint8_t*)fr_mont_dev, status_dev);
+    B200_LAUNCH_CHECK();
+}
+void launch_fr_to_bytes(const void* fr_mont_dev, int n, uint8_t* bytes32_dev, cudaStream_t st) {
+    if (n < 1) return;
+    k_fr_to_bytes<<<div_up(n, 64), 64, 0, st>>>((const uint8_t*)fr_mont_dev, n, bytes32_dev);
+    B200_LAUNCH_CHECK();
+}
+
+// y_i = p_i(z_i) (evaluate_polynomial_in_evaluation_form, kzg/src/eip_4844.rs:954-1003) for the blob verifiers
+// (:662-666, 700-718): the same fused kernel as the proof path; the quotient it also produces is discarded.
+void KzgSettingsDev::evaluate_blobs(const uint8_t* blobs, const uint8_t* z_bytes, int z_reduce, int n, uint8_t* z32, uint8_t* y32,
+                                    int* status, cudaStream_t st, int lane) {
+    if (n < 1 || n > max_batch_) throw CudaError(-1, "blob batch exceeds the settings' capacity");
+    Lane& ln = lanes_[lane % kLanes];
+    size_t total = (size_t)n * kFieldElementsPerBlob;
+    k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, nullptr, (uint8_t*)ln.poly, status);
+    k_z_to_fr<<<div_up(n, 64), 64, 0, st>>>(z_bytes, n, z_reduce, (uint8_t*)ln.z, status);
+    k_quotient<<<n, kQThreads, kFieldElementsPerBlob * 32 + 8 * 32 + 64, st>>>((const uint8_t*)ln.poly, (const uint8_t*)ln.z,
+                                                                              (const uint8_t*)domain_, (uint8_t*)ln.scalars,
+                                                                              (uint8_t*)ln.y);
+    k_fr_to_bytes<<<div_up(n, 64), 64, 0, st>>>((const uint8_t*)ln.z, n, z32);
+    k_fr_to_bytes<<<div_up(n, 64), 64, 0, st>>>((const uint8_t*)ln.y, n, y32);
+    B200_LAUNCH_CHECK();
+    launches_ = 5;
 }
 
 void KzgSettingsDev::validate_commitments(const uint8_t* commitments48, int n, int* status, cudaStream_t st) {

@@ -53,6 +53,25 @@ public:
     // n <= fk20_batch().  The 128 x 64 table of x_ext_fft_columns is built on first use.
     void compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* proofs48, int* status, cudaStream_t st);
     int fk20_batch(cudaStream_t st) { ensure_fk20(st); return fk_batch_; }
+
+    // ---- verification (verify.cu; kzg/src/eip_4844.rs:328-435, 586-866) -----------------------------------------
+    // g2_monomial: 65 x 96-byte compressed points (host).  Decodes them (on-curve check, blst/src/types/g2.rs:50-72)
+    // and precomputes the Miller-loop line tables of [1]G2, [s]G2 and [s^64]G2.  Throws CudaError(1) when malformed.
+    void load_g2(const uint8_t* g2_monomial, int count, cudaStream_t st);
+    bool has_g2() const { return g2_lines_ != nullptr; }
+    const void* g2_monomial_jac_dev() const { return g2_jac_; }  // 65 x blst_p2 (288 B)
+    // y_i = p_i(z_i) for n <= max_batch blobs; z_bytes as in compute_proofs; z32 / y32: canonical big-endian out
+    void evaluate_blobs(const uint8_t* blobs, const uint8_t* z_bytes, int z_reduce, int n, uint8_t* z32, uint8_t* y32,
+                        int* status, cudaStream_t st, int lane = 0);
+    // verify_kzg_proof_batch (kzg/src/eip_4844.rs:380-435) for any n >= 1: all inputs are device arrays of big-endian
+    // wire bytes; r32 = the Fiat-Shamir hash (reduced mod r on the device; ignored for n == 1, where the check is
+    // check_proof_single, blst/src/types/kzg_settings.rs:178-196).  status[0] = 1 when an input is invalid
+    // (non-canonical field element, malformed / off-curve / out-of-subgroup point); *result = 1 iff the pairing
+    // equation holds.
+    void verify_batch(const uint8_t* commitments48, const uint8_t* proofs48, const uint8_t* z32, const uint8_t* y32,
+                      int z_reduce, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st);
+    // e(a1, Q[qa]) == e(b1, Q[qb]) for Jacobian G1 points on the device, Q[i] in {0: [1]G2, 1: [s]G2, 2: [s^64]G2}
+    void pairings_verify(const void* a1_jac, int qa, const void* b1_jac, int qb, int* result, cudaStream_t st);
     int launches_last() const { return launches_; }
 
 private:
@@ -76,9 +95,20 @@ private:
     void* domain_ = nullptr;    // brp_roots_of_unity[0..4096) of the 8192 table (Montgomery)
     void* cells_a_ = nullptr;   // max_batch * 8192 Fr ping-pong buffers (compute_cells), allocated on first use
     void* cells_b_ = nullptr;
+    void* g2_affine_ = nullptr;  // 65 x (x.re, x.im, y.re, y.im)
+    void* g2_jac_ = nullptr;     // 65 x blst_p2
+    void* g2_lines_ = nullptr;   // 3 x 68 x 288 B line tables
+    void* vf_buf_ = nullptr;     // verification workspace, grown on demand
+    size_t vf_cap_ = 0;          // terms the workspace holds
+    void ensure_verify_ws(size_t n);
 };
 
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input
 void launch_uncompress_g1(const uint8_t* in48_dev, void* affine_out_dev, int* flags_dev, int n, cudaStream_t st);
+// uncompress + subgroup check (G1::from_bytes followed by is_inf() || is_valid()); status[i] = 1 on failure
+void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st);
+// Fr::from_bytes (reduce = 0: status[i] = 1 when >= r) / hash_to_bls_field (reduce = 1) -> Montgomery; and back
+void launch_fr_from_bytes(const uint8_t* bytes32_dev, int n, int reduce, void* fr_mont_dev, int* status_dev, cudaStream_t st);
+void launch_fr_to_bytes(const void* fr_mont_dev, int n, uint8_t* bytes32_dev, cudaStream_t st);
 
 }  // namespace b200

@@ -1,0 +1,403 @@
+// pairing.cuh -- BLS12-381 extension tower and optimal-ate pairing check on the device.
+//
+// Replaces, for the verify_* functions, the reference's pairings_verify (blst/src/kzg_proofs.rs:74-100: two
+// Miller loops aggregated by blst, final_exp, blst_fp12_is_one).  Only the boolean "prod e(P_i, Q_i) == 1" is
+// observable, so the layout of the computation is free; it is chosen for the machine:
+//
+//  * every Q_i the KZG verifiers ever pair with is a FIXED point of the trusted setup ([1]G2, [s]G2, [s^64]G2), so the
+//    G2 side of the Miller loop (63 doublings + 5 additions in E'(Fp2), eprint 2010/354 Alg. 26/27) is done once at
+//    load time and kept as 68 line-coefficient triples per point (19.1 KiB); a check only evaluates the lines at P_i.
+//  * a single pairing is a serial chain of ~500 Fp12 multiplications, each 54+ Fp multiplications: one thread would
+//    need ~15 ms.  Fp12 is therefore held in shared memory in the flat basis Fp2[w]/(w^6 - xi), xi = 1 + u,
+//    (w^2 = v, so tower coefficient c_i.c_j is w^(i + 2j)) and ONE WARP computes a product cooperatively: lane
+//    (k, e, h) accumulates half (h) of the six Fp2 products that land on component e (re / im) of output coefficient k,
+//    wrapped terms (i + j >= 6) separately so that xi is applied once; two shuffle exchanges finish the coefficient.
+//    Critical path: 6 Fp multiplications instead of 54 (4 for the sparse line multiplication).
+//  * inversion, Frobenius and the final exponentiation (the addition chain of zkcrypto/bls12_381/src/pairings.rs:
+//    138-171, with plain squarings) are built from the same warp primitives.
+//
+// All w12_* functions must be called by all 32 lanes of a warp with warp-uniform arguments.
+#pragma once
+#include "g1.cuh"
+#include "mont.cuh"
+#include "pairing_consts.cuh"
+
+namespace b200 {
+
+typedef Mont<FpParams, MONT_CALL> pf_t;  // unrolled multiplier behind a call: full speed, small code
+
+template <class A, class B>
+__device__ __forceinline__ A fp_cast(const B& b) {
+    A a;
+#pragma unroll
+    for (int i = 0; i < 12; i++) a.v[i] = b.v[i];
+    return a;
+}
+__device__ __forceinline__ pf_t pf_const(const uint32_t* w) {
+    pf_t r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.v[i] = w[i];
+    return r;
+}
+__device__ __forceinline__ pf_t pf_shfl_xor(const pf_t& a, int m) {
+    pf_t r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.v[i] = __shfl_xor_sync(0xffffffffu, a.v[i], m);
+    return r;
+}
+
+// ---- Fp2 = Fp[u]/(u^2 + 1), one thread (zkcrypto/bls12_381/src/fp2.rs:86-245 for the formulas' provenance) ----------
+struct fp2_t {
+    pf_t re, im;
+    static __device__ __forceinline__ fp2_t zero() { return fp2_t{pf_t::zero(), pf_t::zero()}; }
+    static __device__ __forceinline__ fp2_t one() { return fp2_t{pf_t::one(), pf_t::zero()}; }
+    __device__ __forceinline__ bool is_zero() const { return re.is_zero() && im.is_zero(); }
+    __device__ __forceinline__ bool operator==(const fp2_t& o) const { return re == o.re && im == o.im; }
+    __device__ __forceinline__ fp2_t neg() const { return fp2_t{re.neg(), im.neg()}; }
+    __device__ __forceinline__ fp2_t dbl() const { return fp2_t{re.dbl(), im.dbl()}; }
+    __device__ __forceinline__ fp2_t conj() const { return fp2_t{re, im.neg()}; }
+    __device__ __forceinline__ fp2_t mul_xi() const { return fp2_t{re - im, re + im}; }  // (1 + u)
+    __device__ __forceinline__ fp2_t scale(const pf_t& s) const { return fp2_t{re * s, im * s}; }
+};
+__device__ __forceinline__ fp2_t operator+(const fp2_t& a, const fp2_t& b) { return fp2_t{a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ fp2_t operator-(const fp2_t& a, const fp2_t& b) { return fp2_t{a.re - b.re, a.im - b.im}; }
+static __device__ __noinline__ fp2_t fp2_mul(const fp2_t& a, const fp2_t& b) {  // Karatsuba, 3 Fp products
+    pf_t t0 = a.re * b.re, t1 = a.im * b.im, t2 = (a.re + a.im) * (b.re + b.im);
+    return fp2_t{t0 - t1, t2 - t0 - t1};
+}
+static __device__ __noinline__ fp2_t fp2_sqr(const fp2_t& a) {
+    pf_t m = a.re * a.im;
+    return fp2_t{(a.re + a.im) * (a.re - a.im), m.dbl()};
+}
+__device__ __forceinline__ fp2_t operator*(const fp2_t& a, const fp2_t& b) { return fp2_mul(a, b); }
+static __device__ __noinline__ fp2_t fp2_inverse(const fp2_t& a) {  // conj(a) / (re^2 + im^2); 0 -> 0
+    pf_t t = (a.re * a.re + a.im * a.im).inverse();
+    return fp2_t{a.re * t, (a.im * t).neg()};
+}
+// a^e, e = 12 little-endian words
+static __device__ __noinline__ fp2_t fp2_pow(const fp2_t& a, const uint32_t* e) {
+    fp2_t acc = fp2_t::one();
+    bool started = false;
+    for (int i = 383; i >= 0; i--) {
+        if (started) acc = fp2_sqr(acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) {
+            acc = started ? fp2_mul(acc, a) : a;
+            started = true;
+        }
+    }
+    return acc;
+}
+// words of (p - sub) >> sh
+__device__ __forceinline__ void p_minus_shift(uint32_t* e, uint32_t sub, int sh) {
+    uint32_t borrow = sub;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint32_t t = FpParams::mod(i);
+        e[i] = t - borrow;
+        borrow = t < borrow ? 1u : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) e[i] = (e[i] >> sh) | (i < 11 ? e[i + 1] << (32 - sh) : 0u);
+}
+// square root in Fp2 for p = 3 mod 4 (eprint 2012/685 Alg. 9, as zkcrypto/bls12_381/src/fp2.rs:246-296 uses it)
+static __device__ __noinline__ bool fp2_sqrt(const fp2_t& a, fp2_t& out) {
+    if (a.is_zero()) { out = a; return true; }
+    uint32_t e[12];
+    p_minus_shift(e, 3, 2);  // (p - 3) / 4
+    fp2_t a1 = fp2_pow(a, e);
+    fp2_t alpha = fp2_mul(fp2_sqr(a1), a);
+    fp2_t x0 = fp2_mul(a1, a);
+    fp2_t r;
+    if (alpha == fp2_t::one().neg()) {
+        r = fp2_t{x0.im.neg(), x0.re};  // u * x0
+    } else {
+        p_minus_shift(e, 1, 1);  // (p - 1) / 2
+        fp2_t b = fp2_pow(alpha + fp2_t::one(), e);
+        r = fp2_mul(b, x0);
+    }
+    out = r;
+    return fp2_sqr(r) == a;
+}
+__device__ __forceinline__ bool pf_lex_largest(const pf_t& y) { return cc::fp_is_lex_largest(fp_cast<fpc_t>(y)); }
+__device__ __forceinline__ bool fp2_lex_largest(const fp2_t& a) {  // fp2.rs:172-181
+    return pf_lex_largest(a.im) || (a.im.is_zero() && pf_lex_largest(a.re));
+}
+__device__ __forceinline__ fp2_t load_fp2(const void* p) {
+    return fp2_t{load_field<pf_t>(p), load_field<pf_t>((const uint8_t*)p + 48)};
+}
+__device__ __forceinline__ void store_fp2(void* p, const fp2_t& a) {
+    store_field((uint8_t*)p, a.re);
+    store_field((uint8_t*)p + 48, a.im);
+}
+
+// 48 big-endian bytes -> canonical limbs; false if >= p.  mask: clear the three flag bits of the first byte
+__device__ __forceinline__ bool pf_from_be48(const uint8_t* in, bool mask, pf_t& out) {
+    pf_t x;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const uint8_t* p = in + 4 * (11 - k);
+        x.v[k] = (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+    }
+    if (mask) x.v[11] &= 0x1fffffffu;
+    bool lt = false;
+#pragma unroll
+    for (int i = 11; i >= 0; i--) {
+        uint32_t m = FpParams::mod(i);
+        if (x.v[i] != m) { lt = x.v[i] < m; break; }
+    }
+    out = x.to_mont();
+    return lt;
+}
+// G2 compressed decoding (blst_p2_uncompress via FsG2::from_bytes, blst/src/types/g2.rs:50-72; encoding
+// zkcrypto/bls12_381/src/notes/serialization.rs, g2.rs:402-465): c1 of x first, on-curve check, no subgroup check.
+// Infinity decodes to x = y = 0.
+static __device__ __noinline__ bool g2_uncompress(const uint8_t* in, fp2_t& x, fp2_t& y) {
+    uint32_t b0 = in[0];
+    uint32_t cflag = b0 >> 7, iflag = (b0 >> 6) & 1, sflag = (b0 >> 5) & 1;
+    x = fp2_t::zero();
+    y = fp2_t::zero();
+    if (!cflag) return false;
+    fp2_t xx;
+    if (!pf_from_be48(in, true, xx.im) || !pf_from_be48(in + 48, false, xx.re)) return false;
+    if (iflag) return !sflag && xx.is_zero();
+    pf_t four = pf_t::one().dbl().dbl();
+    fp2_t y2 = fp2_mul(fp2_sqr(xx), xx) + fp2_t{four, four};  // b' = 4(1 + u)
+    fp2_t yy;
+    if (!fp2_sqrt(y2, yy)) return false;
+    if (fp2_lex_largest(yy) != (bool)sflag) yy = yy.neg();
+    x = xx;
+    y = yy;
+    return true;
+}
+
+// ---- G2 side of the Miller loop: line coefficients of a fixed Q ------------------------------------------------------
+static constexpr int kMillerLines = 68;             // 63 doublings + 5 additions for |x| = 0xd201000000010000
+static constexpr int kLineBytes = 3 * 96;           // three Fp2 per line
+static constexpr uint64_t kBlsXHalf = 0xd201000000010000ull >> 1;
+struct g2proj_t { fp2_t x, y, z; };
+// Alg. 26 of eprint 2010/354 (the form zkcrypto/bls12_381/src/pairings.rs:708-737 evaluates): doubles r, returns the
+// tangent line as (l0, l1, l2) with  line(P) = l2 + (l1 * P.x) w^2 + (l0 * P.y) w^3
+static __device__ __noinline__ void g2_line_dbl(g2proj_t& r, fp2_t* l) {
+    fp2_t a = fp2_sqr(r.x), b = fp2_sqr(r.y), c = fp2_sqr(b);
+    fp2_t d = (fp2_sqr(b + r.x) - a - c).dbl();
+    fp2_t e = a.dbl() + a;
+    fp2_t g = r.x + e;
+    fp2_t f = fp2_sqr(e);
+    fp2_t zz = fp2_sqr(r.z);
+    fp2_t x3 = f - d - d;
+    fp2_t z3 = fp2_sqr(r.z + r.y) - b - zz;
+    fp2_t y3 = fp2_mul(d - x3, e) - c.dbl().dbl().dbl();
+    l[1] = fp2_mul(e, zz).dbl().neg();
+    l[2] = fp2_sqr(g) - a - f - b.dbl().dbl();
+    l[0] = fp2_mul(z3, zz).dbl();
+    r.x = x3; r.y = y3; r.z = z3;
+}
+// Alg. 27: r += q (q affine), returns the chord line in the same form (pairings.rs:739-770)
+static __device__ __noinline__ void g2_line_add(g2proj_t& r, const fp2_t& qx, const fp2_t& qy, fp2_t* l) {
+    fp2_t zz = fp2_sqr(r.z), yy = fp2_sqr(qy);
+    fp2_t t0 = fp2_mul(zz, qx);
+    fp2_t t1 = fp2_mul(fp2_sqr(qy + r.z) - yy - zz, zz);
+    fp2_t t2 = t0 - r.x;
+    fp2_t t3 = fp2_sqr(t2);
+    fp2_t t4 = t3.dbl().dbl();
+    fp2_t t5 = fp2_mul(t4, t2);
+    fp2_t t6 = t1 - r.y - r.y;
+    fp2_t t9 = fp2_mul(t6, qx);
+    fp2_t t7 = fp2_mul(t4, r.x);
+    fp2_t x3 = fp2_sqr(t6) - t5 - t7 - t7;
+    fp2_t z3 = fp2_sqr(r.z + t2) - zz - t3;
+    fp2_t t10 = qy + z3;
+    fp2_t t8 = fp2_mul(t7 - x3, t6);
+    fp2_t y3 = t8 - fp2_mul(r.y, t5).dbl();
+    t10 = fp2_sqr(t10) - yy - fp2_sqr(z3);
+    l[2] = t9.dbl() - t10;
+    l[0] = z3.dbl();
+    l[1] = t6.neg().dbl();
+    r.x = x3; r.y = y3; r.z = z3;
+}
+// all 68 lines of the Miller loop of Q = (qx, qy), in evaluation order (pairings.rs:667-693)
+static __device__ __noinline__ void g2_prepare_lines(const fp2_t& qx, const fp2_t& qy, uint8_t* out) {
+    g2proj_t r{qx, qy, fp2_t::one()};
+    fp2_t l[3];
+    int idx = 0;
+    for (int b = 61; b >= 0; b--) {
+        g2_line_dbl(r, l);
+        for (int k = 0; k < 3; k++) store_fp2(out + (size_t)idx * kLineBytes + k * 96, l[k]);
+        idx++;
+        if ((kBlsXHalf >> b) & 1) {
+            g2_line_add(r, qx, qy, l);
+            for (int k = 0; k < 3; k++) store_fp2(out + (size_t)idx * kLineBytes + k * 96, l[k]);
+            idx++;
+        }
+    }
+    g2_line_dbl(r, l);
+    for (int k = 0; k < 3; k++) store_fp2(out + (size_t)idx * kLineBytes + k * 96, l[k]);
+}
+
+// ---- Fp12 on one warp ------------------------------------------------------------------------------------------------
+// An element is 12 pf_t in shared (or global) memory: c[2k + e] = component e (0 = re, 1 = im) of the coefficient of w^k.
+static constexpr int kW12Bytes = 12 * 48;
+
+// dst = a * b.  dst may alias a and/or b.
+static __device__ __noinline__ void w12_mul(pf_t* dst, const pf_t* a, const pf_t* b) {
+    const int lane = threadIdx.x & 31;
+    const int L = lane < 24 ? lane : lane - 24;
+    const int k = L >> 2, e = (L >> 1) & 1, h = L & 1;
+    pf_t S = pf_t::zero(), T = pf_t::zero();
+#pragma unroll 1
+    for (int t = 0; t < 3; t++) {
+        const int i = 3 * h + t;
+        int j = k - i;
+        const bool wrap = j < 0;
+        if (wrap) j += 6;
+        // e = 0: a.re b.re - a.im b.im        e = 1: a.re b.im + a.im b.re
+        pf_t p0 = a[2 * i] * b[2 * j + e];
+        pf_t p1 = a[2 * i + 1] * b[2 * j + (e ^ 1)];
+        pf_t term = e ? p0 + p1 : p0 - p1;
+        pf_t s2 = S + term, t2 = T + term;
+        if (wrap) T = t2; else S = s2;
+    }
+    S = S + pf_shfl_xor(S, 1);
+    T = T + pf_shfl_xor(T, 1);
+    pf_t To = pf_shfl_xor(T, 2);
+    pf_t c = e ? S + T + To : S + T - To;  // xi T = (T.re - T.im) + (T.re + T.im) u
+    __syncwarp();
+    if (lane < 24 && h == 0) dst[2 * k + e] = c;
+    __syncwarp();
+}
+// dst = a * (b0 + b2 w^2 + b3 w^3), sp = {b0.re, b0.im, b2.re, b2.im, b3.re, b3.im}: the Miller-loop line
+static __device__ __noinline__ void w12_mul_sparse(pf_t* dst, const pf_t* a, const pf_t* sp) {
+    const int lane = threadIdx.x & 31;
+    const int L = lane < 24 ? lane : lane - 24;
+    const int k = L >> 2, e = (L >> 1) & 1, h = L & 1;
+    pf_t S = pf_t::zero(), T = pf_t::zero();
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        // h = 0 takes b0 and b3, h = 1 takes b2 (its second round is a dummy)
+        const int slot = h ? 1 : (t ? 2 : 0);
+        const int j = h ? 2 : (t ? 3 : 0);
+        const bool live = !(h && t);
+        int i = k - j;
+        const bool wrap = i < 0;
+        if (wrap) i += 6;
+        pf_t p0 = a[2 * i] * sp[2 * slot + e];
+        pf_t p1 = a[2 * i + 1] * sp[2 * slot + (e ^ 1)];
+        pf_t term = e ? p0 + p1 : p0 - p1;
+        pf_t s2 = S + term, t2 = T + term;
+        if (live) { if (wrap) T = t2; else S = s2; }
+    }
+    S = S + pf_shfl_xor(S, 1);
+    T = T + pf_shfl_xor(T, 1);
+    pf_t To = pf_shfl_xor(T, 2);
+    pf_t c = e ? S + T + To : S + T - To;
+    __syncwarp();
+    if (lane < 24 && h == 0) dst[2 * k + e] = c;
+    __syncwarp();
+}
+__device__ __forceinline__ void w12_copy(pf_t* dst, const pf_t* a) {
+    const int lane = threadIdx.x & 31;
+    pf_t v = a[lane < 12 ? lane : 0];
+    __syncwarp();
+    if (lane < 12) dst[lane] = v;
+    __syncwarp();
+}
+__device__ __forceinline__ void w12_set_one(pf_t* dst) {
+    const int lane = threadIdx.x & 31;
+    if (lane < 12) dst[lane] = lane == 0 ? pf_t::one() : pf_t::zero();
+    __syncwarp();
+}
+__device__ __forceinline__ bool w12_is_one(const pf_t* a) {
+    const int lane = threadIdx.x & 31;
+    bool ok = true;
+    if (lane < 12) ok = a[lane] == (lane == 0 ? pf_t::one() : pf_t::zero());
+    return __all_sync(0xffffffffu, ok);
+}
+// conjugation over Fp6 = the p^6 Frobenius: odd powers of w change sign
+__device__ __forceinline__ void w12_conj(pf_t* dst, const pf_t* a) {
+    const int lane = threadIdx.x & 31;
+    pf_t v = a[lane < 12 ? lane : 0];
+    if ((lane >> 1) & 1) v = v.neg();
+    __syncwarp();
+    if (lane < 12) dst[lane] = v;
+    __syncwarp();
+}
+// dst = a^p: coefficient k becomes conj(a_k) * FROB_GAMMA[k]
+static __device__ __noinline__ void w12_frobenius(pf_t* dst, const pf_t* a) {
+    const int lane = threadIdx.x & 31;
+    const int L = lane < 12 ? lane : 0;
+    const int k = L >> 1, e = L & 1;
+    pf_t gre = pf_const(FROB_GAMMA[k][0]), gim = pf_const(FROB_GAMMA[k][1]);
+    // (are - aim u)(gre + gim u) = are gre + aim gim + (are gim - aim gre) u
+    pf_t p0 = a[2 * k] * (e ? gim : gre);
+    pf_t p1 = a[2 * k + 1] * (e ? gre : gim);
+    pf_t c = e ? p0 - p1 : p0 + p1;
+    __syncwarp();
+    if (lane < 12) dst[L] = c;
+    __syncwarp();
+}
+// dst = 1 / f.  tmp: 4 scratch elements.  With g = f conj(f) in Fp6 and N = g g^(p^2) g^(p^4) in Fp2:
+// 1/f = conj(f) g^(p^2) g^(p^4) / N, one Fp inversion.
+static __device__ __noinline__ void w12_inverse(pf_t* dst, const pf_t* f, pf_t* tmp) {
+    pf_t *t1 = tmp, *t2 = tmp + 12, *t3 = tmp + 24, *t4 = tmp + 36;
+    w12_conj(t1, f);
+    w12_mul(t2, f, t1);                       // g
+    w12_frobenius(t3, t2); w12_frobenius(t3, t3);   // g^(p^2)
+    w12_frobenius(t4, t3); w12_frobenius(t4, t4);   // g^(p^4)
+    w12_mul(t3, t3, t4);                      // h
+    w12_mul(t2, t2, t3);                      // N: only the w^0 coefficient is non-zero
+    fp2_t n{t2[0], t2[1]};
+    fp2_t ni = fp2_inverse(n);
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    if (lane < 12) t2[lane] = lane == 0 ? ni.re : lane == 1 ? ni.im : pf_t::zero();
+    __syncwarp();
+    w12_mul(t3, t3, t2);
+    w12_mul(dst, t1, t3);
+}
+// dst = conj(f^|x|) = f^x for the (negative) BLS parameter; f in the cyclotomic subgroup.  tmp: 1 scratch element
+static __device__ __noinline__ void w12_exp_x(pf_t* dst, const pf_t* f, pf_t* tmp) {
+    const uint64_t X = 0xd201000000010000ull;
+    w12_copy(tmp, f);
+#pragma unroll 1
+    for (int b = 62; b >= 0; b--) {
+        w12_mul(tmp, tmp, tmp);
+        if ((X >> b) & 1) w12_mul(tmp, tmp, f);
+    }
+    w12_conj(dst, tmp);
+}
+// f <- f^((p^12 - 1)/r) (up to the fixed cofactor of the chain in zkcrypto/bls12_381/src/pairings.rs:138-171).
+// ws: 12 scratch elements.
+static __device__ __noinline__ void w12_final_exp(pf_t* f, pf_t* ws) {
+    pf_t *t0 = ws, *t1 = ws + 12, *t2 = ws + 24, *t3 = ws + 36, *t4 = ws + 48, *t5 = ws + 60, *t6 = ws + 72, *sc = ws + 84;
+    // easy part: f^((p^6 - 1)(p^2 + 1))
+    w12_conj(t0, f);
+    w12_inverse(t1, f, sc);
+    w12_mul(t2, t0, t1);
+    w12_copy(t1, t2);
+    w12_frobenius(t2, t2); w12_frobenius(t2, t2);
+    w12_mul(t2, t2, t1);
+    // hard part
+    w12_mul(t1, t2, t2); w12_conj(t1, t1);
+    w12_exp_x(t3, t2, sc);
+    w12_mul(t4, t3, t3);
+    w12_mul(t5, t1, t3);
+    w12_exp_x(t1, t5, sc);
+    w12_exp_x(t0, t1, sc);
+    w12_exp_x(t6, t0, sc);
+    w12_mul(t6, t6, t4);
+    w12_exp_x(t4, t6, sc);
+    w12_conj(t5, t5);
+    w12_mul(t5, t5, t2); w12_mul(t4, t4, t5);
+    w12_conj(t5, t2);
+    w12_mul(t1, t1, t2);
+    w12_frobenius(t1, t1); w12_frobenius(t1, t1); w12_frobenius(t1, t1);
+    w12_mul(t6, t6, t5);
+    w12_frobenius(t6, t6);
+    w12_mul(t3, t3, t0);
+    w12_frobenius(t3, t3); w12_frobenius(t3, t3);
+    w12_mul(t3, t3, t1);
+    w12_mul(t3, t3, t6);
+    w12_mul(f, t3, t4);
+}
+
+}  // namespace b200

@@ -1,0 +1,255 @@
+// verify.cu -- the verification side of EIP-4844 on the device: verify_kzg_proof, verify_blob_kzg_proof and
+// verify_blob_kzg_proof_batch (kzg/src/eip_4844.rs:328-435, 586-866; pairing: blst/src/kzg_proofs.rs:74-100).
+//
+// One code path serves all three.  With r_i the Fiat-Shamir powers (r_0 = 1, so n = 1 is the single check of
+// blst/src/types/kzg_settings.rs:178-196):
+//      A = sum r_i proof_i
+//      B = sum r_i C_i  +  sum (r_i z_i) proof_i  -  (sum r_i y_i) G1           (the reference forms C_i - [y_i]G1 with n
+//                                                                                scalar multiplications; same point)
+//      accept  <=>  e(A, [s]G2) == e(B, G2)   <=>   e(-A, [s]G2) e(B, G2) == 1
+// Both G2 arguments are fixed points of the setup: their Miller-loop lines are tabulated at load time (pairing.cuh).
+// The two linear combinations are short (n and 2n + 1 terms) and latency-bound, so they run as one scalar
+// multiplication per lane quad (g1_quad.cuh) followed by quad trees, not through the bucket engine.
+#include "eip4844.cuh"
+#include "g1.cuh"
+#include "g1_quad.cuh"
+#include "pairing.cuh"
+#include "util.cuh"
+
+#include <vector>
+
+namespace b200 {
+
+// ---- G2 setup points --------------------------------------------------------------------------------------------
+// affine out: 4 Fp per point (x.re, x.im, y.re, y.im); jac out: blst_p2 {x, y, z} with z = 1 (0 for infinity)
+__global__ void __launch_bounds__(32) k_g2_decode(const uint8_t* __restrict__ in96, int n, uint8_t* __restrict__ affine,
+                                                  uint8_t* __restrict__ jac, int* __restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp2_t x, y;
+    if (!g2_uncompress(in96 + (size_t)i * 96, x, y)) flags[i] = 1;
+    store_fp2(affine + (size_t)i * 192, x);
+    store_fp2(affine + (size_t)i * 192 + 96, y);
+    bool inf = x.is_zero() && y.is_zero();
+    store_fp2(jac + (size_t)i * 288, x);
+    store_fp2(jac + (size_t)i * 288 + 96, y);
+    store_fp2(jac + (size_t)i * 288 + 192, inf ? fp2_t::zero() : fp2_t::one());
+}
+// line tables for the points idx[0..m) of the affine array; table t at lines + t * 68 * 288
+struct G2PrepArgs { int idx[4]; int m; };
+__global__ void __launch_bounds__(32) k_g2_prepare(const uint8_t* __restrict__ affine, G2PrepArgs args, uint8_t* __restrict__ lines) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= args.m) return;
+    const uint8_t* q = affine + (size_t)args.idx[t] * 192;
+    g2_prepare_lines(load_fp2(q), load_fp2(q + 96), lines + (size_t)t * kMillerLines * kLineBytes);
+}
+
+// ---- terms of the two linear combinations -------------------------------------------------------------------------
+// Segment 0 (A) and segment 1 (B), each padded to L = 2n + 1 terms: points affine (96 B), scalars canonical (32 B).
+// One thread: the powers of r are a serial chain (compute_powers, kzg/src/eip_4844.rs:316-326) and n is small.
+__global__ void k_verify_terms(const uint8_t* __restrict__ comm_aff, const uint8_t* __restrict__ proof_aff, const uint8_t* __restrict__ z_mont,
+                               const uint8_t* __restrict__ y_mont, const uint8_t* __restrict__ r_mont, int n, uint8_t* __restrict__ pts,
+                               uint8_t* __restrict__ scalars) {
+    if (blockIdx.x || threadIdx.x) return;
+    const size_t L = 2 * (size_t)n + 1;
+    fr_t r = n > 1 ? load_field<fr_t>(r_mont) : fr_t::one();
+    fr_t rp = fr_t::one(), ysum = fr_t::zero();
+    affine_t inf{fp_t::zero(), fp_t::zero()};
+    for (int i = 0; i < n; i++) {
+        affine_t c = load_affine(comm_aff + (size_t)i * 96), p = load_affine(proof_aff + (size_t)i * 96);
+        fr_t z = load_field<fr_t>(z_mont + (size_t)i * 32), y = load_field<fr_t>(y_mont + (size_t)i * 32);
+        fr_t rpc = rp.from_mont();
+        store_affine(pts + (size_t)i * 96, p);
+        store_field(scalars + (size_t)i * 32, rpc);
+        store_affine(pts + (L + i) * 96, c);
+        store_field(scalars + (L + i) * 32, rpc);
+        store_affine(pts + (L + n + i) * 96, p);
+        store_field(scalars + (L + n + i) * 32, (rp * z).from_mont());
+        ysum = ysum + rp * y;
+        rp = rp * r;
+    }
+    for (size_t i = n; i < L; i++) {
+        store_affine(pts + i * 96, inf);
+        store_field(scalars + i * 32, fr_t::zero());
+    }
+    affine_t g{fp_cast<fp_t>(pf_const(G1_GEN_AFFINE[0])), fp_cast<fp_t>(pf_const(G1_GEN_AFFINE[1]))};
+    store_affine(pts + (L + 2 * (size_t)n) * 96, g);
+    store_field(scalars + (L + 2 * (size_t)n) * 32, ysum.neg().from_mont());
+}
+// One lane quad per term: partial[seg][block] = sum of the block's eight [k_i] P_i, in XYZZ (192 B)
+__global__ void __launch_bounds__(32) k_lincomb_quads(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalars, int L,
+                                                      uint8_t* __restrict__ partial) {
+    __shared__ __align__(16) uint8_t table[kQuadTableBytes];
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 2);
+    const int role = threadIdx.x & 3;
+    const bool live = q < L;
+    const size_t t = (size_t)blockIdx.y * L + (live ? q : 0);
+    fp_t x = load_field<fp_t>(pts + t * 96), y = load_field<fp_t>(pts + t * 96 + 48);
+    const bool inf = !live || (x.is_zero() && y.is_zero());
+    fp_t comp = role == 0 ? x : role == 1 ? y : fp_t::one();
+    if (inf) comp = fp_t::zero();
+    fr_t k = load_field<fr_t>(scalars + t * 32);
+    comp = quad_mul_scalar(comp, k.v, table);
+    comp = quad_tree(comp, 32);
+    if (threadIdx.x < 4) store_field(partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 192 + quad_store_offset(), comp);
+}
+// out[seg] = sum of m partials (XYZZ), one warp per segment
+__global__ void __launch_bounds__(32) k_quad_sum(const uint8_t* __restrict__ partial, int m, uint8_t* __restrict__ out) {
+    const uint8_t* p = partial + (size_t)blockIdx.x * m * 192;
+    fp_t acc = fp_t::zero();
+    for (int base = 0; base < m; base += 8) {
+        int q = base + (threadIdx.x >> 2);
+        fp_t c = q < m ? load_field<fp_t>(p + (size_t)q * 192 + quad_store_offset()) : fp_t::zero();
+        acc = quad_add(acc, c);
+    }
+    acc = quad_tree(acc, 32);
+    if (threadIdx.x < 4) store_field(out + (size_t)blockIdx.x * 192 + quad_store_offset(), acc);
+}
+// Jacobian -> XYZZ for pairings_verify's operands
+__global__ void k_jac_to_xyzz2(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out) {
+    if (threadIdx.x >= 2) return;
+    cc::xyzz_t p = cc::jac_to_xyzz(cc::load_jac(threadIdx.x ? b : a));
+    cc::store_xyzz(out + threadIdx.x * 192, p);
+}
+
+// ---- the pairing check: one warp --------------------------------------------------------------------------------
+struct PairingArgs {
+    const uint8_t* g1_xyzz[4];   // P_i, XYZZ
+    const uint8_t* lines[4];     // line table of Q_i
+    int neg[4];                  // use -P_i
+    int n;
+};
+static constexpr int kPairScratchBytes = 4 * kMillerLines * kLineBytes;  // scaled lines of up to four pairs
+__global__ void __launch_bounds__(32) k_pairing_check(PairingArgs args, uint8_t* __restrict__ scratch, int* __restrict__ result) {
+    __shared__ __align__(16) pf_t f[12];
+    __shared__ __align__(16) pf_t ws[12 * 12];
+    const int lane = threadIdx.x;
+    bool skip[4];
+    // evaluate every line at P_i: (l2, l1 * x, l0 * y), 68 lines per pair spread over the lanes
+    for (int p = 0; p < args.n; p++) {
+        const uint8_t* g = args.g1_xyzz[p];
+        pf_t X = load_field<pf_t>(g), Y = load_field<pf_t>(g + 48), ZZZ = load_field<pf_t>(g + 96), ZZ = load_field<pf_t>(g + 144);
+        skip[p] = ZZ.is_zero();
+        pf_t inv = (ZZ * ZZZ).inverse();
+        pf_t px = X * (inv * ZZZ), py = Y * (inv * ZZ);
+        if (args.neg[p]) py = py.neg();
+        for (int idx = lane; idx < kMillerLines; idx += 32) {
+            const uint8_t* l = args.lines[p] + (size_t)idx * kLineBytes;
+            uint8_t* o = scratch + ((size_t)p * kMillerLines + idx) * kLineBytes;
+            store_fp2(o, load_fp2(l + 192));
+            store_fp2(o + 96, load_fp2(l + 96).scale(px));
+            store_fp2(o + 192, load_fp2(l).scale(py));
+        }
+    }
+    __syncwarp();
+    w12_set_one(f);
+    int idx = 0;
+#pragma unroll 1
+    for (int b = 61; b >= -1; b--) {
+        const int steps = (b >= 0 && ((kBlsXHalf >> b) & 1)) ? 2 : 1;
+#pragma unroll 1
+        for (int s = 0; s < steps; s++, idx++)
+            for (int p = 0; p < args.n; p++)
+                if (!skip[p]) w12_mul_sparse(f, f, reinterpret_cast<const pf_t*>(scratch + ((size_t)p * kMillerLines + idx) * kLineBytes));
+        if (b >= 0) w12_mul(f, f, f);
+    }
+    w12_conj(f, f);
+    w12_final_exp(f, ws);
+    bool one = w12_is_one(f);
+    if (lane == 0) *result = one ? 1 : 0;
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+void KzgSettingsDev::load_g2(const uint8_t* g2_monomial, int count, cudaStream_t st) {
+    if (count < 65) throw CudaError(1, "Invalid number of g2 points in trusted setup");
+    uint8_t* comp = dev_alloc<uint8_t>((size_t)count * 96);
+    int* flags = dev_alloc<int>(count);
+    g2_affine_ = dev_alloc<uint8_t>((size_t)count * 192);
+    g2_jac_ = dev_alloc<uint8_t>((size_t)count * 288);
+    g2_lines_ = dev_alloc<uint8_t>((size_t)3 * kMillerLines * kLineBytes);
+    B200_CUDA_CHECK(cudaMemcpyAsync(comp, g2_monomial, (size_t)count * 96, cudaMemcpyHostToDevice, st));
+    B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, count * sizeof(int), st));
+    k_g2_decode<<<div_up(count, 32), 32, 0, st>>>(comp, count, (uint8_t*)g2_affine_, (uint8_t*)g2_jac_, flags);
+    G2PrepArgs pa{{0, 1, 64, 0}, 3};
+    k_g2_prepare<<<1, 32, 0, st>>>((const uint8_t*)g2_affine_, pa, (uint8_t*)g2_lines_);
+    B200_LAUNCH_CHECK();
+    std::vector<int> h(count);
+    B200_CUDA_CHECK(cudaMemcpyAsync(h.data(), flags, count * sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(comp);
+    cudaFree(flags);
+    for (int f : h)
+        if (f) {
+            cudaFree(g2_lines_);
+            g2_lines_ = nullptr;
+            throw CudaError(1, "Failed to uncompress");  // FsG2::from_bytes (blst/src/types/g2.rs:66)
+        }
+}
+
+// workspace layout for n items (L = 2n + 1):
+//   [comm_aff n*96][proof_aff n*96][z n*32][y n*32][r 32][pts 2L*96][scalars 2L*32][partials 2*ceil(L/8)*192][sums 2*192]
+//   [pair scratch]
+void KzgSettingsDev::ensure_verify_ws(size_t n) {
+    if (n <= vf_cap_ && vf_buf_) return;
+    cudaFree(vf_buf_);
+    size_t L = 2 * n + 1, blocks = (L + 7) / 8;
+    size_t bytes = n * (96 + 96 + 32 + 32) + 64 + 2 * L * (96 + 32) + 2 * blocks * 192 + 2 * 192 + kPairScratchBytes + 256;
+    vf_buf_ = dev_alloc<uint8_t>(bytes);
+    vf_cap_ = n;
+}
+
+static void run_pairing(const uint8_t* p0, const uint8_t* l0, int neg0, const uint8_t* p1, const uint8_t* l1, int neg1, uint8_t* scratch,
+                        int* result, cudaStream_t st) {
+    PairingArgs a{};
+    a.n = 2;
+    a.g1_xyzz[0] = p0; a.lines[0] = l0; a.neg[0] = neg0;
+    a.g1_xyzz[1] = p1; a.lines[1] = l1; a.neg[1] = neg1;
+    k_pairing_check<<<1, 32, 0, st>>>(a, scratch, result);
+    B200_LAUNCH_CHECK();
+}
+
+void KzgSettingsDev::verify_batch(const uint8_t* commitments48, const uint8_t* proofs48, const uint8_t* z32, const uint8_t* y32,
+                                  int z_reduce, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st) {
+    if (!g2_lines_) throw CudaError(-1, "trusted setup was loaded without G2 points");
+    if (n < 1) throw CudaError(-1, "verify_batch needs at least one item");
+    ensure_verify_ws(n);
+    const size_t L = 2 * (size_t)n + 1, blocks = (L + 7) / 8;
+    uint8_t* w = (uint8_t*)vf_buf_;
+    uint8_t* comm_aff = w;                 w += (size_t)n * 96;
+    uint8_t* proof_aff = w;                w += (size_t)n * 96;
+    uint8_t* z = w;                        w += (size_t)n * 32;
+    uint8_t* y = w;                        w += (size_t)n * 32;
+    uint8_t* r = w;                        w += 64;
+    uint8_t* pts = w;                      w += 2 * L * 96;
+    uint8_t* scalars = w;                  w += 2 * L * 32;
+    uint8_t* partials = w;                 w += 2 * blocks * 192;
+    uint8_t* sums = w;                     w += 2 * 192;
+    uint8_t* scratch = (uint8_t*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    launch_decode_g1_checked(commitments48, comm_aff, status, n, st);
+    launch_decode_g1_checked(proofs48, proof_aff, status, n, st);
+    launch_fr_from_bytes(z32, n, z_reduce, z, status, st);
+    launch_fr_from_bytes(y32, n, 0, y, status, st);
+    if (n > 1) launch_fr_from_bytes(r32, 1, 1, r, status, st);  // hash_to_bls_field never fails: status untouched
+    k_verify_terms<<<1, 32, 0, st>>>(comm_aff, proof_aff, z, y, r, n, pts, scalars);
+    k_lincomb_quads<<<dim3((unsigned)blocks, 2), 32, 0, st>>>(pts, scalars, (int)L, partials);
+    k_quad_sum<<<2, 32, 0, st>>>(partials, (int)blocks, sums);
+    B200_LAUNCH_CHECK();
+    const uint8_t* lines = (const uint8_t*)g2_lines_;
+    run_pairing(sums, lines + (size_t)1 * kMillerLines * kLineBytes, 1, sums + 192, lines, 0, scratch, result, st);
+    launches_ = 9 + (n > 1);
+}
+
+void KzgSettingsDev::pairings_verify(const void* a1_jac, int qa, const void* b1_jac, int qb, int* result, cudaStream_t st) {
+    if (!g2_lines_) throw CudaError(-1, "trusted setup was loaded without G2 points");
+    if (qa < 0 || qa > 2 || qb < 0 || qb > 2) throw CudaError(-1, "bad G2 table index");
+    ensure_verify_ws(1);
+    uint8_t* w = (uint8_t*)vf_buf_;
+    uint8_t* sums = w;
+    uint8_t* scratch = (uint8_t*)(((uintptr_t)(w + 2 * 192) + 255) & ~(uintptr_t)255);
+    k_jac_to_xyzz2<<<1, 32, 0, st>>>((const uint8_t*)a1_jac, (const uint8_t*)b1_jac, sums);
+    const uint8_t* lines = (const uint8_t*)g2_lines_;
+    const size_t tb = (size_t)kMillerLines * kLineBytes;
+    run_pairing(sums, lines + qa * tb, 1, sums + 192, lines + qb * tb, 0, scratch, result, st);
+}
+
+}  // namespace b200

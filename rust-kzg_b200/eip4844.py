@@ -47,6 +47,11 @@ def _L():
             "compute_cells_and_kzg_proofs": (ci, [vp, vp, vp, S]),
             "b200_compute_cells_batch": (ci, [vp, vp, sz, S]),
             "b200_compute_cell_proofs_batch": (ci, [vp, vp, sz, S]),
+            "verify_kzg_proof": (ci, [vp, vp, vp, vp, vp, S]),
+            "verify_blob_kzg_proof": (ci, [vp, vp, vp, vp, S]),
+            "verify_blob_kzg_proof_batch": (ci, [vp, vp, vp, vp, sz, S]),
+            "b200_verify_kzg_proof_batch": (ci, [vp, vp, vp, vp, vp, sz, S]),
+            "b200_selftest_pairings_verify": (ci, [vp, vp, ci, vp, ci, S]),
             "b200_kzg_launches": (ci, [S]),
             "b200_kzg_max_batch": (ci, [S]),
             "b200_selftest_sha256": (None, [vp, vp, sz, ci]),
@@ -202,6 +207,68 @@ class KZGSettings:
         if rc != C_KZG_OK:
             raise KzgError(rc, "compute_cells_batch")
         return out
+
+    # ---- verification (blst/src/eip_4844.rs:383-471)
+    def verify_kzg_proof(self, commitment, z, y, proof) -> bool:
+        cb, zb, yb, pb = _buf(commitment, 48, "commitment"), _buf(z, 32, "z"), _buf(y, 32, "y"), _buf(proof, 48, "proof")
+        ok = C.c_bool(False)
+        rc = _L().verify_kzg_proof(C.byref(ok), _p(cb), _p(zb), _p(yb), _p(pb), C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "verify_kzg_proof")
+        return bool(ok.value)
+
+    def verify_blob_kzg_proof(self, blob, commitment, proof) -> bool:
+        b, cb, pb = _buf(blob, BYTES_PER_BLOB, "blob"), _buf(commitment, 48, "commitment"), _buf(proof, 48, "proof")
+        ok = C.c_bool(False)
+        rc = _L().verify_blob_kzg_proof(C.byref(ok), _p(b), _p(cb), _p(pb), C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "verify_blob_kzg_proof")
+        return bool(ok.value)
+
+    def verify_blob_kzg_proof_batch(self, blobs, commitments, proofs) -> bool:
+        """blobs: list of bytes / (n,131072) array; commitments, proofs: lists of 48-byte strings / (n,48) arrays"""
+        if not isinstance(blobs, np.ndarray):
+            if len(blobs) != len(commitments) or len(blobs) != len(proofs):
+                raise KzgError(C_KZG_BADARGS, "Invalid amount of arguments")   # kzg/src/eip_4844.rs:770-772
+            blobs = [_buf(b, BYTES_PER_BLOB, "blob") for b in blobs]
+            commitments = [_buf(c, 48, "commitment") for c in commitments]
+            proofs = [_buf(p_, 48, "proof") for p_ in proofs]
+            blobs = np.concatenate(blobs) if blobs else np.zeros(0, np.uint8)
+            commitments = np.concatenate(commitments) if commitments else np.zeros(0, np.uint8)
+            proofs = np.concatenate(proofs) if proofs else np.zeros(0, np.uint8)
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, BYTES_PER_BLOB)
+        commitments = np.ascontiguousarray(commitments, dtype=np.uint8).reshape(-1, 48)
+        proofs = np.ascontiguousarray(proofs, dtype=np.uint8).reshape(-1, 48)
+        n = blobs.shape[0]
+        if commitments.shape[0] != n or proofs.shape[0] != n:
+            raise KzgError(C_KZG_BADARGS, "Invalid amount of arguments")
+        ok = C.c_bool(False)
+        rc = _L().verify_blob_kzg_proof_batch(C.byref(ok), _p(blobs), _p(commitments), _p(proofs), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "verify_blob_kzg_proof_batch")
+        return bool(ok.value)
+
+    def verify_kzg_proof_batch(self, commitments, zs, ys, proofs) -> bool:
+        commitments = np.ascontiguousarray(commitments, dtype=np.uint8).reshape(-1, 48)
+        zs = np.ascontiguousarray(zs, dtype=np.uint8).reshape(-1, 32)
+        ys = np.ascontiguousarray(ys, dtype=np.uint8).reshape(-1, 32)
+        proofs = np.ascontiguousarray(proofs, dtype=np.uint8).reshape(-1, 48)
+        n = commitments.shape[0]
+        ok = C.c_bool(False)
+        rc = _L().b200_verify_kzg_proof_batch(C.byref(ok), _p(commitments), _p(zs), _p(ys), _p(proofs), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "verify_kzg_proof_batch")
+        return bool(ok.value)
+
+    def pairings_verify(self, a1, qa, b1, qb) -> bool:
+        """test hook: e(a1, Q[qa]) == e(b1, Q[qb]); a1, b1 = blst_p1 as 18 u64 limbs; Q = ([1]G2, [s]G2, [s^64]G2)"""
+        a = np.ascontiguousarray(a1, dtype=np.uint64).reshape(18)
+        b = np.ascontiguousarray(b1, dtype=np.uint64).reshape(18)
+        ok = C.c_bool(False)
+        rc = _L().b200_selftest_pairings_verify(C.byref(ok), _p(a), qa, _p(b), qb, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "pairings_verify")
+        return bool(ok.value)
 
     # ---- batched extensions: blobs (n,131072) u8, returns (n,48) u8 ...
     def blob_to_kzg_commitment_batch(self, blobs, out=None):
