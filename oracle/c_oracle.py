@@ -61,6 +61,9 @@ def _load():
         "ko_pairings_verify": (ci, [vp, vp, vp, vp]), "ko_settings_g2_monomial": (vp, [vp]),
         "ko_verify_kzg_proof": (ci, [vp, vp, vp, vp, vp, vp]), "ko_verify_blob_kzg_proof": (ci, [vp, vp, vp, vp, vp]),
         "ko_verify_blob_kzg_proof_batch": (ci, [vp, vp, vp, vp, sz, vp]),
+        "ko_recover_cells_and_kzg_proofs": (ci, [vp, vp, vp, vp, sz, vp]),
+        "ko_compute_verify_cell_kzg_proof_batch_challenge": (ci, [vp, vp, sz, vp, vp, vp, vp, sz]),
+        "ko_verify_cell_kzg_proof_batch": (ci, [vp, vp, vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(lib, name)
@@ -495,5 +498,58 @@ def verify_blob_kzg_proof_batch(blobs, commitments, proofs, s: KZGSettings) -> b
     ps = _bytes_arr(b"".join(proofs)) if n else np.zeros(1, np.uint8)
     ok = C.c_int(0)
     if lib.ko_verify_blob_kzg_proof_batch(C.byref(ok), _p(bl), _p(cs), _p(ps), n, s.h):
+        raise OracleError("bad input")
+    return bool(ok.value)
+
+
+# ---- EIP-7594 recovery / cell verification (kzg/src/das.rs:101-207, 294-452) ----
+def _cells_arr(cells):
+    if any(len(c) != 2048 for c in cells):
+        raise OracleError("Invalid byte length")
+    return _bytes_arr(b"".join(cells)) if cells else np.zeros(1, np.uint8)
+
+
+def _g1s_arr(items):
+    if any(len(c) != 48 for c in items):
+        raise OracleError("Invalid byte length")
+    return _bytes_arr(b"".join(items)) if items else np.zeros(1, np.uint8)
+
+
+def recover_cells_and_kzg_proofs(cell_indices, cells, s: KZGSettings, want_proofs=True):
+    """-> (128 cells, 128 proofs or None)"""
+    if len(cell_indices) != len(cells):
+        raise OracleError("Cell indicies mismatch")
+    n = len(cells)
+    idx = np.asarray(list(cell_indices) or [0], dtype=np.uint64)
+    out_c = np.zeros(128 * 2048, np.uint8)
+    out_p = np.zeros(128 * 48, np.uint8)
+    if lib.ko_recover_cells_and_kzg_proofs(_p(out_c), _p(out_p) if want_proofs else None, _p(idx), _p(_cells_arr(cells)), n, s.h):
+        raise OracleError("bad input")
+    cb, pb = out_c.tobytes(), out_p.tobytes()
+    return ([cb[i * 2048:(i + 1) * 2048] for i in range(128)],
+            [pb[i * 48:(i + 1) * 48] for i in range(128)] if want_proofs else None)
+
+
+def compute_verify_cell_kzg_proof_batch_challenge(commitments, commitment_indices, cell_indices, cells, proofs) -> bytes:
+    n = len(cells)
+    if len(commitment_indices) != n or len(cell_indices) != n or len(proofs) != n:
+        raise OracleError("Cell count mismatch")
+    out = np.zeros(32, np.uint8)
+    ci = np.asarray(list(commitment_indices) or [0], dtype=np.uint64)
+    ki = np.asarray(list(cell_indices) or [0], dtype=np.uint64)
+    if lib.ko_compute_verify_cell_kzg_proof_batch_challenge(_p(out), _p(_g1s_arr(commitments)), len(commitments), _p(ci), _p(ki),
+                                                            _p(_cells_arr(cells)), _p(_g1s_arr(proofs)), n):
+        raise OracleError("bad input")
+    return out.tobytes()
+
+
+def verify_cell_kzg_proof_batch(commitments, cell_indices, cells, proofs, s: KZGSettings) -> bool:
+    n = len(cells)
+    if len(commitments) != n or len(cell_indices) != n or len(proofs) != n:
+        raise OracleError("count mismatch")
+    ki = np.asarray(list(cell_indices) or [0], dtype=np.uint64)
+    ok = C.c_int(0)
+    if lib.ko_verify_cell_kzg_proof_batch(C.byref(ok), _p(_g1s_arr(commitments)), _p(ki), _p(_cells_arr(cells)),
+                                          _p(_g1s_arr(proofs)), n, s.h):
         raise OracleError("bad input")
     return bool(ok.value)

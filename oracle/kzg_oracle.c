@@ -1286,6 +1286,27 @@ static void toeplitz_coeffs_stride(fr_t *out, const fr_t *in, size_t n, size_t o
     out[0] = in[d_minus_i];
     for (size_t j = 1; j < r - 1; j++) out[2 * r - j] = in[d_minus_i - j * l];
 }
+/* compute_fk20_proofs (kzg/src/das.rs:660-696) + reverse_bit_order of the proofs (:287): mono = the first 4096
+ * monomial coefficients; proofs_out = 128 x 48 compressed bytes in cell order */
+static void fk20_proofs_from_mono(uint8_t *proofs_out, const fr_t *mono, kzg_settings_t *s) {
+    const size_t n = 4096;
+    fk20_setup(s);
+    fr_t *coeffs = (fr_t *)malloc(FK_K2 * CELL_SIZE * sizeof(fr_t));   /* [row j][offset i] */
+    fr_t tc[FK_K2], tf[FK_K2];
+    for (size_t i = 0; i < CELL_SIZE; i++) {
+        toeplitz_coeffs_stride(tc, mono, n, i, CELL_SIZE);
+        ko_fft_fr(s->fs, tf, tc, FK_K2, 0, 1);
+        for (size_t j = 0; j < FK_K2; j++) coeffs[j * CELL_SIZE + i] = tf[j];
+    }
+    p1_t hext[FK_K2], hh[FK_K2], pr[FK_K2];
+    for (size_t j = 0; j < FK_K2; j++)   /* g1_lincomb_batch: one 64-term lincomb per row */
+        ko_g1_lincomb(&hext[j], s->x_ext_fft_columns + j * CELL_SIZE, coeffs + j * CELL_SIZE, CELL_SIZE, 1);
+    ko_fft_g1(s->fs, hh, hext, FK_K2, 1);
+    for (size_t j = FK_K; j < FK_K2; j++) p1_set_inf(&hh[j]);
+    ko_fft_g1(s->fs, pr, hh, FK_K2, 0);
+    for (size_t j = 0; j < FK_K2; j++) ko_p1_compress(proofs_out + 48 * brp_index(j, 7), &pr[j]);
+    free(coeffs);
+}
 /* compute_cells_and_kzg_proofs (kzg/src/das.rs:244-292) through the byte-level wrapper; cells_out (128*2048 B) and
  * proofs_out (128*48 B) may each be NULL but not both.  returns 0 ok, 1 Err */
 API int ko_compute_cells_and_kzg_proofs(uint8_t *cells_out, uint8_t *proofs_out, const uint8_t *blob, void *h) {
@@ -1303,25 +1324,7 @@ API int ko_compute_cells_and_kzg_proofs(uint8_t *cells_out, uint8_t *proofs_out,
         for (size_t i = 0; i < 2 * n; i++) ko_fr_to_bendian(cells_out + 32 * brp_index(i, 13), &ext[i]);
         free(ext);
     }
-    if (proofs_out) {
-        fk20_setup(s);
-        /* compute_fk20_proofs (:660-696) */
-        fr_t *coeffs = (fr_t *)malloc(FK_K2 * CELL_SIZE * sizeof(fr_t));   /* [row j][offset i] */
-        fr_t tc[FK_K2], tf[FK_K2];
-        for (size_t i = 0; i < CELL_SIZE; i++) {
-            toeplitz_coeffs_stride(tc, mono, n, i, CELL_SIZE);
-            ko_fft_fr(s->fs, tf, tc, FK_K2, 0, 1);
-            for (size_t j = 0; j < FK_K2; j++) coeffs[j * CELL_SIZE + i] = tf[j];
-        }
-        p1_t hext[FK_K2], hh[FK_K2], pr[FK_K2];
-        for (size_t j = 0; j < FK_K2; j++)   /* g1_lincomb_batch: one 64-term lincomb per row */
-            ko_g1_lincomb(&hext[j], s->x_ext_fft_columns + j * CELL_SIZE, coeffs + j * CELL_SIZE, CELL_SIZE, 1);
-        ko_fft_g1(s->fs, hh, hext, FK_K2, 1);
-        for (size_t j = FK_K; j < FK_K2; j++) p1_set_inf(&hh[j]);
-        ko_fft_g1(s->fs, pr, hh, FK_K2, 0);
-        for (size_t j = 0; j < FK_K2; j++) ko_p1_compress(proofs_out + 48 * brp_index(j, 7), &pr[j]);
-        free(coeffs);
-    }
+    if (proofs_out) fk20_proofs_from_mono(proofs_out, mono, s);
     free(poly); free(brp); free(mono);
     return 0;
 }
@@ -1454,3 +1457,201 @@ done:
     return rc;
 }
 API const p2_affine_t *ko_settings_g2_monomial(void *h) { return ((kzg_settings_t *)h)->g2_monomial; }
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* EIP-7594 recovery and cell verification (kzg/src/das.rs:101-207, 294-452, 454-616, 697-900).
+ * Return 0 = Ok, 1 = Err (C ABI: BadArgs). */
+#define CELLS_PER_EXT_BLOB 128
+#define BYTES_PER_CELL 2048
+static int cells_to_fr(fr_t *out, const uint8_t *cells, size_t ncells) {
+    for (size_t i = 0; i < ncells * CELL_SIZE; i++)
+        if (ko_fr_from_bendian(&out[i], cells + 32 * i)) return 1;
+    return 0;
+}
+static void shift_poly(fr_t *poly, size_t n, const fr_t *factor) {  /* das.rs:454-460 */
+    fr_t fp = FR_ONE;
+    for (size_t i = 1; i < n; i++) { fr_mul(&fp, &fp, factor); fr_mul(&poly[i], &poly[i], &fp); }
+}
+/* recover_cells (das.rs:549-616); present[i] marks provided cells, data = 8192 evaluations in cell order */
+static int recover_cells(fr_t *data, const uint8_t *present, const kzg_settings_t *s) {
+    const size_t N = 8192;
+    fr_t *brp = (fr_t *)malloc(N * sizeof(fr_t)), *van = (fr_t *)calloc(N, sizeof(fr_t)), *van_eval = (fr_t *)malloc(N * sizeof(fr_t));
+    fr_t *ez = (fr_t *)malloc(N * sizeof(fr_t)), *t = (fr_t *)malloc(N * sizeof(fr_t)), *vc = (fr_t *)malloc(N * sizeof(fr_t));
+    uint8_t *present_brp = (uint8_t *)malloc(N);
+    for (size_t i = 0; i < N; i++) { size_t r = brp_index(i, 13); brp[r] = data[i]; present_brp[r] = present[i / CELL_SIZE]; }
+    size_t missing[CELLS_PER_EXT_BLOB], nm = 0;
+    for (size_t i = 0; i < CELLS_PER_EXT_BLOB; i++) if (!present[i]) missing[nm++] = brp_index(i, 7);
+    int rc = 1;
+    if (nm > CELLS_PER_EXT_BLOB / 2 || nm == 0) goto done;
+    {
+        /* vanishing_polynomial_for_missing_cells (:516-547) with compute_vanishing_polynomial_from_roots (:488-514) */
+        fr_t shortp[CELLS_PER_EXT_BLOB + 1], neg, zero;
+        memset(&zero, 0, sizeof(zero));
+        const size_t stride = N / CELLS_PER_EXT_BLOB;
+        fr_sub(&shortp[0], &zero, &s->fs->roots_of_unity[missing[0] * stride]);
+        for (size_t i = 1; i < nm; i++) {
+            fr_sub(&neg, &zero, &s->fs->roots_of_unity[missing[i] * stride]);
+            fr_add(&shortp[i], &neg, &shortp[i - 1]);
+            for (size_t j = i - 1; j >= 1; j--) { fr_mul(&shortp[j], &shortp[j], &neg); fr_add(&shortp[j], &shortp[j], &shortp[j - 1]); }
+            fr_mul(&shortp[0], &shortp[0], &neg);
+        }
+        shortp[nm] = FR_ONE;
+        for (size_t i = 0; i <= nm; i++) van[i * CELL_SIZE] = shortp[i];
+    }
+    ko_fft_fr(s->fs, van_eval, van, N, 0, 1);
+    for (size_t i = 0; i < N; i++) {
+        if (!present_brp[i]) memset(&ez[i], 0, sizeof(fr_t)); else fr_mul(&ez[i], &brp[i], &van_eval[i]);
+    }
+    ko_fft_fr(s->fs, t, ez, N, 1, 1);
+    {
+        fr_t seven, inv7;
+        fr_from_u64(&seven, 7);
+        fr_inv(&inv7, &seven);
+        shift_poly(t, N, &seven);                       /* coset_fft (:462-473) */
+        ko_fft_fr(s->fs, ez, t, N, 0, 1);
+        memcpy(vc, van, N * sizeof(fr_t));
+        shift_poly(vc, N, &seven);
+        ko_fft_fr(s->fs, t, vc, N, 0, 1);
+        for (size_t i = 0; i < N; i++) { fr_inv(&t[i], &t[i]); fr_mul(&ez[i], &ez[i], &t[i]); }
+        ko_fft_fr(s->fs, t, ez, N, 1, 1);               /* coset_ifft (:475-486) */
+        shift_poly(t, N, &inv7);
+    }
+    ko_fft_fr(s->fs, ez, t, N, 0, 1);
+    for (size_t i = 0; i < N; i++) data[brp_index(i, 13)] = ez[i];
+    rc = 0;
+done:
+    free(brp); free(van); free(van_eval); free(ez); free(t); free(vc); free(present_brp);
+    return rc;
+}
+/* recover_cells_and_kzg_proofs (das.rs:101-207) behind the byte-level wrapper (eth/c_bindings.rs:201-286) */
+API int ko_recover_cells_and_kzg_proofs(uint8_t *cells_out, uint8_t *proofs_out, const u64 *cell_indices, const uint8_t *cells,
+                                        size_t n, void *h) {
+    kzg_settings_t *s = (kzg_settings_t *)h;
+    const size_t N = 8192;
+    if (n > CELLS_PER_EXT_BLOB) return 1;                       /* "Cell length cannot be larger than CELLS_PER_EXT_BLOB" */
+    fr_t *in = (fr_t *)malloc((n ? n : 1) * CELL_SIZE * sizeof(fr_t)), *data = (fr_t *)calloc(N, sizeof(fr_t));
+    uint8_t present[CELLS_PER_EXT_BLOB] = {0};
+    int rc = 1;
+    if (cells_to_fr(in, cells, n)) goto done;
+    if (n < CELLS_PER_EXT_BLOB / 2) goto done;                  /* "Impossible to recover" */
+    for (size_t i = 0; i < n; i++) {
+        if (cell_indices[i] >= CELLS_PER_EXT_BLOB) goto done;
+        if (i + 1 < n && cell_indices[i + 1] <= cell_indices[i]) goto done;   /* strictly ascending */
+        present[cell_indices[i]] = 1;
+        memcpy(data + cell_indices[i] * CELL_SIZE, in + i * CELL_SIZE, CELL_SIZE * sizeof(fr_t));
+    }
+    if (n != CELLS_PER_EXT_BLOB && recover_cells(data, present, s)) goto done;
+    for (size_t i = 0; i < N; i++) ko_fr_to_bendian(cells_out + 32 * i, &data[i]);
+    if (proofs_out) {
+        fr_t *brp = (fr_t *)malloc(N * sizeof(fr_t)), *mono = (fr_t *)malloc(N * sizeof(fr_t));
+        for (size_t i = 0; i < N; i++) brp[brp_index(i, 13)] = data[i];
+        ko_fft_fr(s->fs, mono, brp, N, 1, 1);                   /* poly_lagrange_to_monomial on all 8192 (:186-188) */
+        fk20_proofs_from_mono(proofs_out, mono, s);
+        free(brp); free(mono);
+    }
+    rc = 0;
+done:
+    free(in); free(data);
+    return rc;
+}
+/* compute_verify_cell_kzg_proof_batch_challenge (das.rs:390-452); inputs already validated */
+static void cell_batch_challenge(fr_t *out, const uint8_t *commitments48, size_t ncomm, const u64 *commitment_indices,
+                                 const u64 *cell_indices, const uint8_t *cells, const uint8_t *proofs48, size_t n) {
+    size_t len = 16 + 32 + ncomm * 48 + n * (16 + BYTES_PER_CELL + 48);
+    uint8_t *buf = (uint8_t *)malloc(len), *p = buf;
+    memcpy(p, "RCKZGCBATCH__V1_", 16); p += 16;
+    u64 head[4] = {FIELD_ELEMENTS_PER_BLOB, CELL_SIZE, ncomm, n};
+    for (int k = 0; k < 4; k++) for (int i = 0; i < 8; i++) *p++ = (uint8_t)(head[k] >> (8 * (7 - i)));
+    memcpy(p, commitments48, ncomm * 48); p += ncomm * 48;
+    for (size_t c = 0; c < n; c++) {
+        for (int i = 0; i < 8; i++) *p++ = (uint8_t)(commitment_indices[c] >> (8 * (7 - i)));
+        for (int i = 0; i < 8; i++) *p++ = (uint8_t)(cell_indices[c] >> (8 * (7 - i)));
+        memcpy(p, cells + c * BYTES_PER_CELL, BYTES_PER_CELL); p += BYTES_PER_CELL;
+        memcpy(p, proofs48 + 48 * c, 48); p += 48;
+    }
+    uint8_t d[32];
+    ko_sha256(d, buf, len);
+    ko_fr_from_bendian_unchecked(out, d);
+    free(buf);
+}
+/* blst/src/eip_7594.rs:35-97: every commitment, cell element and proof must decode */
+API int ko_compute_verify_cell_kzg_proof_batch_challenge(uint8_t out32[32], const uint8_t *commitments48, size_t ncomm,
+                                                         const u64 *commitment_indices, const u64 *cell_indices,
+                                                         const uint8_t *cells, const uint8_t *proofs48, size_t n) {
+    p1_affine_t a; fr_t f, r;
+    for (size_t i = 0; i < ncomm; i++) if (ko_p1_uncompress(&a, commitments48 + 48 * i)) return 1;
+    for (size_t i = 0; i < n * CELL_SIZE; i++) if (ko_fr_from_bendian(&f, cells + 32 * i)) return 1;
+    for (size_t i = 0; i < n; i++) if (ko_p1_uncompress(&a, proofs48 + 48 * i)) return 1;
+    cell_batch_challenge(&r, commitments48, ncomm, commitment_indices, cell_indices, cells, proofs48, n);
+    ko_fr_to_bendian(out32, &r);
+    return 0;
+}
+/* verify_cell_kzg_proof_batch (das.rs:294-388) behind the byte-level wrapper (eth/c_bindings.rs:288-352) */
+API int ko_verify_cell_kzg_proof_batch(int *ok, const uint8_t *commitments48, const u64 *cell_indices, const uint8_t *cells,
+                                       const uint8_t *proofs48, size_t n, void *h) {
+    kzg_settings_t *s = (kzg_settings_t *)h;
+    g2_init();
+    size_t nn = n ? n : 1;
+    p1_t *cs = (p1_t *)malloc(nn * sizeof(p1_t)), *ps = (p1_t *)malloc(nn * sizeof(p1_t)), *uc = (p1_t *)malloc(nn * sizeof(p1_t));
+    fr_t *fr = (fr_t *)malloc(nn * CELL_SIZE * sizeof(fr_t)), *rp = (fr_t *)malloc(nn * sizeof(fr_t)), *w = (fr_t *)calloc(nn, sizeof(fr_t));
+    u64 *cidx = (u64 *)malloc(nn * sizeof(u64));
+    uint8_t *ucb = (uint8_t *)malloc(nn * 48);
+    fr_t *agg = (fr_t *)calloc(CELLS_PER_EXT_BLOB * CELL_SIZE, sizeof(fr_t));
+    int rc = 1;
+    for (size_t i = 0; i < n; i++) { p1_affine_t a; if (ko_p1_uncompress(&a, commitments48 + 48 * i)) goto done; p1_from_affine(&cs[i], &a); }
+    if (cells_to_fr(fr, cells, n)) goto done;
+    for (size_t i = 0; i < n; i++) { p1_affine_t a; if (ko_p1_uncompress(&a, proofs48 + 48 * i)) goto done; p1_from_affine(&ps[i], &a); }
+    if (n == 0) { *ok = 1; rc = 0; goto done; }
+    for (size_t i = 0; i < n; i++) if (cell_indices[i] >= CELLS_PER_EXT_BLOB) goto done;
+    for (size_t i = 0; i < n; i++) if (!p1_is_inf(&ps[i]) && !ko_p1_in_g1(&ps[i])) goto done;
+    /* deduplicate_with_indices (:57-76) */
+    size_t nu = 0;
+    for (size_t i = 0; i < n; i++) {
+        size_t j = 0;
+        for (; j < nu; j++) if (memcmp(ucb + 48 * j, commitments48 + 48 * i, 48) == 0) break;
+        if (j == nu) { memcpy(ucb + 48 * nu, commitments48 + 48 * i, 48); uc[nu] = cs[i]; nu++; }
+        cidx[i] = j;
+    }
+    for (size_t j = 0; j < nu; j++) if (!p1_is_inf(&uc[j]) && !ko_p1_in_g1(&uc[j])) goto done;
+    {
+        fr_t r;
+        cell_batch_challenge(&r, ucb, nu, cidx, cell_indices, cells, proofs48, n);
+        rp[0] = FR_ONE;
+        for (size_t i = 1; i < n; i++) fr_mul(&rp[i], &rp[i - 1], &r);
+        p1_t proof_lincomb, final_sum, interp, wsum;
+        ko_msm_naive(&proof_lincomb, ps, rp, n);
+        /* compute_weighted_sum_of_commitments (:697-741) */
+        for (size_t i = 0; i < n; i++) fr_add(&w[cidx[i]], &w[cidx[i]], &rp[i]);
+        ko_msm_naive(&final_sum, uc, w, nu);
+        /* compute_commitment_to_aggregated_interpolation_poly (:780-842) */
+        uint8_t used[CELLS_PER_EXT_BLOB] = {0};
+        for (size_t i = 0; i < n; i++) {
+            used[cell_indices[i]] = 1;
+            for (size_t k = 0; k < CELL_SIZE; k++) {
+                fr_t t; fr_mul(&t, &fr[i * CELL_SIZE + k], &rp[i]);
+                fr_add(&agg[cell_indices[i] * CELL_SIZE + k], &agg[cell_indices[i] * CELL_SIZE + k], &t);
+            }
+        }
+        fr_t poly[CELL_SIZE], col[CELL_SIZE], colp[CELL_SIZE];
+        memset(poly, 0, sizeof(poly));
+        for (size_t c = 0; c < CELLS_PER_EXT_BLOB; c++) {
+            if (!used[c]) continue;
+            for (size_t k = 0; k < CELL_SIZE; k++) col[brp_index(k, 6)] = agg[c * CELL_SIZE + k];
+            ko_fft_fr(s->fs, colp, col, CELL_SIZE, 1, 1);
+            /* get_inv_coset_shift_for_cell (:743-778): roots_of_unity[8192 - brp7(c)] */
+            shift_poly(colp, CELL_SIZE, &s->fs->roots_of_unity[8192 - brp_index(c, 7)]);
+            for (size_t k = 0; k < CELL_SIZE; k++) fr_add(&poly[k], &poly[k], &colp[k]);
+        }
+        ko_msm_naive(&interp, s->g1_monomial, poly, CELL_SIZE);
+        p1_sub(&final_sum, &final_sum, &interp);
+        /* computed_weighted_sum_of_proofs (:844-880): weights r^i * h_k^64 = roots_of_unity[brp7(cell) * 64] */
+        for (size_t i = 0; i < n; i++) fr_mul(&w[i], &rp[i], &s->fs->roots_of_unity[brp_index(cell_indices[i], 7) * CELL_SIZE]);
+        ko_msm_naive(&wsum, ps, w, n);
+        p1_add_or_double(&final_sum, &final_sum, &wsum);
+        *ok = pairings_verify(&final_sum, &G2_GEN, &proof_lincomb, &s->g2_monomial[CELL_SIZE]);
+        rc = 0;
+    }
+done:
+    free(cs); free(ps); free(uc); free(fr); free(rp); free(w); free(cidx); free(ucb); free(agg);
+    return rc;
+}

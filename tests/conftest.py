@@ -60,6 +60,19 @@ def golden_blobs():
 
 
 @pytest.fixture(scope="session")
+def golden_cells():
+    """pool of the well-formed 2048-byte cells the EIP-7594 vectors refer to by index"""
+    with open(os.path.join(GOLDEN, "cells.bin"), "rb") as f:
+        data = f.read()
+    return [data[i:i + 2048] for i in range(0, len(data), 2048)]
+
+
+def cell_of(ref, pool):
+    """a cell reference of vectors.json: pool index, or {"hex": ...} for malformed ones (may raise ValueError)"""
+    return pool[ref] if isinstance(ref, int) else bytes.fromhex(ref["hex"][2:])
+
+
+@pytest.fixture(scope="session")
 def B():
     """the product package; GPU tests only"""
     import rust_kzg_b200

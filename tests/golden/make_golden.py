@@ -7,6 +7,8 @@ Source: /root/reference/kzg-bench/src/test_vectors/<fn>/kzg-mainnet/<case>/data.
 Output: tests/golden/blobs.bin       unique well-formed (131072 B) blobs, concatenated
         tests/golden/vectors.json    per-function case lists; blobs referenced by index ("blob": N) or,
                                      for malformed lengths, just the length ("blob_len")
+        tests/golden/cells.bin       unique well-formed (2048 B) cells of the EIP-7594 vectors, concatenated;
+                                     vectors.json refers to them by index
         tests/golden/cells_sha256.json  sha256 of each of the 128 cells for compute_cells (full cells would be
                                      256 KiB per case; cell 0 and cell 127 are kept verbatim)
 Only data (test vectors) is extracted, no reference source code.
@@ -90,6 +92,55 @@ vec["verify_blob_kzg_proof"] = [
 vec["verify_blob_kzg_proof_batch"] = [
     dict(name=n, blobs=[blob_ref(b) for b in y["input"]["blobs"]], commitments=y["input"]["commitments"],
          proofs=y["input"]["proofs"], output=y["output"]) for n, y in cases("verify_blob_kzg_proof_batch")]
+
+# EIP-7594 recovery / cell verification (kzg-bench/src/tests/eip_7594.rs:190-468): cells are 2048-byte strings that repeat
+# across cases, so they go into a pool (cells.bin) and are referenced by index; malformed ones stay inline.
+cells_pool, cell_index = [], {}
+
+def cell_ref(x):
+    if isinstance(x, list):   # cosets_evals: 64 field elements
+        x = "0x" + "".join(e[2:] for e in x)
+    try:
+        b = unhex(x)
+    except ValueError:
+        return {"hex": x}
+    if len(b) != 2048:
+        return {"hex": x}
+    h = hashlib.sha256(b).digest()
+    if h not in cell_index:
+        cell_index[h] = len(cells_pool)
+        cells_pool.append(b)
+    return cell_index[h]
+
+vc = []
+for n, y in cases("verify_cell_kzg_proof_batch"):
+    i = y["input"]
+    vc.append(dict(name=n, commitments=i["commitments"], cell_indices=i["cell_indices"],
+                   cells=[cell_ref(c) for c in (i["cells"] or [])], proofs=i["proofs"], output=y["output"]))
+vec["verify_cell_kzg_proof_batch"] = vc
+rc = []
+for n, y in cases("recover_cells_and_kzg_proofs"):
+    i, out = y["input"], y["output"]
+    e = dict(name=n, cell_indices=i["cell_indices"], cells=[cell_ref(c) for c in (i["cells"] or [])])
+    if out is None:
+        e["output"] = None
+    else:
+        cells, proofs = out
+        assert len(cells) == 128 and len(proofs) == 128
+        e["output"] = dict(cells=[cell_ref(c) for c in cells], proofs=proofs)
+    rc.append(e)
+vec["recover_cells_and_kzg_proofs"] = rc
+ch = []
+for n, y in cases("compute_verify_cell_kzg_proof_batch_challenge"):
+    i = y["input"]
+    ch.append(dict(name=n, commitments=i["commitments"], commitment_indices=i["commitment_indices"],
+                   cell_indices=i["cell_indices"], cells=[cell_ref(c) for c in (i["cosets_evals"] or [])],
+                   proofs=i["proofs"], output=y["output"]))
+vec["compute_verify_cell_kzg_proof_batch_challenge"] = ch
+with open(os.path.join(OUT, "cells.bin"), "wb") as f:
+    for b in cells_pool:
+        f.write(b)
+print("unique cells:", len(cells_pool))
 
 with open(os.path.join(OUT, "blobs.bin"), "wb") as f:
     for b in blobs:

@@ -257,3 +257,45 @@ def test_pairing_bilinearity(K, oracle_settings):
     assert not K.pairings_verify(g1m[5], g2[3], g1m[2], g2[5])
     a = K.fr_from_ints([0x1234567890ABCDEF1234])[0]
     assert K.pairings_verify(K.p1_mult(g1m[1], a), g2[0], K.p1_mult(g1m[0], a), g2[1])
+
+
+# ---- EIP-7594 recovery / cell verification vectors (kzg-bench/src/tests/eip_7594.rs:190-468) ----------------------
+def test_cell_batch_challenge_vectors(K, vectors, golden_cells):
+    from conftest import cell_of
+    cases = vectors["compute_verify_cell_kzg_proof_batch_challenge"]
+    assert len(cases) == 10
+    for c in cases:
+        got = _run(K, lambda: "0x" + K.compute_verify_cell_kzg_proof_batch_challenge(
+            [H(x) for x in c["commitments"]], c["commitment_indices"], c["cell_indices"],
+            [cell_of(x, golden_cells) for x in c["cells"]], [H(x) for x in c["proofs"]]).hex())
+        assert got == c["output"], c["name"]
+
+
+def test_verify_cell_kzg_proof_batch_vectors(K, oracle_settings, vectors, golden_cells):
+    from conftest import cell_of
+    cases = vectors["verify_cell_kzg_proof_batch"]
+    assert len(cases) == 32
+    seen = {True: 0, False: 0, None: 0}
+    for c in cases:
+        got = _run(K, lambda: K.verify_cell_kzg_proof_batch([H(x) for x in c["commitments"]], c["cell_indices"],
+                                                            [cell_of(x, golden_cells) for x in c["cells"]],
+                                                            [H(x) for x in c["proofs"]], oracle_settings))
+        assert got == c["output"], c["name"]
+        seen[got] += 1
+    assert all(seen.values())
+
+
+def test_recover_cells_and_kzg_proofs_vectors(K, setup_text, vectors, golden_cells):
+    from conftest import cell_of
+    s = K.KZGSettings(setup_text, nthreads=os.cpu_count() or 1)
+    cases = vectors["recover_cells_and_kzg_proofs"]
+    assert len(cases) == 18
+    for c in cases:
+        got = _run(K, lambda: K.recover_cells_and_kzg_proofs(c["cell_indices"], [cell_of(x, golden_cells) for x in c["cells"]], s))
+        want = c["output"]
+        if want is None:
+            assert got is None, c["name"]
+        else:
+            assert got is not None, c["name"]
+            assert got[0] == [cell_of(x, golden_cells) for x in want["cells"]], c["name"]
+            assert got[1] == [H(x) for x in want["proofs"]], c["name"]
