@@ -168,6 +168,19 @@ B200_API C_KZG_RET b200_selftest_pairings_verify(bool *ok, const blst_p1 *a1, in
  * x_ext_fft_columns, inverse + forward fft_g1 of size 128).  Either output pointer may be NULL, not both. */
 typedef struct { uint8_t bytes[2048]; } Cell;
 B200_API C_KZG_RET compute_cells_and_kzg_proofs(Cell *cells, KZGProof *proofs, const Blob *blob, const KZGSettings *s);
+/* kzg/src/eth/c_bindings.rs:201-286 (DAS::recover_cells_and_kzg_proofs, kzg/src/das.rs:101-207): 64..128 cells with strictly
+ * ascending indices -> all 128 cells and, unless recovered_proofs is NULL, their 128 proofs */
+B200_API C_KZG_RET recover_cells_and_kzg_proofs(Cell *recovered_cells, KZGProof *recovered_proofs, const uint64_t *cell_indices,
+                                                const Cell *cells, uint64_t num_cells, const KZGSettings *s);
+/* kzg/src/eth/c_bindings.rs:288-352 (DAS::verify_cell_kzg_proof_batch, kzg/src/das.rs:294-388) */
+B200_API C_KZG_RET verify_cell_kzg_proof_batch(bool *ok, const Bytes48 *commitments_bytes, const uint64_t *cell_indices, const Cell *cells,
+                                               const Bytes48 *proofs_bytes, uint64_t num_cells, const KZGSettings *s);
+/* blst/src/eip_7594.rs:35-97: the Fiat-Shamir challenge of the cell batch verifier as a Montgomery blst_fr.  Needs a loaded
+ * trusted setup (its device context runs the argument checks); C_KZG_ERROR otherwise. */
+B200_API C_KZG_RET compute_verify_cell_kzg_proof_batch_challenge(blst_fr *challenge_out, const Bytes48 *commitment_bytes,
+                                                                 uint64_t num_commitments, const uint64_t *commitment_indices,
+                                                                 const uint64_t *cell_indices, const Cell *cells,
+                                                                 const Bytes48 *proofs_bytes, uint64_t num_cells);
 B200_API C_KZG_RET b200_compute_cells_batch(Cell *cells, const Blob *blobs, size_t n, const KZGSettings *s);
 B200_API C_KZG_RET b200_compute_cell_proofs_batch(KZGProof *proofs, const Blob *blobs, size_t n, const KZGSettings *s);
 

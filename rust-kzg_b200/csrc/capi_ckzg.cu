@@ -584,6 +584,154 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
 C_KZG_RET verify_blob_kzg_proof(bool* ok, const Blob* blob, const Bytes48* commitment_bytes, const Bytes48* proof_bytes, const KZGSettings* s) {
     return verify_blob_kzg_proof_batch(ok, blob, commitment_bytes, proof_bytes, 1, s);
 }
+// ---- EIP-7594 recovery and cell verification (kzg/src/eth/c_bindings.rs:201-352, blst/src/eip_7594.rs:35-97) ------
+static constexpr size_t kCellsPerExtBlob = 128, kBytesPerCell = 2048;
+// Fiat-Shamir input of compute_verify_cell_kzg_proof_batch_challenge (kzg/src/das.rs:390-452)
+static void cell_challenge_hash(uint8_t out[32], const uint8_t* comm48, size_t m, const uint64_t* comm_idx, const uint64_t* cell_idx,
+                                const uint8_t* cells, const uint8_t* proofs48, size_t n) {
+    sha256::Ctx c;
+    uint8_t head[48] = {'R', 'C', 'K', 'Z', 'G', 'C', 'B', 'A', 'T', 'C', 'H', '_', '_', 'V', '1', '_'};
+    const uint64_t hv[4] = {kFieldElementsPerBlob, 64, m, n};
+    for (int k = 0; k < 4; k++)
+        for (int i = 0; i < 8; i++) head[16 + 8 * k + i] = (uint8_t)(hv[k] >> (8 * (7 - i)));
+    c.update(head, 48);
+    c.update(comm48, 48 * m);
+    for (size_t i = 0; i < n; i++) {
+        uint8_t idx[16];
+        for (int b = 0; b < 8; b++) {
+            idx[b] = (uint8_t)(comm_idx[i] >> (8 * (7 - b)));
+            idx[8 + b] = (uint8_t)(cell_idx[i] >> (8 * (7 - b)));
+        }
+        c.update(idx, 16);
+        c.update(cells + i * kBytesPerCell, kBytesPerCell);
+        c.update(proofs48 + 48 * i, 48);
+    }
+    c.finish(out);
+}
+struct DevScratch {  // one-call device + pinned staging
+    uint8_t* d = nullptr;
+    uint8_t* h = nullptr;
+    explicit DevScratch(size_t bytes) {
+        d = dev_alloc<uint8_t>(bytes);
+        if (cudaMallocHost((void**)&h, bytes ? bytes : 16) != cudaSuccess) { cudaFree(d); throw CudaError(-1, "cudaMallocHost failed"); }
+    }
+    ~DevScratch() { cudaFree(d); if (h) cudaFreeHost(h); }
+};
+C_KZG_RET recover_cells_and_kzg_proofs(Cell* recovered_cells, KZGProof* recovered_proofs, const uint64_t* cell_indices, const Cell* cells,
+                                       uint64_t num_cells, const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !recovered_cells || (num_cells && (!cell_indices || !cells))) return C_KZG_BADARGS;
+        const size_t n = num_cells;
+        // kzg/src/das.rs:126-165: at most 128 cells, at least 64, indices < 128 and strictly ascending
+        if (n > kCellsPerExtBlob || n < kCellsPerExtBlob / 2) return C_KZG_BADARGS;
+        for (size_t i = 0; i < n; i++) {
+            if (cell_indices[i] >= kCellsPerExtBlob) return C_KZG_BADARGS;
+            if (i + 1 < n && cell_indices[i + 1] <= cell_indices[i]) return C_KZG_BADARGS;
+        }
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        const size_t o_out = n * kBytesPerCell, o_pr = o_out + kCellsPerExtBlob * kBytesPerCell, o_st = o_pr + kCellsPerExtBlob * 48;
+        DevScratch buf(o_st + 64);
+        cudaStream_t st = ctx->stream;
+        memcpy(buf.h, cells, n * kBytesPerCell);
+        memset(buf.h + o_st, 0, sizeof(int));
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.d, buf.h, n * kBytesPerCell, cudaMemcpyHostToDevice, st));
+        B200_CUDA_CHECK(cudaMemsetAsync(buf.d + o_st, 0, sizeof(int), st));
+        ctx->dev->recover_cells(buf.d, cell_indices, (int)n, buf.d + o_out, recovered_proofs ? buf.d + o_pr : nullptr,
+                                reinterpret_cast<int*>(buf.d + o_st), st);
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.h + o_out, buf.d + o_out, o_st + sizeof(int) - o_out, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (*reinterpret_cast<int*>(buf.h + o_st)) return C_KZG_BADARGS;
+        memcpy(recovered_cells, buf.h + o_out, kCellsPerExtBlob * kBytesPerCell);
+        if (recovered_proofs) memcpy(recovered_proofs, buf.h + o_pr, kCellsPerExtBlob * 48);
+        return C_KZG_OK;
+    });
+}
+C_KZG_RET verify_cell_kzg_proof_batch(bool* ok, const Bytes48* commitments_bytes, const uint64_t* cell_indices, const Cell* cells,
+                                      const Bytes48* proofs_bytes, uint64_t num_cells, const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !ok) return C_KZG_BADARGS;
+        const size_t n = num_cells;
+        if (n == 0) { *ok = true; return C_KZG_OK; }   // kzg/src/das.rs:319-321
+        if (!commitments_bytes || !cell_indices || !cells || !proofs_bytes) return C_KZG_BADARGS;
+        for (size_t i = 0; i < n; i++)
+            if (cell_indices[i] >= kCellsPerExtBlob) return C_KZG_BADARGS;
+        // deduplicate_with_indices (kzg/src/das.rs:57-76) on the canonical encodings
+        std::map<std::string, uint64_t> seen;
+        std::vector<uint8_t> uniq;
+        std::vector<uint64_t> comm_idx(n);
+        for (size_t i = 0; i < n; i++) {
+            std::string key((const char*)commitments_bytes[i].bytes, 48);
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(key, seen.size()).first;
+                uniq.insert(uniq.end(), commitments_bytes[i].bytes, commitments_bytes[i].bytes + 48);
+            }
+            comm_idx[i] = it->second;
+        }
+        const size_t m = seen.size();
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        // device layout: [cells n*2048][proofs n*48][uniq m*48][comm_idx n u32][cell_idx n u32][r 32][status n ints][result]
+        const size_t o_p = n * kBytesPerCell, o_c = o_p + 48 * n, o_ci = (o_c + 48 * m + 15) & ~(size_t)15, o_ki = o_ci + 4 * n,
+                     o_r = o_ki + 4 * n, o_st = o_r + 32, o_res = o_st + 4 * n;
+        DevScratch buf(o_res + 16);
+        memcpy(buf.h, cells, n * kBytesPerCell);
+        memcpy(buf.h + o_p, proofs_bytes, 48 * n);
+        memcpy(buf.h + o_c, uniq.data(), 48 * m);
+        uint32_t* ci = reinterpret_cast<uint32_t*>(buf.h + o_ci);
+        uint32_t* ki = reinterpret_cast<uint32_t*>(buf.h + o_ki);
+        for (size_t i = 0; i < n; i++) { ci[i] = (uint32_t)comm_idx[i]; ki[i] = (uint32_t)cell_indices[i]; }
+        cell_challenge_hash(buf.h + o_r, uniq.data(), m, comm_idx.data(), cell_indices, (const uint8_t*)cells, (const uint8_t*)proofs_bytes, n);
+        memset(buf.h + o_st, 0, 4 * n + 4);
+        cudaStream_t st = ctx->stream;
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.d, buf.h, o_res + 4, cudaMemcpyHostToDevice, st));
+        ctx->dev->verify_cells(buf.d + o_c, (int)m, reinterpret_cast<uint32_t*>(buf.d + o_ci), reinterpret_cast<uint32_t*>(buf.d + o_ki), buf.d,
+                               buf.d + o_p, buf.d + o_r, (int)n, reinterpret_cast<int*>(buf.d + o_st), reinterpret_cast<int*>(buf.d + o_res), st);
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.h + o_st, buf.d + o_st, 4 * n + 4, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (any_set(reinterpret_cast<int*>(buf.h + o_st), (int)n)) return C_KZG_BADARGS;
+        *ok = *reinterpret_cast<int*>(buf.h + o_res) != 0;
+        return C_KZG_OK;
+    });
+}
+// blst/src/eip_7594.rs:35-97: the challenge as a Montgomery blst_fr; every argument must decode
+C_KZG_RET compute_verify_cell_kzg_proof_batch_challenge(blst_fr* challenge_out, const Bytes48* commitment_bytes, uint64_t num_commitments,
+                                                        const uint64_t* commitment_indices, const uint64_t* cell_indices, const Cell* cells,
+                                                        const Bytes48* proofs_bytes, uint64_t num_cells) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        if (!challenge_out) return C_KZG_BADARGS;
+        memset(challenge_out, 0, sizeof(*challenge_out));
+        require_device();
+        // any loaded settings' device context will do (the function takes no settings argument in the reference either)
+        std::shared_ptr<KzgCtx> ctx;
+        {
+            std::lock_guard<std::mutex> lk(g_reg_mu);
+            if (!g_registry.empty()) ctx = g_registry.begin()->second;
+        }
+        if (!ctx) return C_KZG_ERROR;   // no trusted setup loaded: no device context to run the argument checks on
+        const size_t n = num_cells, m = num_commitments;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        const size_t o_p = n * kBytesPerCell, o_c = o_p + 48 * n, o_r = (o_c + 48 * m + 15) & ~(size_t)15, o_fr = o_r + 32, o_st = o_fr + 32;
+        DevScratch buf(o_st + 16);
+        if (n) { memcpy(buf.h, cells, n * kBytesPerCell); memcpy(buf.h + o_p, proofs_bytes, 48 * n); }
+        if (m) memcpy(buf.h + o_c, commitment_bytes, 48 * m);
+        cell_challenge_hash(buf.h + o_r, (const uint8_t*)commitment_bytes, m, commitment_indices, cell_indices, (const uint8_t*)cells,
+                            (const uint8_t*)proofs_bytes, n);
+        memset(buf.h + o_st, 0, 4);
+        cudaStream_t st = ctx->stream;
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.d, buf.h, o_st + 4, cudaMemcpyHostToDevice, st));
+        int* d_st = reinterpret_cast<int*>(buf.d + o_st);
+        ctx->dev->check_challenge_inputs(buf.d + o_c, (int)m, buf.d, buf.d + o_p, (int)n, d_st, st);
+        launch_fr_from_bytes(buf.d + o_r, 1, 1, buf.d + o_fr, d_st, st);   // hash_to_bls_field -> Montgomery
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.h + o_fr, buf.d + o_fr, 32 + 4, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (*reinterpret_cast<int*>(buf.h + o_st)) return C_KZG_BADARGS;
+        memcpy(challenge_out, buf.h + o_fr, 32);
+        return C_KZG_OK;
+    });
+}
+
 /* test hook for the pairing alone: e(a1, Q[qa]) == e(b1, Q[qb]), Q = {[1]G2, [s]G2, [s^64]G2}; host Jacobian points */
 C_KZG_RET b200_selftest_pairings_verify(bool* ok, const blst_p1* a1, int qa, const blst_p1* b1, int qb, const KZGSettings* s) {
     return ckzg_guard([&]() -> C_KZG_RET {

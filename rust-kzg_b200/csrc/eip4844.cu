@@ -7,26 +7,9 @@
 
 #include "g1.cuh"
 #include "util.cuh"
+#include "wire.cuh"
 
 namespace b200 {
-
-// ---------------------------------------------------------------------------------------------------------------
-// wire formats
-// 32 big-endian bytes -> 8 little-endian words
-__device__ __forceinline__ void load_be32(const uint8_t* p, uint32_t w[8]) {
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);  // blobs are 32-byte aligned inside a 128 KiB array
-#pragma unroll
-    for (int i = 0; i < 8; i++) w[7 - i] = __byte_perm(q[i], 0, 0x0123);
-}
-__device__ __forceinline__ bool lt_r(const uint32_t w[8]) {  // w < r ?
-#pragma unroll
-    for (int i = 7; i >= 0; i--) {
-        uint32_t m = FrParams::mod(i);
-        if (w[i] < m) return true;
-        if (w[i] > m) return false;
-    }
-    return false;
-}
 
 // bytes_to_blob (kzg/src/eip_4844.rs:867-880) = 4096 x Fr::from_bytes (blst/src/types/fr.rs:64-86): big-endian,
 // canonical (< r) or the whole blob is rejected.  Writes the canonical little-endian scalar (MSM input) and,
@@ -321,6 +304,11 @@ __global__ void __launch_bounds__(256) k_cells_out(const uint8_t* __restrict__ e
     for (int k = 0; k < 8; k++) o[k] = __byte_perm(v.v[7 - k], 0, 0x0123);
 }
 
+void launch_cells_out(const void* ext_dev, uint8_t* cells_dev, size_t total, cudaStream_t st) {
+    k_cells_out<<<div_up(total, 256), 256, 0, st>>>((const uint8_t*)ext_dev, cells_dev, total);
+    B200_LAUNCH_CHECK();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // FK20 cell proofs (compute_fk20_proofs, kzg/src/das.rs:660-696; setup blst/src/types/kzg_settings.rs:38-101)
 constexpr int kCellSize = 64, kFkK = 64, kFkK2 = 128;
@@ -350,17 +338,18 @@ __global__ void __launch_bounds__(64) k_fk_table(const uint8_t* __restrict__ poi
     cc::store_affine(table_aff + (size_t)gid * 96, cc::jac_to_affine(p));
 }
 // toeplitz_coeffs_stride (kzg/src/das.rs:626-658) for every (blob, offset): 128 Fr each
-__global__ void __launch_bounds__(256) k_fk_toeplitz(const uint8_t* __restrict__ mono, uint8_t* __restrict__ out, size_t total) {
+__global__ void __launch_bounds__(256) k_fk_toeplitz(const uint8_t* __restrict__ mono, uint8_t* __restrict__ out, size_t total,
+                                                     size_t mono_stride) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     size_t t = gid % kFkK2, bi = gid / kFkK2, i = bi % kCellSize, b = bi / kCellSize;
     const size_t d = kFieldElementsPerBlob - 1;
     fr_t v = fr_t::zero();
     if (t == 0) {
-        v = load_field_ro<fr_t>(mono + (b * kFieldElementsPerBlob + d - i) * 32);
+        v = load_field_ro<fr_t>(mono + (b * mono_stride + d - i) * 32);
     } else if (t > (size_t)kFkK2 - (kFkK - 1)) {  // t = 2r - j, j = 1 .. r-2
         size_t j = kFkK2 - t;
-        v = load_field_ro<fr_t>(mono + (b * kFieldElementsPerBlob + d - i - j * kCellSize) * 32);
+        v = load_field_ro<fr_t>(mono + (b * mono_stride + d - i - j * kCellSize) * 32);
     }
     store_field(out + gid * 32, v);
 }
@@ -439,7 +428,7 @@ KzgSettingsDev::~KzgSettingsDev() {
     for (Lane& ln : lanes_) { cudaFree(ln.scalars); cudaFree(ln.poly); cudaFree(ln.z); cudaFree(ln.y); cudaFree(ln.out_jac); }
     cudaFree(cells_a_); cudaFree(cells_b_);
     cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_);
-    cudaFree(g2_affine_); cudaFree(g2_jac_); cudaFree(g2_lines_); cudaFree(vf_buf_);
+    cudaFree(g2_affine_); cudaFree(g2_jac_); cudaFree(g2_lines_); cudaFree(vf_buf_); cudaFree(das_buf_);
 }
 
 void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st, int lane) {
@@ -536,9 +525,17 @@ void KzgSettingsDev::compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* p
     k_cells_brp_in<<<div_up(total, 256), 256, 0, st>>>((const uint8_t*)lanes_[0].poly, (uint8_t*)cells_a_, total);
     B200_LAUNCH_CHECK();
     fs_->fft_fr(cells_a_, cells_b_, kFieldElementsPerBlob, true, n, st);
+    fk20_from_mono(cells_b_, kFieldElementsPerBlob, n, proofs48, st);
+    launches_ = 8 + fk_msm_->launches_per_run() + 2 * 9;
+}
+// compute_fk20_proofs (kzg/src/das.rs:660-696) from polynomials in monomial form: blob b's coefficients 0..4095 start at
+// mono + b * stride Fr (Montgomery)
+void KzgSettingsDev::fk20_from_mono(const void* mono, size_t stride, int n, uint8_t* proofs48, cudaStream_t st) {
+    ensure_fk20(st);
+    if (n < 1 || n > fk_batch_) throw CudaError(-1, "blob batch exceeds the FK20 capacity");
     // Toeplitz coefficient vectors and their 128-point transforms
     size_t tt = (size_t)n * kCellSize * kFkK2;
-    k_fk_toeplitz<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)cells_b_, (uint8_t*)fk_a_, tt);
+    k_fk_toeplitz<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)mono, (uint8_t*)fk_a_, tt, stride);
     B200_LAUNCH_CHECK();
     fs_->fft_fr(fk_a_, fk_b_, kFkK2, false, n * kCellSize, st);
     k_fk_transpose<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)fk_b_, (uint8_t*)fk_a_, tt, (const uint8_t*)fs_->inv_pow2_dev(7));
@@ -550,7 +547,6 @@ void KzgSettingsDev::compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* p
     B200_CUDA_CHECK(cudaMemset2DAsync((uint8_t*)fk_pts_ + (size_t)kFkK * 144, (size_t)kFkK2 * 144, 0, (size_t)kFkK * 144, n, st));
     fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, false, n, st);
     launch_points_to_compressed(fk_pts_, proofs48, n * kFkK2, st, 7);  // reverse_bit_order(proofs) (:287)
-    launches_ = 8 + fk_msm_->launches_per_run() + 2 * 9;
 }
 
 // G1::from_bytes + "!is_inf && !is_valid -> Err" of the verify_* functions (kzg/src/eip_4844.rs:601-606, 655-660,

@@ -53,6 +53,7 @@ public:
     // n <= fk20_batch().  The 128 x 64 table of x_ext_fft_columns is built on first use.
     void compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* proofs48, int* status, cudaStream_t st);
     int fk20_batch(cudaStream_t st) { ensure_fk20(st); return fk_batch_; }
+    void fk20_from_mono(const void* mono, size_t stride, int n, uint8_t* proofs48, cudaStream_t st);
 
     // ---- verification (verify.cu; kzg/src/eip_4844.rs:328-435, 586-866) -----------------------------------------
     // g2_monomial: 65 x 96-byte compressed points (host).  Decodes them (on-curve check, blst/src/types/g2.rs:50-72)
@@ -70,6 +71,18 @@ public:
     // equation holds.
     void verify_batch(const uint8_t* commitments48, const uint8_t* proofs48, const uint8_t* z32, const uint8_t* y32,
                       int z_reduce, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st);
+    // ---- EIP-7594 recovery and cell verification (das7594.cu; kzg/src/das.rs:101-207, 294-388) -------------------
+    // recover_cells_and_kzg_proofs for one extended blob.  cells: n x 2048 wire bytes (device); cell_idx: their cell
+    // indices (host, already validated: n in [64, 128], < 128, strictly ascending).  cells_out: 128 x 2048 bytes,
+    // proofs48: 128 x 48 bytes or nullptr (device).  status[0] = 1 when a field element is not canonical.
+    void recover_cells(const uint8_t* cells, const uint64_t* cell_idx, int n, uint8_t* cells_out, uint8_t* proofs48, int* status,
+                       cudaStream_t st);
+    // verify_cell_kzg_proof_batch: commitments48 = m unique commitments (device), comm_idx / cell_idx: n indices each
+    // (device, uint32), cells n x 2048, proofs48 n x 48, r32 = Fiat-Shamir hash.  status[0..n) flags invalid inputs.
+    void verify_cells(const uint8_t* commitments48, int m, const uint32_t* comm_idx, const uint32_t* cell_idx, const uint8_t* cells,
+                      const uint8_t* proofs48, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st);
+    void check_challenge_inputs(const uint8_t* commitments48, int m, const uint8_t* cells, const uint8_t* proofs48, int n, int* status,
+                                cudaStream_t st);
     // e(a1, Q[qa]) == e(b1, Q[qb]) for Jacobian G1 points on the device, Q[i] in {0: [1]G2, 1: [s]G2, 2: [s^64]G2}
     void pairings_verify(const void* a1_jac, int qa, const void* b1_jac, int qb, int* result, cudaStream_t st);
     int launches_last() const { return launches_; }
@@ -101,6 +114,11 @@ private:
     void* vf_buf_ = nullptr;     // verification workspace, grown on demand
     size_t vf_cap_ = 0;          // terms the workspace holds
     void ensure_verify_ws(size_t n);
+    void lincomb2_and_pair(const uint8_t* pts, const uint8_t* scalars, size_t L, uint8_t* partials, uint8_t* sums, uint8_t* scratch,
+                           int qa, int qb, int* result, cudaStream_t st);
+    void* das_buf_ = nullptr;    // recovery / cell-verification workspace (das7594.cu), grown on demand
+    size_t das_bytes_ = 0;
+    uint8_t* ensure_das_ws(size_t bytes);
 };
 
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input
@@ -109,6 +127,8 @@ void launch_uncompress_g1(const uint8_t* in48_dev, void* affine_out_dev, int* fl
 void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st);
 // Fr::from_bytes (reduce = 0: status[i] = 1 when >= r) / hash_to_bls_field (reduce = 1) -> Montgomery; and back
 void launch_fr_from_bytes(const uint8_t* bytes32_dev, int n, int reduce, void* fr_mont_dev, int* status_dev, cudaStream_t st);
+// bit-reverse (13 bits per 8192-element extended blob) + big-endian serialisation: evaluations -> cells
+void launch_cells_out(const void* ext_dev, uint8_t* cells_dev, size_t total, cudaStream_t st);
 void launch_fr_to_bytes(const void* fr_mont_dev, int n, uint8_t* bytes32_dev, cudaStream_t st);
 
 }  // namespace b200

@@ -208,6 +208,18 @@ static void run_pairing(const uint8_t* p0, const uint8_t* l0, int neg0, const ui
     B200_LAUNCH_CHECK();
 }
 
+// segment 0 = pts[0..L), segment 1 = pts[L..2L) (affine, canonical scalars): result = e(-S0, Q[qa]) e(S1, Q[qb]) == 1
+void KzgSettingsDev::lincomb2_and_pair(const uint8_t* pts, const uint8_t* scalars, size_t L, uint8_t* partials, uint8_t* sums,
+                                       uint8_t* scratch, int qa, int qb, int* result, cudaStream_t st) {
+    const size_t blocks = (L + 7) / 8;
+    k_lincomb_quads<<<dim3((unsigned)blocks, 2), 32, 0, st>>>(pts, scalars, (int)L, partials);
+    k_quad_sum<<<2, 32, 0, st>>>(partials, (int)blocks, sums);
+    B200_LAUNCH_CHECK();
+    const uint8_t* lines = (const uint8_t*)g2_lines_;
+    const size_t tb = (size_t)kMillerLines * kLineBytes;
+    run_pairing(sums, lines + qa * tb, 1, sums + 192, lines + qb * tb, 0, scratch, result, st);
+}
+
 void KzgSettingsDev::verify_batch(const uint8_t* commitments48, const uint8_t* proofs48, const uint8_t* z32, const uint8_t* y32,
                                   int z_reduce, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st) {
     if (!g2_lines_) throw CudaError(-1, "trusted setup was loaded without G2 points");
@@ -231,11 +243,8 @@ void KzgSettingsDev::verify_batch(const uint8_t* commitments48, const uint8_t* p
     launch_fr_from_bytes(y32, n, 0, y, status, st);
     if (n > 1) launch_fr_from_bytes(r32, 1, 1, r, status, st);  // hash_to_bls_field never fails: status untouched
     k_verify_terms<<<1, 32, 0, st>>>(comm_aff, proof_aff, z, y, r, n, pts, scalars);
-    k_lincomb_quads<<<dim3((unsigned)blocks, 2), 32, 0, st>>>(pts, scalars, (int)L, partials);
-    k_quad_sum<<<2, 32, 0, st>>>(partials, (int)blocks, sums);
     B200_LAUNCH_CHECK();
-    const uint8_t* lines = (const uint8_t*)g2_lines_;
-    run_pairing(sums, lines + (size_t)1 * kMillerLines * kLineBytes, 1, sums + 192, lines, 0, scratch, result, st);
+    lincomb2_and_pair(pts, scalars, L, partials, sums, scratch, 1, 0, result, st);
     launches_ = 9 + (n > 1);
 }
 

@@ -52,6 +52,9 @@ def _L():
             "verify_blob_kzg_proof_batch": (ci, [vp, vp, vp, vp, sz, S]),
             "b200_verify_kzg_proof_batch": (ci, [vp, vp, vp, vp, vp, sz, S]),
             "b200_selftest_pairings_verify": (ci, [vp, vp, ci, vp, ci, S]),
+            "recover_cells_and_kzg_proofs": (ci, [vp, vp, vp, vp, u64, S]),
+            "verify_cell_kzg_proof_batch": (ci, [vp, vp, vp, vp, vp, u64, S]),
+            "compute_verify_cell_kzg_proof_batch_challenge": (ci, [vp, vp, u64, vp, vp, vp, vp, u64]),
             "b200_kzg_launches": (ci, [S]),
             "b200_kzg_max_batch": (ci, [S]),
             "b200_selftest_sha256": (None, [vp, vp, sz, ci]),
@@ -269,6 +272,63 @@ class KZGSettings:
         if rc != C_KZG_OK:
             raise KzgError(rc, "pairings_verify")
         return bool(ok.value)
+
+    # ---- EIP-7594 recovery / cell verification (kzg/src/eth/c_bindings.rs:201-352)
+    @staticmethod
+    def _cells(cells):
+        arrs = [_buf(c, 2048, "cell") for c in cells]
+        return np.concatenate(arrs) if arrs else np.zeros(1, np.uint8)
+
+    @staticmethod
+    def _g1s(items, what):
+        arrs = [_buf(c, 48, what) for c in items]
+        return np.concatenate(arrs) if arrs else np.zeros(1, np.uint8)
+
+    @staticmethod
+    def _u64s(vals):
+        for v in vals:
+            if not 0 <= int(v) < 1 << 64:
+                raise KzgError(C_KZG_BADARGS, "index out of range")
+        return np.asarray([int(v) for v in vals] or [0], dtype=np.uint64)
+
+    def recover_cells_and_kzg_proofs(self, cell_indices, cells, want_proofs=True):
+        """-> (128 cells of 2048 bytes, 128 proofs of 48 bytes or None)"""
+        if len(cell_indices) != len(cells):
+            raise KzgError(C_KZG_BADARGS, "Cell indicies mismatch")      # kzg/src/das.rs:119-124
+        n = len(cells)
+        idx, cb = self._u64s(cell_indices), self._cells(cells)
+        out_c, out_p = np.zeros(128 * 2048, np.uint8), np.zeros(128 * 48, np.uint8)
+        rc = _L().recover_cells_and_kzg_proofs(_p(out_c), _p(out_p) if want_proofs else None, _p(idx), _p(cb), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "recover_cells_and_kzg_proofs")
+        craw, praw = out_c.tobytes(), out_p.tobytes()
+        return ([craw[i * 2048:(i + 1) * 2048] for i in range(128)],
+                [praw[i * 48:(i + 1) * 48] for i in range(128)] if want_proofs else None)
+
+    def verify_cell_kzg_proof_batch(self, commitments, cell_indices, cells, proofs) -> bool:
+        n = len(cells)
+        if len(commitments) != n or len(cell_indices) != n or len(proofs) != n:
+            raise KzgError(C_KZG_BADARGS, "count mismatch")               # kzg/src/das.rs:306-317
+        cb, idx = self._g1s(commitments, "commitment"), self._u64s(cell_indices)
+        cl, pb = self._cells(cells), self._g1s(proofs, "proof")
+        ok = C.c_bool(False)
+        rc = _L().verify_cell_kzg_proof_batch(C.byref(ok), _p(cb), _p(idx), _p(cl), _p(pb), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "verify_cell_kzg_proof_batch")
+        return bool(ok.value)
+
+    def compute_verify_cell_kzg_proof_batch_challenge(self, commitments, commitment_indices, cell_indices, cells, proofs):
+        """-> the challenge as a Montgomery blst_fr (4 u64 limbs)"""
+        n = len(cells)
+        if len(commitment_indices) != n or len(cell_indices) != n or len(proofs) != n:
+            raise KzgError(C_KZG_BADARGS, "Cell count mismatch")          # kzg/src/das.rs:401-406
+        cb, ci, ki = self._g1s(commitments, "commitment"), self._u64s(commitment_indices), self._u64s(cell_indices)
+        cl, pb = self._cells(cells), self._g1s(proofs, "proof")
+        out = np.zeros(4, np.uint64)
+        rc = _L().compute_verify_cell_kzg_proof_batch_challenge(_p(out), _p(cb), len(commitments), _p(ci), _p(ki), _p(cl), _p(pb), n)
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_verify_cell_kzg_proof_batch_challenge")
+        return out
 
     # ---- batched extensions: blobs (n,131072) u8, returns (n,48) u8 ...
     def blob_to_kzg_commitment_batch(self, blobs, out=None):
