@@ -163,6 +163,13 @@ B200_API C_KZG_RET b200_verify_kzg_proof_batch(bool *ok, const Bytes48 *commitme
 /* test hook: e(a1, Q[qa]) == e(b1, Q[qb]) with Q = {[1]G2, [s]G2, [s^64]G2} (pairings_verify, blst/src/kzg_proofs.rs:74-100) */
 B200_API C_KZG_RET b200_selftest_pairings_verify(bool *ok, const blst_p1 *a1, int qa, const blst_p1 *b1, int qb, const KZGSettings *s);
 
+/* blst/src/eip_4844.rs:498-530: helper exports of the reference's C ABI (used by its binding tests).  compute_challenge
+ * writes the Fiat-Shamir challenge (Montgomery blst_fr) of a blob and a Jacobian commitment; the blob must be valid (the
+ * reference unwraps).  bytes_to_kzg_commitment = G1::from_bytes (no subgroup check); bytes_from_bls_field = Fr::to_bytes. */
+B200_API void compute_challenge(blst_fr *eval_challenge_out, const Blob *blob, const blst_p1 *commitment);
+B200_API C_KZG_RET bytes_to_kzg_commitment(blst_p1 *out, const Bytes48 *b);
+B200_API void bytes_from_bls_field(Bytes32 *out, const blst_fr *inp);
+
 /* EIP-7594 compute_cells_and_kzg_proofs (kzg/src/das.rs:244-292; C ABI kzg/src/eth/c_bindings.rs:134-199):
  * cells = BRP(NTT_8192(INTT_4096(BRP(blob)))); proofs by FK20 (64 x NTT_128, 128 fixed-base lincombs of 64 points over
  * x_ext_fft_columns, inverse + forward fft_g1 of size 128).  Either output pointer may be NULL, not both. */

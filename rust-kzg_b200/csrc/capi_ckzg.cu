@@ -732,6 +732,61 @@ C_KZG_RET compute_verify_cell_kzg_proof_batch_challenge(blst_fr* challenge_out, 
     });
 }
 
+// ---- the three helper exports of blst/src/eip_4844.rs:498-530 (no settings argument: they run on the default stream) ----
+void compute_challenge(blst_fr* eval_challenge_out, const Blob* blob, const blst_p1* commitment) {
+    if (!eval_challenge_out) return;
+    memset(eval_challenge_out, 0, sizeof(*eval_challenge_out));
+    if (!blob || !commitment) return;
+    ckzg_guard([&]() -> C_KZG_RET {
+        require_device();
+        DevScratch buf(144 + 48 + 32 + 32);
+        memcpy(buf.h, commitment, 144);
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.d, buf.h, 144, cudaMemcpyHostToDevice, nullptr));
+        launch_points_to_compressed(buf.d, buf.d + 144, 1, nullptr);          // commitment.to_bytes() (kzg/src/eip_4844.rs:936-938)
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.h + 144, buf.d + 144, 48, cudaMemcpyDeviceToHost, nullptr));
+        B200_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+        challenge_hash(buf.h + 192, blob->bytes, buf.h + 144);
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.d + 192, buf.h + 192, 32, cudaMemcpyHostToDevice, nullptr));
+        launch_fr_from_bytes(buf.d + 192, 1, 1, buf.d + 224, nullptr, nullptr);  // hash_to_bls_field -> Montgomery
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.h + 224, buf.d + 224, 32, cudaMemcpyDeviceToHost, nullptr));
+        B200_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+        memcpy(eval_challenge_out, buf.h + 224, 32);
+        return C_KZG_OK;
+    });
+}
+C_KZG_RET bytes_to_kzg_commitment(blst_p1* out, const Bytes48* b) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        if (!out || !b) return C_KZG_BADARGS;
+        require_device();
+        DevScratch buf(48 + 96 + 144 + 16);
+        memcpy(buf.h, b->bytes, 48);
+        memset(buf.h + 288, 0, 4);
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.d, buf.h, 48, cudaMemcpyHostToDevice, nullptr));
+        B200_CUDA_CHECK(cudaMemsetAsync(buf.d + 288, 0, 4, nullptr));
+        launch_uncompress_g1(buf.d, buf.d + 48, reinterpret_cast<int*>(buf.d + 288), 1, nullptr);   // FsG1::from_bytes: no subgroup check
+        launch_affine_to_jac(buf.d + 48, buf.d + 144, 1, nullptr);
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.h + 144, buf.d + 144, 148, cudaMemcpyDeviceToHost, nullptr));
+        B200_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+        if (*reinterpret_cast<int*>(buf.h + 288)) return C_KZG_BADARGS;
+        memcpy(out, buf.h + 144, 144);
+        return C_KZG_OK;
+    });
+}
+void bytes_from_bls_field(Bytes32* out, const blst_fr* inp) {
+    if (!out || !inp) return;
+    ckzg_guard([&]() -> C_KZG_RET {
+        require_device();
+        DevScratch buf(64);
+        memcpy(buf.h, inp, 32);
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.d, buf.h, 32, cudaMemcpyHostToDevice, nullptr));
+        launch_fr_to_bytes(buf.d, 1, buf.d + 32, nullptr);
+        B200_CUDA_CHECK(cudaMemcpyAsync(buf.h + 32, buf.d + 32, 32, cudaMemcpyDeviceToHost, nullptr));
+        B200_CUDA_CHECK(cudaStreamSynchronize(nullptr));
+        memcpy(out->bytes, buf.h + 32, 32);
+        return C_KZG_OK;
+    });
+}
+
 /* test hook for the pairing alone: e(a1, Q[qa]) == e(b1, Q[qb]), Q = {[1]G2, [s]G2, [s^64]G2}; host Jacobian points */
 C_KZG_RET b200_selftest_pairings_verify(bool* ok, const blst_p1* a1, int qa, const blst_p1* b1, int qb, const KZGSettings* s) {
     return ckzg_guard([&]() -> C_KZG_RET {

@@ -563,6 +563,11 @@ void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int
     k_decode_g1_checked<<<div_up(n, 32), 32, 0, st>>>(in48_dev, n, (uint8_t*)affine_out_dev, status_dev);
     B200_LAUNCH_CHECK();
 }
+void launch_affine_to_jac(const void* affine_dev, void* jac_dev, int n, cudaStream_t st) {
+    if (n < 1) return;
+    k_affine_to_jac<<<div_up(n, 128), 128, 0, st>>>((const uint8_t*)affine_dev, (uint8_t*)jac_dev, nullptr, n, 0, 0);
+    B200_LAUNCH_CHECK();
+}
 void launch_fr_from_bytes(const uint8_t* bytes32_dev, int n, int reduce, void* fr_mont_dev, int* status_dev, cudaStream_t st) {
     if (n < 1) return;
     k_z_to_fr<<<div_up(n, 64), 64, 0, st>>>(bytes32_dev, n, reduce, (uint8_t*)fr_mont_dev, status_dev);

@@ -125,6 +125,8 @@ private:
 void launch_uncompress_g1(const uint8_t* in48_dev, void* affine_out_dev, int* flags_dev, int n, cudaStream_t st);
 // uncompress + subgroup check (G1::from_bytes followed by is_inf() || is_valid()); status[i] = 1 on failure
 void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st);
+// blst_p1_from_affine for n points
+void launch_affine_to_jac(const void* affine_dev, void* jac_dev, int n, cudaStream_t st);
 // Fr::from_bytes (reduce = 0: status[i] = 1 when >= r) / hash_to_bls_field (reduce = 1) -> Montgomery; and back
 void launch_fr_from_bytes(const uint8_t* bytes32_dev, int n, int reduce, void* fr_mont_dev, int* status_dev, cudaStream_t st);
 // bit-reverse (13 bits per 8192-element extended blob) + big-endian serialisation: evaluations -> cells

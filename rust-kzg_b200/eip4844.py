@@ -8,7 +8,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["KZGSettings", "KzgError", "BYTES_PER_BLOB", "load_trusted_setup_file", "default_trusted_setup_path"]
+__all__ = ["KZGSettings", "KzgError", "BYTES_PER_BLOB", "load_trusted_setup_file", "default_trusted_setup_path",
+           "compute_challenge", "bytes_to_kzg_commitment", "bytes_from_bls_field"]
 
 BYTES_PER_BLOB = 131072
 C_KZG_OK, C_KZG_BADARGS, C_KZG_ERROR, C_KZG_MALLOC = 0, 1, 2, 3
@@ -55,6 +56,9 @@ def _L():
             "recover_cells_and_kzg_proofs": (ci, [vp, vp, vp, vp, u64, S]),
             "verify_cell_kzg_proof_batch": (ci, [vp, vp, vp, vp, vp, u64, S]),
             "compute_verify_cell_kzg_proof_batch_challenge": (ci, [vp, vp, u64, vp, vp, vp, vp, u64]),
+            "compute_challenge": (None, [vp, vp, vp]),
+            "bytes_to_kzg_commitment": (ci, [vp, vp]),
+            "bytes_from_bls_field": (None, [vp, vp]),
             "b200_kzg_launches": (ci, [S]),
             "b200_kzg_max_batch": (ci, [S]),
             "b200_selftest_sha256": (None, [vp, vp, sz, ci]),
@@ -90,6 +94,32 @@ def _buf(b, size=None, what="argument"):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+# ---- helper exports of blst/src/eip_4844.rs:498-530 (no settings argument)
+def compute_challenge(blob, commitment_p1):
+    """blob bytes + commitment as blst_p1 (18 u64 limbs) -> challenge as a Montgomery blst_fr (4 u64 limbs)"""
+    b = _buf(blob, BYTES_PER_BLOB, "blob")
+    c = np.ascontiguousarray(commitment_p1, dtype=np.uint64).reshape(18)
+    out = np.zeros(4, np.uint64)
+    _L().compute_challenge(_p(out), _p(b), _p(c))
+    return out
+
+
+def bytes_to_kzg_commitment(b48):
+    b = _buf(b48, 48, "commitment")
+    out = np.zeros(18, np.uint64)
+    rc = _L().bytes_to_kzg_commitment(_p(out), _p(b))
+    if rc != C_KZG_OK:
+        raise KzgError(rc, "bytes_to_kzg_commitment")
+    return out
+
+
+def bytes_from_bls_field(fr) -> bytes:
+    f = np.ascontiguousarray(fr, dtype=np.uint64).reshape(4)
+    out = np.zeros(32, np.uint8)
+    _L().bytes_from_bls_field(_p(out), _p(f))
+    return out.tobytes()
 
 
 class KZGSettings:

@@ -265,3 +265,17 @@ def test_cell_proofs_batch_matches_oracle(B, K, ts, oracle_settings):
     # both outputs NULL is rejected (kzg/src/das.rs:250-252)
     import ctypes as C
     assert B.lib().compute_cells_and_kzg_proofs(None, None, blobs[0].ctypes.data_as(C.c_void_p), C.byref(ts.c)) == 1
+
+
+def test_helper_exports_compute_challenge_vectors(B, K, vectors, golden_blobs):
+    """compute_challenge / bytes_to_kzg_commitment / bytes_from_bls_field (blst/src/eip_4844.rs:498-530) on the reference's
+    compute_challenge vectors"""
+    for c in vectors["compute_challenge"]:
+        p1 = B.bytes_to_kzg_commitment(H(c["commitment"]))
+        assert K.p1_compress(p1) == H(c["commitment"])
+        fr = B.compute_challenge(golden_blobs[c["blob"]], p1)
+        assert "0x" + B.bytes_from_bls_field(fr).hex() == c["output"], c["name"]
+    with pytest.raises(B.KzgError):
+        B.bytes_to_kzg_commitment(bytes(48))           # compression flag missing
+    x = K.fr_from_ints([R_MOD - 5])[0]
+    assert B.bytes_from_bls_field(x) == (R_MOD - 5).to_bytes(32, "big")
