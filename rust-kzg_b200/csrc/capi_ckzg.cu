@@ -506,27 +506,47 @@ static void batch_challenge_hash(uint8_t out[32], const uint8_t* c48, const uint
     }
     c.finish(out);
 }
-// verify_kzg_proof_batch (kzg/src/eip_4844.rs:380-435) on host arrays of wire bytes; ctx->mu held by the caller
-static C_KZG_RET verify_core(KzgCtx& ctx, bool* ok, const uint8_t* c48, const uint8_t* z32, const uint8_t* y32, const uint8_t* p48, size_t n) {
+// verify_kzg_proof_batch (kzg/src/eip_4844.rs:380-435) on host arrays of wire bytes; ctx->mu held by the caller.
+// Stage 1 (points): copy + decode + subgroup-check the commitments and proofs on the side stream -- for the blob
+// verifiers this runs under the blob transfer, the host hashing and the polynomial evaluations.
+// Stage 2 (finish): z, y and the Fiat-Shamir challenge arrive, two short lincombs and the pairing run on the main stream.
+struct VerifyLayout {
+    size_t n, o_p, o_z, o_y, o_r, o_st, o_res;
+    explicit VerifyLayout(size_t n_) : n(n_), o_p(48 * n_), o_z(96 * n_), o_y(128 * n_), o_r(160 * n_), o_st(160 * n_ + 32),
+                                       o_res(160 * n_ + 32 + n_ * sizeof(int)) {}
+};
+static void verify_stage_points(KzgCtx& ctx, const uint8_t* c48, const uint8_t* p48, size_t n) {
     ctx.ensure_verify(n);
-    uint8_t* h = ctx.h_verify;
-    uint8_t* d = ctx.d_verify;
-    const size_t o_p = 48 * n, o_z = 96 * n, o_y = 128 * n, o_r = 160 * n, o_st = o_r + 32, o_res = o_st + n * sizeof(int);
+    VerifyLayout L(n);
+    uint8_t *h = ctx.h_verify, *d = ctx.d_verify;
+    Stage& g = ctx.stage[0];
     memcpy(h, c48, 48 * n);
-    memcpy(h + o_p, p48, 48 * n);
-    memcpy(h + o_z, z32, 32 * n);
-    memcpy(h + o_y, y32, 32 * n);
-    if (n > 1) batch_challenge_hash(h + o_r, c48, z32, y32, p48, n); else memset(h + o_r, 0, 32);
-    memset(h + o_st, 0, n * sizeof(int) + sizeof(int));
+    memcpy(h + L.o_p, p48, 48 * n);
+    B200_CUDA_CHECK(cudaMemcpyAsync(d, h, 96 * n, cudaMemcpyHostToDevice, g.side));
+    B200_CUDA_CHECK(cudaMemsetAsync(d + L.o_st, 0, n * sizeof(int) + sizeof(int), g.side));
+    ctx.dev->verify_decode(d, d + L.o_p, (int)n, reinterpret_cast<int*>(d + L.o_st), g.side);
+    B200_CUDA_CHECK(cudaEventRecord(g.ev_side, g.side));
+}
+static C_KZG_RET verify_finish(KzgCtx& ctx, bool* ok, const uint8_t* c48, const uint8_t* z32, const uint8_t* y32, const uint8_t* p48, size_t n) {
+    VerifyLayout L(n);
+    uint8_t *h = ctx.h_verify, *d = ctx.d_verify;
+    memcpy(h + L.o_z, z32, 32 * n);
+    memcpy(h + L.o_y, y32, 32 * n);
+    if (n > 1) batch_challenge_hash(h + L.o_r, c48, z32, y32, p48, n); else memset(h + L.o_r, 0, 32);
     cudaStream_t st = ctx.stream;
-    B200_CUDA_CHECK(cudaMemcpyAsync(d, h, o_res + sizeof(int), cudaMemcpyHostToDevice, st));
-    ctx.dev->verify_batch(d, d + o_p, d + o_z, d + o_y, 0, d + o_r, (int)n, reinterpret_cast<int*>(d + o_st),
-                          reinterpret_cast<int*>(d + o_res), st);
-    B200_CUDA_CHECK(cudaMemcpyAsync(h + o_st, d + o_st, n * sizeof(int) + sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(st, ctx.stage[0].ev_side, 0));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d + L.o_z, h + L.o_z, 64 * n + 32, cudaMemcpyHostToDevice, st));
+    ctx.dev->verify_batch(d, d + L.o_p, d + L.o_z, d + L.o_y, 0, d + L.o_r, (int)n, reinterpret_cast<int*>(d + L.o_st),
+                          reinterpret_cast<int*>(d + L.o_res), st, /*skip_decode=*/true);
+    B200_CUDA_CHECK(cudaMemcpyAsync(h + L.o_st, d + L.o_st, n * sizeof(int) + sizeof(int), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (any_set(reinterpret_cast<int*>(h + o_st), (int)n)) return C_KZG_BADARGS;
-    *ok = *reinterpret_cast<int*>(h + o_res) != 0;
+    if (any_set(reinterpret_cast<int*>(h + L.o_st), (int)n)) return C_KZG_BADARGS;
+    *ok = *reinterpret_cast<int*>(h + L.o_res) != 0;
     return C_KZG_OK;
+}
+static C_KZG_RET verify_core(KzgCtx& ctx, bool* ok, const uint8_t* c48, const uint8_t* z32, const uint8_t* y32, const uint8_t* p48, size_t n) {
+    verify_stage_points(ctx, c48, p48, n);
+    return verify_finish(ctx, ok, c48, z32, y32, p48, n);
 }
 /* b200 extension: verify_kzg_proof_batch over caller-supplied (commitment, z, y, proof) tuples */
 C_KZG_RET b200_verify_kzg_proof_batch(bool* ok, const Bytes48* commitments, const Bytes32* zs, const Bytes32* ys, const Bytes48* proofs,
@@ -557,6 +577,7 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
         // phase 1, chunked over the two lanes: z_i = challenge(blob_i, C_i) hashed on the host while the blobs cross
         // PCIe, y_i = p_i(z_i) on the device (compute_challenges_and_evaluate_polynomial, :700-718)
         std::vector<uint8_t> zs(32 * n), ys(32 * n);
+        verify_stage_points(*ctx, (const uint8_t*)commitments_bytes, (const uint8_t*)proofs_bytes, n);
         C_KZG_RET rc = run_chunks(*ctx, n, ctx->max_batch,
             [&](int lane, size_t off, int m) {
                 Stage& g = ctx->stage[lane];
@@ -576,9 +597,12 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
                 memcpy(ys.data() + 32 * off, g.h_y32(), (size_t)m * 32);
                 return C_KZG_OK;
             });
-        if (rc != C_KZG_OK) return rc;
+        if (rc != C_KZG_OK) {
+            cudaStreamSynchronize(ctx->stage[0].side);   // the early point decoding must not outlive this call's buffers
+            return rc;
+        }
         // phase 2: one batched pairing check over all n (verify_kzg_proof_batch, :380-435)
-        return verify_core(*ctx, ok, (const uint8_t*)commitments_bytes, zs.data(), ys.data(), (const uint8_t*)proofs_bytes, n);
+        return verify_finish(*ctx, ok, (const uint8_t*)commitments_bytes, zs.data(), ys.data(), (const uint8_t*)proofs_bytes, n);
     });
 }
 C_KZG_RET verify_blob_kzg_proof(bool* ok, const Blob* blob, const Bytes48* commitment_bytes, const Bytes48* proof_bytes, const KZGSettings* s) {

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "g1.cuh"
+#include "g1_quad.cuh"
 #include "util.cuh"
 #include "wire.cuh"
 
@@ -125,46 +126,6 @@ __global__ void k_affine_to_jac(const uint8_t* __restrict__ aff, uint8_t* __rest
     cc::jac_t p{a.x, a.y, a.is_inf() ? cc::fp_t::zero() : cc::fp_t::one()};
     cc::store_jac(jac + (size_t)j * 144, p);
     if (aff_out) cc::store_affine(aff_out + (size_t)j * 96, a);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// subgroup membership (blst_p1_in_g1 via G1::is_valid, blst/src/types/g1.rs:110-119).  Uses the endomorphism test
-// of eprint 2021/1130 sec. 6 as zkcrypto does (zkcrypto/bls12_381/src/g1.rs:401-410): P in G1  <=>
-// (beta*x, y) == -[z^2] P, z = -0xd201000000010000: two 64-bit scalar multiplications instead of one by r.
-__device__ __forceinline__ void mul_by_abs_z(cc::xyzz_t& acc, const cc::affine_t& base) {
-    // |z| = 0xd201000000010000, MSB first; acc starts as base
-    const uint64_t Z = 0xd201000000010000ull;
-    for (int bit = 62; bit >= 0; bit--) {
-        cc::xyzz_dbl(acc);
-        if ((Z >> bit) & 1) cc::xyzz_add_affine(acc, base);
-    }
-}
-__device__ __forceinline__ bool in_g1(const cc::affine_t& p) {
-    using cc::fp_t;
-    if (p.is_inf()) return true;
-    cc::xyzz_t t = cc::affine_to_xyzz(p);
-    mul_by_abs_z(t, p);                         // |z| P
-    cc::affine_t zp = cc::xyzz_to_affine(t);    // one inversion; keeps the second ladder a mixed-add ladder
-    if (zp.is_inf()) return false;
-    cc::xyzz_t u = cc::affine_to_xyzz(zp);
-    mul_by_abs_z(u, zp);                        // z^2 P
-    if (u.is_inf()) return false;
-    fp_t beta;
-    {
-        const uint32_t Bm[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
-                                 0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
-#pragma unroll
-        for (int i = 0; i < 12; i++) beta.v[i] = Bm[i];
-    }
-    // (beta x, y) == -(X/ZZ, Y/ZZZ)  <=>  beta x ZZ == X  and  y ZZZ == -Y
-    return (beta * p.x * u.zz == u.x) && (p.y * u.zzz == u.y.neg());
-}
-// status[i] = 1 unless commitment i decodes and (is infinity or lies in G1)
-__global__ void __launch_bounds__(32) k_validate_commitments(const uint8_t* __restrict__ in, int n, int* __restrict__ status) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    cc::affine_t a;
-    if (!uncompress_point(in + (size_t)i * 48, a) || !in_g1(a)) status[i] = 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -550,17 +511,86 @@ void KzgSettingsDev::fk20_from_mono(const void* mono, size_t stride, int n, uint
 }
 
 // G1::from_bytes + "!is_inf && !is_valid -> Err" of the verify_* functions (kzg/src/eip_4844.rs:601-606, 655-660,
-// 720-736): affine out, status[i] = 1 when point i is malformed, off the curve or outside the subgroup
-__global__ void __launch_bounds__(32) k_decode_g1_checked(const uint8_t* __restrict__ in, int n, uint8_t* __restrict__ out, int* __restrict__ status) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    cc::affine_t a;
-    if (!uncompress_point(in + (size_t)i * 48, a) || !in_g1(a)) status[i] = 1;
-    cc::store_affine(out + (size_t)i * 96, a);
+// 720-736) and of compute_blob_kzg_proof (:556-558): affine out (may be nullptr), status[i % status_mod] = 1 when point i
+// is malformed, off the curve or outside the subgroup.
+// One lane QUAD per point: decoding (a 381-bit square-root chain) runs redundantly on the four lanes, then the subgroup
+// test -- (beta x, y) == -[z^2] P, two 64-bit ladders (eprint 2021/1130 sec. 6, zkcrypto/bls12_381/src/g1.rs:401-410) --
+// runs on the quad arithmetic of g1_quad.cuh: 3 / 4 multiplication levels per doubling / addition instead of 9 / 14
+// multiplications, and every quad of the warp follows the same instruction stream (the scalar is a constant).
+__device__ __forceinline__ bool uncompress_point_u(const uint8_t* in, affine_t& out) {
+    uint32_t b0 = in[0];
+    uint32_t cflag = b0 >> 7, iflag = (b0 >> 6) & 1, sflag = (b0 >> 5) & 1;
+    fp_t x;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const uint8_t* p = in + 4 * (11 - k);
+        x.v[k] = (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+    }
+    x.v[11] &= 0x1fffffffu;
+    out.x = fp_t::zero();
+    out.y = fp_t::zero();
+    if (!cflag) return false;
+    if (iflag) return !sflag && x.is_zero();
+    bool lt = false;
+#pragma unroll
+    for (int i = 11; i >= 0; i--) {
+        uint32_t m = FpParams::mod(i);
+        if (x.v[i] != m) { lt = x.v[i] < m; break; }
+    }
+    if (!lt) return false;
+    fp_t xm = x.to_mont();
+    fp_t four = fp_t::one().dbl().dbl();
+    fp_t y2 = xm.sqr() * xm + four;
+    const uint32_t E[12] = {0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u,
+                            0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au};  // (p+1)/4
+    fp_t y = y2.pow_words(E);
+    if (y.sqr() != y2) return false;
+    if (fp_is_lex_largest(y) != (bool)sflag) y = y.neg();
+    out.x = xm;
+    out.y = y;
+    return true;
 }
-void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st) {
+__device__ __forceinline__ fp_t quad_mul_by_abs_z(const fp_t& base) {
+    const uint64_t Z = 0xd201000000010000ull;
+    fp_t acc = base;
+#pragma unroll 1
+    for (int bit = 62; bit >= 0; bit--) {
+        acc = quad_dbl(acc);
+        if ((Z >> bit) & 1) acc = quad_add(acc, base);
+    }
+    return acc;
+}
+__global__ void __launch_bounds__(32) k_decode_g1_checked(const uint8_t* __restrict__ in, int n, uint8_t* __restrict__ out,
+                                                          int* __restrict__ status, int status_mod) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 2), role = threadIdx.x & 3, base = threadIdx.x & ~3;
+    const bool live = q < n;
+    const int i = live ? q : 0;
+    affine_t a;
+    bool ok = uncompress_point_u(in + (size_t)i * 48, a);
+    const bool inf = a.is_inf();
+    fp_t comp = role == 0 ? a.x : role == 1 ? a.y : fp_t::one();
+    if (inf) comp = fp_t::zero();
+    fp_t t = quad_mul_by_abs_z(comp);                      // |z| P
+    const bool t_inf = __shfl_sync(kFullMask, (int)t.is_zero(), base | 2);
+    fp_t u = quad_mul_by_abs_z(t);                         // z^2 P
+    xyzz_t U = quad_gather(u);                             // valid on the quad's first lane
+    if (role == 0 && live) {
+        if (ok && !inf) {
+            fp_t beta;
+            const uint32_t Bm[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
+                                     0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
+#pragma unroll
+            for (int k = 0; k < 12; k++) beta.v[k] = Bm[k];
+            // (beta x, y) == -(X/ZZ, Y/ZZZ)  <=>  beta x ZZ == X  and  y ZZZ == -Y
+            ok = !t_inf && !U.is_inf() && (beta * a.x * U.zz == U.x) && (a.y * U.zzz == U.y.neg());
+        }
+        if (!ok) status[i % status_mod] = 1;
+        if (out) store_affine(out + (size_t)i * 96, a);
+    }
+}
+void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st, int status_mod) {
     if (n < 1) return;
-    k_decode_g1_checked<<<div_up(n, 32), 32, 0, st>>>(in48_dev, n, (uint8_t*)affine_out_dev, status_dev);
+    k_decode_g1_checked<<<div_up(n, 8), 32, 0, st>>>(in48_dev, n, (uint8_t*)affine_out_dev, status_dev, status_mod > 0 ? status_mod : n);
     B200_LAUNCH_CHECK();
 }
 void launch_affine_to_jac(const void* affine_dev, void* jac_dev, int n, cudaStream_t st) {
@@ -599,8 +629,7 @@ void KzgSettingsDev::evaluate_blobs(const uint8_t* blobs, const uint8_t* z_bytes
 
 void KzgSettingsDev::validate_commitments(const uint8_t* commitments48, int n, int* status, cudaStream_t st) {
     if (n < 1) return;
-    k_validate_commitments<<<div_up(n, 32), 32, 0, st>>>(commitments48, n, status);
-    B200_LAUNCH_CHECK();
+    launch_decode_g1_checked(commitments48, nullptr, status, n, st);
 }
 
 }  // namespace b200

@@ -70,7 +70,9 @@ public:
     // (non-canonical field element, malformed / off-curve / out-of-subgroup point); *result = 1 iff the pairing
     // equation holds.
     void verify_batch(const uint8_t* commitments48, const uint8_t* proofs48, const uint8_t* z32, const uint8_t* y32,
-                      int z_reduce, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st);
+                      int z_reduce, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st, bool skip_decode = false);
+    // the point-decoding stage of verify_batch on its own (then call verify_batch(..., skip_decode = true) with the same n)
+    void verify_decode(const uint8_t* commitments48, const uint8_t* proofs48, int n, int* status, cudaStream_t st);
     // ---- EIP-7594 recovery and cell verification (das7594.cu; kzg/src/das.rs:101-207, 294-388) -------------------
     // recover_cells_and_kzg_proofs for one extended blob.  cells: n x 2048 wire bytes (device); cell_idx: their cell
     // indices (host, already validated: n in [64, 128], < 128, strictly ascending).  cells_out: 128 x 2048 bytes,
@@ -124,7 +126,8 @@ private:
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input
 void launch_uncompress_g1(const uint8_t* in48_dev, void* affine_out_dev, int* flags_dev, int n, cudaStream_t st);
 // uncompress + subgroup check (G1::from_bytes followed by is_inf() || is_valid()); status[i] = 1 on failure
-void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st);
+// (status index = i % status_mod, status_mod = 0 -> n; affine_out_dev may be nullptr)
+void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st, int status_mod = 0);
 // blst_p1_from_affine for n points
 void launch_affine_to_jac(const void* affine_dev, void* jac_dev, int n, cudaStream_t st);
 // Fr::from_bytes (reduce = 0: status[i] = 1 when >= r) / hash_to_bls_field (reduce = 1) -> Montgomery; and back

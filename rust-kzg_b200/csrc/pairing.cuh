@@ -265,26 +265,26 @@ static __device__ __noinline__ void w12_mul(pf_t* dst, const pf_t* a, const pf_t
     if (lane < 24 && h == 0) dst[2 * k + e] = c;
     __syncwarp();
 }
-// dst = a * (b0 + b2 w^2 + b3 w^3), sp = {b0.re, b0.im, b2.re, b2.im, b3.re, b3.im}: the Miller-loop line
+// dst = a * (b0 + b2 w^2 + b3 w^3), sp = {b0.re, b0.im, b2.re, b2.im, b3.re, b3.im}: the Miller-loop line.
+// Each output component is a signed sum of six Fp products (three Fp2 coefficients of b); lane half h takes three.
 static __device__ __noinline__ void w12_mul_sparse(pf_t* dst, const pf_t* a, const pf_t* sp) {
     const int lane = threadIdx.x & 31;
     const int L = lane < 24 ? lane : lane - 24;
     const int k = L >> 2, e = (L >> 1) & 1, h = L & 1;
     pf_t S = pf_t::zero(), T = pf_t::zero();
 #pragma unroll 1
-    for (int t = 0; t < 2; t++) {
-        // h = 0 takes b0 and b3, h = 1 takes b2 (its second round is a dummy)
-        const int slot = h ? 1 : (t ? 2 : 0);
-        const int j = h ? 2 : (t ? 3 : 0);
-        const bool live = !(h && t);
+    for (int t = 0; t < 3; t++) {
+        const int q = 3 * h + t;              // product index: slot = q / 2 (b0, b2, b3), part = q % 2
+        const int slot = q >> 1, part = q & 1;
+        const int j = slot == 0 ? 0 : slot + 1;
         int i = k - j;
         const bool wrap = i < 0;
         if (wrap) i += 6;
-        pf_t p0 = a[2 * i] * sp[2 * slot + e];
-        pf_t p1 = a[2 * i + 1] * sp[2 * slot + (e ^ 1)];
-        pf_t term = e ? p0 + p1 : p0 - p1;
-        pf_t s2 = S + term, t2 = T + term;
-        if (live) { if (wrap) T = t2; else S = s2; }
+        // e = 0: + a.re b.re - a.im b.im        e = 1: + a.re b.im + a.im b.re
+        pf_t p = a[2 * i + part] * sp[2 * slot + (e ^ part)];
+        const bool minus = (e == 0) && part;
+        pf_t s2 = minus ? S - p : S + p, t2 = minus ? T - p : T + p;
+        if (wrap) T = t2; else S = s2;
     }
     S = S + pf_shfl_xor(S, 1);
     T = T + pf_shfl_xor(T, 1);
@@ -292,6 +292,51 @@ static __device__ __noinline__ void w12_mul_sparse(pf_t* dst, const pf_t* a, con
     pf_t c = e ? S + T + To : S + T - To;
     __syncwarp();
     if (lane < 24 && h == 0) dst[2 * k + e] = c;
+    __syncwarp();
+}
+// dst = a^2 for a in the cyclotomic subgroup (after the easy part of the final exponentiation): Granger-Scott
+// (eprint 2009/565, the form zkcrypto/bls12_381/src/pairings.rs:66-113 uses) in the flat basis.  With
+// F(x, y) = (xi y^2 + x^2, 2 x y):  (A0, A1) = F(a0, a3), (B0, B1) = F(a1, a4), (C0, C1) = F(a2, a5) and
+//   a0' = 3 A0 - 2 a0   a3' = 3 A1 + 2 a3   a2' = 3 B0 - 2 a2   a5' = 3 B1 + 2 a5   a4' = 3 C0 - 2 a4   a1' = 3 xi C1 + 2 a1.
+// The nine Fp2 squarings (x^2, y^2, (x + y)^2 per pair) are 18 Fp products, one per lane; sq: 18 scratch pf_t.
+static __device__ __noinline__ void w12_cyclotomic_sqr(pf_t* dst, const pf_t* a, pf_t* sq) {
+    const int lane = threadIdx.x & 31;
+    {
+        const int L = lane < 18 ? lane : 0;
+        const int p = L / 6, which = (L >> 1) % 3, part = L & 1;
+        pf_t xr = a[2 * p], xi_ = a[2 * p + 1], yr = a[2 * (p + 3)], yi = a[2 * (p + 3) + 1];
+        pf_t re = which == 0 ? xr : which == 1 ? yr : xr + yr;
+        pf_t im = which == 0 ? xi_ : which == 1 ? yi : xi_ + yi;
+        // (re + im u)^2 = (re + im)(re - im) + 2 re im u
+        pf_t m = part ? re * im : (re + im) * (re - im);
+        if (part) m = m.dbl();
+        if (lane < 18) sq[L] = m;
+    }
+    __syncwarp();
+    {
+        const int L = lane < 12 ? lane : 0;
+        const int k = L >> 1, e = L & 1;
+        const int p = k % 3;                                   // pair (a_p, a_{p+3}) holds both k = p and k = p + 3 ... see table
+        // which F feeds coefficient k: k=0,3 <- pair 0; k=2,5 <- pair 1; k=4,1 <- pair 2
+        const int pr = (k == 0 || k == 3) ? 0 : (k == 2 || k == 5) ? 1 : 2;
+        const bool first = (k == 0 || k == 2 || k == 4);       // takes F's first component (xi y^2 + x^2), minus sign
+        const pf_t* q = sq + 6 * pr;                           // x^2 (re, im), y^2 (re, im), (x+y)^2 (re, im)
+        pf_t v;
+        if (first) {
+            pf_t xiy = e ? q[2] + q[3] : q[2] - q[3];          // component e of xi * y^2
+            v = xiy + q[e];
+        } else {
+            pf_t c1r = q[4] - q[0] - q[2], c1i = q[5] - q[1] - q[3];   // 2 x y
+            v = e ? c1i : c1r;
+            if (k == 1) v = e ? c1r + c1i : c1r - c1i;          // xi * C1
+        }
+        pf_t old2 = a[L].dbl();
+        pf_t r = v.dbl() + v;
+        r = first ? r - old2 : r + old2;
+        (void)p;
+        __syncwarp();
+        if (lane < 12) dst[L] = r;
+    }
     __syncwarp();
 }
 __device__ __forceinline__ void w12_copy(pf_t* dst, const pf_t* a) {
@@ -354,13 +399,13 @@ static __device__ __noinline__ void w12_inverse(pf_t* dst, const pf_t* f, pf_t* 
     w12_mul(t3, t3, t2);
     w12_mul(dst, t1, t3);
 }
-// dst = conj(f^|x|) = f^x for the (negative) BLS parameter; f in the cyclotomic subgroup.  tmp: 1 scratch element
+// dst = conj(f^|x|) = f^x for the (negative) BLS parameter; f in the cyclotomic subgroup.  tmp: 3 scratch elements
 static __device__ __noinline__ void w12_exp_x(pf_t* dst, const pf_t* f, pf_t* tmp) {
     const uint64_t X = 0xd201000000010000ull;
     w12_copy(tmp, f);
 #pragma unroll 1
     for (int b = 62; b >= 0; b--) {
-        w12_mul(tmp, tmp, tmp);
+        w12_cyclotomic_sqr(tmp, tmp, tmp + 12);
         if ((X >> b) & 1) w12_mul(tmp, tmp, f);
     }
     w12_conj(dst, tmp);
@@ -377,9 +422,9 @@ static __device__ __noinline__ void w12_final_exp(pf_t* f, pf_t* ws) {
     w12_frobenius(t2, t2); w12_frobenius(t2, t2);
     w12_mul(t2, t2, t1);
     // hard part
-    w12_mul(t1, t2, t2); w12_conj(t1, t1);
+    w12_cyclotomic_sqr(t1, t2, sc); w12_conj(t1, t1);
     w12_exp_x(t3, t2, sc);
-    w12_mul(t4, t3, t3);
+    w12_cyclotomic_sqr(t4, t3, sc);
     w12_mul(t5, t1, t3);
     w12_exp_x(t1, t5, sc);
     w12_exp_x(t0, t1, sc);

@@ -220,8 +220,22 @@ void KzgSettingsDev::lincomb2_and_pair(const uint8_t* pts, const uint8_t* scalar
     run_pairing(sums, lines + qa * tb, 1, sums + 192, lines + qb * tb, 0, scratch, result, st);
 }
 
+// decode + subgroup-check the 2n points into the workspace (may run early, on another stream, while z / y are still
+// being produced); one launch when the two arrays are contiguous
+void KzgSettingsDev::verify_decode(const uint8_t* commitments48, const uint8_t* proofs48, int n, int* status, cudaStream_t st) {
+    ensure_verify_ws(n);
+    uint8_t* comm_aff = (uint8_t*)vf_buf_;
+    uint8_t* proof_aff = comm_aff + (size_t)n * 96;
+    if (proofs48 == commitments48 + (size_t)n * 48) {
+        launch_decode_g1_checked(commitments48, comm_aff, status, 2 * n, st, n);
+    } else {
+        launch_decode_g1_checked(commitments48, comm_aff, status, n, st);
+        launch_decode_g1_checked(proofs48, proof_aff, status, n, st);
+    }
+}
+
 void KzgSettingsDev::verify_batch(const uint8_t* commitments48, const uint8_t* proofs48, const uint8_t* z32, const uint8_t* y32,
-                                  int z_reduce, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st) {
+                                  int z_reduce, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st, bool skip_decode) {
     if (!g2_lines_) throw CudaError(-1, "trusted setup was loaded without G2 points");
     if (n < 1) throw CudaError(-1, "verify_batch needs at least one item");
     ensure_verify_ws(n);
@@ -237,8 +251,7 @@ void KzgSettingsDev::verify_batch(const uint8_t* commitments48, const uint8_t* p
     uint8_t* partials = w;                 w += 2 * blocks * 192;
     uint8_t* sums = w;                     w += 2 * 192;
     uint8_t* scratch = (uint8_t*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
-    launch_decode_g1_checked(commitments48, comm_aff, status, n, st);
-    launch_decode_g1_checked(proofs48, proof_aff, status, n, st);
+    if (!skip_decode) verify_decode(commitments48, proofs48, n, status, st);
     launch_fr_from_bytes(z32, n, z_reduce, z, status, st);
     launch_fr_from_bytes(y32, n, 0, y, status, st);
     if (n > 1) launch_fr_from_bytes(r32, 1, 1, r, status, st);  // hash_to_bls_field never fails: status untouched

@@ -72,3 +72,14 @@ elif what in ("cells", "fk20"):
     for _ in range(reps):
         (ts.compute_cells_batch if what == "cells" else ts.compute_cell_proofs_batch)(blobs)
     torch.cuda.synchronize()
+elif what == "verify":
+    ts = B.KZGSettings.load_trusted_setup_file()
+    nb = n
+    blobs = rng.integers(0, 256, size=(nb, 4096, 32), dtype=np.uint8)
+    blobs[:, :, 0] = 0
+    blobs = blobs.reshape(nb, 131072)
+    comm = ts.blob_to_kzg_commitment_batch(blobs)
+    proofs = ts.compute_blob_kzg_proof_batch(blobs, comm)
+    for _ in range(reps):
+        assert ts.verify_blob_kzg_proof_batch(blobs, comm, proofs)
+    torch.cuda.synchronize()
