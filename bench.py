@@ -459,6 +459,34 @@ def extra_metrics(B, K, osettings, torch):
             "cpu_port_blobs_per_s": 1.0 / dt_cpu, "cpu_cores": os.cpu_count()}
     except Exception as e:  # an extra: never lose the headline line over it
         ex["compute_cells_and_kzg_proofs"] = {"error": repr(e)[:200]}
+    # verification side: pairing on the device, host byte arrays in, bool out; CPU port beside it
+    try:
+        proofs64 = h_out.numpy().copy()                      # compute_blob_kzg_proof results of the 64 blobs above
+        ok_all = ts.verify_blob_kzg_proof_batch(blobs, comm, proofs64)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ts.verify_blob_kzg_proof_batch(blobs, comm, proofs64)
+        dt = (time.perf_counter() - t0) / reps
+        badp = proofs64.copy()
+        badp[7] = proofs64[8]
+        rej = ts.verify_blob_kzg_proof_batch(blobs, comm, badp)
+        t0 = time.perf_counter()
+        ts.verify_blob_kzg_proof_batch(h_big.numpy(), h_big_comm.numpy(), h_big_proof.numpy())
+        dt_big = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            one_ok = ts.verify_blob_kzg_proof(blobs[3], comm[3], proofs64[3])
+        dt_one = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        cpu_ok = K.verify_blob_kzg_proof_batch([blobs[i].tobytes() for i in range(8)], [comm[i].tobytes() for i in range(8)],
+                                               [proofs64[i].tobytes() for i in range(8)], osettings)
+        dt_cpu = time.perf_counter() - t0
+        ex["verify_blob_kzg_proof_batch"] = {
+            "e2e_blobs_per_s": nb / dt, "ms_per_batch": dt * 1e3, "batch": nb, "accepts_valid": bool(ok_all and one_ok and cpu_ok),
+            "rejects_swapped_proof": bool(rej is False), "e2e_stream512_blobs_per_s": big / dt_big,
+            "single_verify_blob_kzg_proof_ms": dt_one * 1e3, "cpu_port_blobs_per_s": 8 / dt_cpu, "cpu_cores": 1}
+    except Exception as e:
+        ex["verify_blob_kzg_proof_batch"] = {"error": repr(e)[:200]}
     ts.free()
     # Fr NTT sweep (BASELINE config 4)
     fs = B.FFTSettings(20)

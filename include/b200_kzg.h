@@ -129,8 +129,8 @@ typedef KZGSettings CKZGSettings;
 
 /* blst/src/eip_4844.rs:180-222.  Decompresses the points on the GPU, builds the fixed-base MSM table and the
  * roots-of-unity tables, decodes the 65 G2 points and tabulates the Miller-loop lines of [1]G2, [s]G2, [s^64]G2, fills
- * the host arrays.  BADARGS on wrong counts / undecodable points.  The reference's pairing sanity check for
- * monomial-form ("old") setups (kzg/src/eip_4844.rs:1005-1020) is NOT performed. */
+ * the host arrays.  BADARGS on wrong counts / undecodable points / a monomial-form array in the Lagrange slot (the
+ * pairing check of kzg/src/eip_4844.rs:1005-1020, 1064-1068, run on the device). */
 B200_API C_KZG_RET load_trusted_setup(KZGSettings *out, const uint8_t *g1_monomial_bytes, uint64_t num_g1_monomial_bytes,
                              const uint8_t *g1_lagrange_bytes, uint64_t num_g1_lagrange_bytes,
                              const uint8_t *g2_monomial_bytes, uint64_t num_g2_monomial_bytes, uint64_t precompute);

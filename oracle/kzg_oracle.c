@@ -1025,7 +1025,7 @@ typedef struct {
 static int hexval(int c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; }
 
 /* load_trusted_setup_string + load_trusted_setup_rust (eip_4844.rs:151-228, 1022-1086).
- * The pairing sanity check (is_trusted_setup_in_lagrange_form, :1005-1020) and G2 are outside the hot path. */
+ * including the pairing sanity check (is_trusted_setup_in_lagrange_form, :1005-1020). */
 API void *ko_load_trusted_setup_text(const char *text, size_t len) {
     ko_init();
     const char *p = text, *end = text + len;
@@ -1062,6 +1062,8 @@ API void *ko_load_trusted_setup_text(const char *text, size_t len) {
         p1_from_affine(&s->g1_monomial[i], &a);
     }
     free(raw);
+    /* is_trusted_setup_in_lagrange_form (eip_4844.rs:1005-1020, 1064-1068); lagrange[1] is at bit-reversed slot 2048 */
+    if (!bad && pairings_verify(&s->g1_lagrange_brp[2048], &s->g2_monomial[0], &s->g1_lagrange_brp[0], &s->g2_monomial[1])) bad = 1;
     if (bad) { free(s->g1_lagrange_brp); free(s->g1_monomial); free(s); return NULL; }
     s->fs = (fft_settings_t *)ko_fft_settings_new(13);
     s->nthreads = 1;

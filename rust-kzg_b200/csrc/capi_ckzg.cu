@@ -155,6 +155,19 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
         ctx->d_status = ctx->stage[0].d_status;
         ctx->dev.reset(new KzgSettingsDev(g1_monomial, g1_lagrange, mb, ctx->stream));
         ctx->dev->load_g2(g2_monomial, (int)kG2, ctx->stream);  // G2::from_bytes of all 65 points (eip_4844.rs:1050-1053)
+        // is_trusted_setup_in_lagrange_form (eip_4844.rs:1005-1020, 1064-1068): a monomial-form array in the Lagrange slot
+        // satisfies e(L[1], G2) == e(L[0], [s]G2) and is rejected.  L[1] sits at bit-reversed position 2048.
+        {
+            int* d_res = dev_alloc<int>(1);
+            const uint8_t* lag = (const uint8_t*)ctx->dev->g1_lagrange_brp_jac_dev();
+            ctx->dev->pairings_verify(lag + (size_t)2048 * 144, 0, lag, 1, d_res, ctx->stream);
+            int res = 0;
+            cudaError_t e = cudaMemcpyAsync(&res, d_res, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(d_res);
+            B200_CUDA_CHECK(e);
+            if (res) throw CudaError(1, "Trusted setup is not in Lagrange form");
+        }
     } catch (const CudaError& e) {
         if (e.code != 1) fprintf(stderr, "b200kzg: load_trusted_setup failed: %s\n", e.what());
         return e.code == 1 ? C_KZG_BADARGS : C_KZG_ERROR;

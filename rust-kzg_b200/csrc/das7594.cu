@@ -267,8 +267,8 @@ void KzgSettingsDev::verify_cells(const uint8_t* commitments48, int m, const uin
     size_t bytes = (size_t)m * 96 + (size_t)n * 96 + (size_t)n * kCellFr * 32 + (size_t)n * 32 + 64 + 2 * colb + 2 * L * (96 + 32) +
                    2 * blocks * 192 + 2 * 192 + 4 * kMillerLines * kLineBytes + 1024;
     uint8_t* w = ensure_das_ws(bytes);
-    uint8_t* comm_aff = w;    w += (size_t)m * 96;
     uint8_t* proof_aff = w;   w += (size_t)n * 96;
+    uint8_t* comm_aff = w;    w += (size_t)m * 96;
     uint8_t* cells_m = w;     w += (size_t)n * kCellFr * 32;
     uint8_t* rp = w;          w += (size_t)n * 32;
     uint8_t* r = w;           w += 64;
@@ -280,8 +280,12 @@ void KzgSettingsDev::verify_cells(const uint8_t* commitments48, int m, const uin
     uint8_t* sums = w;        w += 2 * 192;
     uint8_t* scratch = (uint8_t*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
     // commitments report into status[0..m) (m <= n), proofs and cells into status[i]
-    launch_decode_g1_checked(commitments48, comm_aff, status, m, st);
-    launch_decode_g1_checked(proofs48, proof_aff, status, n, st);
+    if (commitments48 == proofs48 + (size_t)n * 48) {
+        launch_decode_g1_checked(proofs48, proof_aff, status, n + m, st, n);   // one launch; commitment j -> status[j]
+    } else {
+        launch_decode_g1_checked(commitments48, comm_aff, status, m, st);
+        launch_decode_g1_checked(proofs48, proof_aff, status, n, st);
+    }
     k_vc_cells<<<div_up((size_t)n * kCellFr, 256), 256, 0, st>>>(cells, n, cells_m, status);
     launch_fr_from_bytes(r32, 1, 1, r, status, st);
     k_vc_powers<<<div_up(n, 256), 256, 0, st>>>(r, n, rp);

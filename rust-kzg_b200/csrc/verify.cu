@@ -125,18 +125,19 @@ __global__ void __launch_bounds__(32) k_pairing_check(PairingArgs args, uint8_t*
     __shared__ __align__(16) pf_t ws[12 * 12];
     const int lane = threadIdx.x;
     bool skip[4];
-    // evaluate every line at P_i: (l2, l1 * x, l0 * y), 68 lines per pair spread over the lanes
+    // evaluate every line at P_i, 68 lines per pair spread over the lanes.  P_i = (X/ZZ, Y/ZZZ) is NOT normalised: the
+    // line is scaled by ZZ*ZZZ in Fp instead -- (l2 ZZ ZZZ, l1 X ZZZ, l0 Y ZZ) -- and factors from Fp* vanish in the final
+    // exponentiation ((p^12 - 1)/r is a multiple of p - 1), which saves a field inversion per pair.
     for (int p = 0; p < args.n; p++) {
         const uint8_t* g = args.g1_xyzz[p];
         pf_t X = load_field<pf_t>(g), Y = load_field<pf_t>(g + 48), ZZZ = load_field<pf_t>(g + 96), ZZ = load_field<pf_t>(g + 144);
         skip[p] = ZZ.is_zero();
-        pf_t inv = (ZZ * ZZZ).inverse();
-        pf_t px = X * (inv * ZZZ), py = Y * (inv * ZZ);
+        pf_t px = X * ZZZ, py = Y * ZZ, sc = ZZ * ZZZ;
         if (args.neg[p]) py = py.neg();
         for (int idx = lane; idx < kMillerLines; idx += 32) {
             const uint8_t* l = args.lines[p] + (size_t)idx * kLineBytes;
             uint8_t* o = scratch + ((size_t)p * kMillerLines + idx) * kLineBytes;
-            store_fp2(o, load_fp2(l + 192));
+            store_fp2(o, load_fp2(l + 192).scale(sc));
             store_fp2(o + 96, load_fp2(l + 96).scale(px));
             store_fp2(o + 192, load_fp2(l).scale(py));
         }

@@ -83,3 +83,17 @@ elif what == "verify":
     for _ in range(reps):
         assert ts.verify_blob_kzg_proof_batch(blobs, comm, proofs)
     torch.cuda.synchronize()
+elif what in ("verifycells", "recover"):
+    ts = B.KZGSettings.load_trusted_setup_file()
+    blob = rng.integers(0, 256, size=(4096, 32), dtype=np.uint8)
+    blob[:, 0] = 0
+    blob = blob.tobytes()
+    cells, proofs = ts.compute_cells_and_kzg_proofs(blob)
+    c0 = ts.blob_to_kzg_commitment(blob)
+    for _ in range(reps):
+        if what == "verifycells":
+            assert ts.verify_cell_kzg_proof_batch([c0] * 128, list(range(128)), cells, proofs)
+        else:
+            half = list(range(0, 128, 2))
+            ts.recover_cells_and_kzg_proofs(half, [cells[i] for i in half], want_proofs=False)
+    torch.cuda.synchronize()

@@ -10,6 +10,11 @@ $NCU -c 400 --log-file gpurun_out/launches_blob1.csv python scripts/ncu_target.p
 $NCU -c 600 --log-file gpurun_out/launches_proof64.csv python scripts/ncu_target.py proof 64 2 > /dev/null 2>&1
 $NCU -c 400 --log-file gpurun_out/launches_ntt20.csv python scripts/ncu_target.py ntt 20 3 > /dev/null 2>&1
 $NCU -c 3000 --log-file gpurun_out/launches_fk20.csv python scripts/ncu_target.py fk20 16 1 > /dev/null 2>&1
+$NCU -c 600 --log-file gpurun_out/launches_verify64.csv python scripts/ncu_target.py verify 64 2 > /dev/null 2>&1
+$NCU -c 600 --log-file gpurun_out/launches_verifycells.csv python scripts/ncu_target.py verifycells 128 2 > /dev/null 2>&1
+$NCU -c 600 --log-file gpurun_out/launches_recover.csv python scripts/ncu_target.py recover 64 2 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_pairing_check -s 1 -c 1 -f -o gpurun_out/prof_pairing \
+    python scripts/ncu_target.py verify 64 2 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_accumulate -s 1 -c 1 -f -o gpurun_out/prof_accumulate_2p20 \
     python scripts/ncu_target.py msm 20 2 > /dev/null 2>&1
 ls -la gpurun_out

@@ -33,7 +33,11 @@ def test_header_symbols_are_exported(B):
     assert len(names) >= 35
     # the reference-facing names must be exactly the ones the reference's FFI binds
     for must in ("prepare_msm", "mult_pippenger_prepared", "mult_pippenger", "load_trusted_setup", "load_trusted_setup_file",
-                 "free_trusted_setup", "blob_to_kzg_commitment", "compute_kzg_proof", "compute_blob_kzg_proof"):
+                 "free_trusted_setup", "blob_to_kzg_commitment", "compute_kzg_proof", "compute_blob_kzg_proof",
+                 "verify_kzg_proof", "verify_blob_kzg_proof", "verify_blob_kzg_proof_batch", "compute_challenge",
+                 "bytes_to_kzg_commitment", "bytes_from_bls_field", "compute_cells_and_kzg_proofs",
+                 "recover_cells_and_kzg_proofs", "verify_cell_kzg_proof_batch",
+                 "compute_verify_cell_kzg_proof_batch_challenge"):
         assert must in names
     out = subprocess.check_output(["nm", "-D", "--defined-only", B.LIB_PATH], text=True)
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}

