@@ -500,6 +500,14 @@ def extra_metrics(B, K, osettings, torch):
         ms = timed(lambda: fs.fft_fr_device(d_o.data_ptr(), d_in.data_ptr(), m, False, 1, 0))
         rec = {"ms": ms, "elements_per_s": m / (ms * 1e-3), "butterflies_per_s": (m // 2) * logn / (ms * 1e-3),
                "hbm_gbs_algorithmic": 64 * m * (2 if logn > 11 else 1) / (ms * 1e-3) / 1e9}
+        if logn == 20:
+            # integer roofline of the transform: (n/2 log n butterflies + n inter-pass twiddles) x 136 IMAD.WIDE per Fr
+            # multiplication against the measured IMAD.WIDE peak
+            try:
+                imad = B.microbench_int()["imad_per_s"]
+                rec["int_roofline_frac"] = ((m // 2) * logn + m) * 136 / (ms * 1e-3) / imad
+            except Exception:
+                pass
         if logn <= 16:
             rec["parity_ok"] = bool(np.array_equal(d_o.cpu().numpy().view(np.uint64).reshape(m, 4), ofs.fft_fr(data, False, nthreads=os.cpu_count() or 1)))
         ntt["2^%d" % logn] = rec

@@ -2,6 +2,7 @@
 #include "ntt.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "mont.cuh"
 #include "util.cuh"
@@ -43,8 +44,11 @@ __device__ __forceinline__ int slot(int i) { return i ^ ((i >> 3) & 7); }
 // R consecutive radix-2 DIT stages (t .. t+R-1) on the 2^R elements whose in-column indices differ only in bits
 // t .. t+R-1, entirely in registers: one shared-memory round trip and one barrier per R stages instead of per stage.
 // The butterfly is the reference's (blst/src/fft_fr.rs:98-103): lo' = lo + w*hi, hi' = lo - w*hi.
+// Stage twiddles w_m^k, k < m/2, come from a per-CTA copy in shared memory (filled once per CTA, shared by its G
+// columns): seven of them are consumed per 3-stage group, and fetching them through L1/L2 showed up as the largest
+// stall (long scoreboard, ncu r01) of a kernel that is otherwise bound by the multiply pipe.
 template <int R>
-__device__ __forceinline__ void butterfly_group(uint8_t* sm, const NttPass& p, int m, int t, int unit) {
+__device__ __forceinline__ void butterfly_group(uint8_t* sm, const uint8_t* tw, const NttPass& p, int m, int t, int unit) {
     constexpr int E = 1 << R;
     const int units_per_col = m >> R;
     const int g = unit / units_per_col, rem = unit - g * units_per_col;
@@ -61,7 +65,7 @@ __device__ __forceinline__ void butterfly_group(uint8_t* sm, const NttPass& p, i
             const int low = lo + (b << t);  // index mod 2^(t+s) of the pairs whose low s group-bits equal b
             fr_t w;
             const bool has_w = low != 0;
-            if (has_w) w = root_at(p, ((size_t)low << (p.log_m - 1 - (t + s))) * p.unit_m);
+            if (has_w) w = load_field<fr_t>(tw + ((size_t)low << (p.log_m - 1 - (t + s))) * 32);
 #pragma unroll
             for (int j = 0; j < E; j++) {
                 if ((j & ((1 << (s + 1)) - 1)) != b) continue;  // j has bit s clear and low s bits == b
@@ -76,10 +80,13 @@ __device__ __forceinline__ void butterfly_group(uint8_t* sm, const NttPass& p, i
     for (int j = 0; j < E; j++) store_field(sm + (size_t)slot(g * m + base + (j << t)) * 32, x[j]);
 }
 
-__global__ void __launch_bounds__(kNttThreads, 2) k_ntt_pass(NttPass p) {
+template <int RMAX, int MINB>
+__global__ void __launch_bounds__(kNttThreads, MINB) k_ntt_pass(NttPass p) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int m = 1 << p.log_m;
     const int tile = p.G * m;
+    uint8_t* tw = sm + (size_t)tile * 32;
+    for (int k = threadIdx.x; k < (m >> 1); k += blockDim.x) store_field(tw + (size_t)k * 32, root_at(p, (size_t)k * p.unit_m));
     const size_t col0 = (size_t)blockIdx.x * p.G;
     const uint8_t* in = p.in + (size_t)blockIdx.y * p.batch_stride * 32;
     uint8_t* out = p.out + (size_t)blockIdx.y * p.batch_stride * 32;
@@ -102,15 +109,22 @@ __global__ void __launch_bounds__(kNttThreads, 2) k_ntt_pass(NttPass p) {
 
     // butterflies: groups of three stages, then whatever is left (two or one)
     int t = 0;
-    for (; t + 3 <= p.log_m; t += 3) {
-        for (int u = threadIdx.x; u < (tile >> 3); u += blockDim.x) butterfly_group<3>(sm, p, m, t, u);
-        __syncthreads();
+    if (RMAX >= 3) {
+        for (; t + 3 <= p.log_m; t += 3) {
+            for (int u = threadIdx.x; u < (tile >> 3); u += blockDim.x) butterfly_group<3>(sm, tw, p, m, t, u);
+            __syncthreads();
+        }
+    } else {
+        for (; t + 2 <= p.log_m - 1 || t + 2 == p.log_m; t += 2) {
+            for (int u = threadIdx.x; u < (tile >> 2); u += blockDim.x) butterfly_group<2>(sm, tw, p, m, t, u);
+            __syncthreads();
+        }
     }
     if (p.log_m - t == 2) {
-        for (int u = threadIdx.x; u < (tile >> 2); u += blockDim.x) butterfly_group<2>(sm, p, m, t, u);
+        for (int u = threadIdx.x; u < (tile >> 2); u += blockDim.x) butterfly_group<2>(sm, tw, p, m, t, u);
         __syncthreads();
     } else if (p.log_m - t == 1) {
-        for (int u = threadIdx.x; u < (tile >> 1); u += blockDim.x) butterfly_group<1>(sm, p, m, t, u);
+        for (int u = threadIdx.x; u < (tile >> 1); u += blockDim.x) butterfly_group<1>(sm, tw, p, m, t, u);
         __syncthreads();
     }
 
@@ -186,7 +200,9 @@ FFTSettingsDev::FFTSettingsDev(int scale, cudaStream_t st) : scale_(scale) {
     k_root_powers<<<1, 32, 0, st>>>(exp_dev, pw, scale, inv_n);
     k_roots_table<<<div_up(max_width_ + 1, 128), 128, 0, st>>>(pw, (uint8_t*)roots_, (uint8_t*)brp_roots_, max_width_, scale);
     B200_LAUNCH_CHECK();
-    B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileElems * 32));
+    const int max_shm = (kTileElems + (1 << (kMaxLogM - 1))) * 32;
+    B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_shm));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_shm));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
@@ -207,10 +223,28 @@ void FFTSettingsDev::ensure_scratch(size_t elems) {
     scratch_elems_ = elems;
 }
 
+// Kernel shape.  Default: radix-4 register groups (two stages per shared-memory round trip), 80 registers, three CTAs per
+// SM -- measured on B200 (scripts/ntt_timing.py): 2^12 57 -> 24 us, 2^16 74 -> 31 us, 2^20 282 -> 254 us against the
+// radix-8 groups at 128 registers / two CTAs per SM, because the transform is bound by the multiply pipe and needs the
+// extra warps to keep it fed (ncu: FMA-heavy pipe 68 % busy, top stall math-pipe throttle).  B200_NTT_VARIANT=3 selects
+// the radix-8 form.  Tile = points per CTA: small transforms use small tiles so that the pass fills more SMs.
+static int ntt_variant() {
+    static const int v = getenv("B200_NTT_VARIANT") ? atoi(getenv("B200_NTT_VARIANT")) : 2;
+    return v;
+}
+static int tile_elems(size_t n) {
+    static const int t = getenv("B200_NTT_TILE") ? atoi(getenv("B200_NTT_TILE")) : 0;
+    if (t) return t;
+    if (ntt_variant() == 3) return kTileElems;
+    return n <= ((size_t)1 << 16) ? kTileElems / 4 : kTileElems / 2;
+}
 static void launch_pass(const NttPass& p, int batch, cudaStream_t st) {
     int m = 1 << p.log_m;
     unsigned blocks = div_up(p.ncols, (size_t)p.G);
-    k_ntt_pass<<<dim3(blocks, (unsigned)batch), kNttThreads, (size_t)p.G * m * 32, st>>>(p);
+    const int variant = ntt_variant();
+    const size_t shm = ((size_t)p.G * m + (m >> 1)) * 32;
+    if (variant == 3) k_ntt_pass<3, 2><<<dim3(blocks, (unsigned)batch), kNttThreads, shm, st>>>(p);
+    else k_ntt_pass<2, 3><<<dim3(blocks, (unsigned)batch), kNttThreads, shm, st>>>(p);
     B200_LAUNCH_CHECK();
 }
 
@@ -242,7 +276,7 @@ void FFTSettingsDev::run_passes(const void* in, void* out, size_t n, bool invers
     ensure_scratch((size_t)batch * n);
     // pass 1: for every column j1 < n1, transform the n2 points x[j1 + n1*j2]; times w_n^(i2*j1); in-place layout
     p.in = (const uint8_t*)in; p.out = (uint8_t*)scratch_;
-    p.log_m = k2; p.G = std::max(1, kTileElems >> k2); p.ncols = n1;
+    p.log_m = k2; p.G = std::max(1, tile_elems(n) >> k2); p.ncols = n1;
     p.in_cstride = 1; p.in_rstride = n1; p.out_cstride = 1; p.out_rstride = n1;
     p.in_col_fast = 1; p.out_col_fast = 1;
     p.unit_m = max_width_ >> k2;
@@ -251,7 +285,7 @@ void FFTSettingsDev::run_passes(const void* in, void* out, size_t n, bool invers
     launch_pass(p, batch, st);
     // pass 2: for every i2 < n2, transform the n1 contiguous points y[n1*i2 + j1]; X[i2 + n2*i1]
     p.in = (const uint8_t*)scratch_; p.out = (uint8_t*)out;
-    p.log_m = k1; p.G = std::max(1, kTileElems >> k1); p.ncols = n2;
+    p.log_m = k1; p.G = std::max(1, tile_elems(n) >> k1); p.ncols = n2;
     p.in_cstride = n1; p.in_rstride = 1; p.out_cstride = 1; p.out_rstride = n2;
     p.in_col_fast = 0; p.out_col_fast = 1;
     p.unit_m = max_width_ >> k1;
