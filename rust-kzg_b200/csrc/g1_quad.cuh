@@ -175,15 +175,65 @@ __device__ __forceinline__ fp_t quad_tree(fp_t a, int lanes) {
     }
     return a;
 }
-// [k] p for quad-distributed p; k canonical little-endian words, the same value on the four lanes of a quad.
-// Fixed 4-bit windows, most significant first: 16-entry table of multiples per quad in shared memory
-// (kQuadTableBytes per warp; every lane only ever touches its own component slots, so no synchronisation), then 64 x
-// (4 quad doublings + 1 quad addition).  The instruction stream is uniform across the warp's quads -- with a
-// bit-serial double-and-add every quad would pay for an addition whenever any of the eight needs one.
-static constexpr int kQuadTableBytes = 8 * 16 * 192;
+// k = k1 + k2 * z^2 with 0 <= k1 < z^2 (128 bits) and k2 < 2^128, for canonical k < r: plain long division, because
+// z^2 = 0xac45a4010001a4020000000100000000 (z = the BLS parameter) is the GLV eigenvalue up to sign -- r = z^4 - z^2 + 1, so
+// (-z^2)^2 + (-z^2) + 1 = 0 mod r, and the curve endomorphism (x, y) -> (beta x, y) acts on G1 as multiplication by -z^2
+// (the same relation the subgroup test uses, eprint 2021/1130 sec. 6).  Hence [k]P = [k1]P + [k2](beta x, -y): two
+// half-length scalars over one shared doubling chain.
+__device__ __forceinline__ void glv_split(const uint32_t (&k)[8], uint32_t (&k1)[4], uint32_t (&k2)[4]) {
+    const uint32_t Z2[4] = {0x00000000u, 0x00000001u, 0x0001a402u, 0xac45a401u};
+    uint32_t rem[5] = {0, 0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int bit = 255; bit >= 0; bit--) {
+        // rem = (rem << 1) | bit of k
+#pragma unroll
+        for (int i = 4; i > 0; i--) rem[i] = (rem[i] << 1) | (rem[i - 1] >> 31);
+        rem[0] = (rem[0] << 1) | ((k[bit >> 5] >> (bit & 31)) & 1u);
+        // rem >= Z2 ?
+        bool ge = rem[4] != 0;
+        if (!ge) {
+            ge = true;
+#pragma unroll
+            for (int i = 3; i >= 0; i--) {
+                if (rem[i] != Z2[i]) { ge = rem[i] > Z2[i]; break; }
+            }
+        }
+        if (ge) {
+            uint32_t borrow = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint64_t d = (uint64_t)rem[i] - Z2[i] - borrow;
+                rem[i] = (uint32_t)d;
+                borrow = (uint32_t)(d >> 63);
+            }
+            rem[4] -= borrow;
+            if (bit < 128) q[bit >> 5] |= 1u << (bit & 31);   // the quotient of k < r fits 128 bits
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { k1[i] = rem[i]; k2[i] = q[i]; }
+}
+// [k] p for quad-distributed p; k canonical little-endian words (< r), the same value on the four lanes of a quad.
+// GLV split (above), then fixed 4-bit windows over the 128-bit halves, most significant first: 16-entry table of
+// multiples d * P per quad in shared memory plus the X coordinates of d * (beta x, -y) (Y is negated on the fly, ZZ / ZZZ
+// are shared) -- kQuadTableBytes per warp; every lane only ever touches its own component slots, so no synchronisation --
+// then 32 x (4 quad doublings + 2 quad additions) instead of 64 x (4 + 1).  The instruction stream is uniform across the
+// warp's quads -- with a bit-serial double-and-add every quad would pay for an addition whenever any of the eight needs one.
+static constexpr int kQuadTableStride = 16 * 192 + 16 * 48;
+static constexpr int kQuadTableBytes = 8 * kQuadTableStride;
 __device__ __forceinline__ fp_t quad_mul_scalar(const fp_t& p, const uint32_t (&k)[8], uint8_t* warp_table) {
-    const int lane = threadIdx.x & 31;
-    uint8_t* tab = warp_table + (lane >> 2) * (16 * 192) + quad_store_offset();
+    const int lane = threadIdx.x & 31, role = lane & 3;
+    uint8_t* tab = warp_table + (lane >> 2) * kQuadTableStride + quad_store_offset();
+    uint8_t* tabx = warp_table + (lane >> 2) * kQuadTableStride + 16 * 192;   // beta * X_d, 48 B each
+    uint32_t k1[4], k2[4];
+    glv_split(k, k1, k2);
+    fp_t beta;
+    {
+        const uint32_t Bm[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
+                                 0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
+#pragma unroll
+        for (int i = 0; i < 12; i++) beta.v[i] = Bm[i];
+    }
     store_field(tab, fp_t::zero());
     store_field(tab + 192, p);
 #pragma unroll 1
@@ -191,13 +241,24 @@ __device__ __forceinline__ fp_t quad_mul_scalar(const fp_t& p, const uint32_t (&
         fp_t t = (d & 1) ? quad_add(load_field<fp_t>(tab + (d - 1) * 192), p) : quad_dbl(load_field<fp_t>(tab + (d >> 1) * 192));
         store_field(tab + d * 192, t);
     }
-    fp_t acc = load_field<fp_t>(tab + ((k[7] >> 28) & 15) * 192);
 #pragma unroll 1
-    for (int j = 62; j >= 0; j--) {
+    for (int d = 0; d < 16; d++) {
+        fp_t bx = load_field<fp_t>(tab + d * 192) * beta;      // only the X lane's product is kept
+        if (role == 0) store_field(tabx + d * 48, bx);
+    }
+    fp_t acc = fp_t::zero();
 #pragma unroll 1
-        for (int r = 0; r < 4; r++) acc = quad_dbl(acc);
-        uint32_t d = (k[j >> 3] >> ((j & 7) * 4)) & 15;
-        acc = quad_add(acc, load_field<fp_t>(tab + d * 192));
+    for (int j = 31; j >= 0; j--) {
+        if (j != 31) {
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) acc = quad_dbl(acc);
+        }
+        const uint32_t d1 = (k1[j >> 3] >> ((j & 7) * 4)) & 15, d2 = (k2[j >> 3] >> ((j & 7) * 4)) & 15;
+        acc = quad_add(acc, load_field<fp_t>(tab + d1 * 192));
+        fp_t e = load_field<fp_t>(tab + d2 * 192);             // d2 * (beta x, -y) = (beta X_d2, -Y_d2, ZZ_d2, ZZZ_d2)
+        if (role == 0) e = load_field<fp_t>(tabx + d2 * 48);
+        if (role == 1) e = e.neg();
+        acc = quad_add(acc, e);
     }
     return acc;
 }
