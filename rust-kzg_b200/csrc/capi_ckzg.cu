@@ -83,6 +83,19 @@ struct KzgCtx {
     uint8_t* h_verify = nullptr;
     size_t verify_cap = 0;
     static size_t verify_bytes(size_t n) { return n * (48 + 48 + 32 + 32 + sizeof(int)) + 32 + 64; }
+    // general staging for the EIP-7594 entry points: device + pinned host, grown on demand, reused across calls
+    uint8_t* d_scratch = nullptr;
+    uint8_t* h_scratch = nullptr;
+    size_t scratch_cap = 0;
+    void ensure_scratch(size_t bytes) {
+        if (bytes <= scratch_cap) return;
+        cudaFree(d_scratch);
+        if (h_scratch) cudaFreeHost(h_scratch);
+        d_scratch = nullptr; h_scratch = nullptr; scratch_cap = 0;
+        d_scratch = dev_alloc<uint8_t>(bytes);
+        B200_CUDA_CHECK(cudaMallocHost((void**)&h_scratch, bytes));
+        scratch_cap = bytes;
+    }
     void ensure_verify(size_t n) {
         if (n <= verify_cap) return;
         cudaFree(d_verify);
@@ -93,8 +106,9 @@ struct KzgCtx {
         verify_cap = n;
     }
     ~KzgCtx() {
-        cudaFree(d_cells); cudaFree(d_proofs); cudaFree(d_verify);
+        cudaFree(d_cells); cudaFree(d_proofs); cudaFree(d_verify); cudaFree(d_scratch);
         if (h_verify) cudaFreeHost(h_verify);
+        if (h_scratch) cudaFreeHost(h_scratch);
         dev.reset();
     }
 };
@@ -645,14 +659,24 @@ static void cell_challenge_hash(uint8_t out[32], const uint8_t* comm48, size_t m
     }
     c.finish(out);
 }
-struct DevScratch {  // one-call device + pinned staging
+struct DevScratch {  // device + pinned staging: borrowed from the context (caller holds ctx.mu) or owned for one call
     uint8_t* d = nullptr;
     uint8_t* h = nullptr;
+    bool owned = true;
     explicit DevScratch(size_t bytes) {
         d = dev_alloc<uint8_t>(bytes);
         if (cudaMallocHost((void**)&h, bytes ? bytes : 16) != cudaSuccess) { cudaFree(d); throw CudaError(-1, "cudaMallocHost failed"); }
     }
-    ~DevScratch() { cudaFree(d); if (h) cudaFreeHost(h); }
+    DevScratch(KzgCtx& ctx, size_t bytes) : owned(false) {
+        ctx.ensure_scratch(bytes);
+        d = ctx.d_scratch;
+        h = ctx.h_scratch;
+    }
+    ~DevScratch() {
+        if (!owned) return;
+        cudaFree(d);
+        if (h) cudaFreeHost(h);
+    }
 };
 C_KZG_RET recover_cells_and_kzg_proofs(Cell* recovered_cells, KZGProof* recovered_proofs, const uint64_t* cell_indices, const Cell* cells,
                                        uint64_t num_cells, const KZGSettings* s) {
@@ -668,7 +692,7 @@ C_KZG_RET recover_cells_and_kzg_proofs(Cell* recovered_cells, KZGProof* recovere
         }
         std::lock_guard<std::mutex> lk(ctx->mu);
         const size_t o_out = n * kBytesPerCell, o_pr = o_out + kCellsPerExtBlob * kBytesPerCell, o_st = o_pr + kCellsPerExtBlob * 48;
-        DevScratch buf(o_st + 64);
+        DevScratch buf(*ctx, o_st + 64);
         cudaStream_t st = ctx->stream;
         memcpy(buf.h, cells, n * kBytesPerCell);
         memset(buf.h + o_st, 0, sizeof(int));
@@ -712,7 +736,7 @@ C_KZG_RET verify_cell_kzg_proof_batch(bool* ok, const Bytes48* commitments_bytes
         // device layout: [cells n*2048][proofs n*48][uniq m*48][comm_idx n u32][cell_idx n u32][r 32][status n ints][result]
         const size_t o_p = n * kBytesPerCell, o_c = o_p + 48 * n, o_ci = (o_c + 48 * m + 15) & ~(size_t)15, o_ki = o_ci + 4 * n,
                      o_r = o_ki + 4 * n, o_st = o_r + 32, o_res = o_st + 4 * n;
-        DevScratch buf(o_res + 16);
+        DevScratch buf(*ctx, o_res + 16);
         memcpy(buf.h, cells, n * kBytesPerCell);
         memcpy(buf.h + o_p, proofs_bytes, 48 * n);
         memcpy(buf.h + o_c, uniq.data(), 48 * m);
@@ -750,7 +774,7 @@ C_KZG_RET compute_verify_cell_kzg_proof_batch_challenge(blst_fr* challenge_out, 
         const size_t n = num_cells, m = num_commitments;
         std::lock_guard<std::mutex> lk(ctx->mu);
         const size_t o_p = n * kBytesPerCell, o_c = o_p + 48 * n, o_r = (o_c + 48 * m + 15) & ~(size_t)15, o_fr = o_r + 32, o_st = o_fr + 32;
-        DevScratch buf(o_st + 16);
+        DevScratch buf(*ctx, o_st + 16);
         if (n) { memcpy(buf.h, cells, n * kBytesPerCell); memcpy(buf.h + o_p, proofs_bytes, 48 * n); }
         if (m) memcpy(buf.h + o_c, commitment_bytes, 48 * m);
         cell_challenge_hash(buf.h + o_r, (const uint8_t*)commitment_bytes, m, commitment_indices, cell_indices, (const uint8_t*)cells,

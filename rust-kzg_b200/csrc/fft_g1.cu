@@ -31,8 +31,11 @@ __global__ void __launch_bounds__(32) k_g1_stage(uint8_t* __restrict__ work, siz
     const size_t b = live ? q : 0;
     uint8_t* w = work + (size_t)blockIdx.y * n * 192;
     const size_t half = (size_t)1 << s;
-    const size_t lowk = b & (half - 1);
-    const size_t i = ((b >> s) << (s + 1)) | lowk;
+    // butterflies are numbered twiddle-major: all those with the same twiddle index lowk are consecutive, so the ones
+    // multiplying by w^0 = 1 (a 2^-s fraction of the stage) fill whole warps, which then skip the scalar multiplication
+    const int hi_bits = log_n - 1 - s;
+    const size_t lowk = b >> hi_bits;
+    const size_t i = ((b & (((size_t)1 << hi_bits) - 1)) << (s + 1)) | lowk;
     const int off = quad_store_offset();
     fp_t lo = load_field<fp_t>(w + i * 192 + off), t = load_field<fp_t>(w + (i + half) * 192 + off);
     if (__any_sync(kFullMask, lowk != 0)) {
