@@ -13,6 +13,7 @@
 #include "g1.cuh"
 #include "pairing.cuh"
 #include "util.cuh"
+#include "warp_inverse.cuh"
 #include "wire.cuh"
 
 #include <vector>
@@ -85,9 +86,13 @@ __global__ void __launch_bounds__(256) k_fr_shift(const uint8_t* __restrict__ a,
 }
 // out[i] = a[i] / b[i]   (batch_inverse + product, das.rs:596-602)
 __global__ void __launch_bounds__(256) k_fr_div(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ out, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;   // n is a multiple of the warp size: whole warps are live
     if (i >= n) return;
-    store_field(out + (size_t)i * 32, load_field<fr_t>(a + (size_t)i * 32) * load_field<fr_t>(b + (size_t)i * 32).inverse());
+    fr_t d = load_field<fr_t>(b + (size_t)i * 32);
+    const bool z = d.is_zero();                      // cannot happen for Z on the coset; 0 -> 0 as the scalar inverse does
+    fr_t inv = warp_inverse(z ? fr_t::one() : d);
+    if (z) inv = fr_t::zero();
+    store_field(out + (size_t)i * 32, load_field<fr_t>(a + (size_t)i * 32) * inv);
 }
 // natural-order evaluations -> bit-reversed order (reverse_bit_order of 8192 elements)
 __global__ void __launch_bounds__(256) k_fr_brp13(const uint8_t* __restrict__ a, uint8_t* __restrict__ out) {

@@ -8,6 +8,7 @@
 #include "g1.cuh"
 #include "g1_quad.cuh"
 #include "util.cuh"
+#include "warp_inverse.cuh"
 #include "wire.cuh"
 
 namespace b200 {
@@ -132,7 +133,8 @@ __global__ void k_affine_to_jac(const uint8_t* __restrict__ aff, uint8_t* __rest
 // compute_kzg_proof_rust up to the MSM (kzg/src/eip_4844.rs:437-519) with
 // evaluate_polynomial_in_evaluation_form (:954-1003) fused in.  One CTA per blob:
 //   d_i = z - w_i;  inv_i = 1/d_i by the batch-inversion product trick of fr_batch_inv (:882-914), per thread over
-//   its 16 elements with one Fermat inversion per thread (all threads invert in parallel: same latency as one);
+//   its 16 elements with one inversion per WARP (warp_inverse.cuh: prefix/suffix products by shuffle scans, every lane
+//   inverts the same total -- 32 different binary-Euclid inversions in a warp would run the union of their branches);
 //   y = (z^4096 - 1)/4096 * sum p_i w_i inv_i;   q_i = (p_i - y)/(w_i - z) = (y - p_i) inv_i.
 // The reference's second batch inversion is unnecessary: 1/(w_i - z) = -inv_i.
 // z equal to a domain point w_m (:458-462, 484-510): y = p_m, q_m = (1/z) sum_{i != m} (p_i - y) w_i inv_i.
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kQThreads) k_quotient(const uint8_t* __restric
         store_field(pref + (size_t)i * 32, acc);
         acc = acc * d;
     }
-    fr_t inv = acc.inverse();
+    fr_t inv = warp_inverse(acc);   // acc != 0: zero differences were replaced by one above
     fr_t ysum = fr_t::zero();
 #pragma unroll 1
     for (int k = kQPer - 1; k >= 0; k--) {
