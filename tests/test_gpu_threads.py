@@ -1,0 +1,88 @@
+"""Handles are Send + Sync on the Rust side (kzg/src/msm/sppark.rs:24-44) and the c-kzg settings are shared by rayon
+workers (kzg/src/eip_4844.rs:781-815): concurrent calls on one settings object / one prepared MSM must serialise
+internally and stay bit-exact; several settings objects can coexist and be freed independently."""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _blobs(rng, n):
+    b = rng.integers(0, 256, size=(n, 4096, 32), dtype=np.uint8)
+    b[:, :, 0] = 0
+    return b.reshape(n, -1)
+
+
+def test_concurrent_calls_on_one_settings_object(B):
+    ts = B.KZGSettings.load_trusted_setup_file()
+    rng = np.random.default_rng(31)
+    blobs = _blobs(rng, 6)
+    want_c = [ts.blob_to_kzg_commitment(b) for b in blobs]
+    want_p = [ts.compute_blob_kzg_proof(b, c) for b, c in zip(blobs, want_c)]
+    errors = []
+
+    def worker(k):
+        try:
+            for rep in range(3):
+                i = (k + rep) % len(blobs)
+                assert ts.blob_to_kzg_commitment(blobs[i]) == want_c[i]
+                assert ts.compute_blob_kzg_proof(blobs[i], want_c[i]) == want_p[i]
+                assert ts.verify_blob_kzg_proof(blobs[i], want_c[i], want_p[i]) is True
+                assert ts.verify_blob_kzg_proof(blobs[i], want_c[i], want_p[(i + 1) % len(blobs)]) is False
+                cells = ts.compute_cells(blobs[i])
+                assert ts.recover_cells_and_kzg_proofs(list(range(0, 128, 2)), cells[0::2], want_proofs=False)[0] == cells
+        except Exception as e:  # surfaced in the main thread
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    ts.free()
+    assert not errors, errors
+
+
+def test_two_settings_objects_and_reload(B):
+    rng = np.random.default_rng(32)
+    blob = _blobs(rng, 1)[0]
+    a = B.KZGSettings.load_trusted_setup_file()
+    b = B.KZGSettings.load_trusted_setup_file()
+    ca, cb = a.blob_to_kzg_commitment(blob), b.blob_to_kzg_commitment(blob)
+    assert ca == cb
+    a.free()
+    with pytest.raises(B.KzgError):
+        a.blob_to_kzg_commitment(blob)                 # freed settings: BADARGS, not a crash
+    assert b.verify_blob_kzg_proof(blob, cb, b.compute_blob_kzg_proof(blob, cb)) is True
+    for _ in range(3):                                 # load / free cycles release the device context
+        c = B.KZGSettings.load_trusted_setup_file()
+        assert c.blob_to_kzg_commitment(blob) == cb
+        c.free()
+    b.free()
+
+
+def test_concurrent_prepared_msm(B, K, lagrange_affine):
+    rng = np.random.default_rng(33)
+    msm = B.PreparedMsm(lagrange_affine)
+    scs = [rng.integers(0, 1 << 62, size=(4096, 4), dtype=np.uint64) for _ in range(4)]
+    want = [K.p1_compress(msm.mult(s)) for s in scs]
+    assert want[0] == K.p1_compress(K.msm_affine(lagrange_affine, scs[0], nthreads=4))
+    errors = []
+
+    def worker(k):
+        try:
+            for rep in range(4):
+                i = (k + rep) % 4
+                assert K.p1_compress(msm.mult(scs[i])) == want[i]
+        except Exception as e:
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    msm.close()
+    assert not errors, errors
