@@ -390,7 +390,7 @@ KzgSettingsDev::~KzgSettingsDev() {
     cudaFree(lagrange_jac_); cudaFree(monomial_jac_); cudaFree(domain_);
     for (Lane& ln : lanes_) { cudaFree(ln.scalars); cudaFree(ln.poly); cudaFree(ln.z); cudaFree(ln.y); cudaFree(ln.out_jac); }
     cudaFree(cells_a_); cudaFree(cells_b_);
-    cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_);
+    cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_); cudaFree(fk_direct_);
     cudaFree(g2_affine_); cudaFree(g2_jac_); cudaFree(g2_lines_); cudaFree(vf_buf_); cudaFree(das_buf_);
 }
 
@@ -468,6 +468,17 @@ void KzgSettingsDev::ensure_fk20(cudaStream_t st) {
     cfg.L = 64;
     cfg.bases_period = kFkK2;
     fk_msm_.reset(new MsmEngine(cfg, table, false, st));
+    // direct lookup table of every digit multiple (fk20_direct.cu): 3 GiB of HBM for a lincomb stage without buckets.
+    // B200_FK20_DIRECT=0 keeps the bucket engine (A/B, or when HBM is short); the table needs the engine's 8-bit rows.
+    if (cfg.c == 8 && env_int_local("B200_FK20_DIRECT", 1)) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, fk_direct_table_bytes()) == cudaSuccess) {
+            fk_direct_ = p;
+            launch_fk_direct_build(fk_msm_->table(), fk_direct_, st);
+        } else {
+            cudaGetLastError();   // not enough memory: the bucket engine serves the lincombs
+        }
+    }
     fk_a_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kCellSize * kFkK2 * 32);
     fk_b_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kCellSize * kFkK2 * 32);
     fk_pts_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kFkK2 * 144);
@@ -504,7 +515,8 @@ void KzgSettingsDev::fk20_from_mono(const void* mono, size_t stride, int n, uint
     k_fk_transpose<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)fk_b_, (uint8_t*)fk_a_, tt, (const uint8_t*)fs_->inv_pow2_dev(7));
     B200_LAUNCH_CHECK();
     // g1_lincomb_batch: 128 lincombs of 64 fixed points per blob (kzg/src/das.rs:676-680)
-    fk_msm_->run(fk_a_, kCellSize, n * kFkK2, false, fk_pts_, st);
+    if (fk_direct_) launch_fk_direct_lincomb(fk_a_, fk_direct_, fk_pts_, n * kFkK2, st);
+    else fk_msm_->run(fk_a_, kCellSize, n * kFkK2, false, fk_pts_, st);
     // h = inverse fft_g1, upper half := identity, forward fft_g1 (:682-695)
     fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, true, n, st, /*apply_scale=*/false);
     B200_CUDA_CHECK(cudaMemset2DAsync((uint8_t*)fk_pts_ + (size_t)kFkK * 144, (size_t)kFkK2 * 144, 0, (size_t)kFkK * 144, n, st));

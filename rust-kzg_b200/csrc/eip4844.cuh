@@ -94,6 +94,7 @@ private:
     std::unique_ptr<MsmEngine> fk_msm_;
     int fk_batch_ = 0;
     void *fk_a_ = nullptr, *fk_b_ = nullptr, *fk_pts_ = nullptr;
+    void* fk_direct_ = nullptr;  // every digit multiple of the 8192 column points (fk20_direct.cu), or nullptr
     int max_batch_;
     int launches_ = 0;
     std::unique_ptr<FFTSettingsDev> fs_;
@@ -123,6 +124,10 @@ private:
     uint8_t* ensure_das_ws(size_t bytes);
 };
 
+// FK20 lincombs by direct table lookup (fk20_direct.cu): rows = the engine's [32][8192] fixed-base rows for c = 8
+size_t fk_direct_table_bytes();
+void launch_fk_direct_build(const void* rows, void* table, cudaStream_t st);
+void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_jac, int nvec, cudaStream_t st);
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input
 void launch_uncompress_g1(const uint8_t* in48_dev, void* affine_out_dev, int* flags_dev, int n, cudaStream_t st);
 // uncompress + subgroup check (G1::from_bytes followed by is_inf() || is_valid()); status[i] = 1 on failure

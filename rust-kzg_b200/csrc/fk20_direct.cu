@@ -1,0 +1,104 @@
+// fk20_direct.cu -- the 128 lincombs of 64 fixed points per blob in compute_fk20_proofs (g1_lincomb_batch over
+// x_ext_fft_columns, kzg/src/das.rs:676-680; the reference precomputes BGMW tables for them, kzg/src/msm/bgmw.rs:306-380)
+// as DIRECT table lookups instead of a bucket pass.
+//
+// With only 64 points per lincomb and 8192 lincombs per 64-blob batch the bucket method spends as much time sorting and
+// reducing 8192 tiny bucket sets (one CTA each, ~45 % of the MSM stage, profiles/r01_verify.md) as adding points.  HBM is
+// large, so every multiple is tabulated: for column point P (8192 of them), window j < 32 and digit d = 1..128 the table
+// holds d * 2^(8j) * P in affine form -- 8192 * 32 * 128 * 96 B = 3 GiB.  A lincomb is then the plain sum of 64 * 32
+// looked-up points: one warp per lincomb, lane j owns window j (Booth digits d_j = byte_j + bit_{8j-1} - 256 bit_{8j+7}
+// need no carry chain), 64 mixed additions per lane with the next entry's gather in flight, one warp tree at the end.
+// No sort, no buckets, no per-lincomb reduction kernels.
+#include "eip4844.cuh"
+#include "g1.cuh"
+#include "g1_quad.cuh"
+#include "util.cuh"
+#include "warp_inverse.cuh"
+
+namespace b200 {
+
+static constexpr int kDPts = 8192, kDW = 32, kDDigits = 128, kDCell = 64, kDChunk = 16;
+
+size_t fk_direct_table_bytes() { return (size_t)kDPts * kDW * kDDigits * 96; }
+
+// rows: the fixed-base rows of the MSM engine, row j = 2^(8j) * P_pt (affine), row-major [32][8192].
+// One thread per (pt, j): the 128 multiples by repeated mixed addition, converted to affine sixteen at a time with one
+// field inversion per warp (Montgomery's trick inside the thread, warp_inverse across the lanes).
+__global__ void __launch_bounds__(128) k_fk_direct_build(const uint8_t* __restrict__ rows, uint8_t* __restrict__ table) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // grid covers exactly 8192 * 32 threads
+    const size_t pt = t / kDW, j = t % kDW;
+    cc::affine_t base = cc::load_affine(rows + (j * kDPts + pt) * 96);
+    uint8_t* out = table + ((pt * kDW + j) * kDDigits) * 96;
+    cc::xyzz_t acc = cc::affine_to_xyzz(base);
+    for (int c0 = 0; c0 < kDDigits; c0 += kDChunk) {
+        cc::xyzz_t pts[kDChunk];
+        cc::fp_t pre[kDChunk];
+        cc::fp_t run = cc::fp_t::one();
+        for (int e = 0; e < kDChunk; e++) {
+            pts[e] = acc;
+            pre[e] = run;
+            run = run * (acc.is_inf() ? cc::fp_t::one() : acc.zzz);
+            cc::xyzz_add_affine(acc, base);
+        }
+        cc::fp_t inv = warp_inverse(run);
+        for (int e = kDChunk - 1; e >= 0; e--) {
+            cc::affine_t a{cc::fp_t::zero(), cc::fp_t::zero()};
+            if (!pts[e].is_inf()) {
+                cc::fp_t izzz = inv * pre[e];
+                inv = inv * pts[e].zzz;
+                cc::fp_t s = pts[e].zz * izzz;           // 1/ZZ = (ZZ / ZZZ)^2 because ZZ^3 = ZZZ^2
+                a.x = pts[e].x * s.sqr();
+                a.y = pts[e].y * izzz;
+            }
+            cc::store_affine(out + (size_t)(c0 + e) * 96, a);
+        }
+    }
+}
+void launch_fk_direct_build(const void* rows, void* table, cudaStream_t st) {
+    k_fk_direct_build<<<kDPts * kDW / 128, 128, 0, st>>>((const uint8_t*)rows, (uint8_t*)table);
+    B200_LAUNCH_CHECK();
+}
+
+__device__ __forceinline__ const uint8_t* fk_entry(const uint8_t* table, size_t row, int i, int lane, int d) {
+    int mag = d < 0 ? -d : d;
+    return table + ((((row * kDCell + i) * kDW + lane) * kDDigits) + (mag ? mag - 1 : 0)) * 96;
+}
+// one warp per lincomb v (= blob * 128 + row): out[v] = sum_i scalars[v][i] * column[row][i]
+__global__ void __launch_bounds__(128, 3) k_fk_direct_lincomb(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
+                                                              uint8_t* __restrict__ out_jac, int nvec) {
+    const int lane = threadIdx.x & 31;
+    const size_t v = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (v >= (size_t)nvec) return;                       // whole warps leave together
+    const size_t row = v % 128;
+    const uint32_t* sc = reinterpret_cast<const uint32_t*>(scalars + v * kDCell * 32);
+    // Booth digit of window `lane` of scalar i: byte + (bit below) - 256 * (top bit of the byte)
+    auto digit = [&](int i) -> int {
+        uint32_t w = sc[i * 8 + (lane >> 2)];
+        uint32_t byte = (w >> ((lane & 3) * 8)) & 0xffu;
+        uint32_t below = lane == 0 ? 0u : ((lane & 3) ? (w >> ((lane & 3) * 8 - 1)) & 1u : sc[i * 8 + (lane >> 2) - 1] >> 31);
+        return (int)byte + (int)below - (int)((byte >> 7) << 8);
+    };
+    xyzz_t acc = xyzz_t::inf();
+    int d = digit(0);
+    affine_t p = load_affine(fk_entry(table, row, 0, lane, d));
+    for (int i = 0; i < kDCell; i++) {
+        affine_t cur = p;
+        const int cd = d;
+        if (i + 1 < kDCell) {
+            d = digit(i + 1);
+            p = load_affine(fk_entry(table, row, i + 1, lane, d));
+        }
+        if (cd != 0) {
+            cur.y = cur.y.cneg(cd < 0);
+            xyzz_add_affine(acc, cur);
+        }
+    }
+    xyzz_t total = warp_sum_xyzz(acc);
+    if (lane == 0) store_jac(out_jac + v * 144, xyzz_to_jac(total));
+}
+void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_jac, int nvec, cudaStream_t st) {
+    k_fk_direct_lincomb<<<div_up(nvec, 4), 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)out_jac, nvec);
+    B200_LAUNCH_CHECK();
+}
+
+}  // namespace b200
