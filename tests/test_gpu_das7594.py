@@ -88,3 +88,29 @@ def test_cells_round_trip_random_blob(B, K, ts, oracle_settings):
     got = ts.recover_cells_and_kzg_proofs(sub, cs, want_proofs=False)[0]
     want = K.recover_cells_and_kzg_proofs(sub, cs, oracle_settings, want_proofs=False)[0]
     assert got == want
+
+
+def test_verify_cells_many_blobs_shuffled(B, K, ts, oracle_settings):
+    """384 cells of three blobs in random order (three unique commitments, repeated cells): accepted; a cell moved to the
+    wrong commitment is rejected; the oracle agrees on a 24-cell sample"""
+    rng = np.random.default_rng(22)
+    blobs = rng.integers(0, 256, size=(3, 4096, 32), dtype=np.uint8)
+    blobs[:, :, 0] = 0
+    blobs = [b.tobytes() for b in blobs.reshape(3, -1)]
+    comms = [ts.blob_to_kzg_commitment(b) for b in blobs]
+    per_blob = [ts.compute_cells_and_kzg_proofs(b) for b in blobs]
+    items = [(k, i) for k in range(3) for i in range(128)] + [(1, 5), (1, 5), (2, 127)]
+    order = rng.permutation(len(items))
+    items = [items[o] for o in order]
+    c = [comms[k] for k, i in items]
+    idx = [i for k, i in items]
+    cells = [per_blob[k][0][i] for k, i in items]
+    proofs = [per_blob[k][1][i] for k, i in items]
+    assert ts.verify_cell_kzg_proof_batch(c, idx, cells, proofs) is True
+    wrong = list(c)
+    wrong[17] = comms[(items[17][0] + 1) % 3]
+    assert ts.verify_cell_kzg_proof_batch(wrong, idx, cells, proofs) is False
+    sub = slice(10, 34)
+    assert K.verify_cell_kzg_proof_batch(c[sub], idx[sub], cells[sub], proofs[sub], oracle_settings) is True
+    assert K.verify_cell_kzg_proof_batch(wrong[sub], idx[sub], cells[sub], proofs[sub], oracle_settings) is False
+    assert ts.verify_cell_kzg_proof_batch(wrong[sub], idx[sub], cells[sub], proofs[sub]) is False
