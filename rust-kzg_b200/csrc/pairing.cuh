@@ -9,14 +9,15 @@
 //    load time and kept as 68 line-coefficient triples per point (19.1 KiB); a check only evaluates the lines at P_i.
 //  * a single pairing is a serial chain of ~500 Fp12 multiplications, each 54+ Fp multiplications: one thread would
 //    need ~15 ms.  Fp12 is therefore held in shared memory in the flat basis Fp2[w]/(w^6 - xi), xi = 1 + u,
-//    (w^2 = v, so tower coefficient c_i.c_j is w^(i + 2j)) and ONE WARP computes a product cooperatively: lane
-//    (k, e, h) accumulates half (h) of the six Fp2 products that land on component e (re / im) of output coefficient k,
-//    wrapped terms (i + j >= 6) separately so that xi is applied once; two shuffle exchanges finish the coefficient.
-//    Critical path: 6 Fp multiplications instead of 54 (4 for the sparse line multiplication).
+//    (w^2 = v, so tower coefficient c_i.c_j is w^(i + 2j)) and ONE CTA OF FOUR WARPS computes a product cooperatively:
+//    thread (k, e, q) forms one of the six terms that land on component e (re / im) of output coefficient k, so the four
+//    multiply pipes of the SM work on the same product; twelve threads sum the terms, wrapped ones (i + j >= 6)
+//    separately so that xi is applied once.  Critical path: 2 Fp multiplications instead of 54 (1 for the sparse line
+//    multiplication, 1 for a cyclotomic squaring).
 //  * inversion, Frobenius and the final exponentiation (the addition chain of zkcrypto/bls12_381/src/pairings.rs:
 //    138-171, with plain squarings) are built from the same warp primitives.
 //
-// All w12_* functions must be called by all 32 lanes of a warp with warp-uniform arguments.
+// All w12_* functions must be called by all kPairThreads threads of the CTA with uniform arguments.
 #pragma once
 #include "g1.cuh"
 #include "mont.cuh"
@@ -234,215 +235,243 @@ static __device__ __noinline__ void g2_prepare_lines(const fp2_t& qx, const fp2_
     for (int k = 0; k < 3; k++) store_fp2(out + (size_t)idx * kLineBytes + k * 96, l[k]);
 }
 
-// ---- Fp12 on one warp ------------------------------------------------------------------------------------------------
+// ---- Fp12 on one CTA of four warps -----------------------------------------------------------------------------------
 // An element is 12 pf_t in shared (or global) memory: c[2k + e] = component e (0 = re, 1 = im) of the coefficient of w^k.
+// Every w12_* function is called by ALL kPairThreads threads of the CTA with uniform arguments and ends with a barrier.
+// A product is split over 72 threads -- thread (k, e, q) forms the q-th of the six terms of component e of output
+// coefficient k, two Fp multiplications for a full product, one for the sparse line -- one per SM sub-partition's worth
+// of warps, so the four multiply pipes of the SM work on one Fp12 product at the same time; twelve threads then sum the
+// terms (wrapped ones, i + j >= 6, separately, so that xi = 1 + u is applied once).
+static constexpr int kPairThreads = 128;
 static constexpr int kW12Bytes = 12 * 48;
+static constexpr int kW12Terms = 72;   // scratch pf_t for the terms of one product
 
-// dst = a * b.  dst may alias a and/or b.
-static __device__ __noinline__ void w12_mul(pf_t* dst, const pf_t* a, const pf_t* b) {
-    const int lane = threadIdx.x & 31;
-    const int L = lane < 24 ? lane : lane - 24;
-    const int k = L >> 2, e = (L >> 1) & 1, h = L & 1;
-    pf_t S = pf_t::zero(), T = pf_t::zero();
+// dst[k, e] = S + xi-part of T, with S / T the sums of the unwrapped / wrapped terms; wrapmask[k] bit q = term q wraps.
+// Thread (k, e) sums its own six terms; the other component's wrapped sum comes from the partner lane by shuffle.
+__device__ __forceinline__ void w12_reduce_terms(pf_t* dst, const pf_t* prod, const uint32_t* wrapmask) {
+    const int t = threadIdx.x;
+    if (t < 12) {
+        const int k = t >> 1, e = t & 1;
+        const uint32_t wm = wrapmask[k];
+        const pf_t* own = prod + t * 6;
+        pf_t S = pf_t::zero(), T = pf_t::zero();
 #pragma unroll 1
-    for (int t = 0; t < 3; t++) {
-        const int i = 3 * h + t;
+        for (int q = 0; q < 6; q++) {
+            pf_t v = own[q];
+            if ((wm >> q) & 1) T = T + v; else S = S + v;     // wm is the same for both lanes of a coefficient
+        }
+        pf_t To;
+#pragma unroll
+        for (int i = 0; i < 12; i++) To.v[i] = __shfl_xor_sync(0xfffu, T.v[i], 1);
+        // xi T = (T.re - T.im) + (T.re + T.im) u
+        pf_t ST = S + T;
+        dst[t] = e ? ST + To : ST - To;
+    }
+    __syncthreads();
+}
+// dst = a * b.  dst may alias a and/or b.  prod: kW12Terms scratch elements.
+static __device__ __noinline__ void w12_mul(pf_t* dst, const pf_t* a, const pf_t* b, pf_t* prod) {
+    const int t = threadIdx.x;
+    if (t < kW12Terms) {
+        const int ke = t / 6, i = t - ke * 6, k = ke >> 1, e = ke & 1;
         int j = k - i;
-        const bool wrap = j < 0;
-        if (wrap) j += 6;
+        if (j < 0) j += 6;
         // e = 0: a.re b.re - a.im b.im        e = 1: a.re b.im + a.im b.re
         pf_t p0 = a[2 * i] * b[2 * j + e];
         pf_t p1 = a[2 * i + 1] * b[2 * j + (e ^ 1)];
-        pf_t term = e ? p0 + p1 : p0 - p1;
-        pf_t s2 = S + term, t2 = T + term;
-        if (wrap) T = t2; else S = s2;
+        prod[t] = e ? p0 + p1 : p0 - p1;
     }
-    S = S + pf_shfl_xor(S, 1);
-    T = T + pf_shfl_xor(T, 1);
-    pf_t To = pf_shfl_xor(T, 2);
-    pf_t c = e ? S + T + To : S + T - To;  // xi T = (T.re - T.im) + (T.re + T.im) u
-    __syncwarp();
-    if (lane < 24 && h == 0) dst[2 * k + e] = c;
-    __syncwarp();
+    __syncthreads();
+    const uint32_t wrap[6] = {0x3eu, 0x3cu, 0x38u, 0x30u, 0x20u, 0x00u};   // term i wraps iff i > k
+    w12_reduce_terms(dst, prod, wrap);
 }
 // dst = a * (b0 + b2 w^2 + b3 w^3), sp = {b0.re, b0.im, b2.re, b2.im, b3.re, b3.im}: the Miller-loop line.
-// Each output component is a signed sum of six Fp products (three Fp2 coefficients of b); lane half h takes three.
-static __device__ __noinline__ void w12_mul_sparse(pf_t* dst, const pf_t* a, const pf_t* sp) {
-    const int lane = threadIdx.x & 31;
-    const int L = lane < 24 ? lane : lane - 24;
-    const int k = L >> 2, e = (L >> 1) & 1, h = L & 1;
-    pf_t S = pf_t::zero(), T = pf_t::zero();
-#pragma unroll 1
-    for (int t = 0; t < 3; t++) {
-        const int q = 3 * h + t;              // product index: slot = q / 2 (b0, b2, b3), part = q % 2
+// Term q of (k, e): slot = q / 2 (b0, b2, b3), part = q % 2 -- a single signed Fp product.
+static __device__ __noinline__ void w12_mul_sparse(pf_t* dst, const pf_t* a, const pf_t* sp, pf_t* prod) {
+    const int t = threadIdx.x;
+    if (t < kW12Terms) {
+        const int ke = t / 6, q = t - ke * 6, k = ke >> 1, e = ke & 1;
         const int slot = q >> 1, part = q & 1;
         const int j = slot == 0 ? 0 : slot + 1;
         int i = k - j;
-        const bool wrap = i < 0;
-        if (wrap) i += 6;
+        if (i < 0) i += 6;
         // e = 0: + a.re b.re - a.im b.im        e = 1: + a.re b.im + a.im b.re
         pf_t p = a[2 * i + part] * sp[2 * slot + (e ^ part)];
-        const bool minus = (e == 0) && part;
-        pf_t s2 = minus ? S - p : S + p, t2 = minus ? T - p : T + p;
-        if (wrap) T = t2; else S = s2;
+        prod[t] = (e == 0 && part) ? p.neg() : p;
     }
-    S = S + pf_shfl_xor(S, 1);
-    T = T + pf_shfl_xor(T, 1);
-    pf_t To = pf_shfl_xor(T, 2);
-    pf_t c = e ? S + T + To : S + T - To;
-    __syncwarp();
-    if (lane < 24 && h == 0) dst[2 * k + e] = c;
-    __syncwarp();
+    __syncthreads();
+    // slots 1 (j = 2) and 2 (j = 3) wrap when k < j: bits (2,3) for k < 2, bits (4,5) for k < 3
+    const uint32_t wrap[6] = {0x3cu, 0x3cu, 0x30u, 0x00u, 0x00u, 0x00u};
+    w12_reduce_terms(dst, prod, wrap);
 }
 // dst = a^2 for a in the cyclotomic subgroup (after the easy part of the final exponentiation): Granger-Scott
 // (eprint 2009/565, the form zkcrypto/bls12_381/src/pairings.rs:66-113 uses) in the flat basis.  With
 // F(x, y) = (xi y^2 + x^2, 2 x y):  (A0, A1) = F(a0, a3), (B0, B1) = F(a1, a4), (C0, C1) = F(a2, a5) and
 //   a0' = 3 A0 - 2 a0   a3' = 3 A1 + 2 a3   a2' = 3 B0 - 2 a2   a5' = 3 B1 + 2 a5   a4' = 3 C0 - 2 a4   a1' = 3 xi C1 + 2 a1.
-// The nine Fp2 squarings (x^2, y^2, (x + y)^2 per pair) are 18 Fp products, one per lane; sq: 18 scratch pf_t.
+// The nine Fp2 squarings (x^2, y^2, (x + y)^2 per pair) are 18 Fp products, one per thread; sq: 18 scratch pf_t.
 static __device__ __noinline__ void w12_cyclotomic_sqr(pf_t* dst, const pf_t* a, pf_t* sq) {
-    const int lane = threadIdx.x & 31;
-    {
-        const int L = lane < 18 ? lane : 0;
-        const int p = L / 6, which = (L >> 1) % 3, part = L & 1;
+    const int t = threadIdx.x;
+    // Both phases are written branch-free over the participating lanes (operands chosen by selects, absent terms are
+    // zero): a lone warp pays ~100 cycles of carry-chain latency per field addition, so divergent paths that each add a
+    // few elements cost more than the multiplication in the middle.
+    if (t < 18) {
+        const int p = t / 6, which = (t >> 1) % 3, part = t & 1;
+        const pf_t zero = pf_t::zero();
         pf_t xr = a[2 * p], xi_ = a[2 * p + 1], yr = a[2 * (p + 3)], yi = a[2 * (p + 3) + 1];
-        pf_t re = which == 0 ? xr : which == 1 ? yr : xr + yr;
-        pf_t im = which == 0 ? xi_ : which == 1 ? yi : xi_ + yi;
-        // (re + im u)^2 = (re + im)(re - im) + 2 re im u
-        pf_t m = part ? re * im : (re + im) * (re - im);
-        if (part) m = m.dbl();
-        if (lane < 18) sq[L] = m;
+        pf_t re = (which == 1 ? zero : xr) + (which == 0 ? zero : yr);
+        pf_t im = (which == 1 ? zero : xi_) + (which == 0 ? zero : yi);
+        // (re + im u)^2 = (re + im)(re - im) + (re + re) im u
+        pf_t opa = re + (part ? re : im);
+        pf_t opb = part ? im : re - im;
+        sq[t] = opa * opb;
     }
-    __syncwarp();
-    {
-        const int L = lane < 12 ? lane : 0;
-        const int k = L >> 1, e = L & 1;
-        const int p = k % 3;                                   // pair (a_p, a_{p+3}) holds both k = p and k = p + 3 ... see table
-        // which F feeds coefficient k: k=0,3 <- pair 0; k=2,5 <- pair 1; k=4,1 <- pair 2
+    __syncthreads();
+    pf_t r;
+    if (t < 12) {
+        const int k = t >> 1, e = t & 1;
+        // which F feeds coefficient k: k = 0, 3 <- pair 0; k = 2, 5 <- pair 1; k = 4, 1 <- pair 2
         const int pr = (k == 0 || k == 3) ? 0 : (k == 2 || k == 5) ? 1 : 2;
-        const bool first = (k == 0 || k == 2 || k == 4);       // takes F's first component (xi y^2 + x^2), minus sign
-        const pf_t* q = sq + 6 * pr;                           // x^2 (re, im), y^2 (re, im), (x+y)^2 (re, im)
-        pf_t v;
-        if (first) {
-            pf_t xiy = e ? q[2] + q[3] : q[2] - q[3];          // component e of xi * y^2
-            v = xiy + q[e];
-        } else {
-            pf_t c1r = q[4] - q[0] - q[2], c1i = q[5] - q[1] - q[3];   // 2 x y
-            v = e ? c1i : c1r;
-            if (k == 1) v = e ? c1r + c1i : c1r - c1i;          // xi * C1
-        }
-        pf_t old2 = a[L].dbl();
-        pf_t r = v.dbl() + v;
-        r = first ? r - old2 : r + old2;
-        (void)p;
-        __syncwarp();
-        if (lane < 12) dst[L] = r;
+        const bool first = (k == 0 || k == 2 || k == 4);       // F's first component (xi y^2 + x^2), combined with "- 2 a_k"
+        const pf_t* q = sq + 6 * pr;                           // x^2 (re, im), y^2 (re, im), (x + y)^2 (re, im)
+        // v = P1 + P2 + P3 - N1 - N2 - N3 with
+        //   first,  e = 0:  y2.re + x2.re - y2.im             first,  e = 1:  y2.re + y2.im + x2.im
+        //   second, k != 1: s.e - x2.e - y2.e                 (2 x y, s = (x + y)^2)
+        //   k = 1,  e = 0:  (s.re - x2.re - y2.re) - (s.im - x2.im - y2.im)      k = 1, e = 1: the sum of the two
+        const pf_t zero = pf_t::zero();
+        const bool k1 = k == 1;
+        pf_t P1 = first ? q[2] : q[4 + (k1 ? 0 : e)];
+        pf_t P2 = first ? q[e] : (k1 ? (e ? q[5] : q[1]) : zero);
+        pf_t P3 = first ? (e ? q[3] : zero) : (k1 && !e ? q[3] : zero);
+        pf_t N1 = first ? (e ? zero : q[3]) : q[k1 ? 0 : e];
+        pf_t N2 = first ? zero : q[2 + (k1 ? 0 : e)];
+        pf_t N3 = first ? zero : (k1 ? (e ? q[1] : q[5]) : zero);
+        pf_t N4 = (k1 && e) ? q[3] : zero;
+        pf_t v = ((P1 + P2) + P3) - ((N1 + N2) + (N3 + N4));
+        // 3 v -/+ 2 a_k = v + 2 (v -/+ a_k)
+        pf_t ak = a[t];
+        pf_t w = v + (first ? ak.neg() : ak);
+        r = v + w.dbl();
     }
-    __syncwarp();
+    __syncthreads();                                           // dst may alias a
+    if (t < 12) dst[t] = r;
+    __syncthreads();
 }
 __device__ __forceinline__ void w12_copy(pf_t* dst, const pf_t* a) {
-    const int lane = threadIdx.x & 31;
-    pf_t v = a[lane < 12 ? lane : 0];
-    __syncwarp();
-    if (lane < 12) dst[lane] = v;
-    __syncwarp();
+    const int t = threadIdx.x;
+    pf_t v;
+    if (t < 12) v = a[t];
+    __syncthreads();
+    if (t < 12) dst[t] = v;
+    __syncthreads();
 }
 __device__ __forceinline__ void w12_set_one(pf_t* dst) {
-    const int lane = threadIdx.x & 31;
-    if (lane < 12) dst[lane] = lane == 0 ? pf_t::one() : pf_t::zero();
-    __syncwarp();
+    const int t = threadIdx.x;
+    if (t < 12) dst[t] = t == 0 ? pf_t::one() : pf_t::zero();
+    __syncthreads();
 }
 __device__ __forceinline__ bool w12_is_one(const pf_t* a) {
-    const int lane = threadIdx.x & 31;
+    const int t = threadIdx.x;
     bool ok = true;
-    if (lane < 12) ok = a[lane] == (lane == 0 ? pf_t::one() : pf_t::zero());
-    return __all_sync(0xffffffffu, ok);
+    if (t < 12) ok = a[t] == (t == 0 ? pf_t::one() : pf_t::zero());
+    return __syncthreads_and(ok) != 0;
 }
 // conjugation over Fp6 = the p^6 Frobenius: odd powers of w change sign
 __device__ __forceinline__ void w12_conj(pf_t* dst, const pf_t* a) {
-    const int lane = threadIdx.x & 31;
-    pf_t v = a[lane < 12 ? lane : 0];
-    if ((lane >> 1) & 1) v = v.neg();
-    __syncwarp();
-    if (lane < 12) dst[lane] = v;
-    __syncwarp();
+    const int t = threadIdx.x;
+    pf_t v;
+    if (t < 12) {
+        v = a[t];
+        if ((t >> 1) & 1) v = v.neg();
+    }
+    __syncthreads();
+    if (t < 12) dst[t] = v;
+    __syncthreads();
 }
 // dst = a^p: coefficient k becomes conj(a_k) * FROB_GAMMA[k]
 static __device__ __noinline__ void w12_frobenius(pf_t* dst, const pf_t* a) {
-    const int lane = threadIdx.x & 31;
-    const int L = lane < 12 ? lane : 0;
-    const int k = L >> 1, e = L & 1;
-    pf_t gre = pf_const(FROB_GAMMA[k][0]), gim = pf_const(FROB_GAMMA[k][1]);
-    // (are - aim u)(gre + gim u) = are gre + aim gim + (are gim - aim gre) u
-    pf_t p0 = a[2 * k] * (e ? gim : gre);
-    pf_t p1 = a[2 * k + 1] * (e ? gre : gim);
-    pf_t c = e ? p0 - p1 : p0 + p1;
-    __syncwarp();
-    if (lane < 12) dst[L] = c;
-    __syncwarp();
+    const int t = threadIdx.x;
+    pf_t c;
+    if (t < 12) {
+        const int k = t >> 1, e = t & 1;
+        pf_t gre = pf_const(FROB_GAMMA[k][0]), gim = pf_const(FROB_GAMMA[k][1]);
+        // (are - aim u)(gre + gim u) = are gre + aim gim + (are gim - aim gre) u
+        pf_t p0 = a[2 * k] * (e ? gim : gre);
+        pf_t p1 = a[2 * k + 1] * (e ? gre : gim);
+        c = e ? p0 - p1 : p0 + p1;
+    }
+    __syncthreads();
+    if (t < 12) dst[t] = c;
+    __syncthreads();
 }
-// dst = 1 / f.  tmp: 4 scratch elements.  With g = f conj(f) in Fp6 and N = g g^(p^2) g^(p^4) in Fp2:
+// dst = 1 / f.  tmp: 4 scratch elements + kW12Terms.  With g = f conj(f) in Fp6 and N = g g^(p^2) g^(p^4) in Fp2:
 // 1/f = conj(f) g^(p^2) g^(p^4) / N, one Fp inversion.
 static __device__ __noinline__ void w12_inverse(pf_t* dst, const pf_t* f, pf_t* tmp) {
-    pf_t *t1 = tmp, *t2 = tmp + 12, *t3 = tmp + 24, *t4 = tmp + 36;
+    pf_t *t1 = tmp, *t2 = tmp + 12, *t3 = tmp + 24, *t4 = tmp + 36, *prod = tmp + 48;
     w12_conj(t1, f);
-    w12_mul(t2, f, t1);                       // g
-    w12_frobenius(t3, t2); w12_frobenius(t3, t3);   // g^(p^2)
-    w12_frobenius(t4, t3); w12_frobenius(t4, t4);   // g^(p^4)
-    w12_mul(t3, t3, t4);                      // h
-    w12_mul(t2, t2, t3);                      // N: only the w^0 coefficient is non-zero
-    fp2_t n{t2[0], t2[1]};
-    fp2_t ni = fp2_inverse(n);
-    __syncwarp();
-    const int lane = threadIdx.x & 31;
-    if (lane < 12) t2[lane] = lane == 0 ? ni.re : lane == 1 ? ni.im : pf_t::zero();
-    __syncwarp();
-    w12_mul(t3, t3, t2);
-    w12_mul(dst, t1, t3);
+    w12_mul(t2, f, t1, prod);                        // g
+    w12_frobenius(t3, t2); w12_frobenius(t3, t3);    // g^(p^2)
+    w12_frobenius(t4, t3); w12_frobenius(t4, t4);    // g^(p^4)
+    w12_mul(t3, t3, t4, prod);                       // h
+    w12_mul(t2, t2, t3, prod);                       // N: only the w^0 coefficient is non-zero
+    if (threadIdx.x == 0) {
+        fp2_t ni = fp2_inverse(fp2_t{t2[0], t2[1]});
+        t2[0] = ni.re;
+        t2[1] = ni.im;
+    } else if (threadIdx.x < 12 && threadIdx.x >= 2) {
+        t2[threadIdx.x] = pf_t::zero();
+    }
+    __syncthreads();
+    w12_mul(t3, t3, t2, prod);
+    w12_mul(dst, t1, t3, prod);
 }
-// dst = conj(f^|x|) = f^x for the (negative) BLS parameter; f in the cyclotomic subgroup.  tmp: 3 scratch elements
+// dst = conj(f^|x|) = f^x for the (negative) BLS parameter; f in the cyclotomic subgroup.
+// tmp: 1 scratch element + kW12Terms
 static __device__ __noinline__ void w12_exp_x(pf_t* dst, const pf_t* f, pf_t* tmp) {
     const uint64_t X = 0xd201000000010000ull;
+    pf_t* prod = tmp + 12;
     w12_copy(tmp, f);
 #pragma unroll 1
     for (int b = 62; b >= 0; b--) {
-        w12_cyclotomic_sqr(tmp, tmp, tmp + 12);
-        if ((X >> b) & 1) w12_mul(tmp, tmp, f);
+        w12_cyclotomic_sqr(tmp, tmp, prod);
+        if ((X >> b) & 1) w12_mul(tmp, tmp, f, prod);
     }
     w12_conj(dst, tmp);
 }
 // f <- f^((p^12 - 1)/r) (up to the fixed cofactor of the chain in zkcrypto/bls12_381/src/pairings.rs:138-171).
-// ws: 12 scratch elements.
+// ws: 7 + 4 scratch elements + kW12Terms.
+static constexpr int kW12FinalExpScratch = 11 * 12 + kW12Terms;
 static __device__ __noinline__ void w12_final_exp(pf_t* f, pf_t* ws) {
     pf_t *t0 = ws, *t1 = ws + 12, *t2 = ws + 24, *t3 = ws + 36, *t4 = ws + 48, *t5 = ws + 60, *t6 = ws + 72, *sc = ws + 84;
+    pf_t* prod = ws + 132;
     // easy part: f^((p^6 - 1)(p^2 + 1))
     w12_conj(t0, f);
     w12_inverse(t1, f, sc);
-    w12_mul(t2, t0, t1);
+    w12_mul(t2, t0, t1, prod);
     w12_copy(t1, t2);
     w12_frobenius(t2, t2); w12_frobenius(t2, t2);
-    w12_mul(t2, t2, t1);
+    w12_mul(t2, t2, t1, prod);
     // hard part
-    w12_cyclotomic_sqr(t1, t2, sc); w12_conj(t1, t1);
+    w12_cyclotomic_sqr(t1, t2, prod); w12_conj(t1, t1);
     w12_exp_x(t3, t2, sc);
-    w12_cyclotomic_sqr(t4, t3, sc);
-    w12_mul(t5, t1, t3);
+    w12_cyclotomic_sqr(t4, t3, prod);
+    w12_mul(t5, t1, t3, prod);
     w12_exp_x(t1, t5, sc);
     w12_exp_x(t0, t1, sc);
     w12_exp_x(t6, t0, sc);
-    w12_mul(t6, t6, t4);
+    w12_mul(t6, t6, t4, prod);
     w12_exp_x(t4, t6, sc);
     w12_conj(t5, t5);
-    w12_mul(t5, t5, t2); w12_mul(t4, t4, t5);
+    w12_mul(t5, t5, t2, prod); w12_mul(t4, t4, t5, prod);
     w12_conj(t5, t2);
-    w12_mul(t1, t1, t2);
+    w12_mul(t1, t1, t2, prod);
     w12_frobenius(t1, t1); w12_frobenius(t1, t1); w12_frobenius(t1, t1);
-    w12_mul(t6, t6, t5);
+    w12_mul(t6, t6, t5, prod);
     w12_frobenius(t6, t6);
-    w12_mul(t3, t3, t0);
+    w12_mul(t3, t3, t0, prod);
     w12_frobenius(t3, t3); w12_frobenius(t3, t3);
-    w12_mul(t3, t3, t1);
-    w12_mul(t3, t3, t6);
-    w12_mul(f, t3, t4);
+    w12_mul(t3, t3, t1, prod);
+    w12_mul(t3, t3, t6, prod);
+    w12_mul(f, t3, t4, prod);
 }
 
 }  // namespace b200

@@ -120,29 +120,29 @@ struct PairingArgs {
     int n;
 };
 static constexpr int kPairScratchBytes = 4 * kMillerLines * kLineBytes;  // scaled lines of up to four pairs
-__global__ void __launch_bounds__(32) k_pairing_check(PairingArgs args, uint8_t* __restrict__ scratch, int* __restrict__ result) {
+__global__ void __launch_bounds__(kPairThreads) k_pairing_check(PairingArgs args, uint8_t* __restrict__ scratch, int* __restrict__ result) {
     __shared__ __align__(16) pf_t f[12];
-    __shared__ __align__(16) pf_t ws[12 * 12];
-    const int lane = threadIdx.x;
+    __shared__ __align__(16) pf_t ws[kW12FinalExpScratch];
+    const int tid = threadIdx.x;
     bool skip[4];
-    // evaluate every line at P_i, 68 lines per pair spread over the lanes.  P_i = (X/ZZ, Y/ZZZ) is NOT normalised: the
+    // evaluate every line at P_i, one (pair, line) per thread.  P_i = (X/ZZ, Y/ZZZ) is NOT normalised: the
     // line is scaled by ZZ*ZZZ in Fp instead -- (l2 ZZ ZZZ, l1 X ZZZ, l0 Y ZZ) -- and factors from Fp* vanish in the final
     // exponentiation ((p^12 - 1)/r is a multiple of p - 1), which saves a field inversion per pair.
-    for (int p = 0; p < args.n; p++) {
+    for (int p = 0; p < args.n; p++) skip[p] = load_field<pf_t>(args.g1_xyzz[p] + 144).is_zero();
+    for (int w = tid; w < args.n * kMillerLines; w += kPairThreads) {
+        const int p = w / kMillerLines, idx = w - p * kMillerLines;
         const uint8_t* g = args.g1_xyzz[p];
         pf_t X = load_field<pf_t>(g), Y = load_field<pf_t>(g + 48), ZZZ = load_field<pf_t>(g + 96), ZZ = load_field<pf_t>(g + 144);
-        skip[p] = ZZ.is_zero();
         pf_t px = X * ZZZ, py = Y * ZZ, sc = ZZ * ZZZ;
         if (args.neg[p]) py = py.neg();
-        for (int idx = lane; idx < kMillerLines; idx += 32) {
-            const uint8_t* l = args.lines[p] + (size_t)idx * kLineBytes;
-            uint8_t* o = scratch + ((size_t)p * kMillerLines + idx) * kLineBytes;
-            store_fp2(o, load_fp2(l + 192).scale(sc));
-            store_fp2(o + 96, load_fp2(l + 96).scale(px));
-            store_fp2(o + 192, load_fp2(l).scale(py));
-        }
+        const uint8_t* l = args.lines[p] + (size_t)idx * kLineBytes;
+        uint8_t* o = scratch + ((size_t)p * kMillerLines + idx) * kLineBytes;
+        store_fp2(o, load_fp2(l + 192).scale(sc));
+        store_fp2(o + 96, load_fp2(l + 96).scale(px));
+        store_fp2(o + 192, load_fp2(l).scale(py));
     }
-    __syncwarp();
+    __syncthreads();
+    pf_t* prod = ws + 132;
     w12_set_one(f);
     int idx = 0;
 #pragma unroll 1
@@ -151,13 +151,13 @@ __global__ void __launch_bounds__(32) k_pairing_check(PairingArgs args, uint8_t*
 #pragma unroll 1
         for (int s = 0; s < steps; s++, idx++)
             for (int p = 0; p < args.n; p++)
-                if (!skip[p]) w12_mul_sparse(f, f, reinterpret_cast<const pf_t*>(scratch + ((size_t)p * kMillerLines + idx) * kLineBytes));
-        if (b >= 0) w12_mul(f, f, f);
+                if (!skip[p]) w12_mul_sparse(f, f, reinterpret_cast<const pf_t*>(scratch + ((size_t)p * kMillerLines + idx) * kLineBytes), prod);
+        if (b >= 0) w12_mul(f, f, f, prod);
     }
     w12_conj(f, f);
     w12_final_exp(f, ws);
     bool one = w12_is_one(f);
-    if (lane == 0) *result = one ? 1 : 0;
+    if (tid == 0) *result = one ? 1 : 0;
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------
@@ -205,7 +205,7 @@ static void run_pairing(const uint8_t* p0, const uint8_t* l0, int neg0, const ui
     a.n = 2;
     a.g1_xyzz[0] = p0; a.lines[0] = l0; a.neg[0] = neg0;
     a.g1_xyzz[1] = p1; a.lines[1] = l1; a.neg[1] = neg1;
-    k_pairing_check<<<1, 32, 0, st>>>(a, scratch, result);
+    k_pairing_check<<<1, kPairThreads, 0, st>>>(a, scratch, result);
     B200_LAUNCH_CHECK();
 }
 
