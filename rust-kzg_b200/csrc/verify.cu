@@ -46,35 +46,66 @@ __global__ void __launch_bounds__(32) k_g2_prepare(const uint8_t* __restrict__ a
 
 // ---- terms of the two linear combinations -------------------------------------------------------------------------
 // Segment 0 (A) and segment 1 (B), each padded to L = 2n + 1 terms: points affine (96 B), scalars canonical (32 B).
-// One thread: the powers of r are a serial chain (compute_powers, kzg/src/eip_4844.rs:316-326) and n is small.
-__global__ void k_verify_terms(const uint8_t* __restrict__ comm_aff, const uint8_t* __restrict__ proof_aff, const uint8_t* __restrict__ z_mont,
-                               const uint8_t* __restrict__ y_mont, const uint8_t* __restrict__ r_mont, int n, uint8_t* __restrict__ pts,
-                               uint8_t* __restrict__ scalars) {
-    if (blockIdx.x || threadIdx.x) return;
+// One thread per item: r^i by square-and-multiply on i (compute_powers, kzg/src/eip_4844.rs:316-326, without the serial
+// chain); the G1 term's scalar -sum r^i y_i is reduced by one CTA afterwards.
+__device__ __forceinline__ fr_t fr_pow_u32(fr_t base, uint32_t e) {
+    fr_t acc = fr_t::one();
+    while (e) {
+        if (e & 1) acc = acc * base;
+        base = base.sqr();
+        e >>= 1;
+    }
+    return acc;
+}
+__global__ void __launch_bounds__(128) k_verify_terms(const uint8_t* __restrict__ comm_aff, const uint8_t* __restrict__ proof_aff,
+                                                      const uint8_t* __restrict__ z_mont, const uint8_t* __restrict__ y_mont,
+                                                      const uint8_t* __restrict__ r_mont, int n, uint8_t* __restrict__ pts,
+                                                      uint8_t* __restrict__ scalars, uint8_t* __restrict__ ry) {
     const size_t L = 2 * (size_t)n + 1;
-    fr_t r = n > 1 ? load_field<fr_t>(r_mont) : fr_t::one();
-    fr_t rp = fr_t::one(), ysum = fr_t::zero();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L) return;
     affine_t inf{fp_t::zero(), fp_t::zero()};
-    for (int i = 0; i < n; i++) {
-        affine_t c = load_affine(comm_aff + (size_t)i * 96), p = load_affine(proof_aff + (size_t)i * 96);
-        fr_t z = load_field<fr_t>(z_mont + (size_t)i * 32), y = load_field<fr_t>(y_mont + (size_t)i * 32);
+    if (i < (size_t)n) {
+        fr_t r = n > 1 ? load_field<fr_t>(r_mont) : fr_t::one();
+        fr_t rp = fr_pow_u32(r, (uint32_t)i);
+        affine_t c = load_affine(comm_aff + i * 96), p = load_affine(proof_aff + i * 96);
+        fr_t z = load_field<fr_t>(z_mont + i * 32), y = load_field<fr_t>(y_mont + i * 32);
         fr_t rpc = rp.from_mont();
-        store_affine(pts + (size_t)i * 96, p);
-        store_field(scalars + (size_t)i * 32, rpc);
+        store_affine(pts + i * 96, p);
+        store_field(scalars + i * 32, rpc);
         store_affine(pts + (L + i) * 96, c);
         store_field(scalars + (L + i) * 32, rpc);
         store_affine(pts + (L + n + i) * 96, p);
         store_field(scalars + (L + n + i) * 32, (rp * z).from_mont());
-        ysum = ysum + rp * y;
-        rp = rp * r;
-    }
-    for (size_t i = n; i < L; i++) {
-        store_affine(pts + i * 96, inf);
+        store_field(ry + i * 32, rp * y);
+    } else {
+        store_affine(pts + i * 96, inf);                      // padding of segment 0
         store_field(scalars + i * 32, fr_t::zero());
     }
-    affine_t g{fp_cast<fp_t>(pf_const(G1_GEN_AFFINE[0])), fp_cast<fp_t>(pf_const(G1_GEN_AFFINE[1]))};
-    store_affine(pts + (L + 2 * (size_t)n) * 96, g);
-    store_field(scalars + (L + 2 * (size_t)n) * 32, ysum.neg().from_mont());
+}
+// scalar of the generator term: -(sum of ry[0..n)), one CTA
+__global__ void __launch_bounds__(256) k_verify_gen_term(const uint8_t* __restrict__ ry, int n, uint8_t* __restrict__ pts,
+                                                         uint8_t* __restrict__ scalars) {
+    __shared__ __align__(16) uint8_t sh[8 * 32];
+    fr_t acc = fr_t::zero();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc = acc + load_field<fr_t>(ry + (size_t)i * 32);
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        fr_t o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) o.v[k] = __shfl_down_sync(0xffffffffu, acc.v[k], d);
+        acc = acc + o;
+    }
+    if ((threadIdx.x & 31) == 0) store_field(sh + (threadIdx.x >> 5) * 32, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fr_t total = load_field<fr_t>(sh);
+        for (int w = 1; w < 8; w++) total = total + load_field<fr_t>(sh + w * 32);
+        const size_t L = 2 * (size_t)n + 1;
+        affine_t g{fp_cast<fp_t>(pf_const(G1_GEN_AFFINE[0])), fp_cast<fp_t>(pf_const(G1_GEN_AFFINE[1]))};
+        store_affine(pts + (L + 2 * (size_t)n) * 96, g);
+        store_field(scalars + (L + 2 * (size_t)n) * 32, total.neg().from_mont());
+    }
 }
 // One lane quad per term: partial[seg][block] = sum of the block's eight [k_i] P_i, in XYZZ (192 B)
 __global__ void __launch_bounds__(32) k_lincomb_quads(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalars, int L,
@@ -188,13 +219,13 @@ void KzgSettingsDev::load_g2(const uint8_t* g2_monomial, int count, cudaStream_t
 }
 
 // workspace layout for n items (L = 2n + 1):
-//   [comm_aff n*96][proof_aff n*96][z n*32][y n*32][r 32][pts 2L*96][scalars 2L*32][partials 2*ceil(L/8)*192][sums 2*192]
+//   [comm_aff n*96][proof_aff n*96][z n*32][y n*32][r 32][ry n*32][pts 2L*96][scalars 2L*32][partials 2*ceil(L/8)*192][sums 2*192]
 //   [pair scratch]
 void KzgSettingsDev::ensure_verify_ws(size_t n) {
     if (n <= vf_cap_ && vf_buf_) return;
     cudaFree(vf_buf_);
     size_t L = 2 * n + 1, blocks = (L + 7) / 8;
-    size_t bytes = n * (96 + 96 + 32 + 32) + 64 + 2 * L * (96 + 32) + 2 * blocks * 192 + 2 * 192 + kPairScratchBytes + 256;
+    size_t bytes = n * (96 + 96 + 32 + 32 + 32) + 64 + 2 * L * (96 + 32) + 2 * blocks * 192 + 2 * 192 + kPairScratchBytes + 256;
     vf_buf_ = dev_alloc<uint8_t>(bytes);
     vf_cap_ = n;
 }
@@ -247,6 +278,7 @@ void KzgSettingsDev::verify_batch(const uint8_t* commitments48, const uint8_t* p
     uint8_t* z = w;                        w += (size_t)n * 32;
     uint8_t* y = w;                        w += (size_t)n * 32;
     uint8_t* r = w;                        w += 64;
+    uint8_t* ry = w;                       w += (size_t)n * 32;
     uint8_t* pts = w;                      w += 2 * L * 96;
     uint8_t* scalars = w;                  w += 2 * L * 32;
     uint8_t* partials = w;                 w += 2 * blocks * 192;
@@ -256,7 +288,8 @@ void KzgSettingsDev::verify_batch(const uint8_t* commitments48, const uint8_t* p
     launch_fr_from_bytes(z32, n, z_reduce, z, status, st);
     launch_fr_from_bytes(y32, n, 0, y, status, st);
     if (n > 1) launch_fr_from_bytes(r32, 1, 1, r, status, st);  // hash_to_bls_field never fails: status untouched
-    k_verify_terms<<<1, 32, 0, st>>>(comm_aff, proof_aff, z, y, r, n, pts, scalars);
+    k_verify_terms<<<div_up(L, 128), 128, 0, st>>>(comm_aff, proof_aff, z, y, r, n, pts, scalars, ry);
+    k_verify_gen_term<<<1, 256, 0, st>>>(ry, n, pts, scalars);
     B200_LAUNCH_CHECK();
     lincomb2_and_pair(pts, scalars, L, partials, sums, scratch, 1, 0, result, st);
     launches_ = 9 + (n > 1);
