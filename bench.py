@@ -515,6 +515,33 @@ def extra_metrics(B, K, osettings, torch):
             rec["parity_ok"] = bool(np.array_equal(d_o.cpu().numpy().view(np.uint64).reshape(m, 4), ofs.fft_fr(data, False, nthreads=os.cpu_count() or 1)))
         ntt["2^%d" % logn] = rec
     ex["fft_fr"] = ntt
+    # DAS extension sweep (BASELINE config 4): n/2 even-index evaluations -> n/2 odd-index ones (data_availability_sampling.rs:78-100)
+    das = {}
+    for logn in (12, 16, 20):
+        h = 1 << (logn - 1)
+        evens = rand_fr(rng, h)
+        d_in = torch.from_numpy(evens.view(np.int64)).cuda()
+        d_o = torch.zeros_like(d_in)
+        ms = timed(lambda: fs.das_fft_extension_device(d_o.data_ptr(), d_in.data_ptr(), h, 1, 0))
+        rec = {"ms": ms, "evens": h, "elements_per_s": h / (ms * 1e-3)}
+        if logn <= 16:
+            rec["parity_ok"] = bool(np.array_equal(d_o.cpu().numpy().view(np.uint64).reshape(h, 4), ofs.das_fft_extension(evens)))
+        das["2^%d" % logn] = rec
+    ex["das_fft_extension"] = das
+    # fft_g1 at the reference's own bench size, scale 15 (18.84 s on one core, 4.96 s on 16); input = the 4096
+    # monomial setup points tiled; parity against the oracle at 2^7
+    try:
+        g1m = osettings.g1_monomial
+        pts = np.ascontiguousarray(np.tile(g1m, (8, 1)))
+        d_pts = torch.from_numpy(pts.view(np.int64)).cuda()
+        d_res = torch.zeros_like(d_pts)
+        ms = timed(lambda: fs.fft_g1_device(d_res.data_ptr(), d_pts.data_ptr(), 1 << 15, False, 1, 0), reps=3, warm=1)
+        small = fs.fft_g1(g1m[:128], False)
+        want = ofs.fft_g1(g1m[:128], False)
+        ok = all(K.p1_compress(small[i]) == K.p1_compress(want[i]) for i in range(128))
+        ex["fft_g1"] = {"2^15": {"ms": ms, "points_per_s": (1 << 15) / (ms * 1e-3)}, "parity_ok_2^7": bool(ok)}
+    except Exception as e:
+        ex["fft_g1"] = {"error": repr(e)[:200]}
     fs.close()
     return ex
 

@@ -12,7 +12,7 @@ import rust_kzg_b200 as B
 rng = np.random.default_rng(3)
 fs = B.FFTSettings(20)
 out = {}
-for logn in (12, 13, 14, 16, 18, 20):
+for logn in (9, 10, 11, 12, 13, 14, 16, 18, 20):
     m = 1 << logn
     a = rng.integers(0, 1 << 62, size=(m, 4), dtype=np.uint64)
     d_in = torch.from_numpy(a.view(np.int64)).cuda()
