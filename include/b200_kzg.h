@@ -160,6 +160,8 @@ B200_API C_KZG_RET verify_blob_kzg_proof_batch(bool *ok, const Blob *blobs, cons
 /* extension: verify_kzg_proof_batch (kzg/src/eip_4844.rs:380-435) over caller-supplied (C, z, y, proof) tuples */
 B200_API C_KZG_RET b200_verify_kzg_proof_batch(bool *ok, const Bytes48 *commitments, const Bytes32 *zs, const Bytes32 *ys,
                                                const Bytes48 *proofs, size_t n, const KZGSettings *s);
+/* test hook: out = sum scalars[i] * points[i] through the lane-quad GLV scalar multiplication (verifiers, fft_g1) */
+B200_API RustError b200_selftest_lincomb_quads(blst_p1 *out, const blst_p1_affine *points, const blst_fr *scalars, size_t n);
 /* test hook: e(a1, Q[qa]) == e(b1, Q[qb]) with Q = {[1]G2, [s]G2, [s^64]G2} (pairings_verify, blst/src/kzg_proofs.rs:74-100) */
 B200_API C_KZG_RET b200_selftest_pairings_verify(bool *ok, const blst_p1 *a1, int qa, const blst_p1 *b1, int qb, const KZGSettings *s);
 

@@ -848,6 +848,26 @@ void bytes_from_bls_field(Bytes32* out, const blst_fr* inp) {
     });
 }
 
+/* test hook: out = sum scalars[i] * points[i] through the lane-quad GLV scalar multiplication (host arrays) */
+RustError b200_selftest_lincomb_quads(blst_p1* out, const blst_p1_affine* points, const blst_fr* scalars, size_t n) {
+    return guarded([&] {
+        require_device();
+        if (!out || !points || !scalars || n == 0) throw CudaError(-1, "bad arguments");
+        uint8_t* d = dev_alloc<uint8_t>(n * (96 + 32) + 144);
+        cudaError_t e = cudaMemcpy(d, points, n * 96, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d + n * 96, scalars, n * 32, cudaMemcpyHostToDevice);
+        try {
+            B200_CUDA_CHECK(e);
+            selftest_lincomb_quads(d, d + n * 96, (int)n, d + n * 128, nullptr);
+            B200_CUDA_CHECK(cudaMemcpy(out, d + n * 128, 144, cudaMemcpyDeviceToHost));
+        } catch (...) {
+            cudaFree(d);
+            throw;
+        }
+        cudaFree(d);
+    });
+}
+
 /* test hook for the pairing alone: e(a1, Q[qa]) == e(b1, Q[qb]), Q = {[1]G2, [s]G2, [s^64]G2}; host Jacobian points */
 C_KZG_RET b200_selftest_pairings_verify(bool* ok, const blst_p1* a1, int qa, const blst_p1* b1, int qb, const KZGSettings* s) {
     return ckzg_guard([&]() -> C_KZG_RET {

@@ -128,6 +128,8 @@ private:
 size_t fk_direct_table_bytes();
 void launch_fk_direct_build(const void* rows, void* table, cudaStream_t st);
 void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_jac, int nvec, cudaStream_t st);
+// test hook (verify.cu): sum k_i P_i through the quad / GLV scalar multiplication used by the verifiers and fft_g1
+void selftest_lincomb_quads(const void* points_affine_dev, const void* scalars_mont_dev, int n, void* out_jac_dev, cudaStream_t st);
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input
 void launch_uncompress_g1(const uint8_t* in48_dev, void* affine_out_dev, int* flags_dev, int n, cudaStream_t st);
 // uncompress + subgroup check (G1::from_bytes followed by is_inf() || is_valid()); status[i] = 1 on failure

@@ -191,6 +191,29 @@ __global__ void __launch_bounds__(kPairThreads) k_pairing_check(PairingArgs args
     if (tid == 0) *result = one ? 1 : 0;
 }
 
+// test hook: out (Jacobian, device) = sum k_i P_i through the quad scalar multiplication path (affine points, Montgomery scalars)
+__global__ void k_mont_to_canon(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_field(out + (size_t)i * 32, load_field<fr_t>(in + (size_t)i * 32).from_mont());
+}
+__global__ void __launch_bounds__(32) k_xyzz_to_jac1(const uint8_t* __restrict__ in, uint8_t* __restrict__ out) {
+    if (threadIdx.x == 0) cc::store_jac(out, cc::xyzz_to_jac(cc::load_xyzz(in)));
+}
+void selftest_lincomb_quads(const void* points_affine_dev, const void* scalars_mont_dev, int n, void* out_jac_dev, cudaStream_t st) {
+    const int blocks = (n + 7) / 8;
+    uint8_t* canon = dev_alloc<uint8_t>((size_t)n * 32);
+    uint8_t* partials = dev_alloc<uint8_t>((size_t)blocks * 192 + 192);
+    k_mont_to_canon<<<div_up(n, 128), 128, 0, st>>>((const uint8_t*)scalars_mont_dev, canon, n);
+    k_lincomb_quads<<<dim3((unsigned)blocks, 1), 32, 0, st>>>((const uint8_t*)points_affine_dev, canon, n, partials);
+    k_quad_sum<<<1, 32, 0, st>>>(partials, blocks, partials + (size_t)blocks * 192);
+    k_xyzz_to_jac1<<<1, 32, 0, st>>>(partials + (size_t)blocks * 192, (uint8_t*)out_jac_dev);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(canon);
+    cudaFree(partials);
+    B200_CUDA_CHECK(e);
+    B200_LAUNCH_CHECK();
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------
 void KzgSettingsDev::load_g2(const uint8_t* g2_monomial, int count, cudaStream_t st) {
     if (count < 65) throw CudaError(1, "Invalid number of g2 points in trusted setup");

@@ -9,7 +9,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["KZGSettings", "KzgError", "BYTES_PER_BLOB", "load_trusted_setup_file", "default_trusted_setup_path",
-           "compute_challenge", "bytes_to_kzg_commitment", "bytes_from_bls_field"]
+           "compute_challenge", "bytes_to_kzg_commitment", "bytes_from_bls_field", "selftest_lincomb_quads"]
 
 BYTES_PER_BLOB = 131072
 C_KZG_OK, C_KZG_BADARGS, C_KZG_ERROR, C_KZG_MALLOC = 0, 1, 2, 3
@@ -94,6 +94,18 @@ def _buf(b, size=None, what="argument"):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def selftest_lincomb_quads(points_affine, scalars_mont):
+    """test hook: sum k_i P_i through the lane-quad GLV scalar multiplication; (n,12) u64 affine, (n,4) u64 Montgomery"""
+    pts = np.ascontiguousarray(points_affine, dtype=np.uint64).reshape(-1, 12)
+    sc = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros(18, np.uint64)
+    L = _L()
+    f = L.b200_selftest_lincomb_quads
+    f.restype, f.argtypes = _lib.RustError, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    _lib.check(f(_p(out), _p(pts), _p(sc), pts.shape[0]))
+    return out
 
 
 # ---- helper exports of blst/src/eip_4844.rs:498-530 (no settings argument)

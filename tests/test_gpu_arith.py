@@ -131,3 +131,25 @@ def test_compress_kat(B, K):
     comp = np.zeros((1000, 48), np.uint8)
     _lib.check(B.lib().b200_selftest_p1_compress(_p(comp), _p(pts), 1000))
     assert comp.tobytes() == dat
+
+
+def test_quad_glv_scalar_multiplication_edges(B, K, lagrange_affine):
+    """the lane-quad scalar multiplication splits k = k1 + k2 z^2 (GLV): scalars at and around the split boundaries, the ends
+    of the range, points at infinity and repeated points, against the oracle's naive MSM"""
+    from conftest import R_MOD, rand_ints
+    z2 = 0xd201000000010000 ** 2
+    edge = [0, 1, 2, z2 - 1, z2, z2 + 1, 2 * z2, 7 * z2 - 3, (1 << 128) - 1, 1 << 128, (1 << 128) + 1, (z2 - 1) * z2, z2 * z2 - z2,
+            R_MOD - 1, R_MOD - 2, R_MOD - z2, R_MOD - z2 - 1, R_MOD - z2 + 1, (R_MOD - 1) // 2, 0xF, 0xF0, 0xFFFFFFFF << 124]
+    rng = np.random.default_rng(41)
+    for n, ints in ((len(edge), edge), (1, [R_MOD - 1]), (9, rand_ints(rng, 9, R_MOD)), (64, rand_ints(rng, 64, R_MOD)),
+                    (203, rand_ints(rng, 203, R_MOD))):
+        pts = lagrange_affine[:n].copy()
+        if n > 8:
+            pts[3] = 0                      # infinity
+            pts[5] = pts[4]                 # P twice: the tree sum meets P + P
+            ints = list(ints)
+            ints[5] = ints[4]
+        sc = K.fr_from_ints([v % R_MOD for v in ints])
+        got = B.selftest_lincomb_quads(pts, sc)
+        want = K.msm_affine(pts, sc, nthreads=2)
+        assert K.p1_compress(got) == K.p1_compress(want), n
