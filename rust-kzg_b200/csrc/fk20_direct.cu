@@ -10,6 +10,8 @@
 // need no carry chain), 64 mixed additions per lane with the next entry's gather in flight, one warp tree at the end.
 // No sort, no buckets, no per-lincomb reduction kernels.
 #include "eip4844.cuh"
+
+#include <cstdlib>
 #include "g1.cuh"
 #include "g1_quad.cuh"
 #include "util.cuh"
@@ -64,10 +66,28 @@ __device__ __forceinline__ const uint8_t* fk_entry(const uint8_t* table, size_t 
     return table + ((((row * kDCell + i) * kDW + lane) * kDDigits) + (mag ? mag - 1 : 0)) * 96;
 }
 // one warp per lincomb v (= blob * 128 + row): out[v] = sum_i scalars[v][i] * column[row][i]
-__global__ void __launch_bounds__(128, 3) k_fk_direct_lincomb(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
-                                                              uint8_t* __restrict__ out_jac, int nvec) {
+// AR selects the arithmetic instantiation: b200:: (multiplier inlined) or b200::cl:: (multiplier behind a call, a loop body
+// that fits the instruction cache -- ncu showed "no instruction" as the second largest stall of the inlined form here).
+struct ArInline {
+    typedef b200::fp_t fp;
+    typedef b200::affine_t affine;
+    typedef b200::xyzz_t xyzz;
+    static __device__ __forceinline__ affine load(const void* p) { return b200::load_affine(p); }
+    static __device__ __forceinline__ void add(xyzz& acc, const affine& p) { b200::xyzz_add_affine(acc, p); }
+};
+struct ArCall {
+    typedef b200::cl::fp_t fp;
+    typedef b200::cl::affine_t affine;
+    typedef b200::cl::xyzz_t xyzz;
+    static __device__ __forceinline__ affine load(const void* p) { return b200::cl::load_affine(p); }
+    static __device__ __forceinline__ void add(xyzz& acc, const affine& p) { b200::cl::xyzz_add_affine(acc, p); }
+};
+template <class AR, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 384 / (32 * WARPS)) k_fk_direct_lincomb(const uint8_t* __restrict__ scalars,
+                                                                                   const uint8_t* __restrict__ table,
+                                                                                   uint8_t* __restrict__ out_jac, int nvec) {
     const int lane = threadIdx.x & 31;
-    const size_t v = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t v = (size_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (v >= (size_t)nvec) return;                       // whole warps leave together
     const size_t row = v % 128;
     const uint32_t* sc = reinterpret_cast<const uint32_t*>(scalars + v * kDCell * 32);
@@ -78,26 +98,38 @@ __global__ void __launch_bounds__(128, 3) k_fk_direct_lincomb(const uint8_t* __r
         uint32_t below = lane == 0 ? 0u : ((lane & 3) ? (w >> ((lane & 3) * 8 - 1)) & 1u : sc[i * 8 + (lane >> 2) - 1] >> 31);
         return (int)byte + (int)below - (int)((byte >> 7) << 8);
     };
-    xyzz_t acc = xyzz_t::inf();
+    typename AR::xyzz acc = AR::xyzz::inf();
     int d = digit(0);
-    affine_t p = load_affine(fk_entry(table, row, 0, lane, d));
+    typename AR::affine p = AR::load(fk_entry(table, row, 0, lane, d));
+#pragma unroll 1
     for (int i = 0; i < kDCell; i++) {
-        affine_t cur = p;
+        typename AR::affine cur = p;
         const int cd = d;
         if (i + 1 < kDCell) {
             d = digit(i + 1);
-            p = load_affine(fk_entry(table, row, i + 1, lane, d));
+            p = AR::load(fk_entry(table, row, i + 1, lane, d));
         }
-        if (cd != 0) {
-            cur.y = cur.y.cneg(cd < 0);
-            xyzz_add_affine(acc, cur);
-        }
+        if (cd == 0) cur = typename AR::affine{AR::fp::zero(), AR::fp::zero()};   // adding infinity: same instruction stream
+        cur.y = cur.y.cneg(cd < 0);
+        AR::add(acc, cur);
     }
-    xyzz_t total = warp_sum_xyzz(acc);
+    // the tree sum runs on the inlined-multiplier types (same memory layout)
+    xyzz_t a2;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { a2.x.v[k] = acc.x.v[k]; a2.y.v[k] = acc.y.v[k]; a2.zzz.v[k] = acc.zzz.v[k]; a2.zz.v[k] = acc.zz.v[k]; }
+    xyzz_t total = warp_sum_xyzz(a2);
     if (lane == 0) store_jac(out_jac + v * 144, xyzz_to_jac(total));
 }
 void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_jac, int nvec, cudaStream_t st) {
-    k_fk_direct_lincomb<<<div_up(nvec, 4), 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)out_jac, nvec);
+    // measured (scripts/fk20_timing.py, proofs of 64 blobs): inlined multiplier, 4 warps per CTA 19.5 ms; behind a call 18.9;
+    // inlined, 2 warps 19.3; behind a call, 2 warps per CTA 18.8 (default: smaller code, finer-grained last wave)
+    static const int variant = getenv("B200_FK20_LINCOMB") ? atoi(getenv("B200_FK20_LINCOMB")) : 3;
+    const uint8_t *s8 = (const uint8_t*)scalars, *t8 = (const uint8_t*)table;
+    uint8_t* o8 = (uint8_t*)out_jac;
+    if (variant == 1) k_fk_direct_lincomb<ArCall, 4><<<div_up(nvec, 4), 128, 0, st>>>(s8, t8, o8, nvec);
+    else if (variant == 2) k_fk_direct_lincomb<ArInline, 2><<<div_up(nvec, 2), 64, 0, st>>>(s8, t8, o8, nvec);
+    else if (variant == 3) k_fk_direct_lincomb<ArCall, 2><<<div_up(nvec, 2), 64, 0, st>>>(s8, t8, o8, nvec);
+    else k_fk_direct_lincomb<ArInline, 4><<<div_up(nvec, 4), 128, 0, st>>>(s8, t8, o8, nvec);
     B200_LAUNCH_CHECK();
 }
 
