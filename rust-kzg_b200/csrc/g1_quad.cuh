@@ -67,6 +67,15 @@ __device__ __forceinline__ int quad_store_offset() {
     return role == 0 ? 0 : role == 1 ? 48 : role == 2 ? 144 : 96;
 }
 
+// The quad formulas run on one or a few warps per SM: their multiplications go through ONE out-of-line copy of the
+// multiplier (B200_QUAD_INLINE_MUL restores inlining) so that a doubling + an addition are ~2 KiB of code instead of
+// ~45 KiB -- with a lone warp per scheduler every instruction-cache miss is exposed latency.
+#ifdef B200_QUAD_INLINE_MUL
+__device__ __forceinline__ fp_t qmul(const fp_t& a, const fp_t& b) { return a * b; }
+#else
+static __device__ __noinline__ fp_t qmul(fp_t a, fp_t b) { return a * b; }
+#endif
+
 // 2 * a   (dbl-2008-s-1 in three multiplication levels)
 static __device__ __noinline__ fp_t quad_dbl(fp_t a) {
     const int lane = threadIdx.x & 31, role = lane & 3, base = lane & ~3;
@@ -74,21 +83,21 @@ static __device__ __noinline__ fp_t quad_dbl(fp_t a) {
     fp_t U = shfl_idx_fp(a.dbl(), base | 1);                       // U = 2Y on every lane
     // level 1: lane0 X^2 ; lanes 1..3 V = U^2
     fp_t m = role == 0 ? a : U;
-    fp_t l1 = m.sqr();
+    fp_t l1 = qmul(m, m);
     fp_t M = l1.dbl() + l1;                                        // lane0: M = 3 X^2
     fp_t V = shfl_idx_fp(l1, base | 1);
     fp_t Mb = shfl_idx_fp(M, base);
     // level 2: lane0 S = X V ; lane1 W = U V ; lane2 ZZ3 = ZZ V ; lane3 M^2
     fp_t m1 = role == 3 ? Mb : (role == 1 ? U : a);
     fp_t m2 = role == 3 ? Mb : V;
-    fp_t l2 = m1 * m2;
+    fp_t l2 = qmul(m1, m2);
     fp_t MM = shfl_idx_fp(l2, base | 3);
     fp_t Wb = shfl_idx_fp(l2, base | 1);
     fp_t x3 = MM - l2.dbl();                                       // lane0: M^2 - 2S
     // level 3: lane0 M (S - X3) ; lane1 W Y ; lane3 ZZZ3 = W ZZZ ; lane2 idle
     m1 = role == 0 ? M : Wb;
     m2 = role == 0 ? (l2 - x3) : a;
-    fp_t l3 = m1 * m2;
+    fp_t l3 = qmul(m1, m2);
     fp_t t = shfl_idx_fp(l3, base);
     fp_t y3 = t - l3;                                              // lane1
     fp_t r = role == 0 ? x3 : role == 1 ? y3 : role == 2 ? l2 : l3;
@@ -103,7 +112,7 @@ static __device__ __noinline__ fp_t quad_add(fp_t a, fp_t b) {
     const bool b_inf = __shfl_sync(kFullMask, (int)b.is_zero(), base | 2);
     // level 1: own component of a times the opposite component of b: lane0 U1 = X1 ZZ2, lane1 S1 = Y1 ZZZ2,
     //          lane2 U2 = ZZ1 X2, lane3 S2 = ZZZ1 Y2
-    fp_t l1 = a * shfl_xor_fp(b, 2);
+    fp_t l1 = qmul(a, shfl_xor_fp(b, 2));
     fp_t l1x = shfl_xor_fp(l1, 2);
     fp_t pr = role < 2 ? (l1x - l1) : (l1 - l1x);                  // lanes 0,2: P = U2 - U1 ; lanes 1,3: R = S2 - S1
     const bool p_zero = __shfl_sync(kFullMask, (int)pr.is_zero(), base);
@@ -111,19 +120,19 @@ static __device__ __noinline__ fp_t quad_add(fp_t a, fp_t b) {
     // level 2: lane0 PP = P^2 ; lane1 RR = R^2 ; lane2 ZZ1 ZZ2 ; lane3 ZZZ1 ZZZ2
     fp_t m1 = role < 2 ? pr : a;
     fp_t m2 = role < 2 ? pr : b;
-    fp_t l2 = m1 * m2;
+    fp_t l2 = qmul(m1, m2);
     fp_t pp = shfl_idx_fp(l2, base);
     fp_t u1 = shfl_idx_fp(l1, base);
     // level 3: lane0 PPP = P PP ; lane1 Q = U1 PP ; lane2 ZZ3 = (ZZ1 ZZ2) PP ; lane3 idle
     m1 = role == 0 ? pr : role == 1 ? u1 : l2;
-    fp_t l3 = m1 * pp;
+    fp_t l3 = qmul(m1, pp);
     fp_t ppp = shfl_idx_fp(l3, base);
     fp_t s1 = shfl_idx_fp(l1, base | 1);
     fp_t x3 = l2 - ppp - l3.dbl();                                 // lane1: RR - PPP - 2Q
     // level 4: lane0 S1 PPP ; lane1 R (Q - X3) ; lane3 ZZZ3 = (ZZZ1 ZZZ2) PPP ; lane2 idle
     m1 = role == 0 ? s1 : role == 1 ? pr : l2;
     m2 = role == 1 ? (l3 - x3) : ppp;
-    fp_t l4 = m1 * m2;
+    fp_t l4 = qmul(m1, m2);
     fp_t t0 = shfl_idx_fp(l4, base);
     fp_t y3 = l4 - t0;                                             // lane1
     fp_t x3_0 = shfl_idx_fp(x3, base | 1);
