@@ -569,7 +569,7 @@ static constexpr int kMargSerial = 8;  // buckets summed serially per lane befor
 // tree steps waste few lanes -- with 64 groups x 40 marginals the CTA form spends most of its FMA-pipe time on
 // additions with the point at infinity.  S = 2^log_s lanes sum count/S buckets each, then a
 // log_s-step shuffle tree inside the S-lane group.
-__global__ void __launch_bounds__(128) k_marginals_sub(const uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
+__global__ void __launch_bounds__(128, 3) k_marginals_sub(const uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
                                                        int nb, AxisPlan ap, size_t groups, uint8_t* __restrict__ marg) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int a = blockIdx.y;  // one grid row per digit axis: the axes are independent and run concurrently
