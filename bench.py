@@ -228,6 +228,7 @@ def main():
     ms_total = e0.elapsed_time(e1)
     acc_ms_sum, acc_runs = msm.profile_read()
     msm.set_profiling(False)
+    n_entries, n_tasks = msm.last_counts()   # non-zero digits sorted into buckets / accumulate tasks of the last step
     if world > 1:
         t = torch.tensor([ms_total], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -276,7 +277,7 @@ def main():
         pass
     achieved_gbs = BYTES_PER_TERM * n / (acc_ms * 1e-3) / 1e9 if acc_ms else None
     mb = B.microbench_int()
-    adds_per_launch = n * info["W"]
+    adds_per_launch = n_entries - n_tasks   # a task's first point is a load, every other entry one mixed addition
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved_gbs / hbm_peak if achieved_gbs else None, "traffic": traffic,
                 "kernel": "k_accumulate", "kernel_ms": acc_ms, "kernel_share_of_step": acc_ms / ms_step if acc_ms else None,
@@ -286,7 +287,9 @@ def main():
                     "achieved": adds_per_launch * IMAD_PER_ADD / (acc_ms * 1e-3) / 1e12 if acc_ms else None,
                     "peak": mb["imad_per_s"] / 1e12, "peak_source": "b200_microbench_int (dependent-operand IMAD.WIDE loop), measured in this run",
                     "fp_mul_per_s_measured": mb["fpmul_per_s"],
-                    "note": "achieved counts 3000 algorithmic multiply-adds per bucket addition (10 Fp mul x 300); every "
+                    "adds_per_launch": adds_per_launch, "entries": n_entries, "tasks": n_tasks,
+                    "note": "achieved counts 3000 algorithmic multiply-adds per bucket addition (10 Fp mul x 300) over the "
+                            "additions k_accumulate actually performs (entries - tasks, read back from the device); every "
                             "IMAD.WIDE form issues at 32/clk/SM on sm_100a (measured, with or without carry), ncu shows "
                             "the FMA-heavy pipe 86% busy in k_accumulate (profiles/r01_accumulate_full.md)"}
     if int_roofline["achieved"]:

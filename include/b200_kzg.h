@@ -72,6 +72,10 @@ B200_API RustError b200_g1_sum_device(void *out_dev, const void *points_dev, siz
 
 /* introspection (bench / tests): window bits, windows, table bytes, kernel launches of the last run */
 B200_API void b200_msm_info(void *msm, int *c, int *W, size_t *table_bytes, int *launches);
+/* work of the last run on this handle: entries = non-zero digits sorted into buckets, tasks = accumulate tasks; the
+ * accumulate kernel did  entries - tasks  mixed additions (a task's first point is a load).  Synchronises the handle's
+ * stream. */
+B200_API RustError b200_msm_last_counts(void *msm, size_t *entries, size_t *tasks);
 
 
 /* ============================================================================================================== */

@@ -26,11 +26,17 @@ MsmConfig choose_config(size_t n, bool fixed, int max_batch) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
     int c;
-    if (fixed) c = lg >= 18 ? 16 : lg >= 14 ? lg - 2 : lg >= 11 ? 12 : lg >= 8 ? 10 : 8;
+    // fixed, >= 2^20 points: c = 20, W = 13 (260 bits: the top window still holds 15 scalar bits, so its digits spread
+    // over 2^15 buckets -- with c = 18, 19 or 21 the top window has 3 or 8 bits and a handful of buckets get 2^20 entries):
+    // measured at 2^20 c = 16 / 18 / 19 / 20 / 21 -> 7.22 / 14.4 / 9.85 / 6.53 / 14.6 ms (scripts/msm_window_sweep.py)
+    if (fixed) c = lg >= 20 ? 20 : lg >= 18 ? 16 : lg >= 14 ? lg - 2 : lg >= 11 ? 12 : lg >= 8 ? 10 : 8;
     else c = lg >= 20 ? 16 : lg >= 16 ? 14 : lg >= 12 ? 12 : lg >= 9 ? 10 : 8;
     c = env_int(fixed ? "B200_MSM_C" : "B200_MSM_VC", c);
     if (c < 4) c = 4;
-    if (c > 16) c = 16;  // the reduce handles up to 15 bucket-index bits (three 5-bit digits)
+    // beyond 16 the bucket set is folded by segments before the 15-bit reduce (k_segment_fold); a variable-base call has
+    // one bucket set per window and the scans take at most 2^24 keys
+    const int cmax = fixed ? 22 : 20;
+    if (c > cmax) c = cmax;
     MsmConfig cfg;
     cfg.c = c;
     cfg.W = (256 + c - 1) / c;
@@ -169,6 +175,16 @@ void b200_msm_info(void* msm, int* c, int* W, size_t* table_bytes, int* launches
     if (W) *W = h->eng->config().W;
     if (table_bytes) *table_bytes = h->eng->table_bytes();
     if (launches) *launches = h->eng->launches_per_run();
+}
+
+RustError b200_msm_last_counts(void* msm, size_t* entries, size_t* tasks) {
+    return guarded([&] {
+        MsmHandle* h = static_cast<MsmHandle*>(msm);
+        if (!h) throw CudaError(-1, "null msm handle");
+        std::lock_guard<std::mutex> lk(h->mu);
+        B200_CUDA_CHECK(cudaDeviceSynchronize());  // the last run may have been on a caller's stream (device variant)
+        h->eng->last_counts(entries, tasks, h->stream);
+    });
 }
 
 void b200_msm_set_profiling(void* msm, int on) {

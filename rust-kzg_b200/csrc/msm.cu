@@ -13,7 +13,9 @@
 namespace b200 {
 
 static constexpr int kMinTaskLen = 4;     // shortest accumulate task (entries) for latency-bound calls
-static constexpr int kAccThreads = 128;  // accumulate CTA: 4 warps, one per SM sub-partition
+static constexpr int kAccThreads = 128;
+static constexpr int kReduceBits = 15;   // bucket-index bits the marginal-sum reduce handles (three 5-bit digits)
+static constexpr int kMaxWindow = 22;    // wider windows than kReduceBits + 1 go through k_segment_fold first  // accumulate CTA: 4 warps, one per SM sub-partition
 
 // ---------------------------------------------------------------------------------------------------------------
 // 1 / 3: signed digits of every scalar; histogram (SCATTER = false) or counting-sort scatter (SCATTER = true).
@@ -203,11 +205,15 @@ __global__ void __launch_bounds__(256) k_task_emit(const uint32_t* __restrict__ 
                                                    const uint32_t* __restrict__ task_base, size_t nkeys, int L,
                                                    uint32_t* __restrict__ size_hist, uint32_t* __restrict__ sorted_tasks) {
     size_t key = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (key >= nkeys) return;
-    uint32_t cnt = counts[key];
-    if (!cnt) return;
-    uint32_t tc = (cnt + L - 1) / L, rem = cnt - (tc - 1) * L;
-    uint32_t start = offsets[key], slot = task_base[key];
+    const uint32_t cnt = key < nkeys ? counts[key] : 0;
+    const bool live = cnt != 0;
+    uint32_t tc = 0, rem = 0xffffffffu, start = 0, slot = 0;
+    if (live) {
+        tc = (cnt + L - 1) / L;
+        rem = cnt - (tc - 1) * L;
+        start = offsets[key];
+        slot = task_base[key];
+    }
     const uint32_t* base = size_hist + L + 1;
     uint32_t* cur = size_hist + 2 * L + 2;
     if (tc > 1) {
@@ -218,10 +224,19 @@ __global__ void __launch_bounds__(256) k_task_emit(const uint32_t* __restrict__ 
             sorted_tasks[3 * (size_t)(p + q) + 2] = slot + q;
         }
     }
-    uint32_t p = base[rem] + atomicAdd(&cur[rem], 1u);
-    sorted_tasks[3 * (size_t)p] = start + (tc - 1) * L;
-    sorted_tasks[3 * (size_t)p + 1] = rem;
-    sorted_tasks[3 * (size_t)p + 2] = slot + tc - 1;
+    // the cursor of a length class is a hot address (2^19 buckets share ~40 classes at c = 20): lanes of a warp with the
+    // same class take their slots with ONE atomic (whole warps reach this point: the grid is a multiple of 32 threads)
+    const unsigned peers = __match_any_sync(0xffffffffu, rem);
+    if (live) {
+        const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        uint32_t first = 0;
+        if (lane == leader) first = atomicAdd(&cur[rem], (uint32_t)__popc(peers));
+        first = __shfl_sync(peers, first, leader);
+        uint32_t p = base[rem] + first + __popc(peers & ((1u << lane) - 1));
+        sorted_tasks[3 * (size_t)p] = start + (tc - 1) * L;
+        sorted_tasks[3 * (size_t)p + 1] = rem;
+        sorted_tasks[3 * (size_t)p + 2] = slot + tc - 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -526,16 +541,58 @@ struct AxisPlan {
     int sh[3];  // digit bit offsets
 };
 
+// 6a': wide windows (c > 16).  The marginal form below handles 15 bucket-index bits; a wider bucket set is first folded
+// by SEGMENTS of 2^kf consecutive buckets, one thread per segment (2^15 segments per group: a throughput kernel, the
+// chains are 2 * 2^kf additions).  With b = hi * 2^kf + lo and weights b + 1:
+//      sum_b (b+1) B_b = 2^kf * sum_hi (hi+1) T_hi  -  sum_hi R_hi,
+//      T_hi = sum_lo B_(hi,lo),   R_hi = sum_lo (2^kf - 1 - lo) B_(hi,lo)   (an ascending running sum: acc += run; run += B)
+// so the T_hi go through the 15-bit reduce unchanged and the R_hi only need a plain sum.  This is the reference's
+// p1_integrate_buckets (kzg/src/msm/tiling_pippenger_ops.rs:21-45) applied per segment instead of over the whole set.
+__global__ void __launch_bounds__(128) k_segment_fold(const uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
+                                                      size_t nseg, int kf, uint8_t* __restrict__ seg_t, uint8_t* __restrict__ seg_r) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const size_t key0 = s << kf;
+    xyzz_t run = xyzz_t::inf(), acc = xyzz_t::inf();
+#pragma unroll 1
+    for (int lo = 0; lo < (1 << kf); lo++) {
+        xyzz_add(acc, run);
+        uint32_t s0 = task_base[key0 + lo];
+        if (task_base[key0 + lo + 1] > s0) {
+            xyzz_t part = load_xyzz(partials + (size_t)s0 * 192);
+            xyzz_add(run, part);
+        }
+    }
+    store_xyzz(seg_t + s * 192, run);
+    store_xyzz(seg_r + s * 192, acc);
+}
+// identity slot map for point arrays that have exactly one slot per key (the folded segments)
+__global__ void k_iota(uint32_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
 // 6b: marginal sums.  CTA (v, a, g) adds up the nb >> w[a] buckets of group g whose digit a equals v.
 template <int kMargThreads>
 __global__ void __launch_bounds__(kMargThreads) k_marginals(const uint8_t* __restrict__ partials,
                                                             const uint32_t* __restrict__ task_base, int nb, AxisPlan ap,
-                                                            uint8_t* __restrict__ marg) {
+                                                            uint8_t* __restrict__ marg,
+                                                            const uint8_t* __restrict__ partials_r, uint8_t* __restrict__ marg_r) {
     __shared__ __align__(16) uint8_t sh[(kMargThreads / 32) * 192];
-    const int v = blockIdx.x, a = blockIdx.y;
+    const int v = blockIdx.x;
+    int a = blockIdx.y;
     const size_t g = blockIdx.z;
+    int wa, sa;
+    if (a == ap.D) {
+        // extra grid row (wide windows only): plain sum of the segment running sums R, as the 32 marginals of one
+        // 5-bit digit over the second point array (k_group_finish adds them up)
+        partials = partials_r;
+        marg = marg_r;
+        a = 0; wa = 5; sa = 0;
+    } else {
+        wa = ap.w[a]; sa = ap.sh[a];
+    }
     uint8_t* dst = marg + ((g * 3 + a) * 32 + v) * 192;
-    const int wa = ap.w[a], sa = ap.sh[a];
     if (v >= (1 << wa)) {
         if (threadIdx.x == 0) store_xyzz(dst, xyzz_t::inf());
         return;
@@ -612,9 +669,12 @@ __global__ void __launch_bounds__(128, 3) k_marginals_sub(const uint8_t* __restr
 
 // 6c: one CTA per group, one warp per digit axis: weighted sum over the <= 32 marginals, scale by 2^sh, combine.
 // Everything after the suffix scan runs on quad-distributed points (g1_quad.cuh).
-__global__ void __launch_bounds__(96) k_group_finish(const uint8_t* __restrict__ marg, AxisPlan ap,
-                                                     uint8_t* __restrict__ group_sums, uint8_t* __restrict__ out_jac) {
-    __shared__ __align__(16) uint8_t sh[4 * 192];
+// marg_r != nullptr (wide windows, see k_segment_fold): the fourth warp sums the 32 plain marginals of the R_hi and the
+// result is 2^kf * (15-bit reduce of the T_hi) - sum R.
+__global__ void __launch_bounds__(128) k_group_finish(const uint8_t* __restrict__ marg, AxisPlan ap,
+                                                      uint8_t* __restrict__ group_sums, uint8_t* __restrict__ out_jac,
+                                                      const uint8_t* __restrict__ marg_r, int kf) {
+    __shared__ __align__(16) uint8_t sh[5 * 192];
     const size_t g = blockIdx.x;
     const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
     const int off = quad_store_offset();
@@ -627,11 +687,21 @@ __global__ void __launch_bounds__(96) k_group_finish(const uint8_t* __restrict__
         fp_t w = seg_sum_quad(suf, width < 4 ? 4 : width);
         for (int k = 0; k < ap.sh[a]; k++) w = quad_dbl(w);
         if (lane < 4) store_field(sh + a * 192 + off, w);
+    } else if (a == 3 && marg_r) {
+        xyzz_t m = load_xyzz(marg_r + ((g * 3) * 32 + lane) * 192);
+        fp_t w = seg_sum_quad(m, 32);
+        if (lane < 4) store_field(sh + 4 * 192 + off, w);
     }
     __syncthreads();
     if (a == 0) {
         fp_t acc = load_field<fp_t>(sh + 3 * 192 + off);  // the "+1" of the weights b+1
         for (int k = 0; k < ap.D; k++) acc = quad_add(acc, load_field<fp_t>(sh + k * 192 + off));
+        if (marg_r) {
+            for (int k = 0; k < kf; k++) acc = quad_dbl(acc);
+            fp_t r = load_field<fp_t>(sh + 4 * 192 + off);
+            if ((lane & 3) == 1) r = r.neg();             // -(X, Y, ZZ, ZZZ) = (X, -Y, ZZ, ZZZ); infinity stays all-zero
+            acc = quad_add(acc, r);
+        }
         if (group_sums && lane < 4) store_field(group_sums + g * 192 + off, acc);
         if (out_jac) {
             // Jacobian (X*ZZ, Y*ZZZ, ZZ), see xyzz_to_jac; infinity is all-zero in both forms
@@ -739,7 +809,7 @@ void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int co
 
 // ---------------------------------------------------------------------------------------------------------------
 MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points, cudaStream_t stream) : cfg_(cfg) {
-    if (cfg_.c < 2 || cfg_.c > 16 || cfg_.c * cfg_.W < 256) throw CudaError(-1, "MsmEngine: bad window configuration");
+    if (cfg_.c < 2 || cfg_.c > kMaxWindow || cfg_.c * cfg_.W < 256) throw CudaError(-1, "MsmEngine: bad window configuration");
     if (cfg_.L < 1 || cfg_.L > 1024) throw CudaError(-1, "MsmEngine: bad task length");
     if (!cfg_.fixed) cfg_.max_batch = 1;
     if (!cfg_.fixed || cfg_.bases_period < 1) cfg_.bases_period = 1;
@@ -766,6 +836,17 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     chunk_sums_ = dev_alloc<uint8_t>(groups_max_ * 3 * 32 * 192);  // marginal sums [group][axis][32]
     group_sums_ = dev_alloc<uint8_t>(groups_max_ * 192);
     pair_base_ = dev_alloc<uint32_t>(keys_max_ + 1);
+    if (cfg_.c - 1 > kReduceBits) {
+        // wide windows: folded segments (T and R point per segment), their identity slot map, marginals of the R sums
+        const size_t nseg = keys_max_ >> (cfg_.c - 1 - kReduceBits);
+        seg_t_ = dev_alloc<uint8_t>(nseg * 192);
+        seg_r_ = dev_alloc<uint8_t>(nseg * 192);
+        seg_ident_ = dev_alloc<uint32_t>(nseg + 1);
+        chunk_sums_r_ = dev_alloc<uint8_t>(groups_max_ * 3 * 32 * 192);
+        k_iota<<<div_up(nseg + 1, 256), 256, 0, stream>>>(seg_ident_, nseg + 1);
+        B200_LAUNCH_CHECK();
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
     {
         const char* e = getenv("B200_AFFINE_ROUNDS");
         // OFF by default: measured on B200 (MSM 2^20) the rounds make the accumulation phase 16.1 ms instead of 6.4 ms --
@@ -801,6 +882,17 @@ void MsmEngine::profile_read(double* accumulate_ms_sum, int* runs) {
     prof_count_ = 0;
 }
 
+void MsmEngine::last_counts(size_t* entries, size_t* tasks, cudaStream_t stream) {
+    uint32_t e = 0, t = 0;
+    if (last_nkeys_) {
+        B200_CUDA_CHECK(cudaMemcpyAsync(&e, offsets_ + last_nkeys_, 4, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaMemcpyAsync(&t, task_base_ + last_nkeys_, 4, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    if (entries) *entries = e;
+    if (tasks) *tasks = t;
+}
+
 MsmEngine::~MsmEngine() {
     for (auto& e : prof_ev_)
         if (e) cudaEventDestroy(e);
@@ -812,6 +904,7 @@ MsmEngine::~MsmEngine() {
     cudaFree(table_); cudaFree(counts_); cudaFree(offsets_); cudaFree(cursor_); cudaFree(task_base_); cudaFree(entries_);
     cudaFree(sorted_tasks_); cudaFree(size_hist_); cudaFree(scan_tmp_); cudaFree(partials_); cudaFree(chunk_sums_);
     cudaFree(group_sums_);
+    cudaFree(seg_t_); cudaFree(seg_r_); cudaFree(seg_ident_); cudaFree(chunk_sums_r_);
 }
 
 void MsmEngine::set_points(const void* points_dev, size_t npoints, cudaStream_t stream) {
@@ -949,9 +1042,21 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     else
         k_bucket_combine<false, false><<<div_up(nkeys, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
     k_bucket_combine<true, false><<<148 * 4, 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
+    // wide windows: fold segments of 2^kf buckets first; the marginal reduce then sees nbr = 2^15 "buckets" T_hi per group
+    const int kf = c - 1 > kReduceBits ? c - 1 - kReduceBits : 0;
+    const int nbr = nb_ >> kf;
+    const uint8_t* rpart = (const uint8_t*)partials_;
+    const uint32_t* rbase = task_base_;
+    if (kf) {
+        const size_t nseg = groups * nbr;
+        k_segment_fold<<<div_up(nseg, 128), 128, 0, st>>>((const uint8_t*)partials_, task_base_, nseg, kf, (uint8_t*)seg_t_, (uint8_t*)seg_r_);
+        launches++;
+        rpart = (const uint8_t*)seg_t_;
+        rbase = seg_ident_;
+    }
     AxisPlan ap{};
     {
-        int bits = c - 1;
+        int bits = c - 1 - kf;
         ap.D = (bits + 4) / 5;
         if (ap.D < 1) ap.D = 1;
         int off = 0;
@@ -962,7 +1067,7 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
             off += wa;
         }
     }
-    if (groups * 32 * ap.D >= 2048) {
+    if (!kf && groups * 32 * ap.D >= 2048) {
         // many groups: lane-efficient sub-warp marginals, one launch per digit axis.  Slots of digit values that do
         // not exist (v >= 2^w) must read as infinity (all-zero XYZZ).
         B200_CUDA_CHECK(cudaMemsetAsync(chunk_sums_, 0, groups * 3 * 32 * 192, st));
@@ -976,25 +1081,29 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
                                                                              (uint8_t*)chunk_sums_);
         launches += 3;
     } else {
-        // one CTA per marginal; 256 threads once a marginal covers >= 1024 buckets (shorter serial chains)
-        if ((nb_ >> ap.w[0]) >= 1024)
-            k_marginals<256><<<dim3(32, ap.D, (unsigned)groups), 256, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap,
-                                                                              (uint8_t*)chunk_sums_);
+        // one CTA per marginal; 256 threads once a marginal covers >= 1024 buckets (shorter serial chains).
+        // Wide windows: one more grid row sums the R_hi (32 plain marginals, added up by k_group_finish's fourth warp).
+        const dim3 mgrid(32, ap.D + (kf ? 1 : 0), (unsigned)groups);
+        if ((nbr >> ap.w[0]) >= 1024)
+            k_marginals<256><<<mgrid, 256, 0, st>>>(rpart, rbase, nbr, ap, (uint8_t*)chunk_sums_, (const uint8_t*)seg_r_,
+                                                    (uint8_t*)chunk_sums_r_);
         else
-            k_marginals<128><<<dim3(32, ap.D, (unsigned)groups), 128, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap,
-                                                                              (uint8_t*)chunk_sums_);
+            k_marginals<128><<<mgrid, 128, 0, st>>>(rpart, rbase, nbr, ap, (uint8_t*)chunk_sums_, (const uint8_t*)seg_r_,
+                                                    (uint8_t*)chunk_sums_r_);
         launches += 3;
     }
+    const uint8_t* marg_r = kf ? (const uint8_t*)chunk_sums_r_ : nullptr;
     if (cfg_.fixed) {
-        k_group_finish<<<(unsigned)groups, 96, 0, st>>>((const uint8_t*)chunk_sums_, ap, nullptr, (uint8_t*)out_dev);
+        k_group_finish<<<(unsigned)groups, 128, 0, st>>>((const uint8_t*)chunk_sums_, ap, nullptr, (uint8_t*)out_dev, marg_r, kf);
         launches += 1;
     } else {
-        k_group_finish<<<(unsigned)groups, 96, 0, st>>>((const uint8_t*)chunk_sums_, ap, (uint8_t*)group_sums_, nullptr);
+        k_group_finish<<<(unsigned)groups, 128, 0, st>>>((const uint8_t*)chunk_sums_, ap, (uint8_t*)group_sums_, nullptr, marg_r, kf);
         k_horner<<<1, 32, 0, st>>>((const uint8_t*)group_sums_, W, c, (uint8_t*)out_dev);
         launches += 2;
     }
     B200_LAUNCH_CHECK();
     launches_ = launches;
+    last_nkeys_ = nkeys;
 }
 
 }  // namespace b200

@@ -66,6 +66,8 @@ public:
     // k_accumulate with CUDA events on the launching stream; profile_read() sums the completed pairs and resets.
     void set_profiling(bool on) { profiling_ = on; }
     void profile_read(double* accumulate_ms_sum, int* runs);
+    // entries (non-zero digits) and accumulate tasks of the last run(); synchronises `stream`
+    void last_counts(size_t* entries, size_t* tasks, cudaStream_t stream);
 
 private:
     MsmConfig cfg_;
@@ -76,6 +78,7 @@ private:
     size_t tasks_max_;
     size_t table_bytes_;
     int launches_ = 0;
+    size_t last_nkeys_ = 0;
     bool profiling_ = false;
     static constexpr int kProfSlots = 512;
     cudaEvent_t prof_ev_[2 * kProfSlots] = {};
@@ -99,6 +102,10 @@ private:
     void* partials_ = nullptr;  // xyzz per task
     void* chunk_sums_ = nullptr;
     void* group_sums_ = nullptr;
+    void* seg_t_ = nullptr;            // wide windows (c > 16): per-segment sums T and running sums R, see k_segment_fold
+    void* seg_r_ = nullptr;
+    uint32_t* seg_ident_ = nullptr;    // identity slot map for the segment arrays
+    void* chunk_sums_r_ = nullptr;     // marginals of the R sums
 };
 
 // helpers shared with other translation units

@@ -45,6 +45,12 @@ class PreparedMsm:
         _L().b200_msm_info(self.h, C.byref(c), C.byref(w), C.byref(tb), C.byref(l))
         return {"c": c.value, "W": w.value, "table_bytes": tb.value, "launches": l.value}
 
+    def last_counts(self):
+        """(entries, tasks) of the last run: the accumulate kernel did entries - tasks mixed additions."""
+        e, t = C.c_size_t(), C.c_size_t()
+        _lib.check(_L().b200_msm_last_counts(self.h, C.byref(e), C.byref(t)))
+        return e.value, t.value
+
     def mult(self, scalars):
         """multi_scalar_mult_prepared: -> Jacobian point (18 u64)."""
         sc = _u64(scalars, 4)

@@ -170,3 +170,47 @@ def test_adversarial_distributions_at_scale(B, K, lagrange_affine):
         assert K.p1_compress(h.mult(sc)) == K.p1_compress(exp), name
         assert K.p1_compress(B.mult_pippenger(pts, sc)) == K.p1_compress(exp), name + "/variable"
     h.close()
+
+
+def _with_env(name, value, fn):
+    import os
+    old = os.environ.get(name)
+    os.environ[name] = str(value)
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("c", [17, 18, 20, 22])
+def test_wide_windows_segment_fold(B, K, lagrange_affine, c):
+    """windows wider than 16 bits: the bucket set is folded by segments of 2^(c-16) buckets before the 15-bit reduce
+    (k_segment_fold); same group element as the reference's p1_integrate_buckets (tiling_pippenger_ops.rs:21-45)."""
+    n = 1 << 14
+    rng = np.random.default_rng(100 + c)
+    sc = rand_fr_mont(rng, n)
+    pts = np.tile(lagrange_affine, (n // 4096, 1))
+    folded = sc[:4096].copy()
+    for k in range(1, n // 4096):
+        folded = K.fr_add(folded, sc[k * 4096:(k + 1) * 4096])
+    exp = K.msm_affine(lagrange_affine, folded, nthreads=8)
+    h = _with_env("B200_MSM_C", c, lambda: B.PreparedMsm(pts))
+    assert h.info()["c"] == c
+    _same(K, h.mult(sc), exp)
+    # edge scalars: every term in the top bucket of a segment / bucket 0 / cancelling signs
+    for name, ints in {"r-1": [R_MOD - 1] * 4096, "ones": [1] * 4096, "zeros": [0] * 4096,
+                       "half-window": [(1 << (c - 1)) % R_MOD] * 4096,
+                       "small": [int(x) for x in rng.integers(0, 1 << 20, 4096)]}.items():
+        s4 = K.fr_from_ints(ints)
+        assert K.p1_compress(h.mult(s4)) == K.p1_compress(K.msm_affine(lagrange_affine, s4, nthreads=8)), name
+    h.close()
+    # variable base through the same reduce (one bucket set per window + Horner)
+    if c == 20:
+        # engines of the variable-base call are cached per capacity: 2^15 terms is a capacity no other test uses, so the
+        # override is what this engine is built with
+        pts2, sc2 = np.concatenate([pts, pts]), np.concatenate([sc, sc])
+        got = _with_env("B200_MSM_VC", c, lambda: B.mult_pippenger(pts2, sc2))
+        _same(K, got, K.p1_add(exp, exp))
