@@ -99,7 +99,8 @@ private:
     int launches_ = 0;
     std::unique_ptr<FFTSettingsDev> fs_;
     struct Lane {
-        std::unique_ptr<MsmEngine> msm;
+        std::unique_ptr<MsmEngine> msm;    // commitments (blob elements: usually < 2^248, window width 12)
+        std::unique_ptr<MsmEngine> msm_q;  // proofs (quotient values: uniform in Fr, window width 13 + segment fold)
         void* scalars = nullptr;   // max_batch * 4096 canonical scalars (MSM input)
         void* poly = nullptr;      // max_batch * 4096 Montgomery field elements
         void* z = nullptr;         // max_batch Montgomery

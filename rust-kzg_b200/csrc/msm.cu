@@ -53,12 +53,27 @@ __global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalar
         if (mag != 0) {
             size_t group = fixed ? vec : vec * W + j;
             size_t key = group * nb + (mag - 1);
+            // top window: it may hold only a few scalar bits (c = 13: bit 247 and up, and blob elements are < 2^248),
+            // so thousands of neighbouring scalars hit the same one or two keys -- lanes of a warp with the same key
+            // share ONE atomic there (same-address atomics serialise in L2)
+            uint32_t cnt = 1, rank = 0;
+            bool leader = true;
+            unsigned peers = 0;
+            const bool agg = j == W - 1;
+            if (agg) {
+                peers = __match_any_sync(__activemask(), key);
+                cnt = __popc(peers);
+                rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1));
+                leader = rank == 0;
+            }
             if (SCATTER) {
-                uint32_t pos = atomicAdd(&ctr[key], 1u);
+                uint32_t pos = 0;
+                if (leader) pos = atomicAdd(&ctr[key], cnt);
+                if (agg) pos = __shfl_sync(peers, pos, __ffs(peers) - 1) + rank;
                 uint32_t idx = (uint32_t)(fixed ? (size_t)j * row_stride + (vec % period) * period_n + i : i);
                 entries[pos] = idx | (neg << 31);
             } else {
-                atomicAdd(&ctr[key], 1u);
+                if (leader) atomicAdd(&ctr[key], cnt);
             }
         }
     }
@@ -474,9 +489,12 @@ __device__ __forceinline__ xyzz_t warp_suffix_scan_xyzz(xyzz_t v, int width) {
 // ceil(tc/kCombLanes) + log2(kCombLanes) additions deep instead of tc - 1).
 // WARP = true: a small grid of warps strides over the keys and folds buckets with more than 32 partials.
 static constexpr int kCombLanes = 8;
+// warp_min: buckets with more partials than this go to the WARP form.  32 when most buckets are cut (the per-thread
+// chains are what the machine is filled with); 4 when cut buckets are the exception (skewed digits, e.g. a top window
+// with one or two scalar bits: a 32-partial chain on one thread would be 0.4 ms of latency).
 template <bool WARP, bool SUB>
 __global__ void __launch_bounds__(128) k_bucket_combine(uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
-                                                        size_t nkeys) {
+                                                        size_t nkeys, uint32_t warp_min) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (WARP) {
         // rare case (adversarial scalar distributions): each warp scans 32 keys per step with coalesced loads and
@@ -486,7 +504,7 @@ __global__ void __launch_bounds__(128) k_bucket_combine(uint8_t* __restrict__ pa
         for (size_t key0 = (gid >> 5) * 32; key0 < nkeys; key0 += nwarps * 32) {
             size_t key = key0 + lane;
             uint32_t my0 = key < nkeys ? task_base[key] : 0, my1 = key < nkeys ? task_base[key + 1] : 0;
-            unsigned big = __ballot_sync(0xffffffffu, my1 - my0 > 32);
+            unsigned big = __ballot_sync(0xffffffffu, my1 - my0 > warp_min);
             while (big) {
                 int src = __ffs(big) - 1;
                 big &= big - 1;
@@ -508,7 +526,7 @@ __global__ void __launch_bounds__(128) k_bucket_combine(uint8_t* __restrict__ pa
         uint32_t s0 = 0, s1 = 0;
         if (key < nkeys) { s0 = task_base[key]; s1 = task_base[key + 1]; }
         const uint32_t tc = s1 - s0;
-        const bool live = tc >= 2 && tc <= 32;
+        const bool live = tc >= 2 && tc <= warp_min;
         // a warp none of whose buckets was cut has nothing to do
         if (!__any_sync(0xffffffffu, live)) return;
         xyzz_t acc = xyzz_t::inf();
@@ -526,7 +544,7 @@ __global__ void __launch_bounds__(128) k_bucket_combine(uint8_t* __restrict__ pa
     if (key >= nkeys) return;
     uint32_t s0 = task_base[key], s1 = task_base[key + 1];
     uint32_t tc = s1 - s0;
-    if (tc < 2 || tc > 32) return;
+    if (tc < 2 || tc > warp_min) return;
     xyzz_t acc = load_xyzz(partials + (size_t)s0 * 192);
     for (uint32_t s = s0 + 1; s < s1; s++) {
         xyzz_t part = load_xyzz(partials + (size_t)s * 192);
@@ -548,23 +566,25 @@ struct AxisPlan {
 //      T_hi = sum_lo B_(hi,lo),   R_hi = sum_lo (2^kf - 1 - lo) B_(hi,lo)   (an ascending running sum: acc += run; run += B)
 // so the T_hi go through the 15-bit reduce unchanged and the R_hi only need a plain sum.  This is the reference's
 // p1_integrate_buckets (kzg/src/msm/tiling_pippenger_ops.rs:21-45) applied per segment instead of over the whole set.
+// The additions go through the out-of-line multiplier (namespace cl): the kernel is two point additions in a short loop,
+// ~4 KiB of code instead of ~90 KiB -- with one or two warps per scheduler instruction fetch is exposed latency.
 __global__ void __launch_bounds__(128) k_segment_fold(const uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
                                                       size_t nseg, int kf, uint8_t* __restrict__ seg_t, uint8_t* __restrict__ seg_r) {
     size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseg) return;
     const size_t key0 = s << kf;
-    xyzz_t run = xyzz_t::inf(), acc = xyzz_t::inf();
+    cl::xyzz_t run = cl::xyzz_t::inf(), acc = cl::xyzz_t::inf();
 #pragma unroll 1
     for (int lo = 0; lo < (1 << kf); lo++) {
-        xyzz_add(acc, run);
+        cl::xyzz_add(acc, run);
         uint32_t s0 = task_base[key0 + lo];
         if (task_base[key0 + lo + 1] > s0) {
-            xyzz_t part = load_xyzz(partials + (size_t)s0 * 192);
-            xyzz_add(run, part);
+            cl::xyzz_t part = cl::load_xyzz(partials + (size_t)s0 * 192);
+            cl::xyzz_add(run, part);
         }
     }
-    store_xyzz(seg_t + s * 192, run);
-    store_xyzz(seg_r + s * 192, acc);
+    cl::store_xyzz(seg_t + s * 192, run);
+    cl::store_xyzz(seg_r + s * 192, acc);
 }
 // identity slot map for point arrays that have exactly one slot per key (the folded segments)
 __global__ void k_iota(uint32_t* __restrict__ out, size_t n) {
@@ -588,7 +608,7 @@ __global__ void __launch_bounds__(kMargThreads) k_marginals(const uint8_t* __res
         // 5-bit digit over the second point array (k_group_finish adds them up)
         partials = partials_r;
         marg = marg_r;
-        a = 0; wa = 5; sa = 0;
+        a = 0; wa = nb >= 32 ? 5 : 0; sa = 0;
     } else {
         wa = ap.w[a]; sa = ap.sh[a];
     }
@@ -627,10 +647,19 @@ static constexpr int kMargSerial = 8;  // buckets summed serially per lane befor
 // additions with the point at infinity.  S = 2^log_s lanes sum count/S buckets each, then a
 // log_s-step shuffle tree inside the S-lane group.
 __global__ void __launch_bounds__(128, 3) k_marginals_sub(const uint8_t* __restrict__ partials, const uint32_t* __restrict__ task_base,
-                                                       int nb, AxisPlan ap, size_t groups, uint8_t* __restrict__ marg) {
+                                                       int nb, AxisPlan ap, size_t groups, uint8_t* __restrict__ marg,
+                                                       const uint8_t* __restrict__ partials_r, uint8_t* __restrict__ marg_r) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int a = blockIdx.y;  // one grid row per digit axis: the axes are independent and run concurrently
-    const int wa = ap.w[a], sa = ap.sh[a];
+    int a = blockIdx.y;  // one grid row per digit axis: the axes are independent and run concurrently
+    int wa, sa;
+    if (a == ap.D) {
+        // extra row after a segment fold: plain sum of the R points as the 32 marginals of one 5-bit digit (see k_marginals)
+        partials = partials_r;
+        marg = marg_r;
+        a = 0; wa = nb >= 32 ? 5 : 0; sa = 0;
+    } else {
+        wa = ap.w[a]; sa = ap.sh[a];
+    }
     int log_s = 0;
     while (log_s < 5 && ((nb >> wa) >> log_s) > kMargSerial) log_s++;
     const int S = 1 << log_s;
@@ -836,9 +865,10 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     chunk_sums_ = dev_alloc<uint8_t>(groups_max_ * 3 * 32 * 192);  // marginal sums [group][axis][32]
     group_sums_ = dev_alloc<uint8_t>(groups_max_ * 192);
     pair_base_ = dev_alloc<uint32_t>(keys_max_ + 1);
-    if (cfg_.c - 1 > kReduceBits) {
-        // wide windows: folded segments (T and R point per segment), their identity slot map, marginals of the R sums
-        const size_t nseg = keys_max_ >> (cfg_.c - 1 - kReduceBits);
+    kf_ = std::max(cfg_.c - 1 > kReduceBits ? cfg_.c - 1 - kReduceBits : 0, std::min(cfg_.fold, cfg_.c - 2));
+    if (kf_ > 0) {
+        // folded segments (T and R point per segment), their identity slot map, marginals of the R sums
+        const size_t nseg = keys_max_ >> kf_;
         seg_t_ = dev_alloc<uint8_t>(nseg * 192);
         seg_r_ = dev_alloc<uint8_t>(nseg * 192);
         seg_ident_ = dev_alloc<uint32_t>(nseg + 1);
@@ -1037,13 +1067,14 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     }
     launches++;
     // 6 reduce
+    const uint32_t warp_min = (double)total * W / (double)nkeys <= 0.5 * L ? 4 : 32;
     if (nkeys <= 8192)
-        k_bucket_combine<false, true><<<div_up(nkeys * kCombLanes, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
+        k_bucket_combine<false, true><<<div_up(nkeys * kCombLanes, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys, warp_min);
     else
-        k_bucket_combine<false, false><<<div_up(nkeys, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
-    k_bucket_combine<true, false><<<148 * 4, 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys);
+        k_bucket_combine<false, false><<<div_up(nkeys, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys, warp_min);
+    k_bucket_combine<true, false><<<148 * 4, 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys, warp_min);
     // wide windows: fold segments of 2^kf buckets first; the marginal reduce then sees nbr = 2^15 "buckets" T_hi per group
-    const int kf = c - 1 > kReduceBits ? c - 1 - kReduceBits : 0;
+    const int kf = kf_;
     const int nbr = nb_ >> kf;
     const uint8_t* rpart = (const uint8_t*)partials_;
     const uint32_t* rbase = task_base_;
@@ -1067,18 +1098,20 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
             off += wa;
         }
     }
-    if (!kf && groups * 32 * ap.D >= 2048) {
-        // many groups: lane-efficient sub-warp marginals, one launch per digit axis.  Slots of digit values that do
-        // not exist (v >= 2^w) must read as infinity (all-zero XYZZ).
+    if (groups * 32 * ap.D >= 2048) {
+        // many groups: lane-efficient sub-warp marginals, one grid row per digit axis (plus one for the R points after
+        // a segment fold).  Slots of digit values that do not exist (v >= 2^w) must read as infinity (all-zero XYZZ).
         B200_CUDA_CHECK(cudaMemsetAsync(chunk_sums_, 0, groups * 3 * 32 * 192, st));
+        if (kf) B200_CUDA_CHECK(cudaMemsetAsync(chunk_sums_r_, 0, groups * 3 * 32 * 192, st));
         size_t max_threads = 0;
-        for (int a = 0; a < ap.D; a++) {
+        for (int a = 0; a < ap.D + (kf ? 1 : 0); a++) {
+            const int wa = a < ap.D ? ap.w[a] : (nbr >= 32 ? 5 : 0);
             int log_s = 0;
-            while (log_s < 5 && ((nb_ >> ap.w[a]) >> log_s) > kMargSerial) log_s++;
-            max_threads = std::max(max_threads, (groups << ap.w[a]) << log_s);
+            while (log_s < 5 && ((nbr >> wa) >> log_s) > kMargSerial) log_s++;
+            max_threads = std::max(max_threads, (groups << wa) << log_s);
         }
-        k_marginals_sub<<<dim3(div_up(max_threads, 128), ap.D), 128, 0, st>>>((const uint8_t*)partials_, task_base_, nb_, ap, groups,
-                                                                             (uint8_t*)chunk_sums_);
+        k_marginals_sub<<<dim3(div_up(max_threads, 128), ap.D + (kf ? 1 : 0)), 128, 0, st>>>(
+            rpart, rbase, nbr, ap, groups, (uint8_t*)chunk_sums_, (const uint8_t*)seg_r_, (uint8_t*)chunk_sums_r_);
         launches += 3;
     } else {
         // one CTA per marginal; 256 threads once a marginal covers >= 1024 buckets (shorter serial chains).

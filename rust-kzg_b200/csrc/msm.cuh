@@ -36,6 +36,8 @@ struct MsmConfig {
     size_t n;       // points per scalar vector
     int max_batch;  // scalar vectors per call (FIXED only; VARIABLE uses 1)
     int L;          // max entries per accumulate task
+    int fold = -1;  // bucket-index bits folded by k_segment_fold before the marginal reduce; -1: only what the reduce
+                    // cannot take (c - 1 - 15 bits for windows wider than 16)
     int bases_period = 1;  // FIXED only: the table holds bases_period * n points per row and scalar vector v uses the
                            // bases [(v mod bases_period) * n, +n)  (FK20: 128 rows of 64 points, kzg/src/msm/bgmw.rs:306-380)
 };
@@ -79,6 +81,7 @@ private:
     size_t table_bytes_;
     int launches_ = 0;
     size_t last_nkeys_ = 0;
+    int kf_ = 0;          // segment-fold bits actually used
     bool profiling_ = false;
     static constexpr int kProfSlots = 512;
     cudaEvent_t prof_ev_[2 * kProfSlots] = {};
