@@ -40,6 +40,7 @@ MsmConfig choose_config(size_t n, bool fixed, int max_batch) {
     MsmConfig cfg;
     cfg.c = c;
     cfg.W = (256 + c - 1) / c;
+    cfg.c0 = fixed ? env_int("B200_MSM_C0", 0) : 0;   // narrower window 0 (tests / tuning); must keep c0 + (W-1) c >= 256
     cfg.fixed = fixed;
     cfg.n = n;
     cfg.max_batch = fixed ? max_batch : 1;

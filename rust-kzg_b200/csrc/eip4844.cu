@@ -359,6 +359,7 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
         MsmConfig cfg;
         cfg.c = env_int_local("B200_BLOB_C", 12);
         cfg.fold = env_int_local("B200_BLOB_FOLD", -1);
+        cfg.c0 = env_int_local("B200_BLOB_C0", 0);
         cfg.W = (256 + cfg.c - 1) / cfg.c;
         cfg.fixed = true;
         cfg.n = n;
@@ -372,6 +373,7 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
         MsmConfig cfg_q = cfg;
         cfg_q.c = env_int_local("B200_PROOF_C", 13);
         cfg_q.fold = env_int_local("B200_PROOF_FOLD", 2);
+        cfg_q.c0 = 0;
         cfg_q.W = (256 + cfg_q.c - 1) / cfg_q.c;
         for (Lane& ln : lanes_) {
             ln.msm.reset(new MsmEngine(cfg, aff_brp, false, st));

@@ -25,7 +25,7 @@ static constexpr int kMaxWindow = 22;    // wider windows than kReduceBits + 1 g
 // Same digit set as the reference's Booth recoding (kzg/src/msm/pippenger_utils.rs:251-281): sum digit_j 2^(cj) = s.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalars, size_t n, size_t row_stride, size_t total,
-                                                int c, int W, int nb, int fixed, int mont, uint32_t* __restrict__ ctr,
+                                                int c, int c0, int W, int nb, int fixed, int mont, uint32_t* __restrict__ ctr,
                                                 uint32_t* __restrict__ entries, size_t period, size_t period_n, size_t gid0) {
     size_t gid = gid0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
@@ -36,10 +36,11 @@ __global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalar
 #pragma unroll
     for (int k = 0; k < 8; k++) w[k] = s.v[k];
     w[8] = 0;
-    const uint32_t mask = (1u << c) - 1;
     uint32_t carry = 0;
     for (int j = 0; j < W; j++) {
-        int o = c * j;
+        // window j: cw bits from bit o (window 0 may be narrower than the others, see MsmConfig::c0)
+        const int o = j ? c0 + c * (j - 1) : 0, cw = j ? c : c0;
+        const uint32_t mask = (1u << cw) - 1;
         uint32_t raw = 0;
         if (o < 256) {
             int word = o >> 5, sh = o & 31;
@@ -47,8 +48,8 @@ __global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalar
             raw = (uint32_t)(two >> sh) & mask;
         }
         raw += carry;
-        uint32_t neg = raw > (uint32_t)nb;
-        uint32_t mag = neg ? (1u << c) - raw : raw;
+        uint32_t neg = raw > (1u << (cw - 1));
+        uint32_t mag = neg ? (1u << cw) - raw : raw;
         carry = neg;
         if (mag != 0) {
             size_t group = fixed ? vec : vec * W + j;
@@ -756,14 +757,14 @@ __global__ void __launch_bounds__(32) k_horner(const uint8_t* __restrict__ group
 
 // table rows for FIXED engines: row j = 2^(c*j) * P_i, affine.  One thread per point walks all rows
 // (c doublings in XYZZ, then back to affine with one warp-shared field inversion).  One-time cost at prepare.
-__global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table, size_t n, int W, int c) {
+__global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table, size_t n, int W, int c, int c0) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     if (!live) i = n - 1;
     cc::affine_t p = cc::load_affine(table + i * 96);
     for (int j = 1; j < W; j++) {
         cc::xyzz_t q = cc::affine_to_xyzz(p);
-        for (int k = 0; k < c; k++) cc::xyzz_dbl(q);
+        for (int k = 0; k < (j == 1 ? c0 : c); k++) cc::xyzz_dbl(q);   // row j = 2^(c0 + (j-1) c) * P
         const bool inf = q.is_inf();
         // 1/ZZZ; then 1/ZZ = ZZZ^-2 * ZZ^2  (ZZ^3 = ZZZ^2), as xyzz_to_affine
         cc::fp_t izzz = warp_inverse(inf ? cc::fp_t::one() : q.zzz);
@@ -838,7 +839,9 @@ void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int co
 
 // ---------------------------------------------------------------------------------------------------------------
 MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points, cudaStream_t stream) : cfg_(cfg) {
-    if (cfg_.c < 2 || cfg_.c > kMaxWindow || cfg_.c * cfg_.W < 256) throw CudaError(-1, "MsmEngine: bad window configuration");
+    if (!cfg_.fixed || cfg_.c0 <= 0 || cfg_.c0 > cfg_.c) cfg_.c0 = cfg_.c;
+    if (cfg_.c < 2 || cfg_.c > kMaxWindow || cfg_.c0 + cfg_.c * (cfg_.W - 1) < 256)
+        throw CudaError(-1, "MsmEngine: bad window configuration");
     if (cfg_.L < 1 || cfg_.L > 1024) throw CudaError(-1, "MsmEngine: bad task length");
     if (!cfg_.fixed) cfg_.max_batch = 1;
     if (!cfg_.fixed || cfg_.bases_period < 1) cfg_.bases_period = 1;
@@ -892,7 +895,7 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     if (points) {
         B200_CUDA_CHECK(cudaMemcpyAsync(table_, points, table_points * 96, host_points ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
         if (cfg_.fixed && cfg_.W > 1) {
-            k_build_rows<<<div_up(table_points, 128), 128, 0, stream>>>((uint8_t*)table_, table_points, cfg_.W, cfg_.c);
+            k_build_rows<<<div_up(table_points, 128), 128, 0, stream>>>((uint8_t*)table_, table_points, cfg_.W, cfg_.c, cfg_.c0);
             B200_LAUNCH_CHECK();
         }
         B200_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -946,7 +949,7 @@ void MsmEngine::set_points(const void* points_dev, size_t npoints, cudaStream_t 
 void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mont, void* out_dev, cudaStream_t st,
                     const void* scalars_host) {
     if (npoints > cfg_.n || batch < 1 || batch > cfg_.max_batch) throw CudaError(-1, "MsmEngine::run: bad sizes");
-    const int c = cfg_.c, W = cfg_.W;
+    const int c = cfg_.c, W = cfg_.W, c0 = cfg_.c0;
     const size_t groups = cfg_.fixed ? (size_t)batch : (size_t)W;
     const size_t nkeys = groups * nb_;
     const size_t total = (size_t)batch * npoints;
@@ -989,12 +992,12 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
                                             cudaMemcpyHostToDevice, copy_stream_));
             B200_CUDA_CHECK(cudaEventRecord(copy_ev_[k], copy_stream_));
             B200_CUDA_CHECK(cudaStreamWaitEvent(st, copy_ev_[k], 0));
-            k_digits<false><<<div_up(hi - lo, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, hi, c, W, nb_, cfg_.fixed,
+            k_digits<false><<<div_up(hi - lo, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, hi, c, c0, W, nb_, cfg_.fixed,
                                                                  mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n, lo);
             launches++;
         }
     } else {
-        k_digits<false><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, W, nb_,
+        k_digits<false><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, c0, W, nb_,
                                                             cfg_.fixed, mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n, 0);
         launches++;
     }
@@ -1002,7 +1005,7 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     launches += scan_exclusive(counts_, nkeys, 0, offsets_, cursor_, scan_tmp_, st);
     launches += scan_exclusive(counts_, nkeys, (uint32_t)L, task_base_, nullptr, scan_tmp_, st);
     // 3 scatter
-    k_digits<true><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, W, nb_,
+    k_digits<true><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, c0, W, nb_,
                                                        cfg_.fixed, mont, cursor_, entries_, (size_t)cfg_.bases_period, cfg_.n, 0);
     launches++;
     // 5a batch-affine rounds (FIXED engines with room for the two point buffers): halve every bucket's list R times

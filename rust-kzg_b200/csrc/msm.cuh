@@ -36,6 +36,9 @@ struct MsmConfig {
     size_t n;       // points per scalar vector
     int max_batch;  // scalar vectors per call (FIXED only; VARIABLE uses 1)
     int L;          // max entries per accumulate task
+    int c0 = 0;     // FIXED only: width of window 0 when it differs from c (0 = c); windows j >= 1 start at bit c0 + (j-1)*c.
+                    // With c0 = 256 - (W-1)*c the TOP window ends at bit 256 and is full: inputs with zero top bits (blob
+                    // elements < 2^248) then still spread its digits over many buckets instead of one or two.
     int fold = -1;  // bucket-index bits folded by k_segment_fold before the marginal reduce; -1: only what the reduce
                     // cannot take (c - 1 - 15 bits for windows wider than 16)
     int bases_period = 1;  // FIXED only: the table holds bases_period * n points per row and scalar vector v uses the

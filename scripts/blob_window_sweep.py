@@ -1,5 +1,6 @@
 """Window width / segment-fold sweep of the 64-blob commitment and proof MSMs (B200_BLOB_C, B200_BLOB_FOLD); every
 configuration is checked byte-for-byte against the first one and against the oracle on three blobs.
+Arguments: commit_c:commit_fold[:proof_c:proof_fold] (B200_PROOF_C, B200_PROOF_FOLD; default 13:2).
 Run under gpurun:  python scripts/blob_window_sweep.py 12:-1 12:2 13:2 13:3 14:3"""
 import json
 import os
@@ -43,9 +44,14 @@ def main():
     exp_c = {i: K.blob_to_kzg_commitment(blobs[i].tobytes(), osettings) for i in (0, 17, 63)}
     ref = None
     res = {}
-    for c, fold in cfgs:
+    for cfg in cfgs:
+        c, fold = cfg[0], cfg[1]
+        pc, pfold = (cfg[2], cfg[3]) if len(cfg) >= 4 else (13, 2)     # c:fold[:proof_c:proof_fold]
         os.environ["B200_BLOB_C"] = str(c)
         os.environ["B200_BLOB_FOLD"] = str(fold)
+        os.environ["B200_PROOF_C"] = str(pc)
+        os.environ["B200_PROOF_FOLD"] = str(pfold)
+        os.environ["B200_BLOB_C0"] = str(cfg[4] if len(cfg) >= 5 else 0)                # ...[:commit_c0]
         ts = B.KZGSettings.load_trusted_setup_file()
         ms_c = timed(lambda: ts.blob_to_kzg_commitment_device(d_out.data_ptr(), d_blobs.data_ptr(), nb, d_st.data_ptr(), 0))
         comm = d_out.cpu().numpy().copy()
@@ -56,8 +62,9 @@ def main():
         if ref is None:
             ref = (comm, proofs)
         ok = ok and np.array_equal(comm, ref[0]) and np.array_equal(proofs, ref[1])
-        res["%d:%d" % (c, fold)] = {"commit_ms": ms_c, "proof_ms": ms_p, "parity_ok": bool(ok)}
-        print(c, fold, res["%d:%d" % (c, fold)], flush=True)
+        key = ":".join(str(x) for x in cfg)
+        res[key] = {"commit_ms": ms_c, "proof_ms": ms_p, "parity_ok": bool(ok)}
+        print(key, res[key], flush=True)
         ts.free()
         torch.cuda.empty_cache()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

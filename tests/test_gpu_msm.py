@@ -214,3 +214,20 @@ def test_wide_windows_segment_fold(B, K, lagrange_affine, c):
         pts2, sc2 = np.concatenate([pts, pts]), np.concatenate([sc, sc])
         got = _with_env("B200_MSM_VC", c, lambda: B.mult_pippenger(pts2, sc2))
         _same(K, got, K.p1_add(exp, exp))
+
+
+@pytest.mark.parametrize("c,c0", [(13, 9), (15, 1), (20, 16), (12, 4)])
+def test_narrow_first_window(B, K, lagrange_affine, c, c0):
+    """window 0 of c0 bits, the others of c bits, so that the top window ends exactly at bit 256 (MsmConfig::c0): same
+    digits-times-table-rows identity as uniform windows, checked on random, blob-like (< 2^248) and edge scalars."""
+    n = 4096
+    rng = np.random.default_rng(200 + c)
+    h = _with_env("B200_MSM_C", c, lambda: _with_env("B200_MSM_C0", c0, lambda: B.PreparedMsm(lagrange_affine)))
+    assert h.info()["c"] == c
+    cases = {"random": rand_ints(rng, n, R_MOD), "blob-like": rand_ints(rng, n, 1 << 248), "r-1": [R_MOD - 1] * n,
+             "ones": [1] * n, "low-window-edge": [((1 << (c0 - 1)) + (1 << 255) % R_MOD) % R_MOD] * n if c0 > 1 else [3] * n,
+             "zeros": [0] * n}
+    for name, ints in cases.items():
+        sc = K.fr_from_ints(ints)
+        assert K.p1_compress(h.mult(sc)) == K.p1_compress(K.msm_affine(lagrange_affine, sc, nthreads=8)), name
+    h.close()
