@@ -72,6 +72,9 @@ B200_API RustError b200_g1_sum_device(void *out_dev, const void *points_dev, siz
 
 /* introspection (bench / tests): window bits, windows, table bytes, kernel launches of the last run */
 B200_API void b200_msm_info(void *msm, int *c, int *W, size_t *table_bytes, int *launches);
+/* the window plan a handle for `npoints` bases would get (host-only, no device needed): window bits c, width of window 0,
+ * number of windows W (c0 + (W-1) c >= 256), bucket-index bits folded by segments ahead of the reduce (c > 16) */
+B200_API void b200_msm_plan(size_t npoints, int fixed, int *c, int *c0, int *W, int *fold_bits);
 /* work of the last run on this handle: entries = non-zero digits sorted into buckets, tasks = accumulate tasks; the
  * accumulate kernel did  entries - tasks  mixed additions (a task's first point is a load).  Synchronises the handle's
  * stream. */

@@ -102,6 +102,15 @@ void* prepare_msm(const blst_p1_affine points[], size_t npoints) {
 
 void b200_free_msm(void* msm) { delete static_cast<MsmHandle*>(msm); }
 
+void b200_msm_plan(size_t npoints, int fixed, int* c, int* c0, int* W, int* fold_bits) {
+    MsmConfig cfg = choose_config(npoints ? npoints : 1, fixed != 0, 1);
+    const int w0 = fixed && cfg.c0 > 0 && cfg.c0 <= cfg.c ? cfg.c0 : cfg.c;
+    if (c) *c = cfg.c;
+    if (c0) *c0 = w0;
+    if (W) *W = cfg.W;
+    if (fold_bits) *fold_bits = cfg.c > 16 ? cfg.c - 16 : 0;   // what the 15-bit marginal reduce cannot take (msm.cu)
+}
+
 RustError b200_msm_prepared_device(void* msm, void* out_dev, size_t npoints, const void* scalars_dev, int batch,
                                    void* stream) {
     return guarded([&] {

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["PreparedMsm", "g1_lincomb", "mult_pippenger", "microbench_int", "g1_sum_device"]
+__all__ = ["PreparedMsm", "g1_lincomb", "mult_pippenger", "microbench_int", "g1_sum_device", "msm_plan"]
 
 
 def _L():
@@ -27,6 +27,13 @@ def _p(a):
 def _u64(a, width):
     a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, width)
     return a
+
+
+def msm_plan(npoints, fixed=True):
+    """window plan of an MSM over `npoints` bases (host-only): {"c", "c0", "W", "fold_bits"}"""
+    c, c0, w, f = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _L().b200_msm_plan(npoints, int(fixed), C.byref(c), C.byref(c0), C.byref(w), C.byref(f))
+    return {"c": c.value, "c0": c0.value, "W": w.value, "fold_bits": f.value}
 
 
 class PreparedMsm:
