@@ -20,7 +20,9 @@
 //   3 scatter        counting-sort the (point index, sign) entries by key                          [HBM/atomics]
 //   4 tasks          cut every bucket into tasks of <= L entries, counting-sort tasks by length    [tiny]
 //   5 accumulate     one thread per task: XYZZ += affine over its entries  (the dominant kernel)   [integer pipe]
-//   6 reduce         per group: sum_b b * B_b  (chunked running sums, scalar offset, tree sum)     [latency]
+//   6 reduce         per group: sum_b b * B_b.  Windows wider than 16 bits (or MsmConfig::fold): running sums over
+//                    segments of 2^k buckets first (k_segment_fold); then digit-marginal tree sums over <= 2^15
+//                    (segment) sums and a warp suffix scan per digit                               [latency]
 //   7 (VARIABLE)     Horner over the W window sums
 #pragma once
 #include <cuda_runtime.h>
