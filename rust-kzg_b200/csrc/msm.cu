@@ -20,9 +20,10 @@ static constexpr int kMaxWindow = 22;    // wider windows than kReduceBits + 1 g
 // ---------------------------------------------------------------------------------------------------------------
 // 1 / 3: signed digits of every scalar; histogram (SCATTER = false) or counting-sort scatter (SCATTER = true).
 // Scalars are read with two 128-bit loads per thread, consecutive threads read consecutive scalars (coalesced).
-// The digit of window j is  raw = bits[c*j, c*j+c) + carry;  raw > 2^(c-1) becomes raw - 2^c with carry 1, so
-// |digit| <= 2^(c-1) and bucket |digit| - 1 of 2^(c-1) buckets; c*W >= 256 > 255 bits guarantees no final carry.
-// Same digit set as the reference's Booth recoding (kzg/src/msm/pippenger_utils.rs:251-281): sum digit_j 2^(cj) = s.
+// The digit of window j is  raw = bits[o_j, o_j+cw) + carry  (o_j = c0 + c*(j-1), cw = c; window 0: o = 0, cw = c0 <= c);
+// raw > 2^(cw-1) becomes raw - 2^cw with carry 1, so |digit| <= 2^(c-1): bucket |digit| - 1 of 2^(c-1) buckets; windows
+// reaching bit 256 (c0 + c*(W-1) >= 256, s < r < 0.91 * 2^255) leave no final carry.  Same digit set as the reference's
+// Booth recoding (kzg/src/msm/pippenger_utils.rs:251-281): sum_j digit_j 2^(o_j) = s (tests/test_msm_plan_cpu.py).
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalars, size_t n, size_t row_stride, size_t total,
                                                 int c, int c0, int W, int nb, int fixed, int mont, uint32_t* __restrict__ ctr,
