@@ -309,7 +309,10 @@ def main():
         "data": "synthetic",
         "config": {"workload": "MSM 2^%d random Fr scalars x EIP-4844 trusted-setup G1 points (4096 Lagrange points tiled), "
                                "per GPU; prepared fixed-base table resident in HBM" % LOG_N,
-                   "points_per_s": value / ADDS_PER_TERM, "window_bits": info["c"], "windows": info["W"],
+                   "points_per_s": value / ADDS_PER_TERM,
+                   "adds_unit": "16 canonical bucket additions per term (BASELINE.md section 2) for every arm, whatever "
+                                "window width the engine uses; int_roofline counts the additions actually performed",
+                   "window_bits": info["c"], "windows": info["W"],
                    "table_bytes": info["table_bytes"], "seed": SEED, "prng": "numpy PCG64",
                    "l2": "inputs larger than L2: %d MiB scalars + %.1f GiB table per step" % (n * 32 >> 20, info["table_bytes"] / 2 ** 30),
                    "parity": "compressed result == folded-scalar oracle (checked before timing)",
