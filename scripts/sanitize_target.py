@@ -1,4 +1,5 @@
-"""Small end-to-end pass over the verification / EIP-7594 kernels for compute-sanitizer (memcheck / racecheck)."""
+"""Small end-to-end pass over the verification / EIP-7594 kernels for compute-sanitizer (memcheck / racecheck).
+Modes: (none) blob pipeline + NTT; `cells` adds EIP-7594; `widemsm` adds the wide-window MSM kernels."""
 import os
 import sys
 
@@ -24,6 +25,19 @@ if len(sys.argv) > 1 and sys.argv[1] == "cells":
     assert rc == cells and rp == cproofs
     assert ts.verify_cell_kzg_proof_batch([comm[0].tobytes()] * 5, [0, 7, 7, 100, 127], [cells[i] for i in (0, 7, 7, 100, 127)],
                                           [cproofs[i] for i in (0, 7, 7, 100, 127)])
+if len(sys.argv) > 1 and sys.argv[1] == "widemsm":
+    # the wide-window kernels (k_segment_fold, the R row of k_marginals, mixed window widths) on a small problem
+    from oracle import c_oracle as K
+    text = open(os.path.join(os.path.dirname(B.LIB_PATH), "data", "trusted_setup.txt")).read()
+    L = K.p1s_to_affine(K.KZGSettings(text).g1_lagrange_brp)
+    sc = rng.integers(0, 1 << 62, size=(4096, 4), dtype=np.uint64)
+    exp = K.p1_compress(K.msm_affine(L, sc))
+    for c, c0 in ((20, 0), (17, 0), (13, 9)):
+        os.environ["B200_MSM_C"], os.environ["B200_MSM_C0"] = str(c), str(c0)
+        h = B.PreparedMsm(L)
+        assert K.p1_compress(h.mult(sc)) == exp, (c, c0)
+        h.close()
+    del os.environ["B200_MSM_C"], os.environ["B200_MSM_C0"]
 fs = B.FFTSettings(13)
 a = rng.integers(0, 1 << 62, size=(8192, 4), dtype=np.uint64)
 assert np.array_equal(fs.fft_fr(fs.fft_fr(a, False), True), a)
