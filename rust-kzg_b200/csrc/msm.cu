@@ -13,9 +13,9 @@
 namespace b200 {
 
 static constexpr int kMinTaskLen = 4;     // shortest accumulate task (entries) for latency-bound calls
-static constexpr int kAccThreads = 128;
+static constexpr int kAccThreads = 128;  // accumulate CTA: 4 warps, one per SM sub-partition
 static constexpr int kReduceBits = 15;   // bucket-index bits the marginal-sum reduce handles (three 5-bit digits)
-static constexpr int kMaxWindow = 22;    // wider windows than kReduceBits + 1 go through k_segment_fold first  // accumulate CTA: 4 warps, one per SM sub-partition
+static constexpr int kMaxWindow = 22;    // wider windows than kReduceBits + 1 go through k_segment_fold first
 
 // ---------------------------------------------------------------------------------------------------------------
 // 1 / 3: signed digits of every scalar; histogram (SCATTER = false) or counting-sort scatter (SCATTER = true).
