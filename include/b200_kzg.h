@@ -127,8 +127,8 @@ typedef struct {
     blst_p1 *g1_values_monomial;      /* 4096 */
     blst_p1 *g1_values_lagrange_brp;  /* 4096 */
     blst_p2 *g2_values_monomial;      /* 65 */
-    blst_p1 **x_ext_fft_columns;      /* NULL (FK20 data, out of scope) */
-    blst_p1_affine **tables;          /* NULL */
+    blst_p1 **x_ext_fft_columns;      /* [128][64] FK20 Toeplitz columns (blst/src/types/kzg_settings.rs:84-101), one heap row each */
+    blst_p1_affine **tables;          /* NULL: the reference's CPU precomputation; this backend's tables live in HBM */
     size_t wbits;
     size_t scratch_size;
 } KZGSettings;

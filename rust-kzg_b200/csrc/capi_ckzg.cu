@@ -6,6 +6,8 @@
 // side registry keyed by the g1_values_lagrange_brp pointer (the reference keys its PrecomputationTableManager the
 // same way, kzg/src/eip_4844.rs:105-145) -- but instead of rebuilding an FsKZGSettings on every call
 // (blst/src/types/kzg_settings.rs:314-437) the resident context is looked up.
+#include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -17,6 +19,7 @@
 
 #include "../../include/b200_kzg.h"
 #include "capi_common.cuh"
+#include "coalesce.cuh"
 #include "eip4844.cuh"
 #include "sha256.cpp.inc"
 #include "util.cuh"
@@ -31,6 +34,10 @@ constexpr size_t kG1 = 4096, kG2 = 65;
 struct Stage {
     cudaStream_t stream = nullptr, side = nullptr;
     cudaEvent_t ev_in = nullptr, ev_side = nullptr;
+    // end of the last enqueue a device-pointer entry point left on a CALLER's stream: whoever uses this lane's
+    // workspace next makes its stream wait on it first (the workspace is shared, the streams are not)
+    cudaEvent_t ev_busy = nullptr;
+    bool busy = false;
     uint8_t *d_blobs = nullptr, *d_z = nullptr, *d_comm = nullptr, *d_out48 = nullptr, *d_y32 = nullptr;
     int *d_status = nullptr, *d_status2 = nullptr;
     uint8_t* h_small = nullptr;  // pinned: [48 * mb out][32 * mb y][int * mb][int * mb][32 * mb z]
@@ -41,6 +48,7 @@ struct Stage {
         B200_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
         B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_busy, cudaEventDisableTiming));
         d_blobs = dev_alloc<uint8_t>((size_t)mb * kBytesPerBlob);
         d_z = dev_alloc<uint8_t>((size_t)mb * 32);
         d_comm = dev_alloc<uint8_t>((size_t)mb * 48);
@@ -55,6 +63,7 @@ struct Stage {
         if (h_small) cudaFreeHost(h_small);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_side) cudaEventDestroy(ev_side);
+        if (ev_busy) cudaEventDestroy(ev_busy);
         if (stream) cudaStreamDestroy(stream);
         if (side) cudaStreamDestroy(side);
     }
@@ -65,8 +74,64 @@ struct Stage {
     uint8_t* h_z() { return h_small + 88 * (size_t)mb; }
 };
 
+// Ownership of the device lanes (Stage + MSM engines + workspace each).  A coalesced batch of single-blob calls takes ANY
+// free lane; everything else (explicit batches, cells / FK20, verification, recovery) takes ALL of them.  A pending
+// take-all blocks new single takers, so it cannot starve.
+struct LanePool {
+    static constexpr unsigned kFull = (1u << KzgSettingsDev::kLanes) - 1;
+    std::mutex m;
+    std::condition_variable cv;
+    unsigned free_mask = kFull;
+    int all_waiters = 0;
+    int acquire_any() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return free_mask != 0 && all_waiters == 0; });
+        int lane = __builtin_ctz(free_mask);
+        free_mask &= ~(1u << lane);
+        return lane;
+    }
+    void acquire_all() {
+        std::unique_lock<std::mutex> lk(m);
+        all_waiters++;
+        cv.wait(lk, [&] { return free_mask == kFull; });
+        all_waiters--;
+        free_mask = 0;
+    }
+    void release(int lane) {
+        { std::lock_guard<std::mutex> lk(m); free_mask |= 1u << lane; }
+        cv.notify_all();
+    }
+    void release_all() {
+        { std::lock_guard<std::mutex> lk(m); free_mask = kFull; }
+        cv.notify_all();
+    }
+};
+
+// ---- request coalescer (coalesce.cuh): one open batch per single-blob entry point ------------------------------------
+enum CoKind { CO_COMMIT = 0, CO_PROOF = 1, CO_BLOB_PROOF = 2, CO_KINDS = 3 };
+struct CoBatch : CoBatchBase {
+    uint8_t* h_in = nullptr;   // pinned: [mb blobs][mb x 48 commitments][mb x 32 z]
+    uint8_t* h_out = nullptr;  // pinned: [mb x 48 out][mb x 32 y][mb int status][mb int status2]
+    int mb = 0;
+    uint8_t* blob(int i) { return h_in + (size_t)i * kBytesPerBlob; }
+    uint8_t* comm(int i) { return h_in + (size_t)mb * kBytesPerBlob + 48 * (size_t)i; }
+    uint8_t* z(int i) { return h_in + (size_t)mb * (kBytesPerBlob + 48) + 32 * (size_t)i; }
+    uint8_t* out48(int i) { return h_out + 48 * (size_t)i; }
+    uint8_t* y32(int i) { return h_out + 48 * (size_t)mb + 32 * (size_t)i; }
+    int* status() { return reinterpret_cast<int*>(h_out + 80 * (size_t)mb); }
+    int* status2() { return status() + mb; }
+    ~CoBatch() {
+        if (h_in) cudaFreeHost(h_in);
+        if (h_out) cudaFreeHost(h_out);
+    }
+};
+typedef CoQueue<CoBatch, CO_KINDS> Coalescer;
+
 struct KzgCtx {
-    std::mutex mu;
+    LanePool pool;
+    Coalescer co;
+    int device = 0;            // CUDA device the context lives on: every entry point switches to it (DeviceScope)
+    int co_cap = 0;            // most single-blob requests packed into one launch sequence (<= max_batch)
     std::unique_ptr<KzgSettingsDev> dev;
     int max_batch = 0;
     Stage stage[KzgSettingsDev::kLanes];
@@ -113,7 +178,54 @@ struct KzgCtx {
     }
 };
 
-// Run `n` items in chunks of at most `cap`, alternating between the two lanes: chunk k+1 is enqueued (copies, host
+// Before a lane's workspace is used on `user` (nullptr: the lane's own streams), order that stream after whatever a
+// device-pointer entry point last enqueued against the same workspace on some caller's stream.
+void lane_enter(Stage& g, cudaStream_t user) {
+    if (!g.busy) return;
+    if (user) {
+        B200_CUDA_CHECK(cudaStreamWaitEvent(user, g.ev_busy, 0));
+    } else {
+        B200_CUDA_CHECK(cudaStreamWaitEvent(g.stream, g.ev_busy, 0));
+        B200_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.ev_busy, 0));
+    }
+}
+// ... and after such an enqueue, remember where it ends
+void lane_leave_async(Stage& g, cudaStream_t user) {
+    B200_CUDA_CHECK(cudaEventRecord(g.ev_busy, user));
+    g.busy = true;
+}
+struct AllLanes {   // exclusive use of the context: all lanes, on the context's device
+    KzgCtx& c;
+    DeviceScope ds;
+    explicit AllLanes(KzgCtx& ctx) : c(ctx), ds(ctx.device) {
+        c.pool.acquire_all();
+        try {
+            for (Stage& g : c.stage) lane_enter(g, nullptr);
+        } catch (...) {
+            c.pool.release_all();
+            throw;
+        }
+    }
+    ~AllLanes() { c.pool.release_all(); }
+    AllLanes(const AllLanes&) = delete;
+};
+struct OneLane {    // one lane (any), for a coalesced batch or a device-pointer call
+    KzgCtx& c;
+    DeviceScope ds;
+    int lane;
+    explicit OneLane(KzgCtx& ctx, cudaStream_t user = nullptr) : c(ctx), ds(ctx.device), lane(ctx.pool.acquire_any()) {
+        try {
+            lane_enter(c.stage[lane], user);
+        } catch (...) {
+            c.pool.release(lane);
+            throw;
+        }
+    }
+    ~OneLane() { c.pool.release(lane); }
+    OneLane(const OneLane&) = delete;
+};
+
+// Run `n` items in chunks of at most `cap`, alternating between the lanes: chunk k+1 is enqueued (copies, host
 // hashing, kernels) while chunk k is still executing, and a lane is drained only when it is needed again.
 // launch(lane, off, m) enqueues a chunk; finish(lane, off, m) runs after that lane's stream has been synchronised.
 template <class Launch, class Finish>
@@ -156,12 +268,17 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
                     const uint8_t* g2_monomial, size_t n_g2) {
     zero_settings(out);
     // load_trusted_setup_rust's length checks (kzg/src/eip_4844.rs:1037-1049)
-    if (n_mono / 48 != kG1 || n_lag / 48 != kG1 || n_g2 / 96 != kG2) return C_KZG_BADARGS;
+    // (chunks(48) + from_bytes: a trailing partial point fails to decode, so the byte counts must be exact)
+    if (n_mono != kG1 * 48 || n_lag != kG1 * 48 || n_g2 != kG2 * 96) return C_KZG_BADARGS;
+    if (!g1_monomial || !g1_lagrange || !g2_monomial) return C_KZG_BADARGS;
     std::shared_ptr<KzgCtx> ctx(new KzgCtx());
     try {
         require_device();
+        B200_CUDA_CHECK(cudaGetDevice(&ctx->device));
         ctx->max_batch = env_int("B200_KZG_MAX_BATCH", 64);
         if (ctx->max_batch < 1) ctx->max_batch = 1;
+        ctx->co_cap = std::max(1, std::min(ctx->max_batch, env_int("B200_KZG_COALESCE", ctx->max_batch)));
+        ctx->co.max_batches = KzgSettingsDev::kLanes + 2;   // one per lane in flight + the ones filling
         const int mb = ctx->max_batch;
         for (Stage& st : ctx->stage) st.init(mb);
         ctx->stream = ctx->stage[0].stream;
@@ -212,8 +329,36 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
         return C_KZG_ERROR;
     }
     for (size_t i = 0; i <= w; i++) out->reverse_roots_of_unity[i] = out->roots_of_unity[w - i];
-    out->x_ext_fft_columns = nullptr;  // FK20 data: outside this backend's path
-    out->tables = nullptr;
+    // x_ext_fft_columns[128][64], one heap row per column like kzg_settings_to_c (blst/src/eip_4844.rs:104-131): the
+    // reference's TryFrom<&CKZGSettings> (blst/src/types/kzg_settings.rs:398-417) walks all 128 row pointers
+    {
+        const size_t rows = 128, cols = 64;
+        out->x_ext_fft_columns = (blst_p1**)calloc(rows, sizeof(blst_p1*));
+        bool got = out->x_ext_fft_columns != nullptr;
+        for (size_t r = 0; got && r < rows; r++) got = (out->x_ext_fft_columns[r] = (blst_p1*)malloc(cols * sizeof(blst_p1))) != nullptr;
+        if (!got) {
+            free_trusted_setup(out);
+            return C_KZG_MALLOC;
+        }
+        uint8_t* d_cols = nullptr;
+        bool copied = false;
+        try {
+            d_cols = dev_alloc<uint8_t>(rows * cols * 144);
+            ctx->dev->x_ext_fft_columns(d_cols, ctx->stream);
+            copied = true;
+            for (size_t r = 0; copied && r < rows; r++)
+                copied = cudaMemcpy(out->x_ext_fft_columns[r], d_cols + r * cols * 144, cols * 144, cudaMemcpyDeviceToHost) == cudaSuccess;
+        } catch (const std::exception& e) {
+            fprintf(stderr, "b200kzg: load_trusted_setup failed: %s\n", e.what());
+            copied = false;
+        }
+        cudaFree(d_cols);
+        if (!copied) {
+            free_trusted_setup(out);
+            return C_KZG_ERROR;
+        }
+    }
+    out->tables = nullptr;   // the reference's CPU precomputation (bgmw / wbits): this backend's table lives in HBM
     out->wbits = 0;
     out->scratch_size = 0;
     std::lock_guard<std::mutex> lk(g_reg_mu);
@@ -300,6 +445,108 @@ bool any_set(const int* st, int n) {
     return false;
 }
 
+// ---- enqueue one chunk of m <= max_batch items on a lane (host pointers in, pinned host pointers out) ---------------
+// blob_to_kzg_commitment (blst/src/eip_4844.rs:163-175)
+void enqueue_commit(KzgCtx& ctx, int lane, const uint8_t* blobs, int m, uint8_t* h_out48, int* h_st) {
+    Stage& g = ctx.stage[lane];
+    B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
+    ctx.dev->blob_to_commitments(g.d_blobs, m, g.d_out48, g.d_status, g.stream, lane);
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_out48, g.d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, g.stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_st, g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+}
+// compute_kzg_proof (blst/src/eip_4844.rs:476-496)
+void enqueue_proof(KzgCtx& ctx, int lane, const uint8_t* blobs, const uint8_t* zs, int m, uint8_t* h_out48, uint8_t* h_y32, int* h_st) {
+    Stage& g = ctx.stage[lane];
+    B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(g.d_z, zs, (size_t)m * 32, cudaMemcpyHostToDevice, g.stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
+    ctx.dev->compute_proofs(g.d_blobs, g.d_z, 0, m, g.d_out48, g.d_y32, g.d_status, g.stream, lane);
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_out48, g.d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, g.stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_y32, g.d_y32, (size_t)m * 32, cudaMemcpyDeviceToHost, g.stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_st, g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+}
+// compute_blob_kzg_proof (blst/src/eip_4844.rs:274-291).  z_hashed: the m Fiat-Shamir hashes when the callers have
+// already computed them (pinned), else nullptr: hash here, on the host, while the blobs cross PCIe.
+void enqueue_blob_proof(KzgCtx& ctx, int lane, const uint8_t* blobs, const uint8_t* commitments, const uint8_t* z_hashed, int m,
+                        uint8_t* h_out48, int* h_st, int* h_st2) {
+    Stage& g = ctx.stage[lane];
+    // commitments first: their validation (decode + subgroup test) runs on the side stream under everything else
+    B200_CUDA_CHECK(cudaMemcpyAsync(g.d_comm, commitments, (size_t)m * 48, cudaMemcpyHostToDevice, g.stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(g.d_status2, 0, m * sizeof(int), g.stream));
+    B200_CUDA_CHECK(cudaEventRecord(g.ev_in, g.stream));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.ev_in, 0));
+    ctx.dev->validate_commitments(g.d_comm, m, g.d_status2, g.side);
+    B200_CUDA_CHECK(cudaEventRecord(g.ev_side, g.side));
+    B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
+    if (!z_hashed) {
+        // the hash chain runs on the host while the blobs cross PCIe (and the other lanes compute)
+        challenge_hash_many(g.h_z(), blobs, commitments, m);
+        z_hashed = g.h_z();
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(g.d_z, z_hashed, (size_t)m * 32, cudaMemcpyHostToDevice, g.stream));
+    ctx.dev->compute_proofs(g.d_blobs, g.d_z, 1, m, g.d_out48, nullptr, g.d_status, g.stream, lane);
+    B200_CUDA_CHECK(cudaStreamWaitEvent(g.stream, g.ev_side, 0));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_out48, g.d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, g.stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_st, g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_st2, g.d_status2, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+}
+
+// ---- the coalesced single-item call --------------------------------------------------------------------------------
+// One request of `kind`: blob (+ z32 for CO_PROOF, + commitment48 for CO_BLOB_PROOF) -> out48 (+ y32 for CO_PROOF).
+C_KZG_RET coalesced_call(KzgCtx& ctx, int kind, const uint8_t* blob, const uint8_t* arg, uint8_t* out48, uint8_t* y32) {
+    Coalescer& co = ctx.co;
+    Coalescer::Claim cl = co.claim(kind, ctx.co_cap, [&] {
+        std::unique_ptr<CoBatch> nb(new CoBatch());
+        nb->mb = ctx.max_batch;
+        DeviceScope ds(ctx.device);
+        B200_CUDA_CHECK(cudaMallocHost((void**)&nb->h_in, (size_t)nb->mb * (kBytesPerBlob + 48 + 32)));
+        B200_CUDA_CHECK(cudaMallocHost((void**)&nb->h_out, (size_t)nb->mb * (48 + 32 + 2 * sizeof(int))));
+        return nb;
+    });
+    CoBatch* B = cl.b;
+    const int idx = cl.idx;
+    // every caller stages its own inputs, in parallel with the others (and with whatever runs on the device)
+    memcpy(B->blob(idx), blob, kBytesPerBlob);
+    if (kind == CO_PROOF) memcpy(B->z(idx), arg, 32);
+    if (kind == CO_BLOB_PROOF) {
+        memcpy(B->comm(idx), arg, 48);
+        challenge_hash(B->z(idx), blob, arg);
+    }
+    Coalescer::staged(B);
+    if (cl.leader) {
+        int rc = C_KZG_OK;
+        try {
+            OneLane ln(ctx);   // blocks while every lane is busy: meanwhile the batch keeps filling
+            const int n = co.close(B);
+            Stage& g = ctx.stage[ln.lane];
+            if (kind == CO_COMMIT) enqueue_commit(ctx, ln.lane, B->h_in, n, B->out48(0), B->status());
+            else if (kind == CO_PROOF) enqueue_proof(ctx, ln.lane, B->h_in, B->z(0), n, B->out48(0), B->y32(0), B->status());
+            else enqueue_blob_proof(ctx, ln.lane, B->h_in, B->comm(0), B->z(0), n, B->out48(0), B->status(), B->status2());
+            B200_CUDA_CHECK(cudaStreamSynchronize(g.stream));
+        } catch (const std::exception& e) {
+            cudaGetLastError();
+            fprintf(stderr, "b200kzg: %s\n", e.what());
+            rc = C_KZG_ERROR;
+        }
+        co.publish(B, rc);
+    } else {
+        co.wait(B);
+    }
+    C_KZG_RET rc = (C_KZG_RET)B->rc;
+    if (rc == C_KZG_OK) {
+        if (B->status()[idx] || (kind == CO_BLOB_PROOF && B->status2()[idx])) {
+            rc = C_KZG_BADARGS;
+        } else {
+            memcpy(out48, B->out48(idx), 48);
+            if (kind == CO_PROOF) memcpy(y32, B->y32(idx), 32);
+        }
+    }
+    co.consume(B);
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -317,8 +564,15 @@ C_KZG_RET load_trusted_setup_file(KZGSettings* out, FILE* in) {
     if (!out) return C_KZG_BADARGS;
     zero_settings(out);
     if (!in) return C_KZG_BADARGS;
-    std::vector<char> buf(1024 * 1024);
-    size_t len = fread(buf.data(), 1, buf.size(), in);
+    // the whole stream, whatever its size (the reference reads the file to a String first, blst/src/eip_4844.rs:232-240)
+    std::vector<char> buf(1 << 20);
+    size_t len = 0;
+    for (;;) {
+        len += fread(buf.data() + len, 1, buf.size() - len, in);
+        if (len < buf.size()) break;
+        if (buf.size() >= ((size_t)1 << 28)) return C_KZG_BADARGS;
+        buf.resize(buf.size() * 2);
+    }
     std::vector<uint8_t> mono, lag, g2;
     if (!parse_setup_text(buf.data(), len, mono, lag, g2)) return C_KZG_BADARGS;
     return load_impl(out, mono.data(), mono.size(), lag.data(), lag.size(), g2.data(), g2.size());
@@ -332,6 +586,10 @@ void free_trusted_setup(KZGSettings* s) {
     }
     free(s->roots_of_unity); free(s->brp_roots_of_unity); free(s->reverse_roots_of_unity);
     free(s->g1_values_monomial); free(s->g1_values_lagrange_brp); free(s->g2_values_monomial);
+    if (s->x_ext_fft_columns) {
+        for (size_t r = 0; r < 128; r++) free(s->x_ext_fft_columns[r]);
+        free(s->x_ext_fft_columns);
+    }
     zero_settings(s);
 }
 
@@ -340,15 +598,11 @@ C_KZG_RET b200_blob_to_kzg_commitment_batch(KZGCommitment* out, const Blob* blob
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
         if (!ctx || !out || !blobs) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         return run_chunks(*ctx, n, ctx->max_batch,
             [&](int lane, size_t off, int m) {
                 Stage& g = ctx->stage[lane];
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
-                B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
-                ctx->dev->blob_to_commitments(g.d_blobs, m, g.d_out48, g.d_status, g.stream, lane);
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_out48(), g.d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, g.stream));
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_status(), g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+                enqueue_commit(*ctx, lane, (const uint8_t*)(blobs + off), m, g.h_out48(), g.h_status());
             },
             [&](int lane, size_t off, int m) -> C_KZG_RET {
                 Stage& g = ctx->stage[lane];
@@ -364,17 +618,11 @@ C_KZG_RET b200_compute_kzg_proof_batch(KZGProof* proofs, Bytes32* ys, const Blob
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
         if (!ctx || !proofs || !ys || !blobs || !zs) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         return run_chunks(*ctx, n, ctx->max_batch,
             [&](int lane, size_t off, int m) {
                 Stage& g = ctx->stage[lane];
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_z, zs + off, (size_t)m * 32, cudaMemcpyHostToDevice, g.stream));
-                B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
-                ctx->dev->compute_proofs(g.d_blobs, g.d_z, 0, m, g.d_out48, g.d_y32, g.d_status, g.stream, lane);
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_out48(), g.d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, g.stream));
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_y32(), g.d_y32, (size_t)m * 32, cudaMemcpyDeviceToHost, g.stream));
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_status(), g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+                enqueue_proof(*ctx, lane, (const uint8_t*)(blobs + off), (const uint8_t*)(zs + off), m, g.h_out48(), g.h_y32(), g.h_status());
             },
             [&](int lane, size_t off, int m) -> C_KZG_RET {
                 Stage& g = ctx->stage[lane];
@@ -391,27 +639,12 @@ C_KZG_RET b200_compute_blob_kzg_proof_batch(KZGProof* out, const Blob* blobs, co
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
         if (!ctx || !out || !blobs || !commitments) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         return run_chunks(*ctx, n, ctx->max_batch,
             [&](int lane, size_t off, int m) {
                 Stage& g = ctx->stage[lane];
-                // commitments first: their validation (decode + subgroup test) runs on the side stream under everything else
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_comm, commitments + off, (size_t)m * 48, cudaMemcpyHostToDevice, g.stream));
-                B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
-                B200_CUDA_CHECK(cudaMemsetAsync(g.d_status2, 0, m * sizeof(int), g.stream));
-                B200_CUDA_CHECK(cudaEventRecord(g.ev_in, g.stream));
-                B200_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.ev_in, 0));
-                ctx->dev->validate_commitments(g.d_comm, m, g.d_status2, g.side);
-                B200_CUDA_CHECK(cudaEventRecord(g.ev_side, g.side));
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
-                // the hash chain runs on the host while the blobs cross PCIe (and the other lane computes)
-                challenge_hash_many(g.h_z(), (const uint8_t*)(blobs + off), (const uint8_t*)(commitments + off), m);
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.d_z, g.h_z(), (size_t)m * 32, cudaMemcpyHostToDevice, g.stream));
-                ctx->dev->compute_proofs(g.d_blobs, g.d_z, 1, m, g.d_out48, nullptr, g.d_status, g.stream, lane);
-                B200_CUDA_CHECK(cudaStreamWaitEvent(g.stream, g.ev_side, 0));
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_out48(), g.d_out48, (size_t)m * 48, cudaMemcpyDeviceToHost, g.stream));
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_status(), g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
-                B200_CUDA_CHECK(cudaMemcpyAsync(g.h_status2(), g.d_status2, m * sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+                enqueue_blob_proof(*ctx, lane, (const uint8_t*)(blobs + off), (const uint8_t*)(commitments + off), nullptr, m, g.h_out48(),
+                                   g.h_status(), g.h_status2());
             },
             [&](int lane, size_t off, int m) -> C_KZG_RET {
                 Stage& g = ctx->stage[lane];
@@ -422,25 +655,40 @@ C_KZG_RET b200_compute_blob_kzg_proof_batch(KZGProof* out, const Blob* blobs, co
     });
 }
 
-// ---- the c-kzg-4844 single-blob entry points ---------------------------------------------------------------------
+// ---- the c-kzg-4844 single-blob entry points: concurrent callers are coalesced (see Coalescer) -------------------
 C_KZG_RET blob_to_kzg_commitment(KZGCommitment* out, const Blob* blob, const KZGSettings* s) {
-    return b200_blob_to_kzg_commitment_batch(out, blob, 1, s);
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !out || !blob) return C_KZG_BADARGS;
+        return coalesced_call(*ctx, CO_COMMIT, blob->bytes, nullptr, out->bytes, nullptr);
+    });
 }
 C_KZG_RET compute_kzg_proof(KZGProof* proof_out, Bytes32* y_out, const Blob* blob, const Bytes32* z_bytes, const KZGSettings* s) {
-    return b200_compute_kzg_proof_batch(proof_out, y_out, blob, z_bytes, 1, s);
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !proof_out || !y_out || !blob || !z_bytes) return C_KZG_BADARGS;
+        return coalesced_call(*ctx, CO_PROOF, blob->bytes, z_bytes->bytes, proof_out->bytes, y_out->bytes);
+    });
 }
 C_KZG_RET compute_blob_kzg_proof(KZGProof* out, const Blob* blob, const Bytes48* commitment_bytes, const KZGSettings* s) {
-    return b200_compute_blob_kzg_proof_batch(out, blob, commitment_bytes, 1, s);
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !out || !blob || !commitment_bytes) return C_KZG_BADARGS;
+        return coalesced_call(*ctx, CO_BLOB_PROOF, blob->bytes, commitment_bytes->bytes, out->bytes, nullptr);
+    });
 }
 
 // ---- device-pointer extensions (inputs resident in HBM; asynchronous on `stream`) --------------------------------
+// The lane's workspace is shared with the host-pointer paths while `stream` is the caller's: the end of the enqueue is
+// recorded in the lane (lane_leave_async) and the lane's next user, on whatever stream, waits on it (lane_enter).
 C_KZG_RET b200_blob_to_kzg_commitment_device(void* out48_dev, const void* blobs_dev, size_t n, int* status_dev,
                                              const KZGSettings* s, void* stream) {
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
         if (!ctx || n > (size_t)ctx->max_batch) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        ctx->dev->blob_to_commitments((const uint8_t*)blobs_dev, (int)n, (uint8_t*)out48_dev, status_dev, (cudaStream_t)stream);
+        OneLane ln(*ctx, (cudaStream_t)stream);
+        ctx->dev->blob_to_commitments((const uint8_t*)blobs_dev, (int)n, (uint8_t*)out48_dev, status_dev, (cudaStream_t)stream, ln.lane);
+        lane_leave_async(ctx->stage[ln.lane], (cudaStream_t)stream);
         return C_KZG_OK;
     });
 }
@@ -449,9 +697,10 @@ C_KZG_RET b200_compute_kzg_proof_device(void* proofs48_dev, void* y32_dev, const
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
         if (!ctx || n > (size_t)ctx->max_batch) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        OneLane ln(*ctx, (cudaStream_t)stream);
         ctx->dev->compute_proofs((const uint8_t*)blobs_dev, (const uint8_t*)z32_dev, z_reduce, (int)n, (uint8_t*)proofs48_dev,
-                                 (uint8_t*)y32_dev, status_dev, (cudaStream_t)stream);
+                                 (uint8_t*)y32_dev, status_dev, (cudaStream_t)stream, ln.lane);
+        lane_leave_async(ctx->stage[ln.lane], (cudaStream_t)stream);
         return C_KZG_OK;
     });
 }
@@ -460,7 +709,7 @@ C_KZG_RET b200_compute_cells_batch(Cell* cells, const Blob* blobs, size_t n, con
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
         if (!ctx || !cells || !blobs) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         if (!ctx->d_cells) ctx->d_cells = dev_alloc<uint8_t>((size_t)ctx->max_batch * 128 * 2048);
         uint8_t* d_cells = ctx->d_cells;
         C_KZG_RET rc = C_KZG_OK;
@@ -484,7 +733,7 @@ C_KZG_RET b200_compute_cell_proofs_batch(KZGProof* proofs, const Blob* blobs, si
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
         if (!ctx || !proofs || !blobs) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         const int cap = ctx->dev->fk20_batch(ctx->stream);
         if (!ctx->d_proofs) ctx->d_proofs = dev_alloc<uint8_t>((size_t)cap * 128 * 48);
         uint8_t* d_proofs = ctx->d_proofs;
@@ -584,7 +833,7 @@ C_KZG_RET b200_verify_kzg_proof_batch(bool* ok, const Bytes48* commitments, cons
         *ok = false;
         if (n == 0) { *ok = true; return C_KZG_OK; }
         if (!commitments || !zs || !ys || !proofs) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         return verify_core(*ctx, ok, (const uint8_t*)commitments, (const uint8_t*)zs, (const uint8_t*)ys, (const uint8_t*)proofs, n);
     });
 }
@@ -600,7 +849,7 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
         *ok = false;
         if (n == 0) { *ok = true; return C_KZG_OK; }  // kzg/src/eip_4844.rs:760-763
         if (!blobs || !commitments_bytes || !proofs_bytes) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         // phase 1, chunked over the two lanes: z_i = challenge(blob_i, C_i) hashed on the host while the blobs cross
         // PCIe, y_i = p_i(z_i) on the device (compute_challenges_and_evaluate_polynomial, :700-718)
         std::vector<uint8_t> zs(32 * n), ys(32 * n);
@@ -690,7 +939,7 @@ C_KZG_RET recover_cells_and_kzg_proofs(Cell* recovered_cells, KZGProof* recovere
             if (cell_indices[i] >= kCellsPerExtBlob) return C_KZG_BADARGS;
             if (i + 1 < n && cell_indices[i + 1] <= cell_indices[i]) return C_KZG_BADARGS;
         }
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         const size_t o_out = n * kBytesPerCell, o_pr = o_out + kCellsPerExtBlob * kBytesPerCell, o_st = o_pr + kCellsPerExtBlob * 48;
         DevScratch buf(*ctx, o_st + 64);
         cudaStream_t st = ctx->stream;
@@ -712,7 +961,9 @@ C_KZG_RET verify_cell_kzg_proof_batch(bool* ok, const Bytes48* commitments_bytes
                                       const Bytes48* proofs_bytes, uint64_t num_cells, const KZGSettings* s) {
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
-        if (!ctx || !ok) return C_KZG_BADARGS;
+        if (!ok) return C_KZG_BADARGS;
+        *ok = false;
+        if (!ctx) return C_KZG_BADARGS;
         const size_t n = num_cells;
         if (n == 0) { *ok = true; return C_KZG_OK; }   // kzg/src/das.rs:319-321
         if (!commitments_bytes || !cell_indices || !cells || !proofs_bytes) return C_KZG_BADARGS;
@@ -732,7 +983,7 @@ C_KZG_RET verify_cell_kzg_proof_batch(bool* ok, const Bytes48* commitments_bytes
             comm_idx[i] = it->second;
         }
         const size_t m = seen.size();
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         // device layout: [cells n*2048][proofs n*48][uniq m*48][comm_idx n u32][cell_idx n u32][r 32][status n ints][result]
         const size_t o_p = n * kBytesPerCell, o_c = o_p + 48 * n, o_ci = (o_c + 48 * m + 15) & ~(size_t)15, o_ki = o_ci + 4 * n,
                      o_r = o_ki + 4 * n, o_st = o_r + 32, o_res = o_st + 4 * n;
@@ -763,27 +1014,23 @@ C_KZG_RET compute_verify_cell_kzg_proof_batch_challenge(blst_fr* challenge_out, 
     return ckzg_guard([&]() -> C_KZG_RET {
         if (!challenge_out) return C_KZG_BADARGS;
         memset(challenge_out, 0, sizeof(*challenge_out));
-        require_device();
-        // any loaded settings' device context will do (the function takes no settings argument in the reference either)
-        std::shared_ptr<KzgCtx> ctx;
-        {
-            std::lock_guard<std::mutex> lk(g_reg_mu);
-            if (!g_registry.empty()) ctx = g_registry.begin()->second;
-        }
-        if (!ctx) return C_KZG_ERROR;   // no trusted setup loaded: no device context to run the argument checks on
         const size_t n = num_cells, m = num_commitments;
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        const size_t o_p = n * kBytesPerCell, o_c = o_p + 48 * n, o_r = (o_c + 48 * m + 15) & ~(size_t)15, o_fr = o_r + 32, o_st = o_fr + 32;
-        DevScratch buf(*ctx, o_st + 16);
+        if (m && !commitment_bytes) return C_KZG_BADARGS;
+        if (n && (!commitment_indices || !cell_indices || !cells || !proofs_bytes)) return C_KZG_BADARGS;
+        require_device();
+        // Standalone like the reference's function: no settings object, own scratch, the default stream of the current device.
+        const size_t o_p = n * kBytesPerCell, o_c = o_p + 48 * n, o_r = (o_c + 48 * m + 15) & ~(size_t)15, o_fr = o_r + 32, o_st = o_fr + 32,
+                     o_ws = (o_st + 16 + 255) & ~(size_t)255;
+        DevScratch buf(o_ws + check_challenge_ws_bytes((int)m, (int)n));
         if (n) { memcpy(buf.h, cells, n * kBytesPerCell); memcpy(buf.h + o_p, proofs_bytes, 48 * n); }
         if (m) memcpy(buf.h + o_c, commitment_bytes, 48 * m);
         cell_challenge_hash(buf.h + o_r, (const uint8_t*)commitment_bytes, m, commitment_indices, cell_indices, (const uint8_t*)cells,
                             (const uint8_t*)proofs_bytes, n);
         memset(buf.h + o_st, 0, 4);
-        cudaStream_t st = ctx->stream;
+        cudaStream_t st = nullptr;
         B200_CUDA_CHECK(cudaMemcpyAsync(buf.d, buf.h, o_st + 4, cudaMemcpyHostToDevice, st));
         int* d_st = reinterpret_cast<int*>(buf.d + o_st);
-        ctx->dev->check_challenge_inputs(buf.d + o_c, (int)m, buf.d, buf.d + o_p, (int)n, d_st, st);
+        launch_check_challenge_inputs(buf.d + o_ws, buf.d + o_c, (int)m, buf.d, buf.d + o_p, (int)n, d_st, st);
         launch_fr_from_bytes(buf.d + o_r, 1, 1, buf.d + o_fr, d_st, st);   // hash_to_bls_field -> Montgomery
         B200_CUDA_CHECK(cudaMemcpyAsync(buf.h + o_fr, buf.d + o_fr, 32 + 4, cudaMemcpyDeviceToHost, st));
         B200_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -873,7 +1120,7 @@ C_KZG_RET b200_selftest_pairings_verify(bool* ok, const blst_p1* a1, int qa, con
     return ckzg_guard([&]() -> C_KZG_RET {
         auto ctx = find_ctx(s);
         if (!ctx || !ok || !a1 || !b1) return C_KZG_BADARGS;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        AllLanes lk(*ctx);
         ctx->ensure_verify(4);
         uint8_t* d = ctx->d_verify;
         B200_CUDA_CHECK(cudaMemcpyAsync(d, a1, 144, cudaMemcpyHostToDevice, ctx->stream));

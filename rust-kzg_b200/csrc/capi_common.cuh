@@ -14,7 +14,7 @@ inline void require_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
-        throw CudaError(e == cudaSuccess ? -2 : (int)e,
+        throw CudaError(e == cudaSuccess ? -2 : kCudaErrorBase + (int)e,
                         "b200kzg: no CUDA device available -- this backend has no CPU fallback");
 }
 
@@ -35,5 +35,19 @@ inline RustError guarded(F&& f) {
 }
 
 int env_int(const char* name, int dflt);
+
+// Every entry point runs on the device its context / handle was created on, whatever device is current in the calling
+// thread (settings objects and handles are used from arbitrary host threads; the reference's are Send + Sync).
+struct DeviceScope {
+    int prev = -1, dev;
+    explicit DeviceScope(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) B200_CUDA_CHECK(cudaSetDevice(dev));
+    }
+    ~DeviceScope() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+
 
 }  // namespace b200

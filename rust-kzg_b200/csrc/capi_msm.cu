@@ -4,9 +4,12 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <string>
+#include <utility>
 
 #include "../../include/b200_kzg.h"
 #include "capi_common.cuh"
+#include "coalesce.cuh"
 #include "g1.cuh"
 #include "msm.cuh"
 #include "util.cuh"
@@ -48,42 +51,81 @@ MsmConfig choose_config(size_t n, bool fixed, int max_batch) {
     return cfg;
 }
 
+// one open batch of single mult_pippenger_prepared calls (coalesce.cuh); slots are n scalars wide, short calls are
+// zero-padded (a zero scalar has no non-zero digit: it never reaches a bucket)
+struct MsmCoBatch : CoBatchBase {
+    uint8_t* h_in = nullptr;    // pinned: max_batch x n x 32
+    uint8_t* h_out = nullptr;   // pinned: max_batch x 144
+    std::string msg;
+    ~MsmCoBatch() {
+        if (h_in) cudaFreeHost(h_in);
+        if (h_out) cudaFreeHost(h_out);
+    }
+};
+
 struct MsmHandle {
-    std::mutex mu;  // the handle is Send + Sync on the Rust side: serialise users
+    std::mutex mu;  // the handle is Send + Sync on the Rust side: serialise users of the engine and its workspace
     std::unique_ptr<MsmEngine> eng;
     size_t npoints = 0;
+    int device = 0;                  // the device the table lives on; entry points switch to it (DeviceScope)
     cudaStream_t stream = nullptr;
+    // end of the last enqueue of b200_msm_prepared_device on a CALLER's stream: the engine's workspace is shared, so the
+    // next user orders its stream after it, whatever stream that is
+    cudaEvent_t ev_busy = nullptr;
+    bool busy = false;
     uint8_t* scalars_dev = nullptr;  // staging for host-pointer calls
     uint8_t* out_dev = nullptr;
     size_t scalars_cap = 0;
     int out_cap = 0;
+    CoQueue<MsmCoBatch, 1> co;
     ~MsmHandle() {
         cudaFree(scalars_dev);
         cudaFree(out_dev);
+        if (ev_busy) cudaEventDestroy(ev_busy);
         if (stream) cudaStreamDestroy(stream);
     }
     void ensure_staging(size_t nscalars, int batch) {
         if (nscalars > scalars_cap) {
             cudaFree(scalars_dev);
+            scalars_dev = nullptr; scalars_cap = 0;
             scalars_dev = dev_alloc<uint8_t>(nscalars * 32);
             scalars_cap = nscalars;
         }
         if (batch > out_cap) {
             cudaFree(out_dev);
+            out_dev = nullptr; out_cap = 0;
             out_dev = dev_alloc<uint8_t>((size_t)batch * 144);
             out_cap = batch;
         }
+    }
+    // caller holds mu
+    void enter(cudaStream_t user) {
+        if (busy) B200_CUDA_CHECK(cudaStreamWaitEvent(user, ev_busy, 0));
+    }
+    void leave_async(cudaStream_t user) {
+        B200_CUDA_CHECK(cudaEventRecord(ev_busy, user));
+        busy = true;
     }
 };
 
 MsmHandle* msm_handle_create(const void* points, size_t npoints, bool host_points, bool fixed, int max_batch) {
     require_device();
     std::unique_ptr<MsmHandle> h(new MsmHandle());
+    B200_CUDA_CHECK(cudaGetDevice(&h->device));
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_busy, cudaEventDisableTiming));
     MsmConfig cfg = choose_config(npoints, fixed, max_batch);
     h->eng.reset(new MsmEngine(cfg, points, host_points, h->stream));
     h->npoints = npoints;
+    h->co.max_batches = 3;
     return h.release();
+}
+
+// scalar vectors one launch sequence may carry: small prepared MSMs (the 4096-point commitment MSM behind g1_lincomb) are
+// latency-bound one at a time, so concurrent calls are packed; a 2^18-term MSM fills the machine on its own
+static int default_max_batch(size_t npoints) {
+    size_t b = npoints ? ((size_t)1 << 18) / npoints : 1;
+    return (int)std::min<size_t>(64, std::max<size_t>(1, b));
 }
 
 }  // namespace b200
@@ -93,7 +135,7 @@ extern "C" {
 void* prepare_msm(const blst_p1_affine points[], size_t npoints) {
     try {
         if (!points || npoints == 0) return nullptr;
-        return msm_handle_create(points, npoints, true, true, env_int("B200_MSM_MAX_BATCH", 1));
+        return msm_handle_create(points, npoints, true, true, env_int("B200_MSM_MAX_BATCH", default_max_batch(npoints)));
     } catch (const std::exception& e) {
         fprintf(stderr, "b200kzg: prepare_msm failed: %s\n", e.what());
         return nullptr;
@@ -116,8 +158,11 @@ RustError b200_msm_prepared_device(void* msm, void* out_dev, size_t npoints, con
     return guarded([&] {
         MsmHandle* h = static_cast<MsmHandle*>(msm);
         if (!h) throw CudaError(-1, "null msm handle");
+        DeviceScope ds(h->device);
         std::lock_guard<std::mutex> lk(h->mu);
+        h->enter((cudaStream_t)stream);
         h->eng->run(scalars_dev, npoints, batch, true, out_dev, (cudaStream_t)stream);
+        h->leave_async((cudaStream_t)stream);
     });
 }
 
@@ -127,11 +172,13 @@ RustError b200_msm_prepared_batch(void* msm, blst_p1 out[], size_t npoints, cons
         if (!h) throw CudaError(-1, "null msm handle");
         if (npoints > h->npoints) throw CudaError(-1, "npoints exceeds the prepared table");
         if (batch < 1 || batch > h->eng->config().max_batch) throw CudaError(-1, "batch exceeds the prepared capacity");
-        std::lock_guard<std::mutex> lk(h->mu);
         if (npoints == 0) {
             memset(out, 0, sizeof(blst_p1) * batch);
             return;
         }
+        DeviceScope ds(h->device);
+        std::lock_guard<std::mutex> lk(h->mu);
+        h->enter(h->stream);
         h->ensure_staging((size_t)batch * npoints, batch);
         h->eng->run(h->scalars_dev, npoints, batch, true, h->out_dev, h->stream, scalars);
         B200_CUDA_CHECK(cudaMemcpyAsync(out, h->out_dev, (size_t)batch * 144, cudaMemcpyDeviceToHost, h->stream));
@@ -139,13 +186,64 @@ RustError b200_msm_prepared_batch(void* msm, blst_p1 out[], size_t npoints, cons
     });
 }
 
+// blst-sppark/cuda/pippenger.cu:28-31.  Handles prepared for more than one scalar vector per launch coalesce concurrent
+// callers (the handle is Send + Sync on the Rust side, kzg/src/msm/sppark.rs:24-44); see coalesce.cuh.
 RustError mult_pippenger_prepared(void* msm, blst_p1* out, size_t npoints, const blst_fr scalars[]) {
-    return b200_msm_prepared_batch(msm, out, npoints, scalars, 1);
+    MsmHandle* h = static_cast<MsmHandle*>(msm);
+    if (!h || !out || (npoints && !scalars) || npoints > h->npoints || npoints == 0 || h->eng->config().max_batch < 2)
+        return b200_msm_prepared_batch(msm, out, npoints, scalars, 1);
+    return guarded([&] {
+        const size_t n = h->npoints;
+        const int cap = h->eng->config().max_batch;
+        auto cl = h->co.claim(0, cap, [&] {
+            std::unique_ptr<MsmCoBatch> nb(new MsmCoBatch());
+            DeviceScope ds(h->device);
+            B200_CUDA_CHECK(cudaMallocHost((void**)&nb->h_in, (size_t)cap * n * 32));
+            B200_CUDA_CHECK(cudaMallocHost((void**)&nb->h_out, (size_t)cap * 144));
+            return nb;
+        });
+        MsmCoBatch* B = cl.b;
+        uint8_t* slot = B->h_in + (size_t)cl.idx * n * 32;
+        memcpy(slot, scalars, npoints * 32);
+        if (npoints < n) memset(slot + npoints * 32, 0, (n - npoints) * 32);
+        h->co.staged(B);
+        if (cl.leader) {
+            int rc = 0;
+            try {
+                DeviceScope ds(h->device);
+                std::lock_guard<std::mutex> lk(h->mu);   // waits while the previous batch runs: meanwhile this one fills
+                const int m = h->co.close(B);
+                h->enter(h->stream);
+                h->ensure_staging((size_t)m * n, m);
+                h->eng->run(h->scalars_dev, n, m, true, h->out_dev, h->stream, B->h_in);
+                B200_CUDA_CHECK(cudaMemcpyAsync(B->h_out, h->out_dev, (size_t)m * 144, cudaMemcpyDeviceToHost, h->stream));
+                B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            } catch (const CudaError& e) {
+                cudaGetLastError();
+                rc = e.code ? e.code : -1;
+                B->msg = e.what();
+            } catch (const std::exception& e) {
+                rc = -1;
+                B->msg = e.what();
+            }
+            h->co.publish(B, rc);
+        } else {
+            h->co.wait(B);
+        }
+        const int rc = B->rc;
+        std::string msg = rc ? B->msg : std::string();
+        if (!rc) memcpy(out, B->h_out + (size_t)cl.idx * 144, 144);
+        h->co.consume(B);
+        if (rc) throw CudaError(rc, msg);
+    });
 }
 
-// variable-base engines are cached per capacity (next power of two) so repeated calls do not re-allocate
+// variable-base engines are cached per capacity (next power of two) so repeated calls do not re-allocate; two per
+// capacity, so that one caller's transfers overlap another caller's kernels
 static std::mutex g_var_mu;
-static std::map<size_t, MsmHandle*> g_var_engines;
+static constexpr int kVarEngines = 2;
+struct VarSlot { MsmHandle* h[kVarEngines] = {}; unsigned next = 0; };
+static std::map<std::pair<int, size_t>, VarSlot> g_var_engines;
 
 RustError mult_pippenger(blst_p1* out, const blst_p1_affine points[], size_t npoints, const blst_fr scalars[]) {
     return guarded([&] {
@@ -156,16 +254,16 @@ RustError mult_pippenger(blst_p1* out, const blst_p1_affine points[], size_t npo
         }
         size_t cap = 256;
         while (cap < npoints) cap <<= 1;
+        int dev = 0;
+        B200_CUDA_CHECK(cudaGetDevice(&dev));   // no handle: the call runs on the calling thread's current device
         MsmHandle* h;
         {
             std::lock_guard<std::mutex> lk(g_var_mu);
-            auto it = g_var_engines.find(cap);
-            if (it == g_var_engines.end()) {
-                h = msm_handle_create(nullptr, cap, true, false, 1);
-                g_var_engines[cap] = h;
-            } else {
-                h = it->second;
-            }
+            VarSlot& vs = g_var_engines[std::make_pair(dev, cap)];
+            // large engines (a 2^20-point one holds ~1 GiB of workspace) are not duplicated
+            const unsigned k = cap >= ((size_t)1 << 18) ? 0 : vs.next++ % kVarEngines;
+            if (!vs.h[k]) vs.h[k] = msm_handle_create(nullptr, cap, true, false, 1);
+            h = vs.h[k];
         }
         std::lock_guard<std::mutex> lk(h->mu);
         h->ensure_staging(npoints, 1);
@@ -191,6 +289,7 @@ RustError b200_msm_last_counts(void* msm, size_t* entries, size_t* tasks) {
     return guarded([&] {
         MsmHandle* h = static_cast<MsmHandle*>(msm);
         if (!h) throw CudaError(-1, "null msm handle");
+        DeviceScope ds(h->device);
         std::lock_guard<std::mutex> lk(h->mu);
         B200_CUDA_CHECK(cudaDeviceSynchronize());  // the last run may have been on a caller's stream (device variant)
         h->eng->last_counts(entries, tasks, h->stream);
@@ -205,6 +304,7 @@ RustError b200_msm_profile_read(void* msm, double* accumulate_ms_sum, int* runs)
     return guarded([&] {
         MsmHandle* h = static_cast<MsmHandle*>(msm);
         if (!h) throw CudaError(-1, "null msm handle");
+        DeviceScope ds(h->device);
         h->eng->profile_read(accumulate_ms_sum, runs);
     });
 }
@@ -212,7 +312,7 @@ RustError b200_msm_profile_read(void* msm, double* accumulate_ms_sum, int* runs)
 RustError b200_g1_sum_device(void* out_dev, const void* points_dev, size_t n, void* stream) {
     return guarded([&] {
         require_device();
-        launch_g1_sum(points_dev, out_dev, (int)n, (cudaStream_t)stream);
+        launch_g1_sum(points_dev, out_dev, (int)n, (cudaStream_t)stream);   // current device: the pointers are the caller's
     });
 }
 

@@ -15,12 +15,24 @@ struct FftHandle {
     std::mutex mu;
     std::unique_ptr<FFTSettingsDev> fs;
     cudaStream_t stream = nullptr;
+    int device = 0;   // the device the tables live on; entry points switch to it (DeviceScope)
+    // end of the last *_device enqueue on a caller's stream (the transform scratch is shared): the next user's stream waits
+    cudaEvent_t ev_busy = nullptr;
+    bool busy = false;
     uint8_t *in_dev = nullptr, *out_dev = nullptr;
     size_t cap = 0;
     ~FftHandle() {
         cudaFree(in_dev);
         cudaFree(out_dev);
+        if (ev_busy) cudaEventDestroy(ev_busy);
         if (stream) cudaStreamDestroy(stream);
+    }
+    void enter(cudaStream_t user) {   // caller holds mu
+        if (busy) B200_CUDA_CHECK(cudaStreamWaitEvent(user, ev_busy, 0));
+    }
+    void leave_async(cudaStream_t user) {
+        B200_CUDA_CHECK(cudaEventRecord(ev_busy, user));
+        busy = true;
     }
     void ensure(size_t elems) {
         if (elems <= cap) return;
@@ -39,7 +51,9 @@ void* b200_fft_settings_new(int scale) {
     try {
         require_device();
         std::unique_ptr<FftHandle> h(new FftHandle());
+        B200_CUDA_CHECK(cudaGetDevice(&h->device));
         B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_busy, cudaEventDisableTiming));
         h->fs.reset(new FFTSettingsDev(scale, h->stream));
         return h.release();
     } catch (const std::exception& e) {
@@ -55,6 +69,7 @@ RustError b200_fft_settings_roots(void* fs, int which, blst_fr* out) {
     return guarded([&] {
         FftHandle* h = static_cast<FftHandle*>(fs);
         if (!h) throw CudaError(-1, "null fft settings");
+        DeviceScope ds(h->device);
         size_t w = h->fs->max_width();
         if (which == 1) {
             B200_CUDA_CHECK(cudaMemcpy(out, h->fs->brp_roots_dev(), w * 32, cudaMemcpyDeviceToHost));
@@ -70,16 +85,22 @@ RustError b200_fft_fr_device(void* fs, void* out_dev, const void* in_dev, size_t
     return guarded([&] {
         FftHandle* h = static_cast<FftHandle*>(fs);
         if (!h) throw CudaError(-1, "null fft settings");
+        DeviceScope ds(h->device);
         std::lock_guard<std::mutex> lk(h->mu);
+        h->enter((cudaStream_t)stream);
         h->fs->fft_fr(in_dev, out_dev, n, inverse != 0, batch, (cudaStream_t)stream);
+        h->leave_async((cudaStream_t)stream);
     });
 }
 RustError b200_das_fft_extension_device(void* fs, void* odds_dev, const void* evens_dev, size_t n, int batch, void* stream) {
     return guarded([&] {
         FftHandle* h = static_cast<FftHandle*>(fs);
         if (!h) throw CudaError(-1, "null fft settings");
+        DeviceScope ds(h->device);
         std::lock_guard<std::mutex> lk(h->mu);
+        h->enter((cudaStream_t)stream);
         h->fs->das_fft_extension(evens_dev, odds_dev, n, batch, (cudaStream_t)stream);
+        h->leave_async((cudaStream_t)stream);
     });
 }
 
@@ -87,7 +108,9 @@ RustError b200_fft_fr(void* fs, blst_fr* out, const blst_fr* in, size_t n, bool 
     return guarded([&] {
         FftHandle* h = static_cast<FftHandle*>(fs);
         if (!h) throw CudaError(-1, "null fft settings");
+        DeviceScope ds(h->device);
         std::lock_guard<std::mutex> lk(h->mu);
+        h->enter(h->stream);
         if (n > h->fs->max_width()) throw CudaError(1, "Supplied list is longer than the available max width");
         if (n == 0 || (n & (n - 1))) throw CudaError(1, "A list with power-of-two length expected");
         h->ensure(n);
@@ -101,7 +124,9 @@ RustError b200_das_fft_extension(void* fs, blst_fr* odds, const blst_fr* evens, 
     return guarded([&] {
         FftHandle* h = static_cast<FftHandle*>(fs);
         if (!h) throw CudaError(-1, "null fft settings");
+        DeviceScope ds(h->device);
         std::lock_guard<std::mutex> lk(h->mu);
+        h->enter(h->stream);
         if (n == 0) throw CudaError(1, "A non-zero list ab expected");
         if (n & (n - 1)) throw CudaError(1, "A list with power-of-two length expected");
         if (n * 2 > h->fs->max_width()) throw CudaError(1, "Supplied list is longer than the available max width");
@@ -116,15 +141,20 @@ RustError b200_fft_g1_device(void* fs, void* out_dev, const void* in_dev, size_t
     return guarded([&] {
         FftHandle* h = static_cast<FftHandle*>(fs);
         if (!h) throw CudaError(-1, "null fft settings");
+        DeviceScope ds(h->device);
         std::lock_guard<std::mutex> lk(h->mu);
+        h->enter((cudaStream_t)stream);
         h->fs->fft_g1(in_dev, out_dev, n, inverse != 0, batch, (cudaStream_t)stream);
+        h->leave_async((cudaStream_t)stream);
     });
 }
 RustError b200_fft_g1(void* fs, blst_p1* out, const blst_p1* in, size_t n, bool inverse) {
     return guarded([&] {
         FftHandle* h = static_cast<FftHandle*>(fs);
         if (!h) throw CudaError(-1, "null fft settings");
+        DeviceScope ds(h->device);
         std::lock_guard<std::mutex> lk(h->mu);
+        h->enter(h->stream);
         if (n > h->fs->max_width()) throw CudaError(1, "Supplied list is longer than the available max width");
         if (n == 0 || (n & (n - 1))) throw CudaError(1, "A list with power-of-two length expected");
         h->ensure(n * 9);  // 2 x 144 B per point inside the 32-byte-element staging buffers

@@ -241,18 +241,21 @@ __global__ void k_any_flag(const int* __restrict__ flags, int n, int* __restrict
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flags[i]) status[0] = 1;
 }
-void KzgSettingsDev::check_challenge_inputs(const uint8_t* commitments48, int m, const uint8_t* cells, const uint8_t* proofs48, int n,
-                                            int* status, cudaStream_t st) {
-    size_t bytes = (size_t)(m + n) * 96 + (size_t)n * kCellFr * 32 + (size_t)(m + 2 * n + 1) * sizeof(int);
-    uint8_t* w = ensure_das_ws(bytes);
+size_t check_challenge_ws_bytes(int m, int n) {
+    return (size_t)(m + n) * 96 + (size_t)n * kCellFr * 32 + (size_t)(m + 2 * n + 1) * sizeof(int);
+}
+// context-free (the reference's compute_verify_cell_kzg_proof_batch_challenge takes no settings, blst/src/eip_7594.rs:35-97):
+// w = device workspace of check_challenge_ws_bytes(m, n) bytes
+void launch_check_challenge_inputs(uint8_t* w, const uint8_t* commitments48, int m, const uint8_t* cells, const uint8_t* proofs48, int n,
+                                   int* status, cudaStream_t st) {
     uint8_t* aff = w;
     uint8_t* cells_m = w + (size_t)(m + n) * 96;
     int* flags = reinterpret_cast<int*>(cells_m + (size_t)n * kCellFr * 32);
     const int nf = m + 2 * n;
-    B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)nf * sizeof(int), st));
-    launch_uncompress_g1(commitments48, aff, flags, m, st);
-    launch_uncompress_g1(proofs48, aff + (size_t)m * 96, flags + m, n, st);
+    B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)(nf + 1) * sizeof(int), st));
+    if (m > 0) launch_uncompress_g1(commitments48, aff, flags, m, st);
     if (n > 0) {
+        launch_uncompress_g1(proofs48, aff + (size_t)m * 96, flags + m, n, st);
         k_vc_cells<<<div_up((size_t)n * kCellFr, 256), 256, 0, st>>>(cells, n, cells_m, flags + m + n);
         B200_LAUNCH_CHECK();
     }
@@ -260,6 +263,10 @@ void KzgSettingsDev::check_challenge_inputs(const uint8_t* commitments48, int m,
         k_any_flag<<<div_up(nf, 256), 256, 0, st>>>(flags, nf, status);
         B200_LAUNCH_CHECK();
     }
+}
+void KzgSettingsDev::check_challenge_inputs(const uint8_t* commitments48, int m, const uint8_t* cells, const uint8_t* proofs48, int n,
+                                            int* status, cudaStream_t st) {
+    launch_check_challenge_inputs(ensure_das_ws(check_challenge_ws_bytes(m, n)), commitments48, m, cells, proofs48, n, status, st);
 }
 
 void KzgSettingsDev::verify_cells(const uint8_t* commitments48, int m, const uint32_t* comm_idx, const uint32_t* cell_idx,

@@ -376,8 +376,9 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
         cfg_q.c0 = 0;
         cfg_q.W = (256 + cfg_q.c - 1) / cfg_q.c;
         for (Lane& ln : lanes_) {
-            ln.msm.reset(new MsmEngine(cfg, aff_brp, false, st));
-            ln.msm_q.reset(new MsmEngine(cfg_q, aff_brp, false, st));
+            // one table per window layout, shared by the lanes: what the L2 has to hold does not grow with the lane count
+            ln.msm.reset(new MsmEngine(cfg, aff_brp, false, st, &ln == lanes_ ? nullptr : lanes_[0].msm.get()));
+            ln.msm_q.reset(new MsmEngine(cfg_q, aff_brp, false, st, &ln == lanes_ ? nullptr : lanes_[0].msm_q.get()));
             ln.scalars = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
             ln.poly = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
             ln.z = dev_alloc<uint8_t>((size_t)max_batch * 32);
@@ -457,6 +458,35 @@ void KzgSettingsDev::compute_cells(const uint8_t* blobs, int n, uint8_t* cells_o
     k_cells_out<<<div_up(2 * total, 256), 256, 0, st>>>((const uint8_t*)cells_b_, cells_out, 2 * total);
     B200_LAUNCH_CHECK();
     launches_ = 7;
+}
+
+// x_ext_fft_columns of FsKZGSettings::new (blst/src/types/kzg_settings.rs:84-101) for the host KZGSettings struct:
+// out[row][offset] (128 x 64 blst_p1, row-major) = toeplitz_part_1 of offset `offset`, entry `row`.  Device buffer out.
+__global__ void __launch_bounds__(128) k_fk_columns_out(const uint8_t* __restrict__ points_jac, uint8_t* __restrict__ out) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= kCellSize * kFkK2) return;
+    int row = gid / kCellSize, offset = gid % kCellSize;
+    const uint4* src = reinterpret_cast<const uint4*>(points_jac + ((size_t)offset * kFkK2 + row) * 144);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)gid * 144);
+#pragma unroll
+    for (int k = 0; k < 9; k++) dst[k] = src[k];
+}
+void KzgSettingsDev::x_ext_fft_columns(void* out_dev, cudaStream_t st) {
+    const int npts = kCellSize * kFkK2;  // 8192
+    uint8_t* x_ext = dev_alloc<uint8_t>((size_t)npts * 144);
+    uint8_t* points = dev_alloc<uint8_t>((size_t)npts * 144);
+    try {
+        k_fk_gather_x<<<div_up(npts, 128), 128, 0, st>>>((const uint8_t*)monomial_jac_, x_ext);
+        B200_LAUNCH_CHECK();
+        fs_->fft_g1(x_ext, points, kFkK2, false, kCellSize, st);
+        k_fk_columns_out<<<div_up(npts, 128), 128, 0, st>>>(points, (uint8_t*)out_dev);
+        B200_LAUNCH_CHECK();
+        B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaFree(x_ext); cudaFree(points);
+        throw;
+    }
+    cudaFree(x_ext); cudaFree(points);
 }
 
 void KzgSettingsDev::ensure_fk20(cudaStream_t st) {

@@ -38,7 +38,7 @@ public:
     // (the reference's Err -> C_KZG_BADARGS); outputs of invalid items are unspecified.
     // Two independent "lanes" (MSM engine + workspace each) let a caller keep two batches in flight on two streams:
     // the latency-bound tail of one batch (bucket reduction, compression) overlaps the accumulation of the next.
-    static constexpr int kLanes = 2;
+    static constexpr int kLanes = 4;
     // blob_to_kzg_commitment_raw (kzg/src/eip_4844.rs:297-314), n <= max_batch
     void blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st, int lane = 0);
     // compute_kzg_proof_raw (kzg/src/eip_4844.rs:521-539); z_bytes: n x 32 big-endian; z_reduce: 0 = reject z >= r
@@ -53,6 +53,9 @@ public:
     // n <= fk20_batch().  The 128 x 64 table of x_ext_fft_columns is built on first use.
     void compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* proofs48, int* status, cudaStream_t st);
     int fk20_batch(cudaStream_t st) { ensure_fk20(st); return fk_batch_; }
+    // the 128 x 64 blst_p1 of FsKZGSettings::x_ext_fft_columns (blst/src/types/kzg_settings.rs:84-101), row-major, into a
+    // DEVICE buffer of 128 * 64 * 144 bytes (for the host-side KZGSettings struct; synchronises st)
+    void x_ext_fft_columns(void* out_dev, cudaStream_t st);
     void fk20_from_mono(const void* mono, size_t stride, int n, uint8_t* proofs48, cudaStream_t st);
 
     // ---- verification (verify.cu; kzg/src/eip_4844.rs:328-435, 586-866) -----------------------------------------
@@ -125,6 +128,10 @@ private:
     uint8_t* ensure_das_ws(size_t bytes);
 };
 
+// argument checks of compute_verify_cell_kzg_proof_batch_challenge without a settings object (das7594.cu)
+size_t check_challenge_ws_bytes(int m, int n);
+void launch_check_challenge_inputs(uint8_t* workspace_dev, const uint8_t* commitments48, int m, const uint8_t* cells, const uint8_t* proofs48,
+                                   int n, int* status, cudaStream_t st);
 // FK20 lincombs by direct table lookup (fk20_direct.cu): rows = the engine's [32][8192] fixed-base rows for c = 8
 size_t fk_direct_table_bytes();
 void launch_fk_direct_build(const void* rows, void* table, cudaStream_t st);

@@ -839,7 +839,8 @@ void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points, cudaStream_t stream) : cfg_(cfg) {
+MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points, cudaStream_t stream, const MsmEngine* share_table)
+    : cfg_(cfg) {
     if (!cfg_.fixed || cfg_.c0 <= 0 || cfg_.c0 > cfg_.c) cfg_.c0 = cfg_.c;
     if (cfg_.c < 2 || cfg_.c > kMaxWindow || cfg_.c0 + cfg_.c * (cfg_.W - 1) < 256)
         throw CudaError(-1, "MsmEngine: bad window configuration");
@@ -856,7 +857,16 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     tasks_max_ = entries_max_ / cfg_.L + keys_max_ + 1;
     size_t rows = cfg_.fixed ? cfg_.W : 1;
     table_bytes_ = rows * table_points * 96;
-    table_ = dev_alloc<uint8_t>(table_bytes_);
+    if (share_table) {
+        const MsmConfig& o = share_table->cfg_;
+        if (!cfg_.fixed || !o.fixed || o.c != cfg_.c || o.c0 != cfg_.c0 || o.W != cfg_.W || o.n != cfg_.n || o.bases_period != cfg_.bases_period)
+            throw CudaError(-1, "MsmEngine: shared table has a different layout");
+        table_ = share_table->table_;
+        owns_table_ = false;
+        points = nullptr;
+    } else {
+        table_ = dev_alloc<uint8_t>(table_bytes_);
+    }
     counts_ = dev_alloc<uint32_t>(keys_max_ + 1);
     offsets_ = dev_alloc<uint32_t>(keys_max_ + 1);
     cursor_ = dev_alloc<uint32_t>(keys_max_ + 1);
@@ -935,7 +945,8 @@ MsmEngine::~MsmEngine() {
     if (copy_start_) cudaEventDestroy(copy_start_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
     cudaFree(pair_base_); cudaFree(aff_buf_[0]); cudaFree(aff_buf_[1]);
-    cudaFree(table_); cudaFree(counts_); cudaFree(offsets_); cudaFree(cursor_); cudaFree(task_base_); cudaFree(entries_);
+    if (owns_table_) cudaFree(table_);
+    cudaFree(counts_); cudaFree(offsets_); cudaFree(cursor_); cudaFree(task_base_); cudaFree(entries_);
     cudaFree(sorted_tasks_); cudaFree(size_hist_); cudaFree(scan_tmp_); cudaFree(partials_); cudaFree(chunk_sums_);
     cudaFree(group_sums_);
     cudaFree(seg_t_); cudaFree(seg_r_); cudaFree(seg_ident_); cudaFree(chunk_sums_r_);

@@ -50,7 +50,10 @@ struct MsmConfig {
 class MsmEngine {
 public:
     // points: n affine points (blst_p1_affine layout), device or host pointer (host_points says which).
-    MsmEngine(const MsmConfig& cfg, const void* points, bool host_points, cudaStream_t stream);
+    // share_table: another FIXED engine with the same bases and window layout whose table this one reads instead of
+    // building its own (the lanes of a settings object: one table in L2 for all of them); it must outlive this engine.
+    MsmEngine(const MsmConfig& cfg, const void* points, bool host_points, cudaStream_t stream,
+              const MsmEngine* share_table = nullptr);
     ~MsmEngine();
     MsmEngine(const MsmEngine&) = delete;
 
@@ -96,6 +99,7 @@ private:
     cudaEvent_t copy_ev_[kCopyChunks] = {};
     cudaEvent_t copy_start_ = nullptr;
     void* table_ = nullptr;      // affine rows
+    bool owns_table_ = true;
     uint32_t* counts_ = nullptr;  // [keys+1]
     uint32_t* offsets_ = nullptr;
     uint32_t* cursor_ = nullptr;

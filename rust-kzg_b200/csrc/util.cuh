@@ -13,12 +13,17 @@ struct CudaError : public std::runtime_error {
     CudaError(int c, const std::string& what) : std::runtime_error(what), code(c) {}
 };
 
+// Error domains: code 1 is the reference's Err(String) -- invalid input, C_KZG_BADARGS at the c-kzg edge -- and is only
+// ever thrown explicitly by validation code.  CUDA runtime failures carry kCudaErrorBase + cudaError_t, so that
+// cudaErrorInvalidValue (= 1) can never be mistaken for a validation error.  Negative codes: internal misuse.
+constexpr int kCudaErrorBase = 0x10000;
 #define B200_CUDA_CHECK(expr)                                                                               \
     do {                                                                                                    \
         cudaError_t _e = (expr);                                                                            \
         if (_e != cudaSuccess)                                                                              \
-            throw ::b200::CudaError((int)_e, std::string(cudaGetErrorString(_e)) + " at " + __FILE__ + ":" + \
-                                                 std::to_string(__LINE__) + " in " #expr);                  \
+            throw ::b200::CudaError(::b200::kCudaErrorBase + (int)_e,                                       \
+                                    std::string(cudaGetErrorString(_e)) + " at " + __FILE__ + ":" +          \
+                                        std::to_string(__LINE__) + " in " #expr);                           \
     } while (0)
 
 #define B200_LAUNCH_CHECK() B200_CUDA_CHECK(cudaGetLastError())

@@ -183,6 +183,15 @@ class KZGSettings:
         ptr = getattr(self.c, name)
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(count, width)).copy()
 
+    def x_ext_fft_columns(self):
+        """the [128][64] blst_p1 of CKZGSettings.x_ext_fft_columns, read through the 128 row pointers exactly as the
+        reference's TryFrom<&CKZGSettings> does (blst/src/types/kzg_settings.rs:398-417)"""
+        rows = C.cast(self.c.x_ext_fft_columns, C.POINTER(C.c_void_p))
+        out = np.zeros((128, 64, 18), np.uint64)
+        for r in range(128):
+            out[r] = np.ctypeslib.as_array(C.cast(rows[r], C.POINTER(C.c_uint64)), shape=(64, 18))
+        return out
+
     @property
     def max_batch(self):
         return _L().b200_kzg_max_batch(C.byref(self.c))

@@ -9,6 +9,7 @@ import pytest
 from conftest import ROOT, SETUP_PATH
 
 EXE = "/tmp/b200_ckzg_roundtrip"
+EXE_T = "/tmp/b200_ckzg_threads"
 
 
 def _build():
@@ -19,6 +20,9 @@ def _build():
     subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "examples", "ckzg_roundtrip.c"), "-L" + lib_dir, "-lb200kzg",
                            "-Wl,-rpath," + lib_dir, "-o", EXE])
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-pthread", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "ckzg_threads.c"), "-L" + lib_dir, "-lb200kzg",
+                           "-Wl,-rpath," + lib_dir, "-o", EXE_T])
 
 
 def test_c_consumer_builds_and_refuses_without_gpu():
@@ -28,6 +32,8 @@ def test_c_consumer_builds_and_refuses_without_gpu():
         pytest.skip("GPU present: covered by the gpu test")
     r = subprocess.run([EXE, SETUP_PATH], capture_output=True, text=True)
     assert r.returncode == 3 and "load_trusted_setup_file" in r.stderr     # C_KZG_ERROR: no device, no CPU path
+    r = subprocess.run([EXE_T, SETUP_PATH, "commit", "4", "2"], capture_output=True, text=True)
+    assert r.returncode == 3 and "load_trusted_setup_file" in r.stderr
 
 
 @pytest.mark.gpu
@@ -35,3 +41,17 @@ def test_c_consumer_round_trips():
     _build()
     r = subprocess.run([EXE, SETUP_PATH], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op,threads", [("commit", 16), ("blob_proof", 8), ("proof", 8), ("mixed", 12)])
+def test_c_pthread_consumer_is_bit_exact_under_coalescing(op, threads):
+    """examples/ckzg_threads.c: N pthreads call the unmodified single-blob symbols on pageable blobs; concurrent requests
+    share launch sequences (csrc/coalesce.cuh) and every result must equal the one computed with a single thread active"""
+    import json
+    _build()
+    r = subprocess.run([EXE_T, SETUP_PATH, op, str(threads), "6", "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["mismatches"] == 0 and line["errors"] == 0 and line["isolation_failures"] == 0
+    assert line["calls"] == threads * 6

@@ -34,6 +34,19 @@ def test_settings_arrays_match_oracle(B, K, ts, oracle_settings):
     assert np.array_equal(ts.array("g1_values_monomial", 4096, 18), oracle_settings.g1_monomial)
 
 
+def test_x_ext_fft_columns_match_oracle(B, K, ts, oracle_settings):
+    """the host x_ext_fft_columns a TryFrom<&CKZGSettings>-style reader walks (blst/src/types/kzg_settings.rs:398-417):
+    128 non-NULL rows of 64 points, the same group elements as FsKZGSettings::new builds (:84-101)"""
+    got = ts.x_ext_fft_columns()
+    want = K.x_ext_fft_columns(oracle_settings)
+    assert got.shape == want.shape == (128, 64, 18)
+    for r in (0, 1, 63, 64, 127):
+        for o in (0, 17, 63):
+            assert K.p1_compress(got[r, o]) == K.p1_compress(want[r, o]), (r, o)
+    # all of them, through one batched comparison of affine forms
+    assert np.array_equal(K.p1s_to_affine(got.reshape(-1, 18)), K.p1s_to_affine(want.reshape(-1, 18)))
+
+
 def test_blob_to_kzg_commitment_vectors(B, ts, vectors, golden_blobs):
     for c in vectors["blob_to_kzg_commitment"]:
         try:

@@ -86,3 +86,78 @@ def test_concurrent_prepared_msm(B, K, lagrange_affine):
         t.join()
     msm.close()
     assert not errors, errors
+
+
+def test_sixteen_threads_mixed_entry_points_coalesce_bit_exact(B, K, oracle_settings):
+    """16 host threads on the UNMODIFIED single-blob c-kzg symbols (the way rayon's par_chunks drives them,
+    kzg/src/eip_4844.rs:770-816): concurrent requests are coalesced into shared launch sequences (csrc/coalesce.cuh) and
+    every caller must still get exactly its own result -- checked against the oracle, with invalid blobs mixed in, which
+    must fail alone."""
+    ts = B.KZGSettings.load_trusted_setup_file()
+    rng = np.random.default_rng(34)
+    blobs = _blobs(rng, 8)
+    zs = [bytes(b[64:96]) for b in blobs]
+    want_c = [K.blob_to_kzg_commitment(bytes(b), oracle_settings) for b in blobs]
+    want_p = [K.compute_blob_kzg_proof(bytes(b), c, oracle_settings) for b, c in zip(blobs, want_c)]
+    want_z = [K.compute_kzg_proof(bytes(b), z, oracle_settings) for b, z in zip(blobs, zs)]
+    bad = blobs[0].copy()
+    bad[32 * 7] = 0xFF                                  # element 7 >= r
+    errors = []
+    start = threading.Barrier(16)
+
+    def worker(k):
+        try:
+            start.wait()
+            for rep in range(6):
+                i = (k + rep) % len(blobs)
+                op = (k + rep) % 4
+                if op == 0:
+                    assert ts.blob_to_kzg_commitment(blobs[i]) == want_c[i]
+                elif op == 1:
+                    assert ts.compute_blob_kzg_proof(blobs[i], want_c[i]) == want_p[i]
+                elif op == 2:
+                    assert tuple(ts.compute_kzg_proof(blobs[i], zs[i])) == tuple(want_z[i])
+                else:
+                    with pytest.raises(B.KzgError) as e:
+                        ts.blob_to_kzg_commitment(bad)
+                    assert e.value.code == 1
+                    assert ts.verify_blob_kzg_proof(blobs[i], want_c[i], want_p[i]) is True
+        except Exception as e:
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(16)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    ts.free()
+    assert not errors, errors
+
+
+def test_concurrent_prepared_msm_coalesces(B, K, lagrange_affine):
+    """a prepared 4096-point handle packs concurrent mult_pippenger_prepared calls (different lengths included: short
+    calls are zero-padded) into one launch sequence; each caller gets its own sum"""
+    rng = np.random.default_rng(35)
+    msm = B.PreparedMsm(lagrange_affine)
+    lens = [4096, 4096, 1000, 8, 4096, 2500, 4096, 1]
+    scs = [rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64) for n in lens]
+    want = [K.p1_compress(K.msm_affine(lagrange_affine[:n], s, nthreads=4)) for n, s in zip(lens, scs)]
+    errors = []
+    start = threading.Barrier(8)
+
+    def worker(k):
+        try:
+            start.wait()
+            for rep in range(4):
+                i = (k + rep) % len(lens)
+                assert K.p1_compress(msm.mult(scs[i])) == want[i], (k, rep)
+        except Exception as e:
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    msm.close()
+    assert not errors, errors
