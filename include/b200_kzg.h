@@ -224,6 +224,19 @@ B200_API RustError b200_selftest_p1_compress(uint8_t *out48, const blst_p1 *p, s
  * and the same for a stream of dependent Fp multiplications through *fpmul_per_s */
 B200_API RustError b200_microbench_int(double *imad_per_s, double *fpmul_per_s);
 
+/* ---- multi-GPU MSM (BASELINE configs[4]): one process per GPU, terms sharded by rank ----------
+ * The reference has no multi-GPU code (its sppark plug uses device 0 only, arkworks3-sppark-wlc/sppark/msm/pippenger.cuh:573-575);
+ * this is the north star's own contract.  Rank 0 creates an NCCL unique id and ships it to the other ranks by any means
+ * (MPI, a file, torch.distributed); every rank then prepares ITS slice of the bases on its current device.  A mult call
+ * takes the rank's slice of the scalars and leaves the FULL sum on every rank: local MSM -> ncclAllGather of the 144-byte
+ * partial results -> one-warp quad-tree add, all on one stream.  world == 1 needs neither an id nor NCCL. */
+B200_API int b200_msm_sharded_unique_id(uint8_t id[128]);   /* 0 on success */
+B200_API void *b200_msm_sharded_prepare(const blst_p1_affine local_points[], size_t n_local, int rank, int world, const uint8_t id[128]);
+B200_API RustError b200_msm_sharded_mult(void *sharded, blst_p1 *out, size_t n_local, const blst_fr local_scalars[]);
+B200_API RustError b200_msm_sharded_mult_device(void *sharded, void *out_dev, size_t n_local, const void *scalars_dev, void *stream);
+B200_API void *b200_msm_sharded_local(void *sharded);        /* the rank-local prepared handle (b200_msm_info, profiling) */
+B200_API void b200_msm_sharded_free(void *sharded);
+
 /* number of CUDA devices usable; 0 means every compute entry point will fail */
 B200_API int b200_device_count(void);
 

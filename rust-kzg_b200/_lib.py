@@ -52,6 +52,12 @@ def load():
         "b200_msm_set_profiling": (None, [vp, ci]),
         "b200_msm_profile_read": (RustError, [vp, C.POINTER(C.c_double), C.POINTER(ci)]),
         "b200_g1_sum_device": (RustError, [vp, vp, sz, vp]),
+        "b200_msm_sharded_unique_id": (ci, [vp]),
+        "b200_msm_sharded_prepare": (vp, [vp, sz, ci, ci, vp]),
+        "b200_msm_sharded_mult": (RustError, [vp, vp, sz, vp]),
+        "b200_msm_sharded_mult_device": (RustError, [vp, vp, sz, vp, vp]),
+        "b200_msm_sharded_local": (vp, [vp]),
+        "b200_msm_sharded_free": (None, [vp]),
         "b200_fft_settings_new": (vp, [ci]),
         "b200_fft_settings_free": (None, [vp]),
         "b200_fft_settings_max_width": (sz, [vp]),

@@ -1,4 +1,6 @@
 // capi_msm.cu -- the sppark-shaped MSM FFI (include/b200_kzg.h, section B1) on top of MsmEngine.
+#include <dlfcn.h>
+
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -313,6 +315,141 @@ RustError b200_g1_sum_device(void* out_dev, const void* points_dev, size_t n, vo
     return guarded([&] {
         require_device();
         launch_g1_sum(points_dev, out_dev, (int)n, (cudaStream_t)stream);   // current device: the pointers are the caller's
+    });
+}
+
+}  // extern "C"
+
+// ---- multi-GPU MSM: one process per GPU, terms sharded by rank ---------------------------------
+// Every rank prepares ITS slice of the bases and passes ITS slice of the scalars; the only exchange is an all-gather of the
+// 144-byte partial results over NCCL (NVLink / NVSwitch) followed by a local add -- NCCL has no reduction over curve points,
+// so the north star's "all-reduce of partial sums" is gather + add.  Everything is enqueued on one stream: the local MSM,
+// the collective and the one-warp quad-tree sum.  NCCL is bound at run time (dlopen of the libnccl.so.2 the process
+// already carries, e.g. torch's), so single-GPU users of this library do not need it.
+namespace {
+struct NcclId128 { char internal[128]; };   // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128)
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId128*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId128, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            if (!nm || !*nm) continue;
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.GetUniqueId = (int (*)(NcclId128*))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void**, int, NcclId128, int))dlsym(api.lib, "ncclCommInitRank");
+        api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+        api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+        api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+    });
+    if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy)
+        throw CudaError(-3, "b200kzg: NCCL (libnccl.so.2) is not available in this process -- the sharded MSM needs it");
+    return api;
+}
+static void nccl_check(int rc, const char* what) {
+    if (rc == 0) return;
+    NcclApi& a = nccl();
+    throw CudaError(-4, std::string(what) + ": " + (a.GetErrorString ? a.GetErrorString(rc) : "NCCL error"));
+}
+struct ShardedMsm {
+    MsmHandle* h = nullptr;       // local engine over this rank's slice of the bases
+    void* comm = nullptr;         // ncclComm_t
+    int rank = 0, world = 1;
+    uint8_t* partial = nullptr;   // 144 B
+    uint8_t* gathered = nullptr;  // world x 144 B
+    uint8_t* total = nullptr;     // 144 B (host-pointer variant)
+    ~ShardedMsm() {
+        if (comm) nccl().CommDestroy(comm);
+        cudaFree(partial); cudaFree(gathered); cudaFree(total);
+        delete h;
+    }
+    // caller holds h->mu and has switched to h->device
+    void enqueue(const void* scalars_dev, const void* scalars_host, size_t n_local, void* out_dev, cudaStream_t st) {
+        h->eng->run(scalars_dev, n_local, 1, true, world > 1 ? partial : (uint8_t*)out_dev, st, scalars_host);
+        if (world > 1) {
+            nccl_check(nccl().AllGather(partial, gathered, 144, /*ncclUint8*/ 1, comm, st), "ncclAllGather");
+            launch_g1_sum(gathered, out_dev, world, st);
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int b200_msm_sharded_unique_id(uint8_t id[128]) {
+    try {
+        NcclId128 u;
+        nccl_check(nccl().GetUniqueId(&u), "ncclGetUniqueId");
+        memcpy(id, u.internal, 128);
+        return 0;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "b200kzg: %s\n", e.what());
+        return -1;
+    }
+}
+void* b200_msm_sharded_prepare(const blst_p1_affine local_points[], size_t n_local, int rank, int world, const uint8_t id[128]) {
+    try {
+        if (!local_points || n_local == 0 || world < 1 || rank < 0 || rank >= world || (world > 1 && !id)) return nullptr;
+        std::unique_ptr<ShardedMsm> s(new ShardedMsm());
+        s->rank = rank;
+        s->world = world;
+        s->h = msm_handle_create(local_points, n_local, true, true, 1);
+        s->partial = dev_alloc<uint8_t>(144);
+        s->gathered = dev_alloc<uint8_t>((size_t)world * 144);
+        s->total = dev_alloc<uint8_t>(144);
+        if (world > 1) {
+            NcclId128 u;
+            memcpy(u.internal, id, 128);
+            nccl_check(nccl().CommInitRank(&s->comm, world, u, rank), "ncclCommInitRank");
+        }
+        return s.release();
+    } catch (const std::exception& e) {
+        fprintf(stderr, "b200kzg: b200_msm_sharded_prepare failed: %s\n", e.what());
+        return nullptr;
+    }
+}
+void b200_msm_sharded_free(void* sh) { delete static_cast<ShardedMsm*>(sh); }
+void* b200_msm_sharded_local(void* sh) { return sh ? static_cast<ShardedMsm*>(sh)->h : nullptr; }
+
+// out_dev: 144 B (device) on every rank = the sum over ALL ranks' terms; asynchronous on `stream`
+RustError b200_msm_sharded_mult_device(void* sh, void* out_dev, size_t n_local, const void* scalars_dev, void* stream) {
+    return guarded([&] {
+        ShardedMsm* s = static_cast<ShardedMsm*>(sh);
+        if (!s) throw CudaError(-1, "null sharded msm handle");
+        if (n_local == 0 || n_local > s->h->npoints) throw CudaError(-1, "n_local exceeds the prepared slice");
+        DeviceScope ds(s->h->device);
+        std::lock_guard<std::mutex> lk(s->h->mu);
+        s->h->enter((cudaStream_t)stream);
+        s->enqueue(scalars_dev, nullptr, n_local, out_dev, (cudaStream_t)stream);
+        s->h->leave_async((cudaStream_t)stream);
+    });
+}
+// host pointers: this rank's n_local scalars in, the full result out on every rank
+RustError b200_msm_sharded_mult(void* sh, blst_p1* out, size_t n_local, const blst_fr local_scalars[]) {
+    return guarded([&] {
+        ShardedMsm* s = static_cast<ShardedMsm*>(sh);
+        if (!s || !out || !local_scalars) throw CudaError(-1, "null argument");
+        if (n_local == 0 || n_local > s->h->npoints) throw CudaError(-1, "n_local exceeds the prepared slice");
+        MsmHandle* h = s->h;
+        DeviceScope ds(h->device);
+        std::lock_guard<std::mutex> lk(h->mu);
+        h->enter(h->stream);
+        h->ensure_staging(n_local, 1);
+        s->enqueue(h->scalars_dev, local_scalars, n_local, s->total, h->stream);
+        B200_CUDA_CHECK(cudaMemcpyAsync(out, s->total, 144, cudaMemcpyDeviceToHost, h->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     });
 }
 

@@ -797,26 +797,23 @@ __global__ void __launch_bounds__(32) k_compress(const uint8_t* __restrict__ jac
     }
     cc::affine_compress(out + (size_t)o * 48, a);
 }
-// sum of `count` Jacobian points by one warp (multi-GPU combine: count = number of ranks)
-__global__ void k_g1_sum(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count) {
-    int lane = threadIdx.x;
-    cc::xyzz_t acc = cc::xyzz_t::inf();
+// sum of `count` Jacobian points by one warp (multi-GPU combine: count = number of ranks).  Lane i takes points i,
+// i + 32, ...; the 32 lane sums are folded by the quad tree of g1_quad.cuh (one plain addition, then every addition on a
+// lane quad: ~4 us each instead of ~13 us), over as few levels as `count` needs.  The result stays quad-distributed
+// and is written as Jacobian (X*ZZ, Y*ZZZ, ZZ), infinity all-zero, like k_group_finish.
+__global__ void __launch_bounds__(32) k_g1_sum(const uint8_t* __restrict__ jac, uint8_t* __restrict__ out, int count) {
+    const int lane = threadIdx.x;
+    xyzz_t acc = xyzz_t::inf();
     for (int i = lane; i < count; i += 32) {
-        cc::xyzz_t p = cc::jac_to_xyzz(cc::load_jac(jac + (size_t)i * 144));
-        cc::xyzz_add(acc, p);
+        xyzz_t p = jac_to_xyzz(load_jac(jac + (size_t)i * 144));
+        xyzz_add(acc, p);
     }
-    for (int d = 16; d >= 1; d >>= 1) {
-        cc::xyzz_t o;
-#pragma unroll
-        for (int k = 0; k < 12; k++) {
-            o.x.v[k] = __shfl_down_sync(0xffffffffu, acc.x.v[k], d);
-            o.y.v[k] = __shfl_down_sync(0xffffffffu, acc.y.v[k], d);
-            o.zzz.v[k] = __shfl_down_sync(0xffffffffu, acc.zzz.v[k], d);
-            o.zz.v[k] = __shfl_down_sync(0xffffffffu, acc.zz.v[k], d);
-        }
-        cc::xyzz_add(acc, o);
-    }
-    if (lane == 0) cc::store_jac(out, cc::xyzz_to_jac(acc));
+    int S = 4;
+    while (S < 32 && S < count) S <<= 1;
+    fp_t q = seg_sum_quad(acc, S);
+    fp_t t = q * shfl_xor_fp(q, 2);
+    if (lane < 2) store_field(out + lane * 48, t);
+    if (lane == 2) store_field(out + 96, q);
 }
 void launch_g1_sum(const void* jac_dev, void* out_jac_dev, int count, cudaStream_t stream) {
     k_g1_sum<<<1, 32, 0, stream>>>((const uint8_t*)jac_dev, (uint8_t*)out_jac_dev, count);

@@ -1,5 +1,6 @@
-"""world_size-2 gloo test of the multi-GPU MSM host logic (sharding, all-gather of 144-byte partials, local add).
-The device pieces are replaced by oracle stand-ins so it runs on CPU; the GPU path uses the same ShardedMsm class."""
+"""world_size-2 gloo test of the multi-GPU MSM host logic: sharding, the unique-id bootstrap (rank 0 creates, everyone
+receives), gather of the 144-byte partials + local add.  The library backend is replaced by an oracle stand-in so it
+runs on CPU; bench.py --gpus N and tests/test_gpu_sharded.py drive the same ShardedMsm class over libb200kzg.so."""
 import os
 import socket
 import sys
@@ -34,31 +35,48 @@ def _worker(rank, world, port, n, q):
     pts = np.tile(L, (n // 4096 + 1, 1))[:n]
     lo, hi = B.shard_bounds(n, rank, world)
 
-    class Handle:                                       # stand-in for PreparedMsm over this rank's slice
-        def mult_device(self, out_ptr, n_local, scalars_ptr, batch, stream):
-            res = K.msm_affine(pts[lo:hi], sc[lo:hi]) if hi > lo else np.zeros(18, np.uint64)
-            holder["partial"].copy_(torch.from_numpy(res.view(np.int64)))
+    class Backend:                                      # stand-in for libb200kzg.so: the oracle computes, gloo gathers
+        def unique_id(self):
+            assert rank == 0                            # only rank 0 may create the id
+            return bytes(range(128))
 
-    holder = {}
+        def prepare(self, p, r, w, uid):
+            assert (r, w) == (rank, world) and np.array_equal(p, pts[lo:hi])
+            return {"uid": uid}
 
-    def alloc(k):
-        t = torch.zeros(k, dtype=torch.int64)
-        if "partial" not in holder:
-            holder["partial"] = t
-        return t
+        def mult(self, h, s):
+            part = K.msm_affine(pts[lo:hi], s) if hi > lo else np.zeros(18, np.uint64)
+            gathered = torch.zeros(18 * world, dtype=torch.int64)
+            dist.all_gather_into_tensor(gathered, torch.from_numpy(part.view(np.int64).copy()))
+            g = gathered.numpy().view(np.uint64).reshape(world, 18)
+            acc = np.zeros(18, np.uint64)
+            for i in range(world):
+                acc = K.p1_add(acc, g[i])
+            return acc
 
-    def g1_sum(out_ptr, pts_ptr, k, stream):
-        g = sm.gathered.numpy().view(np.uint64).reshape(k, 18)
-        acc = np.zeros(18, np.uint64)
-        for i in range(k):
-            acc = K.p1_add(acc, g[i])
-        sm.total.copy_(torch.from_numpy(acc.view(np.int64)))
+        def free(self, h):
+            pass
 
-    sm = B.ShardedMsm(Handle(), rank, world, dist.all_gather_into_tensor, g1_sum, alloc)
-    total = sm.mult(0, hi - lo)
+    def bcast(b):
+        box = [b]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    sm = B.ShardedMsm(pts[lo:hi], rank, world, broadcast=bcast, backend=Backend())
+    total = sm.mult(sc[lo:hi])
     full = K.msm_affine(pts, sc, nthreads=2)
-    q.put((rank, K.p1_compress(total.numpy().view(np.uint64)) == K.p1_compress(full), (lo, hi)))
+    q.put((rank, K.p1_compress(total) == K.p1_compress(full) and sm.uid == bytes(range(128)), (lo, hi)))
+    sm.close()
     dist.destroy_process_group()
+
+
+def test_sharded_msm_fails_loudly_without_a_device():
+    """the product backend has no CPU path: preparing a shard without a GPU raises"""
+    import rust_kzg_b200 as B
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(B.B200Error):
+        B.ShardedMsm(np.zeros((8, 12), np.uint64), 0, 1)
 
 
 @pytest.mark.parametrize("n", [5000, 4097])
