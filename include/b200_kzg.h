@@ -79,6 +79,9 @@ B200_API void b200_msm_plan(size_t npoints, int fixed, int *c, int *c0, int *W, 
  * accumulate kernel did  entries - tasks  mixed additions (a task's first point is a load).  Synchronises the handle's
  * stream. */
 B200_API RustError b200_msm_last_counts(void *msm, size_t *entries, size_t *tasks);
+/* all work counters of the last run, for an exact addition count (bench.py): stats = [entries, tasks, non-empty buckets,
+ * bucket keys, segment-fold bits, buckets per group the marginal reduce sees, digit axes of that reduce, groups] */
+B200_API RustError b200_msm_last_stats(void *msm, uint64_t stats[8]);
 
 
 /* ============================================================================================================== */

@@ -298,6 +298,17 @@ RustError b200_msm_last_counts(void* msm, size_t* entries, size_t* tasks) {
     });
 }
 
+RustError b200_msm_last_stats(void* msm, uint64_t stats[8]) {
+    return guarded([&] {
+        MsmHandle* h = static_cast<MsmHandle*>(msm);
+        if (!h || !stats) throw CudaError(-1, "null argument");
+        DeviceScope ds(h->device);
+        std::lock_guard<std::mutex> lk(h->mu);
+        B200_CUDA_CHECK(cudaDeviceSynchronize());
+        h->eng->last_stats(stats, h->stream);
+    });
+}
+
 void b200_msm_set_profiling(void* msm, int on) {
     MsmHandle* h = static_cast<MsmHandle*>(msm);
     if (h) h->eng->set_profiling(on != 0);

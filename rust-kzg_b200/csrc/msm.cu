@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(256) k_task_hist(const uint32_t* __restrict__ 
         uint32_t cnt = counts[key];
         if (cnt) {
             uint32_t tc = (cnt + L - 1) / L, rem = cnt - (tc - 1) * L;
+            atomicAdd(&sh[0], 1u);   // slot 0 (no task has length 0) counts the non-empty buckets: MsmEngine::last_stats
             atomicAdd(&sh[rem], 1u);
             if (tc > 1) atomicAdd(&sh[L], tc - 1);
         }
@@ -932,6 +933,20 @@ void MsmEngine::last_counts(size_t* entries, size_t* tasks, cudaStream_t stream)
     }
     if (entries) *entries = e;
     if (tasks) *tasks = t;
+}
+
+// [entries, tasks, non-empty buckets, keys, fold bits, buckets per group seen by the marginal reduce, digit axes, groups]
+void MsmEngine::last_stats(uint64_t out[8], cudaStream_t stream) {
+    uint32_t e = 0, t = 0, ne = 0;
+    if (last_nkeys_) {
+        B200_CUDA_CHECK(cudaMemcpyAsync(&e, offsets_ + last_nkeys_, 4, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaMemcpyAsync(&t, task_base_ + last_nkeys_, 4, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaMemcpyAsync(&ne, size_hist_, 4, cudaMemcpyDeviceToHost, stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    const int bits = cfg_.c - 1 - kf_;
+    out[0] = e; out[1] = t; out[2] = ne; out[3] = last_nkeys_; out[4] = (uint64_t)kf_; out[5] = (uint64_t)(nb_ >> kf_);
+    out[6] = (uint64_t)std::max(1, (bits + 4) / 5); out[7] = last_nkeys_ / (size_t)nb_;
 }
 
 MsmEngine::~MsmEngine() {

@@ -78,6 +78,9 @@ public:
     void profile_read(double* accumulate_ms_sum, int* runs);
     // entries (non-zero digits) and accumulate tasks of the last run(); synchronises `stream`
     void last_counts(size_t* entries, size_t* tasks, cudaStream_t stream);
+    // work counters of the last run() for the bench's addition count: [entries, tasks, non-empty buckets, keys, fold
+    // bits, buckets per group the marginal reduce sees, digit axes, groups]; synchronises `stream`
+    void last_stats(uint64_t out[8], cudaStream_t stream);
 
 private:
     MsmConfig cfg_;

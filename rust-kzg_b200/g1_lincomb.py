@@ -39,7 +39,11 @@ def msm_plan(npoints, fixed=True):
 class PreparedMsm:
     """Fixed-base MSM context resident on the GPU (prepare_msm)."""
 
-    def __init__(self, affine_points):
+    def __init__(self, affine_points, _borrowed_handle=None):
+        self._owned = _borrowed_handle is None
+        if not self._owned:                      # view of a handle owned by someone else (ShardedMsm.local_handle)
+            self.h, self.npoints = _borrowed_handle, 0
+            return
         pts = _u64(affine_points, 12)
         self.npoints = pts.shape[0]
         self.h = _L().prepare_msm(_p(pts), self.npoints)
@@ -57,6 +61,18 @@ class PreparedMsm:
         e, t = C.c_size_t(), C.c_size_t()
         _lib.check(_L().b200_msm_last_counts(self.h, C.byref(e), C.byref(t)))
         return e.value, t.value
+
+    def last_stats(self):
+        """work counters of the last run (b200_msm_last_stats) and the additions they imply, by kernel"""
+        st = np.zeros(8, np.uint64)
+        _lib.check(_L().b200_msm_last_stats(self.h, _p(st)))
+        e, t, ne, keys, kf, nbr, D, groups = (int(v) for v in st)
+        adds = {"accumulate": e - t,                      # a task's first point is a load
+                "bucket_combine": t - ne,                  # partials of buckets that were cut into several tasks
+                "segment_fold": (keys + ne) if kf else 0,  # per bucket: acc += run, and run += B when the bucket is non-empty
+                "marginal_reduce": groups * (D + (1 if kf else 0)) * nbr}   # every (segment) sum enters D (+1) marginal trees
+        return {"entries": e, "tasks": t, "nonempty_buckets": ne, "bucket_keys": keys, "fold_bits": kf, "adds": adds,
+                "adds_total": sum(adds.values())}
 
     def mult(self, scalars):
         """multi_scalar_mult_prepared: -> Jacobian point (18 u64)."""
@@ -86,9 +102,9 @@ class PreparedMsm:
         return ms.value, runs.value
 
     def close(self):
-        if self.h:
+        if self.h and self._owned:
             _L().b200_free_msm(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:

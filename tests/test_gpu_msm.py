@@ -231,3 +231,37 @@ def test_narrow_first_window(B, K, lagrange_affine, c, c0):
         sc = K.fr_from_ints(ints)
         assert K.p1_compress(h.mult(sc)) == K.p1_compress(K.msm_affine(lagrange_affine, sc, nthreads=8)), name
     h.close()
+
+
+@pytest.mark.parametrize("logn", [20, 21])
+def test_baseline_config_default_plan_folded_oracle(B, K, lagrange_affine, logn):
+    """BASELINE configs[1] itself (2^20 terms, the auto-selected window plan with the segment fold) and the per-GPU share
+    of configs[4] (2^21): host-pointer call, device-pointer call and an adversarial vector, against the folded-scalar
+    oracle (tiled bases P_i = L[i mod 4096])."""
+    import torch
+    n = 1 << logn
+    rng = np.random.default_rng(300 + logn)
+    sc = rand_fr_mont(rng, n)
+    pts = np.tile(lagrange_affine, (n // 4096, 1))
+    cur = sc
+    while cur.shape[0] > 4096:
+        half = cur.shape[0] // 2
+        cur = K.fr_add(cur[:half], cur[half:])
+    exp = K.p1_compress(K.msm_affine(lagrange_affine, np.ascontiguousarray(cur), nthreads=8))
+    h = B.PreparedMsm(pts)
+    c = B.msm_plan(n, True)["c"]
+    assert h.info()["c"] == c and c >= 17          # the default plan at this size is a wide window: the fold is on the path
+    assert K.p1_compress(h.mult(sc)) == exp
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    d_out = torch.zeros(18, dtype=torch.int64, device="cuda")
+    h.mult_device(d_out.data_ptr(), n, d_sc.data_ptr(), 1, 0)
+    torch.cuda.synchronize()
+    assert K.p1_compress(d_out.cpu().numpy().view(np.uint64)) == exp
+    st = h.last_stats()
+    assert st["entries"] > 0 and st["adds"]["accumulate"] == st["entries"] - st["tasks"] and st["fold_bits"] == c - 16
+    if logn == 20:
+        # every scalar equal: all 2^20 entries of a window in ONE bucket (the all-0x02 consensus blob at MSM scale)
+        same = np.tile(K.fr_from_ints([0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % R_MOD]), (n, 1))
+        tot = K.fr_from_ints([(0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % R_MOD) * (n // 4096) % R_MOD] * 4096)
+        assert K.p1_compress(h.mult(same)) == K.p1_compress(K.msm_affine(lagrange_affine, tot, nthreads=8))
+    h.close()

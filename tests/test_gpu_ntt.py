@@ -138,3 +138,35 @@ def test_fft_g1_roundtrip_and_slow(B, K, oracle_settings):
     with pytest.raises(B200Error, match="longer than the available max width"):
         fs.fft_g1(np.tile(pts, (2, 1)))
     fs.close()
+
+
+@pytest.mark.parametrize("logn,inverse", [(10, False), (10, True), (12, False)])
+def test_fft_g1_matches_oracle_mid_sizes(B, K, oracle_settings, logn, inverse):
+    """fft_g1 at 2^10 / 2^12 (several butterfly stages per lane quad, every twiddle class) vs the oracle's fft_g1_fast"""
+    n = 1 << logn
+    fs, ofs = B.FFTSettings(12), K.FFTSettings(12)
+    pts = np.ascontiguousarray(np.tile(oracle_settings.g1_monomial, (max(1, n // 4096), 1))[:n]).copy()
+    pts[7] = 0                              # a point at infinity
+    pts[9] = pts[8]                         # a repeated point
+    got = fs.fft_g1(pts, inverse)
+    exp = ofs.fft_g1(pts, inverse)
+    assert np.array_equal(K.p1s_to_affine(got), K.p1s_to_affine(exp))
+    fs.close()
+
+
+def test_fft_g1_roundtrip_2p15(B, K, oracle_settings):
+    """the reference's bench size (kzg-bench/src/benches/fft.rs: scale 15): inverse(forward(x)) == x on all 2^15 points,
+    and three outputs against the slow-DFT identity out[k] = sum_j w^(jk) P_j (a 2^15-term oracle MSM each)"""
+    n = 1 << 15
+    fs, ofs = B.FFTSettings(15), K.FFTSettings(15)
+    pts = np.ascontiguousarray(np.tile(oracle_settings.g1_monomial, (n // 4096, 1)))
+    fwd = fs.fft_g1(pts, False)
+    back = fs.fft_g1(fwd, True)
+    aff = K.p1s_to_affine(pts)
+    assert np.array_equal(K.p1s_to_affine(back), aff)
+    roots = ofs.roots_of_unity
+    for k in (1, 4097, n - 1):
+        idx = (np.arange(n, dtype=np.int64) * k) % n
+        want = K.msm_affine(aff, np.ascontiguousarray(roots[idx]), nthreads=8)
+        assert K.p1_compress(fwd[k]) == K.p1_compress(want), k
+    fs.close()
