@@ -101,6 +101,8 @@ int main(int argc, char **argv) {
             if (w[t].op != OP_COMMIT && run_one(&w[t], b, &w[t].proof[b], &w[t].y[b]) != C_KZG_OK) { fprintf(stderr, "reference proof failed\n"); return 4; }
         }
     }
+    uint64_t st0[5], st[5];
+    b200_kzg_coalesce_stats(&s, st0);          /* counters up to here belong to the single-threaded reference pass */
     pthread_t *th = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
     for (int t = 0; t < T; t++) pthread_create(&th[t], NULL, worker_main, &w[t]);
     pthread_barrier_wait(&start);
@@ -108,6 +110,8 @@ int main(int argc, char **argv) {
     long mism = 0, errs = 0;
     for (int t = 0; t < T; t++) { pthread_join(th[t], NULL); mism += w[t].mismatches; errs += w[t].errors; }
     double dt = now_s() - t0;
+    b200_kzg_coalesce_stats(&s, st);
+    for (int i = 0; i < 4; i++) st[i] -= st0[i];
     /* an invalid blob among valid concurrent callers must fail alone (per-request status, not per-batch) */
     long isolation_failures = 0;
     {
@@ -119,8 +123,11 @@ int main(int argc, char **argv) {
         free(bad);
     }
     printf("{\"op\": \"%s\", \"threads\": %d, \"calls\": %ld, \"seconds\": %.6f, \"per_s\": %.1f, \"mismatches\": %ld, \"errors\": %ld, "
-           "\"isolation_failures\": %ld, \"input_memory\": \"pageable (malloc)\"}\n",
-           opname, T, (long)T * calls, dt, (double)T * calls / dt, mism, errs, isolation_failures);
+           "\"isolation_failures\": %ld, \"input_memory\": \"pageable (malloc)\", \"batches\": %llu, \"mean_batch\": %.2f, "
+           "\"max_batch\": %llu, \"mean_lane_wait_us\": %.1f, \"mean_lane_exec_us\": %.1f}\n",
+           opname, T, (long)T * calls, dt, (double)T * calls / dt, mism, errs, isolation_failures, (unsigned long long)st[0],
+           st[0] ? (double)st[1] / (double)st[0] : 0.0, (unsigned long long)st[4], st[0] ? 1e-3 * (double)st[2] / (double)st[0] : 0.0,
+           st[0] ? 1e-3 * (double)st[3] / (double)st[0] : 0.0);
     free_trusted_setup(&s);
     return (mism || errs || isolation_failures) ? 1 : 0;
 }

@@ -82,6 +82,9 @@ B200_API RustError b200_msm_last_counts(void *msm, size_t *entries, size_t *task
 /* all work counters of the last run, for an exact addition count (bench.py): stats = [entries, tasks, non-empty buckets,
  * bucket keys, segment-fold bits, buckets per group the marginal reduce sees, digit axes of that reduce, groups] */
 B200_API RustError b200_msm_last_stats(void *msm, uint64_t stats[8]);
+/* 1 when the last run on this handle used the batch-affine bucket accumulation (k_accumulate_affine: 6 field
+ * multiplications per addition + a shared inversion), 0 for the XYZZ task kernel (10 per addition) */
+B200_API int b200_msm_last_affine(void *msm);
 
 
 /* ============================================================================================================== */
@@ -213,6 +216,10 @@ B200_API C_KZG_RET b200_blob_to_kzg_commitment_device(void *out48_dev, const voi
 B200_API C_KZG_RET b200_compute_kzg_proof_device(void *proofs48_dev, void *y32_dev, const void *blobs_dev, const void *z32_dev, size_t n, int z_reduce, int *status_dev, const KZGSettings *s, void *stream);
 B200_API int b200_kzg_launches(const KZGSettings *s);
 B200_API int b200_kzg_max_batch(const KZGSettings *s);
+/* Concurrent calls of the single-blob functions above are coalesced into shared launch sequences (csrc/coalesce.cuh).
+ * Counters since load: out = [batches run, requests served, ns leaders waited for a device lane, ns batches spent on a
+ * lane, largest batch].  B200_KZG_COALESCE=1 disables packing, B200_KZG_LANES=k limits the lanes single calls may use. */
+B200_API void b200_kzg_coalesce_stats(const KZGSettings *s, uint64_t out[5]);
 B200_API void b200_selftest_sha256(uint8_t out[32], const uint8_t *msg, size_t len, int portable);
 
 /* ---- device self-test hooks: elementwise field / point kernels on host arrays, used by the parity tests ------- */

@@ -7,6 +7,7 @@
 // same way, kzg/src/eip_4844.rs:105-145) -- but instead of rebuilding an FsKZGSettings on every call
 // (blst/src/types/kzg_settings.rs:314-437) the resident context is looked up.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -81,12 +82,13 @@ struct LanePool {
     static constexpr unsigned kFull = (1u << KzgSettingsDev::kLanes) - 1;
     std::mutex m;
     std::condition_variable cv;
+    unsigned usable = kFull;      // lanes a single taker may get (B200_KZG_LANES limits them; take-all always takes all)
     unsigned free_mask = kFull;
     int all_waiters = 0;
     int acquire_any() {
         std::unique_lock<std::mutex> lk(m);
-        cv.wait(lk, [&] { return free_mask != 0 && all_waiters == 0; });
-        int lane = __builtin_ctz(free_mask);
+        cv.wait(lk, [&] { return (free_mask & usable) != 0 && all_waiters == 0; });
+        int lane = __builtin_ctz(free_mask & usable);
         free_mask &= ~(1u << lane);
         return lane;
     }
@@ -132,6 +134,8 @@ struct KzgCtx {
     Coalescer co;
     int device = 0;            // CUDA device the context lives on: every entry point switches to it (DeviceScope)
     int co_cap = 0;            // most single-blob requests packed into one launch sequence (<= max_batch)
+    // coalescer counters (b200_kzg_coalesce_stats): batches run, requests served, ns spent waiting for a lane, ns on a lane
+    std::atomic<uint64_t> st_batches{0}, st_requests{0}, st_wait_ns{0}, st_exec_ns{0}, st_max_batch{0};
     std::unique_ptr<KzgSettingsDev> dev;
     int max_batch = 0;
     Stage stage[KzgSettingsDev::kLanes];
@@ -279,6 +283,10 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
         if (ctx->max_batch < 1) ctx->max_batch = 1;
         ctx->co_cap = std::max(1, std::min(ctx->max_batch, env_int("B200_KZG_COALESCE", ctx->max_batch)));
         ctx->co.max_batches = KzgSettingsDev::kLanes + 2;   // one per lane in flight + the ones filling
+        {
+            const int lanes = std::max(1, std::min((int)KzgSettingsDev::kLanes, env_int("B200_KZG_LANES", KzgSettingsDev::kLanes)));
+            ctx->pool.usable = (1u << lanes) - 1;
+        }
         const int mb = ctx->max_batch;
         for (Stage& st : ctx->stage) st.init(mb);
         ctx->stream = ctx->stage[0].stream;
@@ -518,13 +526,22 @@ C_KZG_RET coalesced_call(KzgCtx& ctx, int kind, const uint8_t* blob, const uint8
     if (cl.leader) {
         int rc = C_KZG_OK;
         try {
+            const auto t0 = std::chrono::steady_clock::now();
             OneLane ln(ctx);   // blocks while every lane is busy: meanwhile the batch keeps filling
+            const auto t1 = std::chrono::steady_clock::now();
             const int n = co.close(B);
             Stage& g = ctx.stage[ln.lane];
             if (kind == CO_COMMIT) enqueue_commit(ctx, ln.lane, B->h_in, n, B->out48(0), B->status());
             else if (kind == CO_PROOF) enqueue_proof(ctx, ln.lane, B->h_in, B->z(0), n, B->out48(0), B->y32(0), B->status());
             else enqueue_blob_proof(ctx, ln.lane, B->h_in, B->comm(0), B->z(0), n, B->out48(0), B->status(), B->status2());
             B200_CUDA_CHECK(cudaStreamSynchronize(g.stream));
+            const auto t2 = std::chrono::steady_clock::now();
+            ctx.st_batches++;
+            ctx.st_requests += (uint64_t)n;
+            ctx.st_wait_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+            ctx.st_exec_ns += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count();
+            uint64_t mx = ctx.st_max_batch.load();
+            while ((uint64_t)n > mx && !ctx.st_max_batch.compare_exchange_weak(mx, (uint64_t)n)) {}
         } catch (const std::exception& e) {
             cudaGetLastError();
             fprintf(stderr, "b200kzg: %s\n", e.what());
@@ -1138,6 +1155,14 @@ C_KZG_RET b200_selftest_pairings_verify(bool* ok, const blst_p1* a1, int qa, con
 int b200_kzg_launches(const KZGSettings* s) {
     auto ctx = find_ctx(s);
     return ctx ? ctx->dev->launches_last() : 0;
+}
+// coalescer counters since load: [batches, requests, ns waiting for a lane, ns on a lane (enqueue to drained), largest batch]
+void b200_kzg_coalesce_stats(const KZGSettings* s, uint64_t out[5]) {
+    auto ctx = find_ctx(s);
+    if (!out) return;
+    for (int i = 0; i < 5; i++) out[i] = 0;
+    if (!ctx) return;
+    out[0] = ctx->st_batches; out[1] = ctx->st_requests; out[2] = ctx->st_wait_ns; out[3] = ctx->st_exec_ns; out[4] = ctx->st_max_batch;
 }
 int b200_kzg_max_batch(const KZGSettings* s) {
     auto ctx = find_ctx(s);

@@ -50,6 +50,11 @@ MsmConfig choose_config(size_t n, bool fixed, int max_batch) {
     cfg.n = n;
     cfg.max_batch = fixed ? max_batch : 1;
     cfg.L = env_int("B200_MSM_L", 64);
+    // batch-affine accumulation (6 instead of 10 field multiplications per bucket addition, k_accumulate_affine): bit-exact
+    // and tested, but OFF by default -- measured on B200 it loses to the XYZZ task kernel (7.3 - 7.9 ms against 4.95 ms at
+    // 2^20): the 24-36 lock-step rounds each end in one field inversion whose latency (~60 us even with the bingcd inverse)
+    // the two or three resident CTAs cannot hide (profiles/r02_affine.md).  B200_MSM_AFFINE=1 turns it on for A/B runs.
+    cfg.affine = fixed && lg >= 17 && env_int("B200_MSM_AFFINE", 0) != 0;
     return cfg;
 }
 
@@ -278,6 +283,11 @@ RustError mult_pippenger(blst_p1* out, const blst_p1_affine points[], size_t npo
     });
 }
 
+/* 1 when the last run on this handle used the batch-affine accumulation (k_accumulate_affine), else 0 */
+int b200_msm_last_affine(void* msm) {
+    MsmHandle* h = static_cast<MsmHandle*>(msm);
+    return h && h->eng->last_run_affine() ? 1 : 0;
+}
 void b200_msm_info(void* msm, int* c, int* W, size_t* table_bytes, int* launches) {
     MsmHandle* h = static_cast<MsmHandle*>(msm);
     if (!h) return;

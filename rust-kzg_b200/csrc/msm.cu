@@ -112,10 +112,17 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     __syncthreads();
     return base + x - v;
 }
-// f: 0 = identity; f > 0: ceil(x / f) (task counts); f | 0x80000000: floor(x / f) (pair counts)
-__device__ __forceinline__ uint32_t scan_map(uint32_t x, uint32_t f) {
+// f: 0 = identity; 0 < f < 2^30: ceil(x / f) (task counts of a bucket with x entries);
+// f = kScanSegments | S: `in` holds bucket OFFSETS and the value is the number of chunks of the global S-entry grid the
+// bucket [in[i], in[i+1]) touches -- its segment count in the batch-affine accumulation (k_accumulate_affine)
+static constexpr uint32_t kScanSegments = 0x40000000u;
+__device__ __forceinline__ uint32_t scan_map(const uint32_t* __restrict__ in, size_t i, uint32_t f) {
+    const uint32_t x = in[i];
     if (f == 0) return x;
-    if (f & 0x80000000u) return x / (f & 0x7fffffffu);
+    if (f & kScanSegments) {
+        const uint32_t S = f & (kScanSegments - 1), x1 = in[i + 1];
+        return x1 > x ? (x1 - 1) / S - x / S + 1 : 0;
+    }
     return (x + f - 1) / f;
 }
 __global__ void __launch_bounds__(kScanBlock) k_scan_partial(const uint32_t* __restrict__ in, size_t n, uint32_t f,
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_partial(const uint32_t* __r
     uint32_t s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; k++)
-        if (base + k < n) { uint32_t x = in[base + k]; s += scan_map(x, f); }
+        if (base + k < n) s += scan_map(in, base + k, f);
     uint32_t total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
@@ -155,8 +162,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_final(const uint32_t* __res
     uint32_t v[kScanItems], s = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) {
-        uint32_t x = base + k < n ? in[base + k] : 0;
-        v[k] = scan_map(x, f);
+        v[k] = base + k < n ? scan_map(in, base + k, f) : 0;
         s += v[k];
     }
     uint32_t total;
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(256) k_task_emit(const uint32_t* __restrict__ 
 // step gathers one 96-byte affine point (six 128-bit read-only loads) and does a mixed addition (8M + 2S).
 // MINB = CTAs per SM the register allocation is held to: 3 (<= 168 registers) or 4 (<= 128)
 template <bool PREFETCH, int MINB>
-__global__ void __launch_bounds__(kAccThreads, MINB) k_accumulate(const uint8_t* __restrict__ table,
+__global__ void __launch_bounds__(kAccThreads, MINB) k_accumulate(const uint8_t* __restrict__ table, const uint32_t stride,
                                                             const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ sorted_tasks,
                                                             const uint32_t* __restrict__ n_tasks_ptr,
@@ -276,13 +282,13 @@ __global__ void __launch_bounds__(kAccThreads, MINB) k_accumulate(const uint8_t*
         // software pipeline: the gather of point k+1 (index load, then six 128-bit loads) is in flight during the
         // ~4000-instruction addition of point k
         uint32_t v = e[0];
-        affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
+        affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * stride);
         for (uint32_t k = 0; k < len; k++) {
             affine_t cur = p;
             uint32_t cv = v;
             if (k + 1 < len) {
                 v = e[k + 1];
-                p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
+                p = load_affine(table + (size_t)(v & 0x7fffffffu) * stride);
             }
             cur.y = cur.y.cneg(cv >> 31);
             xyzz_add_affine(acc, cur);
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(kAccThreads, MINB) k_accumulate(const uint8_t*
     } else {
         for (uint32_t k = 0; k < len; k++) {
             uint32_t v = e[k];
-            affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
+            affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * stride);
             p.y = p.y.cneg(v >> 31);
             xyzz_add_affine(acc, p);
         }
@@ -299,154 +305,229 @@ __global__ void __launch_bounds__(kAccThreads, MINB) k_accumulate(const uint8_t*
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 5a: batch-affine pre-reduction.  A mixed XYZZ addition costs 8M + 2S; adding two AFFINE points costs 3M once
-// 1/(x2 - x1) is known, and inverting K denominators together (Montgomery's trick: 3M each + one inversion) makes
-// that 6M per addition.  The inversion itself is the binary-Euclid routine, which runs on the ALU pipe while the
-// multiplications keep the FMA-heavy pipe busy.  Buckets are summed as trees: every round adds adjacent pairs of each
-// bucket's point list (all pairs of all buckets are independent, so a thread takes K consecutive pairs of the flat
-// pair list, across bucket boundaries), halving the lists; after a few rounds the XYZZ task kernel finishes the rest.
-// All exceptional cases are explicit: infinity operands, P + P (tangent slope) and P + (-P) (result infinity).
-static constexpr int kAffK = 16;  // pairs per thread = denominators per inversion
+// 5b: batch-affine bucket accumulation (the reference's own fastest CPU tables work the same way: WbitsTable's
+// batch-affine tree, kzg/src/msm/wbits.rs:442-488, and arkmsm's BatchAdder, kzg/src/msm/arkmsm/batch_adder.rs).
+//
+// A mixed XYZZ addition costs 8M + 2S = 10 field multiplications.  Adding two AFFINE points costs 3 (lambda = dy/dx,
+// x3 = lambda^2 - x1 - x2, y3 = lambda (x1 - x3) - y1) once 1/dx is known, and Montgomery's trick gives 1/dx for a
+// whole batch at 3 multiplications each plus ONE inversion: 6 per addition.  What makes it pay on this machine is the
+// batch: one CTA inverts 128 lanes x K slots = 1280 denominators at a time, so the binary-Euclid inversion (ALU pipe)
+// and the product tree that shares it (~5 multiplications per lane and step) are a few per cent of the work.
+//
+// Work decomposition: the sorted entry list is cut into CHUNKS of S consecutive entries -- a global grid, independent
+// of the bucket boundaries -- and every thread owns K chunks ("slots"; chunk c = k * G + g for thread g of G).  In step
+// t every slot consumes entry t of its chunk: the first entry of a bucket (or of the chunk) starts a new affine
+// accumulator, every other entry is added to it.  All slots of all threads advance in lock step, so the whole machine
+// does the same amount of work (no tail, whatever the bucket sizes are) and every step is one batch inversion per CTA.
+// A bucket that straddles chunk boundaries leaves one partial sum per chunk it touches ("segment"); the partial slots
+// are numbered bucket-major (task_base, from the segment-count scan), so the existing k_bucket_combine folds them and
+// the reduce stages are unchanged.  The running sums live in an L2-resident scratch array (96 B per slot), the prefix
+// products of Montgomery's trick in shared memory.
+//
+// Exceptional cases, all explicit: infinity in the table or as the running sum (after P + (-P)), P + P (tangent: the
+// denominator becomes 2y and the numerator 3x^2), P + (-P) (infinity; no denominator).
+static constexpr int kBaThreads = 128;
+static constexpr uint32_t kEntryStart = 1u << 30;           // entry flag: first entry of its bucket
+static constexpr uint32_t kEntryIndex = kEntryStart - 1;    // table index bits (sign stays in bit 31)
+enum { BA_NOP = 0, BA_LOAD = 1, BA_ADD = 2, BA_SKIP = 3, BA_COPY = 4, BA_DBL = 5, BA_INF = 6 };
 
-struct AffinePair {
-    affine_t p1, p2;
-};
-// gather mode (round 0): points come from the table through the sorted entries (index | sign << 31)
-__device__ __forceinline__ affine_t load_round_point(const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
-                                                     const uint8_t* __restrict__ buf, size_t pos, bool gather) {
-    if (gather) {
-        uint32_t v = entries[pos];
-        affine_t p = load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
-        if (!p.is_inf()) p.y = p.y.cneg(v >> 31);
-        return p;
+// after the scatter: flag the first entry of every non-empty bucket; count the non-empty buckets (size_hist[0])
+__global__ void __launch_bounds__(256) k_mark_starts(const uint32_t* __restrict__ offsets, size_t nkeys, uint32_t* __restrict__ entries,
+                                                     uint32_t* __restrict__ nonempty) {
+    size_t key = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = false;
+    if (key < nkeys) {
+        uint32_t o = offsets[key];
+        live = offsets[key + 1] > o;
+        if (live) entries[o] |= kEntryStart;
     }
-    return load_affine(buf + pos * 96);
+    unsigned m = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(nonempty, (uint32_t)__popc(m));
 }
-// denominator of the slope: x2 - x1, or 2*y1 when the points coincide; zero means "no inversion needed"
-__device__ __forceinline__ fp_t pair_denominator(const affine_t& p1, const affine_t& p2) {
-    if (p1.is_inf() || p2.is_inf()) return fp_t::zero();
-    fp_t dx = p2.x - p1.x;
-    if (!dx.is_zero()) return dx;
-    if (p1.y == p2.y) return p1.y.dbl();
-    return fp_t::zero();  // P + (-P)
-}
-__global__ void __launch_bounds__(128) k_affine_round(const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
-                                                      const uint8_t* __restrict__ in_buf, uint8_t* __restrict__ out_buf,
-                                                      const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
-                                                      const uint32_t* __restrict__ pair_base, size_t nkeys, int gather) {
-    const size_t total_pairs = pair_base[nkeys];
-    size_t p0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * kAffK;
-    if (p0 >= total_pairs) return;
-    const int npairs = (int)min((size_t)kAffK, total_pairs - p0);
-    // locate the bucket of the first pair: last key with pair_base[key] <= p0
-    size_t lo = 0, hi = nkeys;
+// partial slot of the first segment of every chunk: chunk c starts at entry c * S inside bucket `key` (the last key
+// whose offset is <= c * S), which began floor(offsets[key] / S) chunks earlier
+__global__ void __launch_bounds__(256) k_chunk_first(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_base,
+                                                     size_t nkeys, uint32_t S, size_t nchunks, uint32_t* __restrict__ first_slot) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const size_t p = c * S;
+    if (p >= offsets[nkeys]) return;
+    size_t lo = 0, hi = nkeys;                      // offsets[lo] <= p < offsets[hi]
     while (hi - lo > 1) {
         size_t mid = (lo + hi) >> 1;
-        if (pair_base[mid] <= p0) lo = mid; else hi = mid;
+        if (offsets[mid] <= p) lo = mid; else hi = mid;
     }
-    size_t key0 = lo;
-    uint32_t k0 = (uint32_t)(p0 - pair_base[key0]);
+    first_slot[c] = task_base[lo] + (uint32_t)(c - offsets[lo] / S);
+}
 
-    fp_t prefix[kAffK];
-    fp_t acc = fp_t::one();
+static __device__ __noinline__ fp_t ba_mul(fp_t a, fp_t b) { return a * b; }
+
+// 1 / v for the 128 values of a CTA with ONE field inversion: product tree over the lanes (pairs by shuffle, the 127
+// internal nodes in shared memory, each level computed by as few warps as it has nodes), inversion of the root by warp
+// 0, then the inverses walk down the tree: inv(child) = inv(parent) * sibling.  ~5 multiplications per lane instead of
+// the 12 of two warp-wide scans.  v != 0 on every lane; all 128 threads must call.
+// sm_t / sm_i: 128 field elements each (index 1..127 used, heap order: children of i are 2i and 2i+1).
+__device__ __forceinline__ fp_t cta_batch_inverse(const fp_t& v, uint8_t* sm_t, uint8_t* sm_i) {
+    const int tid = threadIdx.x;
+    const fp_t sib = shfl_xor_fp(v, 1);
     {
-        size_t key = key0;
-        uint32_t k = k0, npk = counts[key] >> 1, off = offsets[key];
-#pragma unroll 1
-        for (int i = 0; i < npairs; i++) {
-            while (k >= npk) { key++; k = 0; npk = counts[key] >> 1; off = offsets[key]; }
-            affine_t a = load_round_point(table, entries, in_buf, (size_t)off + 2 * k, gather);
-            affine_t b = load_round_point(table, entries, in_buf, (size_t)off + 2 * k + 1, gather);
-            fp_t d = pair_denominator(a, b);
-            prefix[i] = acc;
-            if (!d.is_zero()) acc = acc * d;
-            k++;
-        }
+        fp_t pr = ba_mul(v, sib);                                  // node 64 + tid / 2 (both lanes of a pair compute it)
+        if (!(tid & 1)) store_field(sm_t + (size_t)(64 + (tid >> 1)) * 48, pr);
     }
-    fp_t inv = acc.inverse();
-    // second sweep, backwards, recomputing the (cheap) denominators: inv_i = prefix_i * inv; inv *= d_i
-    {
-        // re-walk forward to find the position of the last pair, then go back; simpler: recompute positions per pair
-        // by walking forward again and storing (key, k) compactly
-        uint32_t pk_key[kAffK], pk_k[kAffK];
-        size_t key = key0;
-        uint32_t k = k0, npk = counts[key] >> 1;
+    __syncthreads();
 #pragma unroll 1
-        for (int i = 0; i < npairs; i++) {
-            while (k >= npk) { key++; k = 0; npk = counts[key] >> 1; }
-            pk_key[i] = (uint32_t)key;
-            pk_k[i] = k;
-            k++;
+    for (int size = 32; size >= 1; size >>= 1) {
+        if (tid < size) {
+            const int i = size + tid;
+            fp_t pr = ba_mul(load_field<fp_t>(sm_t + (size_t)(2 * i) * 48), load_field<fp_t>(sm_t + (size_t)(2 * i + 1) * 48));
+            store_field(sm_t + (size_t)i * 48, pr);
         }
+        __syncthreads();
+    }
+    if (tid < 32) {
+        fp_t r = load_field<fp_t>(sm_t + 48).inverse();            // identical on the 32 lanes: no divergence
+        if (tid == 0) store_field(sm_i + 48, r);
+    }
+    __syncthreads();
 #pragma unroll 1
-        for (int i = npairs - 1; i >= 0; i--) {
-            uint32_t off = offsets[pk_key[i]];
-            uint32_t kk = pk_k[i];
-            affine_t a = load_round_point(table, entries, in_buf, (size_t)off + 2 * kk, gather);
-            affine_t b = load_round_point(table, entries, in_buf, (size_t)off + 2 * kk + 1, gather);
-            affine_t r;
-            if (a.is_inf()) {
-                r = b;
-            } else if (b.is_inf()) {
-                r = a;
-            } else {
-                fp_t dx = b.x - a.x;
-                bool dbl = dx.is_zero();
-                if (dbl && !(a.y == b.y)) {
-                    r.x = fp_t::zero();
-                    r.y = fp_t::zero();  // P + (-P)
-                } else {
-                    fp_t d = dbl ? a.y.dbl() : dx;
-                    fp_t inv_i = prefix[i] * inv;
-                    inv = inv * d;
-                    fp_t num;
-                    if (dbl) {
-                        fp_t xx = a.x.sqr();
-                        num = xx.dbl() + xx;  // 3 x^2
-                    } else {
-                        num = b.y - a.y;
+    for (int size = 1; size <= 32; size <<= 1) {                   // parents [size, 2 size) -> children [2 size, 4 size)
+        if (tid < 2 * size) {
+            const int j = 2 * size + tid;
+            fp_t r = ba_mul(load_field<fp_t>(sm_i + (size_t)(j >> 1) * 48), load_field<fp_t>(sm_t + (size_t)(j ^ 1) * 48));
+            store_field(sm_i + (size_t)j * 48, r);
+        }
+        __syncthreads();
+    }
+    return ba_mul(load_field<fp_t>(sm_i + (size_t)(64 + (tid >> 1)) * 48), sib);
+}
+
+// TREE = false (default): every WARP inverts its own 32 x K denominators (two shuffle scans + one inversion, identical on
+// all lanes: warp_inverse.cuh) -- no barrier anywhere, so the warps of an SM drift out of phase and one warp's inversion
+// (ALU pipe) runs under the other warps' multiplications (FMA-heavy pipe).  TREE = true: one inversion per CTA through the
+// shared-memory product tree above (fewer multiplications, but every step ends in a serial, barrier-separated phase).
+template <int K, bool TREE>
+__global__ void __launch_bounds__(kBaThreads, 3) k_accumulate_affine(const uint8_t* __restrict__ table, const uint32_t stride,
+                                                                   const uint32_t* __restrict__ entries,
+                                                                   const uint32_t* __restrict__ n_entries_ptr,
+                                                                   const uint32_t* __restrict__ first_slot, const uint32_t S,
+                                                                   uint8_t* __restrict__ acc_buf, uint8_t* __restrict__ partials) {
+    extern __shared__ __align__(16) uint8_t ba_smem[];
+    uint4* sm_prefix = reinterpret_cast<uint4*>(ba_smem);                  // [K][3][128] : conflict-free 16-byte columns
+    uint8_t* sm_t = ba_smem + (size_t)K * 3 * kBaThreads * 16;             // product tree
+    uint8_t* sm_i = sm_t + 128 * 48;                                       // inverses of the tree nodes
+    uint32_t* sm_next = reinterpret_cast<uint32_t*>(sm_i + 128 * 48);      // [K][128] next partial slot of every chunk
+    const uint32_t tid = threadIdx.x;
+    const size_t G = (size_t)gridDim.x * kBaThreads, g = (size_t)blockIdx.x * kBaThreads + tid;
+    const size_t E = *n_entries_ptr;
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        const size_t c = (size_t)k * G + g;
+        sm_next[k * kBaThreads + tid] = c * S < E ? first_slot[c] : 0u;
+    }
+#pragma unroll 1
+    for (uint32_t step = 0; step < S; step++) {
+        uint64_t modes = 0;
+        fp_t running = fp_t::one();
+        // ---- forward: denominators and their prefix products ------------------------------------------------------
+#pragma unroll 1
+        for (int k = 0; k < K; k++) {
+            const size_t c = (size_t)k * G + g, pos = c * S + step;
+            if (pos >= E) continue;
+            const uint32_t e = entries[pos];
+            uint32_t mode = BA_LOAD;
+            if (step != 0 && !(e & kEntryStart)) {
+                const uint8_t* pp = table + (size_t)(e & kEntryIndex) * stride;
+                const uint8_t* ap = acc_buf + c * 96;
+                const fp_t x2 = load_field_ro<fp_t>(pp), x1 = load_field<fp_t>(ap);
+                mode = BA_ADD;
+                const bool z1 = x1.is_zero(), z2 = x2.is_zero();
+                if (z1 || z2) {                       // possibly an infinity operand (x = 0 is also a valid abscissa)
+                    if (z2 && load_field_ro<fp_t>(pp + 48).is_zero()) mode = BA_SKIP;
+                    else if (z1 && load_field<fp_t>(ap + 48).is_zero()) mode = BA_COPY;
+                }
+                if (mode == BA_ADD) {
+                    fp_t d = x2 - x1;
+                    if (d.is_zero()) {                // same abscissa: P + P or P + (-P)
+                        const fp_t y1 = load_field<fp_t>(ap + 48), y2 = load_field_ro<fp_t>(pp + 48).cneg(e >> 31);
+                        if (y1 == y2 && !y1.is_zero()) { mode = BA_DBL; d = y1.dbl(); } else mode = BA_INF;
                     }
-                    fp_t lam = num * inv_i;
-                    fp_t x3 = lam.sqr() - a.x - b.x;
-                    r.x = x3;
-                    r.y = lam * (a.x - x3) - a.y;
+                    if (mode != BA_INF) {
+                        uint4* pf = sm_prefix + (size_t)k * 3 * kBaThreads + tid;
+                        pf[0] = make_uint4(running.v[0], running.v[1], running.v[2], running.v[3]);
+                        pf[kBaThreads] = make_uint4(running.v[4], running.v[5], running.v[6], running.v[7]);
+                        pf[2 * kBaThreads] = make_uint4(running.v[8], running.v[9], running.v[10], running.v[11]);
+                        running = running * d;
+                    }
                 }
             }
-            store_affine(out_buf + ((size_t)off + kk) * 96, r);
+            modes |= (uint64_t)mode << (3 * k);
+        }
+        // ---- one inversion for the 128 x K denominators of the CTA (step 0 only loads) ------------------------------
+        fp_t inv = fp_t::one();
+        if (step != 0) inv = TREE ? cta_batch_inverse(running, sm_t, sm_i) : warp_inverse(running);
+        // ---- backward: peel the inverses off and finish the additions ---------------------------------------------
+#pragma unroll 1
+        for (int k = K - 1; k >= 0; k--) {
+            const uint32_t mode = (uint32_t)(modes >> (3 * k)) & 7u;
+            if (mode == BA_NOP) continue;
+            const size_t c = (size_t)k * G + g, pos = c * S + step;
+            const uint32_t e = entries[pos];
+            const uint8_t* pp = table + (size_t)(e & kEntryIndex) * stride;
+            uint8_t* ap = acc_buf + c * 96;
+            affine_t res;
+            if (mode == BA_LOAD || mode == BA_COPY) {
+                res = load_affine(pp);
+                res.y = res.y.cneg(e >> 31);
+            } else if (mode == BA_SKIP) {
+                res = load_affine(ap);
+            } else if (mode == BA_INF) {
+                res.x = fp_t::zero();
+                res.y = fp_t::zero();
+            } else {
+                const affine_t a = load_affine(ap);
+                affine_t b = load_affine(pp);
+                b.y = b.y.cneg(e >> 31);
+                const uint4* pf = sm_prefix + (size_t)k * 3 * kBaThreads + tid;
+                fp_t pre;
+                {
+                    uint4 t0 = pf[0], t1 = pf[kBaThreads], t2 = pf[2 * kBaThreads];
+                    pre.v[0] = t0.x; pre.v[1] = t0.y; pre.v[2] = t0.z; pre.v[3] = t0.w;
+                    pre.v[4] = t1.x; pre.v[5] = t1.y; pre.v[6] = t1.z; pre.v[7] = t1.w;
+                    pre.v[8] = t2.x; pre.v[9] = t2.y; pre.v[10] = t2.z; pre.v[11] = t2.w;
+                }
+                fp_t d, num;
+                if (mode == BA_DBL) {
+                    d = a.y.dbl();
+                    fp_t xx = ba_mul(a.x, a.x);
+                    num = xx.dbl() + xx;              // 3 x^2
+                } else {
+                    d = b.x - a.x;
+                    num = b.y - a.y;
+                }
+                const fp_t inv_d = pre * inv;         // 1 / d
+                inv = inv * d;
+                const fp_t lam = num * inv_d;
+                res.x = lam.sqr() - a.x - b.x;
+                res.y = lam * (a.x - res.x) - a.y;
+            }
+            // the segment ends with this entry when the chunk does or the next entry starts a bucket
+            const bool last = step + 1 == S || pos + 1 >= E || (entries[pos + 1] & kEntryStart);
+            if (last) {
+                const uint32_t slot = sm_next[k * kBaThreads + tid]++;
+                xyzz_t out;
+                const bool inf = res.is_inf();
+                out.x = res.x; out.y = res.y;
+                out.zz = inf ? fp_t::zero() : fp_t::one();
+                out.zzz = out.zz;
+                store_xyzz(partials + (size_t)slot * 192, out);
+            } else {
+                store_affine(ap, res);
+            }
         }
     }
 }
-// odd bucket sizes: the unpaired last point moves to the end of the halved list; then counts := ceil(counts / 2)
-__global__ void __launch_bounds__(256) k_affine_leftover(const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
-                                                         const uint8_t* __restrict__ in_buf, uint8_t* __restrict__ out_buf,
-                                                         const uint32_t* __restrict__ offsets, uint32_t* __restrict__ counts,
-                                                         size_t nkeys, int gather) {
-    size_t key = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (key >= nkeys) return;
-    uint32_t c = counts[key];
-    if (c & 1) {
-        uint32_t off = offsets[key];
-        affine_t p = load_round_point(table, entries, in_buf, (size_t)off + c - 1, gather);
-        store_affine(out_buf + ((size_t)off + (c >> 1)) * 96, p);
-    }
-    counts[key] = (c + 1) >> 1;
-}
-// the XYZZ task kernel on an already materialised (and partly reduced) point list: contiguous reads, no gather
-__global__ void __launch_bounds__(kAccThreads) k_accumulate_direct(const uint8_t* __restrict__ buf, const uint32_t* __restrict__ sorted_tasks,
-                                                                   const uint32_t* __restrict__ n_tasks_ptr, uint8_t* __restrict__ partials) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= *n_tasks_ptr) return;
-    uint32_t start = sorted_tasks[3 * t], len = sorted_tasks[3 * t + 1], slot = sorted_tasks[3 * t + 2];
-    xyzz_t acc = xyzz_t::inf();
-    for (uint32_t k = 0; k < len; k++) {
-        affine_t p = load_affine(buf + ((size_t)start + k) * 96);
-        xyzz_add_affine(acc, p);
-    }
-    store_xyzz(partials + (size_t)slot * 192, acc);
-}
-
 // variant with the field multiplication out of line (B200_ACC_CALL=1): same work, ~20x smaller loop body
-__global__ void __launch_bounds__(kAccThreads) k_accumulate_call(const uint8_t* __restrict__ table,
+__global__ void __launch_bounds__(kAccThreads) k_accumulate_call(const uint8_t* __restrict__ table, const uint32_t stride,
                                                                  const uint32_t* __restrict__ entries,
                                                                  const uint32_t* __restrict__ sorted_tasks,
                                                                  const uint32_t* __restrict__ n_tasks_ptr,
@@ -458,7 +539,7 @@ __global__ void __launch_bounds__(kAccThreads) k_accumulate_call(const uint8_t* 
     const uint32_t* e = entries + start;
     for (uint32_t k = 0; k < len; k++) {
         uint32_t v = e[k];
-        cl::affine_t p = cl::load_affine(table + (size_t)(v & 0x7fffffffu) * 96);
+        cl::affine_t p = cl::load_affine(table + (size_t)(v & 0x7fffffffu) * stride);
         p.y = p.y.cneg(v >> 31);
         cl::xyzz_add_affine(acc, p);
     }
@@ -759,11 +840,11 @@ __global__ void __launch_bounds__(32) k_horner(const uint8_t* __restrict__ group
 
 // table rows for FIXED engines: row j = 2^(c*j) * P_i, affine.  One thread per point walks all rows
 // (c doublings in XYZZ, then back to affine with one warp-shared field inversion).  One-time cost at prepare.
-__global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table, size_t n, int W, int c, int c0) {
+__global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table, size_t n, int W, int c, int c0, size_t stride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     if (!live) i = n - 1;
-    cc::affine_t p = cc::load_affine(table + i * 96);
+    cc::affine_t p = cc::load_affine(table + i * stride);
     for (int j = 1; j < W; j++) {
         cc::xyzz_t q = cc::affine_to_xyzz(p);
         for (int k = 0; k < (j == 1 ? c0 : c); k++) cc::xyzz_dbl(q);   // row j = 2^(c0 + (j-1) c) * P
@@ -772,7 +853,7 @@ __global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table,
         cc::fp_t izzz = warp_inverse(inf ? cc::fp_t::one() : q.zzz);
         cc::fp_t izz = izzz.sqr() * q.zz.sqr();
         p = inf ? cc::affine_t{cc::fp_t::zero(), cc::fp_t::zero()} : cc::affine_t{q.x * izz, q.y * izzz};
-        if (live) cc::store_affine(table + ((size_t)j * n + i) * 96, p);
+        if (live) cc::store_affine(table + ((size_t)j * n + i) * stride, p);
     }
 }
 
@@ -837,6 +918,16 @@ void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+typedef void (*ba_kernel_t)(const uint8_t*, uint32_t, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, uint8_t*, uint8_t*);
+static ba_kernel_t ba_kernel(int k, bool tree) {
+    switch (k) {
+        case 8: return tree ? k_accumulate_affine<8, true> : k_accumulate_affine<8, false>;
+        case 12: return tree ? k_accumulate_affine<12, true> : k_accumulate_affine<12, false>;
+        case 16: return tree ? k_accumulate_affine<16, true> : k_accumulate_affine<16, false>;
+        default: return tree ? k_accumulate_affine<10, true> : k_accumulate_affine<10, false>;
+    }
+}
+
 MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points, cudaStream_t stream, const MsmEngine* share_table)
     : cfg_(cfg) {
     if (!cfg_.fixed || cfg_.c0 <= 0 || cfg_.c0 > cfg_.c) cfg_.c0 = cfg_.c;
@@ -853,11 +944,34 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     if (entries_max_ >= (1ull << 32) || (cfg_.fixed ? table_points * cfg_.W : cfg_.n) >= (1ull << 31))
         throw CudaError(-1, "MsmEngine: problem too large for 32-bit entry indices");
     tasks_max_ = entries_max_ / cfg_.L + keys_max_ + 1;
+    if (!cfg_.fixed) cfg_.affine = false;
+    if (getenv("B200_MSM_AFFINE_K")) cfg_.affine_k = atoi(getenv("B200_MSM_AFFINE_K"));
+    if (cfg_.affine_k != 8 && cfg_.affine_k != 10 && cfg_.affine_k != 12 && cfg_.affine_k != 16) cfg_.affine_k = 10;
+    ba_tree_ = getenv("B200_MSM_AFFINE_TREE") && atoi(getenv("B200_MSM_AFFINE_TREE")) != 0;
+    if (cfg_.affine) {
+        // one CTA per (SM, resident slot); the kernel is persistent, so the grid is exactly what fits
+        int dev = 0, sms = 148, occ = 0;
+        B200_CUDA_CHECK(cudaGetDevice(&dev));
+        B200_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        ba_smem_ = (size_t)cfg_.affine_k * 3 * kBaThreads * 16 + 2 * 128 * 48 + (size_t)cfg_.affine_k * kBaThreads * 4;
+        auto kern = ba_kernel(cfg_.affine_k, ba_tree_);
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_));
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBaThreads, ba_smem_));
+        if (occ < 1) throw CudaError(-1, "MsmEngine: k_accumulate_affine does not fit an SM");
+        ba_blocks_ = sms * occ;
+        ba_chunks_max_ = (size_t)ba_blocks_ * kBaThreads * cfg_.affine_k;
+        // every non-empty bucket and every chunk contributes at most one partial sum
+        tasks_max_ = std::max(tasks_max_, keys_max_ + ba_chunks_max_ + 1);
+        first_slot_ = dev_alloc<uint32_t>(ba_chunks_max_);
+        acc_buf_ = dev_alloc<uint8_t>(ba_chunks_max_ * 96);
+    }
     size_t rows = cfg_.fixed ? cfg_.W : 1;
-    table_bytes_ = rows * table_points * 96;
+    stride_ = cfg_.affine ? 128 : 96;
+    table_bytes_ = rows * table_points * stride_;
     if (share_table) {
         const MsmConfig& o = share_table->cfg_;
-        if (!cfg_.fixed || !o.fixed || o.c != cfg_.c || o.c0 != cfg_.c0 || o.W != cfg_.W || o.n != cfg_.n || o.bases_period != cfg_.bases_period)
+        if (!cfg_.fixed || !o.fixed || o.c != cfg_.c || o.c0 != cfg_.c0 || o.W != cfg_.W || o.n != cfg_.n || o.bases_period != cfg_.bases_period ||
+            share_table->stride_ != stride_)
             throw CudaError(-1, "MsmEngine: shared table has a different layout");
         table_ = share_table->table_;
         owns_table_ = false;
@@ -876,7 +990,6 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     partials_ = dev_alloc<uint8_t>(tasks_max_ * 192);
     chunk_sums_ = dev_alloc<uint8_t>(groups_max_ * 3 * 32 * 192);  // marginal sums [group][axis][32]
     group_sums_ = dev_alloc<uint8_t>(groups_max_ * 192);
-    pair_base_ = dev_alloc<uint32_t>(keys_max_ + 1);
     kf_ = std::max(cfg_.c - 1 > kReduceBits ? cfg_.c - 1 - kReduceBits : 0, std::min(cfg_.fold, cfg_.c - 2));
     if (kf_ > 0) {
         // folded segments (T and R point per segment), their identity slot map, marginals of the R sums
@@ -889,22 +1002,12 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
         B200_LAUNCH_CHECK();
         B200_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
-    {
-        const char* e = getenv("B200_AFFINE_ROUNDS");
-        // OFF by default: measured on B200 (MSM 2^20) the rounds make the accumulation phase 16.1 ms instead of 6.4 ms --
-        // one binary-Euclid inversion per 16 additions costs more ALU-pipe time than the 4 multiplications it saves
-        // per addition (profiles/r01_multiplier_variants.md).  Kept as a tested option for larger inversion batches.
-        max_rounds_ = e && *e ? atoi(e) : 0;
-        // two point buffers of one point per entry; only for fixed-base engines and while they stay within 16 GiB
-        if (cfg_.fixed && max_rounds_ > 0 && entries_max_ * 96 * 2 <= (16ull << 30)) {
-            aff_buf_[0] = dev_alloc<uint8_t>(entries_max_ * 96);
-            aff_buf_[1] = dev_alloc<uint8_t>(entries_max_ * 96);
-        }
-    }
     if (points) {
-        B200_CUDA_CHECK(cudaMemcpyAsync(table_, points, table_points * 96, host_points ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
+        const cudaMemcpyKind kind = host_points ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        if (stride_ == 96) B200_CUDA_CHECK(cudaMemcpyAsync(table_, points, table_points * 96, kind, stream));
+        else B200_CUDA_CHECK(cudaMemcpy2DAsync(table_, stride_, points, 96, 96, table_points, kind, stream));
         if (cfg_.fixed && cfg_.W > 1) {
-            k_build_rows<<<div_up(table_points, 128), 128, 0, stream>>>((uint8_t*)table_, table_points, cfg_.W, cfg_.c, cfg_.c0);
+            k_build_rows<<<div_up(table_points, 128), 128, 0, stream>>>((uint8_t*)table_, table_points, cfg_.W, cfg_.c, cfg_.c0, stride_);
             B200_LAUNCH_CHECK();
         }
         B200_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -956,7 +1059,7 @@ MsmEngine::~MsmEngine() {
         if (e) cudaEventDestroy(e);
     if (copy_start_) cudaEventDestroy(copy_start_);
     if (copy_stream_) cudaStreamDestroy(copy_stream_);
-    cudaFree(pair_base_); cudaFree(aff_buf_[0]); cudaFree(aff_buf_[1]);
+    cudaFree(first_slot_); cudaFree(acc_buf_);
     if (owns_table_) cudaFree(table_);
     cudaFree(counts_); cudaFree(offsets_); cudaFree(cursor_); cudaFree(task_base_); cudaFree(entries_);
     cudaFree(sorted_tasks_); cudaFree(size_hist_); cudaFree(scan_tmp_); cudaFree(partials_); cudaFree(chunk_sums_);
@@ -982,7 +1085,10 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     // more, shorter tasks (down to kMinTaskLen) and the partial sums folded by the sub-warp trees of k_bucket_combine
     int L = cfg_.L;
     {
-        const size_t fill = (size_t)148 * 4 * 32 * 2;   // two warps on every SM sub-partition
+        // two warps on every SM sub-partition; B200_MSM_FILL_DIV > 1 aims at a fraction of the machine (several lanes of
+        // a settings object running side by side each get their share: fewer, longer tasks, less combine work)
+        static const int fill_div = std::max(1, getenv("B200_MSM_FILL_DIV") ? atoi(getenv("B200_MSM_FILL_DIV")) : 1);
+        const size_t fill = (size_t)148 * 4 * 32 * 2 / fill_div;
         size_t want = std::max<size_t>(kMinTaskLen, total * W / fill);
         if ((size_t)L > want) L = (int)want;
         while (L < cfg_.L && total * W / L + nkeys + 1 > tasks_max_) L++;
@@ -1025,68 +1131,60 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
                                                             cfg_.fixed, mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n, 0);
         launches++;
     }
+    // batch-affine accumulation when the call fills the machine: S entries per chunk, chunk grid = every slot of every thread
+    const size_t entries_bound = total * W;
+    uint32_t S = 0;
+    if (cfg_.affine && entries_bound >= ((size_t)1 << 21)) {
+        S = (uint32_t)((entries_bound + ba_chunks_max_ - 1) / ba_chunks_max_);
+        if (S < 4) S = 4;
+    }
+    last_affine_ = S != 0;
     // 2 offsets (and a working copy for the scatter cursors), task bases
     launches += scan_exclusive(counts_, nkeys, 0, offsets_, cursor_, scan_tmp_, st);
-    launches += scan_exclusive(counts_, nkeys, (uint32_t)L, task_base_, nullptr, scan_tmp_, st);
+    if (S) launches += scan_exclusive(offsets_, nkeys, kScanSegments | S, task_base_, nullptr, scan_tmp_, st);   // segments per bucket
+    else launches += scan_exclusive(counts_, nkeys, (uint32_t)L, task_base_, nullptr, scan_tmp_, st);
     // 3 scatter
     k_digits<true><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, c0, W, nb_,
                                                        cfg_.fixed, mont, cursor_, entries_, (size_t)cfg_.bases_period, cfg_.n, 0);
     launches++;
-    // 5a batch-affine rounds (FIXED engines with room for the two point buffers): halve every bucket's list R times
     const bool prof = profiling_ && prof_count_ < kProfSlots;
-    if (prof) {
+    auto prof_begin = [&] {
+        if (!prof) return;
         for (int k = 0; k < 2; k++)
             if (!prof_ev_[2 * prof_count_ + k]) B200_CUDA_CHECK(cudaEventCreate(&prof_ev_[2 * prof_count_ + k]));
         B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_], st));
-    }
-    int rounds = 0;
-    const uint8_t* reduced = nullptr;  // buffer holding the current point lists once rounds > 0
-    if (aff_buf_[0]) {
-        // expected entries per bucket decides how many halvings pay: stop while a round still fills the machine
-        double per_bucket = (double)total * W / (double)nkeys;
-        size_t pairs = (size_t)((double)total * W / 2);
-        while (per_bucket >= 8.0 && pairs >= (size_t)kAffK * 32768 && rounds < max_rounds_) {
-            rounds++;
-            per_bucket /= 2;
-            pairs /= 2;
+    };
+    if (S) {
+        // 4' bucket-start flags, first partial slot of every chunk
+        const size_t nchunks = (entries_bound + S - 1) / S;
+        k_mark_starts<<<div_up(nkeys, 256), 256, 0, st>>>(offsets_, nkeys, entries_, size_hist_);
+        k_chunk_first<<<div_up(nchunks, 256), 256, 0, st>>>(offsets_, task_base_, nkeys, S, nchunks, first_slot_);
+        launches += 2;
+        // 5' accumulate: persistent grid, every slot of every thread advances one entry per step
+        prof_begin();
+        ba_kernel(cfg_.affine_k, ba_tree_)<<<ba_blocks_, kBaThreads, ba_smem_, st>>>((const uint8_t*)table_, (uint32_t)stride_, entries_, offsets_ + nkeys,
+                                                                         first_slot_, S, acc_buf_, (uint8_t*)partials_);
+    } else {
+        // 4 tasks sorted by length
+        k_task_hist<<<div_up(nkeys, 256), 256, (L + 1) * sizeof(uint32_t), st>>>(counts_, nkeys, L, size_hist_);
+        k_task_bases<<<1, 32, 0, st>>>(size_hist_, L);
+        k_task_emit<<<div_up(nkeys, 256), 256, 0, st>>>(counts_, offsets_, task_base_, nkeys, L, size_hist_, sorted_tasks_);
+        launches += 3;
+        // 5 accumulate: grid sized for the worst case, surplus threads exit on the device-side task count
+        prof_begin();
+        size_t tasks_bound = std::min(tasks_max_, total * W / L + nkeys + 1);
+        static const bool acc_call = getenv("B200_ACC_CALL") && atoi(getenv("B200_ACC_CALL"));
+        static const bool acc_prefetch = !getenv("B200_ACC_PREFETCH") || atoi(getenv("B200_ACC_PREFETCH"));  // default on: -2.2% at 2^20
+        if (acc_call)
+            k_accumulate_call<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, (uint32_t)stride_, entries_,
+                                                                                       sorted_tasks_, task_base_ + nkeys, (uint8_t*)partials_);
+        else {
+            static const int acc_occ = getenv("B200_ACC_OCC") ? atoi(getenv("B200_ACC_OCC")) : 3;
+            auto kern = acc_prefetch ? (acc_occ == 4 ? k_accumulate<true, 4> : k_accumulate<true, 3>)
+                                     : (acc_occ == 4 ? k_accumulate<false, 4> : k_accumulate<false, 3>);
+            kern<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, (uint32_t)stride_, entries_, sorted_tasks_,
+                                                                           task_base_ + nkeys, (uint8_t*)partials_);
         }
-        size_t pair_bound = total * W / 2;
-        for (int r = 0; r < rounds; r++) {
-            launches += scan_exclusive(counts_, nkeys, 0x80000002u, pair_base_, nullptr, scan_tmp_, st);
-            const uint8_t* in = r == 0 ? nullptr : aff_buf_[(r - 1) & 1];
-            uint8_t* out = aff_buf_[r & 1];
-            size_t threads = pair_bound / kAffK + 1;
-            k_affine_round<<<div_up(threads, 128), 128, 0, st>>>((const uint8_t*)table_, entries_, in, out, offsets_, counts_, pair_base_,
-                                                                nkeys, r == 0);
-            k_affine_leftover<<<div_up(nkeys, 256), 256, 0, st>>>((const uint8_t*)table_, entries_, in, out, offsets_, counts_, nkeys,
-                                                                 r == 0);
-            launches += 2;
-            pair_bound = pair_bound / 2 + nkeys;
-            reduced = out;
-        }
-        if (rounds) launches += scan_exclusive(counts_, nkeys, (uint32_t)L, task_base_, nullptr, scan_tmp_, st);
-    }
-    // 4 tasks sorted by length
-    k_task_hist<<<div_up(nkeys, 256), 256, (L + 1) * sizeof(uint32_t), st>>>(counts_, nkeys, L, size_hist_);
-    k_task_bases<<<1, 32, 0, st>>>(size_hist_, L);
-    k_task_emit<<<div_up(nkeys, 256), 256, 0, st>>>(counts_, offsets_, task_base_, nkeys, L, size_hist_, sorted_tasks_);
-    launches += 3;
-    // 5 accumulate: grid sized for the worst case, surplus threads exit on the device-side task count
-    size_t tasks_bound = std::min(tasks_max_, total * W / L + nkeys + 1);
-    static const bool acc_call = getenv("B200_ACC_CALL") && atoi(getenv("B200_ACC_CALL"));
-    static const bool acc_prefetch = !getenv("B200_ACC_PREFETCH") || atoi(getenv("B200_ACC_PREFETCH"));  // default on: -2.2% at 2^20
-    if (reduced)
-        k_accumulate_direct<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>(reduced, sorted_tasks_, task_base_ + nkeys,
-                                                                                     (uint8_t*)partials_);
-    else if (acc_call)
-        k_accumulate_call<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
-                                                                                   task_base_ + nkeys, (uint8_t*)partials_);
-    else {
-        static const int acc_occ = getenv("B200_ACC_OCC") ? atoi(getenv("B200_ACC_OCC")) : 3;
-        auto kern = acc_prefetch ? (acc_occ == 4 ? k_accumulate<true, 4> : k_accumulate<true, 3>)
-                                 : (acc_occ == 4 ? k_accumulate<false, 4> : k_accumulate<false, 3>);
-        kern<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, entries_, sorted_tasks_,
-                                                                       task_base_ + nkeys, (uint8_t*)partials_);
     }
     if (prof) {
         B200_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_count_ + 1], st));
@@ -1094,7 +1192,8 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     }
     launches++;
     // 6 reduce
-    const uint32_t warp_min = (double)total * W / (double)nkeys <= 0.5 * L ? 4 : 32;
+    // (batch-affine path: almost every bucket has 2-4 segment sums -- they are what the machine is filled with)
+    const uint32_t warp_min = !S && (double)total * W / (double)nkeys <= 0.5 * L ? 4 : 32;
     if (nkeys <= 8192)
         k_bucket_combine<false, true><<<div_up(nkeys * kCombLanes, 128), 128, 0, st>>>((uint8_t*)partials_, task_base_, nkeys, warp_min);
     else

@@ -43,6 +43,9 @@ struct MsmConfig {
                     // elements < 2^248) then still spread its digits over many buckets instead of one or two.
     int fold = -1;  // bucket-index bits folded by k_segment_fold before the marginal reduce; -1: only what the reduce
                     // cannot take (c - 1 - 15 bits for windows wider than 16)
+    bool affine = false;   // FIXED only: batch-affine accumulation (k_accumulate_affine) for calls that fill the machine; the table
+                           // then uses 128-byte slots per point (one aligned line per gather instead of a straddling 96 bytes)
+    int affine_k = 10;     // slots (chunks) per thread of the batch-affine kernel: denominators per inversion = 128 * affine_k
     int bases_period = 1;  // FIXED only: the table holds bases_period * n points per row and scalar vector v uses the
                            // bases [(v mod bases_period) * n, +n)  (FK20: 128 rows of 64 points, kzg/src/msm/bgmw.rs:306-380)
 };
@@ -72,6 +75,8 @@ public:
     // launches of our kernels per run() (for bench.py's gpu_launches)
     int launches_per_run() const { return launches_; }
     const void* table() const { return table_; }
+    size_t table_stride() const { return stride_; }
+    bool last_run_affine() const { return last_affine_; }
     // optional device-side timing of the accumulate kernel (bench.py's roofline): when enabled, every run() brackets
     // k_accumulate with CUDA events on the launching stream; profile_read() sums the completed pairs and resets.
     void set_profiling(bool on) { profiling_ = on; }
@@ -111,9 +116,15 @@ private:
     uint32_t* sorted_tasks_ = nullptr;  // 3 x u32 per task
     uint32_t* size_hist_ = nullptr;     // [L+1] hist, [L+1] base, [L+1] cursor
     uint32_t* scan_tmp_ = nullptr;
-    uint32_t* pair_base_ = nullptr;     // [keys+1] flat pair index of each bucket in a batch-affine round
-    uint8_t* aff_buf_[2] = {nullptr, nullptr};  // ping-pong affine point lists (one slot per entry)
-    int max_rounds_ = 0;
+    // batch-affine accumulation (cfg.affine): chunk grid of the sorted entry list
+    size_t stride_ = 96;                // bytes per table point
+    bool ba_tree_ = false;              // one inversion per CTA (shared-memory product tree) instead of one per warp
+    int ba_blocks_ = 0;                 // co-resident CTAs of k_accumulate_affine (SMs x occupancy): the grid
+    size_t ba_smem_ = 0;
+    size_t ba_chunks_max_ = 0;          // blocks x 128 x K
+    uint32_t* first_slot_ = nullptr;    // [chunks] partial slot of each chunk's first segment
+    uint8_t* acc_buf_ = nullptr;        // [chunks] x 96 B running affine sums (L2 resident)
+    bool last_affine_ = false;          // the last run() took the batch-affine path
     void* partials_ = nullptr;  // xyzz per task
     void* chunk_sums_ = nullptr;
     void* group_sums_ = nullptr;

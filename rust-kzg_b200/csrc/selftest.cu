@@ -22,6 +22,7 @@ __global__ void k_field_op(int op, uint8_t* out, const uint8_t* a, const uint8_t
         case 3: r = x.neg(); break;
         case 4: r = x.inverse(); break;
         case 7: r = x.inverse_fermat(); break;
+        case 9: r = x.inverse_euclid(); break;
         case 8: r = x.sqr(); break;
         case 5: r = x.to_mont(); break;
         default: r = x.from_mont(); break;

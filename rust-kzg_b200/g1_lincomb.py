@@ -54,7 +54,11 @@ class PreparedMsm:
         c, w, l = C.c_int(), C.c_int(), C.c_int()
         tb = C.c_size_t()
         _L().b200_msm_info(self.h, C.byref(c), C.byref(w), C.byref(tb), C.byref(l))
-        return {"c": c.value, "W": w.value, "table_bytes": tb.value, "launches": l.value}
+        aff = bool(_L().b200_msm_last_affine(self.h))
+        return {"c": c.value, "W": w.value, "table_bytes": tb.value, "launches": l.value,
+                # path of the LAST run: batch-affine accumulation (6 M per addition + ~0.6 M of shared inversion work) or XYZZ
+                "accumulate": "affine" if aff else "xyzz", "accumulate_kernel": "k_accumulate_affine" if aff else "k_accumulate",
+                "fp_mul_per_add": 6.6 if aff else 10.0}
 
     def last_counts(self):
         """(entries, tasks) of the last run: the accumulate kernel did entries - tasks mixed additions."""

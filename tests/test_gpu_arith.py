@@ -69,7 +69,8 @@ def test_field_inverse(B, K, which):
     oinv = K.fp_inv if which == "fp" else K.fr_inv
     assert np.array_equal(_field(B, which, 4, a), oinv(a))
     assert np.array_equal(_field(B, which, 16 + 4, a), oinv(a))
-    assert np.array_equal(_field(B, which, 7, a), oinv(a))          # Fermat cross-check of the Euclid inverse
+    assert np.array_equal(_field(B, which, 7, a), oinv(a))          # Fermat cross-check of the bingcd inverse (op 4)
+    assert np.array_equal(_field(B, which, 9, a), oinv(a))          # ... and the bit-serial binary Euclid
     z = np.zeros((4, a.shape[1]), np.uint64)
     assert not _field(B, which, 4, z).any()                         # inverse(0) == 0
 

@@ -265,3 +265,45 @@ def test_baseline_config_default_plan_folded_oracle(B, K, lagrange_affine, logn)
         tot = K.fr_from_ints([(0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF % R_MOD) * (n // 4096) % R_MOD] * 4096)
         assert K.p1_compress(h.mult(same)) == K.p1_compress(K.msm_affine(lagrange_affine, tot, nthreads=8))
     h.close()
+
+
+def test_batch_affine_accumulation_option(B, K, lagrange_affine):
+    """k_accumulate_affine (B200_MSM_AFFINE=1: chunked lock-step affine additions with a shared inversion; off by default,
+    see profiles/r02_affine.md) against the folded-scalar oracle, on inputs that hit every exceptional case of the affine
+    addition law: P + P (the same scalar on every copy of a point), P + (-P) (s and r - s), points at infinity in the
+    table, all-equal scalars (one bucket per window), zeros."""
+    n = 1 << 17                                   # smallest table whose calls take the affine path
+    reps = n // 4096
+    rng = np.random.default_rng(77)
+    pts = np.tile(lagrange_affine, (reps, 1))
+    pts_inf = pts.copy()
+    pts_inf[5::97] = 0
+    base = rand_fr_mont(rng, 4096)
+    neg = K.fr_sub(np.zeros((4096, 4), np.uint64), base)
+    cases = {
+        "uniform": rand_fr_mont(rng, n),
+        "same-scalar-per-point": np.tile(base, (reps, 1)),
+        "plus-minus": np.concatenate([np.tile(base, (reps // 2, 1)), np.tile(neg, (reps // 2, 1))]),
+        "all-equal": np.tile(base[:1], (n, 1)),
+        "zeros": np.zeros((n, 4), np.uint64),
+    }
+
+    def fold(sc):
+        cur = sc
+        while cur.shape[0] > 4096:
+            half = cur.shape[0] // 2
+            cur = K.fr_add(cur[:half], cur[half:])
+        return np.ascontiguousarray(cur)
+
+    for tree in (0, 1):
+        for p, tag in ((pts, ""), (pts_inf, "+inf")):
+            h = _with_env("B200_MSM_AFFINE", 1, lambda: _with_env("B200_MSM_AFFINE_TREE", tree, lambda: B.PreparedMsm(p)))
+            for name, sc in cases.items():
+                sc = np.ascontiguousarray(sc)
+                eff = sc.copy()
+                if tag:
+                    eff[5::97] = 0
+                got = h.mult(sc)
+                assert h.info()["accumulate"] == "affine"
+                assert K.p1_compress(got) == K.p1_compress(K.msm_affine(lagrange_affine, fold(eff), nthreads=8)), (tree, tag, name)
+            h.close()
