@@ -85,6 +85,11 @@ B200_API RustError b200_msm_last_stats(void *msm, uint64_t stats[8]);
 /* 1 when the last run on this handle used the batch-affine bucket accumulation (k_accumulate_affine: 6 field
  * multiplications per addition + a shared inversion), 0 for the XYZZ task kernel (10 per addition) */
 B200_API int b200_msm_last_affine(void *msm);
+/* 1 when the prepared table is scalar-randomised: every scalar is multiplied by a per-base pseudo-random rho_i and the table
+ * holds rho_i^-1 * P_i, so the digit distribution -- and the running time -- does not depend on the caller's scalars.  Applied
+ * at prepare when every base is in the prime-order subgroup (B200_MSM_RANDOMIZE=0 turns it off); the result is the same
+ * group element either way. */
+B200_API int b200_msm_randomized(void *msm);
 
 
 /* ============================================================================================================== */

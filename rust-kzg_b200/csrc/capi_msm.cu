@@ -1,6 +1,7 @@
 // capi_msm.cu -- the sppark-shaped MSM FFI (include/b200_kzg.h, section B1) on top of MsmEngine.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -31,11 +32,14 @@ MsmConfig choose_config(size_t n, bool fixed, int max_batch) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
     int c;
-    // fixed, >= 2^20 points: c = 20, W = 13 (260 bits: the top window still holds 15 scalar bits, so its digits spread
-    // over 2^15 buckets -- with c = 18, 19 or 21 the top window has 3 or 8 bits and a handful of buckets get 2^20 entries):
-    // measured at 2^20 c = 16 / 18 / 19 / 20 / 21 -> 7.22 / 14.4 / 9.85 / 6.53 / 14.6 ms (scripts/msm_window_sweep.py)
-    if (fixed) c = lg >= 20 ? 20 : lg >= 18 ? 16 : lg >= 14 ? lg - 2 : lg >= 11 ? 12 : lg >= 8 ? 10 : 8;
-    else c = lg >= 20 ? 16 : lg >= 16 ? 14 : lg >= 12 ? 12 : lg >= 9 ? 10 : 8;
+    // Window width.  Scalars are < r < 2^255 and, on a prepared table, uniform after the scalar randomisation (msm.cu), so
+    // the TOP window holds t = 255 - (W - 1) c bits and its 2^(t-1) buckets receive n entries: a width is only usable when
+    // that load, 2^(c - t) / W times the average, is moderate.  c = 13 (t = 8), 15 (t = 15), 16 (15), 17 (17) and 20 (15) qualify;
+    // 12, 14, 18, 19, 21, 22 leave the top window 3 - 8 bits against 2^11 .. 2^21 buckets elsewhere (measured at 2^20:
+    // c = 16 / 18 / 19 / 20 / 21 -> 7.22 / 14.4 / 9.85 / 6.3 / 14.6 ms, scripts/msm_window_sweep.py).
+    // fixed, >= 2^20 points: c = 20, W = 13, with the segment fold in front of the 15-bit reduce.
+    if (fixed) c = lg >= 20 ? 20 : lg >= 18 ? 16 : lg >= 16 ? 15 : lg >= 11 ? 13 : lg >= 8 ? 10 : 8;
+    else c = lg >= 20 ? 16 : lg >= 16 ? 15 : lg >= 12 ? 13 : lg >= 9 ? 10 : 8;
     c = env_int(fixed ? "B200_MSM_C" : "B200_MSM_VC", c);
     if (c < 4) c = 4;
     // beyond 16 the bucket set is folded by segments before the 15-bit reduce (k_segment_fold); a variable-base call has
@@ -50,11 +54,17 @@ MsmConfig choose_config(size_t n, bool fixed, int max_batch) {
     cfg.n = n;
     cfg.max_batch = fixed ? max_batch : 1;
     cfg.L = env_int("B200_MSM_L", 64);
+    // 13-bit windows over a few thousand points: a 2-bit segment fold in front of the marginal sums (measured on the 64-vector
+    // batches of the blob pipeline, 3.33 -> 2.99 ms: scripts/blob_window_sweep.py)
+    if (fixed && c == 13) cfg.fold = env_int("B200_MSM_FOLD", 2);
     // batch-affine accumulation (6 instead of 10 field multiplications per bucket addition, k_accumulate_affine): bit-exact
     // and tested, but OFF by default -- measured on B200 it loses to the XYZZ task kernel (7.3 - 7.9 ms against 4.95 ms at
     // 2^20): the 24-36 lock-step rounds each end in one field inversion whose latency (~60 us even with the bingcd inverse)
     // the two or three resident CTAs cannot hide (profiles/r02_affine.md).  B200_MSM_AFFINE=1 turns it on for A/B runs.
     cfg.affine = fixed && lg >= 17 && env_int("B200_MSM_AFFINE", 0) != 0;
+    // per-base scalar randomisation (msm.cu): digit distributions independent of the caller's scalars; the engine applies it
+    // only when every base is in the prime-order subgroup
+    cfg.randomize = fixed && env_int("B200_MSM_RANDOMIZE", 1) != 0;
     return cfg;
 }
 
@@ -157,7 +167,8 @@ void b200_msm_plan(size_t npoints, int fixed, int* c, int* c0, int* W, int* fold
     if (c) *c = cfg.c;
     if (c0) *c0 = w0;
     if (W) *W = cfg.W;
-    if (fold_bits) *fold_bits = cfg.c > 16 ? cfg.c - 16 : 0;   // what the 15-bit marginal reduce cannot take (msm.cu)
+    // what the 15-bit marginal reduce cannot take, or the configured fold of a narrow window (msm.cu: MsmEngine::kf_)
+    if (fold_bits) *fold_bits = std::max(cfg.c > 16 ? cfg.c - 16 : 0, std::min(cfg.fold, cfg.c - 2));
 }
 
 RustError b200_msm_prepared_device(void* msm, void* out_dev, size_t npoints, const void* scalars_dev, int batch,
@@ -283,6 +294,11 @@ RustError mult_pippenger(blst_p1* out, const blst_p1_affine points[], size_t npo
     });
 }
 
+/* 1 when the handle's table is scalar-randomised (all bases were in the prime-order subgroup at prepare), else 0 */
+int b200_msm_randomized(void* msm) {
+    MsmHandle* h = static_cast<MsmHandle*>(msm);
+    return h && h->eng->randomized() ? 1 : 0;
+}
 /* 1 when the last run on this handle used the batch-affine accumulation (k_accumulate_affine), else 0 */
 int b200_msm_last_affine(void* msm) {
     MsmHandle* h = static_cast<MsmHandle*>(msm);

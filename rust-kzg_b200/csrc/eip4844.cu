@@ -357,8 +357,15 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
     if (!bad) {
         fs_.reset(new FFTSettingsDev(13, st));  // FIELD_ELEMENTS_PER_EXT_BLOB = 8192 (kzg/src/eip_4844.rs:1072-1077)
         MsmConfig cfg;
-        cfg.c = env_int_local("B200_BLOB_C", 12);
-        cfg.fold = env_int_local("B200_BLOB_FOLD", -1);
+        // scalar randomisation (msm.cu): the Lagrange points of a real setup are in the prime-order subgroup (the engine checks)
+        cfg.randomize = env_int_local("B200_BLOB_RANDOMIZE", 1) != 0;
+        // randomised scalars are uniform in Fr whatever the blob bytes are: 13-bit windows (W = 20; the top window holds bits
+        // 247..254) with a 2-bit segment fold, as for the proofs -- 64 commitments 2.73 ms against 3.10 ms with c = 12, whose
+        // top window would hold 3 bits and put 7/8 of a blob's elements into four buckets (scripts/blob_window_sweep.py).
+        // Without randomisation blob elements usually have a zero top byte and c = 12 (bits 240..247 fill window 20) is the
+        // better split: 2.85 ms.
+        cfg.c = env_int_local("B200_BLOB_C", cfg.randomize ? 13 : 12);
+        cfg.fold = env_int_local("B200_BLOB_FOLD", cfg.randomize ? 2 : -1);
         cfg.c0 = env_int_local("B200_BLOB_C0", 0);
         cfg.W = (256 + cfg.c - 1) / cfg.c;
         cfg.fixed = true;
@@ -378,7 +385,8 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
         for (Lane& ln : lanes_) {
             // one table per window layout, shared by the lanes: what the L2 has to hold does not grow with the lane count
             ln.msm.reset(new MsmEngine(cfg, aff_brp, false, st, &ln == lanes_ ? nullptr : lanes_[0].msm.get()));
-            ln.msm_q.reset(new MsmEngine(cfg_q, aff_brp, false, st, &ln == lanes_ ? nullptr : lanes_[0].msm_q.get()));
+            const bool same = cfg_q.c == cfg.c && cfg_q.c0 == cfg.c0 && cfg_q.W == cfg.W && cfg_q.randomize == cfg.randomize;
+            ln.msm_q.reset(new MsmEngine(cfg_q, aff_brp, false, st, same ? lanes_[0].msm.get() : &ln == lanes_ ? nullptr : lanes_[0].msm_q.get()));
             ln.scalars = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
             ln.poly = dev_alloc<uint8_t>((size_t)max_batch * n * 32);
             ln.z = dev_alloc<uint8_t>((size_t)max_batch * 32);
@@ -606,16 +614,6 @@ __device__ __forceinline__ bool uncompress_point_u(const uint8_t* in, affine_t& 
     out.x = xm;
     out.y = y;
     return true;
-}
-__device__ __forceinline__ fp_t quad_mul_by_abs_z(const fp_t& base) {
-    const uint64_t Z = 0xd201000000010000ull;
-    fp_t acc = base;
-#pragma unroll 1
-    for (int bit = 62; bit >= 0; bit--) {
-        acc = quad_dbl(acc);
-        if ((Z >> bit) & 1) acc = quad_add(acc, base);
-    }
-    return acc;
 }
 __global__ void __launch_bounds__(32) k_decode_g1_checked(const uint8_t* __restrict__ in, int n, uint8_t* __restrict__ out,
                                                           int* __restrict__ status, int status_mod) {

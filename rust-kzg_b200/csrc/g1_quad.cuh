@@ -272,6 +272,36 @@ __device__ __forceinline__ fp_t quad_mul_scalar(const fp_t& p, const uint32_t (&
     return acc;
 }
 
+// [|z|] p for quad-distributed p, z = -0xd201000000010000 the BLS parameter: the ladder of the subgroup test
+// (beta x, y) == -[z^2] P  (eprint 2021/1130 sec. 6, zkcrypto/bls12_381/src/g1.rs:401-410); the scalar is a constant, so
+// every quad of a warp follows the same instruction stream
+__device__ __forceinline__ fp_t quad_mul_by_abs_z(const fp_t& base) {
+    const uint64_t Z = 0xd201000000010000ull;
+    fp_t acc = base;
+#pragma unroll 1
+    for (int bit = 62; bit >= 0; bit--) {
+        acc = quad_dbl(acc);
+        if ((Z >> bit) & 1) acc = quad_add(acc, base);
+    }
+    return acc;
+}
+// p (affine, non-infinity, on the curve) is in the prime-order subgroup; comp = p quad-distributed (X, Y, 1, 1).
+// The verdict is valid on the first lane of the quad.  All 32 lanes must call.
+__device__ __forceinline__ bool quad_in_subgroup(const affine_t& a, const fp_t& comp) {
+    const int base = threadIdx.x & 28;
+    fp_t t = quad_mul_by_abs_z(comp);                      // |z| P
+    const bool t_inf = __shfl_sync(kFullMask, (int)t.is_zero(), base | 2);
+    fp_t u = quad_mul_by_abs_z(t);                         // z^2 P
+    xyzz_t U = quad_gather(u);                             // valid on the quad's first lane
+    fp_t beta;
+    const uint32_t Bm[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
+                             0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
+#pragma unroll
+    for (int k = 0; k < 12; k++) beta.v[k] = Bm[k];
+    // (beta x, y) == -(X/ZZ, Y/ZZZ)  <=>  beta x ZZ == X  and  y ZZZ == -Y
+    return !t_inf && !U.is_inf() && (beta * a.x * U.zz == U.x) && (a.y * U.zzz == U.y.neg());
+}
+
 // lane 0 of the warp ends up with the sum over the warp's 32 points
 __device__ __forceinline__ xyzz_t warp_sum_xyzz(const xyzz_t& v) { return quad_gather(seg_sum_quad(v, 32)); }
 

@@ -24,15 +24,50 @@ static constexpr int kMaxWindow = 22;    // wider windows than kReduceBits + 1 g
 // raw > 2^(cw-1) becomes raw - 2^cw with carry 1, so |digit| <= 2^(c-1): bucket |digit| - 1 of 2^(c-1) buckets; windows
 // reaching bit 256 (c0 + c*(W-1) >= 256, s < r < 0.91 * 2^255) leave no final carry.  Same digit set as the reference's
 // Booth recoding (kzg/src/msm/pippenger_utils.rs:251-281): sum_j digit_j 2^(o_j) = s (tests/test_msm_plan_cpu.py).
+// ---------------------------------------------------------------------------------------------------------------
+// Scalar randomisation for fixed-base tables (MsmConfig::randomize).  The table is built over Q_i = rho_i^-1 * P_i and every
+// scalar is multiplied by rho_i before it is cut into digits:  sum (s_i rho_i) Q_i = sum s_i P_i  for points of the
+// prime-order subgroup (checked at prepare: k_check_subgroup).  rho_i is pseudo-random and different for every base, so
+// whatever the caller's scalars look like -- all equal (the all-0x02 consensus blob), small, r - 1, zero top bytes -- the
+// DIGITS are uniform: no bucket ever collects a whole window, any window width is safe, and the timing no longer depends
+// on the input (c = 18 / 19 / 21 cost 2.3x because of top-window collisions; all-equal scalars 1.6 - 2.3x).
+// The multiplication replaces the Montgomery conversion the kernel does anyway, so it is free.  Zero scalars stay zero.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+// canonical rho_i, 0 < rho_i < 2^254 < r
+__device__ __forceinline__ fr_t rho_of(uint64_t seed, uint64_t index) {
+    fr_t r;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint64_t w = splitmix64(seed ^ (index * 4 + j) * 0xd1342543de82ef95ull);
+        if (j == 3) w &= 0x3fffffffffffffffull;
+        r.v[2 * j] = (uint32_t)w;
+        r.v[2 * j + 1] = (uint32_t)(w >> 32);
+    }
+    if (r.is_zero()) r.v[0] = 1;
+    return r;
+}
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(const uint4* __restrict__ scalars, size_t n, size_t row_stride, size_t total,
                                                 int c, int c0, int W, int nb, int fixed, int mont, uint32_t* __restrict__ ctr,
-                                                uint32_t* __restrict__ entries, size_t period, size_t period_n, size_t gid0) {
+                                                uint32_t* __restrict__ entries, size_t period, size_t period_n, size_t gid0,
+                                                uint64_t rho_seed) {
     size_t gid = gid0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= total) return;
     size_t vec = gid / n, i = gid - vec * n;
     fr_t s = load_field_ro<fr_t>(scalars + 2 * gid);
-    if (mont) s = s.from_mont();
+    if (rho_seed) {
+        // canonical (s rho_i): Montgomery product of (s R) and rho, or of s and (rho R)
+        fr_t rho = rho_of(rho_seed, (uint64_t)((vec % period) * period_n + i));
+        s = mont ? s * rho : s * rho.to_mont();
+    } else if (mont) {
+        s = s.from_mont();
+    }
     uint32_t w[9];
 #pragma unroll
     for (int k = 0; k < 8; k++) w[k] = s.v[k];
@@ -838,6 +873,43 @@ __global__ void __launch_bounds__(32) k_horner(const uint8_t* __restrict__ group
     if (lane == 2) store_field(out_jac + 96, acc);
 }
 
+// randomisation, step 1: are all bases in the prime-order subgroup (or infinity)?  One lane quad per point.
+__global__ void __launch_bounds__(32) k_check_subgroup(const uint8_t* __restrict__ table, size_t stride, size_t n, int* __restrict__ bad) {
+    const size_t q = (size_t)blockIdx.x * 8 + (threadIdx.x >> 2);
+    const int role = threadIdx.x & 3;
+    const bool live = q < n;
+    affine_t a = load_affine(table + (live ? q : 0) * stride);
+    const bool inf = a.is_inf();
+    fp_t comp = role == 0 ? a.x : role == 1 ? a.y : fp_t::one();
+    if (inf) comp = fp_t::zero();
+    const bool ok = quad_in_subgroup(a, comp);
+    if (role == 0 && live && !inf && !ok) *bad = 1;
+}
+// randomisation, step 2: P_i <- rho_i^-1 * P_i in place (row 0 of the table), one lane quad per point: GLV scalar
+// multiplication on the quad arithmetic, back to affine with one warp-shared field inversion
+__global__ void __launch_bounds__(32) k_scale_points(uint8_t* __restrict__ table, size_t stride, size_t n, uint64_t seed) {
+    __shared__ __align__(16) uint8_t qtable[kQuadTableBytes];
+    const size_t q = (size_t)blockIdx.x * 8 + (threadIdx.x >> 2);
+    const int role = threadIdx.x & 3, base = threadIdx.x & 28;
+    const bool live = q < n;
+    const size_t i = live ? q : 0;
+    affine_t a = load_affine(table + i * stride);
+    const bool inf = a.is_inf();
+    fp_t comp = role == 0 ? a.x : role == 1 ? a.y : fp_t::one();
+    if (inf) comp = fp_t::zero();
+    // k = rho_i^-1 mod r, canonical (the four lanes of a quad compute the same value)
+    fr_t k = warp_inverse(rho_of(seed, (uint64_t)i).to_mont()).from_mont();
+    comp = quad_mul_scalar(comp, k.v, qtable);
+    // affine: x = X / ZZ, y = Y / ZZZ with 1/ZZ = ZZZ^-2 ZZ^2 (ZZ^3 = ZZZ^2)
+    const fp_t zz = shfl_idx_fp(comp, base | 2), zzz = shfl_idx_fp(comp, base | 3);
+    const bool rinf = zz.is_zero();
+    const fp_t izzz = warp_inverse(rinf ? fp_t::one() : zzz);
+    const fp_t izz = izzz.sqr() * zz.sqr();
+    fp_t out = role == 0 ? comp * izz : comp * izzz;
+    if (rinf) out = fp_t::zero();
+    if (live && role < 2) store_field(table + i * stride + role * 48, out);
+}
+
 // table rows for FIXED engines: row j = 2^(c*j) * P_i, affine.  One thread per point walks all rows
 // (c doublings in XYZZ, then back to affine with one warp-shared field inversion).  One-time cost at prepare.
 __global__ void __launch_bounds__(128) k_build_rows(uint8_t* __restrict__ table, size_t n, int W, int c, int c0, size_t stride) {
@@ -974,6 +1046,7 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
             share_table->stride_ != stride_)
             throw CudaError(-1, "MsmEngine: shared table has a different layout");
         table_ = share_table->table_;
+        rho_seed_ = share_table->rho_seed_;
         owns_table_ = false;
         points = nullptr;
     } else {
@@ -1006,6 +1079,22 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
         const cudaMemcpyKind kind = host_points ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
         if (stride_ == 96) B200_CUDA_CHECK(cudaMemcpyAsync(table_, points, table_points * 96, kind, stream));
         else B200_CUDA_CHECK(cudaMemcpy2DAsync(table_, stride_, points, 96, 96, table_points, kind, stream));
+        if (cfg_.fixed && cfg_.randomize) {
+            // scalar randomisation needs bases of the prime-order subgroup: check, then scale row 0 by rho_i^-1
+            int* d_bad = dev_alloc<int>(1);
+            int bad = 0;
+            B200_CUDA_CHECK(cudaMemsetAsync(d_bad, 0, sizeof(int), stream));
+            k_check_subgroup<<<div_up(table_points, 8), 32, 0, stream>>>((const uint8_t*)table_, stride_, table_points, d_bad);
+            cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            cudaFree(d_bad);
+            B200_CUDA_CHECK(e);
+            if (!bad) {
+                rho_seed_ = cfg_.rho_seed ? cfg_.rho_seed : 0x4b5a47b200ull;
+                k_scale_points<<<div_up(table_points, 8), 32, 0, stream>>>((uint8_t*)table_, stride_, table_points, rho_seed_);
+                B200_LAUNCH_CHECK();
+            }
+        }
         if (cfg_.fixed && cfg_.W > 1) {
             k_build_rows<<<div_up(table_points, 128), 128, 0, stream>>>((uint8_t*)table_, table_points, cfg_.W, cfg_.c, cfg_.c0, stride_);
             B200_LAUNCH_CHECK();
@@ -1123,12 +1212,12 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
             B200_CUDA_CHECK(cudaEventRecord(copy_ev_[k], copy_stream_));
             B200_CUDA_CHECK(cudaStreamWaitEvent(st, copy_ev_[k], 0));
             k_digits<false><<<div_up(hi - lo, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, hi, c, c0, W, nb_, cfg_.fixed,
-                                                                 mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n, lo);
+                                                                 mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n, lo, rho_seed_);
             launches++;
         }
     } else {
         k_digits<false><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, c0, W, nb_,
-                                                            cfg_.fixed, mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n, 0);
+                                                            cfg_.fixed, mont, counts_, nullptr, (size_t)cfg_.bases_period, cfg_.n, 0, rho_seed_);
         launches++;
     }
     // batch-affine accumulation when the call fills the machine: S entries per chunk, chunk grid = every slot of every thread
@@ -1145,7 +1234,7 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     else launches += scan_exclusive(counts_, nkeys, (uint32_t)L, task_base_, nullptr, scan_tmp_, st);
     // 3 scatter
     k_digits<true><<<div_up(total, 256), 256, 0, st>>>((const uint4*)scalars_dev, npoints, row_stride, total, c, c0, W, nb_,
-                                                       cfg_.fixed, mont, cursor_, entries_, (size_t)cfg_.bases_period, cfg_.n, 0);
+                                                       cfg_.fixed, mont, cursor_, entries_, (size_t)cfg_.bases_period, cfg_.n, 0, rho_seed_);
     launches++;
     const bool prof = profiling_ && prof_count_ < kProfSlots;
     auto prof_begin = [&] {

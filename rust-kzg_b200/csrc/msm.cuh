@@ -43,6 +43,10 @@ struct MsmConfig {
                     // elements < 2^248) then still spread its digits over many buckets instead of one or two.
     int fold = -1;  // bucket-index bits folded by k_segment_fold before the marginal reduce; -1: only what the reduce
                     // cannot take (c - 1 - 15 bits for windows wider than 16)
+    bool randomize = false;  // FIXED only: multiply every scalar by a per-base pseudo-random rho_i and build the table over
+                             // rho_i^-1 * P_i (msm.cu, "scalar randomisation"): digit distributions become independent of the
+                             // input.  Only applied when every base is in the prime-order subgroup (checked at construction).
+    uint64_t rho_seed = 0;   // 0: the library's fixed seed
     bool affine = false;   // FIXED only: batch-affine accumulation (k_accumulate_affine) for calls that fill the machine; the table
                            // then uses 128-byte slots per point (one aligned line per gather instead of a straddling 96 bytes)
     int affine_k = 10;     // slots (chunks) per thread of the batch-affine kernel: denominators per inversion = 128 * affine_k
@@ -77,6 +81,7 @@ public:
     const void* table() const { return table_; }
     size_t table_stride() const { return stride_; }
     bool last_run_affine() const { return last_affine_; }
+    bool randomized() const { return rho_seed_ != 0; }
     // optional device-side timing of the accumulate kernel (bench.py's roofline): when enabled, every run() brackets
     // k_accumulate with CUDA events on the launching stream; profile_read() sums the completed pairs and resets.
     void set_profiling(bool on) { profiling_ = on; }
@@ -108,6 +113,7 @@ private:
     cudaEvent_t copy_start_ = nullptr;
     void* table_ = nullptr;      // affine rows
     bool owns_table_ = true;
+    uint64_t rho_seed_ = 0;      // != 0: scalar randomisation is active on this table
     uint32_t* counts_ = nullptr;  // [keys+1]
     uint32_t* offsets_ = nullptr;
     uint32_t* cursor_ = nullptr;

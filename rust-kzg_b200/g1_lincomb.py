@@ -58,7 +58,7 @@ class PreparedMsm:
         return {"c": c.value, "W": w.value, "table_bytes": tb.value, "launches": l.value,
                 # path of the LAST run: batch-affine accumulation (6 M per addition + ~0.6 M of shared inversion work) or XYZZ
                 "accumulate": "affine" if aff else "xyzz", "accumulate_kernel": "k_accumulate_affine" if aff else "k_accumulate",
-                "fp_mul_per_add": 6.6 if aff else 10.0}
+                "fp_mul_per_add": 6.6 if aff else 10.0, "randomized": bool(_L().b200_msm_randomized(self.h))}
 
     def last_counts(self):
         """(entries, tasks) of the last run: the accumulate kernel did entries - tasks mixed additions."""

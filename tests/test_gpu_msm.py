@@ -307,3 +307,43 @@ def test_batch_affine_accumulation_option(B, K, lagrange_affine):
                 assert h.info()["accumulate"] == "affine"
                 assert K.p1_compress(got) == K.p1_compress(K.msm_affine(lagrange_affine, fold(eff), nthreads=8)), (tree, tag, name)
             h.close()
+
+
+def test_scalar_randomisation_and_its_subgroup_guard(B, K, lagrange_affine):
+    """Prepared tables multiply every scalar by a per-base rho_i over a table of rho_i^-1 * P_i (csrc/msm.cu): the same
+    group element for bases of the prime-order subgroup -- checked against the oracle with randomisation on and off -- and
+    NOT applied when a base lies outside the subgroup (the identity rho * rho^-1 = 1 holds mod r only), where the plain
+    table must still give the exact integer combination the oracle computes."""
+    rng = np.random.default_rng(91)
+    n = 4096
+    sc = K.fr_from_ints(rand_ints(rng, n, R_MOD))
+    want = K.p1_compress(K.msm_affine(lagrange_affine, sc, nthreads=8))
+    on = B.PreparedMsm(lagrange_affine)
+    assert on.info()["randomized"] is True
+    off = _with_env("B200_MSM_RANDOMIZE", 0, lambda: B.PreparedMsm(lagrange_affine))
+    assert off.info()["randomized"] is False
+    assert K.p1_compress(on.mult(sc)) == want and K.p1_compress(off.mult(sc)) == want
+    on.close()
+    off.close()
+    # a curve point outside G1: decode random abscissas until one is on the curve (blst_p1_uncompress does not test the
+    # subgroup); almost every curve point has a cofactor component
+    outside = None
+    for t in range(200):
+        x = int(rng.integers(1, 1 << 62)) * 0x10001 + t
+        b = bytearray(x.to_bytes(48, "big"))
+        b[0] |= 0x80
+        try:
+            cand = K.p1_uncompress_affine(bytes(b))
+        except Exception:
+            continue
+        if not K.p1_in_g1(K.p1_from_affine(cand)):
+            outside = cand
+            break
+    assert outside is not None
+    pts = lagrange_affine[:256].copy()
+    pts[17] = outside
+    h = B.PreparedMsm(pts)
+    assert h.info()["randomized"] is False                      # the guard: one base outside the subgroup turns it off
+    s256 = K.fr_from_ints(rand_ints(rng, 256, R_MOD))
+    assert K.p1_compress(h.mult(s256)) == K.p1_compress(K.msm_affine(pts, s256, nthreads=4))
+    h.close()

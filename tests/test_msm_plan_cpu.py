@@ -38,10 +38,17 @@ def test_plan_invariants(B):
             assert 4 <= p["c"] <= (22 if fixed else 20)
             assert p["c0"] + (p["W"] - 1) * p["c"] >= 256, p       # the top window absorbs the last carry
             assert p["W"] == -(-256 // p["c"])
-            assert p["fold_bits"] == max(0, p["c"] - 16)
+            # wide windows are folded down to the 15-bit reduce; 13-bit fixed-base windows take the measured 2-bit fold
+            assert p["fold_bits"] == max(p["c"] - 16, 2 if (fixed and p["c"] == 13) else 0, 0)
+            # scalars are < r < 2^255 and uniform on a randomised table: the top window must keep enough of its bits that its
+            # buckets are not overloaded -- 2^(c - t) / W, its load relative to the average, stays below 4
+            t = 255 - (p["W"] - 1) * p["c"]
+            if t <= 0:                       # c divides 255 (15, 17): the last window only ever sees a carry that cannot occur,
+                t += p["c"]                  # the window below it is the top one and is full
+            assert 2.0 ** (p["c"] - t) / p["W"] < 4, p
     assert B.msm_plan(1 << 20)["c"] == 20 and B.msm_plan(1 << 20)["W"] == 13     # measured optimum (profiles/r01_window_sweeps.md)
     assert B.msm_plan(1 << 21)["c"] == 20
-    assert B.msm_plan(1 << 19)["c"] == 16 and B.msm_plan(4096)["c"] == 12
+    assert B.msm_plan(1 << 19)["c"] == 16 and B.msm_plan(4096)["c"] == 13
     assert B.msm_plan(1 << 20, False)["c"] == 16                                  # one bucket set per window: no wide windows
 
 
