@@ -393,6 +393,24 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
             ln.y = dev_alloc<uint8_t>((size_t)max_batch * 32);
             ln.out_jac = dev_alloc<uint8_t>((size_t)max_batch * 144);
         }
+        // direct lookup table of the Lagrange points for batches of up to direct_max_ blobs (1.5 GiB; B200_BLOB_DIRECT=0
+        // or a failed allocation leaves every batch to the bucket engine)
+        direct_max_ = std::min(max_batch, env_int_local("B200_BLOB_DIRECT", 16));
+        if (direct_max_ > 0) {
+            void* p = nullptr;
+            if (cudaMalloc(&p, direct_table_bytes(n)) == cudaSuccess) {
+                lag_direct_ = p;
+                MsmConfig c8;
+                c8.c = 8; c8.W = 32; c8.fixed = true; c8.n = n; c8.max_batch = 1; c8.L = 64;
+                MsmEngine rows8(c8, aff_brp, false, st);          // rows 2^(8j) * P_i, 96-byte stride; dropped after the build
+                launch_direct_build(rows8.table(), lag_direct_, n, st);
+                B200_CUDA_CHECK(cudaStreamSynchronize(st));
+                for (Lane& ln : lanes_) ln.direct_part = dev_alloc<uint8_t>((size_t)direct_max_ * (n / 4) * 192);
+            } else {
+                cudaGetLastError();
+                direct_max_ = 0;
+            }
+        }
         // the 4096 domain = first half of the bit-reversed 8192 roots (kzg/src/eip_4844.rs:463, 976)
         domain_ = dev_alloc<uint8_t>((size_t)n * 32);
         B200_CUDA_CHECK(cudaMemcpyAsync(domain_, fs_->brp_roots_dev(), (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
@@ -410,10 +428,20 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
 
 KzgSettingsDev::~KzgSettingsDev() {
     cudaFree(lagrange_jac_); cudaFree(monomial_jac_); cudaFree(domain_);
-    for (Lane& ln : lanes_) { cudaFree(ln.scalars); cudaFree(ln.poly); cudaFree(ln.z); cudaFree(ln.y); cudaFree(ln.out_jac); }
+    for (Lane& ln : lanes_) { cudaFree(ln.scalars); cudaFree(ln.poly); cudaFree(ln.z); cudaFree(ln.y); cudaFree(ln.out_jac); cudaFree(ln.direct_part); }
+    cudaFree(lag_direct_);
     cudaFree(cells_a_); cudaFree(cells_b_);
     cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_); cudaFree(fk_direct_);
     cudaFree(g2_affine_); cudaFree(g2_jac_); cudaFree(g2_lines_); cudaFree(vf_buf_); cudaFree(das_buf_);
+}
+
+// Small batches: direct table lookups, two launches (fk20_direct.cu); batches that fill the machine: the bucket engine.
+void KzgSettingsDev::lagrange_msm(int lane, MsmEngine& eng, int n, cudaStream_t st) {
+    Lane& ln = lanes_[lane % kLanes];
+    if (lag_direct_ && n <= direct_max_)
+        launch_direct_msm(ln.scalars, lag_direct_, ln.direct_part, ln.out_jac, n, (int)kFieldElementsPerBlob, st);
+    else
+        eng.run(ln.scalars, kFieldElementsPerBlob, n, false, ln.out_jac, st);
 }
 
 void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st, int lane) {
@@ -422,9 +450,9 @@ void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* o
     size_t total = (size_t)n * kFieldElementsPerBlob;
     k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, (uint8_t*)ln.scalars, nullptr, status);
     B200_LAUNCH_CHECK();
-    ln.msm->run(ln.scalars, kFieldElementsPerBlob, n, false, ln.out_jac, st);
+    lagrange_msm(lane, *ln.msm, n, st);
     launch_points_to_compressed(ln.out_jac, out48, n, st);
-    launches_ = 2 + ln.msm->launches_per_run();
+    launches_ = 2 + (lag_direct_ && n <= direct_max_ ? 2 : ln.msm->launches_per_run());
 }
 
 void KzgSettingsDev::compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes, int z_reduce, int n, uint8_t* proofs48,
@@ -438,7 +466,7 @@ void KzgSettingsDev::compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes
                                                                               (const uint8_t*)domain_, (uint8_t*)ln.scalars,
                                                                               (uint8_t*)ln.y);
     B200_LAUNCH_CHECK();
-    ln.msm_q->run(ln.scalars, kFieldElementsPerBlob, n, false, ln.out_jac, st);
+    lagrange_msm(lane, *ln.msm_q, n, st);
     launch_points_to_compressed(ln.out_jac, proofs48, n, st);
     int extra = 0;
     if (y32) {
@@ -446,7 +474,7 @@ void KzgSettingsDev::compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes
         B200_LAUNCH_CHECK();
         extra = 1;
     }
-    launches_ = 4 + extra + ln.msm_q->launches_per_run();
+    launches_ = 4 + extra + (lag_direct_ && n <= direct_max_ ? 2 : ln.msm_q->launches_per_run());
 }
 
 void KzgSettingsDev::compute_cells(const uint8_t* blobs, int n, uint8_t* cells_out, int* status, cudaStream_t st) {

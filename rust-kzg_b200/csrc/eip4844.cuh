@@ -109,7 +109,12 @@ private:
         void* z = nullptr;         // max_batch Montgomery
         void* y = nullptr;         // max_batch Montgomery
         void* out_jac = nullptr;   // max_batch Jacobian results
+        void* direct_part = nullptr;  // partial sums of the direct small-batch MSM
     } lanes_[kLanes];
+    void* lag_direct_ = nullptr;   // every digit multiple of the 4096 Lagrange points (direct small-batch MSM), or nullptr
+    int direct_max_ = 0;           // largest batch the direct form serves (larger ones fill the machine: bucket engine)
+    // sum over the Lagrange points for n vectors of canonical scalars in ln.scalars -> ln.out_jac
+    void lagrange_msm(int lane, MsmEngine& eng, int n, cudaStream_t st);
     void* lagrange_jac_ = nullptr;
     void* monomial_jac_ = nullptr;
     void* domain_ = nullptr;    // brp_roots_of_unity[0..4096) of the 8192 table (Montgomery)
@@ -136,6 +141,10 @@ void launch_check_challenge_inputs(uint8_t* workspace_dev, const uint8_t* commit
 size_t fk_direct_table_bytes();
 void launch_fk_direct_build(const void* rows, void* table, cudaStream_t st);
 void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_jac, int nvec, cudaStream_t st);
+// the same direct tables for small batches of 4096-term MSMs over the Lagrange points (fk20_direct.cu)
+size_t direct_table_bytes(size_t npts);
+void launch_direct_build(const void* rows, void* table, size_t npts, cudaStream_t st);
+void launch_direct_msm(const void* scalars, const void* table, void* partials, void* out_jac, int nvec, int npts, cudaStream_t st);
 // test hook (verify.cu): sum k_i P_i through the quad / GLV scalar multiplication used by the verifiers and fft_g1
 void selftest_lincomb_quads(const void* points_affine_dev, const void* scalars_mont_dev, int n, void* out_jac_dev, cudaStream_t st);
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input

@@ -11,6 +11,7 @@
 // No sort, no buckets, no per-lincomb reduction kernels.
 #include "eip4844.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include "g1.cuh"
 #include "g1_quad.cuh"
@@ -22,14 +23,15 @@ namespace b200 {
 static constexpr int kDPts = 8192, kDW = 32, kDDigits = 128, kDCell = 64, kDChunk = 16;
 
 size_t fk_direct_table_bytes() { return (size_t)kDPts * kDW * kDDigits * 96; }
+size_t direct_table_bytes(size_t npts) { return npts * kDW * kDDigits * 96; }
 
 // rows: the fixed-base rows of the MSM engine, row j = 2^(8j) * P_pt (affine), row-major [32][8192].
 // One thread per (pt, j): the 128 multiples by repeated mixed addition, converted to affine sixteen at a time with one
 // field inversion per warp (Montgomery's trick inside the thread, warp_inverse across the lanes).
-__global__ void __launch_bounds__(128) k_fk_direct_build(const uint8_t* __restrict__ rows, uint8_t* __restrict__ table) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // grid covers exactly 8192 * 32 threads
+__global__ void __launch_bounds__(128) k_fk_direct_build(const uint8_t* __restrict__ rows, uint8_t* __restrict__ table, size_t npts) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // grid covers exactly npts * 32 threads (npts % 4 == 0)
     const size_t pt = t / kDW, j = t % kDW;
-    cc::affine_t base = cc::load_affine(rows + (j * kDPts + pt) * 96);
+    cc::affine_t base = cc::load_affine(rows + (j * npts + pt) * 96);
     uint8_t* out = table + ((pt * kDW + j) * kDDigits) * 96;
     cc::xyzz_t acc = cc::affine_to_xyzz(base);
     for (int c0 = 0; c0 < kDDigits; c0 += kDChunk) {
@@ -56,8 +58,11 @@ __global__ void __launch_bounds__(128) k_fk_direct_build(const uint8_t* __restri
         }
     }
 }
-void launch_fk_direct_build(const void* rows, void* table, cudaStream_t st) {
-    k_fk_direct_build<<<kDPts * kDW / 128, 128, 0, st>>>((const uint8_t*)rows, (uint8_t*)table);
+void launch_fk_direct_build(const void* rows, void* table, cudaStream_t st) { launch_direct_build(rows, table, kDPts, st); }
+// rows: [32][npts] fixed-base rows for c = 8 (96-byte stride); table: npts x 32 x 128 affine points
+void launch_direct_build(const void* rows, void* table, size_t npts, cudaStream_t st) {
+    if (npts % 4) throw CudaError(-1, "direct table: point count must be a multiple of 4");
+    k_fk_direct_build<<<(unsigned)(npts * kDW / 128), 128, 0, st>>>((const uint8_t*)rows, (uint8_t*)table, npts);
     B200_LAUNCH_CHECK();
 }
 
@@ -130,6 +135,86 @@ void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_
     else if (variant == 2) k_fk_direct_lincomb<ArInline, 2><<<div_up(nvec, 2), 64, 0, st>>>(s8, t8, o8, nvec);
     else if (variant == 3) k_fk_direct_lincomb<ArCall, 2><<<div_up(nvec, 2), 64, 0, st>>>(s8, t8, o8, nvec);
     else k_fk_direct_lincomb<ArInline, 4><<<div_up(nvec, 4), 128, 0, st>>>(s8, t8, o8, nvec);
+    B200_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small batches of 4096-term MSMs over the Lagrange points (blob_to_kzg_commitment / compute_kzg_proof of 1 .. 32 blobs) by
+// the same direct lookups.  The bucket pipeline is a chain of ~20 dependent, mostly tiny kernels whose reduction tail
+// (bucket combine, marginal sums, weighted sums) costs ~0.45 ms however little work there is: one blob takes 0.55 ms, and
+// that latency is what concurrent single-blob callers queue behind (coalesce.cuh).  Direct form: a warp takes P consecutive
+// points, lane j owns window j (8-bit Booth digits need no carry chain), P mixed additions per lane with the next gather in
+// flight, one warp tree; a second kernel folds the 4096 / P partial sums of every vector.  No sort, no buckets: two
+// launches, chain length P + 2 trees.  table: 4096 x 32 x 128 affine points (1.5 GiB, built once per settings object).
+template <class AR>
+__global__ void __launch_bounds__(64) k_direct_msm_partial(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
+                                                           uint8_t* __restrict__ partials, int npts, int P, size_t nwarps) {
+    const int lane = threadIdx.x & 31;
+    const size_t w = (size_t)blockIdx.x * 2 + (threadIdx.x >> 5);
+    if (w >= nwarps) return;                                  // whole warps leave together
+    const size_t per_vec = (size_t)npts / P, v = w / per_vec, p0 = (w % per_vec) * P;
+    const uint32_t* sc = reinterpret_cast<const uint32_t*>(scalars + (v * npts + p0) * 32);
+    auto digit = [&](int i) -> int {                          // Booth digit of window `lane` of scalar i (see k_fk_direct_lincomb)
+        uint32_t wd = sc[i * 8 + (lane >> 2)];
+        uint32_t byte = (wd >> ((lane & 3) * 8)) & 0xffu;
+        uint32_t below = lane == 0 ? 0u : ((lane & 3) ? (wd >> ((lane & 3) * 8 - 1)) & 1u : sc[i * 8 + (lane >> 2) - 1] >> 31);
+        return (int)byte + (int)below - (int)((byte >> 7) << 8);
+    };
+    auto entry = [&](int i, int d) -> const uint8_t* {
+        const int mag = d < 0 ? -d : d;
+        return table + ((((p0 + i) * kDW + lane) * kDDigits) + (mag ? mag - 1 : 0)) * 96;
+    };
+    typename AR::xyzz acc = AR::xyzz::inf();
+    int d = digit(0);
+    typename AR::affine p = AR::load(entry(0, d));
+#pragma unroll 1
+    for (int i = 0; i < P; i++) {
+        typename AR::affine cur = p;
+        const int cd = d;
+        if (i + 1 < P) {
+            d = digit(i + 1);
+            p = AR::load(entry(i + 1, d));
+        }
+        if (cd == 0) cur = typename AR::affine{AR::fp::zero(), AR::fp::zero()};
+        cur.y = cur.y.cneg(cd < 0);
+        AR::add(acc, cur);
+    }
+    xyzz_t a2;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { a2.x.v[k] = acc.x.v[k]; a2.y.v[k] = acc.y.v[k]; a2.zzz.v[k] = acc.zzz.v[k]; a2.zz.v[k] = acc.zz.v[k]; }
+    fp_t q = seg_sum_quad(a2, 32);
+    if (lane < 4) store_field(partials + w * 192 + quad_store_offset(), q);
+}
+// one CTA of min(m, 256) threads per vector: m = 4096 / P partial sums (64 <= m <= 512, a power of two) -> Jacobian result
+__global__ void __launch_bounds__(256) k_direct_msm_reduce(const uint8_t* __restrict__ partials, int m, uint8_t* __restrict__ out_jac) {
+    __shared__ __align__(16) uint8_t sh[8 * 192];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint8_t* base = partials + (size_t)blockIdx.x * m * 192;
+    xyzz_t a = load_xyzz(base + (size_t)threadIdx.x * 192);
+    for (int i = threadIdx.x + blockDim.x; i < m; i += blockDim.x) {
+        xyzz_t b = load_xyzz(base + (size_t)i * 192);
+        xyzz_add(a, b);
+    }
+    fp_t q = seg_sum_quad(a, 32);
+    if (lane < 4) store_field(sh + wid * 192 + quad_store_offset(), q);
+    __syncthreads();
+    if (wid == 0) {
+        fp_t c = (lane >> 2) < nw ? load_field<fp_t>(sh + (lane >> 2) * 192 + quad_store_offset()) : fp_t::zero();
+        fp_t t = quad_tree(c, 32);                           // the (at most 8) warp sums, one quad each
+        fp_t j = t * shfl_xor_fp(t, 2);                      // Jacobian (X ZZ, Y ZZZ, ZZ); infinity stays all-zero
+        if (lane < 2) store_field(out_jac + (size_t)blockIdx.x * 144 + lane * 48, j);
+        if (lane == 2) store_field(out_jac + (size_t)blockIdx.x * 144 + 96, t);
+    }
+}
+// scalars: nvec x npts canonical little-endian 32-byte scalars; partials: workspace of nvec * (npts / P) XYZZ points
+void launch_direct_msm(const void* scalars, const void* table, void* partials, void* out_jac, int nvec, int npts, cudaStream_t st) {
+    // P points per warp: as few as keep one wave of warps on the machine (148 SMs x 12 warps), between 8 and 64
+    int P = 8;
+    while (P < 64 && (size_t)nvec * npts / P > 148 * 12) P <<= 1;
+    const size_t nwarps = (size_t)nvec * npts / P;
+    k_direct_msm_partial<ArCall><<<(unsigned)((nwarps + 1) / 2), 64, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)partials,
+                                                                           npts, P, nwarps);
+    k_direct_msm_reduce<<<nvec, std::min(npts / P, 256), 0, st>>>((const uint8_t*)partials, npts / P, (uint8_t*)out_jac);
     B200_LAUNCH_CHECK();
 }
 

@@ -292,3 +292,35 @@ def test_helper_exports_compute_challenge_vectors(B, K, vectors, golden_blobs):
         B.bytes_to_kzg_commitment(bytes(48))           # compression flag missing
     x = K.fr_from_ints([R_MOD - 5])[0]
     assert B.bytes_from_bls_field(x) == (R_MOD - 5).to_bytes(32, "big")
+
+
+def test_direct_small_batch_msm_matches_bucket_engine(B, K, oracle_settings):
+    """batches of up to 24 blobs take the direct-lookup MSM (csrc/fk20_direct.cu: no buckets, two launches), larger ones the
+    bucket engine; both must give the oracle's bytes, also for adversarial blob contents, and agree at the switch-over"""
+    import os
+    rng = np.random.default_rng(55)
+    blobs = rng.integers(0, 256, size=(26, 4096, 32), dtype=np.uint8)
+    blobs[:, :, 0] = 0
+    blobs[1] = 0                                            # zero polynomial: commitment = infinity
+    blobs[2, :, :31] = 0
+    blobs[2, :, 31] = 2                                     # the all-0x02 consensus blob
+    blobs[3] = np.frombuffer((R_MOD - 1).to_bytes(32, "big"), np.uint8)   # every element r - 1
+    blobs = blobs.reshape(26, -1)
+    zs = blobs[0].reshape(4096, 32)[:26].copy()
+    want_c = [K.blob_to_kzg_commitment(blobs[i].tobytes(), oracle_settings) for i in range(26)]
+    want_p = [K.compute_kzg_proof(blobs[i].tobytes(), zs[i].tobytes(), oracle_settings) for i in (0, 2, 3, 25)]
+    for direct in ("24", "0"):
+        os.environ["B200_BLOB_DIRECT"] = direct
+        try:
+            ts = B.KZGSettings.load_trusted_setup_file()
+        finally:
+            del os.environ["B200_BLOB_DIRECT"]
+        for n in (1, 3, 24, 25, 26):
+            got = ts.blob_to_kzg_commitment_batch(blobs[:n])
+            assert [bytes(g) for g in got] == want_c[:n], (direct, n)
+        proofs, ys = ts.compute_kzg_proof_batch(blobs[:26], zs)
+        for k, i in enumerate((0, 2, 3, 25)):
+            assert (bytes(proofs[i]), bytes(ys[i])) == tuple(want_p[k]), (direct, i)
+        p1, y1 = ts.compute_kzg_proof(blobs[2], zs[2])      # single call: a batch of one
+        assert (p1, y1) == tuple(want_p[1])
+        ts.free()
