@@ -238,6 +238,10 @@ B200_API RustError b200_selftest_p1_compress(uint8_t *out48, const blst_p1 *p, s
 /* integer-pipe microbenchmark: returns achieved 32x32->64 multiply-adds per second (all SMs) through *imad_per_s
  * and the same for a stream of dependent Fp multiplications through *fpmul_per_s */
 B200_API RustError b200_microbench_int(double *imad_per_s, double *fpmul_per_s);
+/* field multiplications per second of one multiplier variant (dependent chains, all SMs): field 0 = Fp, 1 = Fr;
+ * mode 0 = interleaved CIOS, 5 = Karatsuba product + row-wise reduction.  Variants are selected in the element-wise hooks
+ * above by adding 16 (rolled loop), 32 (radix 2^28), 64 (FP64 product) or 128 (Karatsuba) to op. */
+B200_API RustError b200_microbench_mul(int field, int mode, double *mul_per_s);
 
 /* ---- multi-GPU MSM (BASELINE configs[4]): one process per GPU, terms sharded by rank ----------
  * The reference has no multi-GPU code (its sppark plug uses device 0 only, arkworks3-sppark-wlc/sppark/msm/pippenger.cuh:573-575);

@@ -18,6 +18,10 @@ namespace cc {
 typedef fpc_t fp_t;
 #include "g1_body.inc"
 }  // namespace cc
+namespace ck {  // Karatsuba product + row-wise reduction (mont.cuh MODE 5): fewer wide multiplies, more ALU work
+typedef fpk_t fp_t;
+#include "g1_body.inc"
+}  // namespace ck
 namespace cl {  // multiplier behind a call: small loop bodies for the instruction cache
 typedef Mont<FpParams, MONT_CALL> fp_t;
 #include "g1_body.inc"

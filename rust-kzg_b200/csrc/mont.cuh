@@ -53,8 +53,12 @@ struct Chain<6, CIN> {
     // acc = a * w (no accumulate), no carries can occur
     static __device__ __forceinline__ void mul(uint32_t* acc, const uint32_t* a, uint32_t w) {
 #pragma unroll
-        for (int k = 0; k < 6; k++)
-            asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(acc[2 * k]), "=r"(acc[2 * k + 1]) : "r"(a[2 * k]), "r"(w));
+        for (int k = 0; k < 6; k++) {
+            uint64_t t;                                   // one IMAD.WIDE.U32 instead of IMAD + IMAD.HI
+            asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[2 * k]), "r"(w));
+            acc[2 * k] = (uint32_t)t;
+            acc[2 * k + 1] = (uint32_t)(t >> 32);
+        }
     }
 };
 
@@ -82,10 +86,104 @@ struct Chain<4, CIN> {
     }
     static __device__ __forceinline__ void mul(uint32_t* acc, const uint32_t* a, uint32_t w) {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            asm("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(acc[2 * k]), "=r"(acc[2 * k + 1]) : "r"(a[2 * k]), "r"(w));
+        for (int k = 0; k < 4; k++) {
+            uint64_t t;                                   // one IMAD.WIDE.U32 instead of IMAD + IMAD.HI
+            asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[2 * k]), "r"(w));
+            acc[2 * k] = (uint32_t)t;
+            acc[2 * k + 1] = (uint32_t)(t >> 32);
+        }
     }
 };
+
+template <bool CIN>
+struct Chain<3, CIN> {
+    static __device__ __forceinline__ void mad(uint32_t* acc, const uint32_t* a, uint32_t w) {
+        if (CIN)
+            asm volatile(
+                "madc.lo.cc.u32 %0, %6, %9, %0;  madc.hi.cc.u32 %1, %6, %9, %1;\n\t"
+                "madc.lo.cc.u32 %2, %7, %9, %2;  madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+                "madc.lo.cc.u32 %4, %8, %9, %4;  madc.hi.cc.u32 %5, %8, %9, %5;"
+                : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5])
+                : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(w));
+        else
+            asm volatile(
+                "mad.lo.cc.u32 %0, %6, %9, %0;   madc.hi.cc.u32 %1, %6, %9, %1;\n\t"
+                "madc.lo.cc.u32 %2, %7, %9, %2;  madc.hi.cc.u32 %3, %7, %9, %3;\n\t"
+                "madc.lo.cc.u32 %4, %8, %9, %4;  madc.hi.cc.u32 %5, %8, %9, %5;"
+                : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5])
+                : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(w));
+    }
+    static __device__ __forceinline__ void mul(uint32_t* acc, const uint32_t* a, uint32_t w) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint64_t t;                                   // one IMAD.WIDE.U32 instead of IMAD + IMAD.HI
+            asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[2 * k]), "r"(w));
+            acc[2 * k] = (uint32_t)t;
+            acc[2 * k + 1] = (uint32_t)(t >> 32);
+        }
+    }
+};
+template <bool CIN>
+struct Chain<2, CIN> {
+    static __device__ __forceinline__ void mad(uint32_t* acc, const uint32_t* a, uint32_t w) {
+        if (CIN)
+            asm volatile(
+                "madc.lo.cc.u32 %0, %4, %6, %0;  madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+                "madc.lo.cc.u32 %2, %5, %6, %2;  madc.hi.cc.u32 %3, %5, %6, %3;"
+                : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3])
+                : "r"(a[0]), "r"(a[2]), "r"(w));
+        else
+            asm volatile(
+                "mad.lo.cc.u32 %0, %4, %6, %0;   madc.hi.cc.u32 %1, %4, %6, %1;\n\t"
+                "madc.lo.cc.u32 %2, %5, %6, %2;  madc.hi.cc.u32 %3, %5, %6, %3;"
+                : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3])
+                : "r"(a[0]), "r"(a[2]), "r"(w));
+    }
+    static __device__ __forceinline__ void mul(uint32_t* acc, const uint32_t* a, uint32_t w) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            uint64_t t;                                   // one IMAD.WIDE.U32 instead of IMAD + IMAD.HI
+            asm("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[2 * k]), "r"(w));
+            acc[2 * k] = (uint32_t)t;
+            acc[2 * k + 1] = (uint32_t)(t >> 32);
+        }
+    }
+};
+
+// Plain product of two H-limb numbers (H even), 2H limbs out, with the same staggered E / O carry-chain rows as the
+// Montgomery multiplier below but no reduction: H * H wide multiply-adds.  Row i leaves limb i of the product in E[0].
+template <int H>
+__device__ __forceinline__ void wide_mul(uint32_t* out, const uint32_t* a, const uint32_t* b) {
+    constexpr int HP = H / 2;
+    uint32_t E[H + 2], O[H + 2];
+    Chain<HP, false>::mul(E, a, b[0]);
+    Chain<HP, false>::mul(O, a + 1, b[0]);
+    E[H] = 0;
+    out[0] = E[0];
+#pragma unroll
+    for (int i = 1; i < H; i++) {
+        // T >>= 32:  E' = O (+ stray E[1]),  O'[k] = E[k+2]
+        uint32_t stray = E[1];
+        uint32_t nE[H + 2], nO[H + 2];
+#pragma unroll
+        for (int k = 0; k < H; k++) nE[k] = O[k];
+#pragma unroll
+        for (int k = 0; k < H - 1; k++) nO[k] = E[k + 2];
+        nO[H - 1] = 0;
+#pragma unroll
+        for (int k = 0; k < H; k++) { E[k] = nE[k]; O[k] = nO[k]; }
+        asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[0]) : "r"(stray));
+        Chain<HP, true>::mad(O, a + 1, b[i]);
+        Chain<HP, false>::mad(E, a, b[i]);
+        asm volatile("addc.u32 %0, 0, 0;" : "=r"(E[H]));
+        out[i] = E[0];
+    }
+    // the high half: (E >> 32) + O
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(out[H]) : "r"(O[0]), "r"(E[1]));
+#pragma unroll
+    for (int k = 1; k < H - 1; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(out[H + k]) : "r"(O[k]), "r"(E[k + 1]));
+    asm volatile("addc.u32 %0, %1, %2;" : "=r"(out[2 * H - 1]) : "r"(O[H - 1]), "r"(E[H]));
+}
 
 // ---- field parameters -------------------------------------------------------------------------------------------
 // moduli: zkcrypto/bls12_381/src/fp.rs:71, scalar.rs:77 (cross-checked with arkworks3-sppark-wlc/sppark/ff/bls12-381.hpp:10-39)
@@ -141,7 +239,7 @@ struct FrParams {
 // kept by making the last reduction step 32N - 28(L-1) bits wide (20 for Fp, 4 for Fr); the result is re-packed to
 // 32-bit limbs from that bit offset.  An experiment that did NOT pay off on B200 (IMAD.WIDE costs the same with or
 // without carries, and this form needs 406 of them instead of 302); kept as an independently derived cross-check.
-enum { MONT_UNROLLED = 0, MONT_COMPACT = 1, MONT_R28 = 2, MONT_CALL = 3, MONT_DFMA = 4 };
+enum { MONT_UNROLLED = 0, MONT_COMPACT = 1, MONT_R28 = 2, MONT_CALL = 3, MONT_DFMA = 4, MONT_KARA = 5 };
 template <class P, int MODE = MONT_UNROLLED>
 struct __align__(16) Mont {
     static constexpr bool COMPACT = MODE == MONT_COMPACT;
@@ -244,6 +342,7 @@ struct __align__(16) Mont {
         if (MODE == MONT_R28) return mul_r28(a, b, false);
         if (MODE == MONT_CALL) return mul_call(a, b);
         if (MODE == MONT_DFMA) return mul_dfma(a, b);
+        if (MODE == MONT_KARA) return mul_kara(a, b);
         return mul_unrolled(a, b);
     }
     // ---- MODE 4: the a*b half of the product on the FP64 pipe ---------------------------------------------------
@@ -466,6 +565,102 @@ struct __align__(16) Mont {
         r.final_sub(hi);
         return r;
     }
+    // ---- MODE 5: one level of Karatsuba on the a*b half --------------------------------------------------------------
+    // Every 32x32->64 multiply costs 4 cycles of the FMA-heavy pipe and that pipe is what bounds the MSM
+    // (profiles/r01_multiplier_variants.md), while the ALU pipe idles: so trade multiplies for additions.  The product
+    // a*b is formed from three half-size products, (a0 + a1)(b0 + b1) - a0 b0 - a1 b1 for the middle term: 3 (N/2)^2
+    // wide multiplies instead of N^2, ~6N additions on the ALU pipe; then the 2N-limb product is Montgomery-reduced row by
+    // row with the same staggered carry chains as the interleaved form (N^2 wide multiplies + N low ones, the limbs of the
+    // high half entering one per row).  Fp: 108 + 144 = 252 wide multiplies instead of 288; Fr: 48 + 64 = 112 instead of 128.
+    static __device__ __forceinline__ void redc(Mont& r, const uint32_t* T) {
+        constexpr int H = N / 2;
+        uint32_t E[N + 2], O[N + 2];
+        uint32_t mod_[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) { mod_[i] = P::mod(i); E[i] = T[i]; O[i] = 0; }
+        E[N] = 0;
+#pragma unroll
+        for (int i = 0;; i++) {
+            // the last limb of the product joins before the last row (T < mod^2: it cannot overflow the carry limb)
+            if (i == N - 1) E[N] += T[2 * N - 1];
+            uint32_t m = E[0] * P::INV;
+            if (i == 0) Chain<H, false>::mad(O, mod_ + 1, m);
+            else Chain<H, true>::mad(O, mod_ + 1, m);     // carry-in: the stray word added to E[0] below
+            Chain<H, false>::mad(E, mod_, m);
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(E[N]));
+            if (i == N - 1) break;
+            // S >>= 32:  E' = O (+ stray E[1]),  O'[k] = E[k+2]; then limb N + i of the product enters at limb N - 1
+            uint32_t stray = E[1];
+            uint32_t nE[N + 2], nO[N + 2];
+#pragma unroll
+            for (int k = 0; k < N; k++) nE[k] = O[k];
+#pragma unroll
+            for (int k = 0; k < N - 1; k++) nO[k] = E[k + 2];
+            nO[N - 1] = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) { E[k] = nE[k]; O[k] = nO[k]; }
+            asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, 0, 0;" : "+r"(E[N - 1]), "=r"(E[N]) : "r"(T[N + i]));
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[0]) : "r"(stray));
+        }
+        uint32_t hi;
+        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(O[0]), "r"(E[1]));
+#pragma unroll
+        for (int k = 1; k < N; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.v[k]) : "r"(O[k]), "r"(E[k + 1]));
+        asm volatile("addc.u32 %0, 0, 0;" : "=r"(hi));
+        r.final_sub(hi);
+    }
+    static __device__ __forceinline__ Mont mul_kara(const Mont& a, const Mont& b) {
+        constexpr int H = N / 2;
+        uint32_t P0[N], P2[N], P1[N + 1], sa[H], sb[H], ca, cb;
+        wide_mul<H>(P0, a.v, b.v);
+        wide_mul<H>(P2, a.v + H, b.v + H);
+        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(sa[0]) : "r"(a.v[0]), "r"(a.v[H]));
+#pragma unroll
+        for (int i = 1; i < H; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(sa[i]) : "r"(a.v[i]), "r"(a.v[H + i]));
+        asm volatile("addc.u32 %0, 0, 0;" : "=r"(ca));
+        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(sb[0]) : "r"(b.v[0]), "r"(b.v[H]));
+#pragma unroll
+        for (int i = 1; i < H; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(sb[i]) : "r"(b.v[i]), "r"(b.v[H + i]));
+        asm volatile("addc.u32 %0, 0, 0;" : "=r"(cb));
+        wide_mul<H>(P1, sa, sb);
+        // (ca 2^(32H) + sa)(cb 2^(32H) + sb): the carry bits add sb, sa and 1 one half-width up
+        {
+            const uint32_t ma = 0u - ca, mb = 0u - cb;
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(P1[H]) : "r"(sb[0] & ma));
+#pragma unroll
+            for (int i = 1; i < H; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(P1[H + i]) : "r"(sb[i] & ma));
+            asm volatile("addc.u32 %0, %1, 0;" : "=r"(P1[N]) : "r"(ca & cb));
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(P1[H]) : "r"(sa[0] & mb));
+#pragma unroll
+            for (int i = 1; i < H; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(P1[H + i]) : "r"(sa[i] & mb));
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(P1[N]));
+        }
+        // middle term M = P1 - P0 - P2 (N + 1 limbs, non-negative)
+        asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(P1[0]) : "r"(P0[0]));
+#pragma unroll
+        for (int i = 1; i < N; i++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(P1[i]) : "r"(P0[i]));
+        asm volatile("subc.u32 %0, %0, 0;" : "+r"(P1[N]));
+        asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(P1[0]) : "r"(P2[0]));
+#pragma unroll
+        for (int i = 1; i < N; i++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(P1[i]) : "r"(P2[i]));
+        asm volatile("subc.u32 %0, %0, 0;" : "+r"(P1[N]));
+        // T = P0 + (M << 32H) + (P2 << 32N)
+        uint32_t T[2 * N];
+#pragma unroll
+        for (int i = 0; i < H; i++) T[i] = P0[i];
+        asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(T[H]) : "r"(P0[H]), "r"(P1[0]));
+#pragma unroll
+        for (int i = 1; i < H; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(T[H + i]) : "r"(P0[H + i]), "r"(P1[i]));
+#pragma unroll
+        for (int i = 0; i < H; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(T[N + i]) : "r"(P2[i]), "r"(P1[H + i]));
+        asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(T[N + H]) : "r"(P2[H]), "r"(P1[N]));
+#pragma unroll
+        for (int i = 1; i < H - 1; i++) asm volatile("addc.cc.u32 %0, %1, 0;" : "=r"(T[N + H + i]) : "r"(P2[H + i]));
+        asm volatile("addc.u32 %0, %1, 0;" : "=r"(T[2 * N - 1]) : "r"(P2[N - 1]));
+        Mont r;
+        redc(r, T);
+        return r;
+    }
     static __device__ __forceinline__ Mont mul_unrolled(const Mont& a, const Mont& b) {
         constexpr int H = N / 2;
         uint32_t E[N + 2], O[N + 2];  // E uses N+1 limbs, O uses N; +1 so that the renaming below stays in bounds
@@ -639,6 +834,8 @@ typedef Mont<FpParams, MONT_R28> fp28_t;      // radix-2^28 variant
 typedef Mont<FrParams, MONT_R28> fr28_t;
 typedef fp_t fpu_t;
 typedef fr_t fru_t;
+typedef Mont<FpParams, MONT_KARA> fpk_t;      // Karatsuba a*b + row-wise reduction
+typedef Mont<FrParams, MONT_KARA> frk_t;
 typedef Mont<FpParams, MONT_DFMA> fpd_t;      // a*b on the FP64 pipe, reduction on IMAD.WIDE
 typedef Mont<FrParams, MONT_DFMA> frd_t;
 

@@ -561,6 +561,34 @@ __global__ void __launch_bounds__(kBaThreads, 3) k_accumulate_affine(const uint8
         }
     }
 }
+// variant on the Karatsuba multiplier (B200_ACC_KARA=1; mont.cuh MODE 5): 252 instead of 288 wide multiplies per field
+// multiplication, paid for with ~120 more additions on the otherwise idle ALU pipe
+template <int MINB>
+__global__ void __launch_bounds__(kAccThreads, MINB) k_accumulate_kara(const uint8_t* __restrict__ table, const uint32_t stride,
+                                                                     const uint32_t* __restrict__ entries,
+                                                                     const uint32_t* __restrict__ sorted_tasks,
+                                                                     const uint32_t* __restrict__ n_tasks_ptr,
+                                                                     uint8_t* __restrict__ partials) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *n_tasks_ptr) return;
+    uint32_t start = sorted_tasks[3 * t], len = sorted_tasks[3 * t + 1], slot = sorted_tasks[3 * t + 2];
+    ck::xyzz_t acc = ck::xyzz_t::inf();
+    const uint32_t* e = entries + start;
+    uint32_t v = e[0];
+    ck::affine_t p = ck::load_affine(table + (size_t)(v & 0x7fffffffu) * stride);
+    for (uint32_t k = 0; k < len; k++) {
+        ck::affine_t cur = p;
+        uint32_t cv = v;
+        if (k + 1 < len) {
+            v = e[k + 1];
+            p = ck::load_affine(table + (size_t)(v & 0x7fffffffu) * stride);
+        }
+        cur.y = cur.y.cneg(cv >> 31);
+        ck::xyzz_add_affine(acc, cur);
+    }
+    ck::store_xyzz(partials + (size_t)slot * 192, acc);
+}
+
 // variant with the field multiplication out of line (B200_ACC_CALL=1): same work, ~20x smaller loop body
 __global__ void __launch_bounds__(kAccThreads) k_accumulate_call(const uint8_t* __restrict__ table, const uint32_t stride,
                                                                  const uint32_t* __restrict__ entries,
@@ -1264,7 +1292,11 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
         size_t tasks_bound = std::min(tasks_max_, total * W / L + nkeys + 1);
         static const bool acc_call = getenv("B200_ACC_CALL") && atoi(getenv("B200_ACC_CALL"));
         static const bool acc_prefetch = !getenv("B200_ACC_PREFETCH") || atoi(getenv("B200_ACC_PREFETCH"));  // default on: -2.2% at 2^20
-        if (acc_call)
+        static const int acc_kara = getenv("B200_ACC_KARA") ? atoi(getenv("B200_ACC_KARA")) : 0;
+        if (acc_kara)
+            (acc_kara == 2 ? k_accumulate_kara<2> : k_accumulate_kara<3>)<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>(
+                (const uint8_t*)table_, (uint32_t)stride_, entries_, sorted_tasks_, task_base_ + nkeys, (uint8_t*)partials_);
+        else if (acc_call)
             k_accumulate_call<<<div_up(tasks_bound, kAccThreads), kAccThreads, 0, st>>>((const uint8_t*)table_, (uint32_t)stride_, entries_,
                                                                                        sorted_tasks_, task_base_ + nkeys, (uint8_t*)partials_);
         else {

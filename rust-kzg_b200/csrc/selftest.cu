@@ -72,6 +72,17 @@ __global__ void __launch_bounds__(256) k_imad_bench(uint64_t* sink, uint32_t a, 
         for (int k = 0; k < 12; k++) s ^= A[c][k];
     if (s == 0x1234567) sink[0] = s;
 }
+template <class F>
+__global__ void __launch_bounds__(128) k_mul_bench(uint8_t* sink, int iters) {
+    F x = F::one(), y = F::rr();
+    x.v[0] ^= threadIdx.x;
+    y.v[1] ^= blockIdx.x;
+    for (int it = 0; it < iters; it++) {
+        x = x * y;
+        y = y * x;
+    }
+    if (x.v[0] == 0x12345 && y.v[3] == 7) store_field(sink, x);
+}
 __global__ void __launch_bounds__(128) k_fpmul_bench(uint8_t* sink, int iters) {
     fp_t x = fp_t::one(), y = fp_t::rr();
     x.v[0] ^= threadIdx.x;
@@ -99,7 +110,9 @@ static RustError field_op(int op, void* out, const void* a, const void* b, size_
         DevBuf<uint8_t> da(bytes), db(bytes), dout(bytes);
         B200_CUDA_CHECK(cudaMemcpy(da.p, a, bytes, cudaMemcpyHostToDevice));
         if (b) B200_CUDA_CHECK(cudaMemcpy(db.p, b, bytes, cudaMemcpyHostToDevice));
-        if (op & 64)
+        if (op & 128)
+            k_field_op<Mont<typename F::params_t, MONT_KARA>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);
+        else if (op & 64)
             k_field_op<Mont<typename F::params_t, MONT_DFMA>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);
         else if (op & 32)
             k_field_op<Mont<typename F::params_t, MONT_R28>><<<div_up(n, 128), 128>>>(op & 15, dout.p, da.p, b ? db.p : nullptr, n);
@@ -177,6 +190,39 @@ RustError b200_microbench_int(double* imad_per_s, double* fpmul_per_s) {
         }
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
+    });
+}
+
+/* multiplications per second of a multiplier variant in a dependent-chain loop on all SMs.
+ * field: 0 Fp, 1 Fr; mode: 0 unrolled CIOS (default), 5 Karatsuba a*b + row-wise reduction */
+RustError b200_microbench_mul(int field, int mode, double* mul_per_s) {
+    return guarded([&] {
+        require_device();
+        int dev = 0, sms = 0;
+        B200_CUDA_CHECK(cudaGetDevice(&dev));
+        B200_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        DevBuf<uint8_t> sink(64);
+        cudaEvent_t e0, e1;
+        B200_CUDA_CHECK(cudaEventCreate(&e0));
+        B200_CUDA_CHECK(cudaEventCreate(&e1));
+        const int iters = 200, blocks = sms * 16, threads = 128;
+        auto launch = [&](int it) {
+            if (field == 0 && mode == 5) k_mul_bench<fpk_t><<<blocks, threads>>>(sink.p, it);
+            else if (field == 0) k_mul_bench<fp_t><<<blocks, threads>>>(sink.p, it);
+            else if (mode == 5) k_mul_bench<frk_t><<<blocks, threads>>>(sink.p, it);
+            else k_mul_bench<fr_t><<<blocks, threads>>>(sink.p, it);
+        };
+        launch(5);
+        B200_CUDA_CHECK(cudaEventRecord(e0));
+        launch(iters);
+        B200_CUDA_CHECK(cudaEventRecord(e1));
+        B200_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        B200_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        B200_LAUNCH_CHECK();
+        if (mul_per_s) *mul_per_s = (double)blocks * threads * iters * 2.0 / (ms * 1e-3);
     });
 }
 

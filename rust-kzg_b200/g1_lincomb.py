@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["PreparedMsm", "g1_lincomb", "mult_pippenger", "microbench_int", "g1_sum_device", "msm_plan"]
+__all__ = ["PreparedMsm", "g1_lincomb", "mult_pippenger", "microbench_int", "microbench_mul", "g1_sum_device", "msm_plan"]
 
 
 def _L():
@@ -141,6 +141,13 @@ def g1_lincomb(affine_points, scalars, length=None, precomputation: PreparedMsm 
 def g1_sum_device(out_ptr, points_ptr, n, stream=0):
     """sum of n Jacobian points resident on the device (multi-GPU combine step)"""
     _lib.check(_L().b200_g1_sum_device(C.c_void_p(out_ptr), C.c_void_p(points_ptr), n, C.c_void_p(stream)))
+
+
+def microbench_mul(field=0, mode=0):
+    """field multiplications per second of a multiplier variant (0 = Fp / 1 = Fr; mode 0 = CIOS, 5 = Karatsuba)"""
+    a = C.c_double()
+    _lib.check(_L().b200_microbench_mul(field, mode, C.byref(a)))
+    return a.value
 
 
 def microbench_int():
