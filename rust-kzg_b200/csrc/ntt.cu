@@ -28,7 +28,8 @@ struct NttPass {
     size_t tw_unit;         // 0: none; else outputs (q, col) are multiplied by w_N^(q*col), w_N = roots[tw_unit]
     size_t twist_unit;      // 0: none; else input element with natural index j is multiplied by roots[j*twist_unit]
     const uint8_t* scale;   // nullptr or one Fr multiplied into every output (n^-1)
-    size_t batch_stride;    // elements between consecutive transforms of the batch
+    size_t batch_stride;      // elements between consecutive transforms of the batch (input)
+    size_t out_batch_stride;  // ... and in the output (differs when the transforms are the rows of a larger one)
 };
 
 __device__ __forceinline__ fr_t root_at(const NttPass& p, size_t e_units) {
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kNttThreads, MINB) k_ntt_pass(NttPass p) {
     for (int k = threadIdx.x; k < (m >> 1); k += blockDim.x) store_field(tw + (size_t)k * 32, root_at(p, (size_t)k * p.unit_m));
     const size_t col0 = (size_t)blockIdx.x * p.G;
     const uint8_t* in = p.in + (size_t)blockIdx.y * p.batch_stride * 32;
-    uint8_t* out = p.out + (size_t)blockIdx.y * p.batch_stride * 32;
+    uint8_t* out = p.out + (size_t)blockIdx.y * p.out_batch_stride * 32;
 
     // load (optionally twisted), bit-reversed row index into shared memory
     for (int e = threadIdx.x; e < tile; e += blockDim.x) {
@@ -211,6 +212,7 @@ FFTSettingsDev::~FFTSettingsDev() {
     cudaFree(brp_roots_);
     cudaFree(scratch_);
     cudaFree(scratch2_);
+    cudaFree(scratch3_);
     cudaFree(g1_work_);
 }
 
@@ -248,36 +250,37 @@ static void launch_pass(const NttPass& p, int batch, cudaStream_t st) {
     B200_LAUNCH_CHECK();
 }
 
-void FFTSettingsDev::run_passes(const void* in, void* out, size_t n, bool inverse, int batch, bool scale,
-                                size_t twist_unit, cudaStream_t st) {
-    int k = 0;
-    while (((size_t)1 << k) < n) k++;
-    const uint8_t* inv_n = (const uint8_t*)roots_ + (max_width_ + 1) * 32 + 33 * 32;
+// batch transforms of 2^k <= 2^22 points: one CTA per transform, or two passes (see ntt.cuh).  in_bstride / out_bstride:
+// elements between consecutive transforms; output element i of a transform goes to out[i * out_mul] (out_mul > 1 when the
+// transforms are the rows of a three-pass transform and their outputs interleave); tmp: batch * 2^k elements of scratch.
+void FFTSettingsDev::transform(const void* in, void* out, int k, bool inverse, int batch, const uint8_t* scale_ptr, size_t twist_unit,
+                               size_t in_bstride, size_t out_bstride, size_t out_mul, void* tmp, cudaStream_t st) {
+    const size_t n = (size_t)1 << k;
     NttPass p{};
     p.roots = (const uint8_t*)roots_;
     p.nmax = max_width_;
     p.inverse = inverse;
-    p.batch_stride = n;
+    p.batch_stride = in_bstride;
+    p.out_batch_stride = out_bstride;
     // one CTA per transform when there are many of them (or they are tiny); a lone mid-size transform is split into two
     // passes so that it spreads over several SMs (2^11 points: 50 -> ~25 us)
     if (k <= kMaxLogM && (k <= 8 || batch >= 16)) {
         p.in = (const uint8_t*)in; p.out = (uint8_t*)out;
         p.log_m = k; p.G = 1; p.ncols = 1;
-        p.in_cstride = 0; p.in_rstride = 1; p.out_cstride = 0; p.out_rstride = 1;
+        p.in_cstride = 0; p.in_rstride = 1; p.out_cstride = 0; p.out_rstride = out_mul;
         p.in_col_fast = 0; p.out_col_fast = 0;
         p.unit_m = max_width_ >> k;
         p.tw_unit = 0; p.twist_unit = twist_unit;
-        p.scale = scale ? inv_n + k * 32 : nullptr;
+        p.scale = scale_ptr;
         launch_pass(p, batch, st);
         launches_ += 1;
         return;
     }
-    if (k > 2 * kMaxLogM) throw CudaError(1, "fft_fr: sizes above 2^22 are not supported by this build");
     int k2 = (k + 1) / 2, k1 = k - k2;  // n2 = 2^k2 (pass 1, strided columns), n1 = 2^k1 (pass 2, contiguous rows)
     size_t n1 = (size_t)1 << k1, n2 = (size_t)1 << k2;
-    ensure_scratch((size_t)batch * n);
     // pass 1: for every column j1 < n1, transform the n2 points x[j1 + n1*j2]; times w_n^(i2*j1); in-place layout
-    p.in = (const uint8_t*)in; p.out = (uint8_t*)scratch_;
+    p.in = (const uint8_t*)in; p.out = (uint8_t*)tmp;
+    p.out_batch_stride = n;
     p.log_m = k2; p.G = std::max(1, tile_elems(n) >> k2); p.ncols = n1;
     p.in_cstride = 1; p.in_rstride = n1; p.out_cstride = 1; p.out_rstride = n1;
     p.in_col_fast = 1; p.out_col_fast = 1;
@@ -286,15 +289,63 @@ void FFTSettingsDev::run_passes(const void* in, void* out, size_t n, bool invers
     p.scale = nullptr;
     launch_pass(p, batch, st);
     // pass 2: for every i2 < n2, transform the n1 contiguous points y[n1*i2 + j1]; X[i2 + n2*i1]
-    p.in = (const uint8_t*)scratch_; p.out = (uint8_t*)out;
+    p.in = (const uint8_t*)tmp; p.out = (uint8_t*)out;
+    p.batch_stride = n;
+    p.out_batch_stride = out_bstride;
     p.log_m = k1; p.G = std::max(1, tile_elems(n) >> k1); p.ncols = n2;
-    p.in_cstride = n1; p.in_rstride = 1; p.out_cstride = 1; p.out_rstride = n2;
+    p.in_cstride = n1; p.in_rstride = 1; p.out_cstride = out_mul; p.out_rstride = n2 * out_mul;
     p.in_col_fast = 0; p.out_col_fast = 1;
     p.unit_m = max_width_ >> k1;
     p.tw_unit = 0; p.twist_unit = 0;
-    p.scale = scale ? inv_n + k * 32 : nullptr;
+    p.scale = scale_ptr;
     launch_pass(p, batch, st);
     launches_ += 2;
+}
+
+void FFTSettingsDev::run_passes(const void* in, void* out, size_t n, bool inverse, int batch, bool scale,
+                                size_t twist_unit, cudaStream_t st) {
+    int k = 0;
+    while (((size_t)1 << k) < n) k++;
+    const uint8_t* inv_n = (const uint8_t*)roots_ + (max_width_ + 1) * 32 + 33 * 32;
+    const uint8_t* scale_ptr = scale ? inv_n + k * 32 : nullptr;
+    if (k <= 2 * kMaxLogM) {
+        if (k > kMaxLogM || !(k <= 8 || batch >= 16)) ensure_scratch((size_t)batch * n);
+        transform(in, out, k, inverse, batch, scale_ptr, twist_unit, n, n, 1, scratch_, st);
+        return;
+    }
+    // Above 2^22 points (the reference accepts scales up to 31, blst/src/types/fft_settings.rs:28-58): one more level of
+    // the same decomposition, n = n1 * 2^11.  Pass A transforms the n1 strided columns of 2^11 points and applies the
+    // twiddle w_n^(i2 j1); the 2^11 rows of n1 <= 2^20 contiguous points are then ordinary (two-pass) transforms whose
+    // outputs interleave: X[i2 + 2^11 i1].  Three full sweeps over the data instead of two.
+    const int kc = kMaxLogM, kr = k - kc;
+    const size_t nc = (size_t)1 << kc, nr = (size_t)1 << kr;
+    ensure_scratch((size_t)batch * n);
+    if (scratch3_elems_ < n) {
+        cudaFree(scratch3_);
+        scratch3_ = nullptr; scratch3_elems_ = 0;
+        scratch3_ = dev_alloc<uint8_t>(n * 32);
+        scratch3_elems_ = n;
+    }
+    for (int b = 0; b < batch; b++) {
+        const uint8_t* src = (const uint8_t*)in + (size_t)b * n * 32;
+        uint8_t* dst = (uint8_t*)out + (size_t)b * n * 32;
+        NttPass p{};
+        p.roots = (const uint8_t*)roots_;
+        p.nmax = max_width_;
+        p.inverse = inverse;
+        p.batch_stride = n; p.out_batch_stride = n;
+        p.in = src; p.out = (uint8_t*)scratch3_;
+        p.log_m = kc; p.G = std::max(1, tile_elems(n) >> kc); p.ncols = nr;
+        p.in_cstride = 1; p.in_rstride = nr; p.out_cstride = 1; p.out_rstride = nr;
+        p.in_col_fast = 1; p.out_col_fast = 1;
+        p.unit_m = max_width_ >> kc;
+        p.tw_unit = max_width_ >> k; p.twist_unit = twist_unit;
+        p.scale = nullptr;
+        launch_pass(p, 1, st);
+        launches_ += 1;
+        // rows: 2^11 transforms of nr points, input row i2 at scratch3 + i2 * nr, output element i1 at dst[i2 + 2^11 * i1]
+        transform(scratch3_, dst, kr, inverse, (int)nc, scale_ptr, 0, nr, 1, nc, scratch_, st);
+    }
 }
 
 void FFTSettingsDev::fft_fr(const void* in_dev, void* out_dev, size_t n, bool inverse, int batch, cudaStream_t st) {

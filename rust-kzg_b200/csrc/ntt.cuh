@@ -3,8 +3,8 @@
 // Contract (blst/src/fft_fr.rs:112-165): natural-order input, natural-order output,
 //   out[i] = sum_j data[j] * w^(i*j),  w = roots_of_unity[max_width / n]  (inverse: w^-1 and a final * n^-1),
 // for any power-of-two n <= max_width.  Field elements are canonical Montgomery residues, so any algorithm that
-// computes these sums is bit-exact; the device uses a two-pass decomposition n = n1 * n2 with every sub-transform
-// (<= 2^11 points) done in shared memory by one CTA:
+// computes these sums is bit-exact; the device uses a two-pass decomposition n = n1 * n2 (three passes above 2^22 points)
+// with every sub-transform (<= 2^11 points) done in shared memory by one CTA:
 //   pass 1  n1 column transforms of size n2 over the stride-n1 sub-sequences, times the twiddle w^(i2*j1)
 //   pass 2  n2 row transforms of size n1 (contiguous rows), written transposed to natural order
 // Algorithmic HBM traffic: 64 B/element/pass (32 B read + 32 B write); two passes above 2^11 points.
@@ -45,6 +45,8 @@ private:
     void ensure_scratch(size_t elems);
     void run_passes(const void* in, void* out, size_t n, bool inverse, int batch, bool scale, size_t twist_unit,
                     cudaStream_t st);
+    void transform(const void* in, void* out, int k, bool inverse, int batch, const uint8_t* scale_ptr, size_t twist_unit,
+                   size_t in_bstride, size_t out_bstride, size_t out_mul, void* tmp, cudaStream_t st);
     int scale_;
     size_t max_width_;
     void* roots_ = nullptr;
@@ -52,6 +54,8 @@ private:
     void* scratch_ = nullptr;
     void* scratch2_ = nullptr;
     size_t scratch_elems_ = 0;
+    void* scratch3_ = nullptr;       // transforms above 2^22 points: output of the extra column pass
+    size_t scratch3_elems_ = 0;
     void* g1_work_ = nullptr;
     size_t g1_work_elems_ = 0;
     int launches_ = 0;

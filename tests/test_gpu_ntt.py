@@ -170,3 +170,17 @@ def test_fft_g1_roundtrip_2p15(B, K, oracle_settings):
         want = K.msm_affine(aff, np.ascontiguousarray(roots[idx]), nthreads=8)
         assert K.p1_compress(fwd[k]) == K.p1_compress(want), k
     fs.close()
+
+
+def test_fft_fr_above_2p22_three_passes(B, K):
+    """the reference accepts scales up to 31 (blst/src/types/fft_settings.rs:28-58); above 2^22 points the device adds a third
+    pass (csrc/ntt.cu).  2^23: forward vs the oracle, inverse(forward(x)) == x, and the DAS extension's zero upper half."""
+    n = 1 << 23
+    fs, ofs = B.FFTSettings(23), K.FFTSettings(23)
+    rng = np.random.default_rng(23)
+    data = rand_fr_mont(rng, n)
+    fwd = fs.fft_fr(data, False)
+    assert np.array_equal(fwd, ofs.fft_fr(data, False, nthreads=8))
+    assert np.array_equal(fs.fft_fr(fwd, True), data)
+    del ofs
+    fs.close()
