@@ -147,11 +147,11 @@ void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_
 // flight, one warp tree; a second kernel folds the 4096 / P partial sums of every vector.  No sort, no buckets: two
 // launches, chain length P + 2 trees.  table: 4096 x 32 x 128 affine points (1.5 GiB, built once per settings object).
 template <class AR>
-__global__ void __launch_bounds__(64) k_direct_msm_partial(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
-                                                           uint8_t* __restrict__ partials, int npts, int P, size_t nwarps) {
-    const int lane = threadIdx.x & 31;
-    const size_t w = (size_t)blockIdx.x * 2 + (threadIdx.x >> 5);
-    if (w >= nwarps) return;                                  // whole warps leave together
+__global__ void __launch_bounds__(128) k_direct_msm_partial(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
+                                                            uint8_t* __restrict__ partials, int npts, int P, size_t nwarps) {
+    __shared__ __align__(16) uint8_t sh[4 * 192];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t w = (size_t)blockIdx.x * 4 + wid;             // nwarps is a multiple of 4: whole CTAs are live
     const size_t per_vec = (size_t)npts / P, v = w / per_vec, p0 = (w % per_vec) * P;
     const uint32_t* sc = reinterpret_cast<const uint32_t*>(scalars + (v * npts + p0) * 32);
     auto digit = [&](int i) -> int {                          // Booth digit of window `lane` of scalar i (see k_fk_direct_lincomb)
@@ -182,15 +182,22 @@ __global__ void __launch_bounds__(64) k_direct_msm_partial(const uint8_t* __rest
     xyzz_t a2;
 #pragma unroll
     for (int k = 0; k < 12; k++) { a2.x.v[k] = acc.x.v[k]; a2.y.v[k] = acc.y.v[k]; a2.zzz.v[k] = acc.zzz.v[k]; a2.zz.v[k] = acc.zz.v[k]; }
+    // warp tree, then the CTA's four warp sums on four quads of warp 0: one partial per CTA (4 P points)
     fp_t q = seg_sum_quad(a2, 32);
-    if (lane < 4) store_field(partials + w * 192 + quad_store_offset(), q);
+    if (lane < 4) store_field(sh + wid * 192 + quad_store_offset(), q);
+    __syncthreads();
+    if (wid == 0) {
+        fp_t c = lane < 16 ? load_field<fp_t>(sh + (lane >> 2) * 192 + quad_store_offset()) : fp_t::zero();
+        fp_t t = quad_tree(c, 16);
+        if (lane < 4) store_field(partials + (size_t)blockIdx.x * 192 + quad_store_offset(), t);
+    }
 }
-// one CTA of min(m, 256) threads per vector: m = 4096 / P partial sums (64 <= m <= 512, a power of two) -> Jacobian result
+// one CTA of 32 .. 256 threads per vector: m = 4096 / (4 P) partial sums (16 <= m <= 128, a power of two) -> Jacobian result
 __global__ void __launch_bounds__(256) k_direct_msm_reduce(const uint8_t* __restrict__ partials, int m, uint8_t* __restrict__ out_jac) {
     __shared__ __align__(16) uint8_t sh[8 * 192];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const uint8_t* base = partials + (size_t)blockIdx.x * m * 192;
-    xyzz_t a = load_xyzz(base + (size_t)threadIdx.x * 192);
+    xyzz_t a = (int)threadIdx.x < m ? load_xyzz(base + (size_t)threadIdx.x * 192) : xyzz_t::inf();
     for (int i = threadIdx.x + blockDim.x; i < m; i += blockDim.x) {
         xyzz_t b = load_xyzz(base + (size_t)i * 192);
         xyzz_add(a, b);
@@ -206,15 +213,17 @@ __global__ void __launch_bounds__(256) k_direct_msm_reduce(const uint8_t* __rest
         if (lane == 2) store_field(out_jac + (size_t)blockIdx.x * 144 + 96, t);
     }
 }
-// scalars: nvec x npts canonical little-endian 32-byte scalars; partials: workspace of nvec * (npts / P) XYZZ points
+// scalars: nvec x npts canonical little-endian 32-byte scalars; partials: workspace of nvec * npts / 32 XYZZ points
 void launch_direct_msm(const void* scalars, const void* table, void* partials, void* out_jac, int nvec, int npts, cudaStream_t st) {
-    // P points per warp: as few as keep one wave of warps on the machine (148 SMs x 12 warps), between 8 and 64
+    // P points per warp: as few as keep one wave of warps on the machine (148 SMs x 12 warps), between 8 and 64;
+    // four warps per CTA leave one partial sum per 4 P points
     int P = 8;
     while (P < 64 && (size_t)nvec * npts / P > 148 * 12) P <<= 1;
     const size_t nwarps = (size_t)nvec * npts / P;
-    k_direct_msm_partial<ArCall><<<(unsigned)((nwarps + 1) / 2), 64, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)partials,
-                                                                           npts, P, nwarps);
-    k_direct_msm_reduce<<<nvec, std::min(npts / P, 256), 0, st>>>((const uint8_t*)partials, npts / P, (uint8_t*)out_jac);
+    const int m = npts / (4 * P);                              // partial sums per vector: 128 .. 16
+    k_direct_msm_partial<ArCall><<<(unsigned)(nwarps / 4), 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)partials,
+                                                                      npts, P, nwarps);
+    k_direct_msm_reduce<<<nvec, std::max(32, std::min(m, 256)), 0, st>>>((const uint8_t*)partials, m, (uint8_t*)out_jac);
     B200_LAUNCH_CHECK();
 }
 
