@@ -34,7 +34,7 @@ constexpr size_t kG1 = 4096, kG2 = 65;
 // one staging lane: stream, device buffers for a chunk of up to max_batch blobs, pinned host buffers for the results
 struct Stage {
     cudaStream_t stream = nullptr, side = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_side = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_side = nullptr, ev_dec = nullptr;
     // end of the last enqueue a device-pointer entry point left on a CALLER's stream: whoever uses this lane's
     // workspace next makes its stream wait on it first (the workspace is shared, the streams are not)
     cudaEvent_t ev_busy = nullptr;
@@ -49,6 +49,7 @@ struct Stage {
         B200_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
         B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_dec, cudaEventDisableTiming));
         B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_busy, cudaEventDisableTiming));
         d_blobs = dev_alloc<uint8_t>((size_t)mb * kBytesPerBlob);
         d_z = dev_alloc<uint8_t>((size_t)mb * 32);
@@ -64,6 +65,7 @@ struct Stage {
         if (h_small) cudaFreeHost(h_small);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_side) cudaEventDestroy(ev_side);
+        if (ev_dec) cudaEventDestroy(ev_dec);
         if (ev_busy) cudaEventDestroy(ev_busy);
         if (stream) cudaStreamDestroy(stream);
         if (side) cudaStreamDestroy(side);
@@ -817,7 +819,8 @@ static void verify_stage_points(KzgCtx& ctx, const uint8_t* c48, const uint8_t* 
     memcpy(h + L.o_p, p48, 48 * n);
     B200_CUDA_CHECK(cudaMemcpyAsync(d, h, 96 * n, cudaMemcpyHostToDevice, g.side));
     B200_CUDA_CHECK(cudaMemsetAsync(d + L.o_st, 0, n * sizeof(int) + sizeof(int), g.side));
-    ctx.dev->verify_decode(d, d + L.o_p, (int)n, reinterpret_cast<int*>(d + L.o_st), g.side);
+    // ev_dec: coordinates decoded (all the lincombs and the pairing need); ev_side: subgroup tests done too (the status)
+    ctx.dev->verify_decode(d, d + L.o_p, (int)n, reinterpret_cast<int*>(d + L.o_st), g.side, g.ev_dec);
     B200_CUDA_CHECK(cudaEventRecord(g.ev_side, g.side));
 }
 static C_KZG_RET verify_finish(KzgCtx& ctx, bool* ok, const uint8_t* c48, const uint8_t* z32, const uint8_t* y32, const uint8_t* p48, size_t n) {
@@ -827,10 +830,13 @@ static C_KZG_RET verify_finish(KzgCtx& ctx, bool* ok, const uint8_t* c48, const 
     memcpy(h + L.o_y, y32, 32 * n);
     if (n > 1) batch_challenge_hash(h + L.o_r, c48, z32, y32, p48, n); else memset(h + L.o_r, 0, 32);
     cudaStream_t st = ctx.stream;
-    B200_CUDA_CHECK(cudaStreamWaitEvent(st, ctx.stage[0].ev_side, 0));
+    // the lincombs and the pairing need the decoded coordinates only; the subgroup tests of the same points keep running on
+    // the side stream beside them (they only ever set status flags) and are joined before the status is read
+    B200_CUDA_CHECK(cudaStreamWaitEvent(st, ctx.stage[0].ev_dec, 0));
     B200_CUDA_CHECK(cudaMemcpyAsync(d + L.o_z, h + L.o_z, 64 * n + 32, cudaMemcpyHostToDevice, st));
     ctx.dev->verify_batch(d, d + L.o_p, d + L.o_z, d + L.o_y, 0, d + L.o_r, (int)n, reinterpret_cast<int*>(d + L.o_st),
                           reinterpret_cast<int*>(d + L.o_res), st, /*skip_decode=*/true);
+    B200_CUDA_CHECK(cudaStreamWaitEvent(st, ctx.stage[0].ev_side, 0));
     B200_CUDA_CHECK(cudaMemcpyAsync(h + L.o_st, d + L.o_st, n * sizeof(int) + sizeof(int), cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
     if (any_set(reinterpret_cast<int*>(h + L.o_st), (int)n)) return C_KZG_BADARGS;

@@ -643,37 +643,44 @@ __device__ __forceinline__ bool uncompress_point_u(const uint8_t* in, affine_t& 
     out.y = y;
     return true;
 }
+// mode 0: decode + subgroup test; 1: decode only (status for malformed / off-curve input); 2: subgroup test only, on the
+// affine points a mode-1 launch left in `out` (so that the test can run beside the caller's critical path)
 __global__ void __launch_bounds__(32) k_decode_g1_checked(const uint8_t* __restrict__ in, int n, uint8_t* __restrict__ out,
-                                                          int* __restrict__ status, int status_mod) {
-    const int q = blockIdx.x * 8 + (threadIdx.x >> 2), role = threadIdx.x & 3, base = threadIdx.x & ~3;
+                                                          int* __restrict__ status, int status_mod, int mode) {
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 2), role = threadIdx.x & 3;
     const bool live = q < n;
     const int i = live ? q : 0;
     affine_t a;
-    bool ok = uncompress_point_u(in + (size_t)i * 48, a);
+    bool ok = true;
+    if (mode == 2) a = load_affine(out + (size_t)i * 96);
+    else ok = uncompress_point_u(in + (size_t)i * 48, a);
     const bool inf = a.is_inf();
-    fp_t comp = role == 0 ? a.x : role == 1 ? a.y : fp_t::one();
-    if (inf) comp = fp_t::zero();
-    fp_t t = quad_mul_by_abs_z(comp);                      // |z| P
-    const bool t_inf = __shfl_sync(kFullMask, (int)t.is_zero(), base | 2);
-    fp_t u = quad_mul_by_abs_z(t);                         // z^2 P
-    xyzz_t U = quad_gather(u);                             // valid on the quad's first lane
+    bool in_g1 = true;
+    if (mode != 1) {
+        fp_t comp = role == 0 ? a.x : role == 1 ? a.y : fp_t::one();
+        if (inf) comp = fp_t::zero();
+        in_g1 = quad_in_subgroup(a, comp);                  // every lane of the warp takes part
+    }
     if (role == 0 && live) {
-        if (ok && !inf) {
-            fp_t beta;
-            const uint32_t Bm[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
-                                     0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
-#pragma unroll
-            for (int k = 0; k < 12; k++) beta.v[k] = Bm[k];
-            // (beta x, y) == -(X/ZZ, Y/ZZZ)  <=>  beta x ZZ == X  and  y ZZZ == -Y
-            ok = !t_inf && !U.is_inf() && (beta * a.x * U.zz == U.x) && (a.y * U.zzz == U.y.neg());
-        }
+        if (ok && !inf) ok = in_g1;
         if (!ok) status[i % status_mod] = 1;
-        if (out) store_affine(out + (size_t)i * 96, a);
+        if (out && mode != 2) store_affine(out + (size_t)i * 96, a);
     }
 }
 void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st, int status_mod) {
     if (n < 1) return;
-    k_decode_g1_checked<<<div_up(n, 8), 32, 0, st>>>(in48_dev, n, (uint8_t*)affine_out_dev, status_dev, status_mod > 0 ? status_mod : n);
+    k_decode_g1_checked<<<div_up(n, 8), 32, 0, st>>>(in48_dev, n, (uint8_t*)affine_out_dev, status_dev, status_mod > 0 ? status_mod : n, 0);
+    B200_LAUNCH_CHECK();
+}
+// the two halves of launch_decode_g1_checked as separate launches: decode (affine_out_dev required), then the subgroup test
+void launch_decode_g1_unchecked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st, int status_mod) {
+    if (n < 1) return;
+    k_decode_g1_checked<<<div_up(n, 8), 32, 0, st>>>(in48_dev, n, (uint8_t*)affine_out_dev, status_dev, status_mod > 0 ? status_mod : n, 1);
+    B200_LAUNCH_CHECK();
+}
+void launch_subgroup_g1(const void* affine_dev, int* status_dev, int n, cudaStream_t st, int status_mod) {
+    if (n < 1) return;
+    k_decode_g1_checked<<<div_up(n, 8), 32, 0, st>>>(nullptr, n, (uint8_t*)const_cast<void*>(affine_dev), status_dev, status_mod > 0 ? status_mod : n, 2);
     B200_LAUNCH_CHECK();
 }
 void launch_affine_to_jac(const void* affine_dev, void* jac_dev, int n, cudaStream_t st) {

@@ -75,7 +75,11 @@ public:
     void verify_batch(const uint8_t* commitments48, const uint8_t* proofs48, const uint8_t* z32, const uint8_t* y32,
                       int z_reduce, const uint8_t* r32, int n, int* status, int* result, cudaStream_t st, bool skip_decode = false);
     // the point-decoding stage of verify_batch on its own (then call verify_batch(..., skip_decode = true) with the same n)
-    void verify_decode(const uint8_t* commitments48, const uint8_t* proofs48, int n, int* status, cudaStream_t st);
+    // decoded: when given, the subgroup test is a second launch and `decoded` is recorded between the two -- a caller
+    // whose critical path only needs the coordinates (the lincombs and the pairing) waits on `decoded` and joins the stream
+    // before it reads the status
+    void verify_decode(const uint8_t* commitments48, const uint8_t* proofs48, int n, int* status, cudaStream_t st,
+                       cudaEvent_t decoded = nullptr);
     // ---- EIP-7594 recovery and cell verification (das7594.cu; kzg/src/das.rs:101-207, 294-388) -------------------
     // recover_cells_and_kzg_proofs for one extended blob.  cells: n x 2048 wire bytes (device); cell_idx: their cell
     // indices (host, already validated: n in [64, 128], < 128, strictly ascending).  cells_out: 128 x 2048 bytes,
@@ -152,6 +156,9 @@ void launch_uncompress_g1(const uint8_t* in48_dev, void* affine_out_dev, int* fl
 // uncompress + subgroup check (G1::from_bytes followed by is_inf() || is_valid()); status[i] = 1 on failure
 // (status index = i % status_mod, status_mod = 0 -> n; affine_out_dev may be nullptr)
 void launch_decode_g1_checked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st, int status_mod = 0);
+// ... the same in two launches: decode only (malformed / off-curve -> status), then the subgroup test on the decoded points
+void launch_decode_g1_unchecked(const uint8_t* in48_dev, void* affine_out_dev, int* status_dev, int n, cudaStream_t st, int status_mod = 0);
+void launch_subgroup_g1(const void* affine_dev, int* status_dev, int n, cudaStream_t st, int status_mod = 0);
 // blst_p1_from_affine for n points
 void launch_affine_to_jac(const void* affine_dev, void* jac_dev, int n, cudaStream_t st);
 // Fr::from_bytes (reduce = 0: status[i] = 1 when >= r) / hash_to_bls_field (reduce = 1) -> Montgomery; and back

@@ -277,16 +277,30 @@ void KzgSettingsDev::lincomb2_and_pair(const uint8_t* pts, const uint8_t* scalar
 
 // decode + subgroup-check the 2n points into the workspace (may run early, on another stream, while z / y are still
 // being produced); one launch when the two arrays are contiguous
-void KzgSettingsDev::verify_decode(const uint8_t* commitments48, const uint8_t* proofs48, int n, int* status, cudaStream_t st) {
+void KzgSettingsDev::verify_decode(const uint8_t* commitments48, const uint8_t* proofs48, int n, int* status, cudaStream_t st,
+                                   cudaEvent_t decoded) {
     ensure_verify_ws(n);
     uint8_t* comm_aff = (uint8_t*)vf_buf_;
     uint8_t* proof_aff = comm_aff + (size_t)n * 96;
-    if (proofs48 == commitments48 + (size_t)n * 48) {
-        launch_decode_g1_checked(commitments48, comm_aff, status, 2 * n, st, n);
-    } else {
-        launch_decode_g1_checked(commitments48, comm_aff, status, n, st);
-        launch_decode_g1_checked(proofs48, proof_aff, status, n, st);
+    const bool contiguous = proofs48 == commitments48 + (size_t)n * 48;
+    if (!decoded) {
+        if (contiguous) {
+            launch_decode_g1_checked(commitments48, comm_aff, status, 2 * n, st, n);
+        } else {
+            launch_decode_g1_checked(commitments48, comm_aff, status, n, st);
+            launch_decode_g1_checked(proofs48, proof_aff, status, n, st);
+        }
+        return;
     }
+    // coordinates first (a square-root chain per point), the subgroup ladders after the event
+    if (contiguous) {
+        launch_decode_g1_unchecked(commitments48, comm_aff, status, 2 * n, st, n);
+    } else {
+        launch_decode_g1_unchecked(commitments48, comm_aff, status, n, st);
+        launch_decode_g1_unchecked(proofs48, proof_aff, status, n, st);
+    }
+    B200_CUDA_CHECK(cudaEventRecord(decoded, st));
+    launch_subgroup_g1(comm_aff, status, 2 * n, st, n);      // comm_aff and proof_aff are adjacent in the workspace
 }
 
 void KzgSettingsDev::verify_batch(const uint8_t* commitments48, const uint8_t* proofs48, const uint8_t* z32, const uint8_t* y32,
