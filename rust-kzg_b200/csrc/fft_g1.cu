@@ -4,6 +4,8 @@
 // same with blst_p1_mult), so the transform is (n/2) log n scalar multiplications, one lane quad each, stage by stage
 // with the working set kept in XYZZ form in HBM (192 B per point).  Same group elements as the reference, hence
 // byte-identical after compression.
+#include <cstdlib>
+
 #include "g1.cuh"
 #include "g1_quad.cuh"
 #include "ntt.cuh"
@@ -51,6 +53,60 @@ __global__ void __launch_bounds__(32) k_g1_stage(uint8_t* __restrict__ work, siz
         store_field(w + (i + half) * 192 + off, dif);
     }
 }
+// Two DIT stages (s, s+1) at the latency of one.  The transform is a chain of log n dependent scalar multiplications
+// (~0.8 ms each on a lane quad) with far fewer butterflies than the machine has lanes, so the chain, not the work, is the
+// cost.  For the four points x0..x3 at j, j + h, j + 2h, j + 3h (h = 2^s) the two stages give
+//     z0 = x0 + a x1 + b x2 + ab x3      z1 = x0 - a x1 + b' x2 - ab' x3
+//     z2 = x0 + a x1 - b x2 - ab x3      z3 = x0 - a x1 - b' x2 + ab' x3
+// with a = w_2h^low, b = w_4h^low, b' = w_4h^(low + h): FIVE independent products [a]x1, [b]x2, [ab]x3, [b']x2, [ab']x3 by
+// roots of unity (one more than the two stages do, but all at the same depth), then eight additions.
+// k_g1_stage2_mul: one lane quad per product; k_g1_stage2_comb: one lane quad per group of four points.
+__global__ void __launch_bounds__(32) k_g1_stage2_mul(const uint8_t* __restrict__ work, uint8_t* __restrict__ tmp, size_t n, int log_n, int s,
+                                                      const uint8_t* __restrict__ roots, size_t nmax, int inverse) {
+    __shared__ __align__(16) uint8_t table[kQuadTableBytes];
+    const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t nprod = 5 * (n >> 2);
+    const bool live = q < nprod;
+    const size_t qq = live ? q : 0;
+    const size_t g = qq / 5;
+    const int which = (int)(qq - g * 5);
+    const size_t h = (size_t)1 << s, low = g & (h - 1), j = ((g >> s) << (s + 2)) | low;
+    // exponents in units of the n-th root
+    const size_t ea = low << (log_n - 1 - s), eb = low << (log_n - 2 - s), ebp = eb + (n >> 2);
+    const size_t src = which == 0 ? j + h : (which == 1 || which == 3) ? j + 2 * h : j + 3 * h;
+    size_t e = which == 0 ? ea : which == 1 ? eb : which == 2 ? ea + eb : which == 3 ? ebp : ea + ebp;
+    e &= n - 1;
+    const uint8_t* w = work + (size_t)blockIdx.y * n * 192;
+    const int off = quad_store_offset();
+    fp_t t = load_field<fp_t>(w + src * 192 + off);
+    const size_t eu = e * (nmax >> log_n);
+    fr_t root = load_field_ro<fr_t>(roots + (inverse && eu ? nmax - eu : eu) * 32).from_mont();
+    t = quad_mul_scalar(t, root.v, table);
+    if (live) store_field(tmp + ((size_t)blockIdx.y * nprod + q) * 192 + off, t);
+}
+__global__ void __launch_bounds__(32) k_g1_stage2_comb(uint8_t* __restrict__ work, const uint8_t* __restrict__ tmp, size_t n, int s) {
+    const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool live = q < (n >> 2);
+    const size_t g = live ? q : 0;
+    const size_t h = (size_t)1 << s, low = g & (h - 1), j = ((g >> s) << (s + 2)) | low;
+    uint8_t* w = work + (size_t)blockIdx.y * n * 192;
+    const uint8_t* pr = tmp + ((size_t)blockIdx.y * 5 * (n >> 2) + g * 5) * 192;
+    const int off = quad_store_offset();
+    const bool yrole = (threadIdx.x & 3) == 1;
+    auto neg = [&](const fp_t& v) { return yrole ? v.neg() : v; };
+    const fp_t x0 = load_field<fp_t>(w + j * 192 + off);
+    const fp_t p0 = load_field<fp_t>(pr + off), p1 = load_field<fp_t>(pr + 192 + off), p2 = load_field<fp_t>(pr + 2 * 192 + off),
+               p3 = load_field<fp_t>(pr + 3 * 192 + off), p4 = load_field<fp_t>(pr + 4 * 192 + off);
+    const fp_t u = quad_add(x0, p0), v = quad_add(x0, neg(p0));
+    const fp_t pp = quad_add(p1, p2), qd = quad_add(p3, neg(p4));
+    const fp_t z0 = quad_add(u, pp), z2 = quad_add(u, neg(pp)), z1 = quad_add(v, qd), z3 = quad_add(v, neg(qd));
+    if (live) {
+        store_field(w + j * 192 + off, z0);
+        store_field(w + (j + h) * 192 + off, z1);
+        store_field(w + (j + 2 * h) * 192 + off, z2);
+        store_field(w + (j + 3 * h) * 192 + off, z3);
+    }
+}
 // XYZZ -> Jacobian, with the [n^-1] scaling of the inverse transform (blst/src/fft_g1.rs:74-79); one quad per point
 __global__ void __launch_bounds__(32) k_g1_out(const uint8_t* __restrict__ work, uint8_t* __restrict__ out_jac, size_t total,
                                                const uint8_t* __restrict__ scale) {
@@ -82,7 +138,38 @@ void FFTSettingsDev::fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n,
     }
     launches_ = 0;
     k_g1_brp_in<<<dim3(div_up(n, 128), (unsigned)batch), 128, 0, st>>>((const uint8_t*)in_jac_dev, (uint8_t*)g1_work_, n, log_n);
-    for (int s = 0; s < log_n; s++) {
+    // stage 0 multiplies by w^0 only; after it the stages run in fused pairs (k_g1_stage2_*: two stages at the latency of
+    // one scalar multiplication) while the launch is small: one warp per eight products with a 27 KiB table each, so
+    // ~1100 warps are resident at a time -- up to 2^12 points per launch the fused products fit one wave (one blob's FK20
+    // transforms: cells + proofs 12.0 -> 6.9 ms); at 64 blobs x 128 points they spill into a second wave and the plain
+    // stages, 20 % less work, win (18.6 vs 21.7 ms per 64 blobs, scripts/fk20_timing.py)
+    const int fuse_env = getenv("B200_FFT_G1_FUSE") ? atoi(getenv("B200_FFT_G1_FUSE")) : -1;   // per call: tests toggle it
+    const bool fuse = fuse_env >= 0 ? fuse_env != 0 : total <= ((size_t)1 << 12);
+    int s = 0;
+    if (!fuse || (log_n & 1)) {
+        if (log_n > 0) {
+            k_g1_stage<<<dim3(div_up(n / 2 * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, n, log_n, 0, (const uint8_t*)roots_,
+                                                                                max_width_, inverse);
+            launches_++;
+        }
+        s = 1;
+    }
+    if (fuse && log_n >= 2) {
+        const size_t need = (size_t)batch * 5 * (n >> 2);
+        if (need > g1_tmp_elems_) {
+            cudaFree(g1_tmp_);
+            g1_tmp_ = nullptr; g1_tmp_elems_ = 0;
+            g1_tmp_ = dev_alloc<uint8_t>(need * 192);
+            g1_tmp_elems_ = need;
+        }
+        for (; s + 2 <= log_n; s += 2) {
+            k_g1_stage2_mul<<<dim3(div_up(5 * (n >> 2) * 4, 32), (unsigned)batch), 32, 0, st>>>((const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n, s,
+                                                                                           (const uint8_t*)roots_, max_width_, inverse);
+            k_g1_stage2_comb<<<dim3(div_up((n >> 2) * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, (const uint8_t*)g1_tmp_, n, s);
+            launches_ += 2;
+        }
+    }
+    for (; s < log_n; s++) {
         k_g1_stage<<<dim3(div_up(n / 2 * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, n, log_n, s, (const uint8_t*)roots_,
                                                                             max_width_, inverse);
         launches_++;

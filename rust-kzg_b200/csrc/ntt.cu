@@ -214,6 +214,7 @@ FFTSettingsDev::~FFTSettingsDev() {
     cudaFree(scratch2_);
     cudaFree(scratch3_);
     cudaFree(g1_work_);
+    cudaFree(g1_tmp_);
 }
 
 void FFTSettingsDev::ensure_scratch(size_t elems) {

@@ -58,6 +58,8 @@ private:
     size_t scratch3_elems_ = 0;
     void* g1_work_ = nullptr;
     size_t g1_work_elems_ = 0;
+    void* g1_tmp_ = nullptr;         // products of the fused double stages of fft_g1
+    size_t g1_tmp_elems_ = 0;
     int launches_ = 0;
 };
 

@@ -184,3 +184,25 @@ def test_fft_fr_above_2p22_three_passes(B, K):
     assert np.array_equal(fs.fft_fr(fwd, True), data)
     del ofs
     fs.close()
+
+
+@pytest.mark.parametrize("logn", [2, 5, 7, 8])
+def test_fft_g1_fused_and_plain_stages_agree(B, K, oracle_settings, logn):
+    """fft_g1 runs its stages in fused pairs (five independent scalar multiplications per four points, csrc/fft_g1.cu) while
+    the transform is small and stage by stage otherwise: both forms against the oracle, forward and inverse"""
+    import os
+    n = 1 << logn
+    ofs = K.FFTSettings(10)
+    pts = oracle_settings.g1_monomial[7:7 + n].copy()
+    if n >= 8:
+        pts[2] = 0
+    want = {inv: K.p1s_to_affine(ofs.fft_g1(pts, inv)) for inv in (False, True)}
+    for fuse in ("1", "0"):
+        os.environ["B200_FFT_G1_FUSE"] = fuse
+        try:
+            fs = B.FFTSettings(10)
+            for inv in (False, True):
+                assert np.array_equal(K.p1s_to_affine(fs.fft_g1(pts, inv)), want[inv]), (fuse, inv)
+            fs.close()
+        finally:
+            del os.environ["B200_FFT_G1_FUSE"]
