@@ -222,20 +222,45 @@ __device__ __forceinline__ void glv_split(const uint32_t (&k)[8], uint32_t (&k1)
 #pragma unroll
     for (int i = 0; i < 4; i++) { k1[i] = rem[i]; k2[i] = q[i]; }
 }
+// signed 4-bit digits of a 128-bit number, least significant first: d_j in [-7, 8], 33 of them (the last is the carry).
+// mag: 33 nibbles |d_j|, sgn: bit j set when d_j < 0.
+__device__ __forceinline__ void booth4(const uint32_t (&k)[4], uint32_t (&mag)[5], uint32_t (&sgn)[2]) {
+#pragma unroll
+    for (int i = 0; i < 5; i++) mag[i] = 0;
+    sgn[0] = sgn[1] = 0;
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int j = 0; j < 32; j++) {
+        uint32_t d = ((k[j >> 3] >> ((j & 7) * 4)) & 15u) + carry;
+        carry = d > 8u;
+        if (carry) {
+            d = 16u - d;
+            sgn[j >> 5] |= 1u << (j & 31);
+        }
+        mag[j >> 3] |= d << ((j & 7) * 4);
+    }
+    mag[4] = carry;
+}
 // [k] p for quad-distributed p; k canonical little-endian words (< r), the same value on the four lanes of a quad.
-// GLV split (above), then fixed 4-bit windows over the 128-bit halves, most significant first: 16-entry table of
-// multiples d * P per quad in shared memory plus the X coordinates of d * (beta x, -y) (Y is negated on the fly, ZZ / ZZZ
-// are shared) -- kQuadTableBytes per warp; every lane only ever touches its own component slots, so no synchronisation --
-// then 32 x (4 quad doublings + 2 quad additions) instead of 64 x (4 + 1).  The instruction stream is uniform across the
-// warp's quads -- with a bit-serial double-and-add every quad would pay for an addition whenever any of the eight needs one.
-static constexpr int kQuadTableStride = 16 * 192 + 16 * 48;
+// GLV split (above), then signed 4-bit windows over the 128-bit halves, most significant first: a table of the multiples
+// d * P, d = 0..8, per quad in shared memory plus the X coordinates of d * (beta x, -y) (Y is negated on the fly, ZZ / ZZZ
+// are shared) -- kQuadTableBytes per warp (17 KiB: signed digits halve the table of an unsigned window, which doubles the
+// warps an SM can hold -- these kernels are latency chains and live on occupancy -- and shortens the table build from 14
+// to 7 point operations); every lane only ever touches its own component slots, so no synchronisation -- then
+// 33 x (4 quad doublings + 2 quad additions).  The instruction stream is uniform across the warp's quads -- with a
+// bit-serial double-and-add every quad would pay for an addition whenever any of the eight needs one.
+static constexpr int kQuadTableEntries = 9;
+static constexpr int kQuadTableStride = kQuadTableEntries * 192 + kQuadTableEntries * 48;
 static constexpr int kQuadTableBytes = 8 * kQuadTableStride;
 __device__ __forceinline__ fp_t quad_mul_scalar(const fp_t& p, const uint32_t (&k)[8], uint8_t* warp_table) {
     const int lane = threadIdx.x & 31, role = lane & 3;
     uint8_t* tab = warp_table + (lane >> 2) * kQuadTableStride + quad_store_offset();
-    uint8_t* tabx = warp_table + (lane >> 2) * kQuadTableStride + 16 * 192;   // beta * X_d, 48 B each
+    uint8_t* tabx = warp_table + (lane >> 2) * kQuadTableStride + kQuadTableEntries * 192;   // beta * X_d, 48 B each
     uint32_t k1[4], k2[4];
     glv_split(k, k1, k2);
+    uint32_t m1[5], s1[2], m2[5], s2[2];
+    booth4(k1, m1, s1);
+    booth4(k2, m2, s2);
     fp_t beta;
     {
         const uint32_t Bm[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
@@ -246,27 +271,30 @@ __device__ __forceinline__ fp_t quad_mul_scalar(const fp_t& p, const uint32_t (&
     store_field(tab, fp_t::zero());
     store_field(tab + 192, p);
 #pragma unroll 1
-    for (int d = 2; d < 16; d++) {
+    for (int d = 2; d < kQuadTableEntries; d++) {
         fp_t t = (d & 1) ? quad_add(load_field<fp_t>(tab + (d - 1) * 192), p) : quad_dbl(load_field<fp_t>(tab + (d >> 1) * 192));
         store_field(tab + d * 192, t);
     }
 #pragma unroll 1
-    for (int d = 0; d < 16; d++) {
+    for (int d = 0; d < kQuadTableEntries; d++) {
         fp_t bx = load_field<fp_t>(tab + d * 192) * beta;      // only the X lane's product is kept
         if (role == 0) store_field(tabx + d * 48, bx);
     }
     fp_t acc = fp_t::zero();
 #pragma unroll 1
-    for (int j = 31; j >= 0; j--) {
-        if (j != 31) {
+    for (int j = 32; j >= 0; j--) {
+        if (j != 32) {
 #pragma unroll 1
             for (int r = 0; r < 4; r++) acc = quad_dbl(acc);
         }
-        const uint32_t d1 = (k1[j >> 3] >> ((j & 7) * 4)) & 15, d2 = (k2[j >> 3] >> ((j & 7) * 4)) & 15;
-        acc = quad_add(acc, load_field<fp_t>(tab + d1 * 192));
-        fp_t e = load_field<fp_t>(tab + d2 * 192);             // d2 * (beta x, -y) = (beta X_d2, -Y_d2, ZZ_d2, ZZZ_d2)
+        const uint32_t d1 = (m1[j >> 3] >> ((j & 7) * 4)) & 15u, d2 = (m2[j >> 3] >> ((j & 7) * 4)) & 15u;
+        const bool n1 = j < 32 && ((s1[j >> 5] >> (j & 31)) & 1u), n2 = j < 32 && ((s2[j >> 5] >> (j & 31)) & 1u);
+        fp_t e = load_field<fp_t>(tab + d1 * 192);             // +-d1 * P
+        if (role == 1 && n1) e = e.neg();
+        acc = quad_add(acc, e);
+        e = load_field<fp_t>(tab + d2 * 192);                  // +-d2 * (beta x, -y) = (beta X_d2, -+Y_d2, ZZ_d2, ZZZ_d2)
         if (role == 0) e = load_field<fp_t>(tabx + d2 * 48);
-        if (role == 1) e = e.neg();
+        if (role == 1 && !n2) e = e.neg();
         acc = quad_add(acc, e);
     }
     return acc;
