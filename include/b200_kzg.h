@@ -256,6 +256,10 @@ B200_API RustError b200_msm_sharded_mult_device(void *sharded, void *out_dev, si
 B200_API void *b200_msm_sharded_local(void *sharded);        /* the rank-local prepared handle (b200_msm_info, profiling) */
 B200_API void b200_msm_sharded_free(void *sharded);
 
+/* microbenchmark behind profiles/r02_affine.md: the kernel time of npairs independent batch-affine point additions (K per
+ * thread, two gathered points per pair, one field inversion per 128 K pairs) over a table of npoints points */
+B200_API RustError b200_bench_affine_pairs(uint32_t npoints, size_t npairs, int K, double *ms);
+
 /* number of CUDA devices usable; 0 means every compute entry point will fail */
 B200_API int b200_device_count(void);
 

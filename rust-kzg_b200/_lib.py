@@ -52,6 +52,7 @@ def load():
         "b200_selftest_p1_compress": (RustError, [vp, vp, sz]),
         "b200_microbench_int": (RustError, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "b200_microbench_mul": (RustError, [ci, ci, C.POINTER(C.c_double)]),
+        "b200_bench_affine_pairs": (RustError, [C.c_uint32, sz, ci, C.POINTER(C.c_double)]),
         "b200_device_count": (ci, []),
         "b200_msm_set_profiling": (None, [vp, ci]),
         "b200_msm_profile_read": (RustError, [vp, C.POINTER(C.c_double), C.POINTER(ci)]),

@@ -490,6 +490,15 @@ RustError b200_msm_sharded_mult(void* sh, blst_p1* out, size_t n_local, const bl
     });
 }
 
+/* microbenchmark: npairs independent batch-affine additions (K per thread, one inversion per 128 K) over a table of npoints
+ * points; returns the kernel time through *ms (profiles/r02_affine.md) */
+RustError b200_bench_affine_pairs(uint32_t npoints, size_t npairs, int K, double* ms) {
+    return guarded([&] {
+        require_device();
+        if (ms) *ms = bench_affine_pairs(npoints, npairs, K, nullptr);
+    });
+}
+
 int b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

@@ -1018,6 +1018,89 @@ void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
+// Microbenchmark (b200_bench_affine_pairs): the rate of INDEPENDENT batch-affine pair additions -- K pairs per thread,
+// two gathered 96-byte points per pair from a large table, prefix products in global memory, one inversion per CTA through
+// the shared-memory product tree -- i.e. one round of a tree-shaped batch-affine accumulation without any bucket logic.
+// It bounds from above what such a design could reach against the XYZZ task kernel's 2.65 G additions/s.
+template <int K>
+__global__ void __launch_bounds__(kBaThreads, 3) k_affine_pairs_bench(const uint8_t* __restrict__ table, uint32_t npoints, size_t npairs,
+                                                                    uint8_t* __restrict__ prefix, uint8_t* __restrict__ out) {
+    __shared__ __align__(16) uint8_t sm_t[128 * 48];
+    __shared__ __align__(16) uint8_t sm_i[128 * 48];
+    const uint32_t tid = threadIdx.x;
+    const size_t p0 = ((size_t)blockIdx.x * kBaThreads + tid) * K;
+    uint4* pf = reinterpret_cast<uint4*>(prefix) + ((size_t)blockIdx.x * K * 3) * kBaThreads + tid;
+    fp_t running = fp_t::one();
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        const size_t p = p0 + k;
+        if (p >= npairs) break;
+        const uint32_t i1 = (uint32_t)(splitmix64(p) % npoints), i2 = (uint32_t)(splitmix64(~p) % npoints);
+        const fp_t x1 = load_field_ro<fp_t>(table + (size_t)i1 * 96), x2 = load_field_ro<fp_t>(table + (size_t)i2 * 96);
+        fp_t d = x2 - x1;
+        if (d.is_zero()) d = fp_t::one();
+        uint4* q = pf + (size_t)k * 3 * kBaThreads;
+        q[0] = make_uint4(running.v[0], running.v[1], running.v[2], running.v[3]);
+        q[kBaThreads] = make_uint4(running.v[4], running.v[5], running.v[6], running.v[7]);
+        q[2 * kBaThreads] = make_uint4(running.v[8], running.v[9], running.v[10], running.v[11]);
+        running = running * d;
+    }
+    fp_t inv = cta_batch_inverse(running, sm_t, sm_i);
+#pragma unroll 1
+    for (int k = K - 1; k >= 0; k--) {
+        const size_t p = p0 + k;
+        if (p >= npairs) continue;
+        const uint32_t i1 = (uint32_t)(splitmix64(p) % npoints), i2 = (uint32_t)(splitmix64(~p) % npoints);
+        const affine_t a = load_affine(table + (size_t)i1 * 96), b = load_affine(table + (size_t)i2 * 96);
+        const uint4* q = pf + (size_t)k * 3 * kBaThreads;
+        fp_t pre;
+        {
+            uint4 t0 = q[0], t1 = q[kBaThreads], t2 = q[2 * kBaThreads];
+            pre.v[0] = t0.x; pre.v[1] = t0.y; pre.v[2] = t0.z; pre.v[3] = t0.w;
+            pre.v[4] = t1.x; pre.v[5] = t1.y; pre.v[6] = t1.z; pre.v[7] = t1.w;
+            pre.v[8] = t2.x; pre.v[9] = t2.y; pre.v[10] = t2.z; pre.v[11] = t2.w;
+        }
+        fp_t d = b.x - a.x;
+        if (d.is_zero()) d = fp_t::one();
+        const fp_t inv_d = pre * inv;
+        inv = inv * d;
+        const fp_t lam = (b.y - a.y) * inv_d;
+        affine_t r;
+        r.x = lam.sqr() - a.x - b.x;
+        r.y = lam * (a.x - r.x) - a.y;
+        store_affine(out + p * 96, r);
+    }
+}
+// returns the kernel time in ms (CUDA events) for npairs additions over a table of npoints pseudo-random "points"
+float bench_affine_pairs(uint32_t npoints, size_t npairs, int K, cudaStream_t st) {
+    uint8_t* table = dev_alloc<uint8_t>((size_t)npoints * 96);
+    uint8_t* out = dev_alloc<uint8_t>(npairs * 96);
+    const size_t threads = (npairs + K - 1) / K, blocks = (threads + kBaThreads - 1) / kBaThreads;
+    uint8_t* prefix = dev_alloc<uint8_t>(blocks * kBaThreads * (size_t)K * 48);
+    // any field elements do: the cost of the arithmetic does not depend on the values (top limb cleared: < p)
+    B200_CUDA_CHECK(cudaMemsetAsync(table, 0x5a, (size_t)npoints * 96, st));
+    k_iota<<<div_up((size_t)npoints * 24, 256), 256, 0, st>>>((uint32_t*)table, (size_t)npoints * 24);   // distinct low limbs
+    cudaEvent_t e0, e1;
+    B200_CUDA_CHECK(cudaEventCreate(&e0));
+    B200_CUDA_CHECK(cudaEventCreate(&e1));
+    float ms = 0;
+    for (int rep = 0; rep < 2; rep++) {
+        B200_CUDA_CHECK(cudaEventRecord(e0, st));
+        if (K == 8) k_affine_pairs_bench<8><<<(unsigned)blocks, kBaThreads, 0, st>>>(table, npoints, npairs, prefix, out);
+        else if (K == 16) k_affine_pairs_bench<16><<<(unsigned)blocks, kBaThreads, 0, st>>>(table, npoints, npairs, prefix, out);
+        else if (K == 64) k_affine_pairs_bench<64><<<(unsigned)blocks, kBaThreads, 0, st>>>(table, npoints, npairs, prefix, out);
+        else k_affine_pairs_bench<32><<<(unsigned)blocks, kBaThreads, 0, st>>>(table, npoints, npairs, prefix, out);
+        B200_CUDA_CHECK(cudaEventRecord(e1, st));
+        B200_CUDA_CHECK(cudaEventSynchronize(e1));
+        B200_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(table); cudaFree(out); cudaFree(prefix);
+    B200_LAUNCH_CHECK();
+    return ms;
+}
+
 typedef void (*ba_kernel_t)(const uint8_t*, uint32_t, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, uint8_t*, uint8_t*);
 static ba_kernel_t ba_kernel(int k, bool tree) {
     switch (k) {

@@ -140,6 +140,8 @@ private:
     void* chunk_sums_r_ = nullptr;     // marginals of the R sums
 };
 
+// microbenchmark of independent batch-affine pair additions (msm.cu): kernel time in ms
+float bench_affine_pairs(uint32_t npoints, size_t npairs, int K, cudaStream_t st);
 // helpers shared with other translation units
 void launch_g1_sum(const void* jac_dev, void* out_jac_dev, int count, cudaStream_t stream);
 void launch_points_to_compressed(const void* jac_dev, uint8_t* out48_dev, int count, cudaStream_t stream, int brp_bits = 0);
