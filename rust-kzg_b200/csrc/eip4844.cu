@@ -405,7 +405,12 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
                 MsmEngine rows8(c8, aff_brp, false, st);          // rows 2^(8j) * P_i, 96-byte stride; dropped after the build
                 launch_direct_build(rows8.table(), lag_direct_, n, st);
                 B200_CUDA_CHECK(cudaStreamSynchronize(st));
-                for (Lane& ln : lanes_) ln.direct_part = dev_alloc<uint8_t>((size_t)direct_max_ * (n / 4) * 192);
+                for (Lane& ln : lanes_) {
+                    ln.direct_part = dev_alloc<uint8_t>((size_t)direct_max_ * (n / 4) * 192);
+                    ln.direct_cnt = dev_alloc<unsigned>(direct_max_);
+                    B200_CUDA_CHECK(cudaMemsetAsync(ln.direct_cnt, 0, direct_max_ * sizeof(unsigned), st));
+                }
+                B200_CUDA_CHECK(cudaStreamSynchronize(st));
             } else {
                 cudaGetLastError();
                 direct_max_ = 0;
@@ -428,20 +433,24 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
 
 KzgSettingsDev::~KzgSettingsDev() {
     cudaFree(lagrange_jac_); cudaFree(monomial_jac_); cudaFree(domain_);
-    for (Lane& ln : lanes_) { cudaFree(ln.scalars); cudaFree(ln.poly); cudaFree(ln.z); cudaFree(ln.y); cudaFree(ln.out_jac); cudaFree(ln.direct_part); }
+    for (Lane& ln : lanes_) { cudaFree(ln.scalars); cudaFree(ln.poly); cudaFree(ln.z); cudaFree(ln.y); cudaFree(ln.out_jac); cudaFree(ln.direct_part); cudaFree(ln.direct_cnt); }
     cudaFree(lag_direct_);
     cudaFree(cells_a_); cudaFree(cells_b_);
     cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_); cudaFree(fk_direct_);
     cudaFree(g2_affine_); cudaFree(g2_jac_); cudaFree(g2_lines_); cudaFree(vf_buf_); cudaFree(das_buf_);
 }
 
-// Small batches: direct table lookups, two launches (fk20_direct.cu); batches that fill the machine: the bucket engine.
-void KzgSettingsDev::lagrange_msm(int lane, MsmEngine& eng, int n, cudaStream_t st) {
+// Small batches: direct table lookups, ONE launch (fk20_direct.cu: sums, fold and compression fused through a last-CTA
+// counter); batches that fill the machine: the bucket engine, then the compression kernel.
+int KzgSettingsDev::lagrange_msm(int lane, MsmEngine& eng, int n, uint8_t* out48, cudaStream_t st) {
     Lane& ln = lanes_[lane % kLanes];
-    if (lag_direct_ && n <= direct_max_)
-        launch_direct_msm(ln.scalars, lag_direct_, ln.direct_part, ln.out_jac, n, (int)kFieldElementsPerBlob, st);
-    else
-        eng.run(ln.scalars, kFieldElementsPerBlob, n, false, ln.out_jac, st);
+    if (lag_direct_ && n <= direct_max_) {
+        launch_direct_msm_compressed(ln.scalars, lag_direct_, ln.direct_part, ln.direct_cnt, out48, n, (int)kFieldElementsPerBlob, st);
+        return 1;
+    }
+    eng.run(ln.scalars, kFieldElementsPerBlob, n, false, ln.out_jac, st);
+    launch_points_to_compressed(ln.out_jac, out48, n, st);
+    return eng.launches_per_run() + 1;
 }
 
 void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* out48, int* status, cudaStream_t st, int lane) {
@@ -450,9 +459,7 @@ void KzgSettingsDev::blob_to_commitments(const uint8_t* blobs, int n, uint8_t* o
     size_t total = (size_t)n * kFieldElementsPerBlob;
     k_blob_to_fr<<<div_up(total, 256), 256, 0, st>>>(blobs, total, (uint8_t*)ln.scalars, nullptr, status);
     B200_LAUNCH_CHECK();
-    lagrange_msm(lane, *ln.msm, n, st);
-    launch_points_to_compressed(ln.out_jac, out48, n, st);
-    launches_ = 2 + (lag_direct_ && n <= direct_max_ ? 2 : ln.msm->launches_per_run());
+    launches_ = 1 + lagrange_msm(lane, *ln.msm, n, out48, st);
 }
 
 void KzgSettingsDev::compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes, int z_reduce, int n, uint8_t* proofs48,
@@ -466,15 +473,14 @@ void KzgSettingsDev::compute_proofs(const uint8_t* blobs, const uint8_t* z_bytes
                                                                               (const uint8_t*)domain_, (uint8_t*)ln.scalars,
                                                                               (uint8_t*)ln.y);
     B200_LAUNCH_CHECK();
-    lagrange_msm(lane, *ln.msm_q, n, st);
-    launch_points_to_compressed(ln.out_jac, proofs48, n, st);
+    const int msm_launches = lagrange_msm(lane, *ln.msm_q, n, proofs48, st);
     int extra = 0;
     if (y32) {
         k_fr_to_bytes<<<div_up(n, 64), 64, 0, st>>>((const uint8_t*)ln.y, n, y32);
         B200_LAUNCH_CHECK();
         extra = 1;
     }
-    launches_ = 4 + extra + (lag_direct_ && n <= direct_max_ ? 2 : ln.msm_q->launches_per_run());
+    launches_ = 3 + extra + msm_launches;
 }
 
 void KzgSettingsDev::compute_cells(const uint8_t* blobs, int n, uint8_t* cells_out, int* status, cudaStream_t st) {

@@ -114,11 +114,12 @@ private:
         void* y = nullptr;         // max_batch Montgomery
         void* out_jac = nullptr;   // max_batch Jacobian results
         void* direct_part = nullptr;  // partial sums of the direct small-batch MSM
+        unsigned* direct_cnt = nullptr;  // per-vector completion counters of its fused kernel (zero between launches)
     } lanes_[kLanes];
     void* lag_direct_ = nullptr;   // every digit multiple of the 4096 Lagrange points (direct small-batch MSM), or nullptr
     int direct_max_ = 0;           // largest batch the direct form serves (larger ones fill the machine: bucket engine)
-    // sum over the Lagrange points for n vectors of canonical scalars in ln.scalars -> ln.out_jac
-    void lagrange_msm(int lane, MsmEngine& eng, int n, cudaStream_t st);
+    // sum over the Lagrange points for n vectors of canonical scalars in ln.scalars -> out48 (compressed); returns launches
+    int lagrange_msm(int lane, MsmEngine& eng, int n, uint8_t* out48, cudaStream_t st);
     void* lagrange_jac_ = nullptr;
     void* monomial_jac_ = nullptr;
     void* domain_ = nullptr;    // brp_roots_of_unity[0..4096) of the 8192 table (Montgomery)
@@ -149,6 +150,8 @@ void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_
 size_t direct_table_bytes(size_t npts);
 void launch_direct_build(const void* rows, void* table, size_t npts, cudaStream_t st);
 void launch_direct_msm(const void* scalars, const void* table, void* partials, void* out_jac, int nvec, int npts, cudaStream_t st);
+void launch_direct_msm_compressed(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, int nvec,
+                                  int npts, cudaStream_t st);
 // test hook (verify.cu): sum k_i P_i through the quad / GLV scalar multiplication used by the verifiers and fft_g1
 void selftest_lincomb_quads(const void* points_affine_dev, const void* scalars_mont_dev, int n, void* out_jac_dev, cudaStream_t st);
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input

@@ -146,10 +146,14 @@ void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_
 // points, lane j owns window j (8-bit Booth digits need no carry chain), P mixed additions per lane with the next gather in
 // flight, one warp tree; a second kernel folds the 4096 / P partial sums of every vector.  No sort, no buckets: two
 // launches, chain length P + 2 trees.  table: 4096 x 32 x 128 affine points (1.5 GiB, built once per settings object).
-template <class AR>
+// FUSED: the CTA that finishes a vector's last partial sum (a counter per vector) also folds the vector's m partials and
+// writes the 48-byte compressed result -- one launch per batch instead of three (direct sums, fold, compression).
+template <class AR, bool FUSED>
 __global__ void __launch_bounds__(128) k_direct_msm_partial(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
-                                                            uint8_t* __restrict__ partials, int npts, int P, size_t nwarps) {
+                                                            uint8_t* __restrict__ partials, int npts, int P, size_t nwarps,
+                                                            unsigned* __restrict__ counters, uint8_t* __restrict__ out48) {
     __shared__ __align__(16) uint8_t sh[4 * 192];
+    __shared__ int sh_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const size_t w = (size_t)blockIdx.x * 4 + wid;             // nwarps is a multiple of 4: whole CTAs are live
     const size_t per_vec = (size_t)npts / P, v = w / per_vec, p0 = (w % per_vec) * P;
@@ -191,6 +195,54 @@ __global__ void __launch_bounds__(128) k_direct_msm_partial(const uint8_t* __res
         fp_t t = quad_tree(c, 16);
         if (lane < 4) store_field(partials + (size_t)blockIdx.x * 192 + quad_store_offset(), t);
     }
+    if (!FUSED) return;
+    // last CTA of this vector?  (partials of a vector are contiguous: m = npts / (4 P) CTAs per vector)
+    const int m = npts / (4 * P);
+    const size_t vec = (size_t)blockIdx.x / m;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(&counters[vec], 1u);
+        sh_last = done == (unsigned)m - 1;
+        if (sh_last) counters[vec] = 0;                       // ready for the next launch on this lane
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    // fold the m partials (16 <= m <= 128) with the CTA's 128 threads, exactly as k_direct_msm_reduce does
+    const uint8_t* base = partials + vec * m * 192;
+    xyzz_t a;
+    if ((int)threadIdx.x < m) {
+        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)threadIdx.x * 192);
+        uint4 tmp[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) tmp[k] = __ldcg(src + k);   // written by other CTAs: read through L2
+        const uint32_t* wv = reinterpret_cast<const uint32_t*>(tmp);
+#pragma unroll
+        for (int k = 0; k < 12; k++) { a.x.v[k] = wv[k]; a.y.v[k] = wv[12 + k]; a.zzz.v[k] = wv[24 + k]; a.zz.v[k] = wv[36 + k]; }
+    } else {
+        a = xyzz_t::inf();
+    }
+    __syncthreads();                                          // sh is reused below
+    fp_t q2 = seg_sum_quad(a, 32);
+    if (lane < 4) store_field(sh + wid * 192 + quad_store_offset(), q2);
+    __syncthreads();
+    if (wid != 0) return;
+    fp_t c2 = lane < 16 ? load_field<fp_t>(sh + (lane >> 2) * 192 + quad_store_offset()) : fp_t::zero();
+    fp_t tot = quad_tree(c2, 16);                             // quad 0: (X, Y, ZZ, ZZZ) of the vector's sum
+    // compressed form (blst_p1_compress): x = X / ZZ, y = Y / ZZZ with 1/ZZ = ZZZ^-2 ZZ^2; one inversion, uniform over the warp
+    const fp_t zz = shfl_idx_fp(tot, 2), zzz = shfl_idx_fp(tot, 3);
+    const bool inf = zz.is_zero();
+    const fp_t izzz = (inf ? fp_t::one() : zzz).inverse();
+    const fp_t izz = izzz.sqr() * zz.sqr();
+    const fp_t coord = lane == 0 ? tot * izz : tot * izzz;    // lane 0: x, lane 1: y
+    const fp_t yv = shfl_idx_fp(coord, 1);
+    if (lane == 0) {
+        cc::affine_t r;
+#pragma unroll
+        for (int k = 0; k < 12; k++) { r.x.v[k] = inf ? 0u : coord.v[k]; r.y.v[k] = inf ? 0u : yv.v[k]; }
+        cc::affine_compress(out48 + vec * 48, r);
+    }
 }
 // one CTA of 32 .. 256 threads per vector: m = 4096 / (4 P) partial sums (16 <= m <= 128, a power of two) -> Jacobian result
 __global__ void __launch_bounds__(256) k_direct_msm_reduce(const uint8_t* __restrict__ partials, int m, uint8_t* __restrict__ out_jac) {
@@ -213,17 +265,30 @@ __global__ void __launch_bounds__(256) k_direct_msm_reduce(const uint8_t* __rest
         if (lane == 2) store_field(out_jac + (size_t)blockIdx.x * 144 + 96, t);
     }
 }
-// scalars: nvec x npts canonical little-endian 32-byte scalars; partials: workspace of nvec * npts / 32 XYZZ points
-void launch_direct_msm(const void* scalars, const void* table, void* partials, void* out_jac, int nvec, int npts, cudaStream_t st) {
+static int direct_p(int nvec, int npts) {
     // P points per warp: as few as keep one wave of warps on the machine (148 SMs x 12 warps), between 8 and 64;
     // four warps per CTA leave one partial sum per 4 P points
     int P = 8;
     while (P < 64 && (size_t)nvec * npts / P > 148 * 12) P <<= 1;
+    return P;
+}
+// scalars: nvec x npts canonical little-endian 32-byte scalars; partials: workspace of nvec * npts / 32 XYZZ points
+void launch_direct_msm(const void* scalars, const void* table, void* partials, void* out_jac, int nvec, int npts, cudaStream_t st) {
+    const int P = direct_p(nvec, npts);
     const size_t nwarps = (size_t)nvec * npts / P;
     const int m = npts / (4 * P);                              // partial sums per vector: 128 .. 16
-    k_direct_msm_partial<ArCall><<<(unsigned)(nwarps / 4), 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)partials,
-                                                                      npts, P, nwarps);
+    k_direct_msm_partial<ArCall, false><<<(unsigned)(nwarps / 4), 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table,
+                                                                             (uint8_t*)partials, npts, P, nwarps, nullptr, nullptr);
     k_direct_msm_reduce<<<nvec, std::max(32, std::min(m, 256)), 0, st>>>((const uint8_t*)partials, m, (uint8_t*)out_jac);
+    B200_LAUNCH_CHECK();
+}
+// the same sums, written as 48-byte compressed points by ONE launch; counters: nvec zero-initialised words (left zero)
+void launch_direct_msm_compressed(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, int nvec,
+                                  int npts, cudaStream_t st) {
+    const int P = direct_p(nvec, npts);
+    const size_t nwarps = (size_t)nvec * npts / P;
+    k_direct_msm_partial<ArCall, true><<<(unsigned)(nwarps / 4), 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table,
+                                                                            (uint8_t*)partials, npts, P, nwarps, counters, out48);
     B200_LAUNCH_CHECK();
 }
 
