@@ -332,6 +332,30 @@ static int env_int_local(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
 }
+// The direct-lookup tables (fk20_direct.cu) trade HBM for additions: the widest window <= want whose table still leaves
+// B200_DIRECT_RESERVE_GB (default 40) of the device free for everything else in the process; 0 when not even the 8-bit one fits.
+static int pick_direct_bits(size_t npts, int want) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    const size_t reserve = (size_t)env_int_local("B200_DIRECT_RESERVE_GB", 40) << 30;
+    const int cand[3] = {want, 11, 8};
+    for (int c : cand)
+        if (c >= 5 && c <= 16 && c <= want && direct_table_bytes(npts, c) + reserve <= free_b) return c;
+    return 0;
+}
+// table of every digit multiple of `points` (n affine points; period > 1: `points` holds period blocks of n): built from the
+// fixed-base rows of a throw-away engine with the same window width; nullptr when the allocation fails
+static void* build_direct_table(const void* points, size_t n, int period, int c, cudaStream_t st) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, direct_table_bytes(n * period, c)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    MsmConfig rc;
+    rc.c = c; rc.W = direct_windows(c); rc.fixed = true; rc.n = n; rc.max_batch = 1; rc.L = 64; rc.randomize = false;
+    rc.bases_period = period;
+    MsmEngine rows(rc, points, false, st);                    // rows 2^(cj) * P_i; dropped after the build
+    launch_direct_build(rows.table(), rows.table_stride(), p, n * period, c, st);
+    B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    return p;
+}
 
 KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lagrange, int max_batch, cudaStream_t st)
     : max_batch_(max_batch) {
@@ -393,27 +417,22 @@ KzgSettingsDev::KzgSettingsDev(const uint8_t* g1_monomial, const uint8_t* g1_lag
             ln.y = dev_alloc<uint8_t>((size_t)max_batch * 32);
             ln.out_jac = dev_alloc<uint8_t>((size_t)max_batch * 144);
         }
-        // direct lookup table of the Lagrange points for batches of up to direct_max_ blobs (1.5 GiB; B200_BLOB_DIRECT=0
-        // or a failed allocation leaves every batch to the bucket engine)
-        direct_max_ = std::min(max_batch, env_int_local("B200_BLOB_DIRECT", 16));
+        // direct lookup table of the Lagrange points (fk20_direct.cu) for batches of up to direct_max_ blobs: 13-bit windows,
+        // 30 GiB, 20 additions per element instead of 32 (B200_BLOB_DIRECT_BITS; narrower when HBM is short).
+        // B200_BLOB_DIRECT=0 or a failed allocation leaves every batch to the bucket engine.
+        direct_max_ = std::min(max_batch, env_int_local("B200_BLOB_DIRECT", 64));
         if (direct_max_ > 0) {
-            void* p = nullptr;
-            if (cudaMalloc(&p, direct_table_bytes(n)) == cudaSuccess) {
-                lag_direct_ = p;
-                MsmConfig c8;
-                c8.c = 8; c8.W = 32; c8.fixed = true; c8.n = n; c8.max_batch = 1; c8.L = 64;
-                MsmEngine rows8(c8, aff_brp, false, st);          // rows 2^(8j) * P_i, 96-byte stride; dropped after the build
-                launch_direct_build(rows8.table(), lag_direct_, n, st);
-                B200_CUDA_CHECK(cudaStreamSynchronize(st));
+            direct_c_ = pick_direct_bits(n, env_int_local("B200_BLOB_DIRECT_BITS", 13));
+            if (direct_c_) lag_direct_ = build_direct_table(aff_brp, n, 1, direct_c_, st);
+            if (lag_direct_) {
                 for (Lane& ln : lanes_) {
-                    ln.direct_part = dev_alloc<uint8_t>((size_t)direct_max_ * (n / 4) * 192);
+                    ln.direct_part = dev_alloc<uint8_t>((size_t)direct_max_ * 128 * 192);
                     ln.direct_cnt = dev_alloc<unsigned>(direct_max_);
                     B200_CUDA_CHECK(cudaMemsetAsync(ln.direct_cnt, 0, direct_max_ * sizeof(unsigned), st));
                 }
                 B200_CUDA_CHECK(cudaStreamSynchronize(st));
             } else {
-                cudaGetLastError();
-                direct_max_ = 0;
+                direct_max_ = direct_c_ = 0;
             }
         }
         // the 4096 domain = first half of the bit-reversed 8192 roots (kzg/src/eip_4844.rs:463, 976)
@@ -445,7 +464,7 @@ KzgSettingsDev::~KzgSettingsDev() {
 int KzgSettingsDev::lagrange_msm(int lane, MsmEngine& eng, int n, uint8_t* out48, cudaStream_t st) {
     Lane& ln = lanes_[lane % kLanes];
     if (lag_direct_ && n <= direct_max_) {
-        launch_direct_msm_compressed(ln.scalars, lag_direct_, ln.direct_part, ln.direct_cnt, out48, n, (int)kFieldElementsPerBlob, st);
+        launch_direct_msm_compressed(ln.scalars, lag_direct_, ln.direct_part, ln.direct_cnt, out48, n, (int)kFieldElementsPerBlob, direct_c_, st);
         return 1;
     }
     eng.run(ln.scalars, kFieldElementsPerBlob, n, false, ln.out_jac, st);
@@ -532,7 +551,7 @@ void KzgSettingsDev::x_ext_fft_columns(void* out_dev, cudaStream_t st) {
 }
 
 void KzgSettingsDev::ensure_fk20(cudaStream_t st) {
-    if (fk_msm_) return;
+    if (fk_ready_) return;
     fk_batch_ = std::max(1, std::min(max_batch_, env_int_local("B200_FK20_BATCH", 64)));
     const int npts = kCellSize * kFkK2;  // 8192
     uint8_t* x_ext = dev_alloc<uint8_t>((size_t)npts * 144);
@@ -544,26 +563,25 @@ void KzgSettingsDev::ensure_fk20(cudaStream_t st) {
     fs_->fft_g1(x_ext, points, kFkK2, false, kCellSize, st);
     k_fk_table<<<div_up(npts, 64), 64, 0, st>>>(points, table);
     B200_LAUNCH_CHECK();
-    MsmConfig cfg;
-    cfg.c = env_int_local("B200_FK20_C", 8);
-    cfg.W = (256 + cfg.c - 1) / cfg.c;
-    cfg.fixed = true;
-    cfg.n = kCellSize;
-    cfg.max_batch = fk_batch_ * kFkK2;
-    cfg.L = 64;
-    cfg.bases_period = kFkK2;
-    fk_msm_.reset(new MsmEngine(cfg, table, false, st));
-    // direct lookup table of every digit multiple (fk20_direct.cu): 3 GiB of HBM for a lincomb stage without buckets.
-    // B200_FK20_DIRECT=0 keeps the bucket engine (A/B, or when HBM is short); the table needs the engine's 8-bit rows.
-    if (cfg.c == 8 && env_int_local("B200_FK20_DIRECT", 1)) {
-        void* p = nullptr;
-        if (cudaMalloc(&p, fk_direct_table_bytes()) == cudaSuccess) {
-            fk_direct_ = p;
-            launch_fk_direct_build(fk_msm_->table(), fk_direct_, st);
-        } else {
-            cudaGetLastError();   // not enough memory: the bucket engine serves the lincombs
-        }
+    // direct lookup table of every digit multiple (fk20_direct.cu): 13-bit windows, 60 GiB of HBM for a lincomb stage of
+    // 64 x 20 additions without buckets (B200_FK20_DIRECT_BITS; narrower when HBM is short).  B200_FK20_DIRECT=0 or a failed
+    // allocation: the bucket engine (8-bit windows, one bucket set per lincomb) serves the lincombs.
+    if (env_int_local("B200_FK20_DIRECT", 1)) {
+        fk_direct_c_ = pick_direct_bits(npts, env_int_local("B200_FK20_DIRECT_BITS", 13));
+        if (fk_direct_c_) fk_direct_ = build_direct_table(table, kCellSize, kFkK2, fk_direct_c_, st);
     }
+    if (!fk_direct_) {
+        MsmConfig cfg;
+        cfg.c = env_int_local("B200_FK20_C", 8);
+        cfg.W = (256 + cfg.c - 1) / cfg.c;
+        cfg.fixed = true;
+        cfg.n = kCellSize;
+        cfg.max_batch = fk_batch_ * kFkK2;
+        cfg.L = 64;
+        cfg.bases_period = kFkK2;
+        fk_msm_.reset(new MsmEngine(cfg, table, false, st));
+    }
+    fk_ready_ = true;
     fk_a_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kCellSize * kFkK2 * 32);
     fk_b_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kCellSize * kFkK2 * 32);
     fk_pts_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kFkK2 * 144);
@@ -585,7 +603,7 @@ void KzgSettingsDev::compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* p
     B200_LAUNCH_CHECK();
     fs_->fft_fr(cells_a_, cells_b_, kFieldElementsPerBlob, true, n, st);
     fk20_from_mono(cells_b_, kFieldElementsPerBlob, n, proofs48, st);
-    launches_ = 8 + fk_msm_->launches_per_run() + 2 * 9;
+    launches_ = 8 + (fk_direct_ ? 1 : fk_msm_->launches_per_run()) + 2 * 9;
 }
 // compute_fk20_proofs (kzg/src/das.rs:660-696) from polynomials in monomial form: blob b's coefficients 0..4095 start at
 // mono + b * stride Fr (Montgomery)
@@ -600,7 +618,7 @@ void KzgSettingsDev::fk20_from_mono(const void* mono, size_t stride, int n, uint
     k_fk_transpose<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)fk_b_, (uint8_t*)fk_a_, tt, (const uint8_t*)fs_->inv_pow2_dev(7));
     B200_LAUNCH_CHECK();
     // g1_lincomb_batch: 128 lincombs of 64 fixed points per blob (kzg/src/das.rs:676-680)
-    if (fk_direct_) launch_fk_direct_lincomb(fk_a_, fk_direct_, fk_pts_, n * kFkK2, st);
+    if (fk_direct_) launch_direct_lincomb(fk_a_, fk_direct_, fk_pts_, n * kFkK2, kFkK2, kCellSize, fk_direct_c_, st);
     else fk_msm_->run(fk_a_, kCellSize, n * kFkK2, false, fk_pts_, st);
     // h = inverse fft_g1, upper half := identity, forward fft_g1 (:682-695)
     fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, true, n, st, /*apply_scale=*/false);

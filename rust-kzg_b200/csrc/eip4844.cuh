@@ -98,10 +98,12 @@ public:
 
 private:
     void ensure_fk20(cudaStream_t st);
-    std::unique_ptr<MsmEngine> fk_msm_;
+    std::unique_ptr<MsmEngine> fk_msm_;   // bucket engine of the lincombs, only when there is no direct table
+    bool fk_ready_ = false;
     int fk_batch_ = 0;
     void *fk_a_ = nullptr, *fk_b_ = nullptr, *fk_pts_ = nullptr;
     void* fk_direct_ = nullptr;  // every digit multiple of the 8192 column points (fk20_direct.cu), or nullptr
+    int fk_direct_c_ = 0;        // its window width
     int max_batch_;
     int launches_ = 0;
     std::unique_ptr<FFTSettingsDev> fs_;
@@ -117,7 +119,8 @@ private:
         unsigned* direct_cnt = nullptr;  // per-vector completion counters of its fused kernel (zero between launches)
     } lanes_[kLanes];
     void* lag_direct_ = nullptr;   // every digit multiple of the 4096 Lagrange points (direct small-batch MSM), or nullptr
-    int direct_max_ = 0;           // largest batch the direct form serves (larger ones fill the machine: bucket engine)
+    int direct_max_ = 0;           // largest batch the direct form serves (0: none; larger ones go to the bucket engine)
+    int direct_c_ = 0;             // window width of lag_direct_
     // sum over the Lagrange points for n vectors of canonical scalars in ln.scalars -> out48 (compressed); returns launches
     int lagrange_msm(int lane, MsmEngine& eng, int n, uint8_t* out48, cudaStream_t st);
     void* lagrange_jac_ = nullptr;
@@ -142,16 +145,16 @@ private:
 size_t check_challenge_ws_bytes(int m, int n);
 void launch_check_challenge_inputs(uint8_t* workspace_dev, const uint8_t* commitments48, int m, const uint8_t* cells, const uint8_t* proofs48,
                                    int n, int* status, cudaStream_t st);
-// FK20 lincombs by direct table lookup (fk20_direct.cu): rows = the engine's [32][8192] fixed-base rows for c = 8
-size_t fk_direct_table_bytes();
-void launch_fk_direct_build(const void* rows, void* table, cudaStream_t st);
-void launch_fk_direct_lincomb(const void* scalars, const void* table, void* out_jac, int nvec, cudaStream_t st);
-// the same direct tables for small batches of 4096-term MSMs over the Lagrange points (fk20_direct.cu)
-size_t direct_table_bytes(size_t npts);
-void launch_direct_build(const void* rows, void* table, size_t npts, cudaStream_t st);
-void launch_direct_msm(const void* scalars, const void* table, void* partials, void* out_jac, int nvec, int npts, cudaStream_t st);
+// fixed-base lincombs by direct table lookup (fk20_direct.cu): every signed digit multiple of every c-bit window of every
+// point; rows = an MSM engine's [W][npts] fixed-base rows for the same window width (W = direct_windows(c))
+int direct_windows(int c);
+size_t direct_table_bytes(size_t npts, int c);
+void launch_direct_build(const void* rows, size_t row_stride, void* table, size_t npts, int c, cudaStream_t st);
+// FK20: vector v is a lincomb of the npv points of column block (v mod period); Jacobian results
+void launch_direct_lincomb(const void* scalars, const void* table, void* out_jac, int nvec, int period, int npv, int c, cudaStream_t st);
+// npts-term MSMs over one point set, compressed results; partials: nvec * 128 * 192 bytes, counters: nvec zeroed words
 void launch_direct_msm_compressed(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, int nvec,
-                                  int npts, cudaStream_t st);
+                                  int npts, int c, cudaStream_t st);
 // test hook (verify.cu): sum k_i P_i through the quad / GLV scalar multiplication used by the verifiers and fft_g1
 void selftest_lincomb_quads(const void* points_affine_dev, const void* scalars_mont_dev, int n, void* out_jac_dev, cudaStream_t st);
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input

@@ -295,8 +295,9 @@ def test_helper_exports_compute_challenge_vectors(B, K, vectors, golden_blobs):
 
 
 def test_direct_small_batch_msm_matches_bucket_engine(B, K, oracle_settings):
-    """batches of up to 24 blobs take the direct-lookup MSM (csrc/fk20_direct.cu: no buckets, two launches), larger ones the
-    bucket engine; both must give the oracle's bytes, also for adversarial blob contents, and agree at the switch-over"""
+    """batches of up to B200_BLOB_DIRECT blobs take the direct-lookup MSM (csrc/fk20_direct.cu: no buckets, one launch), larger
+    ones the bucket engine; every table width (13-bit default, 11 and 8 when HBM is short) and the bucket engine must give the
+    oracle's bytes, also for adversarial blob contents, and agree at the switch-over"""
     import os
     rng = np.random.default_rng(55)
     blobs = rng.integers(0, 256, size=(26, 4096, 32), dtype=np.uint8)
@@ -309,18 +310,46 @@ def test_direct_small_batch_msm_matches_bucket_engine(B, K, oracle_settings):
     zs = blobs[0].reshape(4096, 32)[:26].copy()
     want_c = [K.blob_to_kzg_commitment(blobs[i].tobytes(), oracle_settings) for i in range(26)]
     want_p = [K.compute_kzg_proof(blobs[i].tobytes(), zs[i].tobytes(), oracle_settings) for i in (0, 2, 3, 25)]
-    for direct in ("24", "0"):
+    for direct, bits in (("24", "13"), ("24", "11"), ("64", "8"), ("0", "13")):
         os.environ["B200_BLOB_DIRECT"] = direct
+        os.environ["B200_BLOB_DIRECT_BITS"] = bits
         try:
             ts = B.KZGSettings.load_trusted_setup_file()
         finally:
-            del os.environ["B200_BLOB_DIRECT"]
+            del os.environ["B200_BLOB_DIRECT"], os.environ["B200_BLOB_DIRECT_BITS"]
         for n in (1, 3, 24, 25, 26):
             got = ts.blob_to_kzg_commitment_batch(blobs[:n])
-            assert [bytes(g) for g in got] == want_c[:n], (direct, n)
+            assert [bytes(g) for g in got] == want_c[:n], (direct, bits, n)
         proofs, ys = ts.compute_kzg_proof_batch(blobs[:26], zs)
         for k, i in enumerate((0, 2, 3, 25)):
-            assert (bytes(proofs[i]), bytes(ys[i])) == tuple(want_p[k]), (direct, i)
+            assert (bytes(proofs[i]), bytes(ys[i])) == tuple(want_p[k]), (direct, bits, i)
         p1, y1 = ts.compute_kzg_proof(blobs[2], zs[2])      # single call: a batch of one
         assert (p1, y1) == tuple(want_p[1])
+        ts.free()
+
+
+def test_fk20_lincomb_table_widths_agree(B, K, oracle_settings):
+    """the FK20 lincomb stage by direct lookups on 13- / 11- / 8-bit tables and on the bucket engine (B200_FK20_DIRECT=0):
+    identical cell proofs, and blob 0's equal the oracle's (kzg/src/das.rs:660-696)"""
+    import os
+    rng = np.random.default_rng(56)
+    blobs = rng.integers(0, 256, size=(3, 4096, 32), dtype=np.uint8)
+    blobs[:, :, 0] = 0
+    blobs[1, :, :] = 0
+    blobs[1, :, 31] = 1
+    blobs = blobs.reshape(3, -1)
+    _, want = K.compute_cells_and_kzg_proofs(blobs[0].tobytes(), oracle_settings)
+    ref = None
+    for direct, bits in (("1", "13"), ("1", "11"), ("1", "8"), ("0", "8")):
+        os.environ["B200_FK20_DIRECT"] = direct
+        os.environ["B200_FK20_DIRECT_BITS"] = bits
+        try:
+            ts = B.KZGSettings.load_trusted_setup_file()
+            got = ts.compute_cell_proofs_batch(blobs)      # the tables are built on first use
+        finally:
+            del os.environ["B200_FK20_DIRECT"], os.environ["B200_FK20_DIRECT_BITS"]
+        assert [bytes(g) for g in got[0]] == [bytes(w) for w in want], (direct, bits)
+        if ref is None:
+            ref = got.copy()
+        assert np.array_equal(got, ref), (direct, bits)
         ts.free()
