@@ -550,7 +550,7 @@ def adversarial_msm(B, K, L, torch, pts, uniform_ms):
     for kind in ("all_equal", "r_minus_1", "below_2^64", "ten_percent_zero"):
         sc = np.ascontiguousarray(adversarial_scalars(K, rng, n, kind))
         d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
-        ms = timed_events(torch, lambda: msm.mult_device(d_out.data_ptr(), n, d_sc.data_ptr(), 1, 0), reps=3, warm=1)
+        ms = timed_events(torch, lambda: msm.mult_device(d_out.data_ptr(), n, d_sc.data_ptr(), 1, 0), reps=5, warm=3)
         ok = K.p1_compress(d_out.cpu().numpy().view(np.uint64)) == K.p1_compress(folded_expectation(K, L, sc, os.cpu_count() or 1))
         out[kind] = {"ms": ms, "vs_uniform": ms / uniform_ms, "parity_ok": bool(ok)}
         worst = max(worst, ms / uniform_ms)
