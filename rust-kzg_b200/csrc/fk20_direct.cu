@@ -172,13 +172,19 @@ void launch_direct_lincomb(const void* scalars, const void* table, void* out_jac
 // Batches of npts-term MSMs over the Lagrange points (blob_to_kzg_commitment / compute_kzg_proof) by the same direct
 // lookups.  The bucket pipeline is a chain of ~20 dependent, mostly tiny kernels whose reduction tail (bucket combine,
 // marginal sums, weighted sums) costs ~0.45 ms however little work there is, and that latency is what concurrent
-// single-blob callers queue behind (coalesce.cuh).  Direct form: m CTAs of 128 threads per vector, thread t of the team
-// takes the items t, t + 128 m, ... (P of them), a warp tree and a tree over the CTA's four warps leave one partial sum per
-// CTA; the CTA that finishes a vector's last partial (a counter per vector) folds the m partials, inverts ZZZ and writes the
-// 48-byte compressed result.  One launch per batch; chain length P + three trees + one inversion.
+// single-blob callers queue behind (coalesce.cuh).  Direct form: the items of a vector are cut into SLICES of 128 (thread t
+// of a CTA takes item 128 s + t of slice s), and the nvec * spv slices of the whole batch are dealt out evenly and
+// contiguously to the G CTAs of ONE wave (two CTAs per SM): every SM gets the same number of additions whatever the batch
+// size; a CTA whose range crosses a vector boundary works on both vectors in turn.  Per (CTA, vector) piece: the chain of
+// additions, a warp tree and a tree over the CTA's four warps leave one partial sum; the CTA that finishes a vector's last
+// partial (a counter per vector) folds its partials, inverts ZZZ and writes the 48-byte compressed result.  One launch per
+// batch; chain length + three trees + one inversion.
+__device__ __forceinline__ uint32_t direct_cta_of(uint32_t slice, uint32_t S, uint32_t G) {   // the CTA whose range holds `slice`
+    return (uint32_t)((((uint64_t)slice + 1) * G + S - 1) / S) - 1;
+}
 template <class AR>
 __global__ void __launch_bounds__(128) k_direct_msm(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
-                                                    uint8_t* __restrict__ partials, int npts, int W, int c, int m, int P,
+                                                    uint8_t* __restrict__ partials, int npts, int W, int c, uint32_t spv, uint32_t S,
                                                     unsigned* __restrict__ counters, uint8_t* __restrict__ out48,
                                                     unsigned long long* trace) {
     unsigned long long ts[8];
@@ -187,93 +193,86 @@ __global__ void __launch_bounds__(128) k_direct_msm(const uint8_t* __restrict__ 
     __shared__ __align__(16) uint8_t sh[4 * 192];
     __shared__ int sh_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const size_t vec = (size_t)blockIdx.x / m;
-    const uint32_t tv = (uint32_t)(blockIdx.x % m) * 128u + threadIdx.x;
-    const uint32_t* sc = reinterpret_cast<const uint32_t*>(scalars + vec * npts * 32);
-    xyzz_t a2 = direct_chain<AR>(sc, table, tv, 128u * m, P, W, c);
-    stamp(1);
-    // warp tree, then the CTA's four warp sums on four quads of warp 0: one partial per CTA
-    fp_t q = seg_sum_quad(a2, 32);
-    stamp(2);
-    if (lane < 4) store_field(sh + wid * 192 + quad_store_offset(), q);
-    __syncthreads();
-    if (wid == 0) {
-        fp_t cq = lane < 16 ? load_field<fp_t>(sh + (lane >> 2) * 192 + quad_store_offset()) : fp_t::zero();
-        fp_t t = quad_tree(cq, 16);
-        if (lane < 4) store_field(partials + (size_t)blockIdx.x * 192 + quad_store_offset(), t);
-    }
-    stamp(3);
-    // last CTA of this vector?  (partials of a vector are contiguous)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned done = atomicAdd(&counters[vec], 1u);
-        sh_last = done == (unsigned)m - 1;
-        if (sh_last) counters[vec] = 0;                       // ready for the next launch on this lane
-    }
-    __syncthreads();
-    if (!sh_last) return;
-    __threadfence();
-    // fold the m <= 128 partials with the CTA's 128 threads
-    const uint8_t* base = partials + vec * m * 192;
-    xyzz_t a;
-    if ((int)threadIdx.x < m) {
-        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)threadIdx.x * 192);
-        uint4 tmp[12];
-#pragma unroll
-        for (int k = 0; k < 12; k++) tmp[k] = __ldcg(src + k);   // written by other CTAs: read through L2
-        const uint32_t* wv = reinterpret_cast<const uint32_t*>(tmp);
-#pragma unroll
-        for (int k = 0; k < 12; k++) { a.x.v[k] = wv[k]; a.y.v[k] = wv[12 + k]; a.zzz.v[k] = wv[24 + k]; a.zz.v[k] = wv[36 + k]; }
-    } else {
-        a = xyzz_t::inf();
-    }
-    __syncthreads();                                          // sh is reused below
-    stamp(4);
-    fp_t tot;
-    if (m > 32) {
-        fp_t q2 = seg_sum_quad(a, 32);
-        if (lane < 4) store_field(sh + wid * 192 + quad_store_offset(), q2);
+    const uint32_t G = gridDim.x;
+    const uint32_t b0 = (uint32_t)((uint64_t)blockIdx.x * S / G), b1 = (uint32_t)(((uint64_t)blockIdx.x + 1) * S / G);
+#pragma unroll 1
+    for (uint32_t vec = b0 / spv; vec * spv < b1; vec++) {
+        const uint32_t v0 = vec * spv, s0 = (b0 > v0 ? b0 : v0) - v0, s1 = (b1 < v0 + spv ? b1 : v0 + spv) - v0;
+        const uint32_t* sc = reinterpret_cast<const uint32_t*>(scalars + (size_t)vec * npts * 32);
+        xyzz_t a2 = direct_chain<AR>(sc, table, s0 * 128u + threadIdx.x, 128u, (int)(s1 - s0), W, c);
+        stamp(1);
+        // warp tree, then the CTA's four warp sums on four quads of warp 0: one partial per (CTA, vector)
+        fp_t q = seg_sum_quad(a2, 32);
+        stamp(2);
+        if (lane < 4) store_field(sh + wid * 192 + quad_store_offset(), q);
         __syncthreads();
-        if (wid != 0) return;
-        fp_t c2 = lane < 16 ? load_field<fp_t>(sh + (lane >> 2) * 192 + quad_store_offset()) : fp_t::zero();
-        tot = quad_tree(c2, 16);                              // quad 0: (X, Y, ZZ, ZZZ) of the vector's sum
-    } else {
-        if (wid != 0) return;                                 // one warp holds every partial
-        tot = seg_sum_quad(a, 32);
-    }
-    stamp(5);
-    // compressed form (blst_p1_compress): x = X / ZZ, y = Y / ZZZ with 1/ZZ = ZZZ^-2 ZZ^2; one inversion, uniform over the warp
-    const fp_t zz = shfl_idx_fp(tot, 2), zzz = shfl_idx_fp(tot, 3);
-    const bool inf = zz.is_zero();
-    const fp_t izzz = (inf ? fp_t::one() : zzz).inverse();
-    stamp(6);
-    const fp_t izz = izzz.sqr() * zz.sqr();
-    const fp_t coord = lane == 0 ? tot * izz : tot * izzz;    // lane 0: x, lane 1: y
-    const fp_t yv = shfl_idx_fp(coord, 1);
-    if (lane == 0) {
-        cc::affine_t r;
+        const uint32_t first_cta = direct_cta_of(v0, S, G), m = direct_cta_of(v0 + spv - 1, S, G) - first_cta + 1;
+        uint8_t* base = partials + (size_t)vec * 128 * 192;   // m <= 128 slots per vector
+        if (wid == 0) {
+            fp_t cq = lane < 16 ? load_field<fp_t>(sh + (lane >> 2) * 192 + quad_store_offset()) : fp_t::zero();
+            fp_t t = quad_tree(cq, 16);
+            if (lane < 4) store_field(base + (size_t)(blockIdx.x - first_cta) * 192 + quad_store_offset(), t);
+        }
+        stamp(3);
+        // last CTA of this vector?
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned done = atomicAdd(&counters[vec], 1u);
+            sh_last = done == m - 1;
+            if (sh_last) counters[vec] = 0;                   // ready for the next launch on this lane
+        }
+        __syncthreads();
+        if (!sh_last) continue;                               // CTA-uniform
+        __threadfence();
+        // fold the m <= 128 partials with the CTA's 128 threads
+        xyzz_t a;
+        if (threadIdx.x < m) {
+            const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)threadIdx.x * 192);
+            uint4 tmp[12];
 #pragma unroll
-        for (int k = 0; k < 12; k++) { r.x.v[k] = inf ? 0u : coord.v[k]; r.y.v[k] = inf ? 0u : yv.v[k]; }
-        cc::affine_compress(out48 + vec * 48, r);
-        stamp(7);
-        if (trace && vec == 0)
-            for (int k = 0; k < 8; k++) trace[k] = ts[k];
+            for (int k = 0; k < 12; k++) tmp[k] = __ldcg(src + k);   // written by other CTAs: read through L2
+            const uint32_t* wv = reinterpret_cast<const uint32_t*>(tmp);
+#pragma unroll
+            for (int k = 0; k < 12; k++) { a.x.v[k] = wv[k]; a.y.v[k] = wv[12 + k]; a.zzz.v[k] = wv[24 + k]; a.zz.v[k] = wv[36 + k]; }
+        } else {
+            a = xyzz_t::inf();
+        }
+        stamp(4);
+        fp_t tot = fp_t::zero();
+        if (m > 32) {
+            fp_t q2 = seg_sum_quad(a, 32);
+            if (lane < 4) store_field(sh + wid * 192 + quad_store_offset(), q2);
+            __syncthreads();
+            if (wid == 0) {
+                fp_t c2 = lane < 16 ? load_field<fp_t>(sh + (lane >> 2) * 192 + quad_store_offset()) : fp_t::zero();
+                tot = quad_tree(c2, 16);                      // quad 0: (X, Y, ZZ, ZZZ) of the vector's sum
+            }
+        } else if (wid == 0) {
+            tot = seg_sum_quad(a, 32);                        // one warp holds every partial
+        }
+        stamp(5);
+        if (wid == 0) {
+            // compressed form (blst_p1_compress): x = X / ZZ, y = Y / ZZZ with 1/ZZ = ZZZ^-2 ZZ^2; one inversion, uniform over the warp
+            const fp_t zz = shfl_idx_fp(tot, 2), zzz = shfl_idx_fp(tot, 3);
+            const bool inf = zz.is_zero();
+            const fp_t izzz = (inf ? fp_t::one() : zzz).inverse();
+            stamp(6);
+            const fp_t izz = izzz.sqr() * zz.sqr();
+            const fp_t coord = lane == 0 ? tot * izz : tot * izzz;    // lane 0: x, lane 1: y
+            const fp_t yv = shfl_idx_fp(coord, 1);
+            if (lane == 0) {
+                cc::affine_t r;
+#pragma unroll
+                for (int k = 0; k < 12; k++) { r.x.v[k] = inf ? 0u : coord.v[k]; r.y.v[k] = inf ? 0u : yv.v[k]; }
+                cc::affine_compress(out48 + (size_t)vec * 48, r);
+                stamp(7);
+                if (trace && vec == 0)
+                    for (int k = 0; k < 8; k++) trace[k] = ts[k];
+            }
+        }
+        __syncthreads();                                      // sh is reused by the next piece
     }
-}
-// CTAs per vector: the largest divisor m <= 128 of the (npts * W / 128) item slices of a vector that keeps the whole batch in
-// one wave of resident CTAs (two per SM at ~200 registers); P = slices / m items per thread
-static int direct_ctas_per_vector(int nvec, int slices) {
-    static const int wave = [] {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        return 2 * sms;
-    }();
-    int best = 1;
-    for (int m = 1; m <= 128 && m <= slices; m++)
-        if (slices % m == 0 && (long long)nvec * m <= wave) best = m;
-    return best;
 }
 // scalars: nvec x npts canonical little-endian 32-byte scalars; partials: workspace of nvec * 128 XYZZ points (192 bytes);
 // counters: nvec zero-initialised words (left zero); out48: nvec compressed points
@@ -281,21 +280,34 @@ void launch_direct_msm_compressed(const void* scalars, const void* table, void* 
                                   int npts, int c, cudaStream_t st) {
     const int W = direct_windows(c);
     if (((size_t)npts * W) % 128) throw CudaError(-1, "direct MSM: items per vector must fill whole CTAs");
-    const int slices = (int)((size_t)npts * W / 128);
-    const int m = direct_ctas_per_vector(nvec, slices), P = slices / m;
+    static const int wave = [] {                              // resident CTAs: two per SM at ~200 registers
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return 2 * sms;
+    }();
+    const uint32_t spv = (uint32_t)((size_t)npts * W / 128), S = spv * (uint32_t)nvec;
+    // at least five slices per CTA, and no vector cut into more than the 128 pieces its fold handles
+    uint32_t G = std::min<uint32_t>(std::min<uint32_t>((uint32_t)wave, 128u * (uint32_t)nvec), std::max<uint32_t>(1u, S / 5));
+    auto cta_of = [&](uint32_t slice) { return (uint32_t)((((uint64_t)slice + 1) * G + S - 1) / S) - 1; };
+    for (;; G--) {
+        uint32_t worst = 0;
+        for (uint32_t v = 0; v < (uint32_t)nvec; v++) worst = std::max(worst, cta_of(v * spv + spv - 1) - cta_of(v * spv) + 1);
+        if (worst <= 128 || G == 1) break;
+    }
     // B200_DIRECT_TRACE=1 (debugging aid): %globaltimer stamps of the CTA that finishes vector 0, printed after a sync
     static unsigned long long* trace = [] {
         unsigned long long* t = nullptr;
         if (getenv("B200_DIRECT_TRACE") && atoi(getenv("B200_DIRECT_TRACE"))) cudaMallocManaged(&t, 8 * sizeof(unsigned long long));
         return t;
     }();
-    k_direct_msm<ArCall><<<(unsigned)((size_t)nvec * m), 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)partials,
-                                                                     npts, W, c, m, P, counters, out48, trace);
+    k_direct_msm<ArCall><<<G, 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)partials, npts, W, c, spv, S, counters,
+                                           out48, trace);
     B200_LAUNCH_CHECK();
     if (trace) {
         cudaStreamSynchronize(st);
-        fprintf(stderr, "direct trace (ns) nvec=%d c=%d m=%d P=%d: loop %llu warp-tree %llu cta-tree %llu ticket+load %llu fold %llu inverse %llu compress %llu\n",
-                nvec, c, m, P, trace[1] - trace[0], trace[2] - trace[1], trace[3] - trace[2], trace[4] - trace[3], trace[5] - trace[4],
+        fprintf(stderr, "direct trace (ns) nvec=%d c=%d G=%u slices/CTA=%.1f: loop %llu warp-tree %llu cta-tree %llu ticket+load %llu fold %llu inverse %llu compress %llu\n",
+                nvec, c, G, (double)S / G, trace[1] - trace[0], trace[2] - trace[1], trace[3] - trace[2], trace[4] - trace[3], trace[5] - trace[4],
                 trace[6] - trace[5], trace[7] - trace[6]);
     }
 }
