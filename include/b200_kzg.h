@@ -210,6 +210,11 @@ B200_API C_KZG_RET compute_verify_cell_kzg_proof_batch_challenge(blst_fr *challe
                                                                  const Bytes48 *proofs_bytes, uint64_t num_cells);
 B200_API C_KZG_RET b200_compute_cells_batch(Cell *cells, const Blob *blobs, size_t n, const KZGSettings *s);
 B200_API C_KZG_RET b200_compute_cell_proofs_batch(KZGProof *proofs, const Blob *blobs, size_t n, const KZGSettings *s);
+/* both outputs of compute_cells_and_kzg_proofs (kzg/src/das.rs:244-292) for n blobs in one pass: the blobs are uploaded and
+ * brought to monomial form once, and the cells are copied out while the proofs are still being computed.  Either output
+ * pointer may be NULL, not both; cells = n x 128 Cell, proofs = n x 128 KZGProof.  The single-blob symbol is this with n = 1. */
+B200_API C_KZG_RET b200_compute_cells_and_kzg_proofs_batch(Cell *cells, KZGProof *proofs, const Blob *blobs, size_t n,
+                                                           const KZGSettings *s);
 
 /* Batched extensions: n independent blobs in one launch sequence (BASELINE config 3: 64 blobs).  Any invalid
  * element makes the whole call return C_KZG_BADARGS.  n may exceed the context's batch capacity (chunked). */

@@ -772,15 +772,45 @@ C_KZG_RET b200_compute_cell_proofs_batch(KZGProof* proofs, const Blob* blobs, si
         return rc;
     });
 }
+// cells and FK20 proofs of n blobs in one pass: the blobs cross PCIe once, the monomial form is shared, and the cells
+// (2 KiB x 128 per blob) are copied out on the side stream while the proofs are still being computed
+C_KZG_RET b200_compute_cells_and_kzg_proofs_batch(Cell* cells, KZGProof* proofs, const Blob* blobs, size_t n, const KZGSettings* s) {
+    if (!cells && !proofs) return C_KZG_BADARGS;
+    if (!proofs) return b200_compute_cells_batch(cells, blobs, n, s);
+    if (!cells) return b200_compute_cell_proofs_batch(proofs, blobs, n, s);
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !blobs) return C_KZG_BADARGS;
+        AllLanes lk(*ctx);
+        Stage& g = ctx->stage[0];
+        const int cap = std::min(ctx->max_batch, ctx->dev->fk20_batch(ctx->stream));
+        if (!ctx->d_cells) ctx->d_cells = dev_alloc<uint8_t>((size_t)ctx->max_batch * 128 * 2048);
+        if (!ctx->d_proofs) ctx->d_proofs = dev_alloc<uint8_t>((size_t)ctx->dev->fk20_batch(ctx->stream) * 128 * 48);
+        for (size_t off = 0; off < n; off += cap) {
+            const int m = (int)std::min<size_t>(cap, n - off);
+            B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs + off, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
+            B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, m * sizeof(int), g.stream));
+            ctx->dev->compute_cells_and_proofs(g.d_blobs, m, ctx->d_cells, ctx->d_proofs, g.d_status, g.stream, g.ev_side);
+            // the blob status (Fr::from_bytes of every element) and the cells leave on the side stream under the FK20 kernels;
+            // nothing is written to the caller's arrays when a blob is invalid (the reference fails before any output)
+            B200_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.ev_side, 0));
+            B200_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status(), g.d_status, m * sizeof(int), cudaMemcpyDeviceToHost, g.side));
+            B200_CUDA_CHECK(cudaStreamSynchronize(g.side));
+            const bool bad = any_set(ctx->h_status(), m);
+            if (!bad)
+                B200_CUDA_CHECK(cudaMemcpyAsync(cells + off * 128, ctx->d_cells, (size_t)m * 128 * 2048, cudaMemcpyDeviceToHost, g.side));
+            B200_CUDA_CHECK(cudaStreamSynchronize(g.side));
+            B200_CUDA_CHECK(cudaStreamSynchronize(g.stream));
+            if (bad) return C_KZG_BADARGS;
+            B200_CUDA_CHECK(cudaMemcpy(proofs + off * 128, ctx->d_proofs, (size_t)m * 128 * 48, cudaMemcpyDeviceToHost));
+        }
+        return C_KZG_OK;
+    });
+}
 // kzg/src/eth/c_bindings.rs:134-199 (eip7594 macro): either output may be NULL, not both (kzg/src/das.rs:250-252)
 C_KZG_RET compute_cells_and_kzg_proofs(Cell* cells, KZGProof* proofs, const Blob* blob, const KZGSettings* s) {
-    if (!cells && !proofs) return C_KZG_BADARGS;
-    if (cells) {
-        C_KZG_RET rc = b200_compute_cells_batch(cells, blob, 1, s);
-        if (rc != C_KZG_OK) return rc;
-    }
-    if (proofs) return b200_compute_cell_proofs_batch(proofs, blob, 1, s);
-    return C_KZG_OK;
+    if (!blob) return C_KZG_BADARGS;
+    return b200_compute_cells_and_kzg_proofs_batch(cells, proofs, blob, 1, s);
 }
 
 // ---- verification (blst/src/eip_4844.rs:383-471) -----------------------------------------------------------------

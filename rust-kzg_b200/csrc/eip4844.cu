@@ -605,6 +605,19 @@ void KzgSettingsDev::compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* p
     fk20_from_mono(cells_b_, kFieldElementsPerBlob, n, proofs48, st);
     launches_ = 8 + (fk_direct_ ? 1 : fk_msm_->launches_per_run()) + 2 * 9;
 }
+// compute_cells_and_kzg_proofs with both outputs (kzg/src/das.rs:244-292): one pass from blob bytes to the monomial form, shared
+// by the cells (NTT-8192) and the FK20 proofs.  cells_done is recorded once cells_out is complete, so the caller can copy the
+// cells out on another stream while the proofs -- 80 % of the call -- are still running.
+void KzgSettingsDev::compute_cells_and_proofs(const uint8_t* blobs, int n, uint8_t* cells_out, uint8_t* proofs48, int* status,
+                                              cudaStream_t st, cudaEvent_t cells_done) {
+    ensure_fk20(st);
+    if (n < 1 || n > fk_batch_ || n > max_batch_) throw CudaError(-1, "blob batch exceeds the FK20 capacity");
+    compute_cells(blobs, n, cells_out, status, st);
+    if (cells_done) B200_CUDA_CHECK(cudaEventRecord(cells_done, st));
+    // cells_a_ still holds the zero-padded monomial form (8192 Fr per blob): fft_fr is out of place
+    fk20_from_mono(cells_a_, 2 * kFieldElementsPerBlob, n, proofs48, st);
+    launches_ = 7 + 5 + (fk_direct_ ? 1 : fk_msm_->launches_per_run()) + 2 * 9;
+}
 // compute_fk20_proofs (kzg/src/das.rs:660-696) from polynomials in monomial form: blob b's coefficients 0..4095 start at
 // mono + b * stride Fr (Montgomery)
 void KzgSettingsDev::fk20_from_mono(const void* mono, size_t stride, int n, uint8_t* proofs48, cudaStream_t st) {

@@ -52,6 +52,9 @@ public:
     // FK20 proofs of compute_cells_and_kzg_proofs (kzg/src/das.rs:276-289, 660-696): n x 128 proofs x 48 bytes,
     // n <= fk20_batch().  The 128 x 64 table of x_ext_fft_columns is built on first use.
     void compute_cell_proofs(const uint8_t* blobs, int n, uint8_t* proofs48, int* status, cudaStream_t st);
+    // both at once: the blob -> monomial pass is shared; cells_done (may be nullptr) is recorded when cells_out is complete
+    void compute_cells_and_proofs(const uint8_t* blobs, int n, uint8_t* cells_out, uint8_t* proofs48, int* status, cudaStream_t st,
+                                  cudaEvent_t cells_done);
     int fk20_batch(cudaStream_t st) { ensure_fk20(st); return fk_batch_; }
     // the 128 x 64 blst_p1 of FsKZGSettings::x_ext_fft_columns (blst/src/types/kzg_settings.rs:84-101), row-major, into a
     // DEVICE buffer of 128 * 64 * 144 bytes (for the host-side KZGSettings struct; synchronises st)

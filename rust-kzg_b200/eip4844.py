@@ -48,6 +48,7 @@ def _L():
             "compute_cells_and_kzg_proofs": (ci, [vp, vp, vp, S]),
             "b200_compute_cells_batch": (ci, [vp, vp, sz, S]),
             "b200_compute_cell_proofs_batch": (ci, [vp, vp, sz, S]),
+            "b200_compute_cells_and_kzg_proofs_batch": (ci, [vp, vp, vp, sz, S]),
             "verify_kzg_proof": (ci, [vp, vp, vp, vp, vp, S]),
             "verify_blob_kzg_proof": (ci, [vp, vp, vp, vp, S]),
             "verify_blob_kzg_proof_batch": (ci, [vp, vp, vp, vp, sz, S]),
@@ -252,6 +253,18 @@ class KZGSettings:
         if rc != C_KZG_OK:
             raise KzgError(rc, "compute_cell_proofs_batch")
         return out
+
+    def compute_cells_and_kzg_proofs_batch(self, blobs, cells_out=None, proofs_out=None):
+        """both outputs for n blobs in one pass -> (n,128,2048) cells, (n,128,48) proofs; caller-owned arrays are filled in place"""
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, BYTES_PER_BLOB)
+        n = blobs.shape[0]
+        cells = np.zeros((n, 128, 2048), np.uint8) if cells_out is None else cells_out
+        proofs = np.zeros((n, 128, 48), np.uint8) if proofs_out is None else proofs_out
+        assert cells.flags.c_contiguous and proofs.flags.c_contiguous and cells.nbytes == n * 128 * 2048 and proofs.nbytes == n * 128 * 48
+        rc = _L().b200_compute_cells_and_kzg_proofs_batch(_p(cells), _p(proofs), _p(blobs), n, C.byref(self.c))
+        if rc != C_KZG_OK:
+            raise KzgError(rc, "compute_cells_and_kzg_proofs_batch")
+        return cells, proofs
 
     def compute_cells_batch(self, blobs):
         blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(-1, BYTES_PER_BLOB)

@@ -280,6 +280,29 @@ def test_cell_proofs_batch_matches_oracle(B, K, ts, oracle_settings):
     assert B.lib().compute_cells_and_kzg_proofs(None, None, blobs[0].ctypes.data_as(C.c_void_p), C.byref(ts.c)) == 1
 
 
+def test_cells_and_proofs_batch_in_one_pass(B, K, ts, oracle_settings):
+    """b200_compute_cells_and_kzg_proofs_batch: the shared blob -> monomial pass with the cells copied out under the FK20
+    kernels gives the bytes of the two separate calls and of the oracle; an invalid blob fails the call before any output"""
+    rng = np.random.default_rng(79)
+    blobs = _rand_blobs(rng, 5)
+    cells, proofs = ts.compute_cells_and_kzg_proofs_batch(blobs)
+    assert np.array_equal(cells, ts.compute_cells_batch(blobs))
+    assert np.array_equal(proofs, ts.compute_cell_proofs_batch(blobs))
+    oracle_settings.set_threads(8)
+    oc, op = K.compute_cells_and_kzg_proofs(blobs[4].tobytes(), oracle_settings)
+    oracle_settings.set_threads(1)
+    assert cells[4].tobytes() == b"".join(oc) and proofs[4].tobytes() == b"".join(op)
+    c1, p1 = ts.compute_cells_and_kzg_proofs(blobs[4])           # the c-kzg symbol is the batch of one
+    assert b"".join(c1) == cells[4].tobytes() and b"".join(p1) == proofs[4].tobytes()
+    bad = blobs.copy()
+    bad[2, :32] = 0xff                                            # element 0 of blob 2 >= r
+    cells_out = np.full((5, 128, 2048), 7, np.uint8)
+    proofs_out = np.full((5, 128, 48), 7, np.uint8)
+    with pytest.raises(B.KzgError):
+        ts.compute_cells_and_kzg_proofs_batch(bad, cells_out, proofs_out)
+    assert (cells_out == 7).all() and (proofs_out == 7).all()
+
+
 def test_helper_exports_compute_challenge_vectors(B, K, vectors, golden_blobs):
     """compute_challenge / bytes_to_kzg_commitment / bytes_from_bls_field (blst/src/eip_4844.rs:498-530) on the reference's
     compute_challenge vectors"""
