@@ -230,6 +230,11 @@ B200_API int b200_kzg_max_batch(const KZGSettings *s);
  * Counters since load: out = [batches run, requests served, ns leaders waited for a device lane, ns batches spent on a
  * lane, largest batch].  B200_KZG_COALESCE=1 disables packing, B200_KZG_LANES=k limits the lanes single calls may use. */
 B200_API void b200_kzg_coalesce_stats(const KZGSettings *s, uint64_t out[5]);
+/* Direct-lookup tables held by a settings object: out = [window bits of the Lagrange-point table (13 by default,
+ * 11 / 8 when HBM is short, 0 = none: bucket engine), largest blob batch it serves, window bits of the FK20 column table (0
+ * before the first cell-proof call)].  Knobs: B200_BLOB_DIRECT, B200_BLOB_DIRECT_BITS, B200_FK20_DIRECT, B200_FK20_DIRECT_BITS,
+ * B200_DIRECT_RESERVE_GB (HBM that must stay free beside a table, default 40). */
+B200_API void b200_kzg_direct_tables(const KZGSettings *s, int out[3]);
 B200_API void b200_selftest_sha256(uint8_t out[32], const uint8_t *msg, size_t len, int portable);
 
 /* ---- device self-test hooks: elementwise field / point kernels on host arrays, used by the parity tests ------- */

@@ -1200,6 +1200,17 @@ void b200_kzg_coalesce_stats(const KZGSettings* s, uint64_t out[5]) {
     if (!ctx) return;
     out[0] = ctx->st_batches; out[1] = ctx->st_requests; out[2] = ctx->st_wait_ns; out[3] = ctx->st_exec_ns; out[4] = ctx->st_max_batch;
 }
+// window widths of the direct-lookup tables this settings object holds: out = [Lagrange table bits, largest batch it serves,
+// FK20 column table bits (0 before the first cell-proof call or when the bucket engine serves the lincombs)]
+void b200_kzg_direct_tables(const KZGSettings* s, int out[3]) {
+    auto ctx = find_ctx(s);
+    if (!out) return;
+    out[0] = out[1] = out[2] = 0;
+    if (!ctx) return;
+    out[0] = ctx->dev->direct_bits();
+    out[1] = ctx->dev->direct_max_batch();
+    out[2] = ctx->dev->fk_direct_bits();
+}
 int b200_kzg_max_batch(const KZGSettings* s) {
     auto ctx = find_ctx(s);
     return ctx ? ctx->max_batch : 0;

@@ -56,6 +56,9 @@ public:
     void compute_cells_and_proofs(const uint8_t* blobs, int n, uint8_t* cells_out, uint8_t* proofs48, int* status, cudaStream_t st,
                                   cudaEvent_t cells_done);
     int fk20_batch(cudaStream_t st) { ensure_fk20(st); return fk_batch_; }
+    int direct_bits() const { return lag_direct_ ? direct_c_ : 0; }
+    int direct_max_batch() const { return lag_direct_ ? direct_max_ : 0; }
+    int fk_direct_bits() const { return fk_direct_ ? fk_direct_c_ : 0; }
     // the 128 x 64 blst_p1 of FsKZGSettings::x_ext_fft_columns (blst/src/types/kzg_settings.rs:84-101), row-major, into a
     // DEVICE buffer of 128 * 64 * 144 bytes (for the host-side KZGSettings struct; synchronises st)
     void x_ext_fft_columns(void* out_dev, cudaStream_t st);

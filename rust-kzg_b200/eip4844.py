@@ -49,6 +49,7 @@ def _L():
             "b200_compute_cells_batch": (ci, [vp, vp, sz, S]),
             "b200_compute_cell_proofs_batch": (ci, [vp, vp, sz, S]),
             "b200_compute_cells_and_kzg_proofs_batch": (ci, [vp, vp, vp, sz, S]),
+            "b200_kzg_direct_tables": (None, [S, vp]),
             "verify_kzg_proof": (ci, [vp, vp, vp, vp, vp, S]),
             "verify_blob_kzg_proof": (ci, [vp, vp, vp, vp, S]),
             "verify_blob_kzg_proof_batch": (ci, [vp, vp, vp, vp, sz, S]),
@@ -253,6 +254,12 @@ class KZGSettings:
         if rc != C_KZG_OK:
             raise KzgError(rc, "compute_cell_proofs_batch")
         return out
+
+    def direct_tables(self):
+        """-> {"blob_bits", "blob_max_batch", "fk20_bits"}: window widths of the direct-lookup tables (0 = bucket engine)"""
+        out = (C.c_int * 3)()
+        _L().b200_kzg_direct_tables(C.byref(self.c), out)
+        return {"blob_bits": out[0], "blob_max_batch": out[1], "fk20_bits": out[2]}
 
     def compute_cells_and_kzg_proofs_batch(self, blobs, cells_out=None, proofs_out=None):
         """both outputs for n blobs in one pass -> (n,128,2048) cells, (n,128,48) proofs; caller-owned arrays are filled in place"""

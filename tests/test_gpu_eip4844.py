@@ -336,10 +336,13 @@ def test_direct_small_batch_msm_matches_bucket_engine(B, K, oracle_settings):
     for direct, bits in (("24", "13"), ("24", "11"), ("64", "8"), ("0", "13")):
         os.environ["B200_BLOB_DIRECT"] = direct
         os.environ["B200_BLOB_DIRECT_BITS"] = bits
+        os.environ["B200_DIRECT_RESERVE_GB"] = "2"         # other settings objects of this session hold tables too
         try:
             ts = B.KZGSettings.load_trusted_setup_file()
         finally:
-            del os.environ["B200_BLOB_DIRECT"], os.environ["B200_BLOB_DIRECT_BITS"]
+            del os.environ["B200_BLOB_DIRECT"], os.environ["B200_BLOB_DIRECT_BITS"], os.environ["B200_DIRECT_RESERVE_GB"]
+        info = ts.direct_tables()
+        assert info["blob_bits"] == (0 if direct == "0" else int(bits)) and info["blob_max_batch"] == int(direct), info
         for n in (1, 3, 24, 25, 26):
             got = ts.blob_to_kzg_commitment_batch(blobs[:n])
             assert [bytes(g) for g in got] == want_c[:n], (direct, bits, n)
@@ -348,6 +351,31 @@ def test_direct_small_batch_msm_matches_bucket_engine(B, K, oracle_settings):
             assert (bytes(proofs[i]), bytes(ys[i])) == tuple(want_p[k]), (direct, bits, i)
         p1, y1 = ts.compute_kzg_proof(blobs[2], zs[2])      # single call: a batch of one
         assert (p1, y1) == tuple(want_p[1])
+        ts.free()
+
+
+def test_direct_tables_step_down_when_hbm_is_short(B, K, oracle_settings):
+    """the tables must leave B200_DIRECT_RESERVE_GB free: with a reserve nothing can satisfy the settings object loads without
+    them (bucket engines), with one only a narrow table fits the width steps down -- same bytes either way"""
+    import os
+    import torch
+    rng = np.random.default_rng(57)
+    blobs = _rand_blobs(rng, 2)
+    want = [K.blob_to_kzg_commitment(blobs[i].tobytes(), oracle_settings) for i in range(2)]
+    free_gb = torch.cuda.mem_get_info()[0] / 2**30
+    # (reserve, widths the Lagrange table may end up with)
+    cases = [(100000, (0,))]
+    if free_gb > 12:
+        cases.append((int(free_gb) - 10, (8, 11)))       # 10 GiB of headroom: the 7.5 GiB table fits, the 30 GiB one does not
+    for reserve, allowed in cases:
+        os.environ["B200_DIRECT_RESERVE_GB"] = str(reserve)
+        try:
+            ts = B.KZGSettings.load_trusted_setup_file()
+        finally:
+            del os.environ["B200_DIRECT_RESERVE_GB"]
+        assert ts.direct_tables()["blob_bits"] in allowed, (reserve, ts.direct_tables(), free_gb)
+        got = ts.blob_to_kzg_commitment_batch(blobs)
+        assert [bytes(g) for g in got] == want, reserve
         ts.free()
 
 
@@ -366,11 +394,15 @@ def test_fk20_lincomb_table_widths_agree(B, K, oracle_settings):
     for direct, bits in (("1", "13"), ("1", "11"), ("1", "8"), ("0", "8")):
         os.environ["B200_FK20_DIRECT"] = direct
         os.environ["B200_FK20_DIRECT_BITS"] = bits
+        os.environ["B200_BLOB_DIRECT"] = "0"               # leave the HBM to the table under test (60 GiB at 13 bits)
+        os.environ["B200_DIRECT_RESERVE_GB"] = "2"
         try:
             ts = B.KZGSettings.load_trusted_setup_file()
             got = ts.compute_cell_proofs_batch(blobs)      # the tables are built on first use
         finally:
-            del os.environ["B200_FK20_DIRECT"], os.environ["B200_FK20_DIRECT_BITS"]
+            del os.environ["B200_FK20_DIRECT"], os.environ["B200_FK20_DIRECT_BITS"], os.environ["B200_BLOB_DIRECT"]
+            del os.environ["B200_DIRECT_RESERVE_GB"]
+        assert ts.direct_tables()["fk20_bits"] == (int(bits) if direct == "1" else 0), ts.direct_tables()
         assert [bytes(g) for g in got[0]] == [bytes(w) for w in want], (direct, bits)
         if ref is None:
             ref = got.copy()
