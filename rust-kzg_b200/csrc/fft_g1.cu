@@ -107,6 +107,77 @@ __global__ void __launch_bounds__(32) k_g1_stage2_comb(uint8_t* __restrict__ wor
         store_field(w + (j + 3 * h) * 192 + off, z3);
     }
 }
+// Three DIT stages (s, s+1, s+2) at the latency of one, for transforms so small that even the fused pairs leave the machine
+// idle (one blob's FK20 transforms: 128 points).  For the eight points x0..x7 at j + m h (h = 2^s) with a = w_2h^low,
+// b / b' = w_4h^(low [+ h]), c_r = w_8h^(low + r h) and beta_r = b (r even) or b' (r odd):
+//     z_r, z_(r+4) = u_r +- V_r,   u_r = (x0 +- a x1) +- beta_r (x2 +- a x3),   V_r = c_r [(x4 +- a x5) +- beta_r (x6 +- a x7)]
+// (inner signs: - for odd r; outer signs: - for r >= 2).  Expanded, that is 21 independent products by roots of unity per
+// group -- [a]x1, [b]x2, [b']x2, [ab]x3, [ab']x3 and [c_r]x4, [a c_r]x5, [c_r beta_r]x6, [a c_r beta_r]x7 for r = 0..3 --
+// instead of the 12 of three plain stages, all at the same depth, then 8 additions per output pair.
+// k_g1_stage3_mul: one lane quad per product; k_g1_stage3_comb: one lane quad per output pair (r, r + 4).
+__global__ void __launch_bounds__(32) k_g1_stage3_mul(const uint8_t* __restrict__ work, uint8_t* __restrict__ tmp, size_t n, int log_n, int s,
+                                                      const uint8_t* __restrict__ roots, size_t nmax, int inverse) {
+    __shared__ __align__(16) uint8_t table[kQuadTableBytes];
+    const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t nprod = 21 * (n >> 3);
+    const bool live = q < nprod;
+    const size_t qq = live ? q : 0;
+    const size_t g = qq / 21;
+    const int which = (int)(qq - g * 21);
+    const size_t h = (size_t)1 << s, low = g & (h - 1), j = ((g >> s) << (s + 3)) | low;
+    // exponents in units of the n-th root
+    const size_t ea = low << (log_n - 1 - s), eb = low << (log_n - 2 - s), ec = low << (log_n - 3 - s);
+    int m, r = 0;
+    size_t e;
+    if (which == 0) { m = 1; e = ea; }
+    else if (which < 5) {                                  // 1: b x2   2: b' x2   3: ab x3   4: ab' x3
+        const int odd = (which - 1) & 1;
+        m = which < 3 ? 2 : 3;
+        e = eb + (odd ? (n >> 2) : 0) + (m == 3 ? ea : 0);
+    } else {                                               // 5 + 4 (m - 4) + r
+        m = 4 + ((which - 5) >> 2);
+        r = (which - 5) & 3;
+        e = ec + (size_t)r * (n >> 3);
+        if (m & 1) e += ea;
+        if (m & 2) e += eb + ((r & 1) ? (n >> 2) : 0);
+    }
+    e &= n - 1;
+    const uint8_t* w = work + (size_t)blockIdx.y * n * 192;
+    const int off = quad_store_offset();
+    fp_t t = load_field<fp_t>(w + (j + (size_t)m * h) * 192 + off);
+    const size_t eu = e * (nmax >> log_n);
+    fr_t root = load_field_ro<fr_t>(roots + (inverse && eu ? nmax - eu : eu) * 32).from_mont();
+    t = quad_mul_scalar(t, root.v, table);
+    if (live) store_field(tmp + ((size_t)blockIdx.y * nprod + q) * 192 + off, t);
+}
+__global__ void __launch_bounds__(32) k_g1_stage3_comb(uint8_t* __restrict__ work, const uint8_t* __restrict__ tmp, size_t n, int s) {
+    const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // four quads per group: both of a warp's groups in lockstep
+    const bool live = q < (n >> 1);
+    const size_t g = (live ? q : 0) >> 2;
+    const int r = (int)(q & 3);
+    const size_t h = (size_t)1 << s, low = g & (h - 1), j = ((g >> s) << (s + 3)) | low;
+    uint8_t* w = work + (size_t)blockIdx.y * n * 192;
+    const uint8_t* pr = tmp + ((size_t)blockIdx.y * 21 * (n >> 3) + g * 21) * 192;
+    const int off = quad_store_offset();
+    const bool yrole = (threadIdx.x & 3) == 1;
+    auto sgn = [&](const fp_t& v, bool minus) { return (minus && yrole) ? v.neg() : v; };
+    auto P = [&](int k) { return load_field<fp_t>(pr + (size_t)k * 192 + off); };
+    const bool in_minus = r & 1, out_minus = r >= 2;
+    const fp_t x0 = load_field<fp_t>(w + j * 192 + off);
+    const fp_t y = quad_add(x0, sgn(P(0), in_minus));
+    const fp_t by = quad_add(P(1 + (r & 1)), sgn(P(3 + (r & 1)), in_minus));
+    const fp_t u = quad_add(y, sgn(by, out_minus));
+    const fp_t v45 = quad_add(P(5 + r), sgn(P(9 + r), in_minus));
+    const fp_t v67 = quad_add(P(13 + r), sgn(P(17 + r), in_minus));
+    const fp_t v = quad_add(v45, sgn(v67, out_minus));
+    const fp_t z_lo = quad_add(u, v), z_hi = quad_add(u, sgn(v, true));
+    // every quad of the warp has read x0 by now (the warp runs in lockstep through the additions above)
+    __syncwarp();
+    if (live) {
+        store_field(w + (j + (size_t)r * h) * 192 + off, z_lo);
+        store_field(w + (j + (size_t)(r + 4) * h) * 192 + off, z_hi);
+    }
+}
 // XYZZ -> Jacobian, with the [n^-1] scaling of the inverse transform (blst/src/fft_g1.rs:74-79); one quad per point
 __global__ void __launch_bounds__(32) k_g1_out(const uint8_t* __restrict__ work, uint8_t* __restrict__ out_jac, size_t total,
                                                const uint8_t* __restrict__ scale) {
@@ -138,29 +209,41 @@ void FFTSettingsDev::fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n,
     }
     launches_ = 0;
     k_g1_brp_in<<<dim3(div_up(n, 128), (unsigned)batch), 128, 0, st>>>((const uint8_t*)in_jac_dev, (uint8_t*)g1_work_, n, log_n);
-    // stage 0 multiplies by w^0 only; after it the stages run in fused pairs (k_g1_stage2_*: two stages at the latency of
-    // one scalar multiplication) while the launch is small: one warp per eight products with a 27 KiB table each, so
-    // ~1100 warps are resident at a time -- up to 2^12 points per launch the fused products fit one wave (one blob's FK20
-    // transforms: cells + proofs 12.0 -> 6.9 ms); at 64 blobs x 128 points they spill into a second wave and the plain
-    // stages, 20 % less work, win (18.6 vs 21.7 ms per 64 blobs, scripts/fk20_timing.py)
-    const int fuse_env = getenv("B200_FFT_G1_FUSE") ? atoi(getenv("B200_FFT_G1_FUSE")) : -1;   // per call: tests toggle it
-    const bool fuse = fuse_env >= 0 ? fuse_env != 0 : total <= ((size_t)1 << 12);
+    // The transform is a chain of log n dependent scalar multiplications; a 128-point transform has only 64 butterflies per
+    // stage.  While the launch is small the stages therefore run fused -- in triples (k_g1_stage3_*) or pairs (k_g1_stage2_*):
+    // more products, all at the depth of one -- and stage by stage once the plain stages fill the machine (at 64 blobs x 128
+    // points the fused products spill into a second wave of resident warps and the plain stages, 20 % less work, win:
+    // 5.6 vs 6.5 ms, scripts/fft_g1_batch_timing.py).
+    // B200_FFT_G1_FUSE (per call: tests toggle it): 0 plain stages, 2 fused pairs, 3 fused triples, unset = by launch size.
+    // Triples (21 products per 8 points instead of 12) up to 2^11 points per launch -- 16 blobs' FK20 transforms, still one
+    // wave of product quads: 128 points x 8 transforms 2.93 -> see scripts/fft_g1_batch_timing.py; pairs up to 2^12.
+    const int fuse_env = getenv("B200_FFT_G1_FUSE") ? atoi(getenv("B200_FFT_G1_FUSE")) : -1;
+    const int fuse = fuse_env >= 0 ? (fuse_env == 1 ? 2 : fuse_env) : total <= ((size_t)1 << 11) ? 3 : total <= ((size_t)1 << 12) ? 2 : 0;
+    auto plain = [&](int st_idx) {
+        k_g1_stage<<<dim3(div_up(n / 2 * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, n, log_n, st_idx, (const uint8_t*)roots_,
+                                                                            max_width_, inverse);
+        launches_++;
+    };
     int s = 0;
-    if (!fuse || (log_n & 1)) {
-        if (log_n > 0) {
-            k_g1_stage<<<dim3(div_up(n / 2 * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, n, log_n, 0, (const uint8_t*)roots_,
-                                                                                max_width_, inverse);
-            launches_++;
-        }
+    if (log_n > 0 && (fuse == 0 || (fuse == 2 && (log_n & 1)) || (fuse == 3 && log_n % 3 != 0))) {
+        plain(0);                                              // stage 0 multiplies by w^0 only: cheap, and it fixes the parity
         s = 1;
     }
-    if (fuse && log_n >= 2) {
-        const size_t need = (size_t)batch * 5 * (n >> 2);
+    if (fuse >= 2 && log_n >= 2) {
+        const size_t need = (size_t)batch * (fuse == 3 ? 21 * (n >> 3) : 5 * (n >> 2));
         if (need > g1_tmp_elems_) {
             cudaFree(g1_tmp_);
             g1_tmp_ = nullptr; g1_tmp_elems_ = 0;
             g1_tmp_ = dev_alloc<uint8_t>(need * 192);
             g1_tmp_elems_ = need;
+        }
+        if (fuse == 3) {
+            for (; s + 3 <= log_n; s += 3) {
+                k_g1_stage3_mul<<<dim3(div_up(21 * (n >> 3) * 4, 32), (unsigned)batch), 32, 0, st>>>((const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n,
+                                                                                                s, (const uint8_t*)roots_, max_width_, inverse);
+                k_g1_stage3_comb<<<dim3(div_up((n >> 1) * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, (const uint8_t*)g1_tmp_, n, s);
+                launches_ += 2;
+            }
         }
         for (; s + 2 <= log_n; s += 2) {
             k_g1_stage2_mul<<<dim3(div_up(5 * (n >> 2) * 4, 32), (unsigned)batch), 32, 0, st>>>((const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n, s,
@@ -169,11 +252,7 @@ void FFTSettingsDev::fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n,
             launches_ += 2;
         }
     }
-    for (; s < log_n; s++) {
-        k_g1_stage<<<dim3(div_up(n / 2 * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, n, log_n, s, (const uint8_t*)roots_,
-                                                                            max_width_, inverse);
-        launches_++;
-    }
+    for (; s < log_n; s++) plain(s);
     const uint8_t* inv_n = (const uint8_t*)roots_ + (max_width_ + 1) * 32 + 33 * 32;
     k_g1_out<<<div_up(total * 4, 32), 32, 0, st>>>((const uint8_t*)g1_work_, (uint8_t*)out_jac_dev, total,
                                                  inverse && log_n && apply_scale ? inv_n + log_n * 32 : nullptr);

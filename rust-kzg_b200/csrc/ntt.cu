@@ -239,6 +239,9 @@ static int tile_elems(size_t n) {
     static const int t = getenv("B200_NTT_TILE") ? atoi(getenv("B200_NTT_TILE")) : 0;
     if (t) return t;
     if (ntt_variant() == 3) return kTileElems;
+    // measured (scripts/ntt_timing.py, B200_NTT_TILE sweep): up to 2^14 points 128-point tiles spread a pass over more SMs
+    // (2^10 21.0 -> 16.9 us, 2^12 23.0 -> 20.9, 2^14 27.1 -> 23.0); 2^16 is best at 512 (31.2 vs 35.4), 2^18 and up at 1024
+    if (n <= ((size_t)1 << 14)) return kTileElems / 16;
     return n <= ((size_t)1 << 16) ? kTileElems / 4 : kTileElems / 2;
 }
 static void launch_pass(const NttPass& p, int batch, cudaStream_t st) {

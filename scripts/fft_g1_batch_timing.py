@@ -23,7 +23,7 @@ for batch in (8, 16, 32, 64, 128, 256):
     d_in = torch.from_numpy(src.view(np.int64)).cuda()
     d_out = torch.zeros_like(d_in)
     row = {}
-    for fuse in ("0", "1"):
+    for fuse in ("0", "2", "3"):
         os.environ["B200_FFT_G1_FUSE"] = fuse
         row["fuse" + fuse + "_ms"] = round(timed(lambda: fs.fft_g1_device(d_out.data_ptr(), d_in.data_ptr(), n, False, batch, 0), reps=3, warm=1), 3)
     res[batch] = row

@@ -19,13 +19,18 @@ run blob64_commit "k_blob_to_fr" blob 64 2
 run blob1_commit "k_blob_to_fr" blob 1 2
 run blob8_commit "k_blob_to_fr" blob 8 2
 run proof64 "k_blob_to_fr" proof 64 2
+run fk20_64 "k_blob_to_fr" fk20 64 1
 run ntt_2p20 "k_ntt_pass" ntt 20 3
 run ntt_2p12 "k_ntt_pass" ntt 12 3
 ncu --set full --clock-control none --import-source on -k regex:k_accumulate -s 1 -c 1 -f -o /tmp/prof_acc python scripts/ncu_target.py msm 20 2 > /dev/null 2>&1
 ncu -i /tmp/prof_acc.ncu-rep --page raw --csv > gpurun_out/r02_accumulate_raw.csv
 python scripts/ncu_raw_table.py gpurun_out/r02_accumulate_raw.csv > gpurun_out/r02_accumulate_table.md
-ncu --set full --clock-control none -k regex:k_direct_msm_partial -s 1 -c 1 -f -o /tmp/prof_direct python scripts/ncu_target.py blob 8 2 > /dev/null 2>&1
-ncu -i /tmp/prof_direct.ncu-rep --page raw --csv > gpurun_out/r02_direct_partial_raw.csv
-python scripts/ncu_raw_table.py gpurun_out/r02_direct_partial_raw.csv > gpurun_out/r02_direct_partial_table.md
+ncu --set full --clock-control none -k regex:k_direct_msm -s 1 -c 1 -f -o /tmp/prof_direct python scripts/ncu_target.py blob 64 2 > /dev/null 2>&1
+ncu -i /tmp/prof_direct.ncu-rep --page raw --csv > gpurun_out/r02_direct_msm_raw.csv
+python scripts/ncu_raw_table.py gpurun_out/r02_direct_msm_raw.csv > gpurun_out/r02_direct_msm_table.md
+ncu --set full --clock-control none -k regex:k_direct_lincomb -s 1 -c 1 -f -o /tmp/prof_lincomb python scripts/ncu_target.py fk20 64 1 > /dev/null 2>&1
+ncu -i /tmp/prof_lincomb.ncu-rep --page raw --csv > gpurun_out/r02_direct_lincomb_raw.csv
+python scripts/ncu_raw_table.py gpurun_out/r02_direct_lincomb_raw.csv > gpurun_out/r02_direct_lincomb_table.md
 cat gpurun_out/r02_launches.md | head -80
 cat gpurun_out/r02_accumulate_table.md
+cat gpurun_out/r02_direct_msm_table.md

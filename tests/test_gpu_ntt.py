@@ -186,10 +186,11 @@ def test_fft_fr_above_2p22_three_passes(B, K):
     fs.close()
 
 
-@pytest.mark.parametrize("logn", [2, 5, 7, 8])
+@pytest.mark.parametrize("logn", [2, 3, 5, 6, 7, 8])
 def test_fft_g1_fused_and_plain_stages_agree(B, K, oracle_settings, logn):
-    """fft_g1 runs its stages in fused pairs (five independent scalar multiplications per four points, csrc/fft_g1.cu) while
-    the transform is small and stage by stage otherwise: both forms against the oracle, forward and inverse"""
+    """fft_g1 runs its stages in fused triples (21 independent scalar multiplications per eight points) or pairs (five per
+    four points, csrc/fft_g1.cu) while the transform is small and stage by stage otherwise: all three forms against the
+    oracle, forward and inverse, for every residue of log n mod 2 and mod 3"""
     import os
     n = 1 << logn
     ofs = K.FFTSettings(10)
@@ -197,7 +198,7 @@ def test_fft_g1_fused_and_plain_stages_agree(B, K, oracle_settings, logn):
     if n >= 8:
         pts[2] = 0
     want = {inv: K.p1s_to_affine(ofs.fft_g1(pts, inv)) for inv in (False, True)}
-    for fuse in ("1", "0"):
+    for fuse in ("3", "2", "0"):
         os.environ["B200_FFT_G1_FUSE"] = fuse
         try:
             fs = B.FFTSettings(10)
