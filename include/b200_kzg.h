@@ -90,6 +90,12 @@ B200_API int b200_msm_last_affine(void *msm);
  * at prepare when every base is in the prime-order subgroup (B200_MSM_RANDOMIZE=0 turns it off); the result is the same
  * group element either way. */
 B200_API int b200_msm_randomized(void *msm);
+/* Fixed-base handles of 1024..8192 points (the 4096-point MSM behind g1_lincomb, kzg/src/eip_4844.rs:463-476) also hold a
+ * direct-lookup table of every signed-digit multiple of every window of every base: a full-length call is then
+ * the plain sum of npoints * W looked-up points in ONE launch (0.2 ms instead of 0.55 ms for 4096 points), shorter calls
+ * and every other size use the bucket pipeline.  Returns the table's window width (B200_MSM_DIRECT_BITS, default 11 =
+ * 7.5 GiB for 4096 points; narrower when HBM is short), 0 when the handle has none (B200_MSM_DIRECT=0). */
+B200_API int b200_msm_direct_bits(void *msm);
 
 
 /* ============================================================================================================== */

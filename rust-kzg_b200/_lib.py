@@ -45,6 +45,7 @@ def load():
         "b200_msm_last_stats": (RustError, [vp, vp]),
         "b200_msm_last_affine": (ci, [vp]),
         "b200_msm_randomized": (ci, [vp]),
+        "b200_msm_direct_bits": (ci, [vp]),
         "b200_msm_plan": (None, [sz, ci, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
         "b200_selftest_fp": (RustError, [ci, vp, vp, vp, sz]),
         "b200_selftest_fr": (RustError, [ci, vp, vp, vp, sz]),

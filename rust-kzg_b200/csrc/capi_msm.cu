@@ -13,6 +13,7 @@
 #include "../../include/b200_kzg.h"
 #include "capi_common.cuh"
 #include "coalesce.cuh"
+#include "eip4844.cuh"
 #include "g1.cuh"
 #include "msm.cuh"
 #include "util.cuh"
@@ -95,7 +96,34 @@ struct MsmHandle {
     size_t scalars_cap = 0;
     int out_cap = 0;
     CoQueue<MsmCoBatch, 1> co;
+    // small fixed-base handles (the 4096-point commitment MSM behind g1_lincomb): direct lookups in a table of every signed
+    // digit multiple (fk20_direct.cu) instead of the bucket pipeline, whose reduction tail is ~0.45 ms however short the call
+    void* direct_table = nullptr;
+    int direct_c = 0;
+    uint8_t* direct_part = nullptr;   // max_batch x 128 partial sums
+    unsigned* direct_cnt = nullptr;   // max_batch completion counters (zero between launches)
+    uint8_t* canon_dev = nullptr;     // canonical copy of the scalars (the engine takes blst_fr, the table digits do not)
+    size_t canon_cap = 0;
+    // sums of `batch` vectors of npoints blst_fr scalars (device, or host when scalars_host != nullptr: copied to
+    // scalars_dev first) -> batch blst_p1 at out; caller holds mu and has called ensure_staging
+    void run(const void* scalars_dev_in, size_t np, int batch, void* out, cudaStream_t st, const void* scalars_host = nullptr) {
+        if (!direct_table || np != npoints) {
+            eng->run(scalars_dev_in, np, batch, true, out, st, scalars_host);
+            return;
+        }
+        const size_t total = (size_t)batch * np;
+        if (scalars_host) B200_CUDA_CHECK(cudaMemcpyAsync(const_cast<void*>(scalars_dev_in), scalars_host, total * 32, cudaMemcpyHostToDevice, st));
+        if (total > canon_cap) {
+            cudaFree(canon_dev);
+            canon_dev = nullptr; canon_cap = 0;
+            canon_dev = dev_alloc<uint8_t>(total * 32);
+            canon_cap = total;
+        }
+        launch_fr_from_mont(scalars_dev_in, canon_dev, total, st);
+        launch_direct_msm(canon_dev, direct_table, direct_part, direct_cnt, nullptr, (uint8_t*)out, batch, (int)np, direct_c, st);
+    }
     ~MsmHandle() {
+        cudaFree(direct_table); cudaFree(direct_part); cudaFree(direct_cnt); cudaFree(canon_dev);
         cudaFree(scalars_dev);
         cudaFree(out_dev);
         if (ev_busy) cudaEventDestroy(ev_busy);
@@ -135,6 +163,30 @@ MsmHandle* msm_handle_create(const void* points, size_t npoints, bool host_point
     h->eng.reset(new MsmEngine(cfg, points, host_points, h->stream));
     h->npoints = npoints;
     h->co.max_batches = 3;
+    // direct-lookup table for small fixed-base handles whose items fill whole 128-thread slices (B200_MSM_DIRECT=0: never;
+    // B200_MSM_DIRECT_BITS: window width, default 11 = 7.5 GiB for 4096 points; narrower or none when HBM is short)
+    if (fixed && points && npoints >= 1024 && npoints <= 8192 && env_int("B200_MSM_DIRECT", 1)) {
+        int c = pick_direct_bits(npoints, env_int("B200_MSM_DIRECT_BITS", 11));
+        while (c && (npoints * direct_windows(c)) % 128) c = c > 8 ? 8 : 0;   // 8-bit windows: 32 per point, any npoints % 4 == 0
+        if (c) {
+            uint8_t* aff = nullptr;
+            const void* src = points;
+            if (host_points) {
+                aff = dev_alloc<uint8_t>(npoints * 96);
+                B200_CUDA_CHECK(cudaMemcpyAsync(aff, points, npoints * 96, cudaMemcpyHostToDevice, h->stream));
+                src = aff;
+            }
+            h->direct_table = build_direct_table(src, npoints, 1, c, h->stream);
+            cudaFree(aff);
+            if (h->direct_table) {
+                h->direct_c = c;
+                h->direct_part = dev_alloc<uint8_t>((size_t)cfg.max_batch * 128 * 192);
+                h->direct_cnt = dev_alloc<unsigned>(cfg.max_batch);
+                B200_CUDA_CHECK(cudaMemsetAsync(h->direct_cnt, 0, cfg.max_batch * sizeof(unsigned), h->stream));
+                B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+            }
+        }
+    }
     return h.release();
 }
 
@@ -179,7 +231,7 @@ RustError b200_msm_prepared_device(void* msm, void* out_dev, size_t npoints, con
         DeviceScope ds(h->device);
         std::lock_guard<std::mutex> lk(h->mu);
         h->enter((cudaStream_t)stream);
-        h->eng->run(scalars_dev, npoints, batch, true, out_dev, (cudaStream_t)stream);
+        h->run(scalars_dev, npoints, batch, out_dev, (cudaStream_t)stream);
         h->leave_async((cudaStream_t)stream);
     });
 }
@@ -198,7 +250,7 @@ RustError b200_msm_prepared_batch(void* msm, blst_p1 out[], size_t npoints, cons
         std::lock_guard<std::mutex> lk(h->mu);
         h->enter(h->stream);
         h->ensure_staging((size_t)batch * npoints, batch);
-        h->eng->run(h->scalars_dev, npoints, batch, true, h->out_dev, h->stream, scalars);
+        h->run(h->scalars_dev, npoints, batch, h->out_dev, h->stream, scalars);
         B200_CUDA_CHECK(cudaMemcpyAsync(out, h->out_dev, (size_t)batch * 144, cudaMemcpyDeviceToHost, h->stream));
         B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
     });
@@ -233,7 +285,7 @@ RustError mult_pippenger_prepared(void* msm, blst_p1* out, size_t npoints, const
                 const int m = h->co.close(B);
                 h->enter(h->stream);
                 h->ensure_staging((size_t)m * n, m);
-                h->eng->run(h->scalars_dev, n, m, true, h->out_dev, h->stream, B->h_in);
+                h->run(h->scalars_dev, n, m, h->out_dev, h->stream, B->h_in);
                 B200_CUDA_CHECK(cudaMemcpyAsync(B->h_out, h->out_dev, (size_t)m * 144, cudaMemcpyDeviceToHost, h->stream));
                 B200_CUDA_CHECK(cudaStreamSynchronize(h->stream));
             } catch (const CudaError& e) {
@@ -294,6 +346,11 @@ RustError mult_pippenger(blst_p1* out, const blst_p1_affine points[], size_t npo
     });
 }
 
+/* window width of the handle's direct-lookup table (full-length calls take it instead of the bucket pipeline), 0 = none */
+int b200_msm_direct_bits(void* msm) {
+    MsmHandle* h = static_cast<MsmHandle*>(msm);
+    return h && h->direct_table ? h->direct_c : 0;
+}
 /* 1 when the handle's table is scalar-randomised (all bases were in the prime-order subgroup at prepare), else 0 */
 int b200_msm_randomized(void* msm) {
     MsmHandle* h = static_cast<MsmHandle*>(msm);

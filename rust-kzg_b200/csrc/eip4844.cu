@@ -334,7 +334,7 @@ static int env_int_local(const char* name, int dflt) {
 }
 // The direct-lookup tables (fk20_direct.cu) trade HBM for additions: the widest window <= want whose table still leaves
 // B200_DIRECT_RESERVE_GB (default 40) of the device free for everything else in the process; 0 when not even the 8-bit one fits.
-static int pick_direct_bits(size_t npts, int want) {
+int pick_direct_bits(size_t npts, int want) {
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return 0; }
     const size_t reserve = (size_t)env_int_local("B200_DIRECT_RESERVE_GB", 40) << 30;
@@ -345,7 +345,7 @@ static int pick_direct_bits(size_t npts, int want) {
 }
 // table of every digit multiple of `points` (n affine points; period > 1: `points` holds period blocks of n): built from the
 // fixed-base rows of a throw-away engine with the same window width; nullptr when the allocation fails
-static void* build_direct_table(const void* points, size_t n, int period, int c, cudaStream_t st) {
+void* build_direct_table(const void* points, size_t n, int period, int c, cudaStream_t st) {
     void* p = nullptr;
     if (cudaMalloc(&p, direct_table_bytes(n * period, c)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     MsmConfig rc;

@@ -161,6 +161,14 @@ void launch_direct_lincomb(const void* scalars, const void* table, void* out_jac
 // npts-term MSMs over one point set, compressed results; partials: nvec * 128 * 192 bytes, counters: nvec zeroed words
 void launch_direct_msm_compressed(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, int nvec,
                                   int npts, int c, cudaStream_t st);
+// the same with a choice of result form: out48 (compressed) or, when out_jac != nullptr, blst_p1 Jacobian points
+void launch_direct_msm(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, uint8_t* out_jac,
+                       int nvec, int npts, int c, cudaStream_t st);
+void launch_fr_from_mont(const void* in, void* out, size_t n, cudaStream_t st);
+// widest window <= want whose table leaves B200_DIRECT_RESERVE_GB free (0: none fits); table of every digit multiple of the
+// n * period affine points at points_dev (nullptr when the allocation fails)
+int pick_direct_bits(size_t npts, int want);
+void* build_direct_table(const void* points_dev, size_t n, int period, int c, cudaStream_t st);
 // test hook (verify.cu): sum k_i P_i through the quad / GLV scalar multiplication used by the verifiers and fft_g1
 void selftest_lincomb_quads(const void* points_affine_dev, const void* scalars_mont_dev, int n, void* out_jac_dev, cudaStream_t st);
 // uncompress n 48-byte points into affine Montgomery form; flags[i] = 1 on malformed / off-curve input

@@ -182,11 +182,14 @@ void launch_direct_lincomb(const void* scalars, const void* table, void* out_jac
 __device__ __forceinline__ uint32_t direct_cta_of(uint32_t slice, uint32_t S, uint32_t G) {   // the CTA whose range holds `slice`
     return (uint32_t)((((uint64_t)slice + 1) * G + S - 1) / S) - 1;
 }
+#ifndef B200_DIRECT_MINB
+#define B200_DIRECT_MINB 2   // measured: 3 CTAs per SM (168 registers, spills in the chain) 2.39 ms per 64 blobs against 2.31
+#endif
 template <class AR>
-__global__ void __launch_bounds__(128) k_direct_msm(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
+__global__ void __launch_bounds__(128, B200_DIRECT_MINB) k_direct_msm(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
                                                     uint8_t* __restrict__ partials, int npts, int W, int c, uint32_t spv, uint32_t S,
                                                     unsigned* __restrict__ counters, uint8_t* __restrict__ out48,
-                                                    unsigned long long* trace) {
+                                                    uint8_t* __restrict__ out_jac, unsigned long long* trace) {
     unsigned long long ts[8];
     auto stamp = [&](int k) { if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ts[k] = t; } };
     stamp(0);
@@ -252,7 +255,12 @@ __global__ void __launch_bounds__(128) k_direct_msm(const uint8_t* __restrict__ 
             tot = seg_sum_quad(a, 32);                        // one warp holds every partial
         }
         stamp(5);
-        if (wid == 0) {
+        if (wid == 0 && out_jac) {
+            // Jacobian (X ZZ, Y ZZZ, ZZ) as k_group_finish writes it (blst_p1); infinity stays all-zero.  No inversion.
+            const fp_t jc = tot * shfl_xor_fp(tot, 2);
+            if (lane < 2) store_field(out_jac + (size_t)vec * 144 + lane * 48, jc);
+            if (lane == 2) store_field(out_jac + (size_t)vec * 144 + 96, tot);
+        } else if (wid == 0) {
             // compressed form (blst_p1_compress): x = X / ZZ, y = Y / ZZZ with 1/ZZ = ZZZ^-2 ZZ^2; one inversion, uniform over the warp
             const fp_t zz = shfl_idx_fp(tot, 2), zzz = shfl_idx_fp(tot, 3);
             const bool inf = zz.is_zero();
@@ -274,17 +282,35 @@ __global__ void __launch_bounds__(128) k_direct_msm(const uint8_t* __restrict__ 
         __syncthreads();                                      // sh is reused by the next piece
     }
 }
-// scalars: nvec x npts canonical little-endian 32-byte scalars; partials: workspace of nvec * 128 XYZZ points (192 bytes);
-// counters: nvec zero-initialised words (left zero); out48: nvec compressed points
+// blst_fr (Montgomery) -> canonical little-endian scalars, the form the Booth digits are read from
+__global__ void k_fr_from_mont(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) store_field(out + i * 32, load_field_ro<fr_t>(in + i * 32).from_mont());
+}
+void launch_fr_from_mont(const void* in, void* out, size_t n, cudaStream_t st) {
+    if (!n) return;
+    k_fr_from_mont<<<(unsigned)div_up(n, (size_t)256), 256, 0, st>>>((const uint8_t*)in, (uint8_t*)out, n);
+    B200_LAUNCH_CHECK();
+}
 void launch_direct_msm_compressed(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, int nvec,
                                   int npts, int c, cudaStream_t st) {
+    launch_direct_msm(scalars, table, partials, counters, out48, nullptr, nvec, npts, c, st);
+}
+// scalars: nvec x npts canonical little-endian 32-byte scalars; partials: workspace of nvec * 128 XYZZ points (192 bytes);
+// counters: nvec zero-initialised words (left zero); results: out48 = nvec compressed points, or (out_jac != nullptr) nvec blst_p1
+void launch_direct_msm(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, uint8_t* out_jac,
+                       int nvec, int npts, int c, cudaStream_t st) {
     const int W = direct_windows(c);
     if (((size_t)npts * W) % 128) throw CudaError(-1, "direct MSM: items per vector must fill whole CTAs");
-    static const int wave = [] {                              // resident CTAs: two per SM at ~200 registers
-        int dev = 0, sms = 148;
+    static const int wave = [] {                              // resident CTAs of this kernel on the whole device
+        int dev = 0, sms = 148, per_sm = 2;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        return 2 * sms;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_direct_msm<ArCall>, 128, 0) != cudaSuccess || per_sm < 1) {
+            cudaGetLastError();
+            per_sm = 2;
+        }
+        return per_sm * sms;
     }();
     const uint32_t spv = (uint32_t)((size_t)npts * W / 128), S = spv * (uint32_t)nvec;
     // at least five slices per CTA, and no vector cut into more than the 128 pieces its fold handles
@@ -302,7 +328,7 @@ void launch_direct_msm_compressed(const void* scalars, const void* table, void* 
         return t;
     }();
     k_direct_msm<ArCall><<<G, 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)partials, npts, W, c, spv, S, counters,
-                                           out48, trace);
+                                           out48, out_jac, trace);
     B200_LAUNCH_CHECK();
     if (trace) {
         cudaStreamSynchronize(st);

@@ -58,7 +58,9 @@ class PreparedMsm:
         return {"c": c.value, "W": w.value, "table_bytes": tb.value, "launches": l.value,
                 # path of the LAST run: batch-affine accumulation (6 M per addition + ~0.6 M of shared inversion work) or XYZZ
                 "accumulate": "affine" if aff else "xyzz", "accumulate_kernel": "k_accumulate_affine" if aff else "k_accumulate",
-                "fp_mul_per_add": 6.6 if aff else 10.0, "randomized": bool(_L().b200_msm_randomized(self.h))}
+                "fp_mul_per_add": 6.6 if aff else 10.0, "randomized": bool(_L().b200_msm_randomized(self.h)),
+                # window width of the direct-lookup table full-length calls use instead of the bucket pipeline (0: none)
+                "direct_bits": int(_L().b200_msm_direct_bits(self.h))}
 
     def last_counts(self):
         """(entries, tasks) of the last run: the accumulate kernel did entries - tasks mixed additions."""

@@ -8,6 +8,16 @@ from conftest import R_MOD, rand_fr_mont, rand_ints
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _bucket_pipeline_only():
+    """4096-point handles would take the direct-lookup table for full-length calls (csrc/capi_msm.cu); the tests of this module
+    pin the bucket pipeline and its window plans, so they switch it off -- test_direct_lookup_handles covers the table path"""
+    import os
+    os.environ["B200_MSM_DIRECT"] = "0"
+    yield
+    del os.environ["B200_MSM_DIRECT"]
+
+
 @pytest.fixture(scope="module")
 def prepared(B, lagrange_affine):
     h = B.PreparedMsm(lagrange_affine)
@@ -346,4 +356,61 @@ def test_scalar_randomisation_and_its_subgroup_guard(B, K, lagrange_affine):
     assert h.info()["randomized"] is False                      # the guard: one base outside the subgroup turns it off
     s256 = K.fr_from_ints(rand_ints(rng, 256, R_MOD))
     assert K.p1_compress(h.mult(s256)) == K.p1_compress(K.msm_affine(pts, s256, nthreads=4))
+    h.close()
+
+
+@pytest.mark.parametrize("bits", [11, 8, 13])
+def test_direct_lookup_handles(B, K, lagrange_affine, bits):
+    """fixed-base handles of 4096 points sum full-length calls by direct lookups in a table of every signed-digit multiple
+    (csrc/fk20_direct.cu, one launch, Jacobian out): random, blob-like and edge scalars, bases at infinity and repeated, the
+    batch entry, coalesced callers, and prefixes (which stay on the bucket pipeline) against the oracle"""
+    import os
+    import threading
+    env = {"B200_MSM_DIRECT": "1", "B200_MSM_DIRECT_BITS": str(bits), "B200_DIRECT_RESERVE_GB": "2"}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        pts = lagrange_affine.copy()
+        pts[5] = 0                                   # the point at infinity (all-zero affine)
+        pts[9] = pts[8]                              # a repeated base
+        h = B.PreparedMsm(pts)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+    assert h.info()["direct_bits"] == bits
+    rng = np.random.default_rng(300 + bits)
+    n = 4096
+    half = 1 << (bits - 1)
+    cases = {"random": rand_ints(rng, n, R_MOD), "blob-like": rand_ints(rng, n, 1 << 248), "r-1": [R_MOD - 1] * n, "ones": [1] * n,
+             "zeros": [0] * n, "half-window": [half] * n, "half-window+1": [half + 1] * n,
+             "window-borrow": [((half << bits) | half) % R_MOD] * n, "all-ones-bits": [(1 << 254) - 1] * n}
+    for name, ints in cases.items():
+        sc = K.fr_from_ints(ints)
+        assert K.p1_compress(h.mult(sc)) == K.p1_compress(K.msm_affine(pts, sc, nthreads=8)), name
+    # prefix: the bucket pipeline on the first 1000 bases
+    sc = K.fr_from_ints(rand_ints(rng, 1000, R_MOD))
+    assert K.p1_compress(h.mult(sc)) == K.p1_compress(K.msm_affine(pts[:1000], sc, nthreads=8))
+    # batch of 5 vectors in one launch; CTA ranges cross the vector boundaries
+    sc5 = K.fr_from_ints(rand_ints(rng, 5 * n, R_MOD))
+    got = h.mult_batch(sc5, 5)
+    for v in range(5):
+        assert K.p1_compress(got[v]) == K.p1_compress(K.msm_affine(pts, sc5[v * n:(v + 1) * n], nthreads=8)), v
+    # coalesced callers
+    want = [K.p1_compress(got[v]) for v in range(5)]
+    errs = []
+
+    def worker(k):
+        try:
+            for rep in range(3):
+                v = (k + rep) % 5
+                assert K.p1_compress(h.mult(sc5[v * n:(v + 1) * n])) == want[v]
+        except Exception as e:                      # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
     h.close()
