@@ -397,7 +397,8 @@ def main():
     }
     extra = dict(shared_extra)
     if not args.no_extra and world == 1:
-        for name, fn in (("variable_base_e2e", lambda: variable_base(B, K, torch, pts, sc, exp)),
+        for name, fn in (("g1_lincomb_4096", lambda: lincomb_4096(B, K, L, torch)),
+                         ("variable_base_e2e", lambda: variable_base(B, K, torch, pts, sc, exp)),
                          ("adversarial_msm", lambda: adversarial_msm(B, K, L, torch, pts, ms_step)),
                          ("blobs", lambda: blob_metrics(B, K, osettings, torch)),
                          ("threads", lambda: thread_metrics()),
@@ -415,6 +416,36 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     print(json.dumps(out))
+
+
+def lincomb_4096(B, K, L, torch):
+    """mult_pippenger_prepared at the size the reference calls g1_lincomb with (4096 Lagrange points, kzg/src/eip_4844.rs:463-476):
+    one call host to host and device-resident, on the handle's direct-lookup table and on the bucket pipeline beside it"""
+    rng = np.random.default_rng(SEED + 9)
+    n = L.shape[0]
+    sc = np.ascontiguousarray(rand_fr(rng, n))
+    want = K.p1_compress(K.msm_affine(L, sc, nthreads=os.cpu_count() or 1))
+    out = {"npoints": int(n), "api": "prepare_msm / mult_pippenger_prepared (C ABI), pageable host scalars"}
+    for label, direct in (("direct_table", "1"), ("bucket_pipeline", "0")):
+        os.environ["B200_MSM_DIRECT"] = direct
+        try:
+            h = B.PreparedMsm(L)
+        finally:
+            del os.environ["B200_MSM_DIRECT"]
+        got = h.mult(sc)
+        for _ in range(5):
+            h.mult(sc)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            h.mult(sc)
+        host_ms = (time.perf_counter() - t0) / 50 * 1e3
+        d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+        d_out = torch.zeros(18, dtype=torch.int64, device="cuda")
+        dev_ms = timed_events(torch, lambda: h.mult_device(d_out.data_ptr(), n, d_sc.data_ptr(), 1, 0), reps=20, warm=5)
+        out[label] = {"host_call_ms": host_ms, "device_ms": dev_ms, "direct_bits": h.info()["direct_bits"],
+                      "parity_ok": bool(K.p1_compress(got) == want and K.p1_compress(d_out.cpu().numpy().view(np.uint64)) == want)}
+        h.close()
+    return out
 
 
 def timed_events(torch, fn, reps=10, warm=3):
