@@ -4,10 +4,14 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "mont.cuh"
 #include "util.cuh"
 
 namespace b200 {
+
+namespace cg = cooperative_groups;
 
 static constexpr int kNttThreads = 256;
 static constexpr int kMaxLogM = 11;          // largest in-CTA sub-transform: 2^11 points = 64 KiB of shared memory
@@ -81,6 +85,31 @@ __device__ __forceinline__ void butterfly_group(uint8_t* sm, const uint8_t* tw, 
     for (int j = 0; j < E; j++) store_field(sm + (size_t)slot(g * m + base + (j << t)) * 32, x[j]);
 }
 
+// all log_m stages of the G sub-transforms of a tile in shared memory: groups of three (RMAX = 3) or two stages, then
+// whatever is left (two or one); ends with a barrier
+template <int RMAX>
+__device__ __forceinline__ void tile_butterflies(uint8_t* sm, const uint8_t* tw, const NttPass& p, int m, int tile) {
+    int t = 0;
+    if (RMAX >= 3) {
+        for (; t + 3 <= p.log_m; t += 3) {
+            for (int u = threadIdx.x; u < (tile >> 3); u += blockDim.x) butterfly_group<3>(sm, tw, p, m, t, u);
+            __syncthreads();
+        }
+    } else {
+        for (; t + 2 <= p.log_m - 1 || t + 2 == p.log_m; t += 2) {
+            for (int u = threadIdx.x; u < (tile >> 2); u += blockDim.x) butterfly_group<2>(sm, tw, p, m, t, u);
+            __syncthreads();
+        }
+    }
+    if (p.log_m - t == 2) {
+        for (int u = threadIdx.x; u < (tile >> 2); u += blockDim.x) butterfly_group<2>(sm, tw, p, m, t, u);
+        __syncthreads();
+    } else if (p.log_m - t == 1) {
+        for (int u = threadIdx.x; u < (tile >> 1); u += blockDim.x) butterfly_group<1>(sm, tw, p, m, t, u);
+        __syncthreads();
+    }
+}
+
 template <int RMAX, int MINB>
 __global__ void __launch_bounds__(kNttThreads, MINB) k_ntt_pass(NttPass p) {
     extern __shared__ __align__(16) uint8_t sm[];
@@ -108,26 +137,7 @@ __global__ void __launch_bounds__(kNttThreads, MINB) k_ntt_pass(NttPass p) {
     }
     __syncthreads();
 
-    // butterflies: groups of three stages, then whatever is left (two or one)
-    int t = 0;
-    if (RMAX >= 3) {
-        for (; t + 3 <= p.log_m; t += 3) {
-            for (int u = threadIdx.x; u < (tile >> 3); u += blockDim.x) butterfly_group<3>(sm, tw, p, m, t, u);
-            __syncthreads();
-        }
-    } else {
-        for (; t + 2 <= p.log_m - 1 || t + 2 == p.log_m; t += 2) {
-            for (int u = threadIdx.x; u < (tile >> 2); u += blockDim.x) butterfly_group<2>(sm, tw, p, m, t, u);
-            __syncthreads();
-        }
-    }
-    if (p.log_m - t == 2) {
-        for (int u = threadIdx.x; u < (tile >> 2); u += blockDim.x) butterfly_group<2>(sm, tw, p, m, t, u);
-        __syncthreads();
-    } else if (p.log_m - t == 1) {
-        for (int u = threadIdx.x; u < (tile >> 1); u += blockDim.x) butterfly_group<1>(sm, tw, p, m, t, u);
-        __syncthreads();
-    }
+    tile_butterflies<RMAX>(sm, tw, p, m, tile);
 
     // store (optionally with the inter-pass twiddle and the 1/n scale)
     fr_t sc;
@@ -141,6 +151,66 @@ __global__ void __launch_bounds__(kNttThreads, MINB) k_ntt_pass(NttPass p) {
         if (p.tw_unit && q && col) x = x * root_at(p, (size_t)q * col * p.tw_unit);
         if (p.scale) x = x * sc;
         store_field(out + (col * p.out_cstride + (size_t)q * p.out_rstride) * 32, x);
+    }
+}
+
+// Both passes of a small transform in ONE launch by a thread-block cluster of C = 8 or 16 CTAs: CTA r transforms the
+// columns [r n1/C, (r+1) n1/C) (pass 1, p1), applies the twiddle w_n^(i2 j1) and writes every value straight into the shared
+// memory of the CTA that owns row i2 in pass 2 (distributed shared memory: the inter-pass transpose never touches HBM),
+// one cluster barrier, then CTA r transforms the rows [r n2/C, (r+1) n2/C) it now holds (p2) and writes natural order.
+// One launch instead of two and no scratch round trip: the small-size latency is launches and dependent phases, not work.
+static constexpr int kClusterMinLog = 9, kClusterMaxLog = 14;    // 2^14 on 8 CTAs: two tiles of 2048 points + twiddles = 132 KiB per CTA
+static constexpr int kClusterMaxShm = 2 * (1 << (kClusterMaxLog - 3)) * 32 + 2 * (1 << 6) * 32;
+__global__ void __launch_bounds__(kNttThreads) k_ntt_cluster(NttPass p1, NttPass p2) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank(), C = (int)cluster.num_blocks();   // 8 or 16 CTAs (launch attribute)
+    const int m1 = 1 << p1.log_m, m2 = 1 << p2.log_m;           // n2 (column length), n1 (row length)
+    const int G1 = m2 / C, G2 = m1 / C;                           // columns / rows per CTA
+    const int tile = G1 * m1;                                     // = G2 * m2 = n / C elements
+    uint8_t* tile_a = sm;
+    uint8_t* tile_b = sm + (size_t)tile * 32;
+    uint8_t* tw1 = tile_b + (size_t)tile * 32;
+    uint8_t* tw2 = tw1 + (size_t)(m1 >> 1) * 32;
+    for (int k = threadIdx.x; k < (m1 >> 1); k += blockDim.x) store_field(tw1 + (size_t)k * 32, root_at(p1, (size_t)k * p1.unit_m));
+    for (int k = threadIdx.x; k < (m2 >> 1); k += blockDim.x) store_field(tw2 + (size_t)k * 32, root_at(p2, (size_t)k * p2.unit_m));
+    const uint8_t* in = p1.in + (size_t)blockIdx.y * p1.batch_stride * 32;
+    uint8_t* out = p2.out + (size_t)blockIdx.y * p2.out_batch_stride * 32;
+    const size_t col0 = (size_t)r * G1;
+    // pass 1 load: column fastest across threads (consecutive columns are consecutive in memory), bit-reversed row index
+    for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+        const int g = e % G1, row = e / G1;
+        const size_t j = (col0 + g) * p1.in_cstride + (size_t)row * p1.in_rstride;
+        fr_t x = load_field_ro<fr_t>(in + j * 32);
+        if (p1.twist_unit) x = x * load_field_ro<fr_t>(p1.roots + (j * p1.twist_unit) * 32);
+        const int rr = (int)(__brev((unsigned)row) >> (32 - p1.log_m));
+        store_field(tile_a + (size_t)slot(g * m1 + rr) * 32, x);
+    }
+    __syncthreads();
+    tile_butterflies<2>(tile_a, tw1, p1, m1, tile);
+    cluster.sync();                                               // every CTA of the cluster is running: its shared memory can be written
+    // exchange: value (i2 = q, j1 = col) times w_n^(q col) goes to row q's owner, at the bit-reversed position of col in the row
+    for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+        const int g = e % G1, q = e / G1;
+        const size_t col = col0 + g;
+        fr_t x = load_field<fr_t>(tile_a + (size_t)slot(g * m1 + q) * 32);
+        if (q && col) x = x * root_at(p1, (size_t)q * col * p1.tw_unit);
+        const int dst = q / G2, gl = q - dst * G2;
+        const int cc = (int)(__brev((unsigned)col) >> (32 - p2.log_m));
+        uint8_t* remote = cluster.map_shared_rank(tile_b, dst);
+        store_field(remote + (size_t)slot(gl * m2 + cc) * 32, x);
+    }
+    cluster.sync();
+    tile_butterflies<2>(tile_b, tw2, p2, m2, tile);
+    // pass 2 store: row i2 = r G2 + g, output element i1 = q at X[i2 + n2 i1]
+    fr_t sc;
+    if (p2.scale) sc = load_field_ro<fr_t>(p2.scale);
+    for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+        const int g = e % G2, q = e / G2;
+        const size_t i2 = (size_t)r * G2 + g;
+        fr_t x = load_field<fr_t>(tile_b + (size_t)slot(g * m2 + q) * 32);
+        if (p2.scale) x = x * sc;
+        store_field(out + (i2 * p2.out_cstride + (size_t)q * p2.out_rstride) * 32, x);
     }
 }
 
@@ -204,6 +274,8 @@ FFTSettingsDev::FFTSettingsDev(int scale, cudaStream_t st) : scale_(scale) {
     const int max_shm = (kTileElems + (1 << (kMaxLogM - 1))) * 32;
     B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_shm));
     B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_shm));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, kClusterMaxShm));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // clusters of 16
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
@@ -282,6 +354,38 @@ void FFTSettingsDev::transform(const void* in, void* out, int k, bool inverse, i
     }
     int k2 = (k + 1) / 2, k1 = k - k2;  // n2 = 2^k2 (pass 1, strided columns), n1 = 2^k1 (pass 2, contiguous rows)
     size_t n1 = (size_t)1 << k1, n2 = (size_t)1 << k2;
+    // B200_NTT_CLUSTER (per call: tests toggle it): 0 never, 8 / 16 that cluster size for every 2^9 .. 2^14, unset: by size
+    const int cl_env = getenv("B200_NTT_CLUSTER") ? atoi(getenv("B200_NTT_CLUSTER")) : -1;
+    const int max_auto = getenv("B200_NTT_CLUSTER_MAXLOG") ? atoi(getenv("B200_NTT_CLUSTER_MAXLOG")) : 12;
+    int ctas = cl_env == 8 || cl_env == 16 ? cl_env : cl_env == 0 ? 0 : (k <= max_auto ? (k >= 11 ? 16 : 8) : 0);
+    if (ctas == 16 && k1 < 4) ctas = 8;                        // at least one column and one row per CTA
+    if (ctas && k >= kClusterMinLog && k <= kClusterMaxLog && ((size_t)2 * (n / ctas) + (n2 >> 1) + (n1 >> 1)) * 32 <= (size_t)kClusterMaxShm) {
+        // one launch: a cluster of eight CTAs per transform, the inter-pass transpose through distributed shared memory
+        NttPass p2 = p;
+        p.in = (const uint8_t*)in;
+        p.log_m = k2; p.ncols = n1;
+        p.in_cstride = 1; p.in_rstride = n1;
+        p.unit_m = max_width_ >> k2;
+        p.tw_unit = max_width_ >> k; p.twist_unit = twist_unit;
+        p2.out = (uint8_t*)out;
+        p2.log_m = k1; p2.ncols = n2;
+        p2.out_cstride = out_mul; p2.out_rstride = n2 * out_mul;
+        p2.unit_m = max_width_ >> k1;
+        p2.scale = scale_ptr;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)ctas, (unsigned)batch);
+        lc.blockDim = dim3(kNttThreads);
+        lc.dynamicSmemBytes = (2 * (n / ctas) + (n2 >> 1) + (n1 >> 1)) * 32;
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        B200_CUDA_CHECK(cudaLaunchKernelEx(&lc, k_ntt_cluster, p, p2));
+        launches_ += 1;
+        return;
+    }
     // pass 1: for every column j1 < n1, transform the n2 points x[j1 + n1*j2]; times w_n^(i2*j1); in-place layout
     p.in = (const uint8_t*)in; p.out = (uint8_t*)tmp;
     p.out_batch_stride = n;

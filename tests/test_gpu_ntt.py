@@ -54,6 +54,41 @@ def test_fft_matches_oracle(B, K, fs20, logn, inverse):
     assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("logn", [9, 10, 11, 12, 13, 14])
+def test_cluster_kernel_matches_two_passes(B, K, fs20, logn):
+    """2^9 .. 2^14 points run both passes in one launch on a thread-block cluster of eight CTAs with the inter-pass transpose
+    through distributed shared memory (csrc/ntt.cu, k_ntt_cluster); B200_NTT_CLUSTER=0 keeps the two-launch form.  Same limbs from
+    both and from the oracle: forward, inverse, the DAS extension (twisted input) and a batch of five transforms on the device"""
+    import os
+    import torch
+    n = 1 << logn
+    rng = np.random.default_rng(400 + logn)
+    data = rand_fr_mont(rng, 5 * n)
+    ofs = K.FFTSettings(20)
+    res = {}
+    for mode in ("16", "8", "0"):
+        os.environ["B200_NTT_CLUSTER"] = mode
+        try:
+            fwd = fs20.fft_fr(data[:n], False)
+            inv = fs20.fft_fr(data[:n], True)
+            das = fs20.das_fft_extension(data[:n])
+            d_in = torch.from_numpy(data.view(np.int64)).cuda()
+            d_out = torch.zeros_like(d_in)
+            fs20.fft_fr_device(d_out.data_ptr(), d_in.data_ptr(), n, True, 5, 0)
+            torch.cuda.synchronize()
+            res[mode] = (fwd, inv, das, d_out.cpu().numpy().view(np.uint64))
+            assert fs20.launches() == (2 if mode == "0" else 1), (mode, fs20.launches())
+        finally:
+            del os.environ["B200_NTT_CLUSTER"]
+    for mode in ("16", "8"):
+        for a, b in zip(res[mode], res["0"]):
+            assert np.array_equal(a, b), mode
+    assert np.array_equal(res["16"][0], ofs.fft_fr(data[:n], False, nthreads=8))
+    assert np.array_equal(res["16"][1], ofs.fft_fr(data[:n], True, nthreads=8))
+    assert np.array_equal(res["16"][2], ofs.das_fft_extension(data[:n]))
+    assert np.array_equal(res["16"][3][4 * n:], ofs.fft_fr(data[4 * n:], True, nthreads=8))
+
+
 def test_fft_slow_dft_and_roundtrip(B, K):
     """fft_fr vs the O(n^2) DFT at 2^12 and forward/inverse roundtrip (kzg-bench/src/tests/fft_fr.rs:5-46)"""
     fs = B.FFTSettings(12)
