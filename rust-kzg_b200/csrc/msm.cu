@@ -843,39 +843,77 @@ __global__ void __launch_bounds__(128, 3) k_marginals_sub(const uint8_t* __restr
     }
 }
 
-// 6c: one CTA per group, one warp per digit axis: weighted sum over the <= 32 marginals, scale by 2^sh, combine.
-// Everything after the suffix scan runs on quad-distributed points (g1_quad.cuh).
-// marg_r != nullptr (wide windows, see k_segment_fold): the fourth warp sums the 32 plain marginals of the R_hi and the
-// result is 2^kf * (15-bit reduce of the T_hi) - sum R.
-__global__ void __launch_bounds__(128) k_group_finish(const uint8_t* __restrict__ marg, AxisPlan ap,
-                                                      uint8_t* __restrict__ group_sums, uint8_t* __restrict__ out_jac,
-                                                      const uint8_t* __restrict__ marg_r, int kf) {
-    __shared__ __align__(16) uint8_t sh[5 * 192];
-    const size_t g = blockIdx.x;
-    const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
+// 6c: one CTA per group: weighted sums sum_v v * M_(a,v) over the <= 32 marginals of every digit axis a, scaled by 2^sh[a],
+// plus the plain sum (the "+1" of the weights b + 1).  The weights are decomposed into BITS: warp (a, k) sums the marginals
+// whose index has bit k set (one masked quad tree, all 15 of them side by side), then one warp per axis runs the five-bit
+// Horner sum_k 2^k S_(a,k) and its 2^sh[a] -- 38 + 37 us of dependent additions instead of the 65 + 38 us of a five-level
+// suffix scan followed by a tree.  Everything runs on quad-distributed points (g1_quad.cuh).
+// marg_r != nullptr (wide windows, see k_segment_fold): warp 16 sums the 32 plain marginals of the R_hi and the result is
+// 2^kf * (15-bit reduce of the T_hi) - sum R.
+// Launch shape: the 17 sums (15 bit sums, the plain sum, the R sum) are spread over six CTAs of three warps per group, so
+// that every warp keeps its full register budget; the CTA that finishes last (a counter per group) runs the Horner stage.
+static constexpr int kFinSlots = 17, kFinCtas = 6, kFinThreads = 96;
+__global__ void __launch_bounds__(kFinThreads) k_group_finish(const uint8_t* __restrict__ marg, AxisPlan ap,
+                                                              uint8_t* __restrict__ group_sums, uint8_t* __restrict__ out_jac,
+                                                              const uint8_t* __restrict__ marg_r, int kf, uint8_t* __restrict__ scratch,
+                                                              unsigned* __restrict__ counters) {
+    __shared__ __align__(16) uint8_t sh[3 * 192];             // the axis results
+    __shared__ int sh_last;
+    const size_t g = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int w = blockIdx.x * 3 + wid;                       // slot 0 .. 17 (17: idle)
     const int off = quad_store_offset();
-    if (a < ap.D) {
-        xyzz_t m = load_xyzz(marg + ((g * 3 + a) * 32 + lane) * 192);
-        const int width = 1 << ap.w[a];                  // marginals of this axis; the other lanes read infinity
-        xyzz_t suf = warp_suffix_scan_xyzz(m, width);    // Suf_l = sum_{v >= l} M_v ; Suf_0 = sum of all buckets
-        if (a == 0 && lane == 0) store_xyzz(sh + 3 * 192, suf);
-        if (lane == 0) suf = xyzz_t::inf();              // sum_v v*M_v = sum_{k >= 1} Suf_k
-        fp_t w = seg_sum_quad(suf, width < 4 ? 4 : width);
-        for (int k = 0; k < ap.sh[a]; k++) w = quad_dbl(w);
-        if (lane < 4) store_field(sh + a * 192 + off, w);
-    } else if (a == 3 && marg_r) {
-        xyzz_t m = load_xyzz(marg_r + ((g * 3) * 32 + lane) * 192);
-        fp_t w = seg_sum_quad(m, 32);
-        if (lane < 4) store_field(sh + 4 * 192 + off, w);
+    uint8_t* slots = scratch + g * kFinSlots * 192;
+    {
+        const int a = w < 15 ? w / 5 : 0, k = w % 5;
+        const bool bit_warp = w < 15 && a < ap.D && k < ap.w[a];
+        const bool plain_warp = w == 15, r_warp = w == 16 && marg_r != nullptr;
+        if (bit_warp || plain_warp || r_warp) {
+            const uint8_t* src = r_warp ? marg_r + ((g * 3) * 32 + lane) * 192 : marg + ((g * 3 + a) * 32 + lane) * 192;
+            xyzz_t m = load_xyzz(src);                         // lanes beyond the axis width read infinity
+            if (bit_warp && !((lane >> k) & 1)) m = xyzz_t::inf();
+            fp_t q = seg_sum_quad(m, 32);
+            if (lane < 4) store_field(slots + w * 192 + off, q);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(&counters[g], 1u);
+        sh_last = done == gridDim.x - 1;
+        if (sh_last) counters[g] = 0;                         // ready for the next run
     }
     __syncthreads();
-    if (a == 0) {
-        fp_t acc = load_field<fp_t>(sh + 3 * 192 + off);  // the "+1" of the weights b+1
-        for (int k = 0; k < ap.D; k++) acc = quad_add(acc, load_field<fp_t>(sh + k * 192 + off));
+    if (!sh_last) return;
+    __threadfence();
+    auto slot = [&](int idx) {                                // written by other CTAs: read through L2
+        fp_t v;
+        const uint4* src = reinterpret_cast<const uint4*>(slots + idx * 192 + off);
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            uint4 t = __ldcg(src + q);
+            v.v[4 * q] = t.x; v.v[4 * q + 1] = t.y; v.v[4 * q + 2] = t.z; v.v[4 * q + 3] = t.w;
+        }
+        return v;
+    };
+    if (wid < ap.D) {
+        const int a = wid, top = ap.w[a] - 1;                  // Horner over the bits of the digit, then the digit's position
+        fp_t acc = top >= 0 ? slot(a * 5 + top) : fp_t::zero();
+        for (int k = top - 1; k >= 0; k--) {
+            acc = quad_dbl(acc);
+            acc = quad_add(acc, slot(a * 5 + k));
+        }
+        for (int k = 0; k < ap.sh[a]; k++) acc = quad_dbl(acc);
+        if (lane < 4) store_field(sh + a * 192 + off, acc);
+    }
+    __syncthreads();
+    if (wid == 0) {
+        fp_t acc = slot(15);                                  // the "+1" of the weights b+1: plain sum of all buckets (axis 0 marginals)
+        for (int a = 0; a < ap.D; a++) acc = quad_add(acc, load_field<fp_t>(sh + a * 192 + off));
         if (marg_r) {
             for (int k = 0; k < kf; k++) acc = quad_dbl(acc);
-            fp_t r = load_field<fp_t>(sh + 4 * 192 + off);
-            if ((lane & 3) == 1) r = r.neg();             // -(X, Y, ZZ, ZZZ) = (X, -Y, ZZ, ZZZ); infinity stays all-zero
+            fp_t r = slot(16);
+            if ((lane & 3) == 1) r = r.neg();                 // -(X, Y, ZZ, ZZZ) = (X, -Y, ZZ, ZZZ); infinity stays all-zero
             acc = quad_add(acc, r);
         }
         if (group_sums && lane < 4) store_field(group_sums + g * 192 + off, acc);
@@ -1173,6 +1211,9 @@ MsmEngine::MsmEngine(const MsmConfig& cfg, const void* points, bool host_points,
     scan_tmp_ = dev_alloc<uint32_t>(kScanBlock * kScanItems + 1);
     partials_ = dev_alloc<uint8_t>(tasks_max_ * 192);
     chunk_sums_ = dev_alloc<uint8_t>(groups_max_ * 3 * 32 * 192);  // marginal sums [group][axis][32]
+    fin_scratch_ = dev_alloc<uint8_t>(groups_max_ * kFinSlots * 192);   // k_group_finish: bit sums of every group
+    fin_cnt_ = dev_alloc<unsigned>(groups_max_);
+    B200_CUDA_CHECK(cudaMemsetAsync(fin_cnt_, 0, groups_max_ * sizeof(unsigned), stream));
     group_sums_ = dev_alloc<uint8_t>(groups_max_ * 192);
     kf_ = std::max(cfg_.c - 1 > kReduceBits ? cfg_.c - 1 - kReduceBits : 0, std::min(cfg_.fold, cfg_.c - 2));
     if (kf_ > 0) {
@@ -1262,7 +1303,7 @@ MsmEngine::~MsmEngine() {
     cudaFree(first_slot_); cudaFree(acc_buf_);
     if (owns_table_) cudaFree(table_);
     cudaFree(counts_); cudaFree(offsets_); cudaFree(cursor_); cudaFree(task_base_); cudaFree(entries_);
-    cudaFree(sorted_tasks_); cudaFree(size_hist_); cudaFree(scan_tmp_); cudaFree(partials_); cudaFree(chunk_sums_);
+    cudaFree(sorted_tasks_); cudaFree(size_hist_); cudaFree(scan_tmp_); cudaFree(partials_); cudaFree(chunk_sums_); cudaFree(fin_scratch_); cudaFree(fin_cnt_);
     cudaFree(group_sums_);
     cudaFree(seg_t_); cudaFree(seg_r_); cudaFree(seg_ident_); cudaFree(chunk_sums_r_);
 }
@@ -1457,10 +1498,12 @@ void MsmEngine::run(const void* scalars_dev, size_t npoints, int batch, bool mon
     }
     const uint8_t* marg_r = kf ? (const uint8_t*)chunk_sums_r_ : nullptr;
     if (cfg_.fixed) {
-        k_group_finish<<<(unsigned)groups, 128, 0, st>>>((const uint8_t*)chunk_sums_, ap, nullptr, (uint8_t*)out_dev, marg_r, kf);
+        k_group_finish<<<dim3(kFinCtas, (unsigned)groups), kFinThreads, 0, st>>>((const uint8_t*)chunk_sums_, ap, nullptr, (uint8_t*)out_dev, marg_r, kf,
+                                                                              (uint8_t*)fin_scratch_, fin_cnt_);
         launches += 1;
     } else {
-        k_group_finish<<<(unsigned)groups, 128, 0, st>>>((const uint8_t*)chunk_sums_, ap, (uint8_t*)group_sums_, nullptr, marg_r, kf);
+        k_group_finish<<<dim3(kFinCtas, (unsigned)groups), kFinThreads, 0, st>>>((const uint8_t*)chunk_sums_, ap, (uint8_t*)group_sums_, nullptr, marg_r, kf,
+                                                                              (uint8_t*)fin_scratch_, fin_cnt_);
         k_horner<<<1, 32, 0, st>>>((const uint8_t*)group_sums_, W, c, (uint8_t*)out_dev);
         launches += 2;
     }

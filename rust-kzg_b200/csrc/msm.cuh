@@ -133,6 +133,8 @@ private:
     bool last_affine_ = false;          // the last run() took the batch-affine path
     void* partials_ = nullptr;  // xyzz per task
     void* chunk_sums_ = nullptr;
+    void* fin_scratch_ = nullptr;      // k_group_finish: 17 partial sums per group
+    unsigned* fin_cnt_ = nullptr;      // ... and its completion counters (zero between runs)
     void* group_sums_ = nullptr;
     void* seg_t_ = nullptr;            // wide windows (c > 16): per-segment sums T and running sums R, see k_segment_fold
     void* seg_r_ = nullptr;
