@@ -11,6 +11,7 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -418,20 +419,88 @@ void challenge_hash(uint8_t out[32], const uint8_t* blob, const uint8_t* commitm
     c.update(commitment, 48);
     c.finish(out);
 }
-void challenge_hash_many(uint8_t* out32, const uint8_t* blobs, const uint8_t* commitments, size_t n) {
+// Host worker pool for the Fiat-Shamir hashes of a batch (SHA-256 over 128 KiB per blob, ~77 us each with SHA-NI): the hashes
+// gate the quotient kernel and the MSM, so they are spread over the host cores; the workers are created once per process and
+// woken per batch (spawning 16 threads per call cost about as much as hashing four blobs on each of them).
+class HashPool {
+public:
+    // begin(): job(i) for i in [0, n) starts on up to width - 1 workers; finish(): the calling thread joins in and returns when
+    // all are done.  Whatever the caller does in between (a blocking copy of pageable blobs) overlaps the hashing.
+    // One batch at a time: concurrent callers queue in begin().  `job` must stay alive until finish() returns.
+    void begin(size_t n, size_t width, const std::function<void(size_t)>& job) {
+        call_mu_.lock();
+        width = std::max<size_t>(1, std::min(width, n));
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while (workers_.size() + 1 < width) workers_.emplace_back([this] { loop(); });
+            job_ = &job; n_ = n; next_.store(0); live_ = width - 1; pending_ = width - 1; gen_++;
+        }
+        if (width > 1) cv_.notify_all();
+    }
+    void finish() {
+        const std::function<void(size_t)>& job = *job_;
+        const size_t n = n_;
+        for (size_t i; (i = next_.fetch_add(1)) < n;) job(i);
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            done_cv_.wait(lk, [&] { return pending_ == 0; });
+            job_ = nullptr;
+        }
+        call_mu_.unlock();
+    }
+    void run(size_t n, size_t width, const std::function<void(size_t)>& job) {
+        begin(n, width, job);
+        finish();
+    }
+    ~HashPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+
+private:
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(size_t)>* job;
+            size_t n;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || (gen_ != seen && live_ > 0); });
+                if (stop_) return;
+                seen = gen_;
+                live_--;                                       // this worker takes part in the current batch
+                job = job_; n = n_;
+            }
+            for (size_t i; (i = next_.fetch_add(1)) < n;) (*job)(i);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_cv_.notify_one();
+        }
+    }
+    std::mutex call_mu_, mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> workers_;
+    const std::function<void(size_t)>* job_ = nullptr;
+    size_t n_ = 0, live_ = 0, pending_ = 0;
+    std::atomic<size_t> next_{0};
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+HashPool& hash_pool() {
+    static HashPool pool;
+    return pool;
+}
+size_t hash_width(size_t n) {
     unsigned hw = std::thread::hardware_concurrency();
     size_t nt = std::min<size_t>(n, hw ? hw : 1);
-    nt = std::min<size_t>(nt, (size_t)env_int("B200_SHA_THREADS", 16));
-    if (nt <= 1) {
-        for (size_t i = 0; i < n; i++) challenge_hash(out32 + 32 * i, blobs + i * kBytesPerBlob, commitments + 48 * i);
-        return;
-    }
-    std::vector<std::thread> th;
-    for (size_t t = 0; t < nt; t++)
-        th.emplace_back([=] {
-            for (size_t i = t; i < n; i += nt) challenge_hash(out32 + 32 * i, blobs + i * kBytesPerBlob, commitments + 48 * i);
-        });
-    for (auto& x : th) x.join();
+    return std::min<size_t>(nt, (size_t)env_int("B200_SHA_THREADS", 16));
+}
+void challenge_hash_many(uint8_t* out32, const uint8_t* blobs, const uint8_t* commitments, size_t n) {
+    hash_pool().run(n, hash_width(n), [&](size_t i) { challenge_hash(out32 + 32 * i, blobs + i * kBytesPerBlob, commitments + 48 * i); });
 }
 
 template <class F>
@@ -489,11 +558,18 @@ void enqueue_blob_proof(KzgCtx& ctx, int lane, const uint8_t* blobs, const uint8
     B200_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.ev_in, 0));
     ctx.dev->validate_commitments(g.d_comm, m, g.d_status2, g.side);
     B200_CUDA_CHECK(cudaEventRecord(g.ev_side, g.side));
-    B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
     if (!z_hashed) {
-        // the hash chain runs on the host while the blobs cross PCIe (and the other lanes compute)
-        challenge_hash_many(g.h_z(), blobs, commitments, m);
-        z_hashed = g.h_z();
+        // the hash chain runs on the host workers while the blobs cross PCIe (and the other lanes compute); the copy of
+        // PAGEABLE blobs blocks this thread while the driver stages them, so the workers are started first
+        uint8_t* hz = g.h_z();
+        const std::function<void(size_t)> job = [=](size_t i) { challenge_hash(hz + 32 * i, blobs + i * kBytesPerBlob, commitments + 48 * i); };
+        hash_pool().begin(m, hash_width(m), job);
+        cudaError_t e = cudaMemcpyAsync(g.d_blobs, blobs, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream);
+        hash_pool().finish();
+        B200_CUDA_CHECK(e);
+        z_hashed = hz;
+    } else {
+        B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, blobs, (size_t)m * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
     }
     B200_CUDA_CHECK(cudaMemcpyAsync(g.d_z, z_hashed, (size_t)m * 32, cudaMemcpyHostToDevice, g.stream));
     ctx.dev->compute_proofs(g.d_blobs, g.d_z, 1, m, g.d_out48, nullptr, g.d_status, g.stream, lane);
