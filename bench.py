@@ -609,6 +609,15 @@ def thread_metrics():
             rec["e2e_threads%d_blobs_per_s" % t] = line.get("per_s")
             rec["threads%d_bit_exact" % t] = bool(r.returncode == 0 and line.get("mismatches") == 0 and line.get("errors") == 0)
         out[key] = rec
+    # compute_cells_and_kzg_proofs per blob from 1 / 9 threads (a block's blobs under a parallel iterator): shared FK20 passes
+    rec = {}
+    for t in (1, 9):
+        r = subprocess.run([exe, setup, "cells", str(t), "12", "2"], capture_output=True, text=True, timeout=300)
+        line = json.loads(r.stdout.strip().splitlines()[-1]) if r.stdout.strip() else {"error": r.stderr[-200:]}
+        rec["e2e_threads%d_blobs_per_s" % t] = line.get("per_s")
+        rec["threads%d_mean_batch" % t] = line.get("mean_batch")
+        rec["threads%d_bit_exact" % t] = bool(r.returncode == 0 and line.get("mismatches") == 0 and line.get("errors") == 0)
+    out["compute_cells_and_kzg_proofs"] = rec
     return out
 
 

@@ -5,7 +5,7 @@
  *
  *   gcc -O2 -pthread -Iinclude examples/ckzg_threads.c -Lrust-kzg_b200 -lb200kzg -Wl,-rpath,$PWD/rust-kzg_b200 -o /tmp/ckzg_threads
  *   /tmp/ckzg_threads rust-kzg_b200/data/trusted_setup.txt <op> <threads> <calls_per_thread> [distinct_blobs]
- *     op: commit | proof | blob_proof | mixed      (mixed: thread t runs op t % 3)
+ *     op: commit | proof | blob_proof | mixed | cells   (mixed: thread t runs op t % 3; cells: compute_cells_and_kzg_proofs)
  *
  * Every thread first computes its reference outputs with ONE thread active (nothing to coalesce with), then all threads
  * run concurrently and every result is compared byte for byte with the single-threaded one.  Prints one JSON line:
@@ -20,7 +20,7 @@
 
 #include "b200_kzg.h"
 
-enum { OP_COMMIT = 0, OP_PROOF = 1, OP_BLOB_PROOF = 2, OP_MIXED = 3 };
+enum { OP_COMMIT = 0, OP_PROOF = 1, OP_BLOB_PROOF = 2, OP_MIXED = 3, OP_CELLS = 4 };
 
 typedef struct {
     int id, op, calls, nblobs;
@@ -29,6 +29,8 @@ typedef struct {
     Bytes48 *commit;      /* per blob: reference commitment */
     Bytes48 *proof;       /* per blob: reference proof of this thread's op */
     Bytes32 *y;           /* per blob: reference y (OP_PROOF) */
+    Cell *ref_cells;      /* per blob: 128 reference cells (OP_CELLS) */
+    KZGProof *ref_cproofs; /* per blob: 128 reference cell proofs (OP_CELLS) */
     Bytes32 z;
     long mismatches, errors;
     pthread_barrier_t *start;
@@ -50,9 +52,18 @@ static int run_one(const Worker *w, int b, Bytes48 *out, Bytes32 *y) {
 
 static void *worker_main(void *arg) {
     Worker *w = (Worker *)arg;
+    Cell *cells = w->op == OP_CELLS ? (Cell *)malloc(128 * sizeof(Cell)) : NULL;
+    KZGProof *cproofs = w->op == OP_CELLS ? (KZGProof *)malloc(128 * sizeof(KZGProof)) : NULL;
     pthread_barrier_wait(w->start);
     for (int i = 0; i < w->calls; i++) {
         int b = i % w->nblobs;
+        if (w->op == OP_CELLS) {
+            memset(cproofs, 0, 128 * sizeof(KZGProof));
+            if (compute_cells_and_kzg_proofs(cells, cproofs, &w->blobs[b], w->s) != C_KZG_OK) { w->errors++; continue; }
+            if (memcmp(cells, w->ref_cells + (size_t)b * 128, 128 * sizeof(Cell)) != 0) w->mismatches++;
+            if (memcmp(cproofs, w->ref_cproofs + (size_t)b * 128, 128 * sizeof(KZGProof)) != 0) w->mismatches++;
+            continue;
+        }
         Bytes48 out;
         Bytes32 y;
         memset(&out, 0, sizeof out);
@@ -62,14 +73,16 @@ static void *worker_main(void *arg) {
         if (memcmp(&out, want, 48) != 0) w->mismatches++;
         if (w->op == OP_PROOF && memcmp(&y, &w->y[b], 32) != 0) w->mismatches++;
     }
+    free(cells);
+    free(cproofs);
     return NULL;
 }
 
 int main(int argc, char **argv) {
-    if (argc < 5) { fprintf(stderr, "usage: %s trusted_setup.txt commit|proof|blob_proof|mixed threads calls_per_thread [distinct_blobs]\n", argv[0]); return 2; }
+    if (argc < 5) { fprintf(stderr, "usage: %s trusted_setup.txt commit|proof|blob_proof|mixed|cells threads calls_per_thread [distinct_blobs]\n", argv[0]); return 2; }
     const char *opname = argv[2];
     int op = !strcmp(opname, "commit") ? OP_COMMIT : !strcmp(opname, "proof") ? OP_PROOF : !strcmp(opname, "blob_proof") ? OP_BLOB_PROOF
-             : !strcmp(opname, "mixed") ? OP_MIXED : -1;
+             : !strcmp(opname, "mixed") ? OP_MIXED : !strcmp(opname, "cells") ? OP_CELLS : -1;
     int T = atoi(argv[3]), calls = atoi(argv[4]), nblobs = argc > 5 ? atoi(argv[5]) : 4;
     if (op < 0 || T < 1 || T > 256 || calls < 1 || nblobs < 1) { fprintf(stderr, "bad arguments\n"); return 2; }
     FILE *f = fopen(argv[1], "r");
@@ -98,11 +111,22 @@ int main(int argc, char **argv) {
         /* single-threaded reference outputs: nothing else is in flight, so each call is a batch of one */
         for (int b = 0; b < nblobs; b++) {
             if (blob_to_kzg_commitment(&w[t].commit[b], &w[t].blobs[b], &s) != C_KZG_OK) { fprintf(stderr, "reference commitment failed\n"); return 4; }
+            if (w[t].op == OP_CELLS) continue;
             if (w[t].op != OP_COMMIT && run_one(&w[t], b, &w[t].proof[b], &w[t].y[b]) != C_KZG_OK) { fprintf(stderr, "reference proof failed\n"); return 4; }
+        }
+        if (w[t].op == OP_CELLS) {
+            w[t].ref_cells = (Cell *)malloc((size_t)nblobs * 128 * sizeof(Cell));
+            w[t].ref_cproofs = (KZGProof *)malloc((size_t)nblobs * 128 * sizeof(KZGProof));
+            for (int b = 0; b < nblobs; b++)
+                if (compute_cells_and_kzg_proofs(w[t].ref_cells + (size_t)b * 128, w[t].ref_cproofs + (size_t)b * 128, &w[t].blobs[b], &s) != C_KZG_OK) {
+                    fprintf(stderr, "reference cells failed\n"); return 4;
+                }
         }
     }
     uint64_t st0[5], st[5];
     b200_kzg_coalesce_stats(&s, st0);          /* counters up to here belong to the single-threaded reference pass */
+    uint64_t cst0[2];
+    b200_kzg_cells_coalesce_stats(&s, cst0);
     pthread_t *th = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
     for (int t = 0; t < T; t++) pthread_create(&th[t], NULL, worker_main, &w[t]);
     pthread_barrier_wait(&start);
@@ -112,6 +136,11 @@ int main(int argc, char **argv) {
     double dt = now_s() - t0;
     b200_kzg_coalesce_stats(&s, st);
     for (int i = 0; i < 4; i++) st[i] -= st0[i];
+    if (op == OP_CELLS) {                       /* its own queue: batches and requests only */
+        uint64_t cs[2];
+        b200_kzg_cells_coalesce_stats(&s, cs);
+        st[0] = cs[0] - cst0[0]; st[1] = cs[1] - cst0[1]; st[2] = st[3] = st[4] = 0;
+    }
     /* an invalid blob among valid concurrent callers must fail alone (per-request status, not per-batch) */
     long isolation_failures = 0;
     {

@@ -236,6 +236,9 @@ B200_API int b200_kzg_max_batch(const KZGSettings *s);
  * Counters since load: out = [batches run, requests served, ns leaders waited for a device lane, ns batches spent on a
  * lane, largest batch].  B200_KZG_COALESCE=1 disables packing, B200_KZG_LANES=k limits the lanes single calls may use. */
 B200_API void b200_kzg_coalesce_stats(const KZGSettings *s, uint64_t out[5]);
+/* compute_cells_and_kzg_proofs (with proofs) is coalesced the same way, in batches of up to 16 blobs (B200_KZG_CELLS_COALESCE;
+ * 1 disables it): a block's blobs under a parallel iterator share one FK20 pass.  out = [batches run, requests served]. */
+B200_API void b200_kzg_cells_coalesce_stats(const KZGSettings *s, uint64_t out[2]);
 /* Direct-lookup tables held by a settings object: out = [window bits of the Lagrange-point table (13 by default,
  * 11 / 8 when HBM is short, 0 = none: bucket engine), largest blob batch it serves, window bits of the FK20 column table (0
  * before the first cell-proof call)].  Knobs: B200_BLOB_DIRECT, B200_BLOB_DIRECT_BITS, B200_FK20_DIRECT, B200_FK20_DIRECT_BITS,

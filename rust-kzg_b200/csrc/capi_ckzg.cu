@@ -131,14 +131,34 @@ struct CoBatch : CoBatchBase {
     }
 };
 typedef CoQueue<CoBatch, CO_KINDS> Coalescer;
+// compute_cells_and_kzg_proofs called per blob from several threads (a block's blobs under rayon par_iter): its own queue --
+// 128 cells + 128 proofs per request, batches of up to 16 blobs (the size the fused fft_g1 stages still serve)
+struct CellsBatch : CoBatchBase {
+    uint8_t *h_in = nullptr, *h_cells = nullptr, *h_proofs = nullptr;   // pinned: cap blobs / cap x 128 x 2048 / cap x 128 x 48
+    int* h_status = nullptr;                                              // pinned: cap
+    int cap = 0;
+    uint8_t* blob(int i) { return h_in + (size_t)i * kBytesPerBlob; }
+    uint8_t* cells(int i) { return h_cells + (size_t)i * 128 * 2048; }
+    uint8_t* proofs(int i) { return h_proofs + (size_t)i * 128 * 48; }
+    ~CellsBatch() {
+        if (h_in) cudaFreeHost(h_in);
+        if (h_cells) cudaFreeHost(h_cells);
+        if (h_proofs) cudaFreeHost(h_proofs);
+        if (h_status) cudaFreeHost(h_status);
+    }
+};
+typedef CoQueue<CellsBatch, 1> CellsCoalescer;
 
 struct KzgCtx {
     LanePool pool;
     Coalescer co;
+    CellsCoalescer co_cells;
+    int cells_cap = 16;        // most single-blob cells + proofs requests per launch sequence (B200_KZG_CELLS_COALESCE; 1: none)
     int device = 0;            // CUDA device the context lives on: every entry point switches to it (DeviceScope)
     int co_cap = 0;            // most single-blob requests packed into one launch sequence (<= max_batch)
     // coalescer counters (b200_kzg_coalesce_stats): batches run, requests served, ns spent waiting for a lane, ns on a lane
     std::atomic<uint64_t> st_batches{0}, st_requests{0}, st_wait_ns{0}, st_exec_ns{0}, st_max_batch{0};
+    std::atomic<uint64_t> st_cells_batches{0}, st_cells_requests{0};   // the same for coalesced compute_cells_and_kzg_proofs
     std::unique_ptr<KzgSettingsDev> dev;
     int max_batch = 0;
     Stage stage[KzgSettingsDev::kLanes];
@@ -285,6 +305,8 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
         ctx->max_batch = env_int("B200_KZG_MAX_BATCH", 64);
         if (ctx->max_batch < 1) ctx->max_batch = 1;
         ctx->co_cap = std::max(1, std::min(ctx->max_batch, env_int("B200_KZG_COALESCE", ctx->max_batch)));
+        ctx->cells_cap = std::max(1, std::min(std::min(ctx->max_batch, 64), env_int("B200_KZG_CELLS_COALESCE", 16)));
+        ctx->co_cells.max_batches = 2;
         ctx->co.max_batches = KzgSettingsDev::kLanes + 2;   // one per lane in flight + the ones filling
         {
             const int lanes = std::max(1, std::min((int)KzgSettingsDev::kLanes, env_int("B200_KZG_LANES", KzgSettingsDev::kLanes)));
@@ -642,6 +664,69 @@ C_KZG_RET coalesced_call(KzgCtx& ctx, int kind, const uint8_t* blob, const uint8
     return rc;
 }
 
+// One compute_cells_and_kzg_proofs request (proofs wanted; cells optional): concurrent callers share one pass over up to
+// cells_cap blobs.  The leader takes every lane (the FK20 workspace is the settings object's, not a lane's); while a batch
+// runs the next one fills.  Each caller copies its own 256 KiB of cells and 6 KiB of proofs out of the pinned staging.
+C_KZG_RET coalesced_cells_call(KzgCtx& ctx, const uint8_t* blob, uint8_t* cells_out, uint8_t* proofs_out) {
+    CellsCoalescer& co = ctx.co_cells;
+    const int cap = ctx.cells_cap;
+    CellsCoalescer::Claim cl = co.claim(0, cap, [&] {
+        std::unique_ptr<CellsBatch> nb(new CellsBatch());
+        nb->cap = cap;
+        DeviceScope ds(ctx.device);
+        B200_CUDA_CHECK(cudaMallocHost((void**)&nb->h_in, (size_t)cap * kBytesPerBlob));
+        B200_CUDA_CHECK(cudaMallocHost((void**)&nb->h_cells, (size_t)cap * 128 * 2048));
+        B200_CUDA_CHECK(cudaMallocHost((void**)&nb->h_proofs, (size_t)cap * 128 * 48));
+        B200_CUDA_CHECK(cudaMallocHost((void**)&nb->h_status, (size_t)cap * sizeof(int)));
+        return nb;
+    });
+    CellsBatch* B = cl.b;
+    const int idx = cl.idx;
+    memcpy(B->blob(idx), blob, kBytesPerBlob);
+    CellsCoalescer::staged(B);
+    if (cl.leader) {
+        int rc = C_KZG_OK;
+        try {
+            DeviceScope ds(ctx.device);
+            AllLanes lk(ctx);   // blocks while the previous batch (or any other user of the lanes) runs: meanwhile this one fills
+            const int n = co.close(B);
+            Stage& g = ctx.stage[0];
+            ctx.dev->fk20_batch(g.stream);
+            if (!ctx.d_cells) ctx.d_cells = dev_alloc<uint8_t>((size_t)ctx.max_batch * 128 * 2048);
+            if (!ctx.d_proofs) ctx.d_proofs = dev_alloc<uint8_t>((size_t)ctx.dev->fk20_batch(g.stream) * 128 * 48);
+            B200_CUDA_CHECK(cudaMemcpyAsync(g.d_blobs, B->h_in, (size_t)n * kBytesPerBlob, cudaMemcpyHostToDevice, g.stream));
+            B200_CUDA_CHECK(cudaMemsetAsync(g.d_status, 0, n * sizeof(int), g.stream));
+            ctx.dev->compute_cells_and_proofs(g.d_blobs, n, ctx.d_cells, ctx.d_proofs, g.d_status, g.stream, g.ev_side);
+            B200_CUDA_CHECK(cudaMemcpyAsync(B->h_proofs, ctx.d_proofs, (size_t)n * 128 * 48, cudaMemcpyDeviceToHost, g.stream));
+            B200_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.ev_side, 0));          // status + cells leave under the FK20 kernels
+            B200_CUDA_CHECK(cudaMemcpyAsync(B->h_status, g.d_status, n * sizeof(int), cudaMemcpyDeviceToHost, g.side));
+            B200_CUDA_CHECK(cudaMemcpyAsync(B->h_cells, ctx.d_cells, (size_t)n * 128 * 2048, cudaMemcpyDeviceToHost, g.side));
+            B200_CUDA_CHECK(cudaStreamSynchronize(g.side));
+            B200_CUDA_CHECK(cudaStreamSynchronize(g.stream));
+            ctx.st_cells_batches++;
+            ctx.st_cells_requests += (uint64_t)n;
+        } catch (const std::exception& e) {
+            cudaGetLastError();
+            fprintf(stderr, "b200kzg: %s\n", e.what());
+            rc = C_KZG_ERROR;
+        }
+        co.publish(B, rc);
+    } else {
+        co.wait(B);
+    }
+    C_KZG_RET rc = (C_KZG_RET)B->rc;
+    if (rc == C_KZG_OK) {
+        if (B->h_status[idx]) {
+            rc = C_KZG_BADARGS;                                                    // this caller's blob is invalid: it fails alone
+        } else {
+            if (cells_out) memcpy(cells_out, B->cells(idx), (size_t)128 * 2048);
+            if (proofs_out) memcpy(proofs_out, B->proofs(idx), (size_t)128 * 48);
+        }
+    }
+    co.consume(B);
+    return rc;
+}
+
 }  // namespace
 
 extern "C" {
@@ -885,8 +970,14 @@ C_KZG_RET b200_compute_cells_and_kzg_proofs_batch(Cell* cells, KZGProof* proofs,
 }
 // kzg/src/eth/c_bindings.rs:134-199 (eip7594 macro): either output may be NULL, not both (kzg/src/das.rs:250-252)
 C_KZG_RET compute_cells_and_kzg_proofs(Cell* cells, KZGProof* proofs, const Blob* blob, const KZGSettings* s) {
-    if (!blob) return C_KZG_BADARGS;
-    return b200_compute_cells_and_kzg_proofs_batch(cells, proofs, blob, 1, s);
+    if (!blob || (!cells && !proofs)) return C_KZG_BADARGS;
+    if (!proofs) return b200_compute_cells_batch(cells, blob, 1, s);            // cells alone: two NTTs, nothing to share
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx) return C_KZG_BADARGS;
+        if (ctx->cells_cap < 2) return b200_compute_cells_and_kzg_proofs_batch(cells, proofs, blob, 1, s);
+        return coalesced_cells_call(*ctx, blob->bytes, (uint8_t*)cells, (uint8_t*)proofs);
+    });
 }
 
 // ---- verification (blst/src/eip_4844.rs:383-471) -----------------------------------------------------------------
@@ -1286,6 +1377,14 @@ void b200_kzg_direct_tables(const KZGSettings* s, int out[3]) {
     out[0] = ctx->dev->direct_bits();
     out[1] = ctx->dev->direct_max_batch();
     out[2] = ctx->dev->fk_direct_bits();
+}
+// the same counters for coalesced compute_cells_and_kzg_proofs calls: out = [batches run, requests served]
+void b200_kzg_cells_coalesce_stats(const KZGSettings* s, uint64_t out[2]) {
+    auto ctx = find_ctx(s);
+    if (!out) return;
+    out[0] = out[1] = 0;
+    if (!ctx) return;
+    out[0] = ctx->st_cells_batches; out[1] = ctx->st_cells_requests;
 }
 int b200_kzg_max_batch(const KZGSettings* s) {
     auto ctx = find_ctx(s);

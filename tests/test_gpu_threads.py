@@ -134,6 +134,52 @@ def test_sixteen_threads_mixed_entry_points_coalesce_bit_exact(B, K, oracle_sett
     assert not errors, errors
 
 
+def test_concurrent_cells_and_proofs_coalesce_bit_exact(B, K, oracle_settings):
+    """compute_cells_and_kzg_proofs called per blob from nine threads (a block's blobs under a parallel iterator) shares FK20
+    passes (csrc/capi_ckzg.cu, coalesced_cells_call): every caller gets exactly the cells and proofs of the sequential call,
+    blob 0's equal the oracle's, an invalid blob fails alone, and calls mixed in from the other entry points still work"""
+    ts = B.KZGSettings.load_trusted_setup_file()
+    rng = np.random.default_rng(35)
+    blobs = _blobs(rng, 6)
+    want = [ts.compute_cells_and_kzg_proofs(b) for b in blobs]            # sequential: batches of one
+    oracle_settings.set_threads(8)
+    oc, op = K.compute_cells_and_kzg_proofs(bytes(blobs[0]), oracle_settings)
+    oracle_settings.set_threads(1)
+    assert want[0][0] == oc and want[0][1] == op
+    want_c = [ts.blob_to_kzg_commitment(b) for b in blobs]
+    bad = blobs[1].copy()
+    bad[32 * 100] = 0xFF
+    b0, r0 = ts.cells_coalesce_stats()
+    errors = []
+    start = threading.Barrier(9)
+
+    def worker(k):
+        try:
+            start.wait()
+            for rep in range(4):
+                i = (k + rep) % len(blobs)
+                if k == 8 and rep % 2 == 0:
+                    with pytest.raises(B.KzgError) as e:
+                        ts.compute_cells_and_kzg_proofs(bad)
+                    assert e.value.code == 1
+                    assert ts.blob_to_kzg_commitment(blobs[i]) == want_c[i]
+                else:
+                    cells, proofs = ts.compute_cells_and_kzg_proofs(blobs[i])
+                    assert cells == want[i][0] and proofs == want[i][1], (k, rep)
+        except Exception as e:
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(9)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    b1, r1 = ts.cells_coalesce_stats()
+    ts.free()
+    assert not errors, errors
+    assert r1 - r0 == 36 and b1 - b0 < 36, (b0, r0, b1, r1)              # some batches carried more than one request
+
+
 def test_concurrent_prepared_msm_coalesces(B, K, lagrange_affine):
     """a prepared 4096-point handle packs concurrent mult_pippenger_prepared calls (different lengths included: short
     calls are zero-padded) into one launch sequence; each caller gets its own sum"""
