@@ -153,6 +153,7 @@ struct KzgCtx {
     LanePool pool;
     Coalescer co;
     CellsCoalescer co_cells;
+    int cells_grace_us = 200;  // how long a leader lingers for the rest of a burst (B200_KZG_CELLS_GRACE_US; 0: not at all)
     int cells_cap = 16;        // most single-blob cells + proofs requests per launch sequence (B200_KZG_CELLS_COALESCE; 1: none)
     int device = 0;            // CUDA device the context lives on: every entry point switches to it (DeviceScope)
     int co_cap = 0;            // most single-blob requests packed into one launch sequence (<= max_batch)
@@ -307,6 +308,7 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
         ctx->co_cap = std::max(1, std::min(ctx->max_batch, env_int("B200_KZG_COALESCE", ctx->max_batch)));
         ctx->cells_cap = std::max(1, std::min(std::min(ctx->max_batch, 64), env_int("B200_KZG_CELLS_COALESCE", 16)));
         ctx->co_cells.max_batches = 2;
+        ctx->cells_grace_us = std::max(0, env_int("B200_KZG_CELLS_GRACE_US", 200));
         ctx->co.max_batches = KzgSettingsDev::kLanes + 2;   // one per lane in flight + the ones filling
         {
             const int lanes = std::max(1, std::min((int)KzgSettingsDev::kLanes, env_int("B200_KZG_LANES", KzgSettingsDev::kLanes)));
@@ -689,6 +691,21 @@ C_KZG_RET coalesced_cells_call(KzgCtx& ctx, const uint8_t* blob, uint8_t* cells_
         try {
             DeviceScope ds(ctx.device);
             AllLanes lk(ctx);   // blocks while the previous batch (or any other user of the lanes) runs: meanwhile this one fills
+            // A burst of callers (a block's blobs from a parallel iterator) arrives within microseconds of each other; the
+            // pass takes ~5 ms whatever its size, so the leader lingers while claims keep coming in (at most 200 us, and
+            // no longer than 60 us after the last one) instead of leaving the rest of the burst to the next pass.
+            if (ctx.cells_grace_us > 0) {
+                const auto t0 = std::chrono::steady_clock::now();
+                auto last_change = t0;
+                int seen = co.claimed_so_far(B);
+                while (seen < cap) {
+                    std::this_thread::sleep_for(std::chrono::microseconds(15));
+                    const auto now = std::chrono::steady_clock::now();
+                    const int c = co.claimed_so_far(B);
+                    if (c != seen) { seen = c; last_change = now; }
+                    if (now - last_change > std::chrono::microseconds(60) || now - t0 > std::chrono::microseconds(ctx.cells_grace_us)) break;
+                }
+            }
             const int n = co.close(B);
             Stage& g = ctx.stage[0];
             ctx.dev->fk20_batch(g.stream);

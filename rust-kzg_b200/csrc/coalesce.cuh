@@ -70,6 +70,11 @@ struct CoQueue {
         }
     }
     static void staged(Batch* b) { b->ready.fetch_add(1, std::memory_order_release); }
+    // leader, before close(): how many slots have been claimed so far
+    int claimed_so_far(Batch* b) {
+        std::lock_guard<std::mutex> lk(mu);
+        return b->claimed;
+    }
     // leader: no more claims; returns the item count once every claimed slot has been staged
     int close(Batch* b) {
         int n;
