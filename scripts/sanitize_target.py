@@ -97,5 +97,42 @@ if len(sys.argv) > 1 and sys.argv[1] == "round2":
 fs = B.FFTSettings(13)
 a = rng.integers(0, 1 << 62, size=(8192, 4), dtype=np.uint64)
 assert np.array_equal(fs.fft_fr(fs.fft_fr(a, False), True), a)
+# the cluster / distributed-shared-memory kernel (2^9 .. 2^12: clusters of 8 and 16 CTAs) against the two-launch form
+for k in (9, 10, 11, 12):
+    v = a[:1 << k]
+    one = (fs.fft_fr(v, False), fs.fft_fr(v, True), fs.das_fft_extension(v))
+    os.environ["B200_NTT_CLUSTER"] = "0"
+    two = (fs.fft_fr(v, False), fs.fft_fr(v, True), fs.das_fft_extension(v))
+    del os.environ["B200_NTT_CLUSTER"]
+    assert all(np.array_equal(x, y) for x, y in zip(one, two)), k
+# prepare_msm on 4096 points: the direct-lookup table with a Jacobian result, one vector and a batch of three
+if True:
+    from oracle import c_oracle as K2
+    text2 = open(os.path.join(os.path.dirname(B.LIB_PATH), "data", "trusted_setup.txt")).read()
+    L2 = K2.p1s_to_affine(K2.KZGSettings(text2).g1_lagrange_brp)
+    os.environ["B200_MSM_DIRECT_BITS"] = "8"
+    h2 = B.PreparedMsm(L2)
+    del os.environ["B200_MSM_DIRECT_BITS"]
+    assert h2.info()["direct_bits"] == 8
+    s3 = rng.integers(0, 1 << 62, size=(3 * 4096, 4), dtype=np.uint64)
+    got3 = h2.mult_batch(s3, 3)
+    assert K2.p1_compress(got3[2]) == K2.p1_compress(K2.msm_affine(L2, s3[2 * 4096:], nthreads=8))
+    assert K2.p1_compress(h2.mult(s3[:4096])) == K2.p1_compress(got3[0])
+    h2.close()
+if len(sys.argv) > 1 and sys.argv[1] == "cells":
+    # coalesced compute_cells_and_kzg_proofs: three callers at once share a pass
+    import threading
+    errs2 = []
+
+    def cworker():
+        try:
+            c2, p2 = ts.compute_cells_and_kzg_proofs(blobs[0].tobytes())
+            assert c2 == cells and p2 == cproofs
+        except Exception as e:
+            errs2.append(repr(e))
+    th2 = [threading.Thread(target=cworker) for _ in range(3)]
+    [t.start() for t in th2]
+    [t.join() for t in th2]
+    assert not errs2, errs2
 ts.free()
 print("sanitize target ok")
