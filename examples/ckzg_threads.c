@@ -5,7 +5,8 @@
  *
  *   gcc -O2 -pthread -Iinclude examples/ckzg_threads.c -Lrust-kzg_b200 -lb200kzg -Wl,-rpath,$PWD/rust-kzg_b200 -o /tmp/ckzg_threads
  *   /tmp/ckzg_threads rust-kzg_b200/data/trusted_setup.txt <op> <threads> <calls_per_thread> [distinct_blobs]
- *     op: commit | proof | blob_proof | mixed | cells   (mixed: thread t runs op t % 3; cells: compute_cells_and_kzg_proofs)
+ *     op: commit | proof | blob_proof | mixed | cells | verify   (mixed: thread t runs op t % 3; cells: compute_cells_and_kzg_proofs;
+ *         verify: verify_blob_kzg_proof on valid triples, every answer must be true)
  *
  * Every thread first computes its reference outputs with ONE thread active (nothing to coalesce with), then all threads
  * run concurrently and every result is compared byte for byte with the single-threaded one.  Prints one JSON line:
@@ -20,7 +21,7 @@
 
 #include "b200_kzg.h"
 
-enum { OP_COMMIT = 0, OP_PROOF = 1, OP_BLOB_PROOF = 2, OP_MIXED = 3, OP_CELLS = 4 };
+enum { OP_COMMIT = 0, OP_PROOF = 1, OP_BLOB_PROOF = 2, OP_MIXED = 3, OP_CELLS = 4, OP_VERIFY = 5 };
 
 typedef struct {
     int id, op, calls, nblobs;
@@ -57,6 +58,12 @@ static void *worker_main(void *arg) {
     pthread_barrier_wait(w->start);
     for (int i = 0; i < w->calls; i++) {
         int b = i % w->nblobs;
+        if (w->op == OP_VERIFY) {
+            bool ok = false;
+            if (verify_blob_kzg_proof(&ok, &w->blobs[b], &w->commit[b], &w->proof[b], w->s) != C_KZG_OK) { w->errors++; continue; }
+            if (!ok) w->mismatches++;
+            continue;
+        }
         if (w->op == OP_CELLS) {
             memset(cproofs, 0, 128 * sizeof(KZGProof));
             if (compute_cells_and_kzg_proofs(cells, cproofs, &w->blobs[b], w->s) != C_KZG_OK) { w->errors++; continue; }
@@ -79,10 +86,10 @@ static void *worker_main(void *arg) {
 }
 
 int main(int argc, char **argv) {
-    if (argc < 5) { fprintf(stderr, "usage: %s trusted_setup.txt commit|proof|blob_proof|mixed|cells threads calls_per_thread [distinct_blobs]\n", argv[0]); return 2; }
+    if (argc < 5) { fprintf(stderr, "usage: %s trusted_setup.txt commit|proof|blob_proof|mixed|cells|verify threads calls_per_thread [distinct_blobs]\n", argv[0]); return 2; }
     const char *opname = argv[2];
     int op = !strcmp(opname, "commit") ? OP_COMMIT : !strcmp(opname, "proof") ? OP_PROOF : !strcmp(opname, "blob_proof") ? OP_BLOB_PROOF
-             : !strcmp(opname, "mixed") ? OP_MIXED : !strcmp(opname, "cells") ? OP_CELLS : -1;
+             : !strcmp(opname, "mixed") ? OP_MIXED : !strcmp(opname, "cells") ? OP_CELLS : !strcmp(opname, "verify") ? OP_VERIFY : -1;
     int T = atoi(argv[3]), calls = atoi(argv[4]), nblobs = argc > 5 ? atoi(argv[5]) : 4;
     if (op < 0 || T < 1 || T > 256 || calls < 1 || nblobs < 1) { fprintf(stderr, "bad arguments\n"); return 2; }
     FILE *f = fopen(argv[1], "r");
@@ -112,6 +119,10 @@ int main(int argc, char **argv) {
         for (int b = 0; b < nblobs; b++) {
             if (blob_to_kzg_commitment(&w[t].commit[b], &w[t].blobs[b], &s) != C_KZG_OK) { fprintf(stderr, "reference commitment failed\n"); return 4; }
             if (w[t].op == OP_CELLS) continue;
+            if (w[t].op == OP_VERIFY) {         /* the proof to verify: compute_blob_kzg_proof of the same blob */
+                if (compute_blob_kzg_proof(&w[t].proof[b], &w[t].blobs[b], &w[t].commit[b], &s) != C_KZG_OK) { fprintf(stderr, "reference proof failed\n"); return 4; }
+                continue;
+            }
             if (w[t].op != OP_COMMIT && run_one(&w[t], b, &w[t].proof[b], &w[t].y[b]) != C_KZG_OK) { fprintf(stderr, "reference proof failed\n"); return 4; }
         }
         if (w[t].op == OP_CELLS) {
@@ -127,6 +138,8 @@ int main(int argc, char **argv) {
     b200_kzg_coalesce_stats(&s, st0);          /* counters up to here belong to the single-threaded reference pass */
     uint64_t cst0[2];
     b200_kzg_cells_coalesce_stats(&s, cst0);
+    uint64_t vst0[3];
+    b200_kzg_verify_coalesce_stats(&s, vst0);
     pthread_t *th = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
     for (int t = 0; t < T; t++) pthread_create(&th[t], NULL, worker_main, &w[t]);
     pthread_barrier_wait(&start);
@@ -136,6 +149,11 @@ int main(int argc, char **argv) {
     double dt = now_s() - t0;
     b200_kzg_coalesce_stats(&s, st);
     for (int i = 0; i < 4; i++) st[i] -= st0[i];
+    if (op == OP_VERIFY) {
+        uint64_t vs[3];
+        b200_kzg_verify_coalesce_stats(&s, vs);
+        st[0] = vs[0] - vst0[0]; st[1] = vs[1] - vst0[1]; st[2] = st[3] = st[4] = 0;
+    }
     if (op == OP_CELLS) {                       /* its own queue: batches and requests only */
         uint64_t cs[2];
         b200_kzg_cells_coalesce_stats(&s, cs);

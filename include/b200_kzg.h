@@ -239,6 +239,12 @@ B200_API void b200_kzg_coalesce_stats(const KZGSettings *s, uint64_t out[5]);
 /* compute_cells_and_kzg_proofs (with proofs) is coalesced the same way, in batches of up to 16 blobs (B200_KZG_CELLS_COALESCE;
  * 1 disables it): a block's blobs under a parallel iterator share one FK20 pass.  out = [batches run, requests served]. */
 B200_API void b200_kzg_cells_coalesce_stats(const KZGSettings *s, uint64_t out[2]);
+/* verify_blob_kzg_proof / verify_kzg_proof called one at a time from several threads are checked as ONE batch (the random
+ * linear combination of the reference's verify_blob_kzg_proof_batch, kzg/src/eip_4844.rs:380-435); when a batch does not pass
+ * as a whole, or an input does not decode, every caller in it is re-checked alone, so each gets exactly its own answer and
+ * status.  A call without concurrent company is the plain single check.  B200_KZG_VERIFY_COALESCE (default 32; 1 disables).
+ * out = [batches checked, requests served, batches whose callers had to be re-checked alone]. */
+B200_API void b200_kzg_verify_coalesce_stats(const KZGSettings *s, uint64_t out[3]);
 /* Direct-lookup tables held by a settings object: out = [window bits of the Lagrange-point table (13 by default,
  * 11 / 8 when HBM is short, 0 = none: bucket engine), largest blob batch it serves, window bits of the FK20 column table (0
  * before the first cell-proof call)].  Knobs: B200_BLOB_DIRECT, B200_BLOB_DIRECT_BITS, B200_FK20_DIRECT, B200_FK20_DIRECT_BITS,

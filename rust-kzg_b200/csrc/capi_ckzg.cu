@@ -148,11 +148,32 @@ struct CellsBatch : CoBatchBase {
     }
 };
 typedef CoQueue<CellsBatch, 1> CellsCoalescer;
+// verify_blob_kzg_proof (kind 0) / verify_kzg_proof (kind 1) called one at a time from several threads (blob sidecars arriving
+// from gossip): concurrent requests are checked as ONE batch -- the random linear combination the reference's own
+// verify_blob_kzg_proof_batch uses (kzg/src/eip_4844.rs:380-435) -- and only when that batch does not verify (or an input
+// does not decode) does every caller fall back to its own single check, so each still gets exactly its own answer
+enum { VK_BLOB = 0, VK_PROOF = 1, VK_KINDS = 2 };
+struct VerifyBatch : CoBatchBase {
+    uint8_t* h_in = nullptr;   // pinned: [cap blobs][cap x 48 C][cap x 48 proof][cap x 32 z][cap x 32 y]
+    int cap = 0;
+    uint8_t* blob(int i) { return h_in + (size_t)i * kBytesPerBlob; }
+    uint8_t* comm(int i) { return h_in + (size_t)cap * kBytesPerBlob + 48 * (size_t)i; }
+    uint8_t* proof(int i) { return comm(cap) + 48 * (size_t)i; }
+    uint8_t* z(int i) { return proof(cap) + 32 * (size_t)i; }
+    uint8_t* y(int i) { return z(cap) + 32 * (size_t)i; }
+    bool all_ok = false;       // the batch verified: every request in it is valid
+    bool single_done = false;  // the batch held one request: its exact verdict is in rc / all_ok
+    ~VerifyBatch() { if (h_in) cudaFreeHost(h_in); }
+};
+typedef CoQueue<VerifyBatch, VK_KINDS> VerifyCoalescer;
 
 struct KzgCtx {
     LanePool pool;
     Coalescer co;
     CellsCoalescer co_cells;
+    VerifyCoalescer co_verify;
+    int vco_cap = 32;          // most single verifications checked as one batch (B200_KZG_VERIFY_COALESCE; 1: none)
+    std::atomic<uint64_t> st_verify_batches{0}, st_verify_requests{0}, st_verify_fallbacks{0};
     int cells_grace_us = 200;  // how long a leader lingers for the rest of a burst (B200_KZG_CELLS_GRACE_US; 0: not at all)
     int cells_cap = 16;        // most single-blob cells + proofs requests per launch sequence (B200_KZG_CELLS_COALESCE; 1: none)
     int device = 0;            // CUDA device the context lives on: every entry point switches to it (DeviceScope)
@@ -308,6 +329,8 @@ C_KZG_RET load_impl(KZGSettings* out, const uint8_t* g1_monomial, size_t n_mono,
         ctx->co_cap = std::max(1, std::min(ctx->max_batch, env_int("B200_KZG_COALESCE", ctx->max_batch)));
         ctx->cells_cap = std::max(1, std::min(std::min(ctx->max_batch, 64), env_int("B200_KZG_CELLS_COALESCE", 16)));
         ctx->co_cells.max_batches = 2;
+        ctx->vco_cap = std::max(1, std::min(64, env_int("B200_KZG_VERIFY_COALESCE", 32)));
+        ctx->co_verify.max_batches = 3;
         ctx->cells_grace_us = std::max(0, env_int("B200_KZG_CELLS_GRACE_US", 200));
         ctx->co.max_batches = KzgSettingsDev::kLanes + 2;   // one per lane in flight + the ones filling
         {
@@ -1074,19 +1097,27 @@ C_KZG_RET b200_verify_kzg_proof_batch(bool* ok, const Bytes48* commitments, cons
         return verify_core(*ctx, ok, (const uint8_t*)commitments, (const uint8_t*)zs, (const uint8_t*)ys, (const uint8_t*)proofs, n);
     });
 }
+static C_KZG_RET coalesced_verify(const std::shared_ptr<KzgCtx>& ctxp, int kind, bool* ok, const uint8_t* blob, const uint8_t* c48,
+                                  const uint8_t* z32, const uint8_t* y32, const uint8_t* p48, bool* fall_back);
 C_KZG_RET verify_kzg_proof(bool* ok, const Bytes48* commitment_bytes, const Bytes32* z_bytes, const Bytes32* y_bytes,
                            const Bytes48* proof_bytes, const KZGSettings* s) {
+    if (ok && commitment_bytes && z_bytes && y_bytes && proof_bytes) {
+        bool fall_back = true;
+        C_KZG_RET rc = ckzg_guard([&]() -> C_KZG_RET {
+            auto ctx = find_ctx(s);
+            if (!ctx) return C_KZG_BADARGS;
+            if (ctx->vco_cap < 2) return C_KZG_OK;
+            return coalesced_verify(ctx, VK_PROOF, ok, nullptr, commitment_bytes->bytes, z_bytes->bytes, y_bytes->bytes, proof_bytes->bytes,
+                                    &fall_back);
+        });
+        if (rc != C_KZG_OK || !fall_back) return rc;
+    }
     return b200_verify_kzg_proof_batch(ok, commitment_bytes, z_bytes, y_bytes, proof_bytes, 1, s);
 }
-C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48* commitments_bytes, const Bytes48* proofs_bytes, size_t n,
-                                      const KZGSettings* s) {
-    return ckzg_guard([&]() -> C_KZG_RET {
-        auto ctx = find_ctx(s);
-        if (!ctx || !ok) return C_KZG_BADARGS;
-        *ok = false;
-        if (n == 0) { *ok = true; return C_KZG_OK; }  // kzg/src/eip_4844.rs:760-763
-        if (!blobs || !commitments_bytes || !proofs_bytes) return C_KZG_BADARGS;
-        AllLanes lk(*ctx);
+// verify_blob_kzg_proof_batch on host arrays; the caller holds every lane
+static C_KZG_RET verify_blobs_locked(const std::shared_ptr<KzgCtx>& ctx, bool* ok, const Blob* blobs, const Bytes48* commitments_bytes,
+                                     const Bytes48* proofs_bytes, size_t n) {
+    {
         // phase 1, chunked over the two lanes: z_i = challenge(blob_i, C_i) hashed on the host while the blobs cross
         // PCIe, y_i = p_i(z_i) on the device (compute_challenges_and_evaluate_polynomial, :700-718)
         std::vector<uint8_t> zs(32 * n), ys(32 * n);
@@ -1116,9 +1147,103 @@ C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48
         }
         // phase 2: one batched pairing check over all n (verify_kzg_proof_batch, :380-435)
         return verify_finish(*ctx, ok, (const uint8_t*)commitments_bytes, zs.data(), ys.data(), (const uint8_t*)proofs_bytes, n);
+    }
+}
+C_KZG_RET verify_blob_kzg_proof_batch(bool* ok, const Blob* blobs, const Bytes48* commitments_bytes, const Bytes48* proofs_bytes, size_t n,
+                                      const KZGSettings* s) {
+    return ckzg_guard([&]() -> C_KZG_RET {
+        auto ctx = find_ctx(s);
+        if (!ctx || !ok) return C_KZG_BADARGS;
+        *ok = false;
+        if (n == 0) { *ok = true; return C_KZG_OK; }  // kzg/src/eip_4844.rs:760-763
+        if (!blobs || !commitments_bytes || !proofs_bytes) return C_KZG_BADARGS;
+        AllLanes lk(*ctx);
+        return verify_blobs_locked(ctx, ok, blobs, commitments_bytes, proofs_bytes, n);
     });
 }
+// One single verification (kind VK_BLOB: blob + commitment + proof; VK_PROOF: commitment + z + y + proof) among concurrent
+// ones: staged into the open batch, checked together, and re-checked alone only if the batch as a whole does not pass.
+static C_KZG_RET coalesced_verify(const std::shared_ptr<KzgCtx>& ctxp, int kind, bool* ok, const uint8_t* blob, const uint8_t* c48,
+                                  const uint8_t* z32, const uint8_t* y32, const uint8_t* p48, bool* fall_back) {
+    KzgCtx& ctx = *ctxp;
+    VerifyCoalescer& co = ctx.co_verify;
+    const int cap = ctx.vco_cap;
+    VerifyCoalescer::Claim cl = co.claim(kind, cap, [&] {
+        std::unique_ptr<VerifyBatch> nb(new VerifyBatch());
+        nb->cap = cap;
+        DeviceScope ds(ctx.device);
+        B200_CUDA_CHECK(cudaMallocHost((void**)&nb->h_in, (size_t)cap * (kBytesPerBlob + 48 + 48 + 32 + 32)));
+        return nb;
+    });
+    VerifyBatch* B = cl.b;
+    const int idx = cl.idx;
+    if (kind == VK_BLOB) memcpy(B->blob(idx), blob, kBytesPerBlob);
+    memcpy(B->comm(idx), c48, 48);
+    memcpy(B->proof(idx), p48, 48);
+    if (kind == VK_PROOF) { memcpy(B->z(idx), z32, 32); memcpy(B->y(idx), y32, 32); }
+    VerifyCoalescer::staged(B);
+    if (cl.leader) {
+        int rc = C_KZG_OK;
+        bool all_ok = false;
+        B->all_ok = false;                                      // batch objects are pooled: no verdict of an earlier use may survive
+        B->single_done = false;
+        try {
+            DeviceScope ds(ctx.device);
+            AllLanes lk(ctx);   // while another pass runs this batch fills
+            if (ctx.cells_grace_us > 0) {                       // a burst of sidecars: linger briefly, as for the cells
+                const auto t0 = std::chrono::steady_clock::now();
+                auto last_change = t0;
+                int seen = co.claimed_so_far(B);
+                while (seen < cap) {
+                    std::this_thread::sleep_for(std::chrono::microseconds(15));
+                    const auto now = std::chrono::steady_clock::now();
+                    const int c = co.claimed_so_far(B);
+                    if (c != seen) { seen = c; last_change = now; }
+                    if (now - last_change > std::chrono::microseconds(60) || now - t0 > std::chrono::microseconds(ctx.cells_grace_us)) break;
+                }
+            }
+            const int n = co.close(B);
+            bool bok = false;
+            C_KZG_RET r = kind == VK_BLOB
+                ? verify_blobs_locked(ctxp, &bok, (const Blob*)B->blob(0), (const Bytes48*)B->comm(0), (const Bytes48*)B->proof(0), (size_t)n)
+                : verify_core(ctx, &bok, B->comm(0), B->z(0), B->y(0), B->proof(0), (size_t)n);
+            all_ok = r == C_KZG_OK && bok;                     // anything else: every caller re-checks its own request
+            ctx.st_verify_batches++;
+            ctx.st_verify_requests += (uint64_t)n;
+            if (!all_ok && n > 1) ctx.st_verify_fallbacks++;
+            if (n == 1 && r != C_KZG_OK) rc = r;               // a batch of one IS the single check: its verdict stands
+            if (n == 1) B->single_done = true;
+        } catch (const std::exception& e) {
+            cudaGetLastError();
+            fprintf(stderr, "b200kzg: %s\n", e.what());
+            rc = C_KZG_ERROR;
+        }
+        B->all_ok = all_ok;
+        co.publish(B, rc);
+    } else {
+        co.wait(B);
+    }
+    C_KZG_RET rc = (C_KZG_RET)B->rc;
+    const bool all_ok = B->all_ok, single_done = B->single_done;
+    co.consume(B);
+    *fall_back = false;
+    if (rc != C_KZG_OK) { *ok = false; return rc; }
+    if (all_ok) { *ok = true; return C_KZG_OK; }
+    if (single_done) { *ok = false; return C_KZG_OK; }         // the lone request was checked exactly and is invalid
+    *fall_back = true;
+    return C_KZG_OK;
+}
 C_KZG_RET verify_blob_kzg_proof(bool* ok, const Blob* blob, const Bytes48* commitment_bytes, const Bytes48* proof_bytes, const KZGSettings* s) {
+    if (ok && blob && commitment_bytes && proof_bytes) {
+        bool fall_back = true;
+        C_KZG_RET rc = ckzg_guard([&]() -> C_KZG_RET {
+            auto ctx = find_ctx(s);
+            if (!ctx) return C_KZG_BADARGS;
+            if (ctx->vco_cap < 2) return C_KZG_OK;             // coalescing off: the plain single check below
+            return coalesced_verify(ctx, VK_BLOB, ok, blob->bytes, commitment_bytes->bytes, nullptr, nullptr, proof_bytes->bytes, &fall_back);
+        });
+        if (rc != C_KZG_OK || !fall_back) return rc;
+    }
     return verify_blob_kzg_proof_batch(ok, blob, commitment_bytes, proof_bytes, 1, s);
 }
 // ---- EIP-7594 recovery and cell verification (kzg/src/eth/c_bindings.rs:201-352, blst/src/eip_7594.rs:35-97) ------
@@ -1394,6 +1519,15 @@ void b200_kzg_direct_tables(const KZGSettings* s, int out[3]) {
     out[0] = ctx->dev->direct_bits();
     out[1] = ctx->dev->direct_max_batch();
     out[2] = ctx->dev->fk_direct_bits();
+}
+// coalesced single verifications: out = [batches checked, requests served, batches that did not pass as a whole (their callers
+// re-checked alone)]
+void b200_kzg_verify_coalesce_stats(const KZGSettings* s, uint64_t out[3]) {
+    auto ctx = find_ctx(s);
+    if (!out) return;
+    out[0] = out[1] = out[2] = 0;
+    if (!ctx) return;
+    out[0] = ctx->st_verify_batches; out[1] = ctx->st_verify_requests; out[2] = ctx->st_verify_fallbacks;
 }
 // the same counters for coalesced compute_cells_and_kzg_proofs calls: out = [batches run, requests served]
 void b200_kzg_cells_coalesce_stats(const KZGSettings* s, uint64_t out[2]) {

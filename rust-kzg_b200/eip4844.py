@@ -51,6 +51,7 @@ def _L():
             "b200_compute_cells_and_kzg_proofs_batch": (ci, [vp, vp, vp, sz, S]),
             "b200_kzg_direct_tables": (None, [S, vp]),
             "b200_kzg_cells_coalesce_stats": (None, [S, vp]),
+            "b200_kzg_verify_coalesce_stats": (None, [S, vp]),
             "verify_kzg_proof": (ci, [vp, vp, vp, vp, vp, S]),
             "verify_blob_kzg_proof": (ci, [vp, vp, vp, vp, S]),
             "verify_blob_kzg_proof_batch": (ci, [vp, vp, vp, vp, sz, S]),
@@ -255,6 +256,12 @@ class KZGSettings:
         if rc != C_KZG_OK:
             raise KzgError(rc, "compute_cell_proofs_batch")
         return out
+
+    def verify_coalesce_stats(self):
+        """-> (batches checked, requests served, batches re-checked one by one) of the coalesced single verifications"""
+        out = (C.c_uint64 * 3)()
+        _L().b200_kzg_verify_coalesce_stats(C.byref(self.c), out)
+        return int(out[0]), int(out[1]), int(out[2])
 
     def cells_coalesce_stats(self):
         """-> (batches run, requests served) of the coalesced compute_cells_and_kzg_proofs calls"""

@@ -180,6 +180,62 @@ def test_concurrent_cells_and_proofs_coalesce_bit_exact(B, K, oracle_settings):
     assert r1 - r0 == 36 and b1 - b0 < 36, (b0, r0, b1, r1)              # some batches carried more than one request
 
 
+def test_concurrent_single_verifications_coalesce_exactly(B, K, oracle_settings):
+    """verify_blob_kzg_proof / verify_kzg_proof called one at a time from twelve threads are checked as one batch
+    (csrc/capi_ckzg.cu, coalesced_verify) and re-checked alone when the batch does not pass: valid requests must come back
+    True, a swapped proof False, an undecodable commitment as an error -- each caller its own answer, whatever else shares
+    the batch"""
+    ts = B.KZGSettings.load_trusted_setup_file()
+    rng = np.random.default_rng(36)
+    blobs = _blobs(rng, 4)
+    comm = [ts.blob_to_kzg_commitment(b) for b in blobs]
+    proofs = [ts.compute_blob_kzg_proof(b, c) for b, c in zip(blobs, comm)]
+    zs = [bytes(b[96:128]) for b in blobs]
+    zp = [ts.compute_kzg_proof(b, z) for b, z in zip(blobs, zs)]
+    bad_comm = bytes(48)                                               # compression flag missing: does not decode
+    errors = []
+
+    def run(threads, mode):
+        start = threading.Barrier(threads)
+
+        def worker(k):
+            try:
+                start.wait()
+                for rep in range(5):
+                    i = (k + rep) % 4
+                    j = (i + 1) % 4
+                    if mode == "valid" or k % 4 == 0:
+                        assert ts.verify_blob_kzg_proof(blobs[i], comm[i], proofs[i]) is True
+                    elif k % 4 == 1:
+                        assert ts.verify_blob_kzg_proof(blobs[i], comm[i], proofs[j]) is False
+                    elif k % 4 == 2:
+                        assert ts.verify_kzg_proof(comm[i], zs[i], zp[i][1], zp[i][0]) is True
+                        assert ts.verify_kzg_proof(comm[i], zs[i], zp[j][1], zp[i][0]) is False
+                    else:
+                        with pytest.raises(B.KzgError) as e:
+                            ts.verify_blob_kzg_proof(blobs[i], bad_comm, proofs[i])
+                        assert e.value.code == 1
+            except Exception as e:
+                errors.append(repr(e))
+
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(threads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    b0, r0, f0 = ts.verify_coalesce_stats()
+    run(12, "valid")
+    b1, r1, f1 = ts.verify_coalesce_stats()
+    assert not errors, errors
+    assert r1 - r0 == 60 and b1 - b0 < 60 and f1 == f0, (b0, r0, f0, b1, r1, f1)   # shared batches, none re-checked
+    run(12, "mixed")
+    b2, r2, f2 = ts.verify_coalesce_stats()
+    ts.free()
+    assert not errors, errors
+    assert f2 > f1, (f1, f2)                                           # batches with a bad request were re-checked one by one
+
+
 def test_concurrent_prepared_msm_coalesces(B, K, lagrange_affine):
     """a prepared 4096-point handle packs concurrent mult_pippenger_prepared calls (different lengths included: short
     calls are zero-padded) into one launch sequence; each caller gets its own sum"""
