@@ -618,6 +618,15 @@ def thread_metrics():
         rec["threads%d_mean_batch" % t] = line.get("mean_batch")
         rec["threads%d_bit_exact" % t] = bool(r.returncode == 0 and line.get("mismatches") == 0 and line.get("errors") == 0)
     out["compute_cells_and_kzg_proofs"] = rec
+    # verify_blob_kzg_proof one at a time from 1 / 16 threads: concurrent requests are checked as one batch
+    rec = {}
+    for t in (1, 16):
+        r = subprocess.run([exe, setup, "verify", str(t), "30", "4"], capture_output=True, text=True, timeout=300)
+        line = json.loads(r.stdout.strip().splitlines()[-1]) if r.stdout.strip() else {"error": r.stderr[-200:]}
+        rec["e2e_threads%d_per_s" % t] = line.get("per_s")
+        rec["threads%d_mean_batch" % t] = line.get("mean_batch")
+        rec["threads%d_all_true" % t] = bool(r.returncode == 0 and line.get("mismatches") == 0 and line.get("errors") == 0)
+    out["verify_blob_kzg_proof"] = rec
     return out
 
 
