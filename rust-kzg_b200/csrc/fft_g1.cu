@@ -25,32 +25,47 @@ __global__ void k_g1_brp_in(const uint8_t* __restrict__ in_jac, uint8_t* __restr
 // one DIT stage: butterflies (i, i + 2^s) with twiddle w_n^(k * n / 2^(s+1)) (blst/src/fft_g1.rs:43-47).
 // One QUAD of lanes per butterfly (g1_quad.cuh): the transform is a chain of log n full scalar multiplications and
 // there are far fewer butterflies than lanes on the machine, so each multiplication is spread over four lanes.
+// SPLIT: two neighbouring quads per butterfly, one GLV half of the scalar multiplication each (quad_mul_scalar_half: a 20 %
+// shorter chain on twice the lanes); afterwards the first quad forms the sum, the second the difference.
+template <bool SPLIT>
 __global__ void __launch_bounds__(32) k_g1_stage(uint8_t* __restrict__ work, size_t n, int log_n, int s, const uint8_t* __restrict__ roots,
                                                  size_t nmax, int inverse) {
     __shared__ __align__(16) uint8_t table[kQuadTableBytes];
-    const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t q2 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t q = SPLIT ? q2 >> 1 : q2;
+    const int half = SPLIT ? (int)(q2 & 1) : 0;
     const bool live = q < n / 2;
     const size_t b = live ? q : 0;
     uint8_t* w = work + (size_t)blockIdx.y * n * 192;
-    const size_t half = (size_t)1 << s;
+    const size_t hstride = (size_t)1 << s;
     // butterflies are numbered twiddle-major: all those with the same twiddle index lowk are consecutive, so the ones
     // multiplying by w^0 = 1 (a 2^-s fraction of the stage) fill whole warps, which then skip the scalar multiplication
     const int hi_bits = log_n - 1 - s;
     const size_t lowk = b >> hi_bits;
     const size_t i = ((b & (((size_t)1 << hi_bits) - 1)) << (s + 1)) | lowk;
     const int off = quad_store_offset();
-    fp_t lo = load_field<fp_t>(w + i * 192 + off), t = load_field<fp_t>(w + (i + half) * 192 + off);
+    fp_t lo = load_field<fp_t>(w + i * 192 + off), t = load_field<fp_t>(w + (i + hstride) * 192 + off);
     if (__any_sync(kFullMask, lowk != 0)) {
         // butterflies with lowk == 0 multiply by roots[0] = 1
         size_t e = (lowk << (log_n - 1 - s)) * (nmax >> log_n);
         fr_t root = load_field_ro<fr_t>(roots + (inverse && e ? nmax - e : e) * 32).from_mont();
-        t = quad_mul_scalar(t, root.v, table);
+        if (SPLIT) {
+            t = quad_mul_scalar_half(t, root.v, table, half);
+            t = quad_add(t, shfl_xor_fp(t, 4));                 // [k1] t + [k2] phi(t), on both quads
+        } else {
+            t = quad_mul_scalar(t, root.v, table);
+        }
     }
     fp_t nt = (threadIdx.x & 3) == 1 ? t.neg() : t;
-    fp_t sum = quad_add(lo, t), dif = quad_add(lo, nt);
-    if (live) {
-        store_field(w + i * 192 + off, sum);
-        store_field(w + (i + half) * 192 + off, dif);
+    if (SPLIT) {
+        fp_t res = quad_add(lo, half ? nt : t);
+        if (live) store_field(w + (i + (half ? hstride : 0)) * 192 + off, res);
+    } else {
+        fp_t sum = quad_add(lo, t), dif = quad_add(lo, nt);
+        if (live) {
+            store_field(w + i * 192 + off, sum);
+            store_field(w + (i + hstride) * 192 + off, dif);
+        }
     }
 }
 // Two DIT stages (s, s+1) at the latency of one.  The transform is a chain of log n dependent scalar multiplications
@@ -61,10 +76,13 @@ __global__ void __launch_bounds__(32) k_g1_stage(uint8_t* __restrict__ work, siz
 // with a = w_2h^low, b = w_4h^low, b' = w_4h^(low + h): FIVE independent products [a]x1, [b]x2, [ab]x3, [b']x2, [ab']x3 by
 // roots of unity (one more than the two stages do, but all at the same depth), then eight additions.
 // k_g1_stage2_mul: one lane quad per product; k_g1_stage2_comb: one lane quad per group of four points.
+template <bool SPLIT>
 __global__ void __launch_bounds__(32) k_g1_stage2_mul(const uint8_t* __restrict__ work, uint8_t* __restrict__ tmp, size_t n, int log_n, int s,
                                                       const uint8_t* __restrict__ roots, size_t nmax, int inverse) {
     __shared__ __align__(16) uint8_t table[kQuadTableBytes];
-    const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t q2 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t q = SPLIT ? q2 >> 1 : q2;
+    const int ghalf = SPLIT ? (int)(q2 & 1) : 0;
     const size_t nprod = 5 * (n >> 2);
     const bool live = q < nprod;
     const size_t qq = live ? q : 0;
@@ -81,8 +99,13 @@ __global__ void __launch_bounds__(32) k_g1_stage2_mul(const uint8_t* __restrict_
     fp_t t = load_field<fp_t>(w + src * 192 + off);
     const size_t eu = e * (nmax >> log_n);
     fr_t root = load_field_ro<fr_t>(roots + (inverse && eu ? nmax - eu : eu) * 32).from_mont();
-    t = quad_mul_scalar(t, root.v, table);
-    if (live) store_field(tmp + ((size_t)blockIdx.y * nprod + q) * 192 + off, t);
+    if (SPLIT) {
+        t = quad_mul_scalar_half(t, root.v, table, ghalf);
+        t = quad_add(t, shfl_xor_fp(t, 4));
+    } else {
+        t = quad_mul_scalar(t, root.v, table);
+    }
+    if (live && ghalf == 0) store_field(tmp + ((size_t)blockIdx.y * nprod + q) * 192 + off, t);
 }
 __global__ void __launch_bounds__(32) k_g1_stage2_comb(uint8_t* __restrict__ work, const uint8_t* __restrict__ tmp, size_t n, int s) {
     const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
@@ -115,10 +138,13 @@ __global__ void __launch_bounds__(32) k_g1_stage2_comb(uint8_t* __restrict__ wor
 // group -- [a]x1, [b]x2, [b']x2, [ab]x3, [ab']x3 and [c_r]x4, [a c_r]x5, [c_r beta_r]x6, [a c_r beta_r]x7 for r = 0..3 --
 // instead of the 12 of three plain stages, all at the same depth, then 8 additions per output pair.
 // k_g1_stage3_mul: one lane quad per product; k_g1_stage3_comb: one lane quad per output pair (r, r + 4).
+template <bool SPLIT>
 __global__ void __launch_bounds__(32) k_g1_stage3_mul(const uint8_t* __restrict__ work, uint8_t* __restrict__ tmp, size_t n, int log_n, int s,
                                                       const uint8_t* __restrict__ roots, size_t nmax, int inverse) {
     __shared__ __align__(16) uint8_t table[kQuadTableBytes];
-    const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t q2 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t q = SPLIT ? q2 >> 1 : q2;
+    const int ghalf = SPLIT ? (int)(q2 & 1) : 0;
     const size_t nprod = 21 * (n >> 3);
     const bool live = q < nprod;
     const size_t qq = live ? q : 0;
@@ -147,8 +173,13 @@ __global__ void __launch_bounds__(32) k_g1_stage3_mul(const uint8_t* __restrict_
     fp_t t = load_field<fp_t>(w + (j + (size_t)m * h) * 192 + off);
     const size_t eu = e * (nmax >> log_n);
     fr_t root = load_field_ro<fr_t>(roots + (inverse && eu ? nmax - eu : eu) * 32).from_mont();
-    t = quad_mul_scalar(t, root.v, table);
-    if (live) store_field(tmp + ((size_t)blockIdx.y * nprod + q) * 192 + off, t);
+    if (SPLIT) {
+        t = quad_mul_scalar_half(t, root.v, table, ghalf);
+        t = quad_add(t, shfl_xor_fp(t, 4));
+    } else {
+        t = quad_mul_scalar(t, root.v, table);
+    }
+    if (live && ghalf == 0) store_field(tmp + ((size_t)blockIdx.y * nprod + q) * 192 + off, t);
 }
 __global__ void __launch_bounds__(32) k_g1_stage3_comb(uint8_t* __restrict__ work, const uint8_t* __restrict__ tmp, size_t n, int s) {
     const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // four quads per group: both of a warp's groups in lockstep
@@ -219,9 +250,19 @@ void FFTSettingsDev::fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n,
     // wave of product quads: 128 points x 8 transforms 2.93 -> see scripts/fft_g1_batch_timing.py; pairs up to 2^12.
     const int fuse_env = getenv("B200_FFT_G1_FUSE") ? atoi(getenv("B200_FFT_G1_FUSE")) : -1;
     const int fuse = fuse_env >= 0 ? (fuse_env == 1 ? 2 : fuse_env) : total <= ((size_t)1 << 11) ? 3 : total <= ((size_t)1 << 12) ? 2 : 0;
+    // B200_FFT_G1_SPLIT (per call): 1 / 0 force two quads / one quad per scalar multiplication; unset: two only while the
+    // doubled launch leaves at most one warp per scheduler (592 x 8 quads) -- the halves do 1.6x the work of the whole, so they
+    // pay off only where the chain, not the multiply pipe, is the limit (scripts/fft_g1_batch_timing.py: 128 points x 8
+    // transforms, plain stages 5.57 -> 4.54 ms, pairs 2.93 -> 2.41; at 16 and more every split form loses to the unsplit one)
+    const int split_env = getenv("B200_FFT_G1_SPLIT") ? atoi(getenv("B200_FFT_G1_SPLIT")) : -1;
+    auto use_split = [&](size_t products) { return split_env >= 0 ? split_env != 0 : products * (size_t)batch * 2 <= (size_t)592 * 8; };
     auto plain = [&](int st_idx) {
-        k_g1_stage<<<dim3(div_up(n / 2 * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, n, log_n, st_idx, (const uint8_t*)roots_,
-                                                                            max_width_, inverse);
+        if (use_split(n / 2))
+            k_g1_stage<true><<<dim3(div_up(n / 2 * 8, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, n, log_n, st_idx,
+                                                                                      (const uint8_t*)roots_, max_width_, inverse);
+        else
+            k_g1_stage<false><<<dim3(div_up(n / 2 * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, n, log_n, st_idx,
+                                                                                       (const uint8_t*)roots_, max_width_, inverse);
         launches_++;
     };
     int s = 0;
@@ -239,15 +280,23 @@ void FFTSettingsDev::fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n,
         }
         if (fuse == 3) {
             for (; s + 3 <= log_n; s += 3) {
-                k_g1_stage3_mul<<<dim3(div_up(21 * (n >> 3) * 4, 32), (unsigned)batch), 32, 0, st>>>((const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n,
-                                                                                                s, (const uint8_t*)roots_, max_width_, inverse);
+                if (use_split(21 * (n >> 3)))
+                    k_g1_stage3_mul<true><<<dim3(div_up(21 * (n >> 3) * 8, 32), (unsigned)batch), 32, 0, st>>>(
+                        (const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n, s, (const uint8_t*)roots_, max_width_, inverse);
+                else
+                    k_g1_stage3_mul<false><<<dim3(div_up(21 * (n >> 3) * 4, 32), (unsigned)batch), 32, 0, st>>>(
+                        (const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n, s, (const uint8_t*)roots_, max_width_, inverse);
                 k_g1_stage3_comb<<<dim3(div_up((n >> 1) * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, (const uint8_t*)g1_tmp_, n, s);
                 launches_ += 2;
             }
         }
         for (; s + 2 <= log_n; s += 2) {
-            k_g1_stage2_mul<<<dim3(div_up(5 * (n >> 2) * 4, 32), (unsigned)batch), 32, 0, st>>>((const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n, s,
-                                                                                           (const uint8_t*)roots_, max_width_, inverse);
+            if (use_split(5 * (n >> 2)))
+                k_g1_stage2_mul<true><<<dim3(div_up(5 * (n >> 2) * 8, 32), (unsigned)batch), 32, 0, st>>>(
+                    (const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n, s, (const uint8_t*)roots_, max_width_, inverse);
+            else
+                k_g1_stage2_mul<false><<<dim3(div_up(5 * (n >> 2) * 4, 32), (unsigned)batch), 32, 0, st>>>(
+                    (const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n, s, (const uint8_t*)roots_, max_width_, inverse);
             k_g1_stage2_comb<<<dim3(div_up((n >> 2) * 4, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, (const uint8_t*)g1_tmp_, n, s);
             launches_ += 2;
         }

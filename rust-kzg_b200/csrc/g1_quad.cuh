@@ -300,6 +300,54 @@ __device__ __forceinline__ fp_t quad_mul_scalar(const fp_t& p, const uint32_t (&
     return acc;
 }
 
+// One GLV half of [k] p: half = 0 gives [k1] p, half = 1 gives [k2] (beta x, -y), so that TWO quads (neighbours in a warp)
+// share one scalar multiplication -- each runs 33 x (4 doublings + 1 addition) instead of 33 x (4 + 2), a 20 % shorter
+// dependent chain, and the caller adds the two halves (shfl_xor 4).  The instruction stream is the same for both halves:
+// only the digit, the sign rule and the source of the X component differ, all per-lane selects.
+__device__ __forceinline__ fp_t quad_mul_scalar_half(const fp_t& p, const uint32_t (&k)[8], uint8_t* warp_table, int half) {
+    const int lane = threadIdx.x & 31, role = lane & 3;
+    uint8_t* tab = warp_table + (lane >> 2) * kQuadTableStride + quad_store_offset();
+    uint8_t* tabx = warp_table + (lane >> 2) * kQuadTableStride + kQuadTableEntries * 192;   // beta * X_d, 48 B each
+    uint32_t k1[4], k2[4];
+    glv_split(k, k1, k2);
+    uint32_t m[5], sg[2];
+    if (half) booth4(k2, m, sg); else booth4(k1, m, sg);
+    fp_t beta;
+    {
+        const uint32_t Bm[12] = {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au,
+                                 0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu};
+#pragma unroll
+        for (int i = 0; i < 12; i++) beta.v[i] = Bm[i];
+    }
+    store_field(tab, fp_t::zero());
+    store_field(tab + 192, p);
+#pragma unroll 1
+    for (int d = 2; d < kQuadTableEntries; d++) {
+        fp_t t = (d & 1) ? quad_add(load_field<fp_t>(tab + (d - 1) * 192), p) : quad_dbl(load_field<fp_t>(tab + (d >> 1) * 192));
+        store_field(tab + d * 192, t);
+    }
+#pragma unroll 1
+    for (int d = 0; d < kQuadTableEntries; d++) {
+        fp_t bx = load_field<fp_t>(tab + d * 192) * beta;      // only the X lane's product is kept
+        if (role == 0) store_field(tabx + d * 48, bx);
+    }
+    const bool use_bx = half && role == 0;
+    fp_t acc = fp_t::zero();
+#pragma unroll 1
+    for (int j = 32; j >= 0; j--) {
+        if (j != 32) {
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) acc = quad_dbl(acc);
+        }
+        const uint32_t d = (m[j >> 3] >> ((j & 7) * 4)) & 15u;
+        const bool neg = j < 32 && ((sg[j >> 5] >> (j & 31)) & 1u);
+        fp_t e = use_bx ? load_field<fp_t>(tabx + d * 48) : load_field<fp_t>(tab + d * 192);
+        if (role == 1 && (neg != (half != 0))) e = e.neg();      // half 1 carries the endomorphism's -y
+        acc = quad_add(acc, e);
+    }
+    return acc;
+}
+
 // [|z|] p for quad-distributed p, z = -0xd201000000010000 the BLS parameter: the ladder of the subgroup test
 // (beta x, y) == -[z^2] P  (eprint 2021/1130 sec. 6, zkcrypto/bls12_381/src/g1.rs:401-410); the scalar is a constant, so
 // every quad of a warp follows the same instruction stream

@@ -24,7 +24,12 @@ for batch in (8, 16, 32, 64, 128, 256):
     d_out = torch.zeros_like(d_in)
     row = {}
     for fuse in ("0", "2", "3"):
-        os.environ["B200_FFT_G1_FUSE"] = fuse
-        row["fuse" + fuse + "_ms"] = round(timed(lambda: fs.fft_g1_device(d_out.data_ptr(), d_in.data_ptr(), n, False, batch, 0), reps=3, warm=1), 3)
+        for split in ("0", "1"):
+            os.environ["B200_FFT_G1_FUSE"] = fuse
+            os.environ["B200_FFT_G1_SPLIT"] = split
+            row["fuse" + fuse + ("_split" if split == "1" else "") + "_ms"] = round(
+                timed(lambda: fs.fft_g1_device(d_out.data_ptr(), d_in.data_ptr(), n, False, batch, 0), reps=3, warm=1), 3)
+    del os.environ["B200_FFT_G1_FUSE"], os.environ["B200_FFT_G1_SPLIT"]
+    row["auto_ms"] = round(timed(lambda: fs.fft_g1_device(d_out.data_ptr(), d_in.data_ptr(), n, False, batch, 0), reps=3, warm=1), 3)
     res[batch] = row
     print(batch, json.dumps(row), flush=True)

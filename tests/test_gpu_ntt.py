@@ -233,12 +233,15 @@ def test_fft_g1_fused_and_plain_stages_agree(B, K, oracle_settings, logn):
     if n >= 8:
         pts[2] = 0
     want = {inv: K.p1s_to_affine(ofs.fft_g1(pts, inv)) for inv in (False, True)}
+    # ... each with one quad per scalar multiplication and with two (one GLV half each, B200_FFT_G1_SPLIT)
     for fuse in ("3", "2", "0"):
-        os.environ["B200_FFT_G1_FUSE"] = fuse
-        try:
-            fs = B.FFTSettings(10)
-            for inv in (False, True):
-                assert np.array_equal(K.p1s_to_affine(fs.fft_g1(pts, inv)), want[inv]), (fuse, inv)
-            fs.close()
-        finally:
-            del os.environ["B200_FFT_G1_FUSE"]
+        for split in ("1", "0"):
+            os.environ["B200_FFT_G1_FUSE"] = fuse
+            os.environ["B200_FFT_G1_SPLIT"] = split
+            try:
+                fs = B.FFTSettings(10)
+                for inv in (False, True):
+                    assert np.array_equal(K.p1s_to_affine(fs.fft_g1(pts, inv)), want[inv]), (fuse, split, inv)
+                fs.close()
+            finally:
+                del os.environ["B200_FFT_G1_FUSE"], os.environ["B200_FFT_G1_SPLIT"]
