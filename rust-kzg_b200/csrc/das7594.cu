@@ -274,7 +274,7 @@ void KzgSettingsDev::verify_cells(const uint8_t* commitments48, int m, const uin
                                   cudaStream_t st) {
     if (!g2_lines_) throw CudaError(-1, "trusted setup was loaded without G2 points");
     if (n < 1 || m < 1 || m > n) throw CudaError(-1, "verify_cells: bad counts");
-    const size_t L = (size_t)n + m + kCellFr, blocks = (L + 7) / 8;
+    const size_t L = (size_t)n + m + kCellFr, blocks = (2 * L + 7) / 8;   // lincomb2_and_pair may use two quads per term
     const size_t colb = (size_t)kCells * kCellFr * 32;
     size_t bytes = (size_t)m * 96 + (size_t)n * 96 + (size_t)n * kCellFr * 32 + (size_t)n * 32 + 64 + 2 * colb + 2 * L * (96 + 32) +
                    2 * blocks * 192 + 2 * 192 + 4 * kMillerLines * kLineBytes + 1024;

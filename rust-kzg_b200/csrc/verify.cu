@@ -107,11 +107,15 @@ __global__ void __launch_bounds__(256) k_verify_gen_term(const uint8_t* __restri
         store_field(scalars + (L + 2 * (size_t)n) * 32, total.neg().from_mont());
     }
 }
-// One lane quad per term: partial[seg][block] = sum of the block's eight [k_i] P_i, in XYZZ (192 B)
+// One lane quad per term: partial[seg][block] = sum of the block's eight [k_i] P_i, in XYZZ (192 B).
+// SPLIT (few terms: a single verification): two quads per term, one GLV half of the scalar multiplication each -- a 20 %
+// shorter chain; the block's tree sums the halves like any other summands.
+template <bool SPLIT>
 __global__ void __launch_bounds__(32) k_lincomb_quads(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalars, int L,
                                                       uint8_t* __restrict__ partial) {
     __shared__ __align__(16) uint8_t table[kQuadTableBytes];
-    const int q = blockIdx.x * 8 + (threadIdx.x >> 2);
+    const int q2 = blockIdx.x * 8 + (threadIdx.x >> 2);
+    const int q = SPLIT ? q2 >> 1 : q2;
     const int role = threadIdx.x & 3;
     const bool live = q < L;
     const size_t t = (size_t)blockIdx.y * L + (live ? q : 0);
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(32) k_lincomb_quads(const uint8_t* __restrict_
     fp_t comp = role == 0 ? x : role == 1 ? y : fp_t::one();
     if (inf) comp = fp_t::zero();
     fr_t k = load_field<fr_t>(scalars + t * 32);
-    comp = quad_mul_scalar(comp, k.v, table);
+    comp = SPLIT ? quad_mul_scalar_half(comp, k.v, table, q2 & 1) : quad_mul_scalar(comp, k.v, table);
     comp = quad_tree(comp, 32);
     if (threadIdx.x < 4) store_field(partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 192 + quad_store_offset(), comp);
 }
@@ -204,7 +208,7 @@ void selftest_lincomb_quads(const void* points_affine_dev, const void* scalars_m
     uint8_t* canon = dev_alloc<uint8_t>((size_t)n * 32);
     uint8_t* partials = dev_alloc<uint8_t>((size_t)blocks * 192 + 192);
     k_mont_to_canon<<<div_up(n, 128), 128, 0, st>>>((const uint8_t*)scalars_mont_dev, canon, n);
-    k_lincomb_quads<<<dim3((unsigned)blocks, 1), 32, 0, st>>>((const uint8_t*)points_affine_dev, canon, n, partials);
+    k_lincomb_quads<false><<<dim3((unsigned)blocks, 1), 32, 0, st>>>((const uint8_t*)points_affine_dev, canon, n, partials);
     k_quad_sum<<<1, 32, 0, st>>>(partials, blocks, partials + (size_t)blocks * 192);
     k_xyzz_to_jac1<<<1, 32, 0, st>>>(partials + (size_t)blocks * 192, (uint8_t*)out_jac_dev);
     cudaError_t e = cudaStreamSynchronize(st);
@@ -242,12 +246,12 @@ void KzgSettingsDev::load_g2(const uint8_t* g2_monomial, int count, cudaStream_t
 }
 
 // workspace layout for n items (L = 2n + 1):
-//   [comm_aff n*96][proof_aff n*96][z n*32][y n*32][r 32][ry n*32][pts 2L*96][scalars 2L*32][partials 2*ceil(L/8)*192][sums 2*192]
+//   [comm_aff n*96][proof_aff n*96][z n*32][y n*32][r 32][ry n*32][pts 2L*96][scalars 2L*32][partials 2*ceil(2L/8)*192][sums 2*192]
 //   [pair scratch]
 void KzgSettingsDev::ensure_verify_ws(size_t n) {
     if (n <= vf_cap_ && vf_buf_) return;
     cudaFree(vf_buf_);
-    size_t L = 2 * n + 1, blocks = (L + 7) / 8;
+    size_t L = 2 * n + 1, blocks = (2 * L + 7) / 8;   // lincomb2_and_pair may use two quads per term
     size_t bytes = n * (96 + 96 + 32 + 32 + 32) + 64 + 2 * L * (96 + 32) + 2 * blocks * 192 + 2 * 192 + kPairScratchBytes + 256;
     vf_buf_ = dev_alloc<uint8_t>(bytes);
     vf_cap_ = n;
@@ -266,8 +270,11 @@ static void run_pairing(const uint8_t* p0, const uint8_t* l0, int neg0, const ui
 // segment 0 = pts[0..L), segment 1 = pts[L..2L) (affine, canonical scalars): result = e(-S0, Q[qa]) e(S1, Q[qb]) == 1
 void KzgSettingsDev::lincomb2_and_pair(const uint8_t* pts, const uint8_t* scalars, size_t L, uint8_t* partials, uint8_t* sums,
                                        uint8_t* scratch, int qa, int qb, int* result, cudaStream_t st) {
-    const size_t blocks = (L + 7) / 8;
-    k_lincomb_quads<<<dim3((unsigned)blocks, 2), 32, 0, st>>>(pts, scalars, (int)L, partials);
+    // few terms (single verifications): two quads per term, one GLV half each (the launch is a handful of warps either way)
+    const bool split = L <= 256;
+    const size_t blocks = split ? (2 * L + 7) / 8 : (L + 7) / 8;
+    if (split) k_lincomb_quads<true><<<dim3((unsigned)blocks, 2), 32, 0, st>>>(pts, scalars, (int)L, partials);
+    else k_lincomb_quads<false><<<dim3((unsigned)blocks, 2), 32, 0, st>>>(pts, scalars, (int)L, partials);
     k_quad_sum<<<2, 32, 0, st>>>(partials, (int)blocks, sums);
     B200_LAUNCH_CHECK();
     const uint8_t* lines = (const uint8_t*)g2_lines_;
@@ -308,7 +315,7 @@ void KzgSettingsDev::verify_batch(const uint8_t* commitments48, const uint8_t* p
     if (!g2_lines_) throw CudaError(-1, "trusted setup was loaded without G2 points");
     if (n < 1) throw CudaError(-1, "verify_batch needs at least one item");
     ensure_verify_ws(n);
-    const size_t L = 2 * (size_t)n + 1, blocks = (L + 7) / 8;
+    const size_t L = 2 * (size_t)n + 1, blocks = (2 * L + 7) / 8;
     uint8_t* w = (uint8_t*)vf_buf_;
     uint8_t* comm_aff = w;                 w += (size_t)n * 96;
     uint8_t* proof_aff = w;                w += (size_t)n * 96;
