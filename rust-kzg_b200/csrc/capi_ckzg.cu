@@ -713,7 +713,9 @@ C_KZG_RET coalesced_cells_call(KzgCtx& ctx, const uint8_t* blob, uint8_t* cells_
         int rc = C_KZG_OK;
         try {
             DeviceScope ds(ctx.device);
+            const auto tl0 = std::chrono::steady_clock::now();
             AllLanes lk(ctx);   // blocks while the previous batch (or any other user of the lanes) runs: meanwhile this one fills
+            const auto tl1 = std::chrono::steady_clock::now();
             // A burst of callers (a block's blobs from a parallel iterator) arrives within microseconds of each other; the
             // pass takes ~5 ms whatever its size, so the leader lingers while claims keep coming in (at most 200 us, and
             // no longer than 60 us after the last one) instead of leaving the rest of the burst to the next pass.
@@ -722,14 +724,16 @@ C_KZG_RET coalesced_cells_call(KzgCtx& ctx, const uint8_t* blob, uint8_t* cells_
                 auto last_change = t0;
                 int seen = co.claimed_so_far(B);
                 while (seen < cap) {
-                    std::this_thread::sleep_for(std::chrono::microseconds(15));
+                    std::this_thread::yield();                  // (a 15 us sleep oversleeps by the timer slack: ~60 us each)
                     const auto now = std::chrono::steady_clock::now();
                     const int c = co.claimed_so_far(B);
                     if (c != seen) { seen = c; last_change = now; }
                     if (now - last_change > std::chrono::microseconds(60) || now - t0 > std::chrono::microseconds(ctx.cells_grace_us)) break;
                 }
             }
+            const auto tl2 = std::chrono::steady_clock::now();
             const int n = co.close(B);
+            const auto tl3 = std::chrono::steady_clock::now();
             Stage& g = ctx.stage[0];
             ctx.dev->fk20_batch(g.stream);
             if (!ctx.d_cells) ctx.d_cells = dev_alloc<uint8_t>((size_t)ctx.max_batch * 128 * 2048);
@@ -745,6 +749,14 @@ C_KZG_RET coalesced_cells_call(KzgCtx& ctx, const uint8_t* blob, uint8_t* cells_
             B200_CUDA_CHECK(cudaStreamSynchronize(g.stream));
             ctx.st_cells_batches++;
             ctx.st_cells_requests += (uint64_t)n;
+            if (getenv("B200_KZG_CELLS_TRACE")) {
+                const auto tl4 = std::chrono::steady_clock::now();
+                auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+                    return (long)std::chrono::duration_cast<std::chrono::microseconds>(b - a).count();
+                };
+                fprintf(stderr, "cells batch n=%d lanes %ld us grace %ld us close %ld us exec %ld us\n", n, us(tl0, tl1), us(tl1, tl2), us(tl2, tl3),
+                        us(tl3, tl4));
+            }
         } catch (const std::exception& e) {
             cudaGetLastError();
             fprintf(stderr, "b200kzg: %s\n", e.what());
@@ -1195,7 +1207,7 @@ static C_KZG_RET coalesced_verify(const std::shared_ptr<KzgCtx>& ctxp, int kind,
                 auto last_change = t0;
                 int seen = co.claimed_so_far(B);
                 while (seen < cap) {
-                    std::this_thread::sleep_for(std::chrono::microseconds(15));
+                    std::this_thread::yield();                  // (a 15 us sleep oversleeps by the timer slack: ~60 us each)
                     const auto now = std::chrono::steady_clock::now();
                     const int c = co.claimed_so_far(B);
                     if (c != seen) { seen = c; last_change = now; }

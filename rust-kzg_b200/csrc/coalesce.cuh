@@ -23,7 +23,8 @@
 namespace b200 {
 
 struct CoBatchBase {
-    int kind = 0, claimed = 0, consumed = 0;
+    int kind = 0, consumed = 0;
+    std::atomic<int> claimed{0};   // written under the queue's mutex; read without it by a lingering leader
     std::atomic<int> ready{0};
     bool done = false;
     int rc = 0;   // failure of the whole batch (device error); per-item validity travels in the payload
@@ -51,7 +52,7 @@ struct CoQueue {
         std::unique_lock<std::mutex> lk(mu);
         for (;;) {
             Batch* b = open[kind];
-            if (b && b->claimed < cap) return Claim{b, b->claimed++, false};
+            if (b && b->claimed.load() < cap) return Claim{b, b->claimed.fetch_add(1), false};
             if (b) open[kind] = nullptr;   // full: its leader will run it; start the next one
             if (!free_list.empty()) {
                 b = free_list.back();
@@ -64,24 +65,21 @@ struct CoQueue {
                 cv_free.wait(lk);
                 continue;
             }
-            b->kind = kind; b->claimed = 1; b->consumed = 0; b->ready.store(0); b->done = false; b->rc = 0;
+            b->kind = kind; b->claimed.store(1); b->consumed = 0; b->ready.store(0); b->done = false; b->rc = 0;
             open[kind] = b;
             return Claim{b, 0, true};
         }
     }
     static void staged(Batch* b) { b->ready.fetch_add(1, std::memory_order_release); }
     // leader, before close(): how many slots have been claimed so far
-    int claimed_so_far(Batch* b) {
-        std::lock_guard<std::mutex> lk(mu);
-        return b->claimed;
-    }
+    static int claimed_so_far(Batch* b) { return b->claimed.load(std::memory_order_relaxed); }   // no lock: the poll must not starve claimers
     // leader: no more claims; returns the item count once every claimed slot has been staged
     int close(Batch* b) {
         int n;
         {
             std::lock_guard<std::mutex> lk(mu);
             if (open[b->kind] == b) open[b->kind] = nullptr;
-            n = b->claimed;
+            n = b->claimed.load();
         }
         while (b->ready.load(std::memory_order_acquire) < n) std::this_thread::yield();
         return n;
@@ -103,7 +101,7 @@ struct CoQueue {
     // every caller, after reading its slot (claimed is final once done is set)
     void consume(Batch* b) {
         std::lock_guard<std::mutex> lk(mu);
-        if (++b->consumed == b->claimed) {
+        if (++b->consumed == b->claimed.load()) {
             free_list.push_back(b);
             cv_free.notify_one();
         }

@@ -581,6 +581,7 @@ void KzgSettingsDev::ensure_fk20(cudaStream_t st) {
         cfg.bases_period = kFkK2;
         fk_msm_.reset(new MsmEngine(cfg, table, false, st));
     }
+    fs_->prepare_g1((size_t)fk_batch_ * kFkK2);   // no buffer growth or lazy kernel load inside a later multi-blob pass
     fk_ready_ = true;
     fk_a_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kCellSize * kFkK2 * 32);
     fk_b_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kCellSize * kFkK2 * 32);

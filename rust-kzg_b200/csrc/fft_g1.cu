@@ -9,6 +9,8 @@
 #include "g1.cuh"
 #include "g1_quad.cuh"
 #include "ntt.cuh"
+
+#include <algorithm>
 #include "util.cuh"
 
 namespace b200 {
@@ -223,6 +225,37 @@ __global__ void __launch_bounds__(32) k_g1_out(const uint8_t* __restrict__ work,
     fp_t t = p * shfl_xor_fp(p, 2);
     if (live && role < 2) store_field(out_jac + i * 144 + role * 48, t);
     if (live && role == 2) store_field(out_jac + i * 144 + 96, p);
+}
+
+// One-time preparation for callers that will run many transforms of up to max_total points per launch (FK20): the work and
+// product buffers at their final size -- growing them later means cudaFree, which synchronises the device under a running
+// batch -- and every stage kernel variant loaded now instead of lazily inside a caller's first multi-blob pass.
+void FFTSettingsDev::prepare_g1(size_t max_total) {
+    if (max_total > g1_work_elems_) {
+        cudaFree(g1_work_);
+        g1_work_ = dev_alloc<uint8_t>(max_total * 192);
+        g1_work_elems_ = max_total;
+    }
+    // the fused forms run up to 2^12 points per launch: 21/8 (triples, to 2^11) or 5/4 (pairs) products per point
+    const size_t fused = std::min<size_t>(max_total, (size_t)1 << 12);
+    const size_t need = std::max<size_t>(21 * (std::min<size_t>(fused, (size_t)1 << 11) >> 3), 5 * (fused >> 2));
+    if (need > g1_tmp_elems_) {
+        cudaFree(g1_tmp_);
+        g1_tmp_ = dev_alloc<uint8_t>(need * 192);
+        g1_tmp_elems_ = need;
+    }
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_g1_stage<true>);
+    cudaFuncGetAttributes(&fa, k_g1_stage<false>);
+    cudaFuncGetAttributes(&fa, k_g1_stage2_mul<true>);
+    cudaFuncGetAttributes(&fa, k_g1_stage2_mul<false>);
+    cudaFuncGetAttributes(&fa, k_g1_stage2_comb);
+    cudaFuncGetAttributes(&fa, k_g1_stage3_mul<true>);
+    cudaFuncGetAttributes(&fa, k_g1_stage3_mul<false>);
+    cudaFuncGetAttributes(&fa, k_g1_stage3_comb);
+    cudaFuncGetAttributes(&fa, k_g1_brp_in);
+    cudaFuncGetAttributes(&fa, k_g1_out);
+    cudaGetLastError();
 }
 
 void FFTSettingsDev::fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n, bool inverse, int batch, cudaStream_t st,

@@ -37,6 +37,8 @@ public:
     // instead saves one scalar multiplication per point: the transform is linear)
     void fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n, bool inverse, int batch, cudaStream_t stream,
                 bool apply_scale = true);
+    // buffers and kernels of fft_g1 made ready for launches of up to max_total points (see fft_g1.cu)
+    void prepare_g1(size_t max_total);
     // (2^log_n)^-1 as a Montgomery Fr, device memory
     const void* inv_pow2_dev(int log_n) const { return (const uint8_t*)roots_ + (max_width_ + 1) * 32 + 33 * 32 + (size_t)log_n * 32; }
     int launches_last() const { return launches_; }
