@@ -455,7 +455,7 @@ KzgSettingsDev::~KzgSettingsDev() {
     for (Lane& ln : lanes_) { cudaFree(ln.scalars); cudaFree(ln.poly); cudaFree(ln.z); cudaFree(ln.y); cudaFree(ln.out_jac); cudaFree(ln.direct_part); cudaFree(ln.direct_cnt); }
     cudaFree(lag_direct_);
     cudaFree(cells_a_); cudaFree(cells_b_);
-    cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_); cudaFree(fk_direct_);
+    cudaFree(fk_a_); cudaFree(fk_b_); cudaFree(fk_pts_); cudaFree(fk_direct_); cudaFree(fk_team_part_); cudaFree(fk_team_cnt_);
     cudaFree(g2_affine_); cudaFree(g2_jac_); cudaFree(g2_lines_); cudaFree(vf_buf_); cudaFree(das_buf_);
 }
 
@@ -581,6 +581,14 @@ void KzgSettingsDev::ensure_fk20(cudaStream_t st) {
         cfg.bases_period = kFkK2;
         fk_msm_.reset(new MsmEngine(cfg, table, false, st));
     }
+    // small batches: the lincombs by teams of CTAs per vector (k_direct_msm with per-vector point blocks) instead of one warp
+    // per lincomb -- one blob's 128 lincombs are 128 warps of 40 additions each, a 0.5 ms chain on an empty machine
+    fk_team_max_ = fk_direct_ && (kCellSize * direct_windows(fk_direct_c_)) % 128 == 0 ? std::min(fk_batch_, env_int_local("B200_FK20_TEAM", 2)) : 0;   // measured: 1 blob 3.91 -> 3.59 ms, 2: 3.93 -> 3.72, 4: equal, 8 and up the warp form wins
+    if (fk_team_max_ > 0) {
+        fk_team_part_ = dev_alloc<uint8_t>((size_t)fk_team_max_ * kFkK2 * 128 * 192);
+        fk_team_cnt_ = dev_alloc<unsigned>((size_t)fk_team_max_ * kFkK2);
+        B200_CUDA_CHECK(cudaMemsetAsync(fk_team_cnt_, 0, (size_t)fk_team_max_ * kFkK2 * sizeof(unsigned), st));
+    }
     fs_->prepare_g1((size_t)fk_batch_ * kFkK2);   // no buffer growth or lazy kernel load inside a later multi-blob pass
     fk_ready_ = true;
     fk_a_ = dev_alloc<uint8_t>((size_t)fk_batch_ * kCellSize * kFkK2 * 32);
@@ -632,7 +640,9 @@ void KzgSettingsDev::fk20_from_mono(const void* mono, size_t stride, int n, uint
     k_fk_transpose<<<div_up(tt, 256), 256, 0, st>>>((const uint8_t*)fk_b_, (uint8_t*)fk_a_, tt, (const uint8_t*)fs_->inv_pow2_dev(7));
     B200_LAUNCH_CHECK();
     // g1_lincomb_batch: 128 lincombs of 64 fixed points per blob (kzg/src/das.rs:676-680)
-    if (fk_direct_) launch_direct_lincomb(fk_a_, fk_direct_, fk_pts_, n * kFkK2, kFkK2, kCellSize, fk_direct_c_, st);
+    if (fk_direct_ && n <= fk_team_max_)
+        launch_direct_msm(fk_a_, fk_direct_, fk_team_part_, fk_team_cnt_, nullptr, (uint8_t*)fk_pts_, n * kFkK2, kCellSize, fk_direct_c_, st, kFkK2);
+    else if (fk_direct_) launch_direct_lincomb(fk_a_, fk_direct_, fk_pts_, n * kFkK2, kFkK2, kCellSize, fk_direct_c_, st);
     else fk_msm_->run(fk_a_, kCellSize, n * kFkK2, false, fk_pts_, st);
     // h = inverse fft_g1, upper half := identity, forward fft_g1 (:682-695)
     fs_->fft_g1(fk_pts_, fk_pts_, kFkK2, true, n, st, /*apply_scale=*/false);

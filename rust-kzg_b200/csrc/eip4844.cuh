@@ -109,6 +109,9 @@ private:
     int fk_batch_ = 0;
     void *fk_a_ = nullptr, *fk_b_ = nullptr, *fk_pts_ = nullptr;
     void* fk_direct_ = nullptr;  // every digit multiple of the 8192 column points (fk20_direct.cu), or nullptr
+    void* fk_team_part_ = nullptr;     // partial sums / completion counters of the team form of the lincombs (small batches)
+    unsigned* fk_team_cnt_ = nullptr;
+    int fk_team_max_ = 0;              // largest blob count the team form serves
     int fk_direct_c_ = 0;        // its window width
     int max_batch_;
     int launches_ = 0;
@@ -162,8 +165,9 @@ void launch_direct_lincomb(const void* scalars, const void* table, void* out_jac
 void launch_direct_msm_compressed(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, int nvec,
                                   int npts, int c, cudaStream_t st);
 // the same with a choice of result form: out48 (compressed) or, when out_jac != nullptr, blst_p1 Jacobian points
+// period > 1: vector v uses the point block (v mod period) of a table over period * npts points (the FK20 columns)
 void launch_direct_msm(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, uint8_t* out_jac,
-                       int nvec, int npts, int c, cudaStream_t st);
+                       int nvec, int npts, int c, cudaStream_t st, int period = 1);
 void launch_fr_from_mont(const void* in, void* out, size_t n, cudaStream_t st);
 // widest window <= want whose table leaves B200_DIRECT_RESERVE_GB free (0: none fits); table of every digit multiple of the
 // n * period affine points at points_dev (nullptr when the allocation fails)

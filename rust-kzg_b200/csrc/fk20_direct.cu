@@ -189,7 +189,7 @@ template <class AR>
 __global__ void __launch_bounds__(128, B200_DIRECT_MINB) k_direct_msm(const uint8_t* __restrict__ scalars, const uint8_t* __restrict__ table,
                                                     uint8_t* __restrict__ partials, int npts, int W, int c, uint32_t spv, uint32_t S,
                                                     unsigned* __restrict__ counters, uint8_t* __restrict__ out48,
-                                                    uint8_t* __restrict__ out_jac, unsigned long long* trace) {
+                                                    uint8_t* __restrict__ out_jac, unsigned long long* trace, int period) {
     unsigned long long ts[8];
     auto stamp = [&](int k) { if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ts[k] = t; } };
     stamp(0);
@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(128, B200_DIRECT_MINB) k_direct_msm(const uint
     for (uint32_t vec = b0 / spv; vec * spv < b1; vec++) {
         const uint32_t v0 = vec * spv, s0 = (b0 > v0 ? b0 : v0) - v0, s1 = (b1 < v0 + spv ? b1 : v0 + spv) - v0;
         const uint32_t* sc = reinterpret_cast<const uint32_t*>(scalars + (size_t)vec * npts * 32);
-        xyzz_t a2 = direct_chain<AR>(sc, table, s0 * 128u + threadIdx.x, 128u, (int)(s1 - s0), W, c);
+        // period > 1 (FK20): vector v sums over the point block v mod period, whose entries start (v mod period) * npts * W items in
+        const uint8_t* tab = table + ((((size_t)(vec % (uint32_t)period) * npts * W) << (c - 1)) * 96);
+        xyzz_t a2 = direct_chain<AR>(sc, tab, s0 * 128u + threadIdx.x, 128u, (int)(s1 - s0), W, c);
         stamp(1);
         // warp tree, then the CTA's four warp sums on four quads of warp 0: one partial per (CTA, vector)
         fp_t q = seg_sum_quad(a2, 32);
@@ -299,7 +301,7 @@ void launch_direct_msm_compressed(const void* scalars, const void* table, void* 
 // scalars: nvec x npts canonical little-endian 32-byte scalars; partials: workspace of nvec * 128 XYZZ points (192 bytes);
 // counters: nvec zero-initialised words (left zero); results: out48 = nvec compressed points, or (out_jac != nullptr) nvec blst_p1
 void launch_direct_msm(const void* scalars, const void* table, void* partials, unsigned* counters, uint8_t* out48, uint8_t* out_jac,
-                       int nvec, int npts, int c, cudaStream_t st) {
+                       int nvec, int npts, int c, cudaStream_t st, int period) {
     const int W = direct_windows(c);
     if (((size_t)npts * W) % 128) throw CudaError(-1, "direct MSM: items per vector must fill whole CTAs");
     static const int wave = [] {                              // resident CTAs of this kernel on the whole device
@@ -328,7 +330,7 @@ void launch_direct_msm(const void* scalars, const void* table, void* partials, u
         return t;
     }();
     k_direct_msm<ArCall><<<G, 128, 0, st>>>((const uint8_t*)scalars, (const uint8_t*)table, (uint8_t*)partials, npts, W, c, spv, S, counters,
-                                           out48, out_jac, trace);
+                                           out48, out_jac, trace, period < 1 ? 1 : period);
     B200_LAUNCH_CHECK();
     if (trace) {
         cudaStreamSynchronize(st);
