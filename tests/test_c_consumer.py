@@ -44,10 +44,11 @@ def test_c_consumer_round_trips():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("op,threads", [("commit", 16), ("blob_proof", 8), ("proof", 8), ("mixed", 12)])
+@pytest.mark.parametrize("op,threads", [("commit", 16), ("blob_proof", 8), ("proof", 8), ("mixed", 12), ("cells", 6), ("verify", 8)])
 def test_c_pthread_consumer_is_bit_exact_under_coalescing(op, threads):
     """examples/ckzg_threads.c: N pthreads call the unmodified single-blob symbols on pageable blobs; concurrent requests
-    share launch sequences (csrc/coalesce.cuh) and every result must equal the one computed with a single thread active"""
+    share launch sequences (csrc/coalesce.cuh) and every result must equal the one computed with a single thread active
+    (cells: compute_cells_and_kzg_proofs, 128 cells + 128 proofs per call; verify: verify_blob_kzg_proof, all true)"""
     import json
     _build()
     r = subprocess.run([EXE_T, SETUP_PATH, op, str(threads), "6", "3"], capture_output=True, text=True, timeout=300)
