@@ -211,6 +211,86 @@ __global__ void __launch_bounds__(32) k_g1_stage3_comb(uint8_t* __restrict__ wor
         store_field(w + (j + (size_t)(r + 4) * h) * 192 + off, z_hi);
     }
 }
+// R <= 6 DIT stages (s .. s+R-1) at the latency of one, for a LONE small transform (one blob's FK20 transforms), where
+// even the fused triples leave the chain of scalar multiplications as the whole cost.  For the 2^R points x_m at j + m h:
+//     z_r = x_0 + sum_{m >= 1} (-1)^popc(r & m) [ prod_{t in bits(m)} w_(2^(t+1) h)^(low + (r mod 2^t) h) ] x_m
+// The bracket depends on r only through u = r mod 2^T, T = the top bit of m, so input m needs 2^T distinct products:
+// (4^R - 1) / 3 per group in all (R = 6: 1365 instead of the 192 of six plain stages), every one at depth one.
+// k_g1_stageR_mul: one lane quad (SPLIT: two) per product, product p -> level T, m = 2^T + (idx >> T), u = idx & (2^T - 1);
+// the group's x_0 is copied behind its products so that the combination never reads what it overwrites.
+// k_g1_stageR_comb: four quads per output r, a quarter of the 2^R terms each, then a two-level quad tree.
+__device__ __forceinline__ size_t stageR_products(int R) { return (((size_t)1 << (2 * R)) - 1) / 3; }
+template <bool SPLIT>
+__global__ void __launch_bounds__(32) k_g1_stageR_mul(const uint8_t* __restrict__ work, uint8_t* __restrict__ tmp, size_t n, int log_n, int s, int R,
+                                                      const uint8_t* __restrict__ roots, size_t nmax, int inverse) {
+    __shared__ __align__(16) uint8_t table[kQuadTableBytes];
+    const size_t q2 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const size_t q = SPLIT ? q2 >> 1 : q2;
+    const int ghalf = SPLIT ? (int)(q2 & 1) : 0;
+    const size_t NP = stageR_products(R), groups = n >> R, total = groups * (NP + 1);
+    const bool live = q < total;
+    const size_t qq = live ? q : 0;
+    const size_t g = qq / (NP + 1), p = qq - g * (NP + 1);
+    const size_t h = (size_t)1 << s, low = g & (h - 1), j = ((g >> s) << (s + R)) | low;
+    const uint8_t* w = work + (size_t)blockIdx.y * n * 192;
+    uint8_t* dst = tmp + ((size_t)blockIdx.y * total + qq) * 192;
+    const int off = quad_store_offset();
+    if (__all_sync(kFullMask, p == NP)) {                      // (never a whole warp in practice; keeps the copy quads cheap)
+        if (live && ghalf == 0) store_field(dst + off, load_field<fp_t>(w + j * 192 + off));
+        return;
+    }
+    int T = 0;
+    while (p < NP && p >= stageR_products(T + 1)) T++;
+    const size_t idx = p < NP ? p - stageR_products(T) : 0;
+    const size_t m = p < NP ? ((size_t)1 << T) + (idx >> T) : 0, u = idx & (((size_t)1 << T) - 1);
+    size_t e = 0;
+    for (int t = 0; t <= T; t++)
+        if ((m >> t) & 1) e += (low + (u & (((size_t)1 << t) - 1)) * h) * (n >> (s + t + 1));
+    e &= n - 1;
+    fp_t t = load_field<fp_t>(w + (j + m * h) * 192 + off);
+    const size_t eu = e * (nmax >> log_n);
+    fr_t root = load_field_ro<fr_t>(roots + (inverse && eu ? nmax - eu : eu) * 32).from_mont();
+    fp_t prod;
+    if (SPLIT) {
+        prod = quad_mul_scalar_half(t, root.v, table, ghalf);
+        prod = quad_add(prod, shfl_xor_fp(prod, 4));
+    } else {
+        prod = quad_mul_scalar(t, root.v, table);
+    }
+    if (p == NP) prod = t;                                     // the x_0 copy (m = 0: t is x_0 itself)
+    if (live && ghalf == 0) store_field(dst + off, prod);
+}
+__global__ void __launch_bounds__(32) k_g1_stageR_comb(uint8_t* __restrict__ work, const uint8_t* __restrict__ tmp, size_t n, int s, int R) {
+    const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;   // four quads per output
+    const size_t outs = n;                                                    // (n >> R) groups x 2^R outputs
+    const bool live = (q >> 2) < outs;
+    const size_t o = live ? q >> 2 : 0;
+    const int part = (int)(q & 3);
+    const size_t g = o >> R, r = o & (((size_t)1 << R) - 1);
+    const size_t NP = stageR_products(R);
+    const size_t h = (size_t)1 << s, low = g & (h - 1), j = ((g >> s) << (s + R)) | low;
+    uint8_t* w = work + (size_t)blockIdx.y * n * 192;
+    const uint8_t* pr = tmp + ((size_t)blockIdx.y * (n >> R) + g) * (NP + 1) * 192;
+    const int off = quad_store_offset();
+    const bool yrole = (threadIdx.x & 3) == 1;
+    const size_t terms = (size_t)1 << R, per = terms >> 2 ? terms >> 2 : 1;
+    fp_t acc = fp_t::zero();
+#pragma unroll 1
+    for (size_t m = part * per; m < (part + 1) * per && m < terms; m++) {
+        fp_t v;
+        if (m == 0) {
+            v = load_field<fp_t>(pr + NP * 192 + off);
+        } else {
+            int T = 63 - __clzll((unsigned long long)m);
+            const size_t p = stageR_products(T) + ((m - ((size_t)1 << T)) << T) + (r & (((size_t)1 << T) - 1));
+            v = load_field<fp_t>(pr + p * 192 + off);
+            if (yrole && (__popcll((unsigned long long)(r & m)) & 1)) v = v.neg();
+        }
+        acc = quad_add(acc, v);
+    }
+    acc = quad_tree(acc, 16);                                  // the four parts of an output are neighbouring quads
+    if (live && part == 0) store_field(w + (j + r * h) * 192 + off, acc);
+}
 // XYZZ -> Jacobian, with the [n^-1] scaling of the inverse transform (blst/src/fft_g1.rs:74-79); one quad per point
 __global__ void __launch_bounds__(32) k_g1_out(const uint8_t* __restrict__ work, uint8_t* __restrict__ out_jac, size_t total,
                                                const uint8_t* __restrict__ scale) {
@@ -282,7 +362,9 @@ void FFTSettingsDev::fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n,
     // Triples (21 products per 8 points instead of 12) up to 2^11 points per launch -- 16 blobs' FK20 transforms, still one
     // wave of product quads: 128 points x 8 transforms 2.93 -> see scripts/fft_g1_batch_timing.py; pairs up to 2^12.
     const int fuse_env = getenv("B200_FFT_G1_FUSE") ? atoi(getenv("B200_FFT_G1_FUSE")) : -1;
-    const int fuse = fuse_env >= 0 ? (fuse_env == 1 ? 2 : fuse_env) : total <= ((size_t)1 << 11) ? 3 : total <= ((size_t)1 << 12) ? 2 : 0;
+    // 4 .. 6: R stages at once (k_g1_stageR_*), the default for launches of up to 256 points (one or two blobs' FK20 transforms: 1.01 / 1.28 ms per 128-point transform against 1.62 for split triples)
+    const int fuse = fuse_env >= 0 ? (fuse_env == 1 ? 2 : fuse_env) : (total <= 256 && log_n >= 5) ? 6 : total <= ((size_t)1 << 11) ? 3
+                                                                       : total <= ((size_t)1 << 12) ? 2 : 0;
     // B200_FFT_G1_SPLIT (per call): 1 / 0 force two quads / one quad per scalar multiplication; unset: two only while the
     // doubled launch leaves at most one warp per scheduler (592 x 8 quads) -- the halves do 1.6x the work of the whole, so they
     // pay off only where the chain, not the multiply pipe, is the limit (scripts/fft_g1_batch_timing.py: 128 points x 8
@@ -299,11 +381,33 @@ void FFTSettingsDev::fft_g1(const void* in_jac_dev, void* out_jac_dev, size_t n,
         launches_++;
     };
     int s = 0;
-    if (log_n > 0 && (fuse == 0 || (fuse == 2 && (log_n & 1)) || (fuse == 3 && log_n % 3 != 0))) {
+    if (fuse >= 4 && fuse <= 6 && log_n >= 2) {
+        const int R = std::min(fuse, std::max(2, log_n - 1));   // stage 0 multiplies by w^0 only: it stays a plain stage
+        const size_t NP = (((size_t)1 << (2 * R)) - 1) / 3;
+        const int lead = log_n % R;                            // leading stages one by one (stage 0 multiplies by w^0 only)
+        for (; s < lead; s++) plain(s);
+        const size_t per = (n >> R) * (NP + 1), need = (size_t)batch * per;
+        if (need > g1_tmp_elems_) {
+            cudaFree(g1_tmp_);
+            g1_tmp_ = nullptr; g1_tmp_elems_ = 0;
+            g1_tmp_ = dev_alloc<uint8_t>(need * 192);
+            g1_tmp_elems_ = need;
+        }
+        for (; s + R <= log_n; s += R) {
+            if (use_split(per))
+                k_g1_stageR_mul<true><<<dim3(div_up(per * 8, 32), (unsigned)batch), 32, 0, st>>>((const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n, s,
+                                                                                             R, (const uint8_t*)roots_, max_width_, inverse);
+            else
+                k_g1_stageR_mul<false><<<dim3(div_up(per * 4, 32), (unsigned)batch), 32, 0, st>>>((const uint8_t*)g1_work_, (uint8_t*)g1_tmp_, n, log_n, s,
+                                                                                              R, (const uint8_t*)roots_, max_width_, inverse);
+            k_g1_stageR_comb<<<dim3(div_up(n * 16, 32), (unsigned)batch), 32, 0, st>>>((uint8_t*)g1_work_, (const uint8_t*)g1_tmp_, n, s, R);
+            launches_ += 2;
+        }
+    } else if (log_n > 0 && (fuse == 0 || (fuse == 2 && (log_n & 1)) || (fuse == 3 && log_n % 3 != 0))) {
         plain(0);                                              // stage 0 multiplies by w^0 only: cheap, and it fixes the parity
         s = 1;
     }
-    if (fuse >= 2 && log_n >= 2) {
+    if ((fuse == 2 || fuse == 3) && log_n >= 2) {
         const size_t need = (size_t)batch * (fuse == 3 ? 21 * (n >> 3) : 5 * (n >> 2));
         if (need > g1_tmp_elems_) {
             cudaFree(g1_tmp_);

@@ -18,12 +18,12 @@ pts = np.ascontiguousarray(K.KZGSettings(text).g1_lagrange_brp, dtype=np.uint64)
 fs = B.FFTSettings(7)
 n = 128
 res = {}
-for batch in (8, 16, 32, 64, 128, 256):
+for batch in (1, 2, 8, 16, 32, 64, 128, 256):
     src = np.tile(pts, (max(1, batch * n // len(pts)), 1))[:batch * n]
     d_in = torch.from_numpy(src.view(np.int64)).cuda()
     d_out = torch.zeros_like(d_in)
     row = {}
-    for fuse in ("0", "2", "3"):
+    for fuse in (("0", "2", "3", "6") if batch <= 8 else ("0", "2", "3")):
         for split in ("0", "1"):
             os.environ["B200_FFT_G1_FUSE"] = fuse
             os.environ["B200_FFT_G1_SPLIT"] = split

@@ -223,9 +223,10 @@ def test_fft_fr_above_2p22_three_passes(B, K):
 
 @pytest.mark.parametrize("logn", [2, 3, 5, 6, 7, 8])
 def test_fft_g1_fused_and_plain_stages_agree(B, K, oracle_settings, logn):
-    """fft_g1 runs its stages in fused triples (21 independent scalar multiplications per eight points) or pairs (five per
-    four points, csrc/fft_g1.cu) while the transform is small and stage by stage otherwise: all three forms against the
-    oracle, forward and inverse, for every residue of log n mod 2 and mod 3"""
+    """fft_g1 runs its stages fused -- up to six at once for a lone small transform ((4^R - 1) / 3 independent scalar
+    multiplications per 2^R points), in triples (21 per eight points) or pairs (five per four points, csrc/fft_g1.cu) -- while
+    the launch is small and stage by stage otherwise: every form against the oracle, forward and inverse, for every residue
+    of log n"""
     import os
     n = 1 << logn
     ofs = K.FFTSettings(10)
@@ -234,7 +235,7 @@ def test_fft_g1_fused_and_plain_stages_agree(B, K, oracle_settings, logn):
         pts[2] = 0
     want = {inv: K.p1s_to_affine(ofs.fft_g1(pts, inv)) for inv in (False, True)}
     # ... each with one quad per scalar multiplication and with two (one GLV half each, B200_FFT_G1_SPLIT)
-    for fuse in ("3", "2", "0"):
+    for fuse in ("6", "4", "3", "2", "0"):
         for split in ("1", "0"):
             os.environ["B200_FFT_G1_FUSE"] = fuse
             os.environ["B200_FFT_G1_SPLIT"] = split
