@@ -318,7 +318,8 @@ void FFTSettingsDev::prepare_g1(size_t max_total) {
     }
     // the fused forms run up to 2^12 points per launch: 21/8 (triples, to 2^11) or 5/4 (pairs) products per point
     const size_t fused = std::min<size_t>(max_total, (size_t)1 << 12);
-    const size_t need = std::max<size_t>(21 * (std::min<size_t>(fused, (size_t)1 << 11) >> 3), 5 * (fused >> 2));
+    size_t need = std::max<size_t>(21 * (std::min<size_t>(fused, (size_t)1 << 11) >> 3), 5 * (fused >> 2));
+    need = std::max<size_t>(need, (std::min<size_t>(max_total, 256) >> 6) * 1366);   // six stages at once: 1365 products + x0 per 64 points
     if (need > g1_tmp_elems_) {
         cudaFree(g1_tmp_);
         g1_tmp_ = dev_alloc<uint8_t>(need * 192);
@@ -333,6 +334,9 @@ void FFTSettingsDev::prepare_g1(size_t max_total) {
     cudaFuncGetAttributes(&fa, k_g1_stage3_mul<true>);
     cudaFuncGetAttributes(&fa, k_g1_stage3_mul<false>);
     cudaFuncGetAttributes(&fa, k_g1_stage3_comb);
+    cudaFuncGetAttributes(&fa, k_g1_stageR_mul<true>);
+    cudaFuncGetAttributes(&fa, k_g1_stageR_mul<false>);
+    cudaFuncGetAttributes(&fa, k_g1_stageR_comb);
     cudaFuncGetAttributes(&fa, k_g1_brp_in);
     cudaFuncGetAttributes(&fa, k_g1_out);
     cudaGetLastError();
